@@ -1,0 +1,126 @@
+"""Batch decode API: many independent Brotli streams per kernel launch.
+
+Host-side mirror of the C ABI's bro_batch_decode / bro_batch_decode_host.  torch is used only as the owner of
+device memory and streams; the decode itself is the CUDA kernel in libbrotli_b200.so.
+"""
+import ctypes
+
+import numpy as np
+
+from . import _lib
+
+
+def pack_streams(streams, align=1):
+    """Concatenate byte strings -> (uint8 array, uint64 offsets[n+1]).  `align` pads each start (kept in offsets
+    as the *end of the previous stream*, so with align > 1 the offsets array describes padded slots and the true
+    lengths must be carried separately; the decoder API uses align=1)."""
+    assert align == 1
+    lens = np.fromiter((len(s) for s in streams), dtype=np.uint64, count=len(streams))
+    off = np.zeros(len(streams) + 1, dtype=np.uint64)
+    np.cumsum(lens, out=off[1:])
+    buf = np.frombuffer(b"".join(streams), dtype=np.uint8) if len(streams) else np.zeros(0, dtype=np.uint8)
+    return buf, off
+
+
+def slot_offsets(capacities, align=16):
+    """Output slot offsets for the given per-stream capacities, each slot start aligned to `align` bytes (aligned
+    slots let the copy phase use full 16-byte stores from the first byte)."""
+    caps = np.asarray(capacities, dtype=np.uint64)
+    padded = (caps + np.uint64(align - 1)) // np.uint64(align) * np.uint64(align)
+    off = np.zeros(len(caps) + 1, dtype=np.uint64)
+    np.cumsum(padded, out=off[1:])
+    return off
+
+
+class BatchDecoder:
+    """One GPU's decoder context (bro_ctx).  Not thread safe; use one per host thread / CUDA stream."""
+
+    def __init__(self, device=None, quirks=0):
+        import torch
+        if not torch.cuda.is_available():
+            raise RuntimeError("brotli_rs_b200 needs a CUDA device: the decoder has no CPU path")
+        self._lib = _lib.load_library()
+        if device is None:
+            device = torch.cuda.current_device()
+        self.device = torch.device("cuda", device) if isinstance(device, int) else torch.device(device)
+        torch.cuda.init()
+        with torch.cuda.device(self.device):
+            torch.zeros(1, device=self.device)       # make sure the primary context exists before the library uses it
+            h = ctypes.c_void_p()
+            st = self._lib.bro_ctx_create(ctypes.byref(h), self.device.index)
+        if st != 0:
+            raise _lib.BroError(st, "bro_ctx_create failed with status %d" % st)
+        self._ctx = h
+        if quirks:
+            self._lib.bro_ctx_set_quirks(self._ctx, quirks)
+
+    def close(self):
+        if getattr(self, "_ctx", None):
+            self._lib.bro_ctx_destroy(self._ctx)
+            self._ctx = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def launch_count(self):
+        return int(self._lib.bro_ctx_launch_count(self._ctx))
+
+    @property
+    def num_warps(self):
+        return int(self._lib.bro_ctx_num_warps(self._ctx))
+
+    def _check(self, st):
+        if st != 0:
+            msg = self._lib.bro_ctx_last_cuda_error(self._ctx).decode() if st == _lib.CUDA_ERROR else None
+            raise _lib.BroError(st, msg and "CUDA error: " + msg)
+
+    def decode_device(self, d_in, d_in_off, d_out, d_out_off, d_out_len=None, d_status=None, stream=None):
+        """bro_batch_decode on torch CUDA tensors (asynchronous on `stream` / the current stream).
+        d_in uint8, d_in_off/d_out_off int64-or-uint64 [n+1], d_out uint8.  Returns (d_out_len, d_status)."""
+        import torch
+        n = d_in_off.numel() - 1
+        assert d_out_off.numel() == n + 1
+        for t in (d_in, d_in_off, d_out, d_out_off):
+            assert t.is_cuda and t.is_contiguous()
+        assert d_in_off.element_size() == 8 and d_out_off.element_size() == 8
+        if d_out_len is None:
+            d_out_len = torch.empty(n, dtype=torch.int64, device=d_in.device)
+        if d_status is None:
+            d_status = torch.empty(n, dtype=torch.int32, device=d_in.device)
+        s = stream if stream is not None else torch.cuda.current_stream(d_in.device)
+        st = self._lib.bro_batch_decode(self._ctx, d_in.data_ptr(), d_in_off.data_ptr(), d_out.data_ptr(),
+                                        d_out_off.data_ptr(), d_out_len.data_ptr(), d_status.data_ptr(), n,
+                                        ctypes.c_void_p(s.cuda_stream))
+        self._check(st)
+        return d_out_len, d_status
+
+    def decode_host(self, in_buf, in_off, out_off, out=None):
+        """bro_batch_decode_host on numpy arrays (or anything exposing a writable buffer, e.g. pinned torch tensors
+        via .numpy()).  Returns (out, out_len, status)."""
+        in_buf = np.ascontiguousarray(in_buf, dtype=np.uint8)
+        in_off = np.ascontiguousarray(in_off, dtype=np.uint64)
+        out_off = np.ascontiguousarray(out_off, dtype=np.uint64)
+        n = len(in_off) - 1
+        if out is None:
+            out = np.empty(int(out_off[-1]), dtype=np.uint8)
+        out_len = np.zeros(n, dtype=np.uint64)
+        status = np.zeros(n, dtype=np.int32)
+        st = self._lib.bro_batch_decode_host(self._ctx, in_buf.ctypes.data, in_off.ctypes.data, out.ctypes.data,
+                                             out_off.ctypes.data, out_len.ctypes.data, status.ctypes.data, n)
+        self._check(st)
+        return out, out_len, status
+
+    def decode_streams(self, streams, capacities):
+        """Convenience: list of byte strings + per-stream output capacities -> list of (status, bytes)."""
+        in_buf, in_off = pack_streams(streams)
+        out_off = slot_offsets(capacities)
+        out, out_len, status = self.decode_host(in_buf, in_off, out_off)
+        res = []
+        for i in range(len(streams)):
+            b = int(out_off[i])
+            res.append((int(status[i]), out[b: b + int(out_len[i])].tobytes()))
+        return res

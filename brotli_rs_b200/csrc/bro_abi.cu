@@ -1,0 +1,271 @@
+// bro_abi.cu -- the extern "C" entry points declared in include/brotli_b200.h.
+//
+// Host side of the drop-in boundary: context management, the batch launch, the host-buffer convenience path
+// (H2D -> kernel -> D2H) and the Read-struct that mirrors brotli::Decompressor<R> (src/lib.rs:378-410,
+// 2173-2193).  No decode work happens on the CPU anywhere in this file.
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <new>
+#include <vector>
+
+#include "../../include/brotli_b200.h"
+#include "bro_kernels.h"
+#include "bro_status.h"
+
+extern "C" const uint8_t bro_dictionary_blob[];   // csrc/dict_blob.c
+#define BRO_DICT_BYTES 122784
+
+struct bro_ctx {
+    int device;
+    int num_sms;
+    int grid;                 // persistent CTAs
+    uint32_t num_warps;
+    uint16_t* d_arena;
+    uint8_t* d_dict;
+    uint32_t* d_counter;
+    int quirks;
+    uint64_t launches;
+    char err[256];
+    // grow-only device staging for the host-buffer path
+    uint8_t* d_in; size_t d_in_cap;
+    uint8_t* d_out; size_t d_out_cap;
+    uint64_t* d_meta; size_t d_meta_cap;   // in_off | out_off | out_len | status
+};
+
+static int bro_fail(bro_ctx* ctx, cudaError_t e, const char* what) {
+    if (ctx) snprintf(ctx->err, sizeof(ctx->err), "%s: %s", what, cudaGetErrorString(e));
+    return BRO_ST_CudaError;
+}
+#define BRO_CUDA(ctx, call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return bro_fail(ctx, e_, #call); } while (0)
+
+extern "C" int bro_ctx_create(bro_ctx** out, int device) {
+    if (!out) return BRO_ST_InvalidArgument;
+    *out = NULL;
+    bro_ctx* ctx = (bro_ctx*)calloc(1, sizeof(bro_ctx));
+    if (!ctx) return BRO_ST_InvalidArgument;
+    cudaError_t e;
+    if (device < 0) { if ((e = cudaGetDevice(&device)) != cudaSuccess) { free(ctx); return BRO_ST_CudaError; } }
+    if ((e = cudaSetDevice(device)) != cudaSuccess) { free(ctx); return BRO_ST_CudaError; }
+    ctx->device = device;
+    cudaDeviceProp prop;
+    if ((e = cudaGetDeviceProperties(&prop, device)) != cudaSuccess) { free(ctx); return BRO_ST_CudaError; }
+    ctx->num_sms = prop.multiProcessorCount;
+    int per_sm = 0;
+    if (bro_kernel_occupancy(&per_sm) != 0 || per_sm < 1) { free(ctx); return BRO_ST_CudaError; }
+    ctx->grid = ctx->num_sms * per_sm;
+    ctx->num_warps = (uint32_t)ctx->grid * (uint32_t)bro_kernel_warps_per_cta();
+    size_t arena = (size_t)ctx->num_warps * bro_kernel_arena_bytes_per_warp();
+    if ((e = cudaMalloc(&ctx->d_arena, arena)) != cudaSuccess ||
+        (e = cudaMalloc(&ctx->d_dict, BRO_DICT_BYTES)) != cudaSuccess ||
+        (e = cudaMalloc(&ctx->d_counter, sizeof(uint32_t))) != cudaSuccess ||
+        (e = cudaMemcpy(ctx->d_dict, bro_dictionary_blob, BRO_DICT_BYTES, cudaMemcpyHostToDevice)) != cudaSuccess) {
+        cudaFree(ctx->d_arena); cudaFree(ctx->d_dict); cudaFree(ctx->d_counter);
+        free(ctx);
+        return BRO_ST_CudaError;
+    }
+    *out = ctx;
+    return BRO_ST_OK;
+}
+
+extern "C" void bro_ctx_destroy(bro_ctx* ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaFree(ctx->d_arena); cudaFree(ctx->d_dict); cudaFree(ctx->d_counter);
+    cudaFree(ctx->d_in); cudaFree(ctx->d_out); cudaFree(ctx->d_meta);
+    free(ctx);
+}
+
+extern "C" int bro_ctx_set_quirks(bro_ctx* ctx, int quirks) {
+    if (!ctx || (quirks != 0 && quirks != 1)) return BRO_ST_InvalidArgument;
+    ctx->quirks = quirks;
+    return BRO_ST_OK;
+}
+
+extern "C" const char* bro_ctx_last_cuda_error(const bro_ctx* ctx) { return ctx ? ctx->err : "no context"; }
+extern "C" uint64_t bro_ctx_launch_count(const bro_ctx* ctx) { return ctx ? ctx->launches : 0; }
+extern "C" uint32_t bro_ctx_num_warps(const bro_ctx* ctx) { return ctx ? ctx->num_warps : 0; }
+
+extern "C" int bro_batch_decode(bro_ctx* ctx, const uint8_t* d_in, const uint64_t* d_in_off, uint8_t* d_out,
+                                const uint64_t* d_out_off, uint64_t* d_out_len, int32_t* d_status, uint32_t n,
+                                void* stream) {
+    if (!ctx) return BRO_ST_InvalidArgument;
+    if (n == 0) return BRO_ST_OK;
+    if (!d_in_off || !d_out_off || !d_out_len || !d_status) return BRO_ST_InvalidArgument;
+    cudaStream_t s = (cudaStream_t)stream;
+    BRO_CUDA(ctx, cudaMemsetAsync(ctx->d_counter, 0, sizeof(uint32_t), s));
+    BroLaunch p;
+    p.in = d_in; p.in_off = d_in_off; p.out = d_out; p.out_off = d_out_off;
+    p.out_len = d_out_len; p.status = d_status; p.n = n;
+    p.arena = ctx->d_arena; p.dict = ctx->d_dict; p.counter = ctx->d_counter; p.quirk_spec = ctx->quirks;
+    int grid = ctx->grid;
+    uint32_t need = (n + (uint32_t)bro_kernel_warps_per_cta() - 1) / (uint32_t)bro_kernel_warps_per_cta();
+    if ((uint32_t)grid > need) grid = (int)need;
+    cudaError_t e = (cudaError_t)bro_kernel_launch(&p, grid, s);
+    if (e != cudaSuccess) return bro_fail(ctx, e, "bro_decode_kernel launch");
+    ctx->launches += 1;
+    return BRO_ST_OK;
+}
+
+static int bro_reserve(bro_ctx* ctx, void** p, size_t* cap, size_t need) {
+    if (*cap >= need) return BRO_ST_OK;
+    if (*p) { BRO_CUDA(ctx, cudaFree(*p)); *p = NULL; *cap = 0; }
+    size_t want = need + (need >> 3) + 256;
+    BRO_CUDA(ctx, cudaMalloc(p, want));
+    *cap = want;
+    return BRO_ST_OK;
+}
+
+extern "C" int bro_batch_decode_host(bro_ctx* ctx, const uint8_t* h_in, const uint64_t* h_in_off, uint8_t* h_out,
+                                     const uint64_t* h_out_off, uint64_t* h_out_len, int32_t* h_status, uint32_t n) {
+    if (!ctx) return BRO_ST_InvalidArgument;
+    if (n == 0) return BRO_ST_OK;
+    if (!h_in_off || !h_out_off || !h_out_len || !h_status) return BRO_ST_InvalidArgument;
+    BRO_CUDA(ctx, cudaSetDevice(ctx->device));
+    const uint64_t in_lo = h_in_off[0], in_hi = h_in_off[n], out_lo = h_out_off[0], out_hi = h_out_off[n];
+    if (in_hi < in_lo || out_hi < out_lo) return BRO_ST_InvalidArgument;
+    const size_t in_bytes = (size_t)(in_hi - in_lo), out_bytes = (size_t)(out_hi - out_lo);
+    const size_t off_bytes = (size_t)(n + 1) * sizeof(uint64_t);
+    const size_t meta_bytes = 2 * off_bytes + (size_t)n * sizeof(uint64_t) + (size_t)n * sizeof(int32_t);
+    int st;
+    if ((st = bro_reserve(ctx, (void**)&ctx->d_in, &ctx->d_in_cap, in_bytes + 16))) return st;
+    if ((st = bro_reserve(ctx, (void**)&ctx->d_out, &ctx->d_out_cap, out_bytes + 16))) return st;
+    if ((st = bro_reserve(ctx, (void**)&ctx->d_meta, &ctx->d_meta_cap, meta_bytes))) return st;
+    uint64_t* d_in_off = ctx->d_meta;
+    uint64_t* d_out_off = d_in_off + (n + 1);
+    uint64_t* d_out_len = d_out_off + (n + 1);
+    int32_t* d_status = (int32_t*)(d_out_len + n);
+    cudaStream_t s = 0;
+    if (in_bytes) BRO_CUDA(ctx, cudaMemcpyAsync(ctx->d_in, h_in + in_lo, in_bytes, cudaMemcpyHostToDevice, s));
+    BRO_CUDA(ctx, cudaMemcpyAsync(d_in_off, h_in_off, off_bytes, cudaMemcpyHostToDevice, s));
+    BRO_CUDA(ctx, cudaMemcpyAsync(d_out_off, h_out_off, off_bytes, cudaMemcpyHostToDevice, s));
+    // offsets are relative to the caller's buffers; rebase the device pointers instead of rewriting the arrays
+    st = bro_batch_decode(ctx, ctx->d_in - in_lo, d_in_off, ctx->d_out - out_lo, d_out_off, d_out_len, d_status, n, s);
+    if (st) return st;
+    if (out_bytes) BRO_CUDA(ctx, cudaMemcpyAsync(h_out + out_lo, ctx->d_out, out_bytes, cudaMemcpyDeviceToHost, s));
+    BRO_CUDA(ctx, cudaMemcpyAsync(h_out_len, d_out_len, (size_t)n * sizeof(uint64_t), cudaMemcpyDeviceToHost, s));
+    BRO_CUDA(ctx, cudaMemcpyAsync(h_status, d_status, (size_t)n * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+    BRO_CUDA(ctx, cudaStreamSynchronize(s));
+    return BRO_ST_OK;
+}
+
+// src/lib.rs:331-354 -- the strings are the observable error payload of the reference (io::Error description)
+extern "C" const char* bro_status_description(int st) {
+    switch (st) {
+    case BRO_ST_OK: return "OK";
+    case BRO_ST_CodeLengthsChecksum: return "Code length check sum did not add up in complex prefix code";
+    case BRO_ST_ExpectedEndOfStream: return "Expected end-of-stream, but stream did not end";
+    case BRO_ST_ExceededExpectedBytes: return "More uncompressed bytes than expected in meta-block";
+    case BRO_ST_InvalidBlockCountCode: return "Encountered invalid value for block count code";
+    case BRO_ST_InvalidBlockSwitchCommandCode: return "Encountered invalid value for block switch command code";
+    case BRO_ST_InvalidLengthInStaticDictionary: return "Encountered invalid length in reference to static dictionary";
+    case BRO_ST_InvalidMSkipLen: return "Most significant byte of MSKIPLEN was zero";
+    case BRO_ST_InvalidSymbol: return "Encountered invalid symbol in prefix code";
+    case BRO_ST_InvalidTransformId: return "Encountered invalid transform id in reference to static dictionary";
+    case BRO_ST_InvalidNonPositiveDistance: return "Encountered invalid non-positive distance";
+    case BRO_ST_LessThanTwoNonZeroCodeLengths: return "Encountered invalid complex prefix code with less than two non-zero codelengths";
+    case BRO_ST_NoCodeLength: return "Encountered invalid complex prefix code with all zero codelengths";
+    case BRO_ST_NonZeroFillBit: return "Enocuntered non-zero fill bit";
+    case BRO_ST_NonZeroReservedBit: return "Enocuntered non-zero reserved bit";
+    case BRO_ST_NonZeroTrailerBit: return "Enocuntered non-zero bit trailing the stream";
+    case BRO_ST_NonZeroTrailerNibble: return "Enocuntered non-zero nibble trailing";
+    case BRO_ST_ParseErrorContextMap: return "Error parsing context map";
+    case BRO_ST_ParseErrorComplexPrefixCodeLengths: return "Error parsing code lengths for complex prefix code";
+    case BRO_ST_ParseErrorDistanceCode: return "Error parsing DistanceCode";
+    case BRO_ST_ParseErrorInsertAndCopyLength: return "Error parsing Insert And Copy Length";
+    case BRO_ST_ParseErrorInsertLiterals: return "Error parsing Insert Literals";
+    case BRO_ST_RingBufferError: return "Error accessing distance ring buffer";
+    case BRO_ST_RunLengthExceededSizeOfContextMap: return "Run length excceeded declared length of context map";
+    case BRO_ST_UnexpectedEOF: return "Encountered unexpected EOF";
+    case BRO_ST_OutputTooSmall: return "output slot too small for the decoded stream";
+    case BRO_ST_CudaError: return "CUDA error";
+    case BRO_ST_PanicUppercaseZero: return "reference panics: uppercase_first on a dictionary word starting with 0x00";
+    case BRO_ST_InvalidArgument: return "invalid argument";
+    default: return "unknown status";
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------
+// The Read-struct: brotli::Decompressor<R: Read>
+// ------------------------------------------------------------------------------------------------------
+struct bro_reader {
+    bro_ctx* ctx;
+    bool own_ctx;
+    bro_read_cb cb;
+    void* user;
+    bool decoded;
+    int status;
+    std::vector<uint8_t> out;
+    size_t served;
+};
+
+extern "C" bro_reader* bro_reader_new(bro_ctx* ctx, bro_read_cb cb, void* user) {
+    if (!cb) return NULL;
+    bro_reader* r = new (std::nothrow) bro_reader();
+    if (!r) return NULL;
+    r->ctx = ctx; r->own_ctx = false; r->cb = cb; r->user = user;
+    r->decoded = false; r->status = BRO_ST_OK; r->served = 0;
+    return r;                                        // like Decompressor::new: no I/O yet (src/lib.rs:398-410)
+}
+
+static void bro_reader_decode(bro_reader* r) {
+    r->decoded = true;
+    // drain R to end of input; an I/O error is indistinguishable from EOF for the reference's bit reader
+    // (src/bitreader/mod.rs:78-82, 199), i.e. the stream is decoded as if it ended there
+    std::vector<uint8_t> in;
+    try {
+        size_t chunk = 1 << 16;
+        for (;;) {
+            size_t old = in.size();
+            in.resize(old + chunk);
+            intptr_t got = r->cb(r->user, in.data() + old, chunk);
+            if (got <= 0) { in.resize(old); break; }
+            in.resize(old + (size_t)got);
+            if (chunk < (1u << 24)) chunk <<= 1;
+        }
+        if (!r->ctx) {
+            int st = bro_ctx_create(&r->ctx, -1);
+            if (st) { r->status = st; return; }
+            r->own_ctx = true;
+        }
+        size_t cap = in.size() * 6 + (1 << 16);
+        for (;;) {
+            r->out.resize(cap);
+            uint64_t in_off[2] = {0, (uint64_t)in.size()}, out_off[2] = {0, (uint64_t)cap}, out_len = 0;
+            int32_t status = 0;
+            int st = bro_batch_decode_host(r->ctx, in.data(), in_off, r->out.data(), out_off, &out_len, &status, 1);
+            if (st) { r->status = st; r->out.clear(); return; }
+            if (status == BRO_ST_OutputTooSmall && cap < 0xf0000000ull) { cap = cap * 4 < 0xf0000000ull ? cap * 4 : 0xf0000000ull; continue; }
+            r->status = status;
+            // bytes produced before an error are not part of the contract: the reference loses the
+            // output of the failing decompress() call, how much depends on the caller's read() sizes
+            r->out.resize(status == BRO_ST_OK ? (size_t)out_len : 0);
+            return;
+        }
+    } catch (...) {
+        r->status = BRO_ST_InvalidArgument;
+        r->out.clear();
+    }
+}
+
+extern "C" intptr_t bro_reader_read(bro_reader* r, uint8_t* buf, size_t len) {
+    if (!r || (!buf && len)) return -(intptr_t)BRO_ST_InvalidArgument;
+    if (!r->decoded) bro_reader_decode(r);
+    if (r->status != BRO_ST_OK) return -(intptr_t)r->status;   // io::Error(InvalidData, description), src/lib.rs:2177
+    size_t left = r->out.size() - r->served;
+    size_t k = len < left ? len : left;
+    if (k) memcpy(buf, r->out.data() + r->served, k);
+    r->served += k;
+    return (intptr_t)k;                                        // 0 = end of stream, repeatable
+}
+
+extern "C" int bro_reader_status(const bro_reader* r) { return r ? r->status : BRO_ST_InvalidArgument; }
+
+extern "C" void bro_reader_free(bro_reader* r) {
+    if (!r) return;
+    if (r->own_ctx) bro_ctx_destroy(r->ctx);
+    delete r;
+}

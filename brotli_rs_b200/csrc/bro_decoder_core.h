@@ -1,0 +1,1003 @@
+// bro_decoder_core.h -- the Brotli stream decoder executed by ONE WARP per stream.
+//
+// This is the B200 replacement for the whole of the reference's L2+L1 layers:
+//   src/lib.rs:412-2170 (stream state machine and every parse_*/decode_* helper), src/bitreader/mod.rs,
+//   src/huffman/{mod.rs,tree/mod.rs}, src/ringbuffer/mod.rs, src/transformation/mod.rs.
+// It is not a translation: the reference walks heap-array trees one bit at a time inside a 45-state enum;
+// here every lane of a warp carries the same (warp-uniform) decoder state, symbols are decoded with an 8-bit
+// root table plus a canonical-code search for longer codes, the compressed bytes are fetched 128 B at a time
+// by the whole warp and handed out by shuffle, prefix tables are built by the 32 lanes together, and all
+// byte movement (LZ77 copies, pattern fills, stored blocks, dictionary words) is lane-parallel.
+//
+// The file compiles in two modes:
+//   * nvcc, sm_100a: BRO_W = 32 lanes, warp intrinsics (the product path, used by bro_kernels.cu);
+//   * BRO_HOSTSIM:   BRO_W = 1 lane, plain C++ -- a host simulation of the very same code used ONLY by the
+//     CPU test-suite (tests/_build/libbro_hostsim.so) to fuzz the decoder logic against the oracle without
+//     a GPU.  It is never linked into libbrotli_b200.so and nothing in the product can reach it.
+//
+// Results are bit-exact with the reference: same bytes, same error class (status = DecompressorError in enum
+// order, src/lib.rs:294-319), including the reference's quirks.
+#pragma once
+#include <stdint.h>
+
+#include "bro_status.h"
+
+#if defined(BRO_HOSTSIM)
+#define BRO_W 1u
+#define BRO_FN static inline
+#define BRO_COLD static
+#define BRO_TABLE_QUAL static const
+#else
+#define BRO_W 32u
+#define BRO_FN __device__ __forceinline__
+#define BRO_COLD __device__ __noinline__
+#define BRO_TABLE_QUAL static __constant__ const
+#endif
+#include "bro_tables_generated.h"
+
+// ------------------------------------------------------------------------------------------------------
+// warp primitives
+// ------------------------------------------------------------------------------------------------------
+#if defined(BRO_HOSTSIM)
+BRO_FN unsigned bro_lane() { return 0; }
+BRO_FN uint32_t bro_shfl(uint32_t v, unsigned) { return v; }
+BRO_FN uint32_t bro_match_any(uint32_t) { return 1u; }
+BRO_FN uint32_t bro_lanemask_lt() { return 0u; }
+BRO_FN void bro_syncwarp() {}
+BRO_FN uint32_t bro_brev(uint32_t x) {
+    x = ((x >> 1) & 0x55555555u) | ((x & 0x55555555u) << 1);
+    x = ((x >> 2) & 0x33333333u) | ((x & 0x33333333u) << 2);
+    x = ((x >> 4) & 0x0f0f0f0fu) | ((x & 0x0f0f0f0fu) << 4);
+    x = ((x >> 8) & 0x00ff00ffu) | ((x & 0x00ff00ffu) << 8);
+    return (x >> 16) | (x << 16);
+}
+BRO_FN uint32_t bro_popc(uint32_t x) { return (uint32_t)__builtin_popcount(x); }
+BRO_FN uint32_t bro_funnel_r(uint32_t lo, uint32_t hi, unsigned sh) {
+    return sh ? (lo >> sh) | (hi << (32 - sh)) : lo;
+}
+#else
+#define BRO_FULL 0xffffffffu
+BRO_FN unsigned bro_lane() { return threadIdx.x & 31u; }
+BRO_FN uint32_t bro_shfl(uint32_t v, unsigned src) { return __shfl_sync(BRO_FULL, v, src); }
+BRO_FN uint32_t bro_match_any(uint32_t v) { return __match_any_sync(BRO_FULL, v); }
+BRO_FN uint32_t bro_lanemask_lt() { uint32_t m; asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m)); return m; }
+BRO_FN void bro_syncwarp() { __syncwarp(); }
+BRO_FN uint32_t bro_brev(uint32_t x) { return __brev(x); }
+BRO_FN uint32_t bro_popc(uint32_t x) { return (uint32_t)__popc(x); }
+BRO_FN uint32_t bro_funnel_r(uint32_t lo, uint32_t hi, unsigned sh) { return __funnelshift_r(lo, hi, sh); }
+#endif
+
+// ------------------------------------------------------------------------------------------------------
+// memory layout of the per-warp table arena (HBM, L1/L2 resident while a stream is being decoded)
+// ------------------------------------------------------------------------------------------------------
+// A prefix-code table ("tree record"), in uint16 units:
+//   [0..255]   root: indexed by the next 8 stream bits; entry = symbol | len<<10 (len 1..8),
+//              0 = no code starts with these bits (hole), 1 = a longer code does (search by length)
+//   [256..271] limit[L]: left-justified 15-bit end of all codes of length <= L (canonical order)
+//   [272..287] base[L]:  (int16) index into sorted[] of the first code of length L minus its code value
+//   [288] single-symbol flag (decode consumes zero bits: src/huffman/tree/mod.rs:87-91)
+//   [289] the single symbol   [290] max code length   [291] reserved
+//   [292..]    sorted[]: symbols in canonical order (by length, then by position)
+#define BRO_T_LIMIT 256
+#define BRO_T_BASE 272
+#define BRO_T_SINGLE 288
+#define BRO_T_SINGLE_SYM 289
+#define BRO_T_MAXDEPTH 290
+#define BRO_T_SORTED 292
+#define BRO_TREE_U16(alphabet) (((BRO_T_SORTED + (alphabet)) + 7u) & ~7u)
+
+// largest output slot one stream may use: positions are 32-bit and one command may add up to 2 * (2^24 + 22594) bytes
+#define BRO_MAX_SLOT 0xf0000000ull
+
+#define BRO_MAX_BLTYPES 256u
+#define BRO_ALPHA_LIT 256u
+#define BRO_ALPHA_CMD 704u
+#define BRO_ALPHA_DIST_MAX 520u   // 16 + 120 + (48 << 3)
+#define BRO_ALPHA_BTYPE_MAX 258u
+#define BRO_ALPHA_BCOUNT 26u
+#define BRO_ALPHA_CMAP_MAX 272u   // 16 + 256
+
+// arena offsets, in uint16 units
+#define BRO_A_CMAP_L 0u                                          // 256*64 bytes
+#define BRO_A_CMAP_D (BRO_A_CMAP_L + 8192u)                      // 256*4 bytes
+#define BRO_A_MODES (BRO_A_CMAP_D + 512u)                        // 256 bytes
+#define BRO_A_BTYPE (BRO_A_MODES + 128u)                         // 3 trees
+#define BRO_A_BCOUNT (BRO_A_BTYPE + 3u * BRO_TREE_U16(BRO_ALPHA_BTYPE_MAX))
+#define BRO_A_CMTREE (BRO_A_BCOUNT + 3u * BRO_TREE_U16(BRO_ALPHA_BCOUNT))
+#define BRO_A_LIT (BRO_A_CMTREE + BRO_TREE_U16(BRO_ALPHA_CMAP_MAX))
+#define BRO_A_CMD (BRO_A_LIT + BRO_MAX_BLTYPES * BRO_TREE_U16(BRO_ALPHA_LIT))
+#define BRO_A_DIST (BRO_A_CMD + BRO_MAX_BLTYPES * BRO_TREE_U16(BRO_ALPHA_CMD))
+#define BRO_ARENA_U16 (BRO_A_DIST + BRO_MAX_BLTYPES * BRO_TREE_U16(BRO_ALPHA_DIST_MAX))
+#define BRO_ARENA_BYTES (2u * BRO_ARENA_U16)
+
+// per-warp on-chip scratch (shared memory on the device)
+struct BroScratch {
+    uint8_t lens[BRO_ALPHA_CMD];   // code lengths of the code being read; reused as the IMTF list
+    uint16_t syms[4];              // explicit symbols of a simple code
+    uint16_t cnt[16];              // per-length counts, then running positions
+    uint16_t limit[16];
+    int16_t base[16];
+    uint8_t clc[32];               // code-length-code table: symbol | len<<5, indexed by 5 stream bits
+    uint8_t word[64];              // dictionary word staging (<= 24 + 13 bytes)
+};
+
+// ------------------------------------------------------------------------------------------------------
+// bit stream: src/bitreader/mod.rs:21-304 restated as a 64-bit LSB-first window.  The warp loads the
+// compressed bytes 128 B at a time (lane i holds word i) and feeds the window by shuffle.
+// ------------------------------------------------------------------------------------------------------
+struct BroBits {
+    const uint8_t* chunk;   // 128-byte aligned address of the chunk held in `cur`
+    const uint8_t* lo;      // first loadable word address (stream start rounded down to 4)
+    const uint8_t* end;     // one past the last byte of the stream
+    uint64_t buf;           // bit window, next bit to read = bit 0
+    uint64_t rem;           // real stream bits not yet moved into the window
+    uint32_t nbits;         // bits in the window (real bits first, then `overrun` padding bits)
+    uint32_t overrun;       // padding bits in the window that lie beyond the end of the stream
+    uint32_t wi;            // next word of the chunk to hand out
+    uint32_t cur, nxt;      // this lane's word of the current / next chunk
+};
+
+BRO_FN uint32_t bro_load_word(const BroBits& s, const uint8_t* a) {
+#if defined(BRO_HOSTSIM)
+    // host buffers are neither padded nor aligned: assemble the word from the bytes that belong to the stream
+    uint32_t w = 0;
+    for (int i = 0; i < 4; i++) if (a + i >= s.lo && a + i < s.end) w |= (uint32_t)a[i] << (8 * i);
+    return w;
+#else
+    // words entirely outside [lo, end) read as zero; words straddling the ends expose neighbouring bytes of the
+    // same allocation, which the bit accounting below never lets a decision depend on
+    if (a < s.lo || a >= s.end) return 0u;
+    return __ldg((const uint32_t*)a);
+#endif
+}
+
+BRO_FN uint32_t bro_next_word(BroBits& s) {
+#if defined(BRO_HOSTSIM)
+    uint32_t w = bro_load_word(s, s.chunk + 4u * s.wi);
+    if (++s.wi == 32u) { s.chunk += 128; s.wi = 0; }
+    return w;
+#else
+    uint32_t w = bro_shfl(s.cur, s.wi);
+    if (++s.wi == 32u) {
+        s.cur = s.nxt;
+        s.chunk += 128;
+        s.nxt = bro_load_word(s, s.chunk + 128 + 4u * bro_lane());
+        s.wi = 0;
+    }
+    return w;
+#endif
+}
+
+BRO_FN void bro_bits_account(BroBits& s, uint32_t loaded) {
+    if (s.rem >= loaded) s.rem -= loaded;
+    else { s.overrun += loaded - (uint32_t)s.rem; s.rem = 0; }
+}
+
+// position the window at byte address `a` (start of stream, or after a stored / metadata block)
+BRO_FN void bro_bits_seek(BroBits& s, const uint8_t* a) {
+    uintptr_t ai = (uintptr_t)a;
+    s.chunk = (const uint8_t*)(ai & ~(uintptr_t)127);
+    s.wi = (uint32_t)(ai & 127u) >> 2;
+#if !defined(BRO_HOSTSIM)
+    s.cur = bro_load_word(s, s.chunk + 4u * bro_lane());
+    s.nxt = bro_load_word(s, s.chunk + 128 + 4u * bro_lane());
+#endif
+    s.rem = a < s.end ? 8ull * (uint64_t)(s.end - a) : 0ull;
+    s.overrun = 0;
+    uint32_t sh = 8u * (uint32_t)(ai & 3u);
+    uint32_t w = bro_next_word(s);
+    s.buf = (uint64_t)(w >> sh);
+    s.nbits = 32u - sh;
+    bro_bits_account(s, s.nbits);
+}
+
+BRO_FN void bro_bits_init(BroBits& s, const uint8_t* start, const uint8_t* end) {
+#if defined(BRO_HOSTSIM)
+    s.lo = start;
+#else
+    s.lo = (const uint8_t*)((uintptr_t)start & ~(uintptr_t)3);
+#endif
+    s.end = end;
+    bro_bits_seek(s, start);
+}
+
+// after this the window holds > 32 bits, of which (nbits - overrun) are real
+BRO_FN void bro_refill(BroBits& s) {
+    if (s.nbits <= 32u) {
+        uint32_t w = bro_next_word(s);
+        s.buf |= (uint64_t)w << s.nbits;
+        s.nbits += 32u;
+        bro_bits_account(s, 32u);
+    }
+}
+
+BRO_FN uint32_t bro_avail(const BroBits& s) { return s.nbits - s.overrun; }
+BRO_FN void bro_consume(BroBits& s, uint32_t n) { s.buf >>= n; s.nbits -= n; }
+
+// n <= 25 bits, least significant first (src/bitreader/mod.rs:140-158).  Returns false at end of input, which
+// every caller in the reference maps to UnexpectedEOF.
+BRO_FN bool bro_read_bits(BroBits& s, uint32_t n, uint32_t& v) {
+    bro_refill(s);
+    if (n > bro_avail(s)) return false;
+    v = (uint32_t)s.buf & ((1u << n) - 1u);
+    bro_consume(s, n);
+    return true;
+}
+
+// src/bitreader/mod.rs:257-267: the bits up to the next byte boundary (0 if already aligned)
+BRO_FN bool bro_read_byte_tail(BroBits& s, uint32_t& v) {
+    bro_refill(s);
+    uint32_t n = bro_avail(s) & 7u;   // real bits left are a whole number of bytes plus the tail
+    v = (uint32_t)s.buf & ((1u << n) - 1u);
+    bro_consume(s, n);
+    return true;
+}
+
+// byte address of the next unread bit (valid when byte aligned)
+BRO_FN const uint8_t* bro_bits_addr(const BroBits& s) {
+    return s.chunk + 4u * s.wi - (s.nbits >> 3);
+}
+
+// ------------------------------------------------------------------------------------------------------
+// prefix code tables
+// ------------------------------------------------------------------------------------------------------
+#define BRO_SYM_OK 0
+#define BRO_SYM_EOF 1
+#define BRO_SYM_HOLE 2
+
+// Decode one symbol (src/huffman/tree/mod.rs:63-92 restated).  The reference walks one bit at a time and
+// stops at the first assigned node; it reports Ok(None) only after max_depth+1 bits if no node was hit (SURVEY
+// Q5), and a failed bit read before that is an EOF.  A table hit whose code is longer than the remaining input
+// is therefore EOF, and a hole is EOF unless max_depth+1 real bits remain.
+BRO_FN int bro_decode_sym(BroBits& s, const uint16_t* T, uint32_t& sym) {
+    bro_refill(s);
+    uint32_t peek = (uint32_t)s.buf;
+    uint32_t e = T[peek & 0xffu];
+    uint32_t len = e >> 10;
+    if (len != 0u) {
+        if (len > bro_avail(s)) return BRO_SYM_EOF;
+        bro_consume(s, len);
+        sym = e & 0x3ffu;
+        return BRO_SYM_OK;
+    }
+    if (T[BRO_T_SINGLE]) { sym = T[BRO_T_SINGLE_SYM]; return BRO_SYM_OK; }
+    if (e == 1u) {
+        uint32_t x = bro_brev(peek) >> 17;   // next 15 bits, first bit read most significant
+        for (uint32_t L = 9; L <= 15u; L++) {
+            if (x < T[BRO_T_LIMIT + L]) {
+                if (L > bro_avail(s)) return BRO_SYM_EOF;
+                sym = T[BRO_T_SORTED + (int)(int16_t)T[BRO_T_BASE + L] + (int)(x >> (15u - L))];
+                bro_consume(s, L);
+                return BRO_SYM_OK;
+            }
+        }
+    }
+    return (bro_avail(s) >= (uint32_t)T[BRO_T_MAXDEPTH] + 1u) ? BRO_SYM_HOLE : BRO_SYM_EOF;
+}
+
+// Build a tree record from n (length, symbol) pairs in sc.lens[] (and sc.syms[] when `explicit_syms`), in
+// the order the reference inserts them: src/huffman/mod.rs:19-43 assigns canonical codes per length in array
+// order; Tree::insert (src/huffman/tree/mod.rs:50-61) counts every insert, and a tree with exactly one
+// insert decodes with zero bits.  The 32 lanes cooperate: counting sort by length, then every lane resolves
+// 8 of the 256 root entries by searching the canonical limits.
+BRO_COLD void bro_build_tree(uint16_t* T, BroScratch& sc, uint32_t n, bool explicit_syms) {
+    const unsigned lane = bro_lane();
+    if (lane < 16u) sc.cnt[lane] = 0;
+#if defined(BRO_HOSTSIM)
+    for (unsigned i = 0; i < 16; i++) sc.cnt[i] = 0;
+#endif
+    bro_syncwarp();
+    // pass 1: histogram of lengths (leaders of equal-length groups add the group size)
+    for (uint32_t i0 = 0; i0 < n; i0 += BRO_W) {
+        uint32_t i = i0 + lane;
+        uint32_t L = i < n ? sc.lens[i] : 0xffu;
+        uint32_t m = bro_match_any(L);
+        if (i < n && (m & bro_lanemask_lt()) == 0u) sc.cnt[L] = (uint16_t)(sc.cnt[L] + bro_popc(m));
+        bro_syncwarp();
+    }
+    // canonical first codes, left-justified limits, sorted[] offsets (uniform, 15 steps)
+    uint32_t code = 0, off = 0, maxdepth = 0, nonzero = 0;
+    uint32_t first[16], offs[16];
+    for (uint32_t L = 1; L <= 15u; L++) {
+        uint32_t c = sc.cnt[L];
+        first[L] = code;
+        offs[L] = off;
+        code = (code + c);
+        uint32_t lim = code << (15u - L);
+        code <<= 1;
+        off += c;
+        nonzero += c;
+        if (c) maxdepth = L;
+        if (lane == 0) {
+            sc.limit[L] = (uint16_t)lim;
+            sc.base[L] = (int16_t)((int)offs[L] - (int)first[L]);
+        }
+    }
+    bro_syncwarp();
+    if (lane == 0) {
+        for (uint32_t L = 1; L <= 15u; L++) { sc.cnt[L] = (uint16_t)offs[L]; T[BRO_T_LIMIT + L] = sc.limit[L]; T[BRO_T_BASE + L] = (uint16_t)sc.base[L]; }
+        T[BRO_T_LIMIT] = 0; T[BRO_T_BASE] = 0;
+        // all-zero lengths happen only for a simple code with NSYM = 1 (max_length == 0: every symbol is inserted
+        // with the empty code, src/huffman/mod.rs:36); a complex code always has >= 2 non-zero lengths
+        bool single = (nonzero == 1u) || (nonzero == 0u);
+        T[BRO_T_SINGLE] = single ? 1 : 0;
+        T[BRO_T_MAXDEPTH] = (uint16_t)maxdepth;
+        T[291] = 0;
+    }
+    bro_syncwarp();
+    // pass 2: stable placement into sorted[] (rank inside the 32-symbol group + running position per length)
+    for (uint32_t i0 = 0; i0 < n; i0 += BRO_W) {
+        uint32_t i = i0 + lane;
+        uint32_t L = i < n ? sc.lens[i] : 0xffu;
+        uint32_t m = bro_match_any(L);
+        bool live = i < n && L != 0u;
+        uint32_t symv = explicit_syms ? (i < n ? sc.syms[i] : 0u) : i;
+        if (live) T[BRO_T_SORTED + sc.cnt[L] + bro_popc(m & bro_lanemask_lt())] = (uint16_t)symv;
+        if (nonzero == 0u && i == 0u) T[BRO_T_SINGLE_SYM] = (uint16_t)symv;
+        bro_syncwarp();
+        if (live && (m & bro_lanemask_lt()) == 0u) sc.cnt[L] = (uint16_t)(sc.cnt[L] + bro_popc(m));
+        bro_syncwarp();
+    }
+    if (nonzero == 1u && lane == 0) T[BRO_T_SINGLE_SYM] = T[BRO_T_SORTED];
+    // root table: entry r is reached when the next 8 stream bits, read LSB first, equal r
+    for (uint32_t r = lane; r < 256u; r += BRO_W) {
+        uint32_t v = bro_brev(r) >> 24;          // the same 8 bits, first bit read most significant
+        uint32_t x = v << 7;
+        uint32_t e = 0;
+        if (nonzero >= 2u) {
+            for (uint32_t L = 1; L <= 15u; L++) {
+                if (x < sc.limit[L]) {
+                    if (L <= 8u) e = (uint32_t)T[BRO_T_SORTED + (int)sc.base[L] + (int)(v >> (8u - L))] | (L << 10);
+                    else e = 1u;
+                    break;
+                }
+            }
+        }
+        T[r] = (uint16_t)e;
+    }
+    bro_syncwarp();
+}
+
+// ------------------------------------------------------------------------------------------------------
+// decoder state
+// ------------------------------------------------------------------------------------------------------
+struct BroBlockCat {          // src/lib.rs:152-160, one per category (literals, insert&copy, distances)
+    uint32_t nbl;
+    uint32_t btype, btype_prev;
+    uint32_t blen;            // valid when nbl >= 2 (the reference's Option<BLen> is Some exactly then)
+};
+
+struct BroDec {
+    BroBits in;
+    uint8_t* out;             // output slot
+    uint32_t cap;             // slot capacity
+    uint32_t pos;             // bytes produced so far (= count_output, src/lib.rs:385)
+    uint32_t window;          // (1 << WBITS) - 16, src/lib.rs:1562
+    uint32_t p1, p2;          // literal_buf, src/lib.rs:389
+    uint32_t dist[4];         // distance_buf, src/lib.rs:393; dist[0] is the last distance
+    uint16_t* arena;          // per-warp table arena
+    BroScratch* sc;
+    const uint8_t* dict;      // 122,784-byte static dictionary image
+    int quirk_spec;
+};
+
+// The fixed code of NBLTYPES / NTREES (src/lib.rs:126-132, 501-525): 0 -> 1, else 1 + (1 << n) + n extra bits
+// with n read from 3 bits.  Any failed bit read is UnexpectedEOF.
+BRO_FN int bro_read_nbltypes(BroDec& d, uint32_t& v) {
+    uint32_t b, n, extra;
+    if (!bro_read_bits(d.in, 1, b)) return BRO_ST_UnexpectedEOF;
+    if (!b) { v = 1; return 0; }
+    if (!bro_read_bits(d.in, 3, n)) return BRO_ST_UnexpectedEOF;
+    if (!bro_read_bits(d.in, n, extra)) return BRO_ST_UnexpectedEOF;
+    v = 1u + (1u << n) + extra;
+    return 0;
+}
+
+// src/lib.rs:597-665
+BRO_COLD int bro_read_simple_code(BroDec& d, uint32_t alphabet, uint16_t* T) {
+    BroScratch& sc = *d.sc;
+    uint32_t bit_width = 0;
+    for (uint32_t a = alphabet - 1u; a; a >>= 1) bit_width++;   // 16 - leading_zeros(alphabet-1 as u16), src/lib.rs:598
+    uint32_t nsym, s[4];
+    if (!bro_read_bits(d.in, 2, nsym)) return BRO_ST_UnexpectedEOF;
+    nsym += 1;
+    for (uint32_t i = 0; i < nsym; i++) {
+        if (!bro_read_bits(d.in, bit_width, s[i])) return BRO_ST_UnexpectedEOF;
+        if (s[i] >= alphabet) return BRO_ST_InvalidSymbol;
+    }
+    for (uint32_t i = 0; i + 1 < nsym; i++)
+        for (uint32_t j = i + 1; j < nsym; j++)
+            if (s[i] == s[j]) return BRO_ST_InvalidSymbol;
+    uint32_t L[4] = {0, 0, 0, 0};
+#define BRO_SWAP(a, b) do { if (s[a] > s[b]) { uint32_t t_ = s[a]; s[a] = s[b]; s[b] = t_; } } while (0)
+    if (nsym == 2) { BRO_SWAP(0, 1); L[0] = L[1] = 1; }
+    else if (nsym == 3) { BRO_SWAP(1, 2); L[0] = 1; L[1] = L[2] = 2; }
+    else if (nsym == 4) {
+        uint32_t tree_select;
+        if (!bro_read_bits(d.in, 1, tree_select)) return BRO_ST_UnexpectedEOF;
+        if (!tree_select) {
+            BRO_SWAP(0, 1); BRO_SWAP(2, 3); BRO_SWAP(0, 2); BRO_SWAP(1, 3); BRO_SWAP(1, 2);
+            L[0] = L[1] = L[2] = L[3] = 2;
+        } else { BRO_SWAP(2, 3); L[0] = 1; L[1] = 2; L[2] = L[3] = 3; }
+    }
+#undef BRO_SWAP
+    bro_syncwarp();
+    if (bro_lane() == 0) for (uint32_t i = 0; i < nsym; i++) { sc.lens[i] = (uint8_t)L[i]; sc.syms[i] = (uint16_t)s[i]; }
+    bro_syncwarp();
+    bro_build_tree(T, sc, nsym, true);
+    return 0;
+}
+
+// src/lib.rs:667-875
+BRO_COLD int bro_read_complex_code(BroDec& d, uint32_t hskip, uint32_t alphabet, uint16_t* T) {
+    BroScratch& sc = *d.sc;
+    const unsigned lane = bro_lane();
+    // code lengths of the code-length code, transmitted in the order 1,2,3,4,0,5,17,6,16,7,8,...,15 with the fixed
+    // code 00->0 01->3 10->4 110->2 1110->1 1111->5 (src/lib.rs:120-125, 669-704)
+    uint32_t cl[18];
+    for (int i = 0; i < 18; i++) cl[i] = 0;
+    uint32_t sum = 0, nonzero = 0;
+    for (uint32_t i = hskip; i < 18u; i++) {
+        uint32_t b, v;
+        if (!bro_read_bits(d.in, 2, b)) return BRO_ST_UnexpectedEOF;
+        if (b == 0u) v = 0;
+        else if (b == 2u) v = 3;          // read order 0,1
+        else if (b == 1u) v = 4;          // read order 1,0
+        else {
+            if (!bro_read_bits(d.in, 1, b)) return BRO_ST_UnexpectedEOF;
+            if (!b) v = 2;
+            else {
+                if (!bro_read_bits(d.in, 1, b)) return BRO_ST_UnexpectedEOF;
+                v = b ? 5 : 1;
+            }
+        }
+        // transmission slot i -> symbol
+        const uint8_t slot_sym[18] = {1, 2, 3, 4, 0, 5, 17, 6, 16, 7, 8, 9, 10, 11, 12, 13, 14, 15};
+        cl[slot_sym[i]] = v;
+        if (v > 0u) {
+            sum += 32u >> v;
+            nonzero += 1;
+            if (sum == 32u) break;
+            if (sum > 32u) return BRO_ST_CodeLengthsChecksum;
+        }
+    }
+    if (nonzero == 0u) return BRO_ST_NoCodeLength;
+    if (nonzero >= 2u && sum < 32u) return BRO_ST_CodeLengthsChecksum;
+
+    // 32-entry table for the code-length code (max length 5), canonical codes by (length, symbol)
+    uint32_t clc_single = 0xffffffffu;
+    {
+        uint32_t code = 0;
+        bro_syncwarp();
+        for (uint32_t L = 1; L <= 5u; L++) {
+            for (uint32_t sy = 0; sy < 18u; sy++) {
+                if (cl[sy] == L) {
+                    uint32_t rev = bro_brev(code) >> (32u - L);
+                    for (uint32_t r = lane; r < 32u; r += BRO_W)
+                        if ((r & ((1u << L) - 1u)) == rev) sc.clc[r] = (uint8_t)(sy | (L << 5));
+                    code++;
+                }
+            }
+            code <<= 1;
+        }
+        if (nonzero == 1u) for (uint32_t sy = 0; sy < 18u; sy++) if (cl[sy]) clc_single = sy;
+        bro_syncwarp();
+    }
+
+    // the symbol code lengths (src/lib.rs:730-864)
+    for (uint32_t i = lane; i < alphabet; i += BRO_W) sc.lens[i] = 0;
+    bro_syncwarp();
+    uint32_t total = 0, last_symbol = 0xffu, last_repeat = 0, have_repeat = 0, last_nz = 8, i = 0, nz = 0;
+    while (i < alphabet) {
+        uint32_t c;
+        if (clc_single != 0xffffffffu) c = clc_single;
+        else {
+            bro_refill(d.in);
+            uint32_t e = sc.clc[(uint32_t)d.in.buf & 31u];
+            uint32_t len = e >> 5;
+            if (len > bro_avail(d.in)) return BRO_ST_UnexpectedEOF;
+            bro_consume(d.in, len);
+            c = e & 31u;
+        }
+        if (c <= 15u) {
+            if (lane == 0) sc.lens[i] = (uint8_t)c;
+            i += 1;
+            last_symbol = c;
+            have_repeat = 0;
+            if (c > 0u) {
+                last_nz = c;
+                nz += 1;
+                total += 32768u >> c;
+                if (total == 32768u) break;
+                if (total > 32768u) return BRO_ST_CodeLengthsChecksum;
+            }
+        } else if (c == 16u) {
+            uint32_t extra, count, newrep;
+            if (!bro_read_bits(d.in, 2, extra)) return BRO_ST_UnexpectedEOF;
+            if (last_symbol == 16u && have_repeat) {
+                newrep = 4u * (last_repeat - 2u) + extra + 3u;
+                if (i + newrep - last_repeat > alphabet) return BRO_ST_ParseErrorComplexPrefixCodeLengths;
+                count = newrep - last_repeat;
+            } else {
+                newrep = 3u + extra;
+                if (i + newrep > alphabet) return BRO_ST_ParseErrorComplexPrefixCodeLengths;
+                count = newrep;
+            }
+            for (uint32_t k = lane; k < count; k += BRO_W) sc.lens[i + k] = (uint8_t)last_nz;
+            i += count;
+            nz += count;
+            total += count * (32768u >> last_nz);
+            last_repeat = newrep;
+            have_repeat = 1;
+            if (total == 32768u) break;
+            if (total > 32768u) return BRO_ST_CodeLengthsChecksum;
+            last_symbol = 16;
+        } else {
+            uint32_t extra;
+            if (!bro_read_bits(d.in, 3, extra)) return BRO_ST_UnexpectedEOF;
+            if (last_symbol == 17u && have_repeat) {
+                uint32_t newrep = 8u * (last_repeat - 2u) + extra + 3u;
+                i += newrep - last_repeat;
+                last_repeat = newrep;
+            } else {
+                i += 3u + extra;
+                last_repeat = 3u + extra;
+            }
+            have_repeat = 1;
+            if (i > alphabet) return BRO_ST_ParseErrorComplexPrefixCodeLengths;
+            last_symbol = 17;
+        }
+    }
+    if (nz < 2u) return BRO_ST_LessThanTwoNonZeroCodeLengths;
+    bro_syncwarp();
+    bro_build_tree(T, sc, alphabet, false);
+    return 0;
+}
+
+// src/lib.rs:877-889
+BRO_FN int bro_read_prefix_code(BroDec& d, uint32_t alphabet, uint16_t* T) {
+    uint32_t kind;
+    if (!bro_read_bits(d.in, 2, kind)) return BRO_ST_UnexpectedEOF;
+    if (kind == 1u) return bro_read_simple_code(d, alphabet, T);
+    return bro_read_complex_code(d, kind, alphabet, T);
+}
+
+// src/lib.rs:957-987
+BRO_FN int bro_read_block_count(BroDec& d, const uint16_t* T, uint32_t& count) {
+    uint32_t sym, extra;
+    int r = bro_decode_sym(d.in, T, sym);
+    if (r != BRO_SYM_OK) return BRO_ST_UnexpectedEOF;          // Ok(None) and Err(_) both map to UnexpectedEOF
+    if (sym > 25u) return BRO_ST_InvalidBlockCountCode;
+    uint32_t be = bro_block_count[sym];
+    if (!bro_read_bits(d.in, be >> 16, extra)) return BRO_ST_UnexpectedEOF;
+    count = (be & 0xffffu) + extra;
+    return 0;
+}
+
+// src/lib.rs:1226-1250 plus the caller's bookkeeping (e.g. 1296-1302)
+BRO_COLD int bro_block_switch(BroDec& d, BroBlockCat& c, uint32_t cat) {
+    uint32_t code, count;
+    int r = bro_decode_sym(d.in, d.arena + BRO_A_BTYPE + cat * BRO_TREE_U16(BRO_ALPHA_BTYPE_MAX), code);
+    if (r == BRO_SYM_HOLE) return BRO_ST_InvalidBlockSwitchCommandCode;
+    if (r == BRO_SYM_EOF) return BRO_ST_UnexpectedEOF;
+    uint32_t bt = code == 0u ? c.btype_prev : code == 1u ? (c.btype + 1u) % c.nbl : code - 2u;
+    int st = bro_read_block_count(d, d.arena + BRO_A_BCOUNT + cat * BRO_TREE_U16(BRO_ALPHA_BCOUNT), count);
+    if (st) return st;
+    c.btype_prev = c.btype;
+    c.btype = bt;
+    c.blen = count - 1u;
+    return 0;
+}
+
+// src/lib.rs:1070-1144 and the IMTF of 1164-1177
+BRO_COLD int bro_read_context_map(BroDec& d, uint32_t ntrees, uint32_t len, uint8_t* cmap) {
+    BroScratch& sc = *d.sc;
+    const unsigned lane = bro_lane();
+    uint32_t b, rlemax = 0;
+    if (!bro_read_bits(d.in, 1, b)) return BRO_ST_UnexpectedEOF;
+    if (b) {
+        if (!bro_read_bits(d.in, 4, rlemax)) return BRO_ST_UnexpectedEOF;
+        rlemax += 1;
+    }
+    uint16_t* T = d.arena + BRO_A_CMTREE;
+    int st = bro_read_prefix_code(d, rlemax + ntrees, T);
+    if (st) return st;
+    uint32_t pushed = 0;
+    while (pushed < len) {
+        uint32_t s;
+        int r = bro_decode_sym(d.in, T, s);
+        if (r == BRO_SYM_EOF) return BRO_ST_UnexpectedEOF;
+        if (r == BRO_SYM_HOLE) return BRO_ST_ParseErrorContextMap;
+        if (s > 0u && s <= rlemax) {
+            uint32_t extra;
+            if (!bro_read_bits(d.in, s, extra)) return BRO_ST_UnexpectedEOF;
+            uint32_t repeat = (1u << s) + extra;
+            if (pushed + repeat > len) return BRO_ST_RunLengthExceededSizeOfContextMap;
+            for (uint32_t k = lane; k < repeat; k += BRO_W) cmap[pushed + k] = 0;
+            pushed += repeat;
+        } else {
+            if (lane == 0) cmap[pushed] = (uint8_t)(s == 0u ? 0u : s - rlemax);
+            pushed += 1;
+        }
+    }
+    if (!bro_read_bits(d.in, 1, b)) return BRO_ST_UnexpectedEOF;
+    if (b) {
+        uint8_t* mtf = sc.lens;   // 256-entry move-to-front list
+        bro_syncwarp();
+        for (uint32_t k = lane; k < 256u; k += BRO_W) mtf[k] = (uint8_t)k;
+        bro_syncwarp();
+        if (lane == 0) {
+            for (uint32_t k = 0; k < len; k++) {
+                uint32_t index = cmap[k];
+                uint8_t value = mtf[index];
+                cmap[k] = value;
+                for (uint32_t j = index; j >= 1u; j--) mtf[j] = mtf[j - 1];
+                mtf[0] = value;
+            }
+        }
+    }
+    bro_syncwarp();
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------------
+// byte movement ("phase two"): every routine is executed by the whole warp
+// ------------------------------------------------------------------------------------------------------
+
+// 16 bytes from an arbitrary address, as four aligned 32-bit loads + a fifth when misaligned
+struct BroV4 { uint32_t x, y, z, w; };
+BRO_FN BroV4 bro_load16(const uint8_t* p) {
+    uintptr_t a = (uintptr_t)p;
+    const uint32_t* w = (const uint32_t*)(a & ~(uintptr_t)3);
+    unsigned sh = 8u * (unsigned)(a & 3u);
+    uint32_t w0 = w[0], w1 = w[1], w2 = w[2], w3 = w[3];
+    BroV4 r;
+    if (sh == 0u) { r.x = w0; r.y = w1; r.z = w2; r.w = w3; }
+    else {
+        uint32_t w4 = w[4];
+        r.x = bro_funnel_r(w0, w1, sh); r.y = bro_funnel_r(w1, w2, sh);
+        r.z = bro_funnel_r(w2, w3, sh); r.w = bro_funnel_r(w3, w4, sh);
+    }
+    return r;
+}
+
+// dst[0..n) = src[0..n) where the regions do not overlap, or dst - src >= 16*BRO_W (so that one warp step never
+// reads a byte written in the same step).  dst is advanced in 16-byte aligned vector stores.
+BRO_FN void bro_copy_far(uint8_t* dst, const uint8_t* src, uint32_t n) {
+    const unsigned lane = bro_lane();
+#if defined(BRO_HOSTSIM)
+    for (uint32_t i = 0; i < n; i++) dst[i] = src[i];
+    (void)lane;
+#else
+    uint32_t head = (uint32_t)((16u - ((uintptr_t)dst & 15u)) & 15u);
+    if (head > n) head = n;
+    if (lane < head) dst[lane] = src[lane];
+    dst += head; src += head; n -= head;
+    while (n >= 512u) {
+        bro_syncwarp();
+        BroV4 v = bro_load16(src + 16u * lane);
+        *(uint4*)(dst + 16u * lane) = make_uint4(v.x, v.y, v.z, v.w);
+        dst += 512; src += 512; n -= 512;
+    }
+    bro_syncwarp();
+    uint32_t nv = n >> 4;
+    if (lane < nv) {
+        BroV4 v = bro_load16(src + 16u * lane);
+        *(uint4*)(dst + 16u * lane) = make_uint4(v.x, v.y, v.z, v.w);
+    }
+    uint32_t done = nv << 4;
+    if (done + lane < n) dst[done + lane] = src[done + lane];
+#endif
+}
+
+// LZ77 backward copy inside the output slot: out[pos .. pos+len) = bytes `dist` back, periodic when dist < len
+// (src/lib.rs:1491-1505; the ring-buffer window of src/ringbuffer/mod.rs is the linear output itself).
+BRO_FN void bro_lz_copy(uint8_t* out, uint32_t pos, uint32_t dist, uint32_t len) {
+    const unsigned lane = bro_lane();
+    bro_syncwarp();
+    uint8_t* dst = out + pos;
+    const uint8_t* src = dst - dist;
+#if defined(BRO_HOSTSIM)
+    for (uint32_t i = 0; i < len; i++) dst[i] = src[i];
+    (void)lane;
+#else
+    if (len <= 32u) {
+        if (lane < len) dst[lane] = src[dist >= len ? lane : lane % dist];
+        return;
+    }
+    if (dist >= len || dist >= 512u) { bro_copy_far(dst, src, len); return; }
+    // periodic fill: the first (m-1)*dist bytes straight from the pattern, the rest from m*dist >= 512 bytes back
+    uint32_t m = (511u + dist) / dist;
+    uint32_t n0 = (m - 1u) * dist;
+    if (n0 > len) n0 = len;
+    for (uint32_t i = lane; i < n0; i += 32u) dst[i] = src[i % dist];
+    if (len > n0) bro_copy_far(dst + n0, dst + n0 - m * dist, len - n0);
+#endif
+}
+
+// Static dictionary word + transform (src/lib.rs:1506-1540, src/transformation/mod.rs:84-209).  Returns the
+// transformed length, or -1 where the reference panics (uppercase_first on a 0x00 byte).
+BRO_COLD int bro_dict_word(BroDec& d, uint32_t copy_len, uint32_t index, uint32_t tid) {
+    BroScratch& sc = *d.sc;
+    const unsigned lane = bro_lane();
+    const uint8_t* w = d.dict + bro_dict_offsets[copy_len] + index * copy_len;
+    uint32_t type = bro_xf_type[tid], plen = bro_xf_prefix_len[tid], slen = bro_xf_suffix_len[tid];
+    uint32_t from = 0, wl = copy_len;
+    if (type >= 3u && type <= 11u) {            // OmitFirstN: base_word[min(N, len-1)..] (Q3) / spec: [min(N,len)..]
+        uint32_t n = type - 2u;
+        from = d.quirk_spec ? (n < wl ? n : wl) : (n < wl - 1u ? n : wl - 1u);
+        wl -= from;
+    } else if (type >= 12u) {                   // OmitLastN: base_word[..max(N,len)-N]
+        uint32_t n = type - 11u;
+        wl = (wl > n ? wl : n) - n;
+    }
+    bro_syncwarp();
+    for (uint32_t i = lane; i < plen; i += BRO_W) sc.word[i] = bro_xf_strings[bro_xf_prefix_off[tid] + i];
+    for (uint32_t i = lane; i < wl; i += BRO_W) sc.word[plen + i] = w[from + i];
+    for (uint32_t i = lane; i < slen; i += BRO_W) sc.word[plen + wl + i] = bro_xf_strings[bro_xf_suffix_off[tid] + i];
+    bro_syncwarp();
+    int ret = (int)(plen + wl + slen);
+    if (type == 1u || type == 2u) {
+        // uppercase_first (src/transformation/mod.rs:42-82) / uppercase_all (3-40): a serial UTF-8 walk
+        uint32_t c0 = sc.word[plen];
+        if (type == 1u && c0 == 0u && !d.quirk_spec) ret = -1;
+        else if (lane == 0) {
+            uint8_t* v = sc.word + plen;
+            uint32_t i = 0;
+            do {
+                uint32_t c = v[i];
+                if (c < 192u) { if (c >= 97u && c <= 122u) v[i] ^= 32; i += 1; }
+                else if (c < 224u) { if (i + 1 < wl) v[i + 1] ^= 32; i += 2; }
+                else { if (i + 2 < wl) v[i + 2] ^= 5; i += 3; }
+            } while (type == 2u && i < wl);
+        }
+        bro_syncwarp();
+    }
+    return ret;
+}
+
+// ------------------------------------------------------------------------------------------------------
+// one compressed meta-block: src/lib.rs:1745-2141
+// ------------------------------------------------------------------------------------------------------
+BRO_FN int bro_step_block(BroDec& d, BroBlockCat& c, uint32_t cat) {   // src/lib.rs:1182-1197 et al.
+    if (c.nbl < 2u) return 0;
+    if (c.blen == 0u) return bro_block_switch(d, c, cat);
+    c.blen -= 1u;
+    return 0;
+}
+
+BRO_FN int bro_decode_compressed_metablock(BroDec& d, uint32_t mlen) {
+    const unsigned lane = bro_lane();
+    uint16_t* A = d.arena;
+    BroBlockCat cat[3];
+    int st;
+    // NBLTYPES{L,I,D}, block type / count codes, first block counts (src/lib.rs:1745-1885)
+    for (uint32_t k = 0; k < 3u; k++) {
+        cat[k].btype = 0; cat[k].btype_prev = 1; cat[k].blen = 0;
+        if ((st = bro_read_nbltypes(d, cat[k].nbl))) return st;
+        if (cat[k].nbl >= 2u) {
+            if ((st = bro_read_prefix_code(d, cat[k].nbl + 2u, A + BRO_A_BTYPE + k * BRO_TREE_U16(BRO_ALPHA_BTYPE_MAX)))) return st;
+            if ((st = bro_read_prefix_code(d, BRO_ALPHA_BCOUNT, A + BRO_A_BCOUNT + k * BRO_TREE_U16(BRO_ALPHA_BCOUNT)))) return st;
+            if ((st = bro_read_block_count(d, A + BRO_A_BCOUNT + k * BRO_TREE_U16(BRO_ALPHA_BCOUNT), cat[k].blen))) return st;
+        }
+    }
+    // NPOSTFIX, NDIRECT (src/lib.rs:548-560), context modes (562-573)
+    uint32_t npostfix, ndirect;
+    if (!bro_read_bits(d.in, 2, npostfix)) return BRO_ST_UnexpectedEOF;
+    if (!bro_read_bits(d.in, 4, ndirect)) return BRO_ST_UnexpectedEOF;
+    ndirect <<= npostfix;
+    uint8_t* modes = (uint8_t*)(A + BRO_A_MODES);
+    for (uint32_t i = 0; i < cat[0].nbl; i++) {
+        uint32_t m;
+        if (!bro_read_bits(d.in, 2, m)) return BRO_ST_UnexpectedEOF;
+        if (lane == 0) modes[i] = (uint8_t)m;
+    }
+    // NTREESL + literal context map, NTREESD + distance context map (src/lib.rs:1916-1973)
+    uint32_t ntl, ntd;
+    uint8_t* cmap_l = (uint8_t*)(A + BRO_A_CMAP_L);
+    uint8_t* cmap_d = (uint8_t*)(A + BRO_A_CMAP_D);
+    if ((st = bro_read_nbltypes(d, ntl))) return st;
+    if (ntl >= 2u) { if ((st = bro_read_context_map(d, ntl, 64u * cat[0].nbl, cmap_l))) return st; }
+    if ((st = bro_read_nbltypes(d, ntd))) return st;
+    if (ntd >= 2u) { if ((st = bro_read_context_map(d, ntd, 4u * cat[2].nbl, cmap_d))) return st; }
+    // prefix codes (src/lib.rs:1016-1068)
+    for (uint32_t i = 0; i < ntl; i++)
+        if ((st = bro_read_prefix_code(d, BRO_ALPHA_LIT, A + BRO_A_LIT + i * BRO_TREE_U16(BRO_ALPHA_LIT)))) return st;
+    for (uint32_t i = 0; i < cat[1].nbl; i++)
+        if ((st = bro_read_prefix_code(d, BRO_ALPHA_CMD, A + BRO_A_CMD + i * BRO_TREE_U16(BRO_ALPHA_CMD)))) return st;
+    const uint32_t dist_alphabet = 16u + ndirect + (48u << npostfix);
+    for (uint32_t i = 0; i < ntd; i++)
+        if ((st = bro_read_prefix_code(d, dist_alphabet, A + BRO_A_DIST + i * BRO_TREE_U16(BRO_ALPHA_DIST_MAX)))) return st;
+    bro_syncwarp();
+
+    const uint32_t mb_begin = d.pos;   // meta_block.count_output == d.pos - mb_begin
+    // command loop (src/lib.rs:2003-2141)
+    for (;;) {
+        // ---- phase one: entropy decode of one insert&copy command ----
+        uint32_t sym, extra;
+        if ((st = bro_step_block(d, cat[1], 1))) return st;
+        int r = bro_decode_sym(d.in, A + BRO_A_CMD + cat[1].btype * BRO_TREE_U16(BRO_ALPHA_CMD), sym);
+        if (r == BRO_SYM_HOLE) return BRO_ST_ParseErrorInsertAndCopyLength;
+        if (r == BRO_SYM_EOF) return BRO_ST_UnexpectedEOF;
+        uint32_t ie = bro_ic_insert[sym], ce = bro_ic_copy[sym];
+        uint32_t insert_len = ie & 0xffffu, copy_len = ce & 0xffffu;
+        if (!bro_read_bits(d.in, ie >> 16, extra)) return BRO_ST_UnexpectedEOF;   // insert extra bits first
+        insert_len += extra;
+        if (!bro_read_bits(d.in, ce >> 16, extra)) return BRO_ST_UnexpectedEOF;
+        copy_len += extra;
+        uint32_t mb_out = d.pos - mb_begin;
+        if (mlen < mb_out + insert_len) return BRO_ST_ExceededExpectedBytes;       // src/lib.rs:2036-2039
+        // literals (src/lib.rs:1286-1365).  The reference decodes all literals of a command before it emits any, so a
+        // decode error inside the run wins over a full output slot: keep decoding (without storing) past the end of
+        // the slot and report OutputTooSmall only if the whole run decoded.
+        for (uint32_t k = 0; k < insert_len; k++) {
+            if ((st = bro_step_block(d, cat[0], 0))) return st;
+            const uint16_t* T = A + BRO_A_LIT;
+            if (ntl >= 2u) {
+                uint32_t bt = cat[0].btype, mode = modes[bt], cid;
+                if (mode == 0u) cid = d.p1 & 0x3fu;
+                else if (mode == 1u) cid = d.p1 >> 2;
+                else if (mode == 2u) cid = (uint32_t)bro_lut0[d.p1] | bro_lut1[d.p2];
+                else cid = ((uint32_t)bro_lut2[d.p1] << 3) | bro_lut2[d.p2];
+                T += (uint32_t)cmap_l[bt * 64u + cid] * BRO_TREE_U16(BRO_ALPHA_LIT);
+            }
+            uint32_t lit;
+            r = bro_decode_sym(d.in, T, lit);
+            if (r == BRO_SYM_HOLE) return BRO_ST_ParseErrorInsertLiterals;
+            if (r == BRO_SYM_EOF) return BRO_ST_UnexpectedEOF;
+            if (lane == 0 && d.pos < d.cap) d.out[d.pos] = (uint8_t)lit;
+            d.pos += 1;
+            d.p2 = d.p1; d.p1 = lit;
+        }
+        if (d.pos > d.cap) { d.pos = d.cap; return BRO_ST_OutputTooSmall; }
+        if (d.pos - mb_begin == mlen) return 0;                                      // src/lib.rs:2069-2070
+        // distance code (src/lib.rs:1367-1410)
+        uint32_t dcode = 0;
+        if (sym >= 128u) {
+            if ((st = bro_step_block(d, cat[2], 2))) return st;
+            const uint16_t* T = A + BRO_A_DIST;
+            if (ntd >= 2u) {
+                uint32_t cid = copy_len <= 4u ? copy_len - 2u : 3u;
+                T += (uint32_t)cmap_d[cat[2].btype * 4u + cid] * BRO_TREE_U16(BRO_ALPHA_DIST_MAX);
+            }
+            r = bro_decode_sym(d.in, T, dcode);
+            if (r == BRO_SYM_HOLE) return BRO_ST_ParseErrorDistanceCode;
+            if (r == BRO_SYM_EOF) return BRO_ST_UnexpectedEOF;
+        }
+        // distance (src/lib.rs:1412-1481)
+        uint32_t distance;
+        if (dcode <= 3u) distance = d.dist[dcode];
+        else if (dcode <= 15u) {
+            int32_t basev = (int32_t)(dcode <= 9u ? d.dist[0] : d.dist[1]);
+            int32_t delta = (int32_t)(((dcode <= 9u ? dcode - 2u : dcode - 8u)) >> 1);
+            int64_t v = (int64_t)(uint32_t)basev + ((dcode & 1u) ? (int64_t)delta : -(int64_t)delta);
+            if (v <= 0) return BRO_ST_InvalidNonPositiveDistance;
+            distance = (uint32_t)v;
+        } else if (dcode <= 15u + ndirect) distance = dcode - 15u;
+        else {
+            uint32_t t = dcode - ndirect - 16u;
+            uint32_t ndistbits = 1u + (t >> (npostfix + 1u));
+            uint32_t dextra;
+            if (!bro_read_bits(d.in, ndistbits, dextra)) return BRO_ST_UnexpectedEOF;
+            uint32_t hcode = t >> npostfix, lcode = t & ((1u << npostfix) - 1u);
+            uint32_t offset = ((2u + (hcode & 1u)) << ndistbits) - 4u;
+            distance = ((offset + dextra) << npostfix) + lcode + ndirect + 1u;
+        }
+        uint32_t max_allowed = d.window < d.pos ? d.window : d.pos;
+        if (dcode > 0u && distance <= max_allowed) {                                // src/lib.rs:1476-1478
+            d.dist[3] = d.dist[2]; d.dist[2] = d.dist[1]; d.dist[1] = d.dist[0]; d.dist[0] = distance;
+        }
+        // ---- phase two: materialise the copy ----
+        mb_out = d.pos - mb_begin;
+        if (distance <= max_allowed) {
+            if (mlen < mb_out + copy_len) return BRO_ST_ExceededExpectedBytes;     // src/lib.rs:2105-2108
+            if (copy_len > d.cap - d.pos) return BRO_ST_OutputTooSmall;
+            bro_lz_copy(d.out, d.pos, distance, copy_len);
+            d.pos += copy_len;
+            bro_syncwarp();
+            d.p1 = d.out[d.pos - 1]; d.p2 = d.out[d.pos - 2];                        // copy_len >= 2
+        } else {
+            if (copy_len < 4u || copy_len > 24u) return BRO_ST_InvalidLengthInStaticDictionary;
+            uint32_t word_id = distance - max_allowed - 1u;
+            uint32_t bits = bro_dict_size_bits[copy_len];
+            uint32_t index = word_id & ((1u << bits) - 1u), tid = word_id >> bits;
+            if (tid > 120u) return BRO_ST_InvalidTransformId;
+            int n = bro_dict_word(d, copy_len, index, tid);
+            if (n < 0) return BRO_ST_PanicUppercaseZero;
+            if (mlen < mb_out + (uint32_t)n) return BRO_ST_ExceededExpectedBytes;  // checked after the transform (Q10)
+            if ((uint32_t)n > d.cap - d.pos) return BRO_ST_OutputTooSmall;
+            for (uint32_t i = lane; i < (uint32_t)n; i += BRO_W) d.out[d.pos + i] = d.sc->word[i];
+            if (n >= 2) { d.p1 = d.sc->word[n - 1]; d.p2 = d.sc->word[n - 2]; }
+            else if (n == 1) { d.p2 = d.p1; d.p1 = d.sc->word[0]; }
+            d.pos += (uint32_t)n;
+            bro_syncwarp();
+        }
+        if (d.pos - mb_begin == mlen) return 0;                                      // src/lib.rs:2128-2130
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------
+// one stream: src/lib.rs:1545-2170.  Returns the status; *out_len = bytes produced.
+// ------------------------------------------------------------------------------------------------------
+BRO_FN int bro_decode_stream(BroDec& d) {
+    uint32_t b, n, v;
+    // WBITS (src/lib.rs:89-119, 412-418): 0 -> 16; 1+n -> 17+n; 1000+m -> 8+m (m>=2), 17 (m=0), m=1 reserved (Q8)
+    if (!bro_read_bits(d.in, 1, b)) return BRO_ST_UnexpectedEOF;
+    uint32_t wbits = 16;
+    if (b) {
+        if (!bro_read_bits(d.in, 3, n)) return BRO_ST_UnexpectedEOF;
+        if (n) wbits = 17u + n;
+        else {
+            if (!bro_read_bits(d.in, 3, n)) return BRO_ST_UnexpectedEOF;
+            if (n == 1u) return BRO_ST_UnexpectedEOF;
+            wbits = n ? 8u + n : 17u;
+        }
+    }
+    d.window = (1u << wbits) - 16u;
+    for (;;) {
+        uint32_t is_last;
+        if (!bro_read_bits(d.in, 1, is_last)) return BRO_ST_UnexpectedEOF;
+        if (is_last) {
+            if (!bro_read_bits(d.in, 1, b)) return BRO_ST_UnexpectedEOF;
+            if (b) break;                                                             // ISLASTEMPTY
+        }
+        if (!bro_read_bits(d.in, 2, n)) return BRO_ST_UnexpectedEOF;              // MNIBBLES
+        if (n == 3u) {
+            // metadata block (src/lib.rs:1617-1683)
+            if (!bro_read_bits(d.in, 1, b)) return BRO_ST_UnexpectedEOF;
+            if (b) return BRO_ST_NonZeroReservedBit;
+            uint32_t skip_bytes, skip = 0;
+            if (!bro_read_bits(d.in, 2, skip_bytes)) return BRO_ST_UnexpectedEOF;
+            if (skip_bytes) {
+                uint32_t last = 0;
+                for (uint32_t i = 0; i < skip_bytes; i++) {
+                    if (!bro_read_bits(d.in, 8, last)) return BRO_ST_UnexpectedEOF;
+                    skip |= last << (d.quirk_spec ? 8u * i : i);                    // sic: << i (Q1, src/lib.rs:463)
+                }
+                if (skip_bytes > 1u && last == 0u) return BRO_ST_UnexpectedEOF;    // InvalidMSkipLen is remapped (Q2)
+                skip += 1;
+            }
+            bro_read_byte_tail(d.in, v);
+            if (v) return BRO_ST_NonZeroFillBit;
+            if (skip_bytes) {
+                const uint8_t* a = bro_bits_addr(d.in);
+                if ((uint64_t)(d.in.end - a) < (uint64_t)skip) return BRO_ST_UnexpectedEOF;
+                bro_bits_seek(d.in, a + skip);
+            }
+            if (is_last) break;
+            continue;
+        }
+        // MLEN (src/lib.rs:469-483)
+        uint32_t nibbles = n + 4u, mlen;
+        if (!bro_read_bits(d.in, 4u * nibbles, mlen)) return BRO_ST_UnexpectedEOF;
+        if (nibbles > 4u && (mlen >> ((nibbles - 1u) * 4u)) == 0u) return BRO_ST_NonZeroTrailerNibble;
+        mlen += 1;
+        if (!is_last) {
+            if (!bro_read_bits(d.in, 1, b)) return BRO_ST_UnexpectedEOF;          // ISUNCOMPRESSED
+            if (b) {
+                // stored block (src/lib.rs:1701-1734): all MLEN bytes are read before any is emitted
+                bro_read_byte_tail(d.in, v);
+                if (v) return BRO_ST_NonZeroFillBit;
+                const uint8_t* a = bro_bits_addr(d.in);
+                if ((uint64_t)(d.in.end - a) < (uint64_t)mlen) return BRO_ST_UnexpectedEOF;
+                if (mlen > d.cap - d.pos) return BRO_ST_OutputTooSmall;
+                bro_syncwarp();
+                bro_copy_far(d.out + d.pos, a, mlen);
+                d.pos += mlen;
+                d.p2 = mlen >= 2u ? a[mlen - 2] : d.p1;
+                d.p1 = a[mlen - 1];
+                bro_bits_seek(d.in, a + mlen);
+                continue;
+            }
+        }
+        int st = bro_decode_compressed_metablock(d, mlen);
+        if (st) return st;
+        if (is_last) break;
+    }
+    // StreamEnd (src/lib.rs:2155-2167)
+    bro_read_byte_tail(d.in, v);
+    if (v) return BRO_ST_NonZeroTrailerBit;
+    bro_refill(d.in);
+    if (bro_avail(d.in) > 0u) return BRO_ST_ExpectedEndOfStream;
+    return BRO_ST_OK;
+}

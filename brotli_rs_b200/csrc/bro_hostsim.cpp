@@ -1,0 +1,34 @@
+// Host simulation of the warp decoder with a 1-lane "warp" -- CPU TEST-SUITE ONLY.
+// Built into tests/_build/libbro_hostsim.so by tests/hostsim.py; never part of libbrotli_b200.so.
+// It lets the CPU test-suite fuzz the decoder logic of bro_decoder_core.h against the oracle without a GPU.
+#define BRO_HOSTSIM 1
+#include <stdlib.h>
+#include <string.h>
+
+#include "bro_decoder_core.h"
+
+extern "C" const uint8_t bro_dictionary_blob[];
+
+extern "C" int bro_hostsim_decode(const uint8_t* in, size_t in_len, uint8_t* out, size_t cap, size_t* out_len, int quirks) {
+    BroDec d;
+    memset(&d, 0, sizeof(d));
+    BroScratch* sc = (BroScratch*)calloc(1, sizeof(BroScratch));
+    uint16_t* arena = (uint16_t*)malloc(BRO_ARENA_BYTES);
+    d.sc = sc;
+    d.arena = arena;
+    d.dict = bro_dictionary_blob;
+    d.out = out;
+    d.cap = cap > BRO_MAX_SLOT ? (uint32_t)BRO_MAX_SLOT : (uint32_t)cap;
+    d.pos = 0;
+    d.p1 = d.p2 = 0;
+    d.dist[0] = 4; d.dist[1] = 11; d.dist[2] = 15; d.dist[3] = 16;
+    d.quirk_spec = quirks;
+    bro_bits_init(d.in, in, in + in_len);
+    int st = bro_decode_stream(d);
+    *out_len = d.pos;
+    free(sc);
+    free(arena);
+    return st;
+}
+
+extern "C" unsigned bro_hostsim_arena_bytes() { return BRO_ARENA_BYTES; }

@@ -1,0 +1,95 @@
+/*
+ * brotli_b200.h -- C ABI of the B200-native batched Brotli decoder (libbrotli_b200.so).
+ *
+ * This is the drop-in boundary for the ONE hot path of ende76/brotli-rs: decoding a Brotli stream behind
+ * `brotli::Decompressor<R: Read>`.  Every entry point is plain C (pointers and sizes, no CUDA or torch types)
+ * so that the reference's host language can bind it over FFI; INTEGRATION.md shows the Rust shim.
+ * Citations are relative to the reference repository.
+ *
+ *   reference interface                                   replaced by
+ *   ---------------------------------------------------   --------------------------------------------
+ *   Decompressor::new(r)            src/lib.rs:398-410    bro_reader_new
+ *   <Decompressor as Read>::read    src/lib.rs:2173-2193  bro_reader_read
+ *   Decompressor::decompress        src/lib.rs:1545-2170  bro_batch_decode / bro_batch_decode_host
+ *                                                         (the whole state machine runs on the GPU, one warp
+ *                                                          per stream, many streams per launch)
+ *   DecompressorError + description src/lib.rs:294-357    int32 status + bro_status_description
+ *   drop(Decompressor)                                    bro_reader_free
+ *
+ * There is no CPU fallback: every decode call runs the CUDA kernel or fails with BRO_ST_CudaError.
+ */
+#ifndef BROTLI_B200_H
+#define BROTLI_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* Status of one stream: 0 = OK, 1..24 = the reference's DecompressorError variants in enum order
+ * (src/lib.rs:294-319), >= 100 = conditions the reference cannot express.  See csrc/bro_status.h. */
+#define BRO_OK 0
+#define BRO_UNEXPECTED_EOF 24
+#define BRO_OUTPUT_TOO_SMALL 100      /* the stream decodes to more bytes than its output slot holds */
+#define BRO_CUDA_ERROR 101            /* a CUDA call failed; bro_ctx_last_cuda_error() has the text */
+#define BRO_PANIC_UPPERCASE_ZERO 102  /* the reference panics here (src/transformation/mod.rs:78) */
+#define BRO_INVALID_ARGUMENT 104
+
+typedef struct bro_ctx bro_ctx;       /* one GPU, one CUDA stream's worth of scratch; not thread safe */
+typedef struct bro_reader bro_reader; /* the Read-struct: one compressed stream, served from a host buffer */
+
+/* Quirk switch: 0 = bit-exact with the reference's code (default), 1 = follow the
+ * Brotli specification where the reference deviates from it. */
+#define BRO_QUIRKS_REFERENCE 0
+#define BRO_QUIRKS_SPEC 1
+
+/* Create a decoder context on CUDA device `device` (-1 = current device).  Allocates the static dictionary
+ * image, the per-warp table arenas and the work counter.  Returns BRO_OK or BRO_CUDA_ERROR. */
+int bro_ctx_create(bro_ctx** ctx, int device);
+void bro_ctx_destroy(bro_ctx* ctx);
+int bro_ctx_set_quirks(bro_ctx* ctx, int quirks);
+const char* bro_ctx_last_cuda_error(const bro_ctx* ctx);
+/* Number of kernel launches issued through this context so far (bench.py's gpu_launches). */
+uint64_t bro_ctx_launch_count(const bro_ctx* ctx);
+/* Resident decoder warps per launch (one stream per warp at a time). */
+uint32_t bro_ctx_num_warps(const bro_ctx* ctx);
+
+/* THE HOT PATH.  Decode n independent streams in one launch; everything is device memory.
+ *   d_in       concatenated compressed streams
+ *   d_in_off   n+1 byte offsets into d_in (stream i = [d_in_off[i], d_in_off[i+1]))
+ *   d_out      output buffer; stream i owns the slot [d_out_off[i], d_out_off[i+1])
+ *   d_out_off  n+1 byte offsets into d_out (slot capacities; a slot never receives bytes past its end)
+ *   d_out_len  n: bytes produced for stream i
+ *   d_status   n: status of stream i (a bad stream never affects another)
+ *   stream     cudaStream_t as void* (NULL = default stream).  The call is asynchronous.
+ * Replaces Decompressor::decompress (src/lib.rs:1545-2170) and all of its helpers. */
+int bro_batch_decode(bro_ctx* ctx, const uint8_t* d_in, const uint64_t* d_in_off, uint8_t* d_out,
+                     const uint64_t* d_out_off, uint64_t* d_out_len, int32_t* d_status, uint32_t n, void* stream);
+
+/* Same, with HOST buffers (pinned memory recommended): copies the inputs to the device, launches, copies the
+ * slots, lengths and statuses back, and synchronises.  This is the end-to-end path a host-language caller uses. */
+int bro_batch_decode_host(bro_ctx* ctx, const uint8_t* h_in, const uint64_t* h_in_off, uint8_t* h_out,
+                          const uint64_t* h_out_off, uint64_t* h_out_len, int32_t* h_status, uint32_t n);
+
+/* The reference's error strings, byte-identical (src/lib.rs:331-354; typos included). */
+const char* bro_status_description(int status);
+
+/* ---- the Read-struct: brotli::Decompressor<R: Read> (src/lib.rs:378-410, 2173-2193) ----
+ * `cb` trampolines to R::read: it fills up to `cap` bytes and returns the count, 0 at end of input, < 0 on an
+ * I/O error (which the reference folds into UnexpectedEOF, src/bitreader/mod.rs:78-82).
+ * Like Decompressor::new, bro_reader_new performs no I/O.  The first bro_reader_read drains `cb`, decodes the
+ * stream on the GPU (one-stream batch; the output slot grows geometrically while the status is
+ * BRO_OUTPUT_TOO_SMALL) and then serves bytes from a host buffer.  Returns the number of bytes written to
+ * `buf` (0 = end of stream) or -(status) when the stream is invalid. */
+typedef intptr_t (*bro_read_cb)(void* user, uint8_t* buf, size_t cap);
+bro_reader* bro_reader_new(bro_ctx* ctx, bro_read_cb cb, void* user);
+intptr_t bro_reader_read(bro_reader* r, uint8_t* buf, size_t len);
+int bro_reader_status(const bro_reader* r);
+void bro_reader_free(bro_reader* r);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BROTLI_B200_H */

@@ -1,0 +1,45 @@
+"""Builds and binds the 1-lane host simulation of the warp decoder (brotli_rs_b200/csrc/bro_hostsim.cpp).
+
+CPU TEST-SUITE ONLY: it lets `pytest -m "not gpu"` exercise the decoder logic of bro_decoder_core.h (table build,
+canonical decode, EOF/hole semantics, every error path) against the oracle where no GPU exists.  The product
+library never contains or calls it.
+"""
+import ctypes
+import os
+import subprocess
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+CSRC = os.path.join(ROOT, "brotli_rs_b200", "csrc")
+BUILD = os.path.join(ROOT, "tests", "_build")
+_LIBS = {}
+
+
+def _build(asan):
+    os.makedirs(BUILD, exist_ok=True)
+    so = os.path.join(BUILD, "libbro_hostsim_asan.so" if asan else "libbro_hostsim.so")
+    srcs = [os.path.join(CSRC, "bro_hostsim.cpp"), os.path.join(ROOT, "oracle", "dict_blob.c")]
+    deps = srcs + [os.path.join(CSRC, f) for f in ("bro_decoder_core.h", "bro_status.h", "bro_tables_generated.h")]
+    if os.path.exists(so) and all(os.path.getmtime(so) >= os.path.getmtime(d) for d in deps):
+        return so
+    flags = ["-O1", "-g", "-fsanitize=address,undefined", "-fno-sanitize-recover=undefined"] if asan else ["-O2"]
+    cmd = ["g++", "-std=c++17", "-fPIC", "-shared", "-Wno-unknown-pragmas"] + flags + ["-o", so] + srcs + \
+          ["-Wa,-I" + os.path.join(ROOT, "brotli_rs_b200", "data")]
+    subprocess.check_call(cmd)
+    return so
+
+
+def lib(asan=False):
+    if asan not in _LIBS:
+        L = ctypes.CDLL(_build(asan))
+        L.bro_hostsim_decode.restype = ctypes.c_int
+        L.bro_hostsim_decode.argtypes = [ctypes.c_char_p, ctypes.c_size_t, ctypes.c_char_p, ctypes.c_size_t,
+                                         ctypes.POINTER(ctypes.c_size_t), ctypes.c_int]
+        _LIBS[asan] = L
+    return _LIBS[asan]
+
+
+def decode(data: bytes, cap: int = 1 << 20, quirks: int = 0):
+    out = ctypes.create_string_buffer(max(cap, 1))
+    n = ctypes.c_size_t()
+    st = lib().bro_hostsim_decode(data, len(data), out, cap, ctypes.byref(n), quirks)
+    return st, out.raw[: n.value]

@@ -1,0 +1,66 @@
+"""The C-ABI library loads on a CPU-only box and exports every symbol include/brotli_b200.h declares
+(no compute calls without a GPU)."""
+import os
+import re
+
+import pytest
+
+from conftest import ROOT
+
+
+def test_library_exports_every_declared_symbol():
+    from brotli_rs_b200 import _lib, build
+    if not os.path.exists(_lib.library_path()):
+        build.build()
+    lib = _lib.load_library()
+    header = open(os.path.join(ROOT, "include", "brotli_b200.h")).read()
+    declared = set(re.findall(r"\b(bro_[a-z_]+)\s*\(", header)) - {"bro_read_cb"}
+    assert declared == set(_lib.ABI_SYMBOLS), declared ^ set(_lib.ABI_SYMBOLS)
+    for sym in declared:
+        assert getattr(lib, sym) is not None
+
+
+def test_status_descriptions_match_reference_strings():
+    """src/lib.rs:331-354, byte-identical (the oracle carries the same table; both restate the reference)."""
+    from brotli_rs_b200 import status_description
+    from oracle import oracle
+    for st in list(range(0, 25)):
+        assert status_description(st) == oracle.description(st)
+    assert status_description(15) == "Enocuntered non-zero bit trailing the stream"
+
+
+def test_product_does_not_import_oracle():
+    """The product path must never route through the oracle or the host simulation."""
+    pkg = os.path.join(ROOT, "brotli_rs_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".h", ".cpp", ".c")) and f != "bro_hostsim.cpp":
+                text = open(os.path.join(dirpath, f), errors="ignore").read()
+                assert "import oracle" not in text and "from oracle" not in text and "liboracle" not in text, f
+                if f.endswith((".cu",)):
+                    assert "BRO_HOSTSIM 1" not in text
+
+
+def test_no_gpu_means_loud_failure():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from brotli_rs_b200 import BatchDecoder, Decompressor
+    with pytest.raises(RuntimeError):
+        BatchDecoder()
+    with pytest.raises(RuntimeError):
+        Decompressor(b"\x06")
+
+
+def test_sharding_balances_bytes():
+    import numpy as np
+    from brotli_rs_b200 import shard_streams
+    rng = np.random.default_rng(0)
+    in_lens = rng.integers(1, 400000, 5200)
+    out_lens = in_lens * rng.integers(1, 60, 5200)
+    for ws in (1, 2, 4, 8):
+        shards = shard_streams(in_lens, out_lens, ws)
+        allidx = np.sort(np.concatenate(shards))
+        assert (allidx == np.arange(5200)).all()
+        tot = np.array([out_lens[s].sum() + in_lens[s].sum() for s in shards], dtype=np.float64)
+        assert tot.max() / tot.mean() < 1.02

@@ -1,0 +1,282 @@
+"""GPU parity tests: the CUDA decoder, called through the C ABI (libbrotli_b200.so), against the oracle.
+
+Bit-exact bar: identical bytes for every valid stream, identical status class for every stream.  Sizes the oracle
+finishes in seconds are compared directly; BASELINE.json's full-size configurations are checked through
+replica-equality (every replica's slot equals replica 0's, and replica 0 equals the oracle)."""
+import os
+
+import numpy as np
+import pytest
+
+import fuzzgen
+from conftest import DATA, FREWSXCV_STATUS, corpus_files, stream_vectors
+from oracle import oracle
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def dec():
+    import torch
+    assert torch.cuda.is_available()
+    from brotli_rs_b200 import BatchDecoder
+    d = BatchDecoder(0)
+    yield d
+    d.close()
+
+
+def oracle_slots(streams, caps):
+    from brotli_rs_b200.batch import pack_streams, slot_offsets
+    in_buf, in_off = pack_streams(streams)
+    out_off = slot_offsets(caps)
+    out, out_len, status = oracle.decode_batch(in_buf, in_off, out_off, nthreads=8)
+    return in_buf, in_off, out_off, out, out_len, status
+
+
+def check_batch(dec, streams, caps, label=""):
+    """Decode on the GPU through bro_batch_decode_host and compare with the oracle run on the same slots."""
+    in_buf, in_off, out_off, ref, ref_len, ref_st = oracle_slots(streams, caps)
+    out, out_len, status = dec.decode_host(in_buf, in_off, out_off)
+    bad = np.nonzero(status != ref_st)[0]
+    assert len(bad) == 0, (label, "status", [(int(i), int(status[i]), int(ref_st[i]), streams[int(i)][:12].hex()) for i in bad[:5]])
+    ok = np.nonzero(ref_st == 0)[0]
+    assert (out_len[ok] == ref_len[ok]).all(), (label, "length")
+    for i in ok:
+        b, n = int(out_off[i]), int(ref_len[i])
+        if not np.array_equal(out[b: b + n], ref[b: b + n]):
+            k = int(np.nonzero(out[b: b + n] != ref[b: b + n])[0][0])
+            raise AssertionError((label, "bytes", int(i), "first diff at", k, "of", n))
+    return status
+
+
+def test_corpus_exact_slots(dec):
+    """bit-exact on every file in data/ (BASELINE north_star); slots sized exactly to the expected output."""
+    files = corpus_files()
+    streams = [c for _, c, _ in files]
+    want = [oracle.decode(c) for c in streams]
+    st = check_batch(dec, streams, [len(w[1]) for w in want], "corpus")
+    for (name, _, exp), s, w in zip(files, st, want):
+        if exp is None:
+            assert int(s) == FREWSXCV_STATUS[name]
+        else:
+            assert int(s) == 0 and w[1] == exp
+
+
+def test_corpus_expected_files(dec):
+    """independently of the oracle: GPU output equals the reference's expected-output files"""
+    files = [f for f in corpus_files() if f[2] is not None]
+    res = dec.decode_streams([c for _, c, _ in files], [len(e) + 32 for _, _, e in files])
+    for (name, _, exp), (st, out) in zip(files, res):
+        assert st == 0 and out == exp, name
+
+
+def test_stream_vectors(dec):
+    """the reference's tests/lib.rs:4-605 + doc-test, through the batch ABI"""
+    from brotli_rs_b200 import status_description
+    vecs = stream_vectors()
+    res = dec.decode_streams([v[1] for v in vecs], [len(v[2]) + 64 if v[2] is not None else 1 << 17 for v in vecs])
+    for (name, _, exp, err), (st, out) in zip(vecs, res):
+        if err is not None:
+            assert st != 0 and err in status_description(st), name
+        else:
+            assert st == 0 and out == exp, name
+
+
+def test_decompressor_read_struct(dec):
+    """the Read-struct boundary: Decompressor::new(r).read_to_end (src/lib.rs:361-376 doc-test shape)"""
+    from brotli_rs_b200 import BroError, Decompressor
+    for name in ("64x", "alice29.txt", "quickfox_repeated", "empty", "metablock_reset"):
+        with open(os.path.join(DATA, name + ".compressed"), "rb") as f:
+            got = Decompressor(f, decoder=dec).read()
+        assert got == open(os.path.join(DATA, name), "rb").read(), name
+    # chunked reads fill the caller's buffer completely until the end, then return 0 repeatedly
+    r = Decompressor(open(os.path.join(DATA, "alice29.txt.compressed"), "rb").read(), decoder=dec)
+    exp = open(os.path.join(DATA, "alice29.txt"), "rb").read()
+    chunks = []
+    while True:
+        b = bytearray(10007)
+        n = r.readinto(b)
+        if n == 0:
+            break
+        assert n == 10007 or len(b"".join(chunks)) + n == len(exp)
+        chunks.append(bytes(b[:n]))
+    assert b"".join(chunks) == exp and r.readinto(bytearray(8)) == 0
+    # an invalid stream raises with the reference's description (tests/lib.rs:36-53)
+    with pytest.raises(BroError, match="non-zero bit"):
+        Decompressor(bytes([0xa1, 0x03]), decoder=dec).read()
+    # a reader without a shared context creates its own
+    assert Decompressor(bytes([0x06])).read() == b""
+
+
+def test_mutation_fuzz(dec):
+    """stand-in for the reference's AFL workflow: mutated corpus streams, status + bytes vs the oracle, with exact,
+    generous and too-small slots; invalid streams must never write outside their slot"""
+    corpus = [c for _, c, _ in corpus_files()]
+    streams = list(fuzzgen.mutations(corpus, seed=11, count=6000))
+    rng = np.random.default_rng(3)
+    caps = []
+    for s in streams:
+        st, out = oracle.decode(s)
+        r = rng.random()
+        caps.append(len(out) if (st == 0 and r < 0.5) else int(rng.integers(0, len(out) + 100)) if r < 0.7 else len(out) + 4096)
+    status = check_batch(dec, streams, caps, "fuzz")
+    assert len(set(int(s) for s in status)) >= 15
+
+
+def test_slot_guard_bytes(dec):
+    """no stream writes past its slot: sentinel bytes between slots survive"""
+    import torch
+    from brotli_rs_b200.batch import pack_streams
+    corpus = [c for _, c, _ in corpus_files()]
+    streams = list(fuzzgen.mutations(corpus, seed=21, count=1500)) + corpus
+    want = [oracle.decode(s) for s in streams]
+    caps = np.array([len(w[1]) if w[0] == 0 else max(0, len(w[1]) - 3) for w in want], dtype=np.uint64)
+    guard = 24
+    off = np.zeros(len(streams) + 1, dtype=np.uint64)
+    # slots of exact capacity followed by a guard gap: out_off[i+1] is the END of slot i, so give every stream
+    # its own [start, end) by interleaving dummy zero-length streams that own the guard gaps
+    starts = np.cumsum(np.concatenate([[0], caps[:-1] + guard])).astype(np.uint64)
+    in_buf, in_off = pack_streams(streams)
+    d_in = torch.from_numpy(in_buf.copy()).cuda()
+    total = int(starts[-1] + caps[-1] + guard)
+    d_out = torch.full((total,), 0xA5, dtype=torch.uint8, device="cuda")
+    # decode stream by stream ranges using a 2-entry offset table per stream would be slow; instead build a batch
+    # of 2n "streams" where the odd ones are empty inputs with the guard gap as their slot (they fail with EOF and
+    # must write nothing)
+    n = len(streams)
+    in_off2 = np.zeros(2 * n + 1, dtype=np.uint64)
+    out_off2 = np.zeros(2 * n + 1, dtype=np.uint64)
+    for i in range(n):
+        in_off2[2 * i] = in_off[i]
+        in_off2[2 * i + 1] = in_off[i + 1]
+        out_off2[2 * i] = starts[i]
+        out_off2[2 * i + 1] = starts[i] + caps[i]
+    in_off2[2 * n] = in_off[n]
+    out_off2[2 * n] = total
+    d_len, d_st = dec.decode_device(d_in, torch.from_numpy(in_off2.astype(np.int64)).cuda(), d_out,
+                                    torch.from_numpy(out_off2.astype(np.int64)).cuda())
+    torch.cuda.synchronize()
+    out = d_out.cpu().numpy()
+    st = d_st.cpu().numpy()
+    ln = d_len.cpu().numpy()
+    for i in range(n):
+        s, e = int(starts[i]), int(starts[i] + caps[i])
+        assert (out[e: e + guard] == 0xA5).all(), ("guard overwritten after stream", i)
+        assert int(st[2 * i + 1]) == 24 and int(ln[2 * i + 1]) == 0
+        if want[i][0] == 0:
+            assert int(st[2 * i]) == 0 and out[s:e].tobytes() == want[i][1]
+
+
+def test_fresh_streams_all_kinds(dec):
+    """fresh streams from the system libbrotlienc over payload kinds, qualities and window sizes"""
+    enc = fuzzgen.libbrotli_enc()
+    if enc is None:
+        pytest.skip("system libbrotlienc not present")
+    raws, streams = [], []
+    k = 0
+    for kind in ("random", "skewed", "repeat2k", "runs", "words", "small_alpha"):
+        for q, lgwin, size in ((0, 22, 50000), (1, 18, 30000), (2, 16, 100000), (5, 16, 262144), (6, 24, 300000), (9, 10, 20000),
+                               (10, 16, 30000), (11, 22, 60000), (11, 16, 9000), (5, 16, 1), (5, 16, 0), (4, 12, 5000)):
+            raw = fuzzgen.synthetic_raw(kind, 500 + k, size) if size else b""
+            k += 1
+            raws.append(raw)
+            streams.append(fuzzgen.compress(enc, raw, q, lgwin))
+    res = dec.decode_streams(streams, [len(r) for r in raws])
+    for i, ((st, out), raw) in enumerate(zip(res, raws)):
+        assert st == 0 and out == raw, i
+
+
+def test_unaligned_device_buffers(dec):
+    """device API with input and output buffers at odd byte offsets (the bit window and the vector copies must not
+    assume alignment)"""
+    import torch
+    from brotli_rs_b200.batch import pack_streams
+    files = [f for f in corpus_files() if f[2] is not None]
+    streams = [c for _, c, _ in files]
+    exps = [e for _, _, e in files]
+    in_buf, in_off = pack_streams(streams)
+    for shift_in, shift_out in ((1, 3), (2, 5), (3, 7), (5, 1), (7, 13)):
+        d_in = torch.zeros(len(in_buf) + 64, dtype=torch.uint8, device="cuda")
+        d_in[shift_in: shift_in + len(in_buf)] = torch.from_numpy(in_buf.copy()).cuda()
+        caps = np.array([len(e) + 1 for e in exps], dtype=np.uint64)      # odd slot sizes -> odd slot starts
+        out_off = np.concatenate([[0], np.cumsum(caps)]).astype(np.uint64)
+        d_out = torch.zeros(int(out_off[-1]) + 64, dtype=torch.uint8, device="cuda")
+        d_len, d_st = dec.decode_device(d_in[shift_in:], torch.from_numpy(in_off.astype(np.int64)).cuda(), d_out[shift_out:],
+                                        torch.from_numpy(out_off.astype(np.int64)).cuda())
+        torch.cuda.synchronize()
+        out = d_out.cpu().numpy()[shift_out:]
+        assert (d_st.cpu().numpy() == 0).all()
+        for i, e in enumerate(exps):
+            assert out[int(out_off[i]): int(out_off[i]) + len(e)].tobytes() == e, (files[i][0], shift_in, shift_out)
+
+
+def _replica_check(dec, streams_unique, replicas, order_seed, caps_unique):
+    """Full-size check by replica equality: decode `replicas` copies of each unique stream (shuffled), verify
+    replica 0 of each against the oracle and every other replica against replica 0 on the GPU."""
+    import torch
+    from brotli_rs_b200.batch import slot_offsets
+    nu = len(streams_unique)
+    want = [oracle.decode(s) for s in streams_unique]
+    idx = np.tile(np.arange(nu), replicas)
+    np.random.default_rng(order_seed).shuffle(idx)
+    lens = np.array([len(s) for s in streams_unique], dtype=np.uint64)
+    in_off = np.concatenate([[0], np.cumsum(lens[idx])]).astype(np.uint64)
+    ubuf = np.frombuffer(b"".join(streams_unique), dtype=np.uint8)
+    uoff = np.concatenate([[0], np.cumsum(lens)]).astype(np.int64)
+    # gather the replicated input on the GPU
+    d_u = torch.from_numpy(ubuf.copy()).cuda()
+    pieces = [d_u[uoff[j]: uoff[j + 1]] for j in idx]
+    d_in = torch.cat(pieces) if pieces else d_u[:0]
+    out_off = slot_offsets(np.asarray(caps_unique, dtype=np.uint64)[idx])
+    d_out = torch.zeros(int(out_off[-1]), dtype=torch.uint8, device="cuda")
+    d_len, d_st = dec.decode_device(d_in, torch.from_numpy(in_off.astype(np.int64)).cuda(), d_out,
+                                    torch.from_numpy(out_off.astype(np.int64)).cuda())
+    torch.cuda.synchronize()
+    st, ln = d_st.cpu().numpy(), d_len.cpu().numpy()
+    first = {}
+    for pos, j in enumerate(idx):
+        j = int(j)
+        assert int(st[pos]) == want[j][0], (pos, j, int(st[pos]), want[j][0])
+        if want[j][0] != 0:
+            continue
+        assert int(ln[pos]) == len(want[j][1])
+        b = int(out_off[pos])
+        sl = d_out[b: b + len(want[j][1])]
+        if j not in first:
+            first[j] = sl
+            assert sl.cpu().numpy().tobytes() == want[j][1], ("replica 0 of", j)
+        else:
+            assert torch.equal(sl, first[j]), ("replica differs", pos, j)
+    return int(ln[st == 0].sum())
+
+
+def test_config_c2_quickfox_repeated_x10k(dec):
+    """BASELINE config 2: 10,000 copies of data/quickfox_repeated.compressed (58 B -> 176,128 B each)"""
+    s = open(os.path.join(DATA, "quickfox_repeated.compressed"), "rb").read()
+    total = _replica_check(dec, [s], 10000, 0, [176128])
+    assert total == 10000 * 176128
+
+
+def test_config_c3_corpus_x1000(dec):
+    """BASELINE config 3: every data/*compressed* stream x 1000 replicas, shuffled with default_rng(0)"""
+    files = corpus_files()
+    streams = [c for _, c, _ in files]
+    caps = [len(e) if e is not None else 70000 for _, _, e in files]
+    total = _replica_check(dec, streams, 1000, 0, caps)
+    assert total == 1000 * 3094120
+
+
+def test_config_c4_c5_samples(dec):
+    """BASELINE configs 4/5 at a size the oracle finishes in seconds: 64 high-ratio WBITS=16 streams (SURVEY C4
+    recipe), 64 stored streams and 64 skewed-literal streams (C5, C5b), each replicated 16x"""
+    enc = fuzzgen.libbrotli_enc()
+    if enc is None:
+        pytest.skip("system libbrotlienc not present")
+    streams, caps = [], []
+    for i in range(64):
+        for kind, size in (("repeat2k", 262144), ("random", 10000), ("skewed", 10000)):
+            raw = fuzzgen.synthetic_raw(kind, 1000 + i, size)
+            streams.append(fuzzgen.compress(enc, raw, 5, 16))
+            caps.append(len(raw))
+    total = _replica_check(dec, streams, 16, 1, caps)
+    assert total == 16 * 64 * (262144 + 10000 + 10000)
