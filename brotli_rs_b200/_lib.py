@@ -30,7 +30,8 @@ class BroError(RuntimeError):
 
 
 def library_path():
-    return os.path.join(HERE, "lib", "libbrotli_b200.so")
+    # BRO_B200_LIB selects an experimental build of the same library (kernel tuning runs); default = the product build
+    return os.environ.get("BRO_B200_LIB") or os.path.join(HERE, "lib", "libbrotli_b200.so")
 
 
 def load_library():

@@ -35,7 +35,19 @@ def stale():
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build(force=False, verbose=False):
+def build(force=False, verbose=False, defines=(), out=None):
+    """defines/out: build an experimental variant (e.g. defines=["BRO_MIN_BLOCKS=3"], out="libvariant.so")."""
+    global LIB
+    if out is not None:
+        LIB_SAVED, LIB = LIB, os.path.join(LIBDIR, out)
+        try:
+            return _build(True, verbose, defines)
+        finally:
+            LIB = LIB_SAVED
+    return _build(force, verbose, defines)
+
+
+def _build(force, verbose, defines):
     if not force and not stale():
         return LIB
     os.makedirs(LIBDIR, exist_ok=True)
@@ -44,13 +56,14 @@ def build(force=False, verbose=False):
     subprocess.check_call([os.environ.get("CC", "gcc"), "-c", "-fPIC", os.path.join(CSRC, BLOB),
                            "-Wa,-I" + os.path.join(HERE, "data"), "-o", blob_o])
     cmd = [nvcc()] + ARCH + ["-lineinfo", "-O3", "-std=c++17", "-shared", "-Xcompiler", "-fPIC",
-                             "-Xptxas", "-v", "-o", LIB] + [os.path.join(CSRC, s) for s in SOURCES] + [blob_o]
+                             "-Xptxas", "-v", "-o", LIB] + ["-D" + d for d in defines] + \
+          [os.path.join(CSRC, s) for s in SOURCES] + [blob_o]
     res = subprocess.run(cmd, capture_output=True, text=True)
     if verbose or res.returncode != 0:
         sys.stderr.write(res.stdout + res.stderr)
     if res.returncode != 0:
         raise RuntimeError("nvcc failed building libbrotli_b200.so")
-    with open(os.path.join(LIBDIR, "ptxas_info.txt"), "w") as f:
+    with open(os.path.join(LIBDIR, os.path.basename(LIB) + ".ptxas_info.txt"), "w") as f:
         f.write(res.stderr)
     return LIB
 

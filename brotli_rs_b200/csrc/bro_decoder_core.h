@@ -130,7 +130,7 @@ struct BroBits {
     const uint8_t* lo;      // first loadable word address (stream start rounded down to 4)
     const uint8_t* end;     // one past the last byte of the stream
     uint64_t buf;           // bit window, next bit to read = bit 0
-    uint64_t rem;           // real stream bits not yet moved into the window
+    uint32_t rem;           // real stream BYTES not yet moved into the window (a stream is < 4 GiB)
     uint32_t nbits;         // bits in the window (real bits first, then `overrun` padding bits)
     uint32_t overrun;       // padding bits in the window that lie beyond the end of the stream
     uint32_t wi;            // next word of the chunk to hand out
@@ -168,9 +168,9 @@ BRO_FN uint32_t bro_next_word(BroBits& s) {
 #endif
 }
 
-BRO_FN void bro_bits_account(BroBits& s, uint32_t loaded) {
-    if (s.rem >= loaded) s.rem -= loaded;
-    else { s.overrun += loaded - (uint32_t)s.rem; s.rem = 0; }
+BRO_FN void bro_bits_account(BroBits& s, uint32_t loaded_bytes) {
+    if (s.rem >= loaded_bytes) s.rem -= loaded_bytes;
+    else { s.overrun += 8u * (loaded_bytes - s.rem); s.rem = 0; }
 }
 
 // position the window at byte address `a` (start of stream, or after a stored / metadata block)
@@ -182,13 +182,13 @@ BRO_FN void bro_bits_seek(BroBits& s, const uint8_t* a) {
     s.cur = bro_load_word(s, s.chunk + 4u * bro_lane());
     s.nxt = bro_load_word(s, s.chunk + 128 + 4u * bro_lane());
 #endif
-    s.rem = a < s.end ? 8ull * (uint64_t)(s.end - a) : 0ull;
+    s.rem = a < s.end ? (uint32_t)(s.end - a) : 0u;
     s.overrun = 0;
     uint32_t sh = 8u * (uint32_t)(ai & 3u);
     uint32_t w = bro_next_word(s);
     s.buf = (uint64_t)(w >> sh);
     s.nbits = 32u - sh;
-    bro_bits_account(s, s.nbits);
+    bro_bits_account(s, s.nbits >> 3);
 }
 
 BRO_FN void bro_bits_init(BroBits& s, const uint8_t* start, const uint8_t* end) {
@@ -207,7 +207,7 @@ BRO_FN void bro_refill(BroBits& s) {
         uint32_t w = bro_next_word(s);
         s.buf |= (uint64_t)w << s.nbits;
         s.nbits += 32u;
-        bro_bits_account(s, 32u);
+        bro_bits_account(s, 4u);
     }
 }
 
@@ -374,7 +374,7 @@ struct BroDec {
     uint32_t pos;             // bytes produced so far (= count_output, src/lib.rs:385)
     uint32_t window;          // (1 << WBITS) - 16, src/lib.rs:1562
     uint32_t p1, p2;          // literal_buf, src/lib.rs:389
-    uint32_t dist[4];         // distance_buf, src/lib.rs:393; dist[0] is the last distance
+    uint32_t d0, d1, d2, d3;  // distance_buf, src/lib.rs:393; d0 is the last distance
     uint16_t* arena;          // per-warp table arena
     BroScratch* sc;
     const uint8_t* dict;      // 122,784-byte static dictionary image
@@ -383,26 +383,25 @@ struct BroDec {
 
 // The fixed code of NBLTYPES / NTREES (src/lib.rs:126-132, 501-525): 0 -> 1, else 1 + (1 << n) + n extra bits
 // with n read from 3 bits.  Any failed bit read is UnexpectedEOF.
-BRO_FN int bro_read_nbltypes(BroDec& d, uint32_t& v) {
+BRO_FN int bro_read_nbltypes(BroBits& in, uint32_t& v) {
     uint32_t b, n, extra;
-    if (!bro_read_bits(d.in, 1, b)) return BRO_ST_UnexpectedEOF;
+    if (!bro_read_bits(in, 1, b)) return BRO_ST_UnexpectedEOF;
     if (!b) { v = 1; return 0; }
-    if (!bro_read_bits(d.in, 3, n)) return BRO_ST_UnexpectedEOF;
-    if (!bro_read_bits(d.in, n, extra)) return BRO_ST_UnexpectedEOF;
+    if (!bro_read_bits(in, 3, n)) return BRO_ST_UnexpectedEOF;
+    if (!bro_read_bits(in, n, extra)) return BRO_ST_UnexpectedEOF;
     v = 1u + (1u << n) + extra;
     return 0;
 }
 
 // src/lib.rs:597-665
-BRO_COLD int bro_read_simple_code(BroDec& d, uint32_t alphabet, uint16_t* T) {
-    BroScratch& sc = *d.sc;
+BRO_COLD int bro_read_simple_code(BroBits& in, BroScratch& sc, uint32_t alphabet, uint16_t* T) {
     uint32_t bit_width = 0;
     for (uint32_t a = alphabet - 1u; a; a >>= 1) bit_width++;   // 16 - leading_zeros(alphabet-1 as u16), src/lib.rs:598
     uint32_t nsym, s[4];
-    if (!bro_read_bits(d.in, 2, nsym)) return BRO_ST_UnexpectedEOF;
+    if (!bro_read_bits(in, 2, nsym)) return BRO_ST_UnexpectedEOF;
     nsym += 1;
     for (uint32_t i = 0; i < nsym; i++) {
-        if (!bro_read_bits(d.in, bit_width, s[i])) return BRO_ST_UnexpectedEOF;
+        if (!bro_read_bits(in, bit_width, s[i])) return BRO_ST_UnexpectedEOF;
         if (s[i] >= alphabet) return BRO_ST_InvalidSymbol;
     }
     for (uint32_t i = 0; i + 1 < nsym; i++)
@@ -414,7 +413,7 @@ BRO_COLD int bro_read_simple_code(BroDec& d, uint32_t alphabet, uint16_t* T) {
     else if (nsym == 3) { BRO_SWAP(1, 2); L[0] = 1; L[1] = L[2] = 2; }
     else if (nsym == 4) {
         uint32_t tree_select;
-        if (!bro_read_bits(d.in, 1, tree_select)) return BRO_ST_UnexpectedEOF;
+        if (!bro_read_bits(in, 1, tree_select)) return BRO_ST_UnexpectedEOF;
         if (!tree_select) {
             BRO_SWAP(0, 1); BRO_SWAP(2, 3); BRO_SWAP(0, 2); BRO_SWAP(1, 3); BRO_SWAP(1, 2);
             L[0] = L[1] = L[2] = L[3] = 2;
@@ -429,8 +428,7 @@ BRO_COLD int bro_read_simple_code(BroDec& d, uint32_t alphabet, uint16_t* T) {
 }
 
 // src/lib.rs:667-875
-BRO_COLD int bro_read_complex_code(BroDec& d, uint32_t hskip, uint32_t alphabet, uint16_t* T) {
-    BroScratch& sc = *d.sc;
+BRO_COLD int bro_read_complex_code(BroBits& in, BroScratch& sc, uint32_t hskip, uint32_t alphabet, uint16_t* T) {
     const unsigned lane = bro_lane();
     // code lengths of the code-length code, transmitted in the order 1,2,3,4,0,5,17,6,16,7,8,...,15 with the fixed
     // code 00->0 01->3 10->4 110->2 1110->1 1111->5 (src/lib.rs:120-125, 669-704)
@@ -439,15 +437,15 @@ BRO_COLD int bro_read_complex_code(BroDec& d, uint32_t hskip, uint32_t alphabet,
     uint32_t sum = 0, nonzero = 0;
     for (uint32_t i = hskip; i < 18u; i++) {
         uint32_t b, v;
-        if (!bro_read_bits(d.in, 2, b)) return BRO_ST_UnexpectedEOF;
+        if (!bro_read_bits(in, 2, b)) return BRO_ST_UnexpectedEOF;
         if (b == 0u) v = 0;
         else if (b == 2u) v = 3;          // read order 0,1
         else if (b == 1u) v = 4;          // read order 1,0
         else {
-            if (!bro_read_bits(d.in, 1, b)) return BRO_ST_UnexpectedEOF;
+            if (!bro_read_bits(in, 1, b)) return BRO_ST_UnexpectedEOF;
             if (!b) v = 2;
             else {
-                if (!bro_read_bits(d.in, 1, b)) return BRO_ST_UnexpectedEOF;
+                if (!bro_read_bits(in, 1, b)) return BRO_ST_UnexpectedEOF;
                 v = b ? 5 : 1;
             }
         }
@@ -492,11 +490,11 @@ BRO_COLD int bro_read_complex_code(BroDec& d, uint32_t hskip, uint32_t alphabet,
         uint32_t c;
         if (clc_single != 0xffffffffu) c = clc_single;
         else {
-            bro_refill(d.in);
-            uint32_t e = sc.clc[(uint32_t)d.in.buf & 31u];
+            bro_refill(in);
+            uint32_t e = sc.clc[(uint32_t)in.buf & 31u];
             uint32_t len = e >> 5;
-            if (len > bro_avail(d.in)) return BRO_ST_UnexpectedEOF;
-            bro_consume(d.in, len);
+            if (len > bro_avail(in)) return BRO_ST_UnexpectedEOF;
+            bro_consume(in, len);
             c = e & 31u;
         }
         if (c <= 15u) {
@@ -513,7 +511,7 @@ BRO_COLD int bro_read_complex_code(BroDec& d, uint32_t hskip, uint32_t alphabet,
             }
         } else if (c == 16u) {
             uint32_t extra, count, newrep;
-            if (!bro_read_bits(d.in, 2, extra)) return BRO_ST_UnexpectedEOF;
+            if (!bro_read_bits(in, 2, extra)) return BRO_ST_UnexpectedEOF;
             if (last_symbol == 16u && have_repeat) {
                 newrep = 4u * (last_repeat - 2u) + extra + 3u;
                 if (i + newrep - last_repeat > alphabet) return BRO_ST_ParseErrorComplexPrefixCodeLengths;
@@ -534,7 +532,7 @@ BRO_COLD int bro_read_complex_code(BroDec& d, uint32_t hskip, uint32_t alphabet,
             last_symbol = 16;
         } else {
             uint32_t extra;
-            if (!bro_read_bits(d.in, 3, extra)) return BRO_ST_UnexpectedEOF;
+            if (!bro_read_bits(in, 3, extra)) return BRO_ST_UnexpectedEOF;
             if (last_symbol == 17u && have_repeat) {
                 uint32_t newrep = 8u * (last_repeat - 2u) + extra + 3u;
                 i += newrep - last_repeat;
@@ -555,33 +553,42 @@ BRO_COLD int bro_read_complex_code(BroDec& d, uint32_t hskip, uint32_t alphabet,
 }
 
 // src/lib.rs:877-889
-BRO_FN int bro_read_prefix_code(BroDec& d, uint32_t alphabet, uint16_t* T) {
+BRO_COLD int bro_read_prefix_code_cold(BroBits& in, BroScratch& sc, uint32_t alphabet, uint16_t* T) {
     uint32_t kind;
-    if (!bro_read_bits(d.in, 2, kind)) return BRO_ST_UnexpectedEOF;
-    if (kind == 1u) return bro_read_simple_code(d, alphabet, T);
-    return bro_read_complex_code(d, kind, alphabet, T);
+    if (!bro_read_bits(in, 2, kind)) return BRO_ST_UnexpectedEOF;
+    if (kind == 1u) return bro_read_simple_code(in, sc, alphabet, T);
+    return bro_read_complex_code(in, sc, kind, alphabet, T);
+}
+
+// The out-of-line (cold) routines take the bit window by reference.  Callers hand them a COPY and copy it back, so
+// that the hot loops' own window never has its address taken and stays in registers.
+BRO_FN int bro_read_prefix_code(BroBits& in, BroScratch& sc, uint32_t alphabet, uint16_t* T) {
+    BroBits t = in;
+    int st = bro_read_prefix_code_cold(t, sc, alphabet, T);
+    in = t;
+    return st;
 }
 
 // src/lib.rs:957-987
-BRO_FN int bro_read_block_count(BroDec& d, const uint16_t* T, uint32_t& count) {
+BRO_FN int bro_read_block_count(BroBits& in, const uint16_t* T, uint32_t& count) {
     uint32_t sym, extra;
-    int r = bro_decode_sym(d.in, T, sym);
+    int r = bro_decode_sym(in, T, sym);
     if (r != BRO_SYM_OK) return BRO_ST_UnexpectedEOF;          // Ok(None) and Err(_) both map to UnexpectedEOF
     if (sym > 25u) return BRO_ST_InvalidBlockCountCode;
     uint32_t be = bro_block_count[sym];
-    if (!bro_read_bits(d.in, be >> 16, extra)) return BRO_ST_UnexpectedEOF;
+    if (!bro_read_bits(in, be >> 16, extra)) return BRO_ST_UnexpectedEOF;
     count = (be & 0xffffu) + extra;
     return 0;
 }
 
 // src/lib.rs:1226-1250 plus the caller's bookkeeping (e.g. 1296-1302)
-BRO_COLD int bro_block_switch(BroDec& d, BroBlockCat& c, uint32_t cat) {
+BRO_COLD int bro_block_switch_cold(BroBits& in, const uint16_t* arena, BroBlockCat& c, uint32_t cat) {
     uint32_t code, count;
-    int r = bro_decode_sym(d.in, d.arena + BRO_A_BTYPE + cat * BRO_TREE_U16(BRO_ALPHA_BTYPE_MAX), code);
+    int r = bro_decode_sym(in, arena + BRO_A_BTYPE + cat * BRO_TREE_U16(BRO_ALPHA_BTYPE_MAX), code);
     if (r == BRO_SYM_HOLE) return BRO_ST_InvalidBlockSwitchCommandCode;
     if (r == BRO_SYM_EOF) return BRO_ST_UnexpectedEOF;
     uint32_t bt = code == 0u ? c.btype_prev : code == 1u ? (c.btype + 1u) % c.nbl : code - 2u;
-    int st = bro_read_block_count(d, d.arena + BRO_A_BCOUNT + cat * BRO_TREE_U16(BRO_ALPHA_BCOUNT), count);
+    int st = bro_read_block_count(in, arena + BRO_A_BCOUNT + cat * BRO_TREE_U16(BRO_ALPHA_BCOUNT), count);
     if (st) return st;
     c.btype_prev = c.btype;
     c.btype = bt;
@@ -589,28 +596,36 @@ BRO_COLD int bro_block_switch(BroDec& d, BroBlockCat& c, uint32_t cat) {
     return 0;
 }
 
+BRO_FN int bro_block_switch(BroBits& in, const uint16_t* arena, BroBlockCat& c, uint32_t cat) {
+    BroBits t = in;
+    BroBlockCat tc = c;
+    int st = bro_block_switch_cold(t, arena, tc, cat);
+    in = t;
+    c = tc;
+    return st;
+}
+
 // src/lib.rs:1070-1144 and the IMTF of 1164-1177
-BRO_COLD int bro_read_context_map(BroDec& d, uint32_t ntrees, uint32_t len, uint8_t* cmap) {
-    BroScratch& sc = *d.sc;
+BRO_COLD int bro_read_context_map_cold(BroBits& in, BroScratch& sc, uint16_t* arena, uint32_t ntrees, uint32_t len, uint8_t* cmap) {
     const unsigned lane = bro_lane();
     uint32_t b, rlemax = 0;
-    if (!bro_read_bits(d.in, 1, b)) return BRO_ST_UnexpectedEOF;
+    if (!bro_read_bits(in, 1, b)) return BRO_ST_UnexpectedEOF;
     if (b) {
-        if (!bro_read_bits(d.in, 4, rlemax)) return BRO_ST_UnexpectedEOF;
+        if (!bro_read_bits(in, 4, rlemax)) return BRO_ST_UnexpectedEOF;
         rlemax += 1;
     }
-    uint16_t* T = d.arena + BRO_A_CMTREE;
-    int st = bro_read_prefix_code(d, rlemax + ntrees, T);
+    uint16_t* T = arena + BRO_A_CMTREE;
+    int st = bro_read_prefix_code_cold(in, sc, rlemax + ntrees, T);
     if (st) return st;
     uint32_t pushed = 0;
     while (pushed < len) {
         uint32_t s;
-        int r = bro_decode_sym(d.in, T, s);
+        int r = bro_decode_sym(in, T, s);
         if (r == BRO_SYM_EOF) return BRO_ST_UnexpectedEOF;
         if (r == BRO_SYM_HOLE) return BRO_ST_ParseErrorContextMap;
         if (s > 0u && s <= rlemax) {
             uint32_t extra;
-            if (!bro_read_bits(d.in, s, extra)) return BRO_ST_UnexpectedEOF;
+            if (!bro_read_bits(in, s, extra)) return BRO_ST_UnexpectedEOF;
             uint32_t repeat = (1u << s) + extra;
             if (pushed + repeat > len) return BRO_ST_RunLengthExceededSizeOfContextMap;
             for (uint32_t k = lane; k < repeat; k += BRO_W) cmap[pushed + k] = 0;
@@ -620,7 +635,7 @@ BRO_COLD int bro_read_context_map(BroDec& d, uint32_t ntrees, uint32_t len, uint
             pushed += 1;
         }
     }
-    if (!bro_read_bits(d.in, 1, b)) return BRO_ST_UnexpectedEOF;
+    if (!bro_read_bits(in, 1, b)) return BRO_ST_UnexpectedEOF;
     if (b) {
         uint8_t* mtf = sc.lens;   // 256-entry move-to-front list
         bro_syncwarp();
@@ -638,6 +653,13 @@ BRO_COLD int bro_read_context_map(BroDec& d, uint32_t ntrees, uint32_t len, uint
     }
     bro_syncwarp();
     return 0;
+}
+
+BRO_FN int bro_read_context_map(BroBits& in, BroScratch& sc, uint16_t* arena, uint32_t ntrees, uint32_t len, uint8_t* cmap) {
+    BroBits t = in;
+    int st = bro_read_context_map_cold(t, sc, arena, ntrees, len, cmap);
+    in = t;
+    return st;
 }
 
 // ------------------------------------------------------------------------------------------------------
@@ -717,15 +739,14 @@ BRO_FN void bro_lz_copy(uint8_t* out, uint32_t pos, uint32_t dist, uint32_t len)
 
 // Static dictionary word + transform (src/lib.rs:1506-1540, src/transformation/mod.rs:84-209).  Returns the
 // transformed length, or -1 where the reference panics (uppercase_first on a 0x00 byte).
-BRO_COLD int bro_dict_word(BroDec& d, uint32_t copy_len, uint32_t index, uint32_t tid) {
-    BroScratch& sc = *d.sc;
+BRO_COLD int bro_dict_word(BroScratch& sc, const uint8_t* dict, int quirk_spec, uint32_t copy_len, uint32_t index, uint32_t tid) {
     const unsigned lane = bro_lane();
-    const uint8_t* w = d.dict + bro_dict_offsets[copy_len] + index * copy_len;
+    const uint8_t* w = dict + bro_dict_offsets[copy_len] + index * copy_len;
     uint32_t type = bro_xf_type[tid], plen = bro_xf_prefix_len[tid], slen = bro_xf_suffix_len[tid];
     uint32_t from = 0, wl = copy_len;
     if (type >= 3u && type <= 11u) {            // OmitFirstN: base_word[min(N, len-1)..] (Q3) / spec: [min(N,len)..]
         uint32_t n = type - 2u;
-        from = d.quirk_spec ? (n < wl ? n : wl) : (n < wl - 1u ? n : wl - 1u);
+        from = quirk_spec ? (n < wl ? n : wl) : (n < wl - 1u ? n : wl - 1u);
         wl -= from;
     } else if (type >= 12u) {                   // OmitLastN: base_word[..max(N,len)-N]
         uint32_t n = type - 11u;
@@ -740,7 +761,7 @@ BRO_COLD int bro_dict_word(BroDec& d, uint32_t copy_len, uint32_t index, uint32_
     if (type == 1u || type == 2u) {
         // uppercase_first (src/transformation/mod.rs:42-82) / uppercase_all (3-40): a serial UTF-8 walk
         uint32_t c0 = sc.word[plen];
-        if (type == 1u && c0 == 0u && !d.quirk_spec) ret = -1;
+        if (type == 1u && c0 == 0u && !quirk_spec) ret = -1;
         else if (lane == 0) {
             uint8_t* v = sc.word + plen;
             uint32_t i = 0;
@@ -761,7 +782,7 @@ BRO_COLD int bro_dict_word(BroDec& d, uint32_t copy_len, uint32_t index, uint32_
 // ------------------------------------------------------------------------------------------------------
 BRO_FN int bro_step_block(BroDec& d, BroBlockCat& c, uint32_t cat) {   // src/lib.rs:1182-1197 et al.
     if (c.nbl < 2u) return 0;
-    if (c.blen == 0u) return bro_block_switch(d, c, cat);
+    if (c.blen == 0u) return bro_block_switch(d.in, d.arena, c, cat);
     c.blen -= 1u;
     return 0;
 }
@@ -772,13 +793,19 @@ BRO_FN int bro_decode_compressed_metablock(BroDec& d, uint32_t mlen) {
     BroBlockCat cat[3];
     int st;
     // NBLTYPES{L,I,D}, block type / count codes, first block counts (src/lib.rs:1745-1885)
+    BroScratch& sc = *d.sc;
+#pragma unroll
     for (uint32_t k = 0; k < 3u; k++) {
         cat[k].btype = 0; cat[k].btype_prev = 1; cat[k].blen = 0;
-        if ((st = bro_read_nbltypes(d, cat[k].nbl))) return st;
+        if ((st = bro_read_nbltypes(d.in, cat[k].nbl))) return st;
         if (cat[k].nbl >= 2u) {
-            if ((st = bro_read_prefix_code(d, cat[k].nbl + 2u, A + BRO_A_BTYPE + k * BRO_TREE_U16(BRO_ALPHA_BTYPE_MAX)))) return st;
-            if ((st = bro_read_prefix_code(d, BRO_ALPHA_BCOUNT, A + BRO_A_BCOUNT + k * BRO_TREE_U16(BRO_ALPHA_BCOUNT)))) return st;
-            if ((st = bro_read_block_count(d, A + BRO_A_BCOUNT + k * BRO_TREE_U16(BRO_ALPHA_BCOUNT), cat[k].blen))) return st;
+            // the two codes of a category are read by one loop so that the table reader has a single call site here
+            for (uint32_t j = 0; j < 2u; j++) {
+                uint16_t* T = j == 0u ? A + BRO_A_BTYPE + k * BRO_TREE_U16(BRO_ALPHA_BTYPE_MAX)
+                                      : A + BRO_A_BCOUNT + k * BRO_TREE_U16(BRO_ALPHA_BCOUNT);
+                if ((st = bro_read_prefix_code(d.in, sc, j == 0u ? cat[k].nbl + 2u : BRO_ALPHA_BCOUNT, T))) return st;
+            }
+            if ((st = bro_read_block_count(d.in, A + BRO_A_BCOUNT + k * BRO_TREE_U16(BRO_ALPHA_BCOUNT), cat[k].blen))) return st;
         }
     }
     // NPOSTFIX, NDIRECT (src/lib.rs:548-560), context modes (562-573)
@@ -793,21 +820,30 @@ BRO_FN int bro_decode_compressed_metablock(BroDec& d, uint32_t mlen) {
         if (lane == 0) modes[i] = (uint8_t)m;
     }
     // NTREESL + literal context map, NTREESD + distance context map (src/lib.rs:1916-1973)
-    uint32_t ntl, ntd;
     uint8_t* cmap_l = (uint8_t*)(A + BRO_A_CMAP_L);
     uint8_t* cmap_d = (uint8_t*)(A + BRO_A_CMAP_D);
-    if ((st = bro_read_nbltypes(d, ntl))) return st;
-    if (ntl >= 2u) { if ((st = bro_read_context_map(d, ntl, 64u * cat[0].nbl, cmap_l))) return st; }
-    if ((st = bro_read_nbltypes(d, ntd))) return st;
-    if (ntd >= 2u) { if ((st = bro_read_context_map(d, ntd, 4u * cat[2].nbl, cmap_d))) return st; }
-    // prefix codes (src/lib.rs:1016-1068)
-    for (uint32_t i = 0; i < ntl; i++)
-        if ((st = bro_read_prefix_code(d, BRO_ALPHA_LIT, A + BRO_A_LIT + i * BRO_TREE_U16(BRO_ALPHA_LIT)))) return st;
-    for (uint32_t i = 0; i < cat[1].nbl; i++)
-        if ((st = bro_read_prefix_code(d, BRO_ALPHA_CMD, A + BRO_A_CMD + i * BRO_TREE_U16(BRO_ALPHA_CMD)))) return st;
+    uint32_t ntl = 1, ntd = 1;
+    for (uint32_t j = 0; j < 2u; j++) {
+        uint32_t nt;
+        if ((st = bro_read_nbltypes(d.in, nt))) return st;
+        if (nt >= 2u) {
+            if ((st = bro_read_context_map(d.in, sc, A, nt, j == 0u ? 64u * cat[0].nbl : 4u * cat[2].nbl, j == 0u ? cmap_l : cmap_d))) return st;
+        }
+        if (j == 0u) ntl = nt; else ntd = nt;
+    }
+    // prefix codes (src/lib.rs:1016-1068): NTREESL literal codes, NBLTYPESI insert&copy codes, NTREESD distance codes
     const uint32_t dist_alphabet = 16u + ndirect + (48u << npostfix);
-    for (uint32_t i = 0; i < ntd; i++)
-        if ((st = bro_read_prefix_code(d, dist_alphabet, A + BRO_A_DIST + i * BRO_TREE_U16(BRO_ALPHA_DIST_MAX)))) return st;
+    {
+        const uint32_t n_l = ntl, n_i = cat[1].nbl, total = ntl + cat[1].nbl + ntd;
+        for (uint32_t i = 0; i < total; i++) {
+            uint32_t alphabet;
+            uint16_t* T;
+            if (i < n_l) { alphabet = BRO_ALPHA_LIT; T = A + BRO_A_LIT + i * BRO_TREE_U16(BRO_ALPHA_LIT); }
+            else if (i < n_l + n_i) { alphabet = BRO_ALPHA_CMD; T = A + BRO_A_CMD + (i - n_l) * BRO_TREE_U16(BRO_ALPHA_CMD); }
+            else { alphabet = dist_alphabet; T = A + BRO_A_DIST + (i - n_l - n_i) * BRO_TREE_U16(BRO_ALPHA_DIST_MAX); }
+            if ((st = bro_read_prefix_code(d.in, sc, alphabet, T))) return st;
+        }
+    }
     bro_syncwarp();
 
     const uint32_t mb_begin = d.pos;   // meta_block.count_output == d.pos - mb_begin
@@ -866,9 +902,9 @@ BRO_FN int bro_decode_compressed_metablock(BroDec& d, uint32_t mlen) {
         }
         // distance (src/lib.rs:1412-1481)
         uint32_t distance;
-        if (dcode <= 3u) distance = d.dist[dcode];
+        if (dcode <= 3u) distance = dcode == 0u ? d.d0 : dcode == 1u ? d.d1 : dcode == 2u ? d.d2 : d.d3;
         else if (dcode <= 15u) {
-            int32_t basev = (int32_t)(dcode <= 9u ? d.dist[0] : d.dist[1]);
+            int32_t basev = (int32_t)(dcode <= 9u ? d.d0 : d.d1);
             int32_t delta = (int32_t)(((dcode <= 9u ? dcode - 2u : dcode - 8u)) >> 1);
             int64_t v = (int64_t)(uint32_t)basev + ((dcode & 1u) ? (int64_t)delta : -(int64_t)delta);
             if (v <= 0) return BRO_ST_InvalidNonPositiveDistance;
@@ -885,7 +921,7 @@ BRO_FN int bro_decode_compressed_metablock(BroDec& d, uint32_t mlen) {
         }
         uint32_t max_allowed = d.window < d.pos ? d.window : d.pos;
         if (dcode > 0u && distance <= max_allowed) {                                // src/lib.rs:1476-1478
-            d.dist[3] = d.dist[2]; d.dist[2] = d.dist[1]; d.dist[1] = d.dist[0]; d.dist[0] = distance;
+            d.d3 = d.d2; d.d2 = d.d1; d.d1 = d.d0; d.d0 = distance;
         }
         // ---- phase two: materialise the copy ----
         mb_out = d.pos - mb_begin;
@@ -902,7 +938,7 @@ BRO_FN int bro_decode_compressed_metablock(BroDec& d, uint32_t mlen) {
             uint32_t bits = bro_dict_size_bits[copy_len];
             uint32_t index = word_id & ((1u << bits) - 1u), tid = word_id >> bits;
             if (tid > 120u) return BRO_ST_InvalidTransformId;
-            int n = bro_dict_word(d, copy_len, index, tid);
+            int n = bro_dict_word(sc, d.dict, d.quirk_spec, copy_len, index, tid);
             if (n < 0) return BRO_ST_PanicUppercaseZero;
             if (mlen < mb_out + (uint32_t)n) return BRO_ST_ExceededExpectedBytes;  // checked after the transform (Q10)
             if ((uint32_t)n > d.cap - d.pos) return BRO_ST_OutputTooSmall;

@@ -21,7 +21,7 @@ extern "C" int bro_hostsim_decode(const uint8_t* in, size_t in_len, uint8_t* out
     d.cap = cap > BRO_MAX_SLOT ? (uint32_t)BRO_MAX_SLOT : (uint32_t)cap;
     d.pos = 0;
     d.p1 = d.p2 = 0;
-    d.dist[0] = 4; d.dist[1] = 11; d.dist[2] = 15; d.dist[3] = 16;
+    d.d0 = 4; d.d1 = 11; d.d2 = 15; d.d3 = 16;
     d.quirk_spec = quirks;
     bro_bits_init(d.in, in, in + in_len);
     int st = bro_decode_stream(d);

@@ -10,8 +10,12 @@
 #include "bro_decoder_core.h"
 #include "bro_kernels.h"
 
+#ifndef BRO_MIN_BLOCKS
+#define BRO_MIN_BLOCKS 4
+#endif
+
 template <int WARPS>
-__global__ void __launch_bounds__(WARPS * 32) bro_decode_kernel(BroLaunch p) {
+__global__ void __launch_bounds__(WARPS * 32, BRO_MIN_BLOCKS) bro_decode_kernel(BroLaunch p) {
     __shared__ BroScratch scratch[WARPS];
     const unsigned warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
     const unsigned gwarp = blockIdx.x * WARPS + warp;
@@ -31,7 +35,7 @@ __global__ void __launch_bounds__(WARPS * 32) bro_decode_kernel(BroLaunch p) {
         d.cap = cap > BRO_MAX_SLOT ? (uint32_t)BRO_MAX_SLOT : (uint32_t)cap;
         d.pos = 0;
         d.p1 = 0; d.p2 = 0;
-        d.dist[0] = 4; d.dist[1] = 11; d.dist[2] = 15; d.dist[3] = 16;   // src/lib.rs:407-408
+        d.d0 = 4; d.d1 = 11; d.d2 = 15; d.d3 = 16;   // src/lib.rs:407-408
         d.quirk_spec = p.quirk_spec;
         bro_bits_init(d.in, p.in + in_b, p.in + in_e);
         int st = bro_decode_stream(d);

@@ -1,0 +1,105 @@
+// brotli_b200.hpp -- C++ twin of the reference's one public type, brotli::Decompressor<R: Read>
+// (reference src/lib.rs:378-410 `pub struct Decompressor<R: Read>` / `new`, and src/lib.rs:2173-2193 `impl Read`),
+// written above the C ABI of brotli_b200.h.  The reference is Rust; no Rust toolchain exists in the build image, so
+// the host side above the ABI is C++ (header only).  INTEGRATION.md carries the Rust shim a maintainer would add.
+//
+//   std::ifstream f("data/64x.compressed", std::ios::binary);
+//   brotli::Decompressor<brotli::IstreamReader> d{brotli::IstreamReader(f)};
+//   std::vector<uint8_t> out;
+//   d.read_to_end(out);                       // == Decompressor::new(f).read_to_end(&mut out)
+//
+// R is any type with `size_t read(uint8_t* buf, size_t cap)` returning 0 at end of input (std::io::Read::read).
+// Errors surface like the reference's io::Error::new(ErrorKind::InvalidData, description): brotli::Error carries the
+// status (DecompressorError number, src/lib.rs:294-319) and what() is the reference's description string.
+#pragma once
+#include <cstdint>
+#include <istream>
+#include <stdexcept>
+#include <utility>
+#include <vector>
+
+#include "brotli_b200.h"
+
+namespace brotli {
+
+class Error : public std::runtime_error {
+public:
+    explicit Error(int status) : std::runtime_error(bro_status_description(status)), status_(status) {}
+    int status() const { return status_; }
+private:
+    int status_;
+};
+
+// Read adapter over std::istream (File / Cursor in the reference's tests).
+class IstreamReader {
+public:
+    explicit IstreamReader(std::istream& s) : s_(&s) {}
+    size_t read(uint8_t* buf, size_t cap) {
+        s_->read(reinterpret_cast<char*>(buf), static_cast<std::streamsize>(cap));
+        return static_cast<size_t>(s_->gcount());
+    }
+private:
+    std::istream* s_;
+};
+
+// Read adapter over a byte slice (`&[u8]` in the reference's tests).
+class SliceReader {
+public:
+    SliceReader(const uint8_t* p, size_t n) : p_(p), n_(n) {}
+    size_t read(uint8_t* buf, size_t cap) {
+        size_t k = cap < n_ ? cap : n_;
+        for (size_t i = 0; i < k; i++) buf[i] = p_[i];
+        p_ += k; n_ -= k;
+        return k;
+    }
+private:
+    const uint8_t* p_;
+    size_t n_;
+};
+
+template <class R>
+class Decompressor {
+public:
+    // Decompressor::new(r): infallible, performs no I/O (src/lib.rs:398-410).  `ctx` may be shared between readers
+    // used from the same thread; with nullptr the reader creates its own context on the current CUDA device.
+    explicit Decompressor(R r, bro_ctx* ctx = nullptr) : r_(std::move(r)), h_(bro_reader_new(ctx, &trampoline, this)) {
+        if (!h_) throw std::bad_alloc();
+    }
+    Decompressor(const Decompressor&) = delete;
+    Decompressor& operator=(const Decompressor&) = delete;
+    ~Decompressor() { bro_reader_free(h_); }
+
+    // Read::read (src/lib.rs:2174-2192): fills buf while data is available; 0 at end of stream; throws on InvalidData.
+    size_t read(uint8_t* buf, size_t len) {
+        intptr_t n = bro_reader_read(h_, buf, len);
+        if (n < 0) throw Error(static_cast<int>(-n));
+        return static_cast<size_t>(n);
+    }
+
+    // Read::read_to_end, the call shape of every reference test, bench and the CLI (src/main.rs:61).
+    size_t read_to_end(std::vector<uint8_t>& out) {
+        size_t total = 0;
+        uint8_t chunk[1 << 16];
+        for (;;) {
+            size_t n = read(chunk, sizeof(chunk));
+            if (n == 0) return total;
+            out.insert(out.end(), chunk, chunk + n);
+            total += n;
+        }
+    }
+
+    int status() const { return bro_reader_status(h_); }
+
+private:
+    static intptr_t trampoline(void* user, uint8_t* buf, size_t cap) {
+        try {
+            return static_cast<intptr_t>(static_cast<Decompressor*>(user)->r_.read(buf, cap));
+        } catch (...) {
+            return -1;   // an input I/O error ends the stream: the reference folds it into UnexpectedEOF
+        }
+    }
+    R r_;
+    bro_reader* h_;
+};
+
+}  // namespace brotli

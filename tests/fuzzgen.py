@@ -1,7 +1,5 @@
 """Seeded stream generators shared by the CPU and GPU parity tests: mutated corpus streams (the stand-in for the
 reference's AFL workflow, docs/notes_afl.txt) and fresh streams from the system libbrotlienc."""
-import ctypes
-
 import numpy as np
 
 
@@ -35,54 +33,4 @@ def mutations(corpus, seed, count, max_len=70000):
         yield bytes(base[:max_len])
 
 
-def libbrotli_enc():
-    try:
-        enc = ctypes.CDLL("libbrotlienc.so.1")
-    except OSError:
-        return None
-    enc.BrotliEncoderCompress.restype = ctypes.c_int
-    enc.BrotliEncoderCompress.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_size_t, ctypes.c_char_p,
-                                          ctypes.POINTER(ctypes.c_size_t), ctypes.c_char_p]
-    return enc
-
-
-def compress(enc, raw, q, lgwin, mode=0):
-    cap = len(raw) + (len(raw) >> 2) + 1024
-    buf = ctypes.create_string_buffer(cap)
-    n = ctypes.c_size_t(cap)
-    assert enc.BrotliEncoderCompress(q, lgwin, mode, len(raw), bytes(raw), ctypes.byref(n), buf) == 1
-    return buf.raw[: n.value]
-
-
-def synthetic_raw(kind, seed, size):
-    """Raw payloads with different command mixes."""
-    rng = np.random.default_rng(seed)
-    if kind == "random":
-        return rng.integers(0, 256, size, dtype=np.uint8).tobytes()
-    if kind == "skewed":                      # entropy-coded literals, few matches (SURVEY C5b)
-        return np.minimum(255, rng.exponential(40, size)).astype(np.uint8).tobytes()
-    if kind == "repeat2k":                    # SURVEY C4: 2 KiB random block repeated with 4 mutations per repetition
-        block = rng.integers(0, 256, 2048, dtype=np.uint8)
-        reps = max(1, size // 2048)
-        a = np.tile(block, reps)
-        for r in range(reps):
-            idx = rng.integers(0, 2048, 4)
-            a[r * 2048 + idx] = rng.integers(0, 256, 4, dtype=np.uint8)
-        return a.tobytes()
-    if kind == "runs":                        # long runs and short periods (overlapping copies)
-        out = bytearray()
-        while len(out) < size:
-            period = int(rng.integers(1, 70))
-            pat = rng.integers(0, 256, period, dtype=np.uint8).tobytes()
-            out += pat * int(rng.integers(1, 4000 // period + 2))
-        return bytes(out[:size])
-    if kind == "words":                       # dictionary-friendly text
-        words = [b"the ", b"of ", b"and ", b"time", b"number of different ", b"people ", b"information ", b"\n",
-                 b"Government", b" which ", b"because", b"THE ", b"Search", b"http://", b"</div>", b"language"]
-        out = bytearray()
-        while len(out) < size:
-            out += words[int(rng.integers(len(words)))]
-        return bytes(out[:size])
-    if kind == "small_alpha":
-        return bytes(rng.integers(0, 4, size, dtype=np.uint8))
-    raise ValueError(kind)
+from brotli_rs_b200.workloads import compress, libbrotli_enc, synthetic_raw  # noqa: E402,F401

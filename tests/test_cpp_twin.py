@@ -1,0 +1,54 @@
+"""The C++ Decompressor twin (include/brotli_b200.hpp) compiles against the C ABI on a CPU box, and on the GPU box
+decodes the reference's doc-test (src/lib.rs:361-376) and rejects an invalid stream with the reference's message."""
+import os
+import subprocess
+
+import pytest
+
+from conftest import DATA, ROOT
+
+SRC = r'''
+#include <cstdio>
+#include <cstring>
+#include <fstream>
+#include <vector>
+#include "brotli_b200.hpp"
+int main(int argc, char** argv) {
+    std::ifstream f(argv[1], std::ios::binary);
+    brotli::Decompressor<brotli::IstreamReader> d{brotli::IstreamReader(f)};
+    std::vector<uint8_t> out;
+    try { d.read_to_end(out); } catch (const brotli::Error& e) { std::printf("ERR %d %s\n", e.status(), e.what()); return 3; }
+    std::ifstream g(argv[2], std::ios::binary);
+    std::vector<uint8_t> exp((std::istreambuf_iterator<char>(g)), std::istreambuf_iterator<char>());
+    std::printf("%s %zu\n", out == exp ? "EQUAL" : "DIFFERENT", out.size());
+    return out == exp ? 0 : 2;
+}
+'''
+
+
+def _build(tmp):
+    from brotli_rs_b200 import _lib, build
+    if not os.path.exists(_lib.library_path()):
+        build.build()
+    src = os.path.join(tmp, "twin.cpp")
+    exe = os.path.join(tmp, "twin")
+    open(src, "w").write(SRC)
+    libdir = os.path.dirname(_lib.library_path())
+    subprocess.check_call(["g++", "-std=c++17", "-O1", "-I", os.path.join(ROOT, "include"), src, "-o", exe,
+                           "-L" + libdir, "-lbrotli_b200", "-Wl,-rpath," + libdir])
+    return exe
+
+
+def test_cpp_twin_compiles_and_links(tmp_path):
+    assert os.path.exists(_build(str(tmp_path)))
+
+
+@pytest.mark.gpu
+def test_cpp_twin_doctest_and_error(tmp_path):
+    exe = _build(str(tmp_path))
+    r = subprocess.run([exe, os.path.join(DATA, "64x.compressed"), os.path.join(DATA, "64x")], capture_output=True, text=True)
+    assert r.returncode == 0 and r.stdout.startswith("EQUAL 64"), r.stdout + r.stderr
+    r = subprocess.run([exe, os.path.join(DATA, "alice29.txt.compressed"), os.path.join(DATA, "alice29.txt")], capture_output=True, text=True)
+    assert r.returncode == 0 and r.stdout.startswith("EQUAL 152089"), r.stdout + r.stderr
+    r = subprocess.run([exe, os.path.join(DATA, "frewsxcv_06.compressed"), os.path.join(DATA, "64x")], capture_output=True, text=True)
+    assert r.returncode == 3 and "ERR 23 Run length excceeded" in r.stdout, r.stdout + r.stderr
