@@ -13,7 +13,7 @@ PANIC_UPPERCASE_ZERO = 102
 
 # every symbol include/brotli_b200.h declares
 ABI_SYMBOLS = [
-    "bro_ctx_create", "bro_ctx_destroy", "bro_ctx_set_quirks", "bro_ctx_last_cuda_error", "bro_ctx_launch_count",
+    "bro_ctx_create", "bro_ctx_destroy", "bro_ctx_set_quirks", "bro_ctx_set_mode", "bro_ctx_last_cuda_error", "bro_ctx_launch_count",
     "bro_ctx_num_warps", "bro_batch_decode", "bro_batch_decode_host", "bro_status_description",
     "bro_reader_new", "bro_reader_read", "bro_reader_status", "bro_reader_free",
 ]
@@ -52,6 +52,8 @@ def load_library():
     L.bro_ctx_destroy.argtypes = [vp]
     L.bro_ctx_set_quirks.restype = ctypes.c_int
     L.bro_ctx_set_quirks.argtypes = [vp, ctypes.c_int]
+    L.bro_ctx_set_mode.restype = ctypes.c_int
+    L.bro_ctx_set_mode.argtypes = [vp, ctypes.c_int]
     L.bro_ctx_last_cuda_error.restype = ctypes.c_char_p
     L.bro_ctx_last_cuda_error.argtypes = [vp]
     L.bro_ctx_launch_count.restype = u64

@@ -35,7 +35,9 @@ def slot_offsets(capacities, align=16):
 class BatchDecoder:
     """One GPU's decoder context (bro_ctx).  Not thread safe; use one per host thread / CUDA stream."""
 
-    def __init__(self, device=None, quirks=0):
+    MODE_AUTO, MODE_WARP, MODE_THREAD = 0, 1, 2
+
+    def __init__(self, device=None, quirks=0, mode=None):
         import torch
         if not torch.cuda.is_available():
             raise RuntimeError("brotli_rs_b200 needs a CUDA device: the decoder has no CPU path")
@@ -53,6 +55,12 @@ class BatchDecoder:
         self._ctx = h
         if quirks:
             self._lib.bro_ctx_set_quirks(self._ctx, quirks)
+        if mode is not None:
+            self.set_mode(mode)
+
+    def set_mode(self, mode):
+        """MODE_AUTO (default) / MODE_WARP / MODE_THREAD -- see bro_ctx_set_mode in include/brotli_b200.h."""
+        self._check(self._lib.bro_ctx_set_mode(self._ctx, int(mode)))
 
     def close(self):
         if getattr(self, "_ctx", None):

@@ -22,11 +22,18 @@ extern "C" const uint8_t bro_dictionary_blob[];   // csrc/dict_blob.c
 struct bro_ctx {
     int device;
     int num_sms;
-    int grid;                 // persistent CTAs
+    int grid;                 // warp kernel: persistent CTAs
     uint32_t num_warps;
-    uint16_t* d_arena;
+    uint16_t* d_arena;        // warp kernel: worst-case arena per warp
+    int grid_t;               // thread kernel: persistent CTAs
+    uint32_t num_threads;
+    uint16_t* d_arena_t;      // thread kernel: 64 KiB arena per thread
     uint8_t* d_dict;
-    uint32_t* d_counter;
+    uint32_t* d_counter;      // [0] thread-kernel queue head, [1] warp-kernel queue head, [2] retry count
+    uint32_t* d_order; size_t d_order_cap;   // size-class order of the current batch
+    uint32_t* d_order_scratch;               // 512 counters
+    int mode;                 // BRO_MODE_AUTO / WARP / THREAD
+    uint32_t thread_threshold;// AUTO: batches of at least this many streams use the thread kernel
     int quirks;
     uint64_t launches;
     char err[256];
@@ -54,16 +61,28 @@ extern "C" int bro_ctx_create(bro_ctx** out, int device) {
     cudaDeviceProp prop;
     if ((e = cudaGetDeviceProperties(&prop, device)) != cudaSuccess) { free(ctx); return BRO_ST_CudaError; }
     ctx->num_sms = prop.multiProcessorCount;
-    int per_sm = 0;
-    if (bro_kernel_occupancy(&per_sm) != 0 || per_sm < 1) { free(ctx); return BRO_ST_CudaError; }
+    int per_sm = 0, per_sm_t = 0;
+    if (bro_warp_kernel_occupancy(&per_sm) != 0 || per_sm < 1 ||
+        bro_thread_kernel_occupancy(&per_sm_t) != 0 || per_sm_t < 1) { free(ctx); return BRO_ST_CudaError; }
     ctx->grid = ctx->num_sms * per_sm;
-    ctx->num_warps = (uint32_t)ctx->grid * (uint32_t)bro_kernel_warps_per_cta();
-    size_t arena = (size_t)ctx->num_warps * bro_kernel_arena_bytes_per_warp();
+    ctx->num_warps = (uint32_t)ctx->grid * (uint32_t)bro_warp_kernel_warps_per_cta();
+    ctx->grid_t = ctx->num_sms * per_sm_t;
+    ctx->num_threads = (uint32_t)ctx->grid_t * (uint32_t)bro_thread_kernel_block();
+    ctx->mode = BRO_MODE_AUTO;
+    // Measured on B200 (profiles/r01_kernel_variants.md): with its tables and windows in HBM the thread-per-stream
+    // kernel is bound by dependent DRAM-latency chains and loses to the warp kernel on every BASELINE workload except
+    // literal-only streams, so AUTO never selects it; it stays available through bro_ctx_set_mode for experiments.
+    ctx->thread_threshold = 0xffffffffu;
+    const char* env = getenv("BRO_B200_MODE");
+    if (env && !strcmp(env, "warp")) ctx->mode = BRO_MODE_WARP;
+    if (env && !strcmp(env, "thread")) ctx->mode = BRO_MODE_THREAD;
+    size_t arena = (size_t)ctx->num_warps * bro_warp_kernel_arena_bytes();
     if ((e = cudaMalloc(&ctx->d_arena, arena)) != cudaSuccess ||
         (e = cudaMalloc(&ctx->d_dict, BRO_DICT_BYTES)) != cudaSuccess ||
-        (e = cudaMalloc(&ctx->d_counter, sizeof(uint32_t))) != cudaSuccess ||
+        (e = cudaMalloc(&ctx->d_counter, 4 * sizeof(uint32_t))) != cudaSuccess ||
+        (e = cudaMalloc(&ctx->d_order_scratch, 512 * sizeof(uint32_t))) != cudaSuccess ||
         (e = cudaMemcpy(ctx->d_dict, bro_dictionary_blob, BRO_DICT_BYTES, cudaMemcpyHostToDevice)) != cudaSuccess) {
-        cudaFree(ctx->d_arena); cudaFree(ctx->d_dict); cudaFree(ctx->d_counter);
+        cudaFree(ctx->d_arena); cudaFree(ctx->d_arena_t); cudaFree(ctx->d_dict); cudaFree(ctx->d_counter); cudaFree(ctx->d_order_scratch);
         free(ctx);
         return BRO_ST_CudaError;
     }
@@ -74,7 +93,8 @@ extern "C" int bro_ctx_create(bro_ctx** out, int device) {
 extern "C" void bro_ctx_destroy(bro_ctx* ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
-    cudaFree(ctx->d_arena); cudaFree(ctx->d_dict); cudaFree(ctx->d_counter);
+    cudaFree(ctx->d_arena); cudaFree(ctx->d_arena_t); cudaFree(ctx->d_dict); cudaFree(ctx->d_counter);
+    cudaFree(ctx->d_order); cudaFree(ctx->d_order_scratch);
     cudaFree(ctx->d_in); cudaFree(ctx->d_out); cudaFree(ctx->d_meta);
     free(ctx);
 }
@@ -82,6 +102,12 @@ extern "C" void bro_ctx_destroy(bro_ctx* ctx) {
 extern "C" int bro_ctx_set_quirks(bro_ctx* ctx, int quirks) {
     if (!ctx || (quirks != 0 && quirks != 1)) return BRO_ST_InvalidArgument;
     ctx->quirks = quirks;
+    return BRO_ST_OK;
+}
+
+extern "C" int bro_ctx_set_mode(bro_ctx* ctx, int mode) {
+    if (!ctx || mode < BRO_MODE_AUTO || mode > BRO_MODE_THREAD) return BRO_ST_InvalidArgument;
+    ctx->mode = mode;
     return BRO_ST_OK;
 }
 
@@ -96,16 +122,43 @@ extern "C" int bro_batch_decode(bro_ctx* ctx, const uint8_t* d_in, const uint64_
     if (n == 0) return BRO_ST_OK;
     if (!d_in_off || !d_out_off || !d_out_len || !d_status) return BRO_ST_InvalidArgument;
     cudaStream_t s = (cudaStream_t)stream;
-    BRO_CUDA(ctx, cudaMemsetAsync(ctx->d_counter, 0, sizeof(uint32_t), s));
+    BRO_CUDA(ctx, cudaMemsetAsync(ctx->d_counter, 0, 4 * sizeof(uint32_t), s));
     BroLaunch p;
     p.in = d_in; p.in_off = d_in_off; p.out = d_out; p.out_off = d_out_off;
     p.out_len = d_out_len; p.status = d_status; p.n = n;
-    p.arena = ctx->d_arena; p.dict = ctx->d_dict; p.counter = ctx->d_counter; p.quirk_spec = ctx->quirks;
-    int grid = ctx->grid;
-    uint32_t need = (n + (uint32_t)bro_kernel_warps_per_cta() - 1) / (uint32_t)bro_kernel_warps_per_cta();
-    if ((uint32_t)grid > need) grid = (int)need;
-    cudaError_t e = (cudaError_t)bro_kernel_launch(&p, grid, s);
-    if (e != cudaSuccess) return bro_fail(ctx, e, "bro_decode_kernel launch");
+    p.dict = ctx->d_dict; p.quirk_spec = ctx->quirks;
+    p.order = NULL; p.retry_count = ctx->d_counter + 2; p.retry_mode = 0;
+    const uint32_t wpc = (uint32_t)bro_warp_kernel_warps_per_cta();
+    int grid_w = ctx->grid;
+    if ((uint32_t)grid_w > (n + wpc - 1) / wpc) grid_w = (int)((n + wpc - 1) / wpc);
+    const bool use_threads = ctx->mode == BRO_MODE_THREAD || (ctx->mode == BRO_MODE_AUTO && n >= ctx->thread_threshold);
+    cudaError_t e;
+    if (use_threads) {
+        // one THREAD per stream, streams handed out by compressed-size class (largest first); streams whose tables
+        // do not fit a thread arena are left for the warp kernel's retry pass
+        if (!ctx->d_arena_t)   // 64 KiB per resident thread (~5 GB on a B200), allocated on first use
+            BRO_CUDA(ctx, cudaMalloc(&ctx->d_arena_t, (size_t)ctx->num_threads * bro_thread_kernel_arena_bytes()));
+        if (ctx->d_order_cap < n) {
+            if (ctx->d_order) { BRO_CUDA(ctx, cudaFree(ctx->d_order)); ctx->d_order = NULL; ctx->d_order_cap = 0; }
+            size_t want = (size_t)n + (n >> 2) + 1024;
+            BRO_CUDA(ctx, cudaMalloc(&ctx->d_order, want * sizeof(uint32_t)));
+            ctx->d_order_cap = want;
+        }
+        e = (cudaError_t)bro_order_launch(d_in_off, n, ctx->d_order, ctx->d_order_scratch, s);
+        if (e != cudaSuccess) return bro_fail(ctx, e, "bro_order kernels launch");
+        ctx->launches += 3;
+        const uint32_t tb = (uint32_t)bro_thread_kernel_block();
+        int grid_t = ctx->grid_t;
+        if ((uint32_t)grid_t > (n + tb - 1) / tb) grid_t = (int)((n + tb - 1) / tb);
+        p.arena = ctx->d_arena_t; p.counter = ctx->d_counter; p.order = ctx->d_order;
+        e = (cudaError_t)bro_thread_kernel_launch(&p, grid_t, s);
+        if (e != cudaSuccess) return bro_fail(ctx, e, "bro_decode_thread_kernel launch");
+        ctx->launches += 1;
+        p.retry_mode = 1; p.order = NULL;
+    }
+    p.arena = ctx->d_arena; p.counter = ctx->d_counter + 1;
+    e = (cudaError_t)bro_warp_kernel_launch(&p, grid_w, s);
+    if (e != cudaSuccess) return bro_fail(ctx, e, "bro_decode_warp_kernel launch");
     ctx->launches += 1;
     return BRO_ST_OK;
 }

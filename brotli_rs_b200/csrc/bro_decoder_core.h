@@ -9,11 +9,16 @@
 // by the whole warp and handed out by shuffle, prefix tables are built by the 32 lanes together, and all
 // byte movement (LZ77 copies, pattern fills, stored blocks, dictionary words) is lane-parallel.
 //
-// The file compiles in two modes:
-//   * nvcc, sm_100a: BRO_W = 32 lanes, warp intrinsics (the product path, used by bro_kernels.cu);
-//   * BRO_HOSTSIM:   BRO_W = 1 lane, plain C++ -- a host simulation of the very same code used ONLY by the
-//     CPU test-suite (tests/_build/libbro_hostsim.so) to fuzz the decoder logic against the oracle without
-//     a GPU.  It is never linked into libbrotli_b200.so and nothing in the product can reach it.
+// The file compiles in three modes:
+//   * nvcc, sm_100a, default:        BRO_W = 32: ONE WARP PER STREAM.  Every lane carries the same decoder state;
+//     table builds and all byte movement are lane-parallel.  Lowest latency per stream, any arena size: used for
+//     small batches and as the general fallback (bro_kernels.cu: bro_decode_warp_kernel).
+//   * nvcc, sm_100a, BRO_THREAD_MODE: BRO_W = 1: ONE THREAD PER STREAM.  The same code with a 1-lane "warp": 32
+//     streams advance per warp instruction, so the serial entropy decode no longer wastes 31/32 of the issue
+//     slots.  Used for large batches (bro_kernels_thread.cu: bro_decode_thread_kernel).
+//   * BRO_HOSTSIM:                   BRO_W = 1 on the host, plain C++ -- a simulation of the very same code used
+//     ONLY by the CPU test-suite (tests/_build/libbro_hostsim.so) to fuzz the decoder logic against the oracle
+//     without a GPU.  It is never linked into libbrotli_b200.so and nothing in the product can reach it.
 //
 // Results are bit-exact with the reference: same bytes, same error class (status = DecompressorError in enum
 // order, src/lib.rs:294-319), including the reference's quirks.
@@ -24,13 +29,24 @@
 
 #if defined(BRO_HOSTSIM)
 #define BRO_W 1u
+#define BRO_SERIAL 1
 #define BRO_FN static inline
 #define BRO_COLD static
 #define BRO_TABLE_QUAL static const
+#elif defined(BRO_THREAD_MODE)
+#define BRO_W 1u
+#define BRO_SERIAL 1
+#define BRO_FN __device__ __forceinline__
+#define BRO_COLD static __device__ __noinline__
+#define BRO_TABLE_QUAL static __constant__ const
+#else
+#if defined(BRO_GROUP_W)
+#define BRO_W BRO_GROUP_W   /* lanes that cooperate on one stream: 32 (a warp), 16, 8 or 4 (sub-warp groups) */
 #else
 #define BRO_W 32u
+#endif
 #define BRO_FN __device__ __forceinline__
-#define BRO_COLD __device__ __noinline__
+#define BRO_COLD static __device__ __noinline__
 #define BRO_TABLE_QUAL static __constant__ const
 #endif
 #include "bro_tables_generated.h"
@@ -38,12 +54,14 @@
 // ------------------------------------------------------------------------------------------------------
 // warp primitives
 // ------------------------------------------------------------------------------------------------------
-#if defined(BRO_HOSTSIM)
+#if defined(BRO_SERIAL)
 BRO_FN unsigned bro_lane() { return 0; }
 BRO_FN uint32_t bro_shfl(uint32_t v, unsigned) { return v; }
 BRO_FN uint32_t bro_match_any(uint32_t) { return 1u; }
 BRO_FN uint32_t bro_lanemask_lt() { return 0u; }
 BRO_FN void bro_syncwarp() {}
+#endif
+#if defined(BRO_HOSTSIM)
 BRO_FN uint32_t bro_brev(uint32_t x) {
     x = ((x >> 1) & 0x55555555u) | ((x & 0x55555555u) << 1);
     x = ((x >> 2) & 0x33333333u) | ((x & 0x33333333u) << 2);
@@ -56,12 +74,17 @@ BRO_FN uint32_t bro_funnel_r(uint32_t lo, uint32_t hi, unsigned sh) {
     return sh ? (lo >> sh) | (hi << (32 - sh)) : lo;
 }
 #else
-#define BRO_FULL 0xffffffffu
-BRO_FN unsigned bro_lane() { return threadIdx.x & 31u; }
-BRO_FN uint32_t bro_shfl(uint32_t v, unsigned src) { return __shfl_sync(BRO_FULL, v, src); }
-BRO_FN uint32_t bro_match_any(uint32_t v) { return __match_any_sync(BRO_FULL, v); }
-BRO_FN uint32_t bro_lanemask_lt() { uint32_t m; asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m)); return m; }
-BRO_FN void bro_syncwarp() { __syncwarp(); }
+#if !defined(BRO_SERIAL)
+// A "group" is BRO_W consecutive lanes of a warp; all collectives are restricted to the group, so the groups of
+// one warp may diverge from each other freely (independent thread scheduling).
+BRO_FN unsigned bro_lane() { return threadIdx.x & (BRO_W - 1u); }
+BRO_FN unsigned bro_group_shift() { return threadIdx.x & 31u & ~(BRO_W - 1u); }
+BRO_FN uint32_t bro_group_mask() { return (BRO_W == 32u ? 0xffffffffu : ((1u << (BRO_W & 31u)) - 1u)) << bro_group_shift(); }
+BRO_FN uint32_t bro_shfl(uint32_t v, unsigned src) { return __shfl_sync(bro_group_mask(), v, (int)src, (int)BRO_W); }
+BRO_FN uint32_t bro_match_any(uint32_t v) { return __match_any_sync(bro_group_mask(), v) >> bro_group_shift(); }
+BRO_FN uint32_t bro_lanemask_lt() { return (1u << bro_lane()) - 1u; }
+BRO_FN void bro_syncwarp() { __syncwarp(bro_group_mask()); }
+#endif
 BRO_FN uint32_t bro_brev(uint32_t x) { return __brev(x); }
 BRO_FN uint32_t bro_popc(uint32_t x) { return (uint32_t)__popc(x); }
 BRO_FN uint32_t bro_funnel_r(uint32_t lo, uint32_t hi, unsigned sh) { return __funnelshift_r(lo, hi, sh); }
@@ -97,18 +120,14 @@ BRO_FN uint32_t bro_funnel_r(uint32_t lo, uint32_t hi, unsigned sh) { return __f
 #define BRO_ALPHA_BCOUNT 26u
 #define BRO_ALPHA_CMAP_MAX 272u   // 16 + 256
 
-// arena offsets, in uint16 units
-#define BRO_A_CMAP_L 0u                                          // 256*64 bytes
-#define BRO_A_CMAP_D (BRO_A_CMAP_L + 8192u)                      // 256*4 bytes
-#define BRO_A_MODES (BRO_A_CMAP_D + 512u)                        // 256 bytes
-#define BRO_A_BTYPE (BRO_A_MODES + 128u)                         // 3 trees
-#define BRO_A_BCOUNT (BRO_A_BTYPE + 3u * BRO_TREE_U16(BRO_ALPHA_BTYPE_MAX))
-#define BRO_A_CMTREE (BRO_A_BCOUNT + 3u * BRO_TREE_U16(BRO_ALPHA_BCOUNT))
-#define BRO_A_LIT (BRO_A_CMTREE + BRO_TREE_U16(BRO_ALPHA_CMAP_MAX))
-#define BRO_A_CMD (BRO_A_LIT + BRO_MAX_BLTYPES * BRO_TREE_U16(BRO_ALPHA_LIT))
-#define BRO_A_DIST (BRO_A_CMD + BRO_MAX_BLTYPES * BRO_TREE_U16(BRO_ALPHA_CMD))
-#define BRO_ARENA_U16 (BRO_A_DIST + BRO_MAX_BLTYPES * BRO_TREE_U16(BRO_ALPHA_DIST_MAX))
-#define BRO_ARENA_BYTES (2u * BRO_ARENA_U16)
+// Worst-case arena (uint16 units): three block-type + block-count tables, context modes, both context maps, the
+// temporary context-map table, and 256 literal + 256 insert&copy + 256 distance tables.
+#define BRO_ARENA_U16_MAX (3u * (BRO_TREE_U16(BRO_ALPHA_BTYPE_MAX) + BRO_TREE_U16(BRO_ALPHA_BCOUNT)) + 128u + 8192u + 512u + \
+                           BRO_TREE_U16(BRO_ALPHA_CMAP_MAX) + BRO_MAX_BLTYPES * (BRO_TREE_U16(BRO_ALPHA_LIT) + \
+                           BRO_TREE_U16(BRO_ALPHA_CMD) + BRO_TREE_U16(BRO_ALPHA_DIST_MAX)) + 64u)
+// Arena of one THREAD in thread-per-stream mode (64 KiB): enough for e.g. 24 literal + 8 insert&copy + 8 distance
+// tables; larger meta-blocks fall back to the warp kernel.  The thread's BroScratch sits at its start.
+#define BRO_THREAD_ARENA_U16 32768u
 
 // per-warp on-chip scratch (shared memory on the device)
 struct BroScratch {
@@ -133,9 +152,11 @@ struct BroBits {
     uint32_t rem;           // real stream BYTES not yet moved into the window (a stream is < 4 GiB)
     uint32_t nbits;         // bits in the window (real bits first, then `overrun` padding bits)
     uint32_t overrun;       // padding bits in the window that lie beyond the end of the stream
+#if !defined(BRO_SERIAL)
     uint32_t wi;            // next word of the chunk to hand out
     uint32_t cur, nxt;      // this lane's word of the current / next chunk
-};
+#endif
+};                          // (1-lane modes: `chunk` is simply the address of the next word to load)
 
 BRO_FN uint32_t bro_load_word(const BroBits& s, const uint8_t* a) {
 #if defined(BRO_HOSTSIM)
@@ -152,16 +173,16 @@ BRO_FN uint32_t bro_load_word(const BroBits& s, const uint8_t* a) {
 }
 
 BRO_FN uint32_t bro_next_word(BroBits& s) {
-#if defined(BRO_HOSTSIM)
-    uint32_t w = bro_load_word(s, s.chunk + 4u * s.wi);
-    if (++s.wi == 32u) { s.chunk += 128; s.wi = 0; }
+#if defined(BRO_SERIAL)
+    uint32_t w = bro_load_word(s, s.chunk);
+    s.chunk += 4;
     return w;
 #else
     uint32_t w = bro_shfl(s.cur, s.wi);
-    if (++s.wi == 32u) {
+    if (++s.wi == BRO_W) {
         s.cur = s.nxt;
-        s.chunk += 128;
-        s.nxt = bro_load_word(s, s.chunk + 128 + 4u * bro_lane());
+        s.chunk += 4u * BRO_W;
+        s.nxt = bro_load_word(s, s.chunk + 4u * BRO_W + 4u * bro_lane());
         s.wi = 0;
     }
     return w;
@@ -176,11 +197,13 @@ BRO_FN void bro_bits_account(BroBits& s, uint32_t loaded_bytes) {
 // position the window at byte address `a` (start of stream, or after a stored / metadata block)
 BRO_FN void bro_bits_seek(BroBits& s, const uint8_t* a) {
     uintptr_t ai = (uintptr_t)a;
-    s.chunk = (const uint8_t*)(ai & ~(uintptr_t)127);
-    s.wi = (uint32_t)(ai & 127u) >> 2;
-#if !defined(BRO_HOSTSIM)
+#if defined(BRO_SERIAL)
+    s.chunk = (const uint8_t*)(ai & ~(uintptr_t)3);
+#else
+    s.chunk = (const uint8_t*)(ai & ~(uintptr_t)(4u * BRO_W - 1u));
+    s.wi = (uint32_t)(ai & (4u * BRO_W - 1u)) >> 2;
     s.cur = bro_load_word(s, s.chunk + 4u * bro_lane());
-    s.nxt = bro_load_word(s, s.chunk + 128 + 4u * bro_lane());
+    s.nxt = bro_load_word(s, s.chunk + 4u * BRO_W + 4u * bro_lane());
 #endif
     s.rem = a < s.end ? (uint32_t)(s.end - a) : 0u;
     s.overrun = 0;
@@ -235,7 +258,11 @@ BRO_FN bool bro_read_byte_tail(BroBits& s, uint32_t& v) {
 
 // byte address of the next unread bit (valid when byte aligned)
 BRO_FN const uint8_t* bro_bits_addr(const BroBits& s) {
+#if defined(BRO_SERIAL)
+    return s.chunk - (s.nbits >> 3);
+#else
     return s.chunk + 4u * s.wi - (s.nbits >> 3);
+#endif
 }
 
 // ------------------------------------------------------------------------------------------------------
@@ -282,10 +309,7 @@ BRO_FN int bro_decode_sym(BroBits& s, const uint16_t* T, uint32_t& sym) {
 // 8 of the 256 root entries by searching the canonical limits.
 BRO_COLD void bro_build_tree(uint16_t* T, BroScratch& sc, uint32_t n, bool explicit_syms) {
     const unsigned lane = bro_lane();
-    if (lane < 16u) sc.cnt[lane] = 0;
-#if defined(BRO_HOSTSIM)
-    for (unsigned i = 0; i < 16; i++) sc.cnt[i] = 0;
-#endif
+    for (unsigned i = lane; i < 16u; i += BRO_W) sc.cnt[i] = 0;
     bro_syncwarp();
     // pass 1: histogram of lengths (leaders of equal-length groups add the group size)
     for (uint32_t i0 = 0; i0 < n; i0 += BRO_W) {
@@ -365,6 +389,7 @@ struct BroBlockCat {          // src/lib.rs:152-160, one per category (literals,
     uint32_t nbl;
     uint32_t btype, btype_prev;
     uint32_t blen;            // valid when nbl >= 2 (the reference's Option<BLen> is Some exactly then)
+    uint32_t t_type, t_count; // arena offsets of the block-type and block-count code tables
 };
 
 struct BroDec {
@@ -375,7 +400,9 @@ struct BroDec {
     uint32_t window;          // (1 << WBITS) - 16, src/lib.rs:1562
     uint32_t p1, p2;          // literal_buf, src/lib.rs:389
     uint32_t d0, d1, d2, d3;  // distance_buf, src/lib.rs:393; d0 is the last distance
-    uint16_t* arena;          // per-warp table arena
+    uint16_t* arena;          // table arena of this warp / thread (bump-allocated per meta-block)
+    uint32_t arena_cap;       // its capacity in uint16 units
+    uint32_t arena_base;      // first free uint16 (thread mode keeps its scratch below it)
     BroScratch* sc;
     const uint8_t* dict;      // 122,784-byte static dictionary image
     int quirk_spec;
@@ -582,13 +609,13 @@ BRO_FN int bro_read_block_count(BroBits& in, const uint16_t* T, uint32_t& count)
 }
 
 // src/lib.rs:1226-1250 plus the caller's bookkeeping (e.g. 1296-1302)
-BRO_COLD int bro_block_switch_cold(BroBits& in, const uint16_t* arena, BroBlockCat& c, uint32_t cat) {
+BRO_COLD int bro_block_switch_cold(BroBits& in, const uint16_t* arena, BroBlockCat& c) {
     uint32_t code, count;
-    int r = bro_decode_sym(in, arena + BRO_A_BTYPE + cat * BRO_TREE_U16(BRO_ALPHA_BTYPE_MAX), code);
+    int r = bro_decode_sym(in, arena + c.t_type, code);
     if (r == BRO_SYM_HOLE) return BRO_ST_InvalidBlockSwitchCommandCode;
     if (r == BRO_SYM_EOF) return BRO_ST_UnexpectedEOF;
     uint32_t bt = code == 0u ? c.btype_prev : code == 1u ? (c.btype + 1u) % c.nbl : code - 2u;
-    int st = bro_read_block_count(in, arena + BRO_A_BCOUNT + cat * BRO_TREE_U16(BRO_ALPHA_BCOUNT), count);
+    int st = bro_read_block_count(in, arena + c.t_count, count);
     if (st) return st;
     c.btype_prev = c.btype;
     c.btype = bt;
@@ -596,17 +623,17 @@ BRO_COLD int bro_block_switch_cold(BroBits& in, const uint16_t* arena, BroBlockC
     return 0;
 }
 
-BRO_FN int bro_block_switch(BroBits& in, const uint16_t* arena, BroBlockCat& c, uint32_t cat) {
+BRO_FN int bro_block_switch(BroBits& in, const uint16_t* arena, BroBlockCat& c) {
     BroBits t = in;
     BroBlockCat tc = c;
-    int st = bro_block_switch_cold(t, arena, tc, cat);
+    int st = bro_block_switch_cold(t, arena, tc);
     in = t;
     c = tc;
     return st;
 }
 
 // src/lib.rs:1070-1144 and the IMTF of 1164-1177
-BRO_COLD int bro_read_context_map_cold(BroBits& in, BroScratch& sc, uint16_t* arena, uint32_t ntrees, uint32_t len, uint8_t* cmap) {
+BRO_COLD int bro_read_context_map_cold(BroBits& in, BroScratch& sc, uint16_t* T, uint32_t t_cap, uint32_t ntrees, uint32_t len, uint8_t* cmap) {
     const unsigned lane = bro_lane();
     uint32_t b, rlemax = 0;
     if (!bro_read_bits(in, 1, b)) return BRO_ST_UnexpectedEOF;
@@ -614,7 +641,7 @@ BRO_COLD int bro_read_context_map_cold(BroBits& in, BroScratch& sc, uint16_t* ar
         if (!bro_read_bits(in, 4, rlemax)) return BRO_ST_UnexpectedEOF;
         rlemax += 1;
     }
-    uint16_t* T = arena + BRO_A_CMTREE;
+    if (BRO_TREE_U16(rlemax + ntrees) > t_cap) return BRO_ST_ArenaTooSmall;   // temporary table above the arena top
     int st = bro_read_prefix_code_cold(in, sc, rlemax + ntrees, T);
     if (st) return st;
     uint32_t pushed = 0;
@@ -655,9 +682,9 @@ BRO_COLD int bro_read_context_map_cold(BroBits& in, BroScratch& sc, uint16_t* ar
     return 0;
 }
 
-BRO_FN int bro_read_context_map(BroBits& in, BroScratch& sc, uint16_t* arena, uint32_t ntrees, uint32_t len, uint8_t* cmap) {
+BRO_FN int bro_read_context_map(BroBits& in, BroScratch& sc, uint16_t* T, uint32_t t_cap, uint32_t ntrees, uint32_t len, uint8_t* cmap) {
     BroBits t = in;
-    int st = bro_read_context_map_cold(t, sc, arena, ntrees, len, cmap);
+    int st = bro_read_context_map_cold(t, sc, T, t_cap, ntrees, len, cmap);
     in = t;
     return st;
 }
@@ -690,16 +717,32 @@ BRO_FN void bro_copy_far(uint8_t* dst, const uint8_t* src, uint32_t n) {
 #if defined(BRO_HOSTSIM)
     for (uint32_t i = 0; i < n; i++) dst[i] = src[i];
     (void)lane;
+#elif defined(BRO_THREAD_MODE)
+    // one thread: byte head until dst is 16-byte aligned, 16-byte stores, byte tail.  Overlap is fine when
+    // dst - src >= 16 (a vector step only reads bytes this thread wrote in earlier steps).
+    (void)lane;
+    uint32_t head = (uint32_t)((16u - ((uintptr_t)dst & 15u)) & 15u);
+    if (head > n) head = n;
+    for (uint32_t i = 0; i < head; i++) dst[i] = src[i];
+    dst += head; src += head; n -= head;
+    for (uint32_t k = n >> 4; k; k--) {
+        BroV4 v = bro_load16(src);
+        *(uint4*)dst = make_uint4(v.x, v.y, v.z, v.w);
+        dst += 16; src += 16;
+    }
+    n &= 15u;
+    for (uint32_t i = 0; i < n; i++) dst[i] = src[i];
 #else
     uint32_t head = (uint32_t)((16u - ((uintptr_t)dst & 15u)) & 15u);
     if (head > n) head = n;
     if (lane < head) dst[lane] = src[lane];
+    if (BRO_W < 16u && lane + BRO_W < head) dst[lane + BRO_W] = src[lane + BRO_W];
     dst += head; src += head; n -= head;
-    while (n >= 512u) {
+    while (n >= 16u * BRO_W) {
         bro_syncwarp();
         BroV4 v = bro_load16(src + 16u * lane);
         *(uint4*)(dst + 16u * lane) = make_uint4(v.x, v.y, v.z, v.w);
-        dst += 512; src += 512; n -= 512;
+        dst += 16u * BRO_W; src += 16u * BRO_W; n -= 16u * BRO_W;
     }
     bro_syncwarp();
     uint32_t nv = n >> 4;
@@ -709,6 +752,7 @@ BRO_FN void bro_copy_far(uint8_t* dst, const uint8_t* src, uint32_t n) {
     }
     uint32_t done = nv << 4;
     if (done + lane < n) dst[done + lane] = src[done + lane];
+    if (BRO_W < 16u && done + lane + BRO_W < n) dst[done + lane + BRO_W] = src[done + lane + BRO_W];
 #endif
 }
 
@@ -722,17 +766,27 @@ BRO_FN void bro_lz_copy(uint8_t* out, uint32_t pos, uint32_t dist, uint32_t len)
 #if defined(BRO_HOSTSIM)
     for (uint32_t i = 0; i < len; i++) dst[i] = src[i];
     (void)lane;
+#elif defined(BRO_THREAD_MODE)
+    (void)lane;
+    if (len < 16u) { for (uint32_t i = 0; i < len; i++) dst[i] = src[i]; return; }
+    if (dist >= 16u) { bro_copy_far(dst, src, len); return; }
+    // short period: bytes until m*dist >= 16 bytes of the pattern exist, then 16-byte steps from m*dist back
+    uint32_t m = (15u + dist) / dist;
+    uint32_t n0 = (m - 1u) * dist;
+    if (n0 > len) n0 = len;
+    for (uint32_t i = 0; i < n0; i++) dst[i] = src[i];
+    if (len > n0) bro_copy_far(dst + n0, dst + n0 - m * dist, len - n0);
 #else
-    if (len <= 32u) {
+    if (len <= BRO_W) {
         if (lane < len) dst[lane] = src[dist >= len ? lane : lane % dist];
         return;
     }
-    if (dist >= len || dist >= 512u) { bro_copy_far(dst, src, len); return; }
-    // periodic fill: the first (m-1)*dist bytes straight from the pattern, the rest from m*dist >= 512 bytes back
-    uint32_t m = (511u + dist) / dist;
+    if (dist >= len || dist >= 16u * BRO_W) { bro_copy_far(dst, src, len); return; }
+    // periodic fill: the first (m-1)*dist bytes straight from the pattern, the rest from m*dist >= 16*BRO_W bytes back
+    uint32_t m = (16u * BRO_W - 1u + dist) / dist;
     uint32_t n0 = (m - 1u) * dist;
     if (n0 > len) n0 = len;
-    for (uint32_t i = lane; i < n0; i += 32u) dst[i] = src[i % dist];
+    for (uint32_t i = lane; i < n0; i += BRO_W) dst[i] = src[i % dist];
     if (len > n0) bro_copy_far(dst + n0, dst + n0 - m * dist, len - n0);
 #endif
 }
@@ -780,9 +834,9 @@ BRO_COLD int bro_dict_word(BroScratch& sc, const uint8_t* dict, int quirk_spec, 
 // ------------------------------------------------------------------------------------------------------
 // one compressed meta-block: src/lib.rs:1745-2141
 // ------------------------------------------------------------------------------------------------------
-BRO_FN int bro_step_block(BroDec& d, BroBlockCat& c, uint32_t cat) {   // src/lib.rs:1182-1197 et al.
+BRO_FN int bro_step_block(BroDec& d, BroBlockCat& c) {   // src/lib.rs:1182-1197 et al.
     if (c.nbl < 2u) return 0;
-    if (c.blen == 0u) return bro_block_switch(d.in, d.arena, c, cat);
+    if (c.blen == 0u) return bro_block_switch(d.in, d.arena, c);
     c.blen -= 1u;
     return 0;
 }
@@ -792,20 +846,26 @@ BRO_FN int bro_decode_compressed_metablock(BroDec& d, uint32_t mlen) {
     uint16_t* A = d.arena;
     BroBlockCat cat[3];
     int st;
-    // NBLTYPES{L,I,D}, block type / count codes, first block counts (src/lib.rs:1745-1885)
     BroScratch& sc = *d.sc;
+    // The arena is bump-allocated per meta-block from the counts the header announces (uint16 units, 16-byte
+    // granules); a meta-block that does not fit reports ArenaTooSmall and the stream is re-run by the warp kernel,
+    // whose arenas hold the worst case (256 + 256 + 256 tables).
+    uint32_t top = d.arena_base;
+#define BRO_ALLOC(var, n_u16) do { (var) = top; top += ((uint32_t)(n_u16) + 7u) & ~7u; if (top > d.arena_cap) return BRO_ST_ArenaTooSmall; } while (0)
+    // NBLTYPES{L,I,D}, block type / count codes, first block counts (src/lib.rs:1745-1885)
 #pragma unroll
     for (uint32_t k = 0; k < 3u; k++) {
-        cat[k].btype = 0; cat[k].btype_prev = 1; cat[k].blen = 0;
+        cat[k].btype = 0; cat[k].btype_prev = 1; cat[k].blen = 0; cat[k].t_type = 0; cat[k].t_count = 0;
         if ((st = bro_read_nbltypes(d.in, cat[k].nbl))) return st;
         if (cat[k].nbl >= 2u) {
+            BRO_ALLOC(cat[k].t_type, BRO_TREE_U16(cat[k].nbl + 2u));
+            BRO_ALLOC(cat[k].t_count, BRO_TREE_U16(BRO_ALPHA_BCOUNT));
             // the two codes of a category are read by one loop so that the table reader has a single call site here
             for (uint32_t j = 0; j < 2u; j++) {
-                uint16_t* T = j == 0u ? A + BRO_A_BTYPE + k * BRO_TREE_U16(BRO_ALPHA_BTYPE_MAX)
-                                      : A + BRO_A_BCOUNT + k * BRO_TREE_U16(BRO_ALPHA_BCOUNT);
-                if ((st = bro_read_prefix_code(d.in, sc, j == 0u ? cat[k].nbl + 2u : BRO_ALPHA_BCOUNT, T))) return st;
+                if ((st = bro_read_prefix_code(d.in, sc, j == 0u ? cat[k].nbl + 2u : BRO_ALPHA_BCOUNT,
+                                               A + (j == 0u ? cat[k].t_type : cat[k].t_count)))) return st;
             }
-            if ((st = bro_read_block_count(d.in, A + BRO_A_BCOUNT + k * BRO_TREE_U16(BRO_ALPHA_BCOUNT), cat[k].blen))) return st;
+            if ((st = bro_read_block_count(d.in, A + cat[k].t_count, cat[k].blen))) return st;
         }
     }
     // NPOSTFIX, NDIRECT (src/lib.rs:548-560), context modes (562-573)
@@ -813,46 +873,61 @@ BRO_FN int bro_decode_compressed_metablock(BroDec& d, uint32_t mlen) {
     if (!bro_read_bits(d.in, 2, npostfix)) return BRO_ST_UnexpectedEOF;
     if (!bro_read_bits(d.in, 4, ndirect)) return BRO_ST_UnexpectedEOF;
     ndirect <<= npostfix;
-    uint8_t* modes = (uint8_t*)(A + BRO_A_MODES);
+    uint32_t o_modes, o_cmap_l, o_cmap_d;
+    BRO_ALLOC(o_modes, (cat[0].nbl + 1u) >> 1);
+    uint8_t* modes = (uint8_t*)(A + o_modes);
     for (uint32_t i = 0; i < cat[0].nbl; i++) {
         uint32_t m;
         if (!bro_read_bits(d.in, 2, m)) return BRO_ST_UnexpectedEOF;
         if (lane == 0) modes[i] = (uint8_t)m;
     }
     // NTREESL + literal context map, NTREESD + distance context map (src/lib.rs:1916-1973)
-    uint8_t* cmap_l = (uint8_t*)(A + BRO_A_CMAP_L);
-    uint8_t* cmap_d = (uint8_t*)(A + BRO_A_CMAP_D);
+    BRO_ALLOC(o_cmap_l, 32u * cat[0].nbl);
+    BRO_ALLOC(o_cmap_d, 2u * cat[2].nbl);
+    uint8_t* cmap_l = (uint8_t*)(A + o_cmap_l);
+    uint8_t* cmap_d = (uint8_t*)(A + o_cmap_d);
     uint32_t ntl = 1, ntd = 1;
     for (uint32_t j = 0; j < 2u; j++) {
         uint32_t nt;
         if ((st = bro_read_nbltypes(d.in, nt))) return st;
         if (nt >= 2u) {
-            if ((st = bro_read_context_map(d.in, sc, A, nt, j == 0u ? 64u * cat[0].nbl : 4u * cat[2].nbl, j == 0u ? cmap_l : cmap_d))) return st;
+            // the context map's own prefix code is temporary: it lives above the arena top and is dropped afterwards
+            if ((st = bro_read_context_map(d.in, sc, A + top, d.arena_cap - top, nt, j == 0u ? 64u * cat[0].nbl : 4u * cat[2].nbl,
+                                           j == 0u ? cmap_l : cmap_d))) return st;
         }
         if (j == 0u) ntl = nt; else ntd = nt;
     }
     // prefix codes (src/lib.rs:1016-1068): NTREESL literal codes, NBLTYPESI insert&copy codes, NTREESD distance codes
     const uint32_t dist_alphabet = 16u + ndirect + (48u << npostfix);
+    const uint32_t dist_stride = BRO_TREE_U16(dist_alphabet);
+    uint32_t o_lit, o_cmd, o_dist;
+    BRO_ALLOC(o_lit, ntl * BRO_TREE_U16(BRO_ALPHA_LIT));
+    BRO_ALLOC(o_cmd, cat[1].nbl * BRO_TREE_U16(BRO_ALPHA_CMD));
+    BRO_ALLOC(o_dist, ntd * dist_stride);
+#undef BRO_ALLOC
     {
         const uint32_t n_l = ntl, n_i = cat[1].nbl, total = ntl + cat[1].nbl + ntd;
         for (uint32_t i = 0; i < total; i++) {
             uint32_t alphabet;
             uint16_t* T;
-            if (i < n_l) { alphabet = BRO_ALPHA_LIT; T = A + BRO_A_LIT + i * BRO_TREE_U16(BRO_ALPHA_LIT); }
-            else if (i < n_l + n_i) { alphabet = BRO_ALPHA_CMD; T = A + BRO_A_CMD + (i - n_l) * BRO_TREE_U16(BRO_ALPHA_CMD); }
-            else { alphabet = dist_alphabet; T = A + BRO_A_DIST + (i - n_l - n_i) * BRO_TREE_U16(BRO_ALPHA_DIST_MAX); }
+            if (i < n_l) { alphabet = BRO_ALPHA_LIT; T = A + o_lit + i * BRO_TREE_U16(BRO_ALPHA_LIT); }
+            else if (i < n_l + n_i) { alphabet = BRO_ALPHA_CMD; T = A + o_cmd + (i - n_l) * BRO_TREE_U16(BRO_ALPHA_CMD); }
+            else { alphabet = dist_alphabet; T = A + o_dist + (i - n_l - n_i) * dist_stride; }
             if ((st = bro_read_prefix_code(d.in, sc, alphabet, T))) return st;
         }
     }
     bro_syncwarp();
+    const uint16_t* const T_lit = A + o_lit;
+    const uint16_t* const T_cmd = A + o_cmd;
+    const uint16_t* const T_dist = A + o_dist;
 
     const uint32_t mb_begin = d.pos;   // meta_block.count_output == d.pos - mb_begin
     // command loop (src/lib.rs:2003-2141)
     for (;;) {
         // ---- phase one: entropy decode of one insert&copy command ----
         uint32_t sym, extra;
-        if ((st = bro_step_block(d, cat[1], 1))) return st;
-        int r = bro_decode_sym(d.in, A + BRO_A_CMD + cat[1].btype * BRO_TREE_U16(BRO_ALPHA_CMD), sym);
+        if ((st = bro_step_block(d, cat[1]))) return st;
+        int r = bro_decode_sym(d.in, T_cmd + cat[1].btype * BRO_TREE_U16(BRO_ALPHA_CMD), sym);
         if (r == BRO_SYM_HOLE) return BRO_ST_ParseErrorInsertAndCopyLength;
         if (r == BRO_SYM_EOF) return BRO_ST_UnexpectedEOF;
         uint32_t ie = bro_ic_insert[sym], ce = bro_ic_copy[sym];
@@ -867,8 +942,8 @@ BRO_FN int bro_decode_compressed_metablock(BroDec& d, uint32_t mlen) {
         // decode error inside the run wins over a full output slot: keep decoding (without storing) past the end of
         // the slot and report OutputTooSmall only if the whole run decoded.
         for (uint32_t k = 0; k < insert_len; k++) {
-            if ((st = bro_step_block(d, cat[0], 0))) return st;
-            const uint16_t* T = A + BRO_A_LIT;
+            if ((st = bro_step_block(d, cat[0]))) return st;
+            const uint16_t* T = T_lit;
             if (ntl >= 2u) {
                 uint32_t bt = cat[0].btype, mode = modes[bt], cid;
                 if (mode == 0u) cid = d.p1 & 0x3fu;
@@ -890,11 +965,11 @@ BRO_FN int bro_decode_compressed_metablock(BroDec& d, uint32_t mlen) {
         // distance code (src/lib.rs:1367-1410)
         uint32_t dcode = 0;
         if (sym >= 128u) {
-            if ((st = bro_step_block(d, cat[2], 2))) return st;
-            const uint16_t* T = A + BRO_A_DIST;
+            if ((st = bro_step_block(d, cat[2]))) return st;
+            const uint16_t* T = T_dist;
             if (ntd >= 2u) {
                 uint32_t cid = copy_len <= 4u ? copy_len - 2u : 3u;
-                T += (uint32_t)cmap_d[cat[2].btype * 4u + cid] * BRO_TREE_U16(BRO_ALPHA_DIST_MAX);
+                T += (uint32_t)cmap_d[cat[2].btype * 4u + cid] * dist_stride;
             }
             r = bro_decode_sym(d.in, T, dcode);
             if (r == BRO_SYM_HOLE) return BRO_ST_ParseErrorDistanceCode;

@@ -9,13 +9,19 @@
 
 extern "C" const uint8_t bro_dictionary_blob[];
 
-extern "C" int bro_hostsim_decode(const uint8_t* in, size_t in_len, uint8_t* out, size_t cap, size_t* out_len, int quirks) {
+// arena_u16 = 0 selects the worst-case arena of the warp kernel; BRO_THREAD_ARENA_U16 simulates the thread kernel
+// (which may answer BRO_ST_ArenaTooSmall, upon which the product re-runs the stream with the warp kernel).
+extern "C" int bro_hostsim_decode(const uint8_t* in, size_t in_len, uint8_t* out, size_t cap, size_t* out_len, int quirks,
+                                  unsigned arena_u16) {
+    if (arena_u16 == 0) arena_u16 = BRO_ARENA_U16_MAX;
     BroDec d;
     memset(&d, 0, sizeof(d));
     BroScratch* sc = (BroScratch*)calloc(1, sizeof(BroScratch));
-    uint16_t* arena = (uint16_t*)malloc(BRO_ARENA_BYTES);
+    uint16_t* arena = (uint16_t*)malloc(2u * (size_t)arena_u16);
     d.sc = sc;
     d.arena = arena;
+    d.arena_cap = arena_u16;
+    d.arena_base = 0;
     d.dict = bro_dictionary_blob;
     d.out = out;
     d.cap = cap > BRO_MAX_SLOT ? (uint32_t)BRO_MAX_SLOT : (uint32_t)cap;
@@ -31,4 +37,4 @@ extern "C" int bro_hostsim_decode(const uint8_t* in, size_t in_len, uint8_t* out
     return st;
 }
 
-extern "C" unsigned bro_hostsim_arena_bytes() { return BRO_ARENA_BYTES; }
+extern "C" unsigned bro_hostsim_thread_arena_u16() { return BRO_THREAD_ARENA_U16; }

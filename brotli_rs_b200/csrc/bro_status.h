@@ -32,3 +32,4 @@
 #define BRO_ST_CudaError 101           /* a CUDA runtime call failed (host-side entry points only) */
 #define BRO_ST_PanicUppercaseZero 102  /* the reference reaches unreachable!() at src/transformation/mod.rs:78 */
 #define BRO_ST_InvalidArgument 104
+#define BRO_ST_ArenaTooSmall 105      /* internal: meta-block needs more table space than a thread arena; re-run by the warp kernel */

@@ -50,6 +50,14 @@ typedef struct bro_reader bro_reader; /* the Read-struct: one compressed stream,
 int bro_ctx_create(bro_ctx** ctx, int device);
 void bro_ctx_destroy(bro_ctx* ctx);
 int bro_ctx_set_quirks(bro_ctx* ctx, int quirks);
+/* Kernel selection.  WARP: one warp per stream (the production kernel, also the retry pass).  THREAD: one thread per
+ * stream with small table arenas, streams ordered by size class; experimental (DESIGN.md has the measurements).
+ * AUTO (default) currently always selects WARP.  The environment variable BRO_B200_MODE=warp|thread sets the
+ * initial mode. */
+#define BRO_MODE_AUTO 0
+#define BRO_MODE_WARP 1
+#define BRO_MODE_THREAD 2
+int bro_ctx_set_mode(bro_ctx* ctx, int mode);
 const char* bro_ctx_last_cuda_error(const bro_ctx* ctx);
 /* Number of kernel launches issued through this context so far (bench.py's gpu_launches). */
 uint64_t bro_ctx_launch_count(const bro_ctx* ctx);

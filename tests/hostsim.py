@@ -33,13 +33,21 @@ def lib(asan=False):
         L = ctypes.CDLL(_build(asan))
         L.bro_hostsim_decode.restype = ctypes.c_int
         L.bro_hostsim_decode.argtypes = [ctypes.c_char_p, ctypes.c_size_t, ctypes.c_char_p, ctypes.c_size_t,
-                                         ctypes.POINTER(ctypes.c_size_t), ctypes.c_int]
+                                         ctypes.POINTER(ctypes.c_size_t), ctypes.c_int, ctypes.c_uint]
         _LIBS[asan] = L
     return _LIBS[asan]
 
 
-def decode(data: bytes, cap: int = 1 << 20, quirks: int = 0):
+ARENA_TOO_SMALL = 105
+
+
+def decode(data: bytes, cap: int = 1 << 20, quirks: int = 0, arena_u16: int = 0):
+    """arena_u16 = 0: worst-case arena (warp kernel); thread_arena_u16(): the thread kernel's 64 KiB arena."""
     out = ctypes.create_string_buffer(max(cap, 1))
     n = ctypes.c_size_t()
-    st = lib().bro_hostsim_decode(data, len(data), out, cap, ctypes.byref(n), quirks)
+    st = lib().bro_hostsim_decode(data, len(data), out, cap, ctypes.byref(n), quirks, arena_u16)
     return st, out.raw[: n.value]
+
+
+def thread_arena_u16():
+    return lib().bro_hostsim_thread_arena_u16()

@@ -15,12 +15,14 @@ from oracle import oracle
 pytestmark = pytest.mark.gpu
 
 
-@pytest.fixture(scope="module")
-def dec():
+@pytest.fixture(scope="module", params=["warp", "thread"])
+def dec(request):
+    """Every parity test runs against both kernels: warp-per-stream (small batches, retry pass) and
+    thread-per-stream (large batches)."""
     import torch
     assert torch.cuda.is_available()
     from brotli_rs_b200 import BatchDecoder
-    d = BatchDecoder(0)
+    d = BatchDecoder(0, mode=BatchDecoder.MODE_WARP if request.param == "warp" else BatchDecoder.MODE_THREAD)
     yield d
     d.close()
 
@@ -280,3 +282,49 @@ def test_config_c4_c5_samples(dec):
             caps.append(len(raw))
     total = _replica_check(dec, streams, 16, 1, caps)
     assert total == 16 * 64 * (262144 + 10000 + 10000)
+
+
+def test_thread_arena_overflow_is_retried_by_warp_kernel(dec):
+    """streams whose meta-blocks need more table space than a thread's 64 KiB arena (many block types / trees) are
+    finished by the warp kernel's retry pass; the caller never sees the internal ArenaTooSmall status"""
+    enc = fuzzgen.libbrotli_enc()
+    if enc is None:
+        pytest.skip("system libbrotlienc not present")
+    parts = [open(os.path.join(DATA, n), "rb").read() for n in ("alice29.txt", "mapsdatazrh", "lcet10.txt", "random_chunks",
+                                                                "plrabn12.txt", "asyoulik.txt")]
+    rng = np.random.default_rng(0)
+    chunks = []
+    for k in range(200):
+        p = parts[k % len(parts)]
+        o = int(rng.integers(0, max(1, len(p) - 3000)))
+        chunks.append(p[o: o + 3000])
+        chunks.append(bytes(rng.integers(0, 256 >> (k % 7), 2000, dtype=np.uint8)))
+    raw = b"".join(chunks)
+    big = [fuzzgen.compress(enc, raw, q, lg) for q, lg in ((9, 18), (9, 22), (11, 22), (10, 18))]
+    small = [c for _, c, e in corpus_files() if e is not None and len(c) < 60000]
+    streams, raws = [], []
+    for r in range(6):
+        for b in big:
+            streams.append(b); raws.append(raw)
+        for c in small:
+            streams.append(c); raws.append(oracle.decode(c)[1])
+    res = dec.decode_streams(streams, [len(r) for r in raws])
+    for i, ((st, out), r) in enumerate(zip(res, raws)):
+        assert st == 0 and out == r, (i, st)
+
+
+def test_auto_mode_launch_counts():
+    """default mode decodes any batch with ONE launch of the warp kernel; thread mode takes 3 ordering kernels, the
+    thread kernel and the warp kernel's retry pass"""
+    from brotli_rs_b200 import BatchDecoder
+    files = [f for f in corpus_files() if f[2] is not None and len(f[1]) < 2000]
+    streams = [c for _, c, _ in files] * 100
+    exps = [e for _, _, e in files] * 100
+    for mode, want in ((None, 1), (BatchDecoder.MODE_THREAD, 5)):
+        d = BatchDecoder(0, mode=mode)
+        before = d.launch_count
+        res = d.decode_streams(streams, [len(e) for e in exps])
+        assert d.launch_count - before == want
+        for (st, out), e in zip(res, exps):
+            assert st == 0 and out == e
+        d.close()
