@@ -50,6 +50,12 @@
 #define BRO_TABLE_QUAL static __constant__ const
 #endif
 #include "bro_tables_generated.h"
+// the byte-movement routines are real calls in the group modes (one copy of their code, small hot loops)
+#if defined(BRO_SERIAL)
+#define BRO_COPY_FN BRO_FN
+#else
+#define BRO_COPY_FN BRO_COLD
+#endif
 
 // ------------------------------------------------------------------------------------------------------
 // warp primitives
@@ -138,6 +144,11 @@ struct BroScratch {
     int16_t base[16];
     uint8_t clc[32];               // code-length-code table: symbol | len<<5, indexed by 5 stream bits
     uint8_t word[64];              // dictionary word staging (<= 24 + 13 bytes)
+    // on-chip copies of the root tables of the current meta-block's literal / insert&copy / distance code when the
+    // meta-block has exactly one of that kind (true for every stream libbrotli produces at quality <= 9)
+    uint16_t root_lit[256];
+    uint16_t root_cmd[256];
+    uint16_t root_dist[256];
 };
 
 // ------------------------------------------------------------------------------------------------------
@@ -145,18 +156,18 @@ struct BroScratch {
 // compressed bytes 128 B at a time (lane i holds word i) and feeds the window by shuffle.
 // ------------------------------------------------------------------------------------------------------
 struct BroBits {
-    const uint8_t* chunk;   // 128-byte aligned address of the chunk held in `cur`
+    const uint8_t* chunk;   // warp/group modes: aligned address of the chunk held in `cur`; 1-lane modes: next word address
     const uint8_t* lo;      // first loadable word address (stream start rounded down to 4)
     const uint8_t* end;     // one past the last byte of the stream
-    uint64_t buf;           // bit window, next bit to read = bit 0
-    uint32_t rem;           // real stream BYTES not yet moved into the window (a stream is < 4 GiB)
-    uint32_t nbits;         // bits in the window (real bits first, then `overrun` padding bits)
-    uint32_t overrun;       // padding bits in the window that lie beyond the end of the stream
+    uint32_t w0, w1;        // bit window: two consecutive little-endian words of the stream; next bit = bit `bp` of w0
+    uint32_t bp;            // 0..31
+    uint32_t avail;         // real stream bits in the window from `bp` on (the rest of w0/w1 is padding past the end)
+    uint32_t rem;           // real stream BYTES not yet loaded into the window (a stream is < 4 GiB)
 #if !defined(BRO_SERIAL)
     uint32_t wi;            // next word of the chunk to hand out
     uint32_t cur, nxt;      // this lane's word of the current / next chunk
 #endif
-};                          // (1-lane modes: `chunk` is simply the address of the next word to load)
+};
 
 BRO_FN uint32_t bro_load_word(const BroBits& s, const uint8_t* a) {
 #if defined(BRO_HOSTSIM)
@@ -189,11 +200,6 @@ BRO_FN uint32_t bro_next_word(BroBits& s) {
 #endif
 }
 
-BRO_FN void bro_bits_account(BroBits& s, uint32_t loaded_bytes) {
-    if (s.rem >= loaded_bytes) s.rem -= loaded_bytes;
-    else { s.overrun += 8u * (loaded_bytes - s.rem); s.rem = 0; }
-}
-
 // position the window at byte address `a` (start of stream, or after a stored / metadata block)
 BRO_FN void bro_bits_seek(BroBits& s, const uint8_t* a) {
     uintptr_t ai = (uintptr_t)a;
@@ -205,13 +211,15 @@ BRO_FN void bro_bits_seek(BroBits& s, const uint8_t* a) {
     s.cur = bro_load_word(s, s.chunk + 4u * bro_lane());
     s.nxt = bro_load_word(s, s.chunk + 4u * BRO_W + 4u * bro_lane());
 #endif
-    s.rem = a < s.end ? (uint32_t)(s.end - a) : 0u;
-    s.overrun = 0;
-    uint32_t sh = 8u * (uint32_t)(ai & 3u);
-    uint32_t w = bro_next_word(s);
-    s.buf = (uint64_t)(w >> sh);
-    s.nbits = 32u - sh;
-    bro_bits_account(s, s.nbits >> 3);
+    uint32_t left = a < s.end ? (uint32_t)(s.end - a) : 0u;      // real bytes from `a` on
+    uint32_t sh = (uint32_t)(ai & 3u);
+    s.w0 = bro_next_word(s);
+    s.w1 = bro_next_word(s);
+    s.bp = 8u * sh;
+    uint32_t in_window = 8u - sh;                                 // bytes of [a, ...) the two words cover
+    if (in_window > left) in_window = left;
+    s.avail = 8u * in_window;
+    s.rem = left - in_window;
 }
 
 BRO_FN void bro_bits_init(BroBits& s, const uint8_t* start, const uint8_t* end) {
@@ -224,25 +232,30 @@ BRO_FN void bro_bits_init(BroBits& s, const uint8_t* start, const uint8_t* end) 
     bro_bits_seek(s, start);
 }
 
-// after this the window holds > 32 bits, of which (nbits - overrun) are real
+// Protocol: bro_refill() (slides the window so that bp < 32), then bro_peek() / bro_avail(), then bro_consume() of at
+// most 32 bits.  Keeping the slide in ONE place per read keeps the hot loops small (the I-cache is a first-order
+// limit for this kernel).
 BRO_FN void bro_refill(BroBits& s) {
-    if (s.nbits <= 32u) {
-        uint32_t w = bro_next_word(s);
-        s.buf |= (uint64_t)w << s.nbits;
-        s.nbits += 32u;
-        bro_bits_account(s, 4u);
+    if (s.bp >= 32u) {
+        s.bp -= 32u;
+        s.w0 = s.w1;
+        s.w1 = bro_next_word(s);
+        uint32_t got = s.rem < 4u ? s.rem : 4u;
+        s.avail += 8u * got;
+        s.rem -= got;
     }
 }
-
-BRO_FN uint32_t bro_avail(const BroBits& s) { return s.nbits - s.overrun; }
-BRO_FN void bro_consume(BroBits& s, uint32_t n) { s.buf >>= n; s.nbits -= n; }
+// The next 32 stream bits, first bit in bit 0 (after bro_refill the window holds more than 32 bits past `bp`).
+BRO_FN uint32_t bro_peek(const BroBits& s) { return bro_funnel_r(s.w0, s.w1, s.bp); }
+BRO_FN uint32_t bro_avail(const BroBits& s) { return s.avail; }
+BRO_FN void bro_consume(BroBits& s, uint32_t n) { s.bp += n; s.avail -= n; }   // n <= 32, n <= avail
 
 // n <= 25 bits, least significant first (src/bitreader/mod.rs:140-158).  Returns false at end of input, which
 // every caller in the reference maps to UnexpectedEOF.
 BRO_FN bool bro_read_bits(BroBits& s, uint32_t n, uint32_t& v) {
     bro_refill(s);
-    if (n > bro_avail(s)) return false;
-    v = (uint32_t)s.buf & ((1u << n) - 1u);
+    if (n > s.avail) return false;
+    v = bro_peek(s) & ((1u << n) - 1u);
     bro_consume(s, n);
     return true;
 }
@@ -250,8 +263,8 @@ BRO_FN bool bro_read_bits(BroBits& s, uint32_t n, uint32_t& v) {
 // src/bitreader/mod.rs:257-267: the bits up to the next byte boundary (0 if already aligned)
 BRO_FN bool bro_read_byte_tail(BroBits& s, uint32_t& v) {
     bro_refill(s);
-    uint32_t n = bro_avail(s) & 7u;   // real bits left are a whole number of bytes plus the tail
-    v = (uint32_t)s.buf & ((1u << n) - 1u);
+    uint32_t n = s.avail & 7u;   // real bits left in the stream are a whole number of bytes plus the tail
+    v = bro_peek(s) & ((1u << n) - 1u);
     bro_consume(s, n);
     return true;
 }
@@ -259,9 +272,9 @@ BRO_FN bool bro_read_byte_tail(BroBits& s, uint32_t& v) {
 // byte address of the next unread bit (valid when byte aligned)
 BRO_FN const uint8_t* bro_bits_addr(const BroBits& s) {
 #if defined(BRO_SERIAL)
-    return s.chunk - (s.nbits >> 3);
+    return s.chunk - 8 + (s.bp >> 3);
 #else
-    return s.chunk + 4u * s.wi - (s.nbits >> 3);
+    return s.chunk + 4u * s.wi - 8 + (s.bp >> 3);
 #endif
 }
 
@@ -276,10 +289,28 @@ BRO_FN const uint8_t* bro_bits_addr(const BroBits& s) {
 // stops at the first assigned node; it reports Ok(None) only after max_depth+1 bits if no node was hit (SURVEY
 // Q5), and a failed bit read before that is an EOF.  A table hit whose code is longer than the remaining input
 // is therefore EOF, and a hole is EOF unless max_depth+1 real bits remain.
-BRO_FN int bro_decode_sym(BroBits& s, const uint16_t* T, uint32_t& sym) {
+// Codes longer than 8 bits, single-symbol tables and holes: out of line, and it does not touch the window.
+// Returns symbol | length << 16 | BRO_SYM_* << 24.
+BRO_COLD uint32_t bro_sym_slow(const uint16_t* T, uint32_t peek, uint32_t e, uint32_t avail) {
+    if (T[BRO_T_SINGLE]) return (uint32_t)T[BRO_T_SINGLE_SYM];
+    if (e == 1u) {
+        uint32_t x = bro_brev(peek) >> 17;   // next 15 bits, first bit read most significant
+        uint32_t L = 9;
+        while (L <= 15u && x >= T[BRO_T_LIMIT + L]) L++;
+        if (L <= 15u) {
+            if (L > avail) return (uint32_t)BRO_SYM_EOF << 24;
+            uint32_t sym = T[BRO_T_SORTED + (int)(int16_t)T[BRO_T_BASE + L] + (int)(x >> (15u - L))];
+            return sym | (L << 16);
+        }
+    }
+    return (uint32_t)((avail >= (uint32_t)T[BRO_T_MAXDEPTH] + 1u) ? BRO_SYM_HOLE : BRO_SYM_EOF) << 24;
+}
+
+// `root` is the 256-entry root table of T: T itself (HBM, L1-cached) or its on-chip copy in the scratch.
+BRO_FN int bro_decode_sym2(BroBits& s, const uint16_t* root, const uint16_t* T, uint32_t& sym) {
     bro_refill(s);
-    uint32_t peek = (uint32_t)s.buf;
-    uint32_t e = T[peek & 0xffu];
+    uint32_t peek = bro_peek(s);
+    uint32_t e = root[peek & 0xffu];
     uint32_t len = e >> 10;
     if (len != 0u) {
         if (len > bro_avail(s)) return BRO_SYM_EOF;
@@ -287,20 +318,13 @@ BRO_FN int bro_decode_sym(BroBits& s, const uint16_t* T, uint32_t& sym) {
         sym = e & 0x3ffu;
         return BRO_SYM_OK;
     }
-    if (T[BRO_T_SINGLE]) { sym = T[BRO_T_SINGLE_SYM]; return BRO_SYM_OK; }
-    if (e == 1u) {
-        uint32_t x = bro_brev(peek) >> 17;   // next 15 bits, first bit read most significant
-        for (uint32_t L = 9; L <= 15u; L++) {
-            if (x < T[BRO_T_LIMIT + L]) {
-                if (L > bro_avail(s)) return BRO_SYM_EOF;
-                sym = T[BRO_T_SORTED + (int)(int16_t)T[BRO_T_BASE + L] + (int)(x >> (15u - L))];
-                bro_consume(s, L);
-                return BRO_SYM_OK;
-            }
-        }
-    }
-    return (bro_avail(s) >= (uint32_t)T[BRO_T_MAXDEPTH] + 1u) ? BRO_SYM_HOLE : BRO_SYM_EOF;
+    uint32_t r = bro_sym_slow(T, peek, e, bro_avail(s));
+    bro_consume(s, (r >> 16) & 0xffu);
+    sym = r & 0xffffu;
+    return (int)(r >> 24);
 }
+
+BRO_FN int bro_decode_sym(BroBits& s, const uint16_t* T, uint32_t& sym) { return bro_decode_sym2(s, T, T, sym); }
 
 // Build a tree record from n (length, symbol) pairs in sc.lens[] (and sc.syms[] when `explicit_syms`), in
 // the order the reference inserts them: src/huffman/mod.rs:19-43 assigns canonical codes per length in array
@@ -518,7 +542,7 @@ BRO_COLD int bro_read_complex_code(BroBits& in, BroScratch& sc, uint32_t hskip, 
         if (clc_single != 0xffffffffu) c = clc_single;
         else {
             bro_refill(in);
-            uint32_t e = sc.clc[(uint32_t)in.buf & 31u];
+            uint32_t e = sc.clc[bro_peek(in) & 31u];
             uint32_t len = e >> 5;
             if (len > bro_avail(in)) return BRO_ST_UnexpectedEOF;
             bro_consume(in, len);
@@ -712,7 +736,7 @@ BRO_FN BroV4 bro_load16(const uint8_t* p) {
 
 // dst[0..n) = src[0..n) where the regions do not overlap, or dst - src >= 16*BRO_W (so that one warp step never
 // reads a byte written in the same step).  dst is advanced in 16-byte aligned vector stores.
-BRO_FN void bro_copy_far(uint8_t* dst, const uint8_t* src, uint32_t n) {
+BRO_COPY_FN void bro_copy_far(uint8_t* dst, const uint8_t* src, uint32_t n) {
     const unsigned lane = bro_lane();
 #if defined(BRO_HOSTSIM)
     for (uint32_t i = 0; i < n; i++) dst[i] = src[i];
@@ -758,7 +782,7 @@ BRO_FN void bro_copy_far(uint8_t* dst, const uint8_t* src, uint32_t n) {
 
 // LZ77 backward copy inside the output slot: out[pos .. pos+len) = bytes `dist` back, periodic when dist < len
 // (src/lib.rs:1491-1505; the ring-buffer window of src/ringbuffer/mod.rs is the linear output itself).
-BRO_FN void bro_lz_copy(uint8_t* out, uint32_t pos, uint32_t dist, uint32_t len) {
+BRO_COPY_FN void bro_lz_copy(uint8_t* out, uint32_t pos, uint32_t dist, uint32_t len) {
     const unsigned lane = bro_lane();
     bro_syncwarp();
     uint8_t* dst = out + pos;
@@ -829,6 +853,180 @@ BRO_COLD int bro_dict_word(BroScratch& sc, const uint8_t* dict, int quirk_spec, 
         bro_syncwarp();
     }
     return ret;
+}
+
+// "Phase two" of a command: materialise the copy -- an LZ77 back-reference into the output produced so far, or a
+// static dictionary word with its transform (src/lib.rs:1483-1542 and 2102-2124).  track_ctx: refresh the literal
+// context bytes p1/p2 from the output (not needed while a meta-block has no context modelling).
+BRO_FN int bro_emit_copy(BroDec& d, BroScratch& sc, uint32_t mlen, uint32_t mb_begin, uint32_t distance, uint32_t max_allowed,
+                         uint32_t copy_len, bool track_ctx) {
+    const unsigned lane = bro_lane();
+    uint32_t mb_out = d.pos - mb_begin;
+    if (distance <= max_allowed) {
+        if (mlen < mb_out + copy_len) return BRO_ST_ExceededExpectedBytes;     // src/lib.rs:2105-2108
+        if (copy_len > d.cap - d.pos) return BRO_ST_OutputTooSmall;
+        bro_lz_copy(d.out, d.pos, distance, copy_len);
+        d.pos += copy_len;
+        if (track_ctx) {
+            bro_syncwarp();
+            d.p1 = d.out[d.pos - 1]; d.p2 = d.out[d.pos - 2];                    // copy_len >= 2
+        }
+    } else {
+        if (copy_len < 4u || copy_len > 24u) return BRO_ST_InvalidLengthInStaticDictionary;
+        uint32_t word_id = distance - max_allowed - 1u;
+        uint32_t bits = bro_dict_size_bits[copy_len];
+        uint32_t index = word_id & ((1u << bits) - 1u), tid = word_id >> bits;
+        if (tid > 120u) return BRO_ST_InvalidTransformId;
+        int n = bro_dict_word(sc, d.dict, d.quirk_spec, copy_len, index, tid);
+        if (n < 0) return BRO_ST_PanicUppercaseZero;
+        if (mlen < mb_out + (uint32_t)n) return BRO_ST_ExceededExpectedBytes;  // checked after the transform (Q10)
+        if ((uint32_t)n > d.cap - d.pos) return BRO_ST_OutputTooSmall;
+        for (uint32_t i = lane; i < (uint32_t)n; i += BRO_W) d.out[d.pos + i] = sc.word[i];
+        if (n >= 2) { d.p1 = sc.word[n - 1]; d.p2 = sc.word[n - 2]; }
+        else if (n == 1) { d.p2 = d.p1; d.p1 = sc.word[0]; }
+        d.pos += (uint32_t)n;
+        bro_syncwarp();
+    }
+    return 0;
+}
+
+// src/lib.rs:1412-1481: distance from the distance code (ring-buffer codes 0-15, direct codes, or extra bits), and
+// the ring-buffer update rule.  Returns 0 or a status.
+BRO_FN int bro_resolve_distance(BroDec& d, uint32_t dcode, uint32_t npostfix, uint32_t ndirect, uint32_t& distance,
+                                uint32_t& max_allowed) {
+    if (dcode <= 3u) distance = dcode == 0u ? d.d0 : dcode == 1u ? d.d1 : dcode == 2u ? d.d2 : d.d3;
+    else if (dcode <= 15u) {
+        int32_t basev = (int32_t)(dcode <= 9u ? d.d0 : d.d1);
+        int32_t delta = (int32_t)(((dcode <= 9u ? dcode - 2u : dcode - 8u)) >> 1);
+        int64_t v = (int64_t)(uint32_t)basev + ((dcode & 1u) ? (int64_t)delta : -(int64_t)delta);
+        if (v <= 0) return BRO_ST_InvalidNonPositiveDistance;
+        distance = (uint32_t)v;
+    } else if (dcode <= 15u + ndirect) distance = dcode - 15u;
+    else {
+        uint32_t t = dcode - ndirect - 16u;
+        uint32_t ndistbits = 1u + (t >> (npostfix + 1u));
+        uint32_t dextra;
+        if (!bro_read_bits(d.in, ndistbits, dextra)) return BRO_ST_UnexpectedEOF;
+        uint32_t hcode = t >> npostfix, lcode = t & ((1u << npostfix) - 1u);
+        uint32_t offset = ((2u + (hcode & 1u)) << ndistbits) - 4u;
+        distance = ((offset + dextra) << npostfix) + lcode + ndirect + 1u;
+    }
+    max_allowed = d.window < d.pos ? d.window : d.pos;
+    if (dcode > 0u && distance <= max_allowed) {                                // src/lib.rs:1476-1478
+        d.d3 = d.d2; d.d2 = d.d1; d.d1 = d.d0; d.d0 = distance;
+    }
+    return 0;
+}
+
+// Reference to a 256-entry root table held on chip (shared memory in the group modes): a 32-bit shared-window
+// address, so that a lookup is one add and one LDS and the base lives in ONE register for the whole loop.
+#if defined(BRO_SERIAL)
+typedef const uint16_t* BroRoot;
+BRO_FN BroRoot bro_root_ref(const uint16_t* p) { return p; }
+BRO_FN uint32_t bro_root_get(BroRoot r, uint32_t idx) { return r[idx]; }
+#else
+typedef uint32_t BroRoot;
+BRO_FN BroRoot bro_root_ref(const uint16_t* p) {
+    uint32_t a = (uint32_t)__cvta_generic_to_shared(p);
+    asm volatile("" : "+r"(a) :: "memory");    // opaque: keep it in a register instead of recomputing it per symbol
+    return a;
+}
+BRO_FN uint32_t bro_root_get(BroRoot r, uint32_t idx) {
+    uint16_t v;
+    asm("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(r + 2u * idx));
+    return v;
+}
+#endif
+
+// One symbol through an on-chip root table.  No end-of-input test on the fast path: the window's `avail` simply goes
+// negative, which is sticky (nothing real is ever loaded again), and the callers test it at their checkpoints --
+// before any decision that could turn garbage bits into a different error, and before any copy is materialised.
+// Returns BRO_SYM_OK or, from the slow path, BRO_SYM_EOF / BRO_SYM_HOLE.
+BRO_FN int bro_decode_sym_onchip(BroBits& s, BroRoot root, const uint16_t* T, uint32_t& sym) {
+    bro_refill(s);
+    uint32_t peek = bro_peek(s);
+    uint32_t e = bro_root_get(root, peek & 0xffu);
+    uint32_t len = e >> 10;
+    if (len != 0u) {
+        bro_consume(s, len);
+        sym = e & 0x3ffu;
+        return BRO_SYM_OK;
+    }
+    uint32_t r = bro_sym_slow(T, peek, e, (int32_t)s.avail < 0 ? 0u : s.avail);
+    bro_consume(s, (r >> 16) & 0xffu);
+    sym = r & 0xffffu;
+    return (int)(r >> 24);
+}
+
+// The command loop of a "simple" meta-block: one literal, one insert&copy and one distance code, no block
+// switches -- i.e. no context modelling, which is every meta-block libbrotli emits at quality <= 9 and the case
+// BASELINE's high-ratio workload consists of.  Same results as the general loop below (src/lib.rs:2003-2141), but the
+// three root tables are on chip, literals are not tracked as context, and end-of-input is tested at checkpoints.
+BRO_FN int bro_commands_simple(BroDec& d, BroScratch& sc, uint32_t mlen, uint32_t npostfix, uint32_t ndirect,
+                               const uint16_t* T_lit, const uint16_t* T_cmd, const uint16_t* T_dist) {
+    const unsigned lane = bro_lane();
+    const uint32_t mb_begin = d.pos;
+    const BroRoot r_lit = bro_root_ref(sc.root_lit), r_cmd = bro_root_ref(sc.root_cmd), r_dist = bro_root_ref(sc.root_dist);
+    int st = 0;
+    for (;;) {
+        // ---- phase one: entropy decode of one insert&copy command ----
+        uint32_t sym, v;
+        int r = bro_decode_sym_onchip(d.in, r_cmd, T_cmd, sym);
+        if (r != BRO_SYM_OK) { st = r == BRO_SYM_HOLE ? BRO_ST_ParseErrorInsertAndCopyLength : BRO_ST_UnexpectedEOF; break; }
+        const uint32_t ie = bro_ic_insert[sym], ce = bro_ic_copy[sym];
+        uint32_t insert_len = ie & 0xffffu, copy_len = ce & 0xffffu;
+        if (!bro_read_bits(d.in, ie >> 16, v)) { st = BRO_ST_UnexpectedEOF; break; }     // insert extra bits first
+        insert_len += v;
+        if (!bro_read_bits(d.in, ce >> 16, v)) { st = BRO_ST_UnexpectedEOF; break; }
+        copy_len += v;
+        if ((int32_t)d.in.avail < 0) { st = BRO_ST_UnexpectedEOF; break; }                // checkpoint
+        if (mlen < (d.pos - mb_begin) + insert_len) { st = BRO_ST_ExceededExpectedBytes; break; }   // src/lib.rs:2036-2039
+        // literals: lane k%W keeps literal k, the group stores W literals with one coalesced store.  A run that does
+        // not fit the slot is still decoded (a decode error wins over OutputTooSmall, as in the general loop).
+        const bool fits = insert_len <= d.cap - d.pos;
+        uint8_t* o = d.out + d.pos;
+        uint32_t mine = 0, k = 0;
+        while (k < insert_len) {
+            uint32_t lit;
+            r = bro_decode_sym_onchip(d.in, r_lit, T_lit, lit);
+            if (r != BRO_SYM_OK) { st = r == BRO_SYM_HOLE ? BRO_ST_ParseErrorInsertLiterals : BRO_ST_UnexpectedEOF; break; }
+            if (lane == (k & (BRO_W - 1u))) mine = lit;
+            k++;
+            if ((k & (BRO_W - 1u)) == 0u && fits) o[k - BRO_W + lane] = (uint8_t)mine;
+        }
+        if (st) break;
+        if ((int32_t)d.in.avail < 0) { st = BRO_ST_UnexpectedEOF; break; }                // checkpoint
+        if (!fits) { d.pos = d.cap; st = BRO_ST_OutputTooSmall; break; }
+        {
+            uint32_t tail = k & (BRO_W - 1u);
+            if (lane < tail) o[k - tail + lane] = (uint8_t)mine;
+        }
+        d.pos += insert_len;
+        if (d.pos - mb_begin == mlen) break;                                              // src/lib.rs:2069-2070
+        // distance code (src/lib.rs:1367-1410) and distance (1412-1481)
+        uint32_t dcode = 0;
+        if (sym >= 128u) {
+            r = bro_decode_sym_onchip(d.in, r_dist, T_dist, dcode);
+            if (r != BRO_SYM_OK) { st = r == BRO_SYM_HOLE ? BRO_ST_ParseErrorDistanceCode : BRO_ST_UnexpectedEOF; break; }
+        }
+        uint32_t distance, max_allowed;
+        if ((st = bro_resolve_distance(d, dcode, npostfix, ndirect, distance, max_allowed))) {
+            if ((int32_t)d.in.avail < 0) st = BRO_ST_UnexpectedEOF;
+            break;
+        }
+        if ((int32_t)d.in.avail < 0) { st = BRO_ST_UnexpectedEOF; break; }                // checkpoint
+        // ---- phase two: materialise the copy ----
+        if ((st = bro_emit_copy(d, sc, mlen, mb_begin, distance, max_allowed, copy_len, false))) break;
+        if (d.pos - mb_begin == mlen) break;                                              // src/lib.rs:2128-2130
+    }
+    if (st == 0) {
+        // literal context for the following meta-block (literal_buf persists)
+        bro_syncwarp();
+        uint32_t m = d.pos - mb_begin;
+        if (m >= 2u) { d.p1 = d.out[d.pos - 1]; d.p2 = d.out[d.pos - 2]; }
+        else { d.p2 = d.p1; d.p1 = d.out[d.pos - 1]; }
+    }
+    return st;
 }
 
 // ------------------------------------------------------------------------------------------------------
@@ -920,6 +1118,17 @@ BRO_FN int bro_decode_compressed_metablock(BroDec& d, uint32_t mlen) {
     const uint16_t* const T_lit = A + o_lit;
     const uint16_t* const T_cmd = A + o_cmd;
     const uint16_t* const T_dist = A + o_dist;
+    // one code of a kind: keep its root table on chip
+    const bool one_lit = ntl == 1u, one_cmd = cat[1].nbl == 1u, one_dist = ntd == 1u;
+    for (uint32_t r = lane; r < 256u; r += BRO_W) {
+        if (one_lit) sc.root_lit[r] = T_lit[r];
+        if (one_cmd) sc.root_cmd[r] = T_cmd[r];
+        if (one_dist) sc.root_dist[r] = T_dist[r];
+    }
+    bro_syncwarp();
+    const bool lit_simple = one_lit && cat[0].nbl == 1u;   // no context modelling, no literal block switches
+    if (lit_simple && one_cmd && one_dist && cat[2].nbl == 1u)
+        return bro_commands_simple(d, sc, mlen, npostfix, ndirect, T_lit, T_cmd, T_dist);
 
     const uint32_t mb_begin = d.pos;   // meta_block.count_output == d.pos - mb_begin
     // command loop (src/lib.rs:2003-2141)
@@ -927,7 +1136,9 @@ BRO_FN int bro_decode_compressed_metablock(BroDec& d, uint32_t mlen) {
         // ---- phase one: entropy decode of one insert&copy command ----
         uint32_t sym, extra;
         if ((st = bro_step_block(d, cat[1]))) return st;
-        int r = bro_decode_sym(d.in, T_cmd + cat[1].btype * BRO_TREE_U16(BRO_ALPHA_CMD), sym);
+        int r;
+        if (one_cmd) r = bro_decode_sym2(d.in, sc.root_cmd, T_cmd, sym);
+        else r = bro_decode_sym(d.in, T_cmd + cat[1].btype * BRO_TREE_U16(BRO_ALPHA_CMD), sym);
         if (r == BRO_SYM_HOLE) return BRO_ST_ParseErrorInsertAndCopyLength;
         if (r == BRO_SYM_EOF) return BRO_ST_UnexpectedEOF;
         uint32_t ie = bro_ic_insert[sym], ce = bro_ic_copy[sym];
@@ -941,6 +1152,23 @@ BRO_FN int bro_decode_compressed_metablock(BroDec& d, uint32_t mlen) {
         // literals (src/lib.rs:1286-1365).  The reference decodes all literals of a command before it emits any, so a
         // decode error inside the run wins over a full output slot: keep decoding (without storing) past the end of
         // the slot and report OutputTooSmall only if the whole run decoded.
+        if (lit_simple && insert_len <= d.cap - d.pos) {
+            // fast path: one literal code, no block switches, the run fits the slot.  Lane k%W keeps literal k and the
+            // group stores W literals with one coalesced store.
+            uint8_t* o = d.out + d.pos;
+            uint32_t mine = 0, k = 0, lit = 0;
+            while (k < insert_len) {
+                r = bro_decode_sym2(d.in, sc.root_lit, T_lit, lit);
+                if (r != BRO_SYM_OK) return r == BRO_SYM_HOLE ? BRO_ST_ParseErrorInsertLiterals : BRO_ST_UnexpectedEOF;
+                if (lane == (k & (BRO_W - 1u))) mine = lit;
+                d.p2 = d.p1; d.p1 = lit;
+                k++;
+                if ((k & (BRO_W - 1u)) == 0u) o[k - BRO_W + lane] = (uint8_t)mine;
+            }
+            uint32_t tail = k & (BRO_W - 1u);
+            if (lane < tail) o[k - tail + lane] = (uint8_t)mine;
+            d.pos += insert_len;
+        } else
         for (uint32_t k = 0; k < insert_len; k++) {
             if ((st = bro_step_block(d, cat[0]))) return st;
             const uint16_t* T = T_lit;
@@ -971,58 +1199,16 @@ BRO_FN int bro_decode_compressed_metablock(BroDec& d, uint32_t mlen) {
                 uint32_t cid = copy_len <= 4u ? copy_len - 2u : 3u;
                 T += (uint32_t)cmap_d[cat[2].btype * 4u + cid] * dist_stride;
             }
-            r = bro_decode_sym(d.in, T, dcode);
+            if (one_dist) r = bro_decode_sym2(d.in, sc.root_dist, T_dist, dcode);
+            else r = bro_decode_sym(d.in, T, dcode);
             if (r == BRO_SYM_HOLE) return BRO_ST_ParseErrorDistanceCode;
             if (r == BRO_SYM_EOF) return BRO_ST_UnexpectedEOF;
         }
         // distance (src/lib.rs:1412-1481)
-        uint32_t distance;
-        if (dcode <= 3u) distance = dcode == 0u ? d.d0 : dcode == 1u ? d.d1 : dcode == 2u ? d.d2 : d.d3;
-        else if (dcode <= 15u) {
-            int32_t basev = (int32_t)(dcode <= 9u ? d.d0 : d.d1);
-            int32_t delta = (int32_t)(((dcode <= 9u ? dcode - 2u : dcode - 8u)) >> 1);
-            int64_t v = (int64_t)(uint32_t)basev + ((dcode & 1u) ? (int64_t)delta : -(int64_t)delta);
-            if (v <= 0) return BRO_ST_InvalidNonPositiveDistance;
-            distance = (uint32_t)v;
-        } else if (dcode <= 15u + ndirect) distance = dcode - 15u;
-        else {
-            uint32_t t = dcode - ndirect - 16u;
-            uint32_t ndistbits = 1u + (t >> (npostfix + 1u));
-            uint32_t dextra;
-            if (!bro_read_bits(d.in, ndistbits, dextra)) return BRO_ST_UnexpectedEOF;
-            uint32_t hcode = t >> npostfix, lcode = t & ((1u << npostfix) - 1u);
-            uint32_t offset = ((2u + (hcode & 1u)) << ndistbits) - 4u;
-            distance = ((offset + dextra) << npostfix) + lcode + ndirect + 1u;
-        }
-        uint32_t max_allowed = d.window < d.pos ? d.window : d.pos;
-        if (dcode > 0u && distance <= max_allowed) {                                // src/lib.rs:1476-1478
-            d.d3 = d.d2; d.d2 = d.d1; d.d1 = d.d0; d.d0 = distance;
-        }
+        uint32_t distance, max_allowed;
+        if ((st = bro_resolve_distance(d, dcode, npostfix, ndirect, distance, max_allowed))) return st;
         // ---- phase two: materialise the copy ----
-        mb_out = d.pos - mb_begin;
-        if (distance <= max_allowed) {
-            if (mlen < mb_out + copy_len) return BRO_ST_ExceededExpectedBytes;     // src/lib.rs:2105-2108
-            if (copy_len > d.cap - d.pos) return BRO_ST_OutputTooSmall;
-            bro_lz_copy(d.out, d.pos, distance, copy_len);
-            d.pos += copy_len;
-            bro_syncwarp();
-            d.p1 = d.out[d.pos - 1]; d.p2 = d.out[d.pos - 2];                        // copy_len >= 2
-        } else {
-            if (copy_len < 4u || copy_len > 24u) return BRO_ST_InvalidLengthInStaticDictionary;
-            uint32_t word_id = distance - max_allowed - 1u;
-            uint32_t bits = bro_dict_size_bits[copy_len];
-            uint32_t index = word_id & ((1u << bits) - 1u), tid = word_id >> bits;
-            if (tid > 120u) return BRO_ST_InvalidTransformId;
-            int n = bro_dict_word(sc, d.dict, d.quirk_spec, copy_len, index, tid);
-            if (n < 0) return BRO_ST_PanicUppercaseZero;
-            if (mlen < mb_out + (uint32_t)n) return BRO_ST_ExceededExpectedBytes;  // checked after the transform (Q10)
-            if ((uint32_t)n > d.cap - d.pos) return BRO_ST_OutputTooSmall;
-            for (uint32_t i = lane; i < (uint32_t)n; i += BRO_W) d.out[d.pos + i] = d.sc->word[i];
-            if (n >= 2) { d.p1 = d.sc->word[n - 1]; d.p2 = d.sc->word[n - 2]; }
-            else if (n == 1) { d.p2 = d.p1; d.p1 = d.sc->word[0]; }
-            d.pos += (uint32_t)n;
-            bro_syncwarp();
-        }
+        if ((st = bro_emit_copy(d, sc, mlen, mb_begin, distance, max_allowed, copy_len, true))) return st;
         if (d.pos - mb_begin == mlen) return 0;                                      // src/lib.rs:2128-2130
     }
 }

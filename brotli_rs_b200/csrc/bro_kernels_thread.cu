@@ -21,10 +21,12 @@
 #define BRO_THREAD_MIN_BLOCKS 4
 #endif
 #define BRO_SCRATCH_U16 ((sizeof(BroScratch) / 2u + 7u) & ~7u)
+#define BRO_THREAD_ARENA_STRIDE_U16 (BRO_THREAD_ARENA_U16 + 704u)
 
 __global__ void __launch_bounds__(BRO_THREAD_BLOCK, BRO_THREAD_MIN_BLOCKS) bro_decode_thread_kernel(BroLaunch p) {
     const unsigned t = blockIdx.x * BRO_THREAD_BLOCK + threadIdx.x;
-    uint16_t* arena = p.arena + (size_t)t * BRO_THREAD_ARENA_U16;
+    // the stride is an odd number of 128-byte lines, so that the threads' root tables do not pile into a few L1 sets
+    uint16_t* arena = p.arena + (size_t)t * BRO_THREAD_ARENA_STRIDE_U16;
     for (;;) {
         uint32_t k = atomicAdd(p.counter, 1u);
         if (k >= p.n) break;
@@ -97,7 +99,7 @@ extern "C" int bro_thread_kernel_occupancy(int* blocks_per_sm) {
     return (int)cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, bro_decode_thread_kernel, BRO_THREAD_BLOCK, 0);
 }
 extern "C" int bro_thread_kernel_block() { return BRO_THREAD_BLOCK; }
-extern "C" size_t bro_thread_kernel_arena_bytes() { return 2u * (size_t)BRO_THREAD_ARENA_U16; }
+extern "C" size_t bro_thread_kernel_arena_bytes() { return 2u * (size_t)BRO_THREAD_ARENA_STRIDE_U16; }
 
 extern "C" int bro_thread_kernel_launch(const BroLaunch* p, int grid, cudaStream_t stream) {
     bro_decode_thread_kernel<<<grid, BRO_THREAD_BLOCK, 0, stream>>>(*p);
