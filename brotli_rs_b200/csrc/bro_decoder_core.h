@@ -985,7 +985,46 @@ BRO_FN int bro_commands_simple(BroDec& d, BroScratch& sc, uint32_t mlen, uint32_
         // not fit the slot is still decoded (a decode error wins over OutputTooSmall, as in the general loop).
         const bool fits = insert_len <= d.cap - d.pos;
         uint8_t* o = d.out + d.pos;
-        uint32_t mine = 0, k = 0;
+        uint32_t k = 0;
+#if !defined(BRO_SERIAL) && BRO_W == 32u
+        // LANE-PARALLEL literal decode.  All literals of the run use one code, so lane l looks up the code that would
+        // start at bit offset l of the next 32 stream bits; the symbols actually present are the chain 0 -> len(0) ->
+        // len(0)+len(len(0)) ... which is walked with one shuffle per symbol, and every chain member stores its
+        // literal at its rank.  A round therefore costs a handful of instructions per literal instead of a full
+        // serial decode; codes longer than 8 bits end a round and take the scalar path.
+        while (k < insert_len) {
+            bro_refill(d.in);
+            const uint32_t w2 = bro_shfl(d.in.cur, d.in.wi);                  // the word after the window, not consumed
+            const uint32_t lo = bro_funnel_r(d.in.w0, d.in.w1, d.in.bp);     // stream bits [0, 32)
+            const uint32_t hi = bro_funnel_r(d.in.w1, w2, d.in.bp);          // stream bits [32, 64)
+            const uint32_t e = bro_root_get(r_lit, bro_funnel_r(lo, hi, lane) & 0xffu);
+            const uint32_t len_l = e >> 10;                                   // 0: longer than 8 bits (or a hole)
+            uint32_t want = insert_len - k, pos = 0, mask = 0, cnt = 0;
+            while (cnt < want) {
+                const uint32_t L = bro_shfl(len_l, pos);
+                if (L == 0u || pos + L > 32u) break;
+                mask |= 1u << pos;
+                pos += L;
+                cnt++;
+                if (pos >= 32u) break;
+            }
+            if (cnt != 0u) {
+                if (fits && ((mask >> lane) & 1u)) o[k + bro_popc(mask & bro_lanemask_lt())] = (uint8_t)e;
+                k += cnt;
+                bro_consume(d.in, pos);
+            } else {
+                uint32_t lit;
+                r = bro_decode_sym_onchip(d.in, r_lit, T_lit, lit);
+                if (r != BRO_SYM_OK) { st = r == BRO_SYM_HOLE ? BRO_ST_ParseErrorInsertLiterals : BRO_ST_UnexpectedEOF; break; }
+                if (fits && lane == 0) o[k] = (uint8_t)lit;
+                k++;
+            }
+        }
+        if (st) break;
+        if ((int32_t)d.in.avail < 0) { st = BRO_ST_UnexpectedEOF; break; }                // checkpoint
+        if (!fits) { d.pos = d.cap; st = BRO_ST_OutputTooSmall; break; }
+#else
+        uint32_t mine = 0;
         while (k < insert_len) {
             uint32_t lit;
             r = bro_decode_sym_onchip(d.in, r_lit, T_lit, lit);
@@ -1001,6 +1040,7 @@ BRO_FN int bro_commands_simple(BroDec& d, BroScratch& sc, uint32_t mlen, uint32_
             uint32_t tail = k & (BRO_W - 1u);
             if (lane < tail) o[k - tail + lane] = (uint8_t)mine;
         }
+#endif
         d.pos += insert_len;
         if (d.pos - mb_begin == mlen) break;                                              // src/lib.rs:2069-2070
         // distance code (src/lib.rs:1367-1410) and distance (1412-1481)
