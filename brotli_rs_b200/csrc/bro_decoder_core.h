@@ -1079,10 +1079,20 @@ BRO_FN int bro_step_block(BroDec& d, BroBlockCat& c) {   // src/lib.rs:1182-1197
     return 0;
 }
 
-BRO_FN int bro_decode_compressed_metablock(BroDec& d, uint32_t mlen) {
+// What the header of a compressed meta-block announces (src/lib.rs:1745-2002), with the arena offsets of its tables.
+struct BroMbInfo {
+    BroBlockCat cat[3];
+    uint32_t npostfix, ndirect, ntl, ntd;
+    uint32_t o_modes, o_cmap_l, o_cmap_d, o_lit, o_cmd, o_dist, dist_stride;
+    bool simple;              // one literal / insert&copy / distance code and no block switches: no context modelling
+};
+
+// Header of a compressed meta-block: block-type codes, NPOSTFIX/NDIRECT, context modes and maps, and all prefix code
+// tables, bump-allocated in the arena.
+BRO_FN int bro_metablock_tables(BroDec& d, BroMbInfo& mb) {
     const unsigned lane = bro_lane();
     uint16_t* A = d.arena;
-    BroBlockCat cat[3];
+    BroBlockCat (&cat)[3] = mb.cat;
     int st;
     BroScratch& sc = *d.sc;
     // The arena is bump-allocated per meta-block from the counts the header announces (uint16 units, 16-byte
@@ -1155,21 +1165,29 @@ BRO_FN int bro_decode_compressed_metablock(BroDec& d, uint32_t mlen) {
         }
     }
     bro_syncwarp();
-    const uint16_t* const T_lit = A + o_lit;
-    const uint16_t* const T_cmd = A + o_cmd;
-    const uint16_t* const T_dist = A + o_dist;
-    // one code of a kind: keep its root table on chip
-    const bool one_lit = ntl == 1u, one_cmd = cat[1].nbl == 1u, one_dist = ntd == 1u;
-    for (uint32_t r = lane; r < 256u; r += BRO_W) {
-        if (one_lit) sc.root_lit[r] = T_lit[r];
-        if (one_cmd) sc.root_cmd[r] = T_cmd[r];
-        if (one_dist) sc.root_dist[r] = T_dist[r];
-    }
-    bro_syncwarp();
-    const bool lit_simple = one_lit && cat[0].nbl == 1u;   // no context modelling, no literal block switches
-    if (lit_simple && one_cmd && one_dist && cat[2].nbl == 1u)
-        return bro_commands_simple(d, sc, mlen, npostfix, ndirect, T_lit, T_cmd, T_dist);
+    mb.npostfix = npostfix; mb.ndirect = ndirect; mb.ntl = ntl; mb.ntd = ntd;
+    mb.o_modes = o_modes; mb.o_cmap_l = o_cmap_l; mb.o_cmap_d = o_cmap_d;
+    mb.o_lit = o_lit; mb.o_cmd = o_cmd; mb.o_dist = o_dist; mb.dist_stride = dist_stride;
+    mb.simple = ntl == 1u && ntd == 1u && cat[0].nbl == 1u && cat[1].nbl == 1u && cat[2].nbl == 1u;
+    return 0;
+}
 
+// The general command loop (src/lib.rs:2003-2141): any number of codes, block switches, literal context modelling.
+BRO_FN int bro_commands_general(BroDec& d, BroScratch& sc, uint32_t mlen, BroMbInfo& mb) {
+    const unsigned lane = bro_lane();
+    uint16_t* A = d.arena;
+    BroBlockCat (&cat)[3] = mb.cat;
+    int st;
+    const uint32_t npostfix = mb.npostfix, ndirect = mb.ndirect, ntl = mb.ntl, ntd = mb.ntd, dist_stride = mb.dist_stride;
+    const uint8_t* modes = (const uint8_t*)(A + mb.o_modes);
+    const uint8_t* cmap_l = (const uint8_t*)(A + mb.o_cmap_l);
+    const uint8_t* cmap_d = (const uint8_t*)(A + mb.o_cmap_d);
+    const uint16_t* const T_lit = A + mb.o_lit;
+    const uint16_t* const T_cmd = A + mb.o_cmd;
+    const uint16_t* const T_dist = A + mb.o_dist;
+    // one code of a kind: its root table is on chip (bro_decode_compressed_metablock)
+    const bool one_lit = ntl == 1u, one_cmd = cat[1].nbl == 1u, one_dist = ntd == 1u;
+    const bool lit_simple = one_lit && cat[0].nbl == 1u;   // no context modelling, no literal block switches
     const uint32_t mb_begin = d.pos;   // meta_block.count_output == d.pos - mb_begin
     // command loop (src/lib.rs:2003-2141)
     for (;;) {
@@ -1253,12 +1271,42 @@ BRO_FN int bro_decode_compressed_metablock(BroDec& d, uint32_t mlen) {
     }
 }
 
+// On-chip copies of the root tables of a meta-block that has exactly one code of a kind.
+BRO_FN void bro_stage_roots(BroDec& d, BroScratch& sc, const BroMbInfo& mb) {
+    const unsigned lane = bro_lane();
+    const uint16_t* T_lit = d.arena + mb.o_lit;
+    const uint16_t* T_cmd = d.arena + mb.o_cmd;
+    const uint16_t* T_dist = d.arena + mb.o_dist;
+    const bool one_lit = mb.ntl == 1u, one_cmd = mb.cat[1].nbl == 1u, one_dist = mb.ntd == 1u;
+    for (uint32_t r = lane; r < 256u; r += BRO_W) {
+        if (one_lit) sc.root_lit[r] = T_lit[r];
+        if (one_cmd) sc.root_cmd[r] = T_cmd[r];
+        if (one_dist) sc.root_dist[r] = T_dist[r];
+    }
+    bro_syncwarp();
+}
+
+// one compressed meta-block after MLEN / ISUNCOMPRESSED: src/lib.rs:1745-2141
+BRO_FN int bro_decode_compressed_metablock(BroDec& d, uint32_t mlen) {
+    BroMbInfo mb;
+    BroScratch& sc = *d.sc;
+    int st = bro_metablock_tables(d, mb);
+    if (st) return st;
+    bro_stage_roots(d, sc, mb);
+    if (mb.simple)
+        return bro_commands_simple(d, sc, mlen, mb.npostfix, mb.ndirect, d.arena + mb.o_lit, d.arena + mb.o_cmd, d.arena + mb.o_dist);
+    return bro_commands_general(d, sc, mlen, mb);
+}
+
 // ------------------------------------------------------------------------------------------------------
 // one stream: src/lib.rs:1545-2170.  Returns the status; *out_len = bytes produced.
 // ------------------------------------------------------------------------------------------------------
-BRO_FN int bro_decode_stream(BroDec& d) {
-    uint32_t b, n, v;
-    // WBITS (src/lib.rs:89-119, 412-418): 0 -> 16; 1+n -> 17+n; 1000+m -> 8+m (m>=2), 17 (m=0), m=1 reserved (Q8)
+#define BRO_MB_COMPRESSED 0x1000   /* bro_next_metablock: a compressed meta-block follows (is_last, mlen set) */
+#define BRO_MB_END 0x1001          /* the stream ended cleanly */
+
+// WBITS (src/lib.rs:89-119, 412-418): 0 -> 16; 1+n -> 17+n; 1000+m -> 8+m (m>=2), 17 (m=0), m=1 reserved (Q8)
+BRO_FN int bro_stream_header(BroDec& d) {
+    uint32_t b, n;
     if (!bro_read_bits(d.in, 1, b)) return BRO_ST_UnexpectedEOF;
     uint32_t wbits = 16;
     if (b) {
@@ -1271,8 +1319,16 @@ BRO_FN int bro_decode_stream(BroDec& d) {
         }
     }
     d.window = (1u << wbits) - 16u;
-    for (;;) {
-        uint32_t is_last;
+    return 0;
+}
+
+// Advance to the next compressed meta-block: consumes meta-block headers, skips metadata blocks and copies stored
+// blocks on the way (src/lib.rs:1572-1734), and runs the end-of-stream checks (2155-2167) when the stream ends.
+// after_last: the meta-block just decoded had ISLAST set.  Returns BRO_MB_COMPRESSED, BRO_MB_END or an error status.
+BRO_FN int bro_next_metablock(BroDec& d, bool after_last, uint32_t& is_last, uint32_t& mlen) {
+    uint32_t b, n, v;
+    bool ended = after_last;
+    while (!ended) {
         if (!bro_read_bits(d.in, 1, is_last)) return BRO_ST_UnexpectedEOF;
         if (is_last) {
             if (!bro_read_bits(d.in, 1, b)) return BRO_ST_UnexpectedEOF;
@@ -1301,11 +1357,11 @@ BRO_FN int bro_decode_stream(BroDec& d) {
                 if ((uint64_t)(d.in.end - a) < (uint64_t)skip) return BRO_ST_UnexpectedEOF;
                 bro_bits_seek(d.in, a + skip);
             }
-            if (is_last) break;
+            if (is_last) ended = true;
             continue;
         }
         // MLEN (src/lib.rs:469-483)
-        uint32_t nibbles = n + 4u, mlen;
+        uint32_t nibbles = n + 4u;
         if (!bro_read_bits(d.in, 4u * nibbles, mlen)) return BRO_ST_UnexpectedEOF;
         if (nibbles > 4u && (mlen >> ((nibbles - 1u) * 4u)) == 0u) return BRO_ST_NonZeroTrailerNibble;
         mlen += 1;
@@ -1327,14 +1383,27 @@ BRO_FN int bro_decode_stream(BroDec& d) {
                 continue;
             }
         }
-        int st = bro_decode_compressed_metablock(d, mlen);
-        if (st) return st;
-        if (is_last) break;
+        return BRO_MB_COMPRESSED;
     }
     // StreamEnd (src/lib.rs:2155-2167)
     bro_read_byte_tail(d.in, v);
     if (v) return BRO_ST_NonZeroTrailerBit;
     bro_refill(d.in);
     if (bro_avail(d.in) > 0u) return BRO_ST_ExpectedEndOfStream;
-    return BRO_ST_OK;
+    return BRO_MB_END;
+}
+
+BRO_FN int bro_decode_stream(BroDec& d) {
+    int st = bro_stream_header(d);
+    if (st) return st;
+    uint32_t is_last = 0, mlen = 0;
+    bool after_last = false;
+    for (;;) {
+        st = bro_next_metablock(d, after_last, is_last, mlen);
+        if (st == BRO_MB_END) return BRO_ST_OK;
+        if (st != BRO_MB_COMPRESSED) return st;
+        st = bro_decode_compressed_metablock(d, mlen);
+        if (st) return st;
+        after_last = is_last != 0u;
+    }
 }
