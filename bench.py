@@ -5,13 +5,15 @@
     python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...      (N > 1, one rank per GPU)
     python bench.py --impl reference ...                                              (the CPU arm)
 
-A "step" is one pass of the hot path (one kernel launch per rank) over the whole batch.  The batch is fixed
+A "step" is one pass of the hot path (one bro_batch_decode call per rank: ordering, parse, copy and fused-retry
+kernels for a large batch, the fused kernel alone for a small one) over the whole batch.  The batch is fixed
 (strong scaling): at N ranks every rank decodes 1/N of the streams, no data-path collective.
 
   value   whole-job uncompressed GB/s with inputs and outputs resident in HBM (CUDA events, max over ranks)
   e2e     the same metric through the reference-facing C ABI call bro_batch_decode_host with pinned HOST buffers:
           the H2D copy of the compressed batch and the D2H copy of every output slot are inside the timed region
-  roofline  algorithmic bytes (compressed read + uncompressed written) per launch / kernel time
+  roofline  the dominant kernel of the step: its algorithmic bytes per launch / its mean duration, both measured live
+          (CUDA events recorded by the library around each kernel); the other kernels are listed under "kernels"
   cpu_baseline  the oracle port of the reference algorithm on the host cores, on a bounded sample (N = 1 only)
 
 Only the cpu_baseline / --impl reference legs execute anything under oracle/; the GPU path never does.
@@ -41,6 +43,8 @@ def parse_args():
     ap.add_argument("--workload", default="c4_highratio_w16")
     ap.add_argument("--streams", type=int, default=None, help="batch size (default: the workload's BASELINE size)")
     ap.add_argument("--e2e-steps", type=int, default=None, help="timed end-to-end steps (default: min(steps, 5))")
+    ap.add_argument("--mode", default="auto", choices=["auto", "warp", "twophase"],
+                    help="decode path (bro_ctx_set_mode); auto = the library's default policy")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-sample-streams", type=int, default=None)
@@ -57,14 +61,20 @@ def measured_peaks():
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
-def ncu_traffic(workload, algorithmic_bytes):
-    """dram bytes per launch from the committed ncu capture of this workload, scaled to this launch's size."""
+def ncu_traffic(workload, algorithmic_bytes, kernel):
+    """dram bytes per launch of `kernel` from the committed ncu capture of this workload, scaled to this launch's size."""
     p = os.path.join(ROOT, "profiles", "ncu_traffic.json")
     if not os.path.exists(p):
         return None
     try:
         rec = json.load(open(p)).get(workload)
         if not rec:
+            return None
+        if "kernels" in rec:
+            rec = rec["kernels"].get(kernel.split(" ")[0])
+            if not rec:
+                return None
+        elif not kernel.startswith("bro_decode_warp_kernel"):
             return None
         return rec["dram_bytes_per_algorithmic_byte"] * algorithmic_bytes
     except Exception:
@@ -257,7 +267,7 @@ def main():
     d_out = torch.empty(int(out_off[-1]), dtype=torch.uint8, device=dev)
     d_len = torch.empty(n, dtype=torch.int64, device=dev)
     d_st = torch.empty(n, dtype=torch.int32, device=dev)
-    dec = BatchDecoder(local_rank)
+    dec = BatchDecoder(local_rank, mode={"auto": None, "warp": BatchDecoder.MODE_WARP, "twophase": BatchDecoder.MODE_TWOPHASE}[args.mode])
 
     comp_bytes = float(in_off[-1])
     uncomp_bytes = float(ulen_out[uidx].sum())
@@ -303,14 +313,49 @@ def main():
     all_comp = sum_over_ranks(comp_bytes)
     value = all_uncomp * args.steps / (total_ms_max * 1e-3) / 1e9
 
-    # ---- roofline of the (single) decode kernel on this rank ----
+    # ---- per-kernel times (CUDA events recorded by the library around its kernels, on the launching stream) and the
+    # roofline of the dominant kernel on this rank ----
     peak, peak_src = measured_peaks()
-    kern_ms = float(np.mean(step_ms))
-    algo_bytes = comp_bytes + uncomp_bytes
+    dec.set_timing(True)
+    ksum = {"order": 0.0, "parse": 0.0, "copy": 0.0, "fused": 0.0}
+    for _ in range(args.steps):
+        dec.decode_device(d_in, d_in_off, d_out, d_out_off, d_len, d_st)
+        for k, v in dec.last_kernel_ms().items():
+            ksum[k] += v
+    dec.set_timing(False)
+    stats = dec.last_batch_stats()
+    kms = {k: v / args.steps for k, v in ksum.items()}
+    # algorithmic bytes per launch: fused = compressed read + uncompressed written; copy = bytes
+    # written by copy records + 16 B per record read; parse = compressed read + bytes it writes itself (literals,
+    # dictionary words) + 16 B per record written
+    two_phase = kms["parse"] > 0.0
+    rec_bytes = 16.0 * stats["copy_records"]
+    if two_phase:
+        retried = stats["retried_streams"]
+        algo = {"copy": stats["copy_bytes"] + rec_bytes,
+                "parse": comp_bytes + max(0.0, uncomp_bytes - stats["copy_bytes"]) + rec_bytes if retried == 0 else comp_bytes + rec_bytes,
+                "fused": (comp_bytes + uncomp_bytes) if retried == n else None, "order": 8.0 * (n + 1) * 2}
+    else:
+        algo = {"fused": comp_bytes + uncomp_bytes}
+    names = {"order": "bro_order_*_kernel (3)", "parse": "bro_parse_kernel", "copy": "bro_copy_kernel", "fused": "bro_decode_warp_kernel"}
+    kernels = {}
+    for k, ms in kms.items():
+        if ms <= 0.0:
+            continue
+        a = algo.get(k)
+        kernels[names[k]] = {"ms": ms, "algorithmic_bytes": a, "achieved_gbs": (a / (ms * 1e-3) / 1e9) if a else None,
+                             "frac": (a / (ms * 1e-3) / 1e9 / peak) if a else None}
+    dom = max((k for k in kms if kms[k] > 0.0), key=lambda k: kms[k])
+    kern_ms = kms[dom]
+    algo_bytes = algo.get(dom) or (comp_bytes + uncomp_bytes)
     achieved = algo_bytes / (kern_ms * 1e-3) / 1e9
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": ncu_traffic(args.workload, algo_bytes), "peak_source": peak_src,
-                "kernel": "bro_decode_kernel", "kernel_ms": kern_ms, "algorithmic_bytes_per_launch": algo_bytes}
+                "traffic": ncu_traffic(args.workload, algo_bytes, names[dom]), "peak_source": peak_src,
+                "kernel": names[dom], "kernel_ms": kern_ms, "algorithmic_bytes_per_launch": algo_bytes,
+                "kernel_share_of_step": kern_ms / float(np.mean(step_ms)), "kernels": kernels,
+                "whole_step": {"ms": float(np.mean(step_ms)), "algorithmic_bytes": comp_bytes + uncomp_bytes,
+                               "frac": (comp_bytes + uncomp_bytes) / (float(np.mean(step_ms)) * 1e-3) / 1e9 / peak},
+                "batch_stats": stats}
 
     # ---- end to end through the C ABI with pinned host buffers ----
     e2e = None
@@ -355,7 +400,7 @@ def main():
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": total_ms_max / args.steps,
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
             "config": {"workload": args.workload, "description": desc, "streams": n_streams,
-                       "unique_streams": len(streams), "streams_per_rank": n,
+                       "unique_streams": len(streams), "streams_per_rank": n, "mode": args.mode,
                        "compressed_bytes": all_comp, "uncompressed_bytes": all_uncomp,
                        "l2_policy": "inputs and outputs far larger than L2 (no flush needed)",
                        "parallelism": "streams sharded over %d rank(s), no data-path collective" % world},

@@ -14,7 +14,7 @@ PANIC_UPPERCASE_ZERO = 102
 # every symbol include/brotli_b200.h declares
 ABI_SYMBOLS = [
     "bro_ctx_create", "bro_ctx_destroy", "bro_ctx_set_quirks", "bro_ctx_set_mode", "bro_ctx_last_cuda_error", "bro_ctx_launch_count",
-    "bro_ctx_num_warps", "bro_batch_decode", "bro_batch_decode_host", "bro_status_description",
+    "bro_ctx_num_warps", "bro_ctx_reserve", "bro_ctx_set_timing", "bro_ctx_last_kernel_ms", "bro_ctx_last_batch_stats", "bro_batch_decode", "bro_batch_decode_host", "bro_status_description",
     "bro_reader_new", "bro_reader_read", "bro_reader_status", "bro_reader_free",
 ]
 
@@ -60,6 +60,14 @@ def load_library():
     L.bro_ctx_launch_count.argtypes = [vp]
     L.bro_ctx_num_warps.restype = u32
     L.bro_ctx_num_warps.argtypes = [vp]
+    L.bro_ctx_set_timing.restype = ctypes.c_int
+    L.bro_ctx_set_timing.argtypes = [vp, ctypes.c_int]
+    L.bro_ctx_last_kernel_ms.restype = ctypes.c_int
+    L.bro_ctx_last_kernel_ms.argtypes = [vp, ctypes.POINTER(ctypes.c_float)]
+    L.bro_ctx_last_batch_stats.restype = ctypes.c_int
+    L.bro_ctx_last_batch_stats.argtypes = [vp, ctypes.POINTER(u64)]
+    L.bro_ctx_reserve.restype = ctypes.c_int
+    L.bro_ctx_reserve.argtypes = [vp, u64, u32]
     L.bro_batch_decode.restype = ctypes.c_int
     L.bro_batch_decode.argtypes = [vp, vp, vp, vp, vp, vp, vp, u32, vp]
     L.bro_batch_decode_host.restype = ctypes.c_int

@@ -35,7 +35,7 @@ def slot_offsets(capacities, align=16):
 class BatchDecoder:
     """One GPU's decoder context (bro_ctx).  Not thread safe; use one per host thread / CUDA stream."""
 
-    MODE_AUTO, MODE_WARP, MODE_THREAD = 0, 1, 2
+    MODE_AUTO, MODE_WARP, MODE_TWOPHASE = 0, 1, 2
 
     def __init__(self, device=None, quirks=0, mode=None):
         import torch
@@ -59,7 +59,7 @@ class BatchDecoder:
             self.set_mode(mode)
 
     def set_mode(self, mode):
-        """MODE_AUTO (default) / MODE_WARP / MODE_THREAD -- see bro_ctx_set_mode in include/brotli_b200.h."""
+        """MODE_AUTO (default) / MODE_WARP / MODE_TWOPHASE -- see bro_ctx_set_mode in include/brotli_b200.h."""
         self._check(self._lib.bro_ctx_set_mode(self._ctx, int(mode)))
 
     def close(self):
@@ -76,6 +76,22 @@ class BatchDecoder:
     @property
     def launch_count(self):
         return int(self._lib.bro_ctx_launch_count(self._ctx))
+
+    def set_timing(self, on):
+        """Record CUDA events around the kernels of every batch (bench.py's per-kernel roofline)."""
+        self._check(self._lib.bro_ctx_set_timing(self._ctx, 1 if on else 0))
+
+    def last_kernel_ms(self):
+        """-> dict of kernel durations (ms) of the last batch; waits for it."""
+        ms = (ctypes.c_float * 4)()
+        self._check(self._lib.bro_ctx_last_kernel_ms(self._ctx, ms))
+        return {"order": float(ms[0]), "parse": float(ms[1]), "copy": float(ms[2]), "fused": float(ms[3])}
+
+    def last_batch_stats(self):
+        """-> dict(copy_bytes, copy_records, retried_streams) of the last batch; synchronises the device."""
+        st = (ctypes.c_uint64 * 4)()
+        self._check(self._lib.bro_ctx_last_batch_stats(self._ctx, st))
+        return {"copy_bytes": int(st[0]), "copy_records": int(st[1]), "retried_streams": int(st[2])}
 
     @property
     def num_warps(self):
@@ -100,6 +116,8 @@ class BatchDecoder:
         if d_status is None:
             d_status = torch.empty(n, dtype=torch.int32, device=d_in.device)
         s = stream if stream is not None else torch.cuda.current_stream(d_in.device)
+        # the buffer's size bounds the compressed bytes of the batch: no read-back of the offsets (bro_ctx_reserve)
+        self._check(self._lib.bro_ctx_reserve(self._ctx, max(1, d_in.numel()), n))
         st = self._lib.bro_batch_decode(self._ctx, d_in.data_ptr(), d_in_off.data_ptr(), d_out.data_ptr(),
                                         d_out_off.data_ptr(), d_out_len.data_ptr(), d_status.data_ptr(), n,
                                         ctypes.c_void_p(s.cuda_stream))

@@ -25,15 +25,23 @@ struct bro_ctx {
     int grid;                 // warp kernel: persistent CTAs
     uint32_t num_warps;
     uint16_t* d_arena;        // warp kernel: worst-case arena per warp
-    int grid_t;               // thread kernel: persistent CTAs
+    int grid_t;               // parse kernel: persistent CTAs
     uint32_t num_threads;
-    uint16_t* d_arena_t;      // thread kernel: 64 KiB arena per thread
+    uint16_t* d_arena_t;      // parse kernel: 64 KiB arena per thread
+    int grid_c;               // copy kernel: persistent CTAs
     uint8_t* d_dict;
-    uint32_t* d_counter;      // [0] thread-kernel queue head, [1] warp-kernel queue head, [2] retry count
-    uint32_t* d_order; size_t d_order_cap;   // size-class order of the current batch
+    uint32_t* d_counter;      // queue heads: [0] parse kernel, [1] warp kernel, [3] copy kernel; [2] retry count;
+                              // [4..7] as two uint64: bytes moved / records executed by the copy kernel (last batch)
+    uint32_t* d_order; size_t d_order_cap;   // size-class order of the current batch | records per stream (2 * cap)
     uint32_t* d_order_scratch;               // 512 counters
-    int mode;                 // BRO_MODE_AUTO / WARP / THREAD
-    uint32_t thread_threshold;// AUTO: batches of at least this many streams use the thread kernel
+    BroRec* d_rec; size_t d_rec_cap;         // copy records (in records)
+    int timing;               // bro_ctx_set_timing: record CUDA events around the kernels of a batch
+    cudaEvent_t ev[5];        // before ordering | before parse | before copy | before fused | after fused
+    int ev_valid;             // the last batch recorded ev[] (two_phase: all five, else ev[3], ev[4])
+    int ev_two_phase;
+    uint64_t reserved_in;     // bro_ctx_reserve: the caller's bound on the compressed bytes of a batch (0 = none)
+    int mode;                 // BRO_MODE_AUTO / WARP / TWOPHASE
+    uint32_t twophase_threshold;   // AUTO: batches of at least this many streams take the two-phase path
     int quirks;
     uint64_t launches;
     char err[256];
@@ -61,25 +69,26 @@ extern "C" int bro_ctx_create(bro_ctx** out, int device) {
     cudaDeviceProp prop;
     if ((e = cudaGetDeviceProperties(&prop, device)) != cudaSuccess) { free(ctx); return BRO_ST_CudaError; }
     ctx->num_sms = prop.multiProcessorCount;
-    int per_sm = 0, per_sm_t = 0;
+    int per_sm = 0, per_sm_t = 0, per_sm_c = 0;
     if (bro_warp_kernel_occupancy(&per_sm) != 0 || per_sm < 1 ||
-        bro_thread_kernel_occupancy(&per_sm_t) != 0 || per_sm_t < 1) { free(ctx); return BRO_ST_CudaError; }
+        bro_parse_kernel_occupancy(&per_sm_t) != 0 || per_sm_t < 1 ||
+        bro_copy_kernel_occupancy(&per_sm_c) != 0 || per_sm_c < 1) { free(ctx); return BRO_ST_CudaError; }
     ctx->grid = ctx->num_sms * per_sm;
     ctx->num_warps = (uint32_t)ctx->grid * (uint32_t)bro_warp_kernel_warps_per_cta();
     ctx->grid_t = ctx->num_sms * per_sm_t;
-    ctx->num_threads = (uint32_t)ctx->grid_t * (uint32_t)bro_thread_kernel_block();
+    ctx->num_threads = (uint32_t)ctx->grid_t * (uint32_t)bro_parse_kernel_block();
+    ctx->grid_c = ctx->num_sms * per_sm_c;
     ctx->mode = BRO_MODE_AUTO;
-    // Measured on B200 (profiles/r01_kernel_variants.md): with its tables and windows in HBM the thread-per-stream
-    // kernel is bound by dependent DRAM-latency chains and loses to the warp kernel on every BASELINE workload except
-    // literal-only streams, so AUTO never selects it; it stays available through bro_ctx_set_mode for experiments.
-    ctx->thread_threshold = 0xffffffffu;
+    // A warp per stream is the lowest latency for a few streams; once there are more streams than resident warps the
+    // two-phase path (32 streams per warp in the entropy decode, then bandwidth-bound copies) wins.
+    ctx->twophase_threshold = ctx->num_warps;
     const char* env = getenv("BRO_B200_MODE");
     if (env && !strcmp(env, "warp")) ctx->mode = BRO_MODE_WARP;
-    if (env && !strcmp(env, "thread")) ctx->mode = BRO_MODE_THREAD;
+    if (env && (!strcmp(env, "twophase") || !strcmp(env, "thread"))) ctx->mode = BRO_MODE_TWOPHASE;
     size_t arena = (size_t)ctx->num_warps * bro_warp_kernel_arena_bytes();
     if ((e = cudaMalloc(&ctx->d_arena, arena)) != cudaSuccess ||
         (e = cudaMalloc(&ctx->d_dict, BRO_DICT_BYTES)) != cudaSuccess ||
-        (e = cudaMalloc(&ctx->d_counter, 4 * sizeof(uint32_t))) != cudaSuccess ||
+        (e = cudaMalloc(&ctx->d_counter, 8 * sizeof(uint32_t))) != cudaSuccess ||
         (e = cudaMalloc(&ctx->d_order_scratch, 512 * sizeof(uint32_t))) != cudaSuccess ||
         (e = cudaMemcpy(ctx->d_dict, bro_dictionary_blob, BRO_DICT_BYTES, cudaMemcpyHostToDevice)) != cudaSuccess) {
         cudaFree(ctx->d_arena); cudaFree(ctx->d_arena_t); cudaFree(ctx->d_dict); cudaFree(ctx->d_counter); cudaFree(ctx->d_order_scratch);
@@ -94,8 +103,9 @@ extern "C" void bro_ctx_destroy(bro_ctx* ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     cudaFree(ctx->d_arena); cudaFree(ctx->d_arena_t); cudaFree(ctx->d_dict); cudaFree(ctx->d_counter);
-    cudaFree(ctx->d_order); cudaFree(ctx->d_order_scratch);
+    cudaFree(ctx->d_order); cudaFree(ctx->d_order_scratch); cudaFree(ctx->d_rec);
     cudaFree(ctx->d_in); cudaFree(ctx->d_out); cudaFree(ctx->d_meta);
+    for (int k = 0; k < 5; k++) if (ctx->ev[k]) cudaEventDestroy(ctx->ev[k]);
     free(ctx);
 }
 
@@ -106,7 +116,7 @@ extern "C" int bro_ctx_set_quirks(bro_ctx* ctx, int quirks) {
 }
 
 extern "C" int bro_ctx_set_mode(bro_ctx* ctx, int mode) {
-    if (!ctx || mode < BRO_MODE_AUTO || mode > BRO_MODE_THREAD) return BRO_ST_InvalidArgument;
+    if (!ctx || mode < BRO_MODE_AUTO || mode > BRO_MODE_TWOPHASE) return BRO_ST_InvalidArgument;
     ctx->mode = mode;
     return BRO_ST_OK;
 }
@@ -115,6 +125,54 @@ extern "C" const char* bro_ctx_last_cuda_error(const bro_ctx* ctx) { return ctx 
 extern "C" uint64_t bro_ctx_launch_count(const bro_ctx* ctx) { return ctx ? ctx->launches : 0; }
 extern "C" uint32_t bro_ctx_num_warps(const bro_ctx* ctx) { return ctx ? ctx->num_warps : 0; }
 
+extern "C" int bro_ctx_set_timing(bro_ctx* ctx, int on) {
+    if (!ctx) return BRO_ST_InvalidArgument;
+    BRO_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (on && !ctx->ev[0]) for (int k = 0; k < 5; k++) BRO_CUDA(ctx, cudaEventCreate(&ctx->ev[k]));
+    ctx->timing = on ? 1 : 0;
+    ctx->ev_valid = 0;
+    return BRO_ST_OK;
+}
+
+extern "C" int bro_ctx_last_kernel_ms(bro_ctx* ctx, float* ms4) {
+    if (!ctx || !ms4) return BRO_ST_InvalidArgument;
+    ms4[0] = ms4[1] = ms4[2] = ms4[3] = 0.0f;
+    if (!ctx->ev_valid) return BRO_ST_InvalidArgument;
+    BRO_CUDA(ctx, cudaEventSynchronize(ctx->ev[4]));
+    if (ctx->ev_two_phase) for (int k = 0; k < 3; k++) BRO_CUDA(ctx, cudaEventElapsedTime(&ms4[k], ctx->ev[k], ctx->ev[k + 1]));
+    BRO_CUDA(ctx, cudaEventElapsedTime(&ms4[3], ctx->ev[3], ctx->ev[4]));
+    return BRO_ST_OK;
+}
+
+extern "C" int bro_ctx_last_batch_stats(bro_ctx* ctx, uint64_t* stats4) {
+    if (!ctx || !stats4) return BRO_ST_InvalidArgument;
+    uint32_t h[8];
+    BRO_CUDA(ctx, cudaSetDevice(ctx->device));
+    BRO_CUDA(ctx, cudaDeviceSynchronize());
+    BRO_CUDA(ctx, cudaMemcpy(h, ctx->d_counter, sizeof(h), cudaMemcpyDeviceToHost));
+    stats4[0] = (uint64_t)h[4] | ((uint64_t)h[5] << 32);     // bytes moved by copy records
+    stats4[1] = (uint64_t)h[6] | ((uint64_t)h[7] << 32);     // copy records executed
+    stats4[2] = h[2];                                        // streams handed to the fused kernel's retry pass
+    stats4[3] = 0;
+    return BRO_ST_OK;
+}
+
+extern "C" int bro_ctx_reserve(bro_ctx* ctx, uint64_t total_in_bytes, uint32_t n_streams) {
+    if (!ctx) return BRO_ST_InvalidArgument;
+    (void)n_streams;
+    ctx->reserved_in = total_in_bytes;
+    return BRO_ST_OK;
+}
+
+static int bro_grow(bro_ctx* ctx, void** p, size_t* cap, size_t need, size_t elem) {
+    if (*cap >= need) return BRO_ST_OK;
+    if (*p) { BRO_CUDA(ctx, cudaFree(*p)); *p = NULL; *cap = 0; }
+    size_t want = need + (need >> 3) + 1024;
+    BRO_CUDA(ctx, cudaMalloc(p, want * elem));
+    *cap = want;
+    return BRO_ST_OK;
+}
+
 extern "C" int bro_batch_decode(bro_ctx* ctx, const uint8_t* d_in, const uint64_t* d_in_off, uint8_t* d_out,
                                 const uint64_t* d_out_off, uint64_t* d_out_len, int32_t* d_status, uint32_t n,
                                 void* stream) {
@@ -122,8 +180,9 @@ extern "C" int bro_batch_decode(bro_ctx* ctx, const uint8_t* d_in, const uint64_
     if (n == 0) return BRO_ST_OK;
     if (!d_in_off || !d_out_off || !d_out_len || !d_status) return BRO_ST_InvalidArgument;
     cudaStream_t s = (cudaStream_t)stream;
-    BRO_CUDA(ctx, cudaMemsetAsync(ctx->d_counter, 0, 4 * sizeof(uint32_t), s));
+    BRO_CUDA(ctx, cudaMemsetAsync(ctx->d_counter, 0, 8 * sizeof(uint32_t), s));
     BroLaunch p;
+    memset(&p, 0, sizeof(p));
     p.in = d_in; p.in_off = d_in_off; p.out = d_out; p.out_off = d_out_off;
     p.out_len = d_out_len; p.status = d_status; p.n = n;
     p.dict = ctx->d_dict; p.quirk_spec = ctx->quirks;
@@ -131,35 +190,64 @@ extern "C" int bro_batch_decode(bro_ctx* ctx, const uint8_t* d_in, const uint64_
     const uint32_t wpc = (uint32_t)bro_warp_kernel_warps_per_cta();
     int grid_w = ctx->grid;
     if ((uint32_t)grid_w > (n + wpc - 1) / wpc) grid_w = (int)((n + wpc - 1) / wpc);
-    const bool use_threads = ctx->mode == BRO_MODE_THREAD || (ctx->mode == BRO_MODE_AUTO && n >= ctx->thread_threshold);
+    const bool two_phase = ctx->mode == BRO_MODE_TWOPHASE || (ctx->mode == BRO_MODE_AUTO && n >= ctx->twophase_threshold);
     cudaError_t e;
-    if (use_threads) {
-        // one THREAD per stream, streams handed out by compressed-size class (largest first); streams whose tables
-        // do not fit a thread arena are left for the warp kernel's retry pass
-        if (!ctx->d_arena_t)   // 64 KiB per resident thread (~5 GB on a B200), allocated on first use
-            BRO_CUDA(ctx, cudaMalloc(&ctx->d_arena_t, (size_t)ctx->num_threads * bro_thread_kernel_arena_bytes()));
-        if (ctx->d_order_cap < n) {
-            if (ctx->d_order) { BRO_CUDA(ctx, cudaFree(ctx->d_order)); ctx->d_order = NULL; ctx->d_order_cap = 0; }
-            size_t want = (size_t)n + (n >> 2) + 1024;
-            BRO_CUDA(ctx, cudaMalloc(&ctx->d_order, want * sizeof(uint32_t)));
-            ctx->d_order_cap = want;
+    if (two_phase) {
+        // PHASE ONE: one thread per stream (bro_parse_kernel), streams handed out by compressed-size class; literals and
+        // dictionary words go into the slots, copies become records.  PHASE TWO: one warp per stream executes the
+        // records (bro_copy_kernel).  Streams phase one cannot decode are left for the fused kernel's retry pass.
+        int st;
+        if (!ctx->d_arena_t)   // 64 KiB per resident thread, allocated on first use
+            BRO_CUDA(ctx, cudaMalloc(&ctx->d_arena_t, (size_t)ctx->num_threads * bro_parse_kernel_arena_bytes()));
+        if ((st = bro_grow(ctx, (void**)&ctx->d_order, &ctx->d_order_cap, (size_t)n, 2 * sizeof(uint32_t)))) return st;
+        // the record arena is sized from the compressed bytes of the batch: the caller's bound (bro_ctx_reserve), else
+        // the two end offsets are read back (16 bytes, blocking on `s`)
+        uint64_t total_in = ctx->reserved_in;
+        if (total_in == 0) {
+            uint64_t ends[2];
+            BRO_CUDA(ctx, cudaMemcpyAsync(&ends[0], d_in_off, sizeof(uint64_t), cudaMemcpyDeviceToHost, s));
+            BRO_CUDA(ctx, cudaMemcpyAsync(&ends[1], d_in_off + n, sizeof(uint64_t), cudaMemcpyDeviceToHost, s));
+            BRO_CUDA(ctx, cudaStreamSynchronize(s));
+            if (ends[1] < ends[0]) return BRO_ST_InvalidArgument;
+            total_in = ends[1] - ends[0];
         }
-        e = (cudaError_t)bro_order_launch(d_in_off, n, ctx->d_order, ctx->d_order_scratch, s);
+        const size_t rec_total = (size_t)(total_in >> 1) + 32u * (size_t)n;
+        if ((st = bro_grow(ctx, (void**)&ctx->d_rec, &ctx->d_rec_cap, rec_total, sizeof(BroRec)))) return st;
+        uint32_t* d_order = ctx->d_order;
+        if (ctx->timing) BRO_CUDA(ctx, cudaEventRecord(ctx->ev[0], s));
+        p.nrec = ctx->d_order + ctx->d_order_cap;
+        p.rec = ctx->d_rec; p.rec_total = ctx->d_rec_cap;
+        e = (cudaError_t)bro_order_launch(d_in_off, n, d_order, ctx->d_order_scratch, s);
         if (e != cudaSuccess) return bro_fail(ctx, e, "bro_order kernels launch");
         ctx->launches += 3;
-        const uint32_t tb = (uint32_t)bro_thread_kernel_block();
+        const uint32_t tb = (uint32_t)bro_parse_kernel_block();
         int grid_t = ctx->grid_t;
         if ((uint32_t)grid_t > (n + tb - 1) / tb) grid_t = (int)((n + tb - 1) / tb);
-        p.arena = ctx->d_arena_t; p.counter = ctx->d_counter; p.order = ctx->d_order;
-        e = (cudaError_t)bro_thread_kernel_launch(&p, grid_t, s);
-        if (e != cudaSuccess) return bro_fail(ctx, e, "bro_decode_thread_kernel launch");
+        p.arena = ctx->d_arena_t; p.counter = ctx->d_counter; p.order = d_order;
+        if (ctx->timing) BRO_CUDA(ctx, cudaEventRecord(ctx->ev[1], s));
+        e = (cudaError_t)bro_parse_kernel_launch(&p, grid_t, s);
+        if (e != cudaSuccess) return bro_fail(ctx, e, "bro_parse_kernel launch");
         ctx->launches += 1;
-        p.retry_mode = 1; p.order = NULL;
+        const uint32_t cw = (uint32_t)bro_copy_kernel_warps_per_cta();
+        int grid_c = ctx->grid_c;
+        if ((uint32_t)grid_c > (n + cw - 1) / cw) grid_c = (int)((n + cw - 1) / cw);
+        p.counter = ctx->d_counter + 3; p.order = NULL;
+        p.copy_stats = (unsigned long long*)(ctx->d_counter + 4);
+        if (ctx->timing) BRO_CUDA(ctx, cudaEventRecord(ctx->ev[2], s));
+        e = (cudaError_t)bro_copy_kernel_launch(&p, grid_c, s);
+        if (e != cudaSuccess) return bro_fail(ctx, e, "bro_copy_kernel launch");
+        ctx->launches += 1;
+        p.retry_mode = 1;
     }
     p.arena = ctx->d_arena; p.counter = ctx->d_counter + 1;
+    if (ctx->timing) BRO_CUDA(ctx, cudaEventRecord(ctx->ev[3], s));
     e = (cudaError_t)bro_warp_kernel_launch(&p, grid_w, s);
     if (e != cudaSuccess) return bro_fail(ctx, e, "bro_decode_warp_kernel launch");
     ctx->launches += 1;
+    if (ctx->timing) {
+        BRO_CUDA(ctx, cudaEventRecord(ctx->ev[4], s));
+        ctx->ev_valid = 1; ctx->ev_two_phase = two_phase ? 1 : 0;
+    }
     return BRO_ST_OK;
 }
 
@@ -196,7 +284,10 @@ extern "C" int bro_batch_decode_host(bro_ctx* ctx, const uint8_t* h_in, const ui
     BRO_CUDA(ctx, cudaMemcpyAsync(d_in_off, h_in_off, off_bytes, cudaMemcpyHostToDevice, s));
     BRO_CUDA(ctx, cudaMemcpyAsync(d_out_off, h_out_off, off_bytes, cudaMemcpyHostToDevice, s));
     // offsets are relative to the caller's buffers; rebase the device pointers instead of rewriting the arrays
+    const uint64_t reserved_saved = ctx->reserved_in;
+    ctx->reserved_in = in_bytes ? in_bytes : 1;        // known here: no read-back of the offsets
     st = bro_batch_decode(ctx, ctx->d_in - in_lo, d_in_off, ctx->d_out - out_lo, d_out_off, d_out_len, d_status, n, s);
+    ctx->reserved_in = reserved_saved;
     if (st) return st;
     if (out_bytes) BRO_CUDA(ctx, cudaMemcpyAsync(h_out + out_lo, ctx->d_out, out_bytes, cudaMemcpyDeviceToHost, s));
     BRO_CUDA(ctx, cudaMemcpyAsync(h_out_len, d_out_len, (size_t)n * sizeof(uint64_t), cudaMemcpyDeviceToHost, s));

@@ -25,6 +25,7 @@
 #pragma once
 #include <stdint.h>
 
+#include "bro_records.h"
 #include "bro_status.h"
 
 #if defined(BRO_HOSTSIM)
@@ -430,7 +431,22 @@ struct BroDec {
     BroScratch* sc;
     const uint8_t* dict;      // 122,784-byte static dictionary image
     int quirk_spec;
+#if defined(BRO_PARSE)
+    BroRec* rec;              // copy records of this stream (phase one of the two-phase path writes, phase two executes)
+    uint32_t nrec, rec_cap;
+    const uint8_t* in_base;   // first byte of the compressed stream (stored-block records hold offsets from it)
+#endif
 };
+
+#if defined(BRO_PARSE)
+BRO_FN bool bro_rec_push(BroDec& d, uint32_t dst, uint32_t len, uint32_t kind, uint32_t a) {
+    if (d.nrec >= d.rec_cap) return false;
+    BroRec r;
+    r.dst = dst; r.len_kind = len | (kind << BRO_REC_KIND_SHIFT); r.a = a; r.b = 0;
+    d.rec[d.nrec++] = r;
+    return true;
+}
+#endif
 
 // The fixed code of NBLTYPES / NTREES (src/lib.rs:126-132, 501-525): 0 -> 1, else 1 + (1 << n) + n extra bits
 // with n read from 3 bits.  Any failed bit read is UnexpectedEOF.
@@ -1144,6 +1160,14 @@ BRO_FN int bro_metablock_tables(BroDec& d, BroMbInfo& mb) {
                                            j == 0u ? cmap_l : cmap_d))) return st;
         }
         if (j == 0u) ntl = nt; else ntd = nt;
+#if defined(BRO_PARSE)
+        // Phase one of the two-phase path never sees the bytes copies produce, so it can decode a meta-block only if
+        // no block type's literal context map depends on the context; found out here, before the prefix codes
+        // (the bulk of the header) are read.
+        if (j == 0u && nt >= 2u)
+            for (uint32_t q = 0; q < 64u * cat[0].nbl; q++)
+                if (cmap_l[q] != cmap_l[q & ~63u]) return BRO_ST_NeedFused;
+#endif
     }
     // prefix codes (src/lib.rs:1016-1068): NTREESL literal codes, NBLTYPESI insert&copy codes, NTREESD distance codes
     const uint32_t dist_alphabet = 16u + ndirect + (48u << npostfix);
@@ -1374,8 +1398,12 @@ BRO_FN int bro_next_metablock(BroDec& d, bool after_last, uint32_t& is_last, uin
                 const uint8_t* a = bro_bits_addr(d.in);
                 if ((uint64_t)(d.in.end - a) < (uint64_t)mlen) return BRO_ST_UnexpectedEOF;
                 if (mlen > d.cap - d.pos) return BRO_ST_OutputTooSmall;
+#if defined(BRO_PARSE)
+                if (!bro_rec_push(d, d.pos, mlen, BRO_REC_STORED, (uint32_t)(a - d.in_base))) return BRO_ST_RecordsFull;
+#else
                 bro_syncwarp();
                 bro_copy_far(d.out + d.pos, a, mlen);
+#endif
                 d.pos += mlen;
                 d.p2 = mlen >= 2u ? a[mlen - 2] : d.p1;
                 d.p1 = a[mlen - 1];

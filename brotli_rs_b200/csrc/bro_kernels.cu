@@ -4,7 +4,8 @@
 // is exhausted, so streams of very different sizes (1 B .. hundreds of KB, 0 .. 65,537 meta-blocks) balance
 // themselves.  The decoder itself is bro_decoder_core.h (32-lane mode); this file provides the per-warp resources
 // (shared-memory scratch, a worst-case table arena in HBM) and the grid.  It serves small batches (lowest latency
-// per stream) and re-runs the streams the thread-per-stream kernel could not fit in its small arenas.
+// per stream) and, as the retry pass of the two-phase path, the streams the parse kernel hands over (literal context
+// modelling, tables larger than a thread arena, more copy records than the stream's share).
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -31,7 +32,7 @@ __global__ void __launch_bounds__(WARPS * 32, BRO_MIN_BLOCKS) bro_decode_warp_ke
         if (lane == 0) i = atomicAdd(p.counter, 1u);
         i = bro_shfl(i, 0);
         if (i >= p.n) break;
-        if (p.retry_mode && p.status[i] != BRO_ST_ArenaTooSmall) continue;
+        if (p.retry_mode && !BRO_ST_IS_RETRY(p.status[i])) continue;
         const uint64_t in_b = p.in_off[i], in_e = p.in_off[i + 1];
         const uint64_t out_b = p.out_off[i], out_e = p.out_off[i + 1];
         BroDec d;

@@ -4,6 +4,8 @@
 #include <stddef.h>
 #include <stdint.h>
 
+#include "bro_records.h"
+
 struct BroLaunch {
     const uint8_t* in;
     const uint64_t* in_off;
@@ -12,15 +14,23 @@ struct BroLaunch {
     uint64_t* out_len;
     int32_t* status;
     uint32_t n;
-    uint16_t* arena;          // warp kernel: num_warps * BRO_ARENA_U16_MAX; thread kernel: num_threads * BRO_THREAD_ARENA_U16
+    uint16_t* arena;          // warp kernel: num_warps * BRO_ARENA_U16_MAX; parse kernel: num_threads * thread arena
     const uint8_t* dict;      // 122,784-byte dictionary image in HBM
-    uint32_t* counter;        // work queue head, zeroed before every launch
-    const uint32_t* order;    // thread kernel: stream indices, largest compressed size first (NULL = identity)
-    uint32_t* retry_count;    // thread kernel increments it per ArenaTooSmall stream; the warp kernel in retry mode
-                              // decodes exactly the streams whose status is ArenaTooSmall (and exits at once if 0)
+    uint32_t* counter;        // work queue head of the kernel being launched, zeroed before every batch
+    const uint32_t* order;    // parse kernel: stream indices by compressed-size class, largest first (NULL = identity)
+    uint32_t* retry_count;    // parse kernel: +1 per stream it hands to the fused kernel (status ArenaTooSmall, NeedFused
+                              // or RecordsFull); the warp kernel in retry mode decodes exactly those (exits at once if 0)
     int retry_mode;
     int quirk_spec;
+    // two-phase path: copy records.  Stream i owns records [rec_base(i), rec_base(i+1)) of `rec`, where
+    // rec_base(i) = ((in_off[i] - in_off[0]) >> 1) + 32 * i; a stream whose share ends beyond rec_total, or that needs
+    // more, is handed to the fused kernel.
+    BroRec* rec;
+    uint64_t rec_total;
+    uint32_t* nrec;           // n: records written for stream i
+    unsigned long long* copy_stats;   // [0] bytes moved by records, [1] records executed (this batch)
 };
+
 
 // warp-per-stream kernel (bro_kernels.cu)
 extern "C" int bro_warp_kernel_occupancy(int* blocks_per_sm);
@@ -28,10 +38,15 @@ extern "C" int bro_warp_kernel_warps_per_cta();
 extern "C" size_t bro_warp_kernel_arena_bytes();
 extern "C" int bro_warp_kernel_launch(const BroLaunch* p, int grid, cudaStream_t stream);
 
-// thread-per-stream kernel and the size-class ordering kernels (bro_kernels_thread.cu)
-extern "C" int bro_thread_kernel_occupancy(int* blocks_per_sm);
-extern "C" int bro_thread_kernel_block();
-extern "C" size_t bro_thread_kernel_arena_bytes();
-extern "C" int bro_thread_kernel_launch(const BroLaunch* p, int grid, cudaStream_t stream);
+// two-phase path, phase one: the parse kernel (one thread per stream) and the size-class ordering kernels
+// (bro_kernels_parse.cu)
+extern "C" int bro_parse_kernel_occupancy(int* blocks_per_sm);
+extern "C" int bro_parse_kernel_block();
+extern "C" size_t bro_parse_kernel_arena_bytes();
+extern "C" int bro_parse_kernel_launch(const BroLaunch* p, int grid, cudaStream_t stream);
+// two-phase path, phase two: the copy kernel (one warp per stream) (bro_kernels_copy.cu)
+extern "C" int bro_copy_kernel_occupancy(int* blocks_per_sm);
+extern "C" int bro_copy_kernel_warps_per_cta();
+extern "C" int bro_copy_kernel_launch(const BroLaunch* p, int grid, cudaStream_t stream);
 // order[] <- stream indices grouped by compressed-size class, largest first.  scratch: 512 uint32.
 extern "C" int bro_order_launch(const uint64_t* in_off, uint32_t n, uint32_t* order, uint32_t* scratch, cudaStream_t stream);

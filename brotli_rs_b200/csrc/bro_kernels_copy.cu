@@ -1,0 +1,176 @@
+// bro_kernels_copy.cu -- PHASE TWO of the two-phase path for sm_100a: the copy kernel (one WARP per stream).
+//
+// Input: the copy records phase one wrote for a stream (bro_parse.h), in stream order: LZ77 back-references into the
+// output produced so far (src/lib.rs:1483-1505; the ring buffer of src/ringbuffer/mod.rs is the linear output slot
+// itself) and stored meta-blocks (src/lib.rs:1701-1734).  Literals and dictionary words are already in the slot.
+//
+// The records of a stream must take effect in order, but most neighbours do not depend on each other.  The warp loads
+// 32 records at a time (one per lane, coalesced) and splits them into GROUPS: a maximal run of records none of which
+// reads a byte that a record of the same run writes.  A group is executed as ONE segmented copy: the bytes of all its
+// records are cut into units (16-byte vector units on 16-byte aligned destinations, single bytes for the ragged
+// ends), the units are numbered by a warp prefix sum, and every lane takes every 32nd unit, finding its record by a
+// binary search over the prefix sums with shuffles.  All 32 lanes therefore move data in every step whatever the
+// record lengths are, all loads of a step are independent, and the only serialisation left is between groups.
+// A record that overlaps its own source (distance < length, a periodic fill) is executed alone by doubling: each pass
+// copies the whole pattern laid down so far.
+//
+// Roofline: HBM.  Algorithmic bytes per stream = output bytes written by records + 16 bytes per record read; sources
+// are re-reads of recent output (L2 hits for windows that fit).
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "bro_decoder_core.h"
+#include "bro_kernels.h"
+
+#ifndef BRO_COPY_WARPS
+#define BRO_COPY_WARPS 8
+#endif
+#ifndef BRO_COPY_MIN_BLOCKS
+#define BRO_COPY_MIN_BLOCKS 6
+#endif
+
+// 16 bytes from an arbitrary address: two aligned 16-byte loads and a funnel (the bytes before/after the 16 wanted
+// ones lie in the same 16-byte granules as wanted bytes, i.e. inside the same allocation)
+__device__ __forceinline__ uint4 bro_ldu16(const uint8_t* p) {
+    const uintptr_t a = (uintptr_t)p;
+    const uint4* q = (const uint4*)(a & ~(uintptr_t)15);
+    const unsigned sh = (unsigned)(a & 15u);
+    uint4 A = q[0];
+    if (sh == 0u) return A;
+    const uint4 B = q[1];
+    uint32_t w0 = A.x, w1 = A.y, w2 = A.z, w3 = A.w, w4 = B.x, w5 = B.y, w6 = B.z, w7 = B.w;
+    if (sh & 8u) { w0 = w2; w1 = w3; w2 = w4; w3 = w5; w4 = w6; w5 = w7; }
+    if (sh & 4u) { w0 = w1; w1 = w2; w2 = w3; w3 = w4; w4 = w5; }
+    const unsigned bs = 8u * (sh & 3u);
+    uint4 r;
+    r.x = __funnelshift_r(w0, w1, bs); r.y = __funnelshift_r(w1, w2, bs);
+    r.z = __funnelshift_r(w2, w3, bs); r.w = __funnelshift_r(w3, w4, bs);
+    return r;
+}
+
+// One record on its own, by the whole warp: dst[0..n) = src[0..n), no overlap.
+__device__ __forceinline__ void bro_warp_copy(uint8_t* dst, const uint8_t* src, uint32_t n, unsigned lane) {
+    uint32_t head = (uint32_t)((16u - ((uintptr_t)dst & 15u)) & 15u);
+    if (head > n) head = n;
+    if (lane < head) dst[lane] = src[lane];
+    dst += head; src += head; n -= head;
+    const uint32_t nv = n >> 4;
+    for (uint32_t v = lane; v < nv; v += 32u) *(uint4*)(dst + 16u * v) = bro_ldu16(src + 16u * v);
+    const uint32_t done = nv << 4;
+    if (done + lane < n) dst[done + lane] = src[done + lane];
+}
+
+template <int WARPS>
+__global__ void __launch_bounds__(WARPS * 32, BRO_COPY_MIN_BLOCKS) bro_copy_kernel(BroLaunch p) {
+    const unsigned lane = threadIdx.x & 31u;
+    for (;;) {
+        uint32_t i = 0;
+        if (lane == 0) i = atomicAdd(p.counter, 1u);
+        i = __shfl_sync(0xffffffffu, i, 0);
+        if (i >= p.n) break;
+        if (p.status[i] != BRO_ST_OK) continue;       // bytes of a failed stream are not part of the contract
+        const uint32_t n = p.nrec[i];
+        if (n == 0u) continue;
+        const uint64_t in_b = p.in_off[i];
+        const BroRec* recs = p.rec + BRO_REC_BASE(p.in_off, i);
+        uint8_t* const out = p.out + p.out_off[i];
+        const uint8_t* const in = p.in + in_b;
+        const uint32_t out_mis = (uint32_t)((uintptr_t)out & 15u);   // destination alignment is that of the address
+        unsigned long long moved = 0;                                // bytes this lane's records move (measurement)
+        for (uint32_t b = 0; b < n; b += 32u) {
+            const uint32_t cnt = n - b < 32u ? n - b : 32u;
+            uint32_t dst = 0, lk = 0, a = 0;
+            if (lane < cnt) {
+                const uint4 r = __ldg((const uint4*)(recs + b + lane));
+                dst = r.x; lk = r.y; a = r.z;
+            }
+            const uint32_t len = lk & BRO_REC_LEN_MASK, kind = lk >> BRO_REC_KIND_SHIFT;
+            moved += len;
+            uint32_t j = 0;
+            while (j < cnt) {
+                // the group [j, e): no record reads what a record of the group writes
+                const uint32_t dst_j = __shfl_sync(0xffffffffu, dst, j);
+                const bool indep = lane >= j && lane < cnt && (kind == BRO_REC_STORED || (dst - a) + len <= dst_j);
+                const uint32_t fail = ~__ballot_sync(0xffffffffu, indep) & (0xffffffffu << j);
+                const uint32_t e = fail ? (uint32_t)__ffs(fail) - 1u : 32u;
+                __syncwarp();      // stores of earlier groups are visible to the loads below
+                if (e == j) {
+                    // a record that overlaps its own source: periodic fill by doubling
+                    const uint32_t dj = dst_j, lj = __shfl_sync(0xffffffffu, len, j), aj = __shfl_sync(0xffffffffu, a, j);
+                    uint32_t done = 0;
+                    while (done < lj) {
+                        uint32_t m = done + aj;                    // bytes of pattern laid down so far
+                        if (m > lj - done) m = lj - done;
+                        bro_warp_copy(out + dj + done, out + dj - aj, m, lane);
+                        done += m;
+                        __syncwarp();
+                    }
+                    j += 1u;
+                    continue;
+                }
+                // units of my record: head bytes up to the next 16-byte boundary, 16-byte vectors, tail bytes
+                const bool mine = lane >= j && lane < e;
+                uint32_t head = (16u - ((dst + out_mis) & 15u)) & 15u;
+                if (head > len) head = len;
+                const uint32_t nvec = (len - head) >> 4, tail = (len - head) & 15u;
+                const uint32_t units = mine ? head + nvec + tail : 0u;
+                uint32_t incl = units;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o);
+                    if ((int)lane >= o) incl += v;
+                }
+                const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
+                for (uint32_t u0 = 0; u0 < total; u0 += 32u) {
+                    const uint32_t u = u0 + lane;
+                    // smallest k with incl[k] > u
+                    uint32_t k = 0;
+#pragma unroll
+                    for (int s = 16; s >= 1; s >>= 1) {
+                        const uint32_t v = __shfl_sync(0xffffffffu, incl, (int)(k + s - 1u));
+                        if (v <= u) k += (uint32_t)s;
+                    }
+                    const int ks = (int)(k & 31u);
+                    const uint32_t r_dst = __shfl_sync(0xffffffffu, dst, ks), r_lk = __shfl_sync(0xffffffffu, lk, ks);
+                    const uint32_t r_a = __shfl_sync(0xffffffffu, a, ks), r_end = __shfl_sync(0xffffffffu, incl, ks);
+                    if (u < total) {
+                        const uint32_t r_len = r_lk & BRO_REC_LEN_MASK, r_kind = r_lk >> BRO_REC_KIND_SHIFT;
+                        uint32_t r_head = (16u - ((r_dst + out_mis) & 15u)) & 15u;
+                        if (r_head > r_len) r_head = r_len;
+                        const uint32_t r_nvec = (r_len - r_head) >> 4;
+                        const uint32_t r_units = r_head + r_nvec + ((r_len - r_head) & 15u);
+                        const uint32_t ul = u - (r_end - r_units);         // unit index inside the record
+                        uint32_t off;                                      // byte offset inside the record
+                        bool vec = false;
+                        if (ul < r_head) off = ul;
+                        else if (ul < r_head + r_nvec) { off = r_head + 16u * (ul - r_head); vec = true; }
+                        else off = r_head + 16u * r_nvec + (ul - r_head - r_nvec);
+                        const uint8_t* src = r_kind == BRO_REC_STORED ? in + r_a + off : out + (r_dst - r_a) + off;
+                        uint8_t* dp = out + r_dst + off;
+                        if (vec) *(uint4*)dp = bro_ldu16(src);
+                        else *dp = *src;
+                    }
+                }
+                j = e;
+            }
+        }
+        // what the roofline of this kernel is computed from: record bytes moved and records read (bench.py)
+#pragma unroll
+        for (int o = 16; o >= 1; o >>= 1) moved += __shfl_xor_sync(0xffffffffu, moved, o);
+        if (lane == 0) {
+            atomicAdd(p.copy_stats, moved);
+            atomicAdd(p.copy_stats + 1, (unsigned long long)n);
+        }
+    }
+}
+
+extern "C" int bro_copy_kernel_occupancy(int* blocks_per_sm) {
+    return (int)cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, bro_copy_kernel<BRO_COPY_WARPS>,
+                                                              BRO_COPY_WARPS * 32, 0);
+}
+extern "C" int bro_copy_kernel_warps_per_cta() { return BRO_COPY_WARPS; }
+
+extern "C" int bro_copy_kernel_launch(const BroLaunch* p, int grid, cudaStream_t stream) {
+    bro_copy_kernel<BRO_COPY_WARPS><<<grid, BRO_COPY_WARPS * 32, 0, stream>>>(*p);
+    return (int)cudaGetLastError();
+}

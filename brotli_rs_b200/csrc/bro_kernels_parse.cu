@@ -1,0 +1,153 @@
+// bro_kernels_parse.cu -- PHASE ONE of the two-phase path for sm_100a: the parse kernel (one THREAD per stream) and
+// the size-class ordering kernels that feed it.
+//
+// Every lane of a warp owns a different stream and runs the flat state machine of bro_parse.h: one trip decodes one
+// prefix-code symbol of whatever kind the lane needs next, so 32 streams advance per warp instruction on the
+// expensive part of the decode.  Literals and dictionary words go straight into the output slots; LZ77
+// back-references and stored meta-blocks become BroRec records for the copy kernel (bro_kernels_copy.cu).
+//
+// Meta-block headers (prefix codes, context maps: long structured code, bro_decoder_core.h with a 1-lane "warp") are
+// entered by the lanes of a warp TOGETHER: a lane that reaches a meta-block boundary waits (up to BRO_PARSE_PATIENCE
+// trips of the others) until every lane is at a boundary, and lanes whose stream ended pull their next stream at the
+// same moment.  Streams are handed out by compressed-size class, so the lanes of a warp hold similar streams.
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#define BRO_THREAD_MODE 1
+#define BRO_PARSE 1
+#include "bro_parse.h"
+#include "bro_kernels.h"
+
+#ifndef BRO_PARSE_BLOCK
+#define BRO_PARSE_BLOCK 128
+#endif
+#ifndef BRO_PARSE_MIN_BLOCKS
+#define BRO_PARSE_MIN_BLOCKS 4
+#endif
+#ifndef BRO_PARSE_PATIENCE
+#define BRO_PARSE_PATIENCE 1024u
+#endif
+#define BRO_SCRATCH_U16 ((sizeof(BroScratch) / 2u + 7u) & ~7u)
+// the stride is an odd number of 128-byte lines, so that the threads' root tables do not pile into a few cache sets
+#define BRO_THREAD_ARENA_STRIDE_U16 (BRO_THREAD_ARENA_U16 + 704u)
+
+__global__ void __launch_bounds__(BRO_PARSE_BLOCK, BRO_PARSE_MIN_BLOCKS) bro_parse_kernel(BroLaunch p) {
+    const unsigned t = blockIdx.x * BRO_PARSE_BLOCK + threadIdx.x;
+    const unsigned lane = threadIdx.x & 31u;
+    uint16_t* const arena = p.arena + (size_t)t * BRO_THREAD_ARENA_STRIDE_U16;
+    BroDec d;
+    BroParse ps;
+    BroMbInfo mb;
+    uint32_t stream = 0;
+    uint32_t waited = 0;          // warp-uniform: trips since the first lane reached a boundary
+    bool exhausted = false;       // warp-uniform: the queue is empty
+    ps.kind = BRO_K_DONE; ps.st = -1;   // st < 0: no stream to report
+    d.sc = (BroScratch*)arena;
+    d.arena = arena;
+    d.arena_cap = BRO_THREAD_ARENA_U16;
+    d.arena_base = BRO_SCRATCH_U16;
+    d.dict = p.dict;
+    d.quirk_spec = p.quirk_spec;
+    for (;;) {
+        const uint32_t at_boundary = __ballot_sync(0xffffffffu, ps.kind >= BRO_K_HEADER);
+        if (at_boundary != 0u) {
+            waited++;
+            if (at_boundary == 0xffffffffu || waited > BRO_PARSE_PATIENCE) {
+                waited = 0;
+                // lanes whose stream ended report it and pull the next one
+                if (ps.kind == BRO_K_DONE && ps.st >= 0) {
+                    p.status[stream] = ps.st;
+                    p.out_len[stream] = d.pos;
+                    p.nrec[stream] = d.nrec;
+                    if (BRO_ST_IS_RETRY(ps.st)) atomicAdd(p.retry_count, 1u);
+                    ps.st = -1;
+                }
+                const uint32_t idle = __ballot_sync(0xffffffffu, ps.kind == BRO_K_DONE);
+                if (idle != 0u && !exhausted) {
+                    const int leader = __ffs(idle) - 1;
+                    uint32_t base = 0;
+                    if ((int)lane == leader) base = atomicAdd(p.counter, (uint32_t)__popc(idle));
+                    base = __shfl_sync(0xffffffffu, base, leader);
+                    if (base + (uint32_t)__popc(idle) >= p.n) exhausted = true;
+                    if (ps.kind == BRO_K_DONE) {
+                        const uint32_t k = base + (uint32_t)__popc(idle & ((1u << lane) - 1u));
+                        if (k < p.n) {
+                            stream = p.order ? p.order[k] : k;
+                            const uint64_t in_b = p.in_off[stream], in_e = p.in_off[stream + 1];
+                            const uint64_t out_b = p.out_off[stream], out_e = p.out_off[stream + 1];
+                            d.out = p.out + out_b;
+                            const uint64_t cap = out_e - out_b;
+                            d.cap = cap > BRO_MAX_SLOT ? (uint32_t)BRO_MAX_SLOT : (uint32_t)cap;
+                            d.pos = 0;
+                            d.p1 = 0; d.p2 = 0;
+                            d.d0 = 4; d.d1 = 11; d.d2 = 15; d.d3 = 16;   // src/lib.rs:407-408
+                            // this stream's share of the record arena: one record per 2 compressed bytes + 32
+                            const uint64_t rec_b = BRO_REC_BASE(p.in_off, stream);
+                            const uint64_t rec_n = BRO_REC_BASE(p.in_off, stream + 1) - rec_b;
+                            d.rec = p.rec + rec_b; d.nrec = 0; d.in_base = p.in + in_b;
+                            d.rec_cap = rec_n > 0x0fffffffull ? 0x0fffffffu : (uint32_t)rec_n;
+                            bro_bits_init(d.in, p.in + in_b, p.in + in_e);
+                            bro_parse_begin(ps);
+                            if (rec_b + rec_n > p.rec_total) bro_parse_finish(ps, BRO_ST_RecordsFull);
+                        }
+                    }
+                }
+                if (__all_sync(0xffffffffu, ps.kind == BRO_K_DONE && ps.st < 0)) break;
+                if (ps.kind == BRO_K_HEADER) bro_parse_header(d, ps, mb);
+            }
+        } else waited = 0;
+        if (ps.kind < BRO_K_HEADER) bro_parse_step(d, ps, mb);
+    }
+}
+
+// ---- size-class ordering: 256 classes (8 per power of two of the compressed size), largest class first ----
+__device__ __forceinline__ uint32_t bro_size_class(uint64_t len) {
+    uint32_t l = len > 0xffffffffull ? 0xffffffffu : (uint32_t)len;
+    uint32_t b = l ? 31u - (uint32_t)__clz(l) : 0u;
+    uint32_t sub = b >= 3u ? (l >> (b - 3u)) & 7u : 0u;
+    return 255u - (b * 8u + sub);
+}
+
+__global__ void bro_order_hist_kernel(const uint64_t* in_off, uint32_t n, uint32_t* hist) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) atomicAdd(&hist[bro_size_class(in_off[i + 1] - in_off[i])], 1u);
+}
+
+__global__ void bro_order_scan_kernel(const uint32_t* hist, uint32_t* cursor) {
+    __shared__ uint32_t s[256];
+    uint32_t t = threadIdx.x;
+    s[t] = hist[t];
+    __syncthreads();
+    if (t == 0) {
+        uint32_t run = 0;
+        for (int k = 0; k < 256; k++) { uint32_t c = s[k]; s[k] = run; run += c; }
+    }
+    __syncthreads();
+    cursor[t] = s[t];
+}
+
+__global__ void bro_order_scatter_kernel(const uint64_t* in_off, uint32_t n, uint32_t* cursor, uint32_t* order) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) order[atomicAdd(&cursor[bro_size_class(in_off[i + 1] - in_off[i])], 1u)] = i;
+}
+
+extern "C" int bro_order_launch(const uint64_t* in_off, uint32_t n, uint32_t* order, uint32_t* scratch, cudaStream_t stream) {
+    cudaError_t e = cudaMemsetAsync(scratch, 0, 512 * sizeof(uint32_t), stream);
+    if (e != cudaSuccess) return (int)e;
+    uint32_t blocks = (n + 255u) / 256u;
+    bro_order_hist_kernel<<<blocks, 256, 0, stream>>>(in_off, n, scratch);
+    bro_order_scan_kernel<<<1, 256, 0, stream>>>(scratch, scratch + 256);
+    bro_order_scatter_kernel<<<blocks, 256, 0, stream>>>(in_off, n, scratch + 256, order);
+    return (int)cudaGetLastError();
+}
+
+extern "C" int bro_parse_kernel_occupancy(int* blocks_per_sm) {
+    return (int)cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, bro_parse_kernel, BRO_PARSE_BLOCK, 0);
+}
+extern "C" int bro_parse_kernel_block() { return BRO_PARSE_BLOCK; }
+extern "C" size_t bro_parse_kernel_arena_bytes() { return 2u * (size_t)BRO_THREAD_ARENA_STRIDE_U16; }
+
+extern "C" int bro_parse_kernel_launch(const BroLaunch* p, int grid, cudaStream_t stream) {
+    bro_parse_kernel<<<grid, BRO_PARSE_BLOCK, 0, stream>>>(*p);
+    return (int)cudaGetLastError();
+}

@@ -32,4 +32,9 @@
 #define BRO_ST_CudaError 101           /* a CUDA runtime call failed (host-side entry points only) */
 #define BRO_ST_PanicUppercaseZero 102  /* the reference reaches unreachable!() at src/transformation/mod.rs:78 */
 #define BRO_ST_InvalidArgument 104
-#define BRO_ST_ArenaTooSmall 105      /* internal: meta-block needs more table space than a thread arena; re-run by the warp kernel */
+/* internal: set by the two-phase path (parse kernel) for streams it hands to the fused warp kernel's retry pass; never
+ * visible to a caller */
+#define BRO_ST_ArenaTooSmall 105      /* meta-block needs more table space than a parse-thread arena */
+#define BRO_ST_NeedFused 106          /* literal context modelling needs the bytes of copies not yet materialised */
+#define BRO_ST_RecordsFull 107        /* more copy records than the stream's share of the record arena */
+#define BRO_ST_IS_RETRY(st) ((st) >= BRO_ST_ArenaTooSmall && (st) <= BRO_ST_RecordsFull)

@@ -11,8 +11,8 @@
  *   Decompressor::new(r)            src/lib.rs:398-410    bro_reader_new
  *   <Decompressor as Read>::read    src/lib.rs:2173-2193  bro_reader_read
  *   Decompressor::decompress        src/lib.rs:1545-2170  bro_batch_decode / bro_batch_decode_host
- *                                                         (the whole state machine runs on the GPU, one warp
- *                                                          per stream, many streams per launch)
+ *                                                         (the whole state machine runs on the GPU, many
+ *                                                          streams per call)
  *   DecompressorError + description src/lib.rs:294-357    int32 status + bro_status_description
  *   drop(Decompressor)                                    bro_reader_free
  *
@@ -50,13 +50,19 @@ typedef struct bro_reader bro_reader; /* the Read-struct: one compressed stream,
 int bro_ctx_create(bro_ctx** ctx, int device);
 void bro_ctx_destroy(bro_ctx* ctx);
 int bro_ctx_set_quirks(bro_ctx* ctx, int quirks);
-/* Kernel selection.  WARP: one warp per stream (the production kernel, also the retry pass).  THREAD: one thread per
- * stream with small table arenas, streams ordered by size class; experimental (DESIGN.md has the measurements).
- * AUTO (default) currently always selects WARP.  The environment variable BRO_B200_MODE=warp|thread sets the
- * initial mode. */
+/* Path selection.
+ *   WARP:     one fused kernel, one warp per stream (entropy decode and copies interleaved per command).  Lowest
+ *             latency for a few streams; also the retry pass of the two-phase path.
+ *   TWOPHASE: phase one decodes the entropy-coded commands with one THREAD per stream (32 streams per warp) and turns
+ *             every LZ77 copy into a record; phase two executes the records with one warp per stream at memory speed.
+ *             Streams phase one cannot decode (literal context modelling, libbrotli quality >= 10) are re-run by the
+ *             fused kernel inside the same call.
+ *   AUTO (default): TWOPHASE for batches with at least as many streams as the GPU has resident decoder warps
+ *             (bro_ctx_num_warps), WARP below.
+ * The environment variable BRO_B200_MODE=warp|twophase sets the initial mode. */
 #define BRO_MODE_AUTO 0
 #define BRO_MODE_WARP 1
-#define BRO_MODE_THREAD 2
+#define BRO_MODE_TWOPHASE 2
 int bro_ctx_set_mode(bro_ctx* ctx, int mode);
 const char* bro_ctx_last_cuda_error(const bro_ctx* ctx);
 /* Number of kernel launches issued through this context so far (bench.py's gpu_launches). */
@@ -64,7 +70,22 @@ uint64_t bro_ctx_launch_count(const bro_ctx* ctx);
 /* Resident decoder warps per launch (one stream per warp at a time). */
 uint32_t bro_ctx_num_warps(const bro_ctx* ctx);
 
-/* THE HOT PATH.  Decode n independent streams in one launch; everything is device memory.
+/* Measurement support (bench.py's roofline): with timing on, every bro_batch_decode records CUDA events around its
+ * kernels on the launching stream; bro_ctx_last_kernel_ms waits for the last batch and returns the durations in ms of
+ * {ordering kernels, parse kernel, copy kernel, fused warp kernel} (0 for kernels the batch did not launch). */
+int bro_ctx_set_timing(bro_ctx* ctx, int on);
+int bro_ctx_last_kernel_ms(bro_ctx* ctx, float* ms4);
+/* Counters of the last batch (synchronises the device): {bytes moved by copy records, copy records executed, streams
+ * handed to the fused kernel's retry pass, reserved}. */
+int bro_ctx_last_batch_stats(bro_ctx* ctx, uint64_t* stats4);
+
+/* Optional: an upper bound on the compressed bytes (d_in_off[n] - d_in_off[0]) of the batches that follow, until changed
+ * (0 = forget).  The two-phase path sizes its copy-record arena from it; without it bro_batch_decode reads the two end
+ * offsets back from the device (16 bytes, blocking on the stream) before it launches.  A bound that turns out too small
+ * costs speed only: streams whose records do not fit are decoded by the fused kernel. */
+int bro_ctx_reserve(bro_ctx* ctx, uint64_t total_in_bytes, uint32_t n_streams);
+
+/* THE HOT PATH.  Decode n independent streams in one call; everything is device memory.
  *   d_in       concatenated compressed streams
  *   d_in_off   n+1 byte offsets into d_in (stream i = [d_in_off[i], d_in_off[i+1]))
  *   d_out      output buffer; stream i owns the slot [d_out_off[i], d_out_off[i+1])

@@ -17,8 +17,9 @@ _LIBS = {}
 def _build(asan):
     os.makedirs(BUILD, exist_ok=True)
     so = os.path.join(BUILD, "libbro_hostsim_asan.so" if asan else "libbro_hostsim.so")
-    srcs = [os.path.join(CSRC, "bro_hostsim.cpp"), os.path.join(ROOT, "oracle", "dict_blob.c")]
-    deps = srcs + [os.path.join(CSRC, f) for f in ("bro_decoder_core.h", "bro_status.h", "bro_tables_generated.h")]
+    srcs = [os.path.join(CSRC, "bro_hostsim.cpp"), os.path.join(CSRC, "bro_hostsim_parse.cpp"),
+            os.path.join(ROOT, "oracle", "dict_blob.c")]
+    deps = srcs + [os.path.join(CSRC, f) for f in ("bro_decoder_core.h", "bro_parse.h", "bro_records.h", "bro_status.h", "bro_tables_generated.h")]
     if os.path.exists(so) and all(os.path.getmtime(so) >= os.path.getmtime(d) for d in deps):
         return so
     flags = ["-O1", "-g", "-fsanitize=address,undefined", "-fno-sanitize-recover=undefined"] if asan else ["-O2"]
@@ -34,11 +35,18 @@ def lib(asan=False):
         L.bro_hostsim_decode.restype = ctypes.c_int
         L.bro_hostsim_decode.argtypes = [ctypes.c_char_p, ctypes.c_size_t, ctypes.c_char_p, ctypes.c_size_t,
                                          ctypes.POINTER(ctypes.c_size_t), ctypes.c_int, ctypes.c_uint]
+        L.bro_hostsim_parse_decode.restype = ctypes.c_int
+        L.bro_hostsim_parse_decode.argtypes = [ctypes.c_char_p, ctypes.c_size_t, ctypes.c_char_p, ctypes.c_size_t,
+                                               ctypes.POINTER(ctypes.c_size_t), ctypes.c_int, ctypes.c_uint, ctypes.c_uint,
+                                               ctypes.POINTER(ctypes.c_uint), ctypes.POINTER(ctypes.c_uint)]
         _LIBS[asan] = L
     return _LIBS[asan]
 
 
 ARENA_TOO_SMALL = 105
+NEED_FUSED = 106
+RECORDS_FULL = 107
+RETRY = (ARENA_TOO_SMALL, NEED_FUSED, RECORDS_FULL)
 
 
 def decode(data: bytes, cap: int = 1 << 20, quirks: int = 0, arena_u16: int = 0):
@@ -51,3 +59,15 @@ def decode(data: bytes, cap: int = 1 << 20, quirks: int = 0, arena_u16: int = 0)
 
 def thread_arena_u16():
     return lib().bro_hostsim_thread_arena_u16()
+
+
+def parse_decode(data: bytes, cap: int = 1 << 20, quirks: int = 0, arena_u16: int = 0, rec_cap: int = 0, asan=False):
+    """The two-phase path: phase one = the parse kernel's per-lane code (flat state machine), phase two = a byte loop
+    over its copy records.  -> (status, bytes, records, machine trips); status may be one of RETRY, which the product
+    answers by re-running the stream with the fused warp kernel."""
+    out = ctypes.create_string_buffer(max(cap, 1))
+    n = ctypes.c_size_t()
+    nrec, steps = ctypes.c_uint(), ctypes.c_uint()
+    st = lib(asan).bro_hostsim_parse_decode(data, len(data), out, cap, ctypes.byref(n), quirks, arena_u16, rec_cap,
+                                            ctypes.byref(nrec), ctypes.byref(steps))
+    return st, out.raw[: n.value], nrec.value, steps.value

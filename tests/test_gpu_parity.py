@@ -15,14 +15,14 @@ from oracle import oracle
 pytestmark = pytest.mark.gpu
 
 
-@pytest.fixture(scope="module", params=["warp", "thread"])
+@pytest.fixture(scope="module", params=["warp", "twophase"])
 def dec(request):
-    """Every parity test runs against both kernels: warp-per-stream (small batches, retry pass) and
-    thread-per-stream (large batches)."""
+    """Every parity test runs against both paths: the fused warp-per-stream kernel (small batches, retry pass) and
+    the two-phase path (parse kernel, copy kernel, fused retry pass; large batches)."""
     import torch
     assert torch.cuda.is_available()
     from brotli_rs_b200 import BatchDecoder
-    d = BatchDecoder(0, mode=BatchDecoder.MODE_WARP if request.param == "warp" else BatchDecoder.MODE_THREAD)
+    d = BatchDecoder(0, mode=BatchDecoder.MODE_WARP if request.param == "warp" else BatchDecoder.MODE_TWOPHASE)
     yield d
     d.close()
 
@@ -284,9 +284,10 @@ def test_config_c4_c5_samples(dec):
     assert total == 16 * 64 * (262144 + 10000 + 10000)
 
 
-def test_thread_arena_overflow_is_retried_by_warp_kernel(dec):
-    """streams whose meta-blocks need more table space than a thread's 64 KiB arena (many block types / trees) are
-    finished by the warp kernel's retry pass; the caller never sees the internal ArenaTooSmall status"""
+def test_parse_handover_is_retried_by_warp_kernel(dec):
+    """streams the parse kernel hands over -- meta-blocks that need more table space than a thread's 64 KiB arena (many
+    block types / trees), literal context modelling, more copies than the record share -- are finished by the fused
+    kernel's retry pass; the caller never sees the internal statuses"""
     enc = fuzzgen.libbrotli_enc()
     if enc is None:
         pytest.skip("system libbrotlienc not present")
@@ -314,17 +315,52 @@ def test_thread_arena_overflow_is_retried_by_warp_kernel(dec):
 
 
 def test_auto_mode_launch_counts():
-    """default mode decodes any batch with ONE launch of the warp kernel; thread mode takes 3 ordering kernels, the
-    thread kernel and the warp kernel's retry pass"""
+    """default mode decodes a small batch with ONE launch of the warp kernel and a large one by the two-phase path:
+    3 ordering kernels, the parse kernel, the copy kernel and the fused kernel's retry pass"""
     from brotli_rs_b200 import BatchDecoder
     files = [f for f in corpus_files() if f[2] is not None and len(f[1]) < 2000]
     streams = [c for _, c, _ in files] * 100
     exps = [e for _, _, e in files] * 100
-    for mode, want in ((None, 1), (BatchDecoder.MODE_THREAD, 5)):
+    for mode, reps, want in ((None, 1, 1), (BatchDecoder.MODE_TWOPHASE, 1, 6), (None, 8, 6)):
         d = BatchDecoder(0, mode=mode)
+        assert len(streams) < d.num_warps <= len(streams) * 8
         before = d.launch_count
-        res = d.decode_streams(streams, [len(e) for e in exps])
+        res = d.decode_streams(streams * reps, [len(e) for e in exps] * reps)
         assert d.launch_count - before == want
-        for (st, out), e in zip(res, exps):
+        for (st, out), e in zip(res, exps * reps):
             assert st == 0 and out == e
         d.close()
+
+
+def test_device_path_without_reservation():
+    """bro_batch_decode without bro_ctx_reserve sizes the record arena by reading the end offsets back; with a bound
+    that is too small the affected streams are decoded by the fused kernel -- same results either way"""
+    import ctypes
+    import torch
+    from brotli_rs_b200 import BatchDecoder
+    from brotli_rs_b200.batch import pack_streams, slot_offsets
+    enc = fuzzgen.libbrotli_enc()
+    if enc is None:
+        pytest.skip("system libbrotlienc not present")
+    raws = [fuzzgen.synthetic_raw("repeat2k", 40 + i, 65536) for i in range(48)]
+    streams = [fuzzgen.compress(enc, r, 5, 16) for r in raws]
+    in_buf, in_off = pack_streams(streams)
+    out_off = slot_offsets([len(r) for r in raws])
+    d = BatchDecoder(0, mode=BatchDecoder.MODE_TWOPHASE)
+    for bound in (0, 64):
+        d_in = torch.from_numpy(in_buf.copy()).cuda()
+        d_in_off = torch.from_numpy(in_off.astype(np.int64)).cuda()
+        d_out_off = torch.from_numpy(out_off.astype(np.int64)).cuda()
+        d_out = torch.zeros(int(out_off[-1]), dtype=torch.uint8, device="cuda")
+        d_len = torch.empty(len(streams), dtype=torch.int64, device="cuda")
+        d_st = torch.empty(len(streams), dtype=torch.int32, device="cuda")
+        d._check(d._lib.bro_ctx_reserve(d._ctx, bound, len(streams)))
+        d._check(d._lib.bro_batch_decode(d._ctx, d_in.data_ptr(), d_in_off.data_ptr(), d_out.data_ptr(), d_out_off.data_ptr(),
+                                         d_len.data_ptr(), d_st.data_ptr(), len(streams),
+                                         ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)))
+        torch.cuda.synchronize()
+        out = d_out.cpu().numpy()
+        assert (d_st.cpu().numpy() == 0).all()
+        for i, r in enumerate(raws):
+            assert out[int(out_off[i]): int(out_off[i]) + len(r)].tobytes() == r, (bound, i)
+    d.close()

@@ -63,3 +63,81 @@ def test_quirk_vectors():
             st, out = oracle.decode(s, quirks=quirks)
             st1, out1 = hostsim.decode(s, cap=1024, quirks=quirks)
             assert st1 == st and (st != 0 or out1 == out), (hx, quirks, st, st1)
+
+
+# ---- the two-phase path: phase one's flat state machine (bro_parse.h) + a byte loop over its copy records ----
+
+def _parse_check(stream, cap, want_st, want_out, label):
+    st1, out1, nrec, steps = hostsim.parse_decode(stream, cap=cap)
+    if st1 in hostsim.RETRY:
+        return False           # the product re-runs such a stream with the fused warp kernel
+    assert st1 == want_st and (want_st != 0 or out1 == want_out), (label, want_st, st1, nrec, steps)
+    return True
+
+
+def test_parse_corpus_and_vectors():
+    handled = 0
+    for name, comp, _ in corpus_files():
+        st, out = oracle.decode(comp)
+        handled += _parse_check(comp, len(out), st, out, name)
+    for name, inp, _, _ in stream_vectors():
+        st, out = oracle.decode(inp)
+        handled += _parse_check(inp, len(out) + 64, st, out, name)
+    assert handled >= 40
+
+
+def test_parse_mutation_fuzz():
+    corpus = [c for _, c, _ in corpus_files()]
+    rng = np.random.default_rng(98)
+    seen, handled = set(), 0
+    for m in fuzzgen.mutations(corpus, seed=6, count=4000):
+        st, out = oracle.decode(m)
+        cap = len(out) if st == 0 else len(out) + (1 << 20)
+        if rng.random() < 0.25:
+            cap = int(rng.integers(0, len(out) + 100))
+        st0, out0 = _oracle_slot(m, cap)
+        if _parse_check(m, cap, st0, out0, (m[:16].hex(), len(m), cap)):
+            handled += 1
+            seen.add(st0)
+    assert handled >= 1500 and len(seen) >= 12
+
+
+def test_parse_fresh_streams():
+    """libbrotli streams of every quality: qualities <= 9 (no literal context modelling) must be handled by the
+    two-phase path itself, block switches and distance context maps included"""
+    enc = fuzzgen.libbrotli_enc()
+    if enc is None:
+        pytest.skip("system libbrotlienc not present")
+    k = 0
+    for kind in ("random", "skewed", "repeat2k", "runs", "words", "small_alpha"):
+        for q, lgwin, size in ((1, 18, 30000), (3, 22, 200000), (5, 16, 70000), (7, 22, 300000), (9, 10, 20000),
+                               (9, 22, 400000), (11, 22, 40000), (11, 16, 9000)):
+            raw = fuzzgen.synthetic_raw(kind, 300 + k, size)
+            k += 1
+            comp = fuzzgen.compress(enc, raw, q, lgwin)
+            st, out, nrec, steps = hostsim.parse_decode(comp, cap=len(raw))
+            if q <= 9 and kind != "words":
+                # very short copies (4-symbol data) can outnumber the stream's share of the record arena
+                assert st == 0 or (st == hostsim.RECORDS_FULL and kind == "small_alpha"), (kind, q, lgwin, st)
+            assert st in hostsim.RETRY or (st, out) == (0, raw), (kind, q, lgwin, st)
+    # text at quality 5..9: block switches for commands and distances, distance context map, no literal contexts
+    import os
+    from conftest import DATA
+    for name in ("alice29.txt", "plrabn12.txt"):
+        raw = open(os.path.join(DATA, name), "rb").read()
+        for q in (5, 9):
+            st, out, nrec, steps = hostsim.parse_decode(fuzzgen.compress(enc, raw, q, 22), cap=len(raw))
+            assert st in hostsim.RETRY or (st, out) == (0, raw), (name, q, st)
+
+
+def test_parse_record_arena_overflow():
+    """a stream with more copies than its share of the record arena is handed to the fused kernel"""
+    enc = fuzzgen.libbrotli_enc()
+    if enc is None:
+        pytest.skip("system libbrotlienc not present")
+    raw = fuzzgen.synthetic_raw("runs", 7, 60000)
+    comp = fuzzgen.compress(enc, raw, 5, 16)
+    st, out, nrec, _ = hostsim.parse_decode(comp, cap=len(raw))
+    assert (st, out) == (0, raw) and nrec > 8
+    st, _, _, _ = hostsim.parse_decode(comp, cap=len(raw), rec_cap=8)
+    assert st == hostsim.RECORDS_FULL

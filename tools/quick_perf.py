@@ -15,9 +15,13 @@ for lib in libs:
         env["BRO_B200_LIB"] = os.path.join(ROOT, "brotli_rs_b200", "lib", lib)
     for w in WL:
         r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--workload", w, "--steps", "5", "--warmup", "2",
-                            "--no-e2e", "--no-cpu-baseline"], capture_output=True, text=True, env=env)
+                            "--no-e2e", "--no-cpu-baseline"] + (["--mode", os.environ["BRO_BENCH_MODE"]] if os.environ.get("BRO_BENCH_MODE") else []),
+                           capture_output=True, text=True, env=env)
         try:
             j = json.loads(r.stdout.strip().splitlines()[-1])
-            print("%-22s %-20s %9.1f GB/s  %8.3f ms  frac %.3f" % (lib or "product", w, j["value"], j["ms_per_step"], j["roofline"]["frac"]), flush=True)
+            ks = "  ".join("%s %.3f ms%s" % (k.split("_kernel")[0].replace("bro_", ""), v["ms"], (" (%.2f)" % v["frac"]) if v["frac"] else "")
+                           for k, v in j["roofline"]["kernels"].items())
+            print("%-22s %-20s %9.1f GB/s  %8.3f ms  | %s | retried %d" % (lib or "product", w, j["value"], j["ms_per_step"], ks,
+                                                                         j["roofline"]["batch_stats"]["retried_streams"]), flush=True)
         except Exception:
             print(lib, w, "FAILED", r.stderr[-400:], flush=True)
