@@ -145,11 +145,13 @@ struct BroScratch {
     int16_t base[16];
     uint8_t clc[32];               // code-length-code table: symbol | len<<5, indexed by 5 stream bits
     uint8_t word[64];              // dictionary word staging (<= 24 + 13 bytes)
+#if !defined(BRO_PARSE)
     // on-chip copies of the root tables of the current meta-block's literal / insert&copy / distance code when the
     // meta-block has exactly one of that kind (true for every stream libbrotli produces at quality <= 9)
     uint16_t root_lit[256];
     uint16_t root_cmd[256];
     uint16_t root_dist[256];
+#endif
 };
 
 // ------------------------------------------------------------------------------------------------------
@@ -237,6 +239,21 @@ BRO_FN void bro_bits_init(BroBits& s, const uint8_t* start, const uint8_t* end) 
 // most 32 bits.  Keeping the slide in ONE place per read keeps the hot loops small (the I-cache is a first-order
 // limit for this kernel).
 BRO_FN void bro_refill(BroBits& s) {
+#if defined(BRO_THREAD_MODE)
+    // one thread per stream: branch-free, so that the lanes of a warp (different streams, different bit positions)
+    // share these instructions instead of taking the slide one group of lanes at a time
+    const bool need = s.bp >= 32u;
+    uint32_t wn = 0;
+    if (need && s.chunk < s.end) wn = __ldg((const uint32_t*)s.chunk);   // chunk >= lo always holds here
+    const uint32_t got = need ? (s.rem < 4u ? s.rem : 4u) : 0u;
+    s.w0 = need ? s.w1 : s.w0;
+    s.w1 = need ? wn : s.w1;
+    s.bp -= need ? 32u : 0u;
+    s.chunk += need ? 4 : 0;
+    s.avail += 8u * got;
+    s.rem -= got;
+    return;
+#endif
     if (s.bp >= 32u) {
         s.bp -= 32u;
         s.w0 = s.w1;
@@ -332,6 +349,61 @@ BRO_FN int bro_decode_sym(BroBits& s, const uint16_t* T, uint32_t& sym) { return
 // order; Tree::insert (src/huffman/tree/mod.rs:50-61) counts every insert, and a tree with exactly one
 // insert decodes with zero bits.  The 32 lanes cooperate: counting sort by length, then every lane resolves
 // 8 of the 256 root entries by searching the canonical limits.
+#if defined(BRO_SERIAL)
+// One thread builds the record (thread-per-stream parse kernel, host simulation).  Everything the thread READS here is
+// in its own scratch (local memory on the device); the table itself is only written: the root is filled by
+// replication as every symbol is placed (its canonical code is known at that moment), so the build never waits for a
+// load from the table arena in HBM.
+BRO_COLD void bro_build_tree(uint16_t* T, BroScratch& sc, uint32_t n, bool explicit_syms) {
+    uint32_t cnt[16], next[16];
+    int base[16];               // canonical index of the first code of a length minus its code value
+    for (uint32_t L = 0; L < 16u; L++) cnt[L] = 0;
+    for (uint32_t i = 0; i < n; i++) cnt[sc.lens[i] & 15u]++;
+    uint32_t code = 0, off = 0, maxdepth = 0, nonzero = 0;
+    T[BRO_T_LIMIT] = 0; T[BRO_T_BASE] = 0;
+    base[0] = 0; next[0] = 0;
+    for (uint32_t L = 1; L <= 15u; L++) {
+        const uint32_t c = cnt[L];
+        next[L] = off;
+        base[L] = (int)off - (int)code;
+        T[BRO_T_BASE + L] = (uint16_t)(int16_t)base[L];
+        code += c;
+        T[BRO_T_LIMIT + L] = (uint16_t)(code << (15u - L));
+        code <<= 1;
+        off += c;
+        nonzero += c;
+        if (c) maxdepth = L;
+    }
+    // all-zero lengths happen only for a simple code with NSYM = 1 (src/huffman/mod.rs:36); a complex code always has
+    // >= 2 non-zero lengths
+    T[BRO_T_SINGLE] = (nonzero <= 1u) ? 1 : 0;
+    T[BRO_T_MAXDEPTH] = (uint16_t)maxdepth;
+    T[291] = 0;
+#if defined(BRO_HOSTSIM)
+    for (uint32_t r = 0; r < 256u; r++) T[r] = 0;
+#else
+    for (uint32_t r = 0; r < 32u; r++) ((uint4*)T)[r] = make_uint4(0u, 0u, 0u, 0u);     // records are 16-byte aligned
+#endif
+    uint32_t single_sym = 0;
+    for (uint32_t i = 0; i < n; i++) {
+        const uint32_t L = sc.lens[i] & 15u;
+        const uint32_t symv = explicit_syms ? sc.syms[i] : i;
+        if (nonzero == 0u && i == 0u) single_sym = symv;
+        if (L == 0u) continue;
+        const uint32_t idx = next[L]++;
+        T[BRO_T_SORTED + idx] = (uint16_t)symv;
+        if (nonzero == 1u) single_sym = symv;
+        if (nonzero >= 2u) {
+            const uint32_t c = (uint32_t)((int)idx - base[L]);      // the canonical code of this symbol
+            if (L <= 8u) {
+                const uint32_t e = symv | (L << 10);
+                for (uint32_t r = bro_brev(c) >> (32u - L); r < 256u; r += 1u << L) T[r] = (uint16_t)e;
+            } else T[bro_brev(c >> (L - 8u)) >> 24] = 1;
+        }
+    }
+    T[BRO_T_SINGLE_SYM] = (uint16_t)single_sym;
+}
+#else
 BRO_COLD void bro_build_tree(uint16_t* T, BroScratch& sc, uint32_t n, bool explicit_syms) {
     const unsigned lane = bro_lane();
     for (unsigned i = lane; i < 16u; i += BRO_W) sc.cnt[i] = 0;
@@ -407,6 +479,8 @@ BRO_COLD void bro_build_tree(uint16_t* T, BroScratch& sc, uint32_t n, bool expli
     bro_syncwarp();
 }
 
+#endif
+
 // ------------------------------------------------------------------------------------------------------
 // decoder state
 // ------------------------------------------------------------------------------------------------------
@@ -460,20 +534,28 @@ BRO_FN int bro_read_nbltypes(BroBits& in, uint32_t& v) {
     return 0;
 }
 
-// src/lib.rs:597-665
-BRO_COLD int bro_read_simple_code(BroBits& in, BroScratch& sc, uint32_t alphabet, uint16_t* T) {
+// The readers below only fill sc.lens[] (and sc.syms[]); the table is built by their caller afterwards.  In the
+// thread-per-stream kernel this matters: lanes leave the loops below at different trips, and they are converged again
+// only once the out-of-line function has returned -- the build then runs once for the whole warp.  For the same
+// reason the loops have a single exit (errors break and are returned after the loop).
+
+// src/lib.rs:597-665.  -> number of (length, symbol) pairs in sc.lens[] / sc.syms[]
+BRO_COLD int bro_read_simple_code(BroBits& in, BroScratch& sc, uint32_t alphabet, uint32_t& n_out) {
     uint32_t bit_width = 0;
     for (uint32_t a = alphabet - 1u; a; a >>= 1) bit_width++;   // 16 - leading_zeros(alphabet-1 as u16), src/lib.rs:598
-    uint32_t nsym, s[4];
+    uint32_t nsym, s[4] = {0, 0, 0, 0};
     if (!bro_read_bits(in, 2, nsym)) return BRO_ST_UnexpectedEOF;
     nsym += 1;
+    int st = 0;
     for (uint32_t i = 0; i < nsym; i++) {
-        if (!bro_read_bits(in, bit_width, s[i])) return BRO_ST_UnexpectedEOF;
-        if (s[i] >= alphabet) return BRO_ST_InvalidSymbol;
+        if (!bro_read_bits(in, bit_width, s[i])) { st = BRO_ST_UnexpectedEOF; break; }
+        if (s[i] >= alphabet) { st = BRO_ST_InvalidSymbol; break; }
     }
+    if (st) return st;
     for (uint32_t i = 0; i + 1 < nsym; i++)
         for (uint32_t j = i + 1; j < nsym; j++)
-            if (s[i] == s[j]) return BRO_ST_InvalidSymbol;
+            if (s[i] == s[j]) st = BRO_ST_InvalidSymbol;
+    if (st) return st;
     uint32_t L[4] = {0, 0, 0, 0};
 #define BRO_SWAP(a, b) do { if (s[a] > s[b]) { uint32_t t_ = s[a]; s[a] = s[b]; s[b] = t_; } } while (0)
     if (nsym == 2) { BRO_SWAP(0, 1); L[0] = L[1] = 1; }
@@ -490,29 +572,30 @@ BRO_COLD int bro_read_simple_code(BroBits& in, BroScratch& sc, uint32_t alphabet
     bro_syncwarp();
     if (bro_lane() == 0) for (uint32_t i = 0; i < nsym; i++) { sc.lens[i] = (uint8_t)L[i]; sc.syms[i] = (uint16_t)s[i]; }
     bro_syncwarp();
-    bro_build_tree(T, sc, nsym, true);
+    n_out = nsym;
     return 0;
 }
 
-// src/lib.rs:667-875
-BRO_COLD int bro_read_complex_code(BroBits& in, BroScratch& sc, uint32_t hskip, uint32_t alphabet, uint16_t* T) {
+// src/lib.rs:667-875.  Fills sc.lens[0..alphabet).
+BRO_COLD int bro_read_complex_code(BroBits& in, BroScratch& sc, uint32_t hskip, uint32_t alphabet) {
     const unsigned lane = bro_lane();
     // code lengths of the code-length code, transmitted in the order 1,2,3,4,0,5,17,6,16,7,8,...,15 with the fixed
     // code 00->0 01->3 10->4 110->2 1110->1 1111->5 (src/lib.rs:120-125, 669-704)
     uint32_t cl[18];
     for (int i = 0; i < 18; i++) cl[i] = 0;
     uint32_t sum = 0, nonzero = 0;
+    int st = 0;
     for (uint32_t i = hskip; i < 18u; i++) {
         uint32_t b, v;
-        if (!bro_read_bits(in, 2, b)) return BRO_ST_UnexpectedEOF;
+        if (!bro_read_bits(in, 2, b)) { st = BRO_ST_UnexpectedEOF; break; }
         if (b == 0u) v = 0;
         else if (b == 2u) v = 3;          // read order 0,1
         else if (b == 1u) v = 4;          // read order 1,0
         else {
-            if (!bro_read_bits(in, 1, b)) return BRO_ST_UnexpectedEOF;
+            if (!bro_read_bits(in, 1, b)) { st = BRO_ST_UnexpectedEOF; break; }
             if (!b) v = 2;
             else {
-                if (!bro_read_bits(in, 1, b)) return BRO_ST_UnexpectedEOF;
+                if (!bro_read_bits(in, 1, b)) { st = BRO_ST_UnexpectedEOF; break; }
                 v = b ? 5 : 1;
             }
         }
@@ -523,9 +606,10 @@ BRO_COLD int bro_read_complex_code(BroBits& in, BroScratch& sc, uint32_t hskip, 
             sum += 32u >> v;
             nonzero += 1;
             if (sum == 32u) break;
-            if (sum > 32u) return BRO_ST_CodeLengthsChecksum;
+            if (sum > 32u) { st = BRO_ST_CodeLengthsChecksum; break; }
         }
     }
+    if (st) return st;
     if (nonzero == 0u) return BRO_ST_NoCodeLength;
     if (nonzero >= 2u && sum < 32u) return BRO_ST_CodeLengthsChecksum;
 
@@ -560,7 +644,7 @@ BRO_COLD int bro_read_complex_code(BroBits& in, BroScratch& sc, uint32_t hskip, 
             bro_refill(in);
             uint32_t e = sc.clc[bro_peek(in) & 31u];
             uint32_t len = e >> 5;
-            if (len > bro_avail(in)) return BRO_ST_UnexpectedEOF;
+            if (len > bro_avail(in)) { st = BRO_ST_UnexpectedEOF; break; }
             bro_consume(in, len);
             c = e & 31u;
         }
@@ -574,18 +658,18 @@ BRO_COLD int bro_read_complex_code(BroBits& in, BroScratch& sc, uint32_t hskip, 
                 nz += 1;
                 total += 32768u >> c;
                 if (total == 32768u) break;
-                if (total > 32768u) return BRO_ST_CodeLengthsChecksum;
+                if (total > 32768u) { st = BRO_ST_CodeLengthsChecksum; break; }
             }
         } else if (c == 16u) {
             uint32_t extra, count, newrep;
-            if (!bro_read_bits(in, 2, extra)) return BRO_ST_UnexpectedEOF;
+            if (!bro_read_bits(in, 2, extra)) { st = BRO_ST_UnexpectedEOF; break; }
             if (last_symbol == 16u && have_repeat) {
                 newrep = 4u * (last_repeat - 2u) + extra + 3u;
-                if (i + newrep - last_repeat > alphabet) return BRO_ST_ParseErrorComplexPrefixCodeLengths;
+                if (i + newrep - last_repeat > alphabet) { st = BRO_ST_ParseErrorComplexPrefixCodeLengths; break; }
                 count = newrep - last_repeat;
             } else {
                 newrep = 3u + extra;
-                if (i + newrep > alphabet) return BRO_ST_ParseErrorComplexPrefixCodeLengths;
+                if (i + newrep > alphabet) { st = BRO_ST_ParseErrorComplexPrefixCodeLengths; break; }
                 count = newrep;
             }
             for (uint32_t k = lane; k < count; k += BRO_W) sc.lens[i + k] = (uint8_t)last_nz;
@@ -595,11 +679,11 @@ BRO_COLD int bro_read_complex_code(BroBits& in, BroScratch& sc, uint32_t hskip, 
             last_repeat = newrep;
             have_repeat = 1;
             if (total == 32768u) break;
-            if (total > 32768u) return BRO_ST_CodeLengthsChecksum;
+            if (total > 32768u) { st = BRO_ST_CodeLengthsChecksum; break; }
             last_symbol = 16;
         } else {
             uint32_t extra;
-            if (!bro_read_bits(in, 3, extra)) return BRO_ST_UnexpectedEOF;
+            if (!bro_read_bits(in, 3, extra)) { st = BRO_ST_UnexpectedEOF; break; }
             if (last_symbol == 17u && have_repeat) {
                 uint32_t newrep = 8u * (last_repeat - 2u) + extra + 3u;
                 i += newrep - last_repeat;
@@ -609,30 +693,35 @@ BRO_COLD int bro_read_complex_code(BroBits& in, BroScratch& sc, uint32_t hskip, 
                 last_repeat = 3u + extra;
             }
             have_repeat = 1;
-            if (i > alphabet) return BRO_ST_ParseErrorComplexPrefixCodeLengths;
+            if (i > alphabet) { st = BRO_ST_ParseErrorComplexPrefixCodeLengths; break; }
             last_symbol = 17;
         }
     }
+    if (st) return st;
     if (nz < 2u) return BRO_ST_LessThanTwoNonZeroCodeLengths;
     bro_syncwarp();
-    bro_build_tree(T, sc, alphabet, false);
     return 0;
 }
 
-// src/lib.rs:877-889
-BRO_COLD int bro_read_prefix_code_cold(BroBits& in, BroScratch& sc, uint32_t alphabet, uint16_t* T) {
+// src/lib.rs:877-889.  -> the arguments of the table build that follows: n pairs, explicit symbols or not.
+BRO_COLD int bro_read_prefix_code_cold(BroBits& in, BroScratch& sc, uint32_t alphabet, uint32_t& n_out, bool& explicit_out) {
     uint32_t kind;
     if (!bro_read_bits(in, 2, kind)) return BRO_ST_UnexpectedEOF;
-    if (kind == 1u) return bro_read_simple_code(in, sc, alphabet, T);
-    return bro_read_complex_code(in, sc, kind, alphabet, T);
+    explicit_out = kind == 1u;
+    n_out = alphabet;
+    if (kind == 1u) return bro_read_simple_code(in, sc, alphabet, n_out);
+    return bro_read_complex_code(in, sc, kind, alphabet);
 }
 
 // The out-of-line (cold) routines take the bit window by reference.  Callers hand them a COPY and copy it back, so
 // that the hot loops' own window never has its address taken and stays in registers.
 BRO_FN int bro_read_prefix_code(BroBits& in, BroScratch& sc, uint32_t alphabet, uint16_t* T) {
     BroBits t = in;
-    int st = bro_read_prefix_code_cold(t, sc, alphabet, T);
+    uint32_t n = 0;
+    bool explicit_syms = false;
+    int st = bro_read_prefix_code_cold(t, sc, alphabet, n, explicit_syms);
     in = t;
+    if (st == 0) bro_build_tree(T, sc, n, explicit_syms);
     return st;
 }
 
@@ -682,8 +771,11 @@ BRO_COLD int bro_read_context_map_cold(BroBits& in, BroScratch& sc, uint16_t* T,
         rlemax += 1;
     }
     if (BRO_TREE_U16(rlemax + ntrees) > t_cap) return BRO_ST_ArenaTooSmall;   // temporary table above the arena top
-    int st = bro_read_prefix_code_cold(in, sc, rlemax + ntrees, T);
+    uint32_t n_pairs = 0;
+    bool explicit_syms = false;
+    int st = bro_read_prefix_code_cold(in, sc, rlemax + ntrees, n_pairs, explicit_syms);
     if (st) return st;
+    bro_build_tree(T, sc, n_pairs, explicit_syms);
     uint32_t pushed = 0;
     while (pushed < len) {
         uint32_t s;
@@ -934,6 +1026,7 @@ BRO_FN int bro_resolve_distance(BroDec& d, uint32_t dcode, uint32_t npostfix, ui
     return 0;
 }
 
+#if !defined(BRO_PARSE)   /* the fused command loops (the two-phase path has its own: bro_parse.h) */
 // Reference to a 256-entry root table held on chip (shared memory in the group modes): a 32-bit shared-window
 // address, so that a lookup is one add and one LDS and the base lives in ONE register for the whole loop.
 #if defined(BRO_SERIAL)
@@ -1085,6 +1178,8 @@ BRO_FN int bro_commands_simple(BroDec& d, BroScratch& sc, uint32_t mlen, uint32_
     return st;
 }
 
+#endif
+
 // ------------------------------------------------------------------------------------------------------
 // one compressed meta-block: src/lib.rs:1745-2141
 // ------------------------------------------------------------------------------------------------------
@@ -1109,41 +1204,44 @@ BRO_FN int bro_metablock_tables(BroDec& d, BroMbInfo& mb) {
     const unsigned lane = bro_lane();
     uint16_t* A = d.arena;
     BroBlockCat (&cat)[3] = mb.cat;
-    int st;
     BroScratch& sc = *d.sc;
+    // Single exit: an error only sets `st` and the remaining steps are skipped, so that in the thread-per-stream kernel
+    // the lanes of a warp meet again after every conditional part (a `return` inside would let the lanes that skip a
+    // part run ahead of the others).
+    int st = 0;
     // The arena is bump-allocated per meta-block from the counts the header announces (uint16 units, 16-byte
     // granules); a meta-block that does not fit reports ArenaTooSmall and the stream is re-run by the warp kernel,
     // whose arenas hold the worst case (256 + 256 + 256 tables).
     uint32_t top = d.arena_base;
-#define BRO_ALLOC(var, n_u16) do { (var) = top; top += ((uint32_t)(n_u16) + 7u) & ~7u; if (top > d.arena_cap) return BRO_ST_ArenaTooSmall; } while (0)
+#define BRO_ALLOC(var, n_u16) do { (var) = top; top += ((uint32_t)(n_u16) + 7u) & ~7u; if (!st && top > d.arena_cap) st = BRO_ST_ArenaTooSmall; } while (0)
+#define BRO_TRY(expr) do { if (!st) st = (expr); } while (0)
     // NBLTYPES{L,I,D}, block type / count codes, first block counts (src/lib.rs:1745-1885)
 #pragma unroll
     for (uint32_t k = 0; k < 3u; k++) {
-        cat[k].btype = 0; cat[k].btype_prev = 1; cat[k].blen = 0; cat[k].t_type = 0; cat[k].t_count = 0;
-        if ((st = bro_read_nbltypes(d.in, cat[k].nbl))) return st;
-        if (cat[k].nbl >= 2u) {
+        cat[k].btype = 0; cat[k].btype_prev = 1; cat[k].blen = 0; cat[k].t_type = 0; cat[k].t_count = 0; cat[k].nbl = 1;
+        BRO_TRY(bro_read_nbltypes(d.in, cat[k].nbl));
+        if (!st && cat[k].nbl >= 2u) {
             BRO_ALLOC(cat[k].t_type, BRO_TREE_U16(cat[k].nbl + 2u));
             BRO_ALLOC(cat[k].t_count, BRO_TREE_U16(BRO_ALPHA_BCOUNT));
             // the two codes of a category are read by one loop so that the table reader has a single call site here
-            for (uint32_t j = 0; j < 2u; j++) {
-                if ((st = bro_read_prefix_code(d.in, sc, j == 0u ? cat[k].nbl + 2u : BRO_ALPHA_BCOUNT,
-                                               A + (j == 0u ? cat[k].t_type : cat[k].t_count)))) return st;
-            }
-            if ((st = bro_read_block_count(d.in, A + cat[k].t_count, cat[k].blen))) return st;
+            for (uint32_t j = 0; j < 2u; j++)
+                BRO_TRY(bro_read_prefix_code(d.in, sc, j == 0u ? cat[k].nbl + 2u : BRO_ALPHA_BCOUNT,
+                                             A + (j == 0u ? cat[k].t_type : cat[k].t_count)));
+            BRO_TRY(bro_read_block_count(d.in, A + cat[k].t_count, cat[k].blen));
         }
     }
     // NPOSTFIX, NDIRECT (src/lib.rs:548-560), context modes (562-573)
-    uint32_t npostfix, ndirect;
-    if (!bro_read_bits(d.in, 2, npostfix)) return BRO_ST_UnexpectedEOF;
-    if (!bro_read_bits(d.in, 4, ndirect)) return BRO_ST_UnexpectedEOF;
+    uint32_t npostfix = 0, ndirect = 0;
+    if (!st && !bro_read_bits(d.in, 2, npostfix)) st = BRO_ST_UnexpectedEOF;
+    if (!st && !bro_read_bits(d.in, 4, ndirect)) st = BRO_ST_UnexpectedEOF;
     ndirect <<= npostfix;
-    uint32_t o_modes, o_cmap_l, o_cmap_d;
+    uint32_t o_modes = 0, o_cmap_l = 0, o_cmap_d = 0;
     BRO_ALLOC(o_modes, (cat[0].nbl + 1u) >> 1);
     uint8_t* modes = (uint8_t*)(A + o_modes);
-    for (uint32_t i = 0; i < cat[0].nbl; i++) {
-        uint32_t m;
-        if (!bro_read_bits(d.in, 2, m)) return BRO_ST_UnexpectedEOF;
-        if (lane == 0) modes[i] = (uint8_t)m;
+    for (uint32_t i = 0; !st && i < cat[0].nbl; i++) {
+        uint32_t m = 0;
+        if (!bro_read_bits(d.in, 2, m)) st = BRO_ST_UnexpectedEOF;
+        else if (lane == 0) modes[i] = (uint8_t)m;
     }
     // NTREESL + literal context map, NTREESD + distance context map (src/lib.rs:1916-1973)
     BRO_ALLOC(o_cmap_l, 32u * cat[0].nbl);
@@ -1152,50 +1250,52 @@ BRO_FN int bro_metablock_tables(BroDec& d, BroMbInfo& mb) {
     uint8_t* cmap_d = (uint8_t*)(A + o_cmap_d);
     uint32_t ntl = 1, ntd = 1;
     for (uint32_t j = 0; j < 2u; j++) {
-        uint32_t nt;
-        if ((st = bro_read_nbltypes(d.in, nt))) return st;
-        if (nt >= 2u) {
+        uint32_t nt = 1;
+        BRO_TRY(bro_read_nbltypes(d.in, nt));
+        if (!st && nt >= 2u) {
             // the context map's own prefix code is temporary: it lives above the arena top and is dropped afterwards
-            if ((st = bro_read_context_map(d.in, sc, A + top, d.arena_cap - top, nt, j == 0u ? 64u * cat[0].nbl : 4u * cat[2].nbl,
-                                           j == 0u ? cmap_l : cmap_d))) return st;
+            st = bro_read_context_map(d.in, sc, A + top, d.arena_cap - top, nt, j == 0u ? 64u * cat[0].nbl : 4u * cat[2].nbl,
+                                      j == 0u ? cmap_l : cmap_d);
         }
         if (j == 0u) ntl = nt; else ntd = nt;
 #if defined(BRO_PARSE)
         // Phase one of the two-phase path never sees the bytes copies produce, so it can decode a meta-block only if
         // no block type's literal context map depends on the context; found out here, before the prefix codes
         // (the bulk of the header) are read.
-        if (j == 0u && nt >= 2u)
+        if (!st && j == 0u && nt >= 2u)
             for (uint32_t q = 0; q < 64u * cat[0].nbl; q++)
-                if (cmap_l[q] != cmap_l[q & ~63u]) return BRO_ST_NeedFused;
+                if (cmap_l[q] != cmap_l[q & ~63u]) st = BRO_ST_NeedFused;
 #endif
     }
     // prefix codes (src/lib.rs:1016-1068): NTREESL literal codes, NBLTYPESI insert&copy codes, NTREESD distance codes
     const uint32_t dist_alphabet = 16u + ndirect + (48u << npostfix);
     const uint32_t dist_stride = BRO_TREE_U16(dist_alphabet);
-    uint32_t o_lit, o_cmd, o_dist;
+    uint32_t o_lit = 0, o_cmd = 0, o_dist = 0;
     BRO_ALLOC(o_lit, ntl * BRO_TREE_U16(BRO_ALPHA_LIT));
     BRO_ALLOC(o_cmd, cat[1].nbl * BRO_TREE_U16(BRO_ALPHA_CMD));
     BRO_ALLOC(o_dist, ntd * dist_stride);
 #undef BRO_ALLOC
     {
         const uint32_t n_l = ntl, n_i = cat[1].nbl, total = ntl + cat[1].nbl + ntd;
-        for (uint32_t i = 0; i < total; i++) {
+        for (uint32_t i = 0; !st && i < total; i++) {
             uint32_t alphabet;
             uint16_t* T;
             if (i < n_l) { alphabet = BRO_ALPHA_LIT; T = A + o_lit + i * BRO_TREE_U16(BRO_ALPHA_LIT); }
             else if (i < n_l + n_i) { alphabet = BRO_ALPHA_CMD; T = A + o_cmd + (i - n_l) * BRO_TREE_U16(BRO_ALPHA_CMD); }
             else { alphabet = dist_alphabet; T = A + o_dist + (i - n_l - n_i) * dist_stride; }
-            if ((st = bro_read_prefix_code(d.in, sc, alphabet, T))) return st;
+            st = bro_read_prefix_code(d.in, sc, alphabet, T);
         }
     }
+#undef BRO_TRY
     bro_syncwarp();
     mb.npostfix = npostfix; mb.ndirect = ndirect; mb.ntl = ntl; mb.ntd = ntd;
     mb.o_modes = o_modes; mb.o_cmap_l = o_cmap_l; mb.o_cmap_d = o_cmap_d;
     mb.o_lit = o_lit; mb.o_cmd = o_cmd; mb.o_dist = o_dist; mb.dist_stride = dist_stride;
     mb.simple = ntl == 1u && ntd == 1u && cat[0].nbl == 1u && cat[1].nbl == 1u && cat[2].nbl == 1u;
-    return 0;
+    return st;
 }
 
+#if !defined(BRO_PARSE)
 // The general command loop (src/lib.rs:2003-2141): any number of codes, block switches, literal context modelling.
 BRO_FN int bro_commands_general(BroDec& d, BroScratch& sc, uint32_t mlen, BroMbInfo& mb) {
     const unsigned lane = bro_lane();
@@ -1322,6 +1422,8 @@ BRO_FN int bro_decode_compressed_metablock(BroDec& d, uint32_t mlen) {
     return bro_commands_general(d, sc, mlen, mb);
 }
 
+#endif
+
 // ------------------------------------------------------------------------------------------------------
 // one stream: src/lib.rs:1545-2170.  Returns the status; *out_len = bytes produced.
 // ------------------------------------------------------------------------------------------------------
@@ -1421,6 +1523,7 @@ BRO_FN int bro_next_metablock(BroDec& d, bool after_last, uint32_t& is_last, uin
     return BRO_MB_END;
 }
 
+#if !defined(BRO_PARSE)
 BRO_FN int bro_decode_stream(BroDec& d) {
     int st = bro_stream_header(d);
     if (st) return st;
@@ -1435,3 +1538,4 @@ BRO_FN int bro_decode_stream(BroDec& d) {
         after_last = is_last != 0u;
     }
 }
+#endif

@@ -1,6 +1,6 @@
 // Host simulation of the TWO-PHASE path -- CPU TEST-SUITE ONLY (tests/_build/libbro_hostsim_parse.so, built by
 // tests/hostsim.py; never part of libbrotli_b200.so).  Phase one is the very code the parse kernel runs per lane
-// (bro_parse.h, the flat state machine); phase two is replaced by the obvious byte loop over the copy records, so
+// (bro_parse.h); phase two is replaced by the obvious byte loop over the copy records, so
 // that the CPU test-suite can check the records phase one writes against the oracle without a GPU.
 #define BRO_HOSTSIM 1
 #define BRO_PARSE 1
@@ -11,8 +11,8 @@
 
 extern "C" const uint8_t bro_dictionary_blob[];
 
-// Returns the status phase one leaves (BRO_ST_NeedFused etc. included).  *n_rec = records written, *n_steps = trips of
-// the flat machine.  rec_cap = 0 selects the product's share: one record per 2 compressed bytes + 32.
+// Returns the status phase one leaves (BRO_ST_NeedFused etc. included).  *n_rec = records written, *n_steps = rounds of
+// the machine.  rec_cap = 0 selects the product's share: one record per 2 compressed bytes + 32.
 extern "C" int bro_hostsim_parse_decode(const uint8_t* in, size_t in_len, uint8_t* out, size_t cap, size_t* out_len,
                                         int quirks, unsigned arena_u16, unsigned rec_cap, unsigned* n_rec, unsigned* n_steps) {
     if (arena_u16 == 0) arena_u16 = BRO_THREAD_ARENA_U16;
@@ -21,11 +21,12 @@ extern "C" int bro_hostsim_parse_decode(const uint8_t* in, size_t in_len, uint8_
     memset(&d, 0, sizeof(d));
     uint16_t* arena = (uint16_t*)malloc(2u * (size_t)arena_u16);
     BroRec* rec = (BroRec*)malloc(sizeof(BroRec) * (size_t)rec_cap);
-    const unsigned scratch_u16 = (unsigned)((sizeof(BroScratch) / 2u + 7u) & ~7u);
-    d.sc = (BroScratch*)arena;
+    BroScratch sc;
+    memset(&sc, 0, sizeof(sc));
+    d.sc = &sc;
     d.arena = arena;
     d.arena_cap = arena_u16;
-    d.arena_base = scratch_u16;
+    d.arena_base = 0;
     d.dict = bro_dictionary_blob;
     d.out = out;
     d.cap = cap > BRO_MAX_SLOT ? (uint32_t)BRO_MAX_SLOT : (uint32_t)cap;
@@ -42,7 +43,7 @@ extern "C" int bro_hostsim_parse_decode(const uint8_t* in, size_t in_len, uint8_
     unsigned steps = 0;
     while (ps.kind != BRO_K_DONE) {
         if (ps.kind == BRO_K_HEADER) bro_parse_header(d, ps, mb);
-        else { bro_parse_step(d, ps, mb); steps++; }
+        else { bro_parse_round(d, ps, mb); steps++; }
     }
     // phase two, the obvious way
     if (ps.st == BRO_ST_OK) {

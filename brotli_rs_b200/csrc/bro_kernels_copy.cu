@@ -28,6 +28,22 @@
 #ifndef BRO_COPY_MIN_BLOCKS
 #define BRO_COPY_MIN_BLOCKS 6
 #endif
+#ifndef BRO_COPY_DEPTH
+#define BRO_COPY_DEPTH 4      // rounds of 32 units in flight per warp; 1 KiB of staging per round and warp
+#endif
+
+// Ampere-style asynchronous copy global -> shared, 16 bytes, L2 only (the sources were written moments ago by this very
+// SM's write-through stores and are not in L1 anyway).  No register holds the data, so a lane can have several in
+// flight; cp.async.wait_all makes the lane's own copies visible to itself.
+__device__ __forceinline__ void bro_cp_async16(uint32_t smem_addr, const void* gptr) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(smem_addr), "l"(gptr) : "memory");
+}
+__device__ __forceinline__ void bro_cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+__device__ __forceinline__ uint4 bro_lds128(uint32_t smem_addr) {
+    uint4 v;
+    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(smem_addr));
+    return v;
+}
 
 // 16 bytes from an arbitrary address: two aligned 16-byte loads and a funnel (the bytes before/after the 16 wanted
 // ones lie in the same 16-byte granules as wanted bytes, i.e. inside the same allocation)
@@ -63,6 +79,10 @@ __device__ __forceinline__ void bro_warp_copy(uint8_t* dst, const uint8_t* src, 
 template <int WARPS>
 __global__ void __launch_bounds__(WARPS * 32, BRO_COPY_MIN_BLOCKS) bro_copy_kernel(BroLaunch p) {
     const unsigned lane = threadIdx.x & 31u;
+    // staging: per warp BRO_COPY_DEPTH rounds x 32 lanes x 32 bytes (the two aligned 16-byte granules that hold a
+    // unit's 16 source bytes)
+    __shared__ __align__(16) uint8_t stage[WARPS * BRO_COPY_DEPTH * 32 * 32];
+    const uint32_t stage_base = (uint32_t)__cvta_generic_to_shared(stage) + (threadIdx.x >> 5) * (BRO_COPY_DEPTH * 32u * 32u);
     for (;;) {
         uint32_t i = 0;
         if (lane == 0) i = atomicAdd(p.counter, 1u);
@@ -121,34 +141,71 @@ __global__ void __launch_bounds__(WARPS * 32, BRO_COPY_MIN_BLOCKS) bro_copy_kern
                     if ((int)lane >= o) incl += v;
                 }
                 const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
-                for (uint32_t u0 = 0; u0 < total; u0 += 32u) {
-                    const uint32_t u = u0 + lane;
-                    // smallest k with incl[k] > u
-                    uint32_t k = 0;
+                // BRO_COPY_DEPTH rounds of 32 units are in flight at a time: ISSUE (find the unit's record, start the
+                // asynchronous copy of its 32 source bytes into this lane's staging slot), wait once, then STORE
+                // (realign from the slot, one aligned 16-byte store).  The load latency is paid once per
+                // BRO_COPY_DEPTH rounds instead of once per round.
+                for (uint32_t u0 = 0; u0 < total; u0 += 32u * BRO_COPY_DEPTH) {
+                    uint32_t m_dp[BRO_COPY_DEPTH], m_info[BRO_COPY_DEPTH];   // destination offset; 0 none | 1 byte | 2 vector, source shift << 8
+                    uint32_t m_byte[BRO_COPY_DEPTH];                         // the byte of a byte unit (not touched before the wait)
 #pragma unroll
-                    for (int s = 16; s >= 1; s >>= 1) {
-                        const uint32_t v = __shfl_sync(0xffffffffu, incl, (int)(k + s - 1u));
-                        if (v <= u) k += (uint32_t)s;
+                    for (int r = 0; r < BRO_COPY_DEPTH; r++) {
+                        const uint32_t u = u0 + 32u * r + lane;
+                        m_info[r] = 0; m_dp[r] = 0; m_byte[r] = 0;
+                        if (u0 + 32u * r >= total) continue;      // warp-uniform
+                        // smallest k with incl[k] > u
+                        uint32_t k = 0;
+#pragma unroll
+                        for (int sft = 16; sft >= 1; sft >>= 1) {
+                            const uint32_t v = __shfl_sync(0xffffffffu, incl, (int)(k + sft - 1u));
+                            if (v <= u) k += (uint32_t)sft;
+                        }
+                        const int ks = (int)(k & 31u);
+                        const uint32_t r_dst = __shfl_sync(0xffffffffu, dst, ks), r_lk = __shfl_sync(0xffffffffu, lk, ks);
+                        const uint32_t r_a = __shfl_sync(0xffffffffu, a, ks), r_end = __shfl_sync(0xffffffffu, incl, ks);
+                        if (u < total) {
+                            const uint32_t r_len = r_lk & BRO_REC_LEN_MASK, r_kind = r_lk >> BRO_REC_KIND_SHIFT;
+                            uint32_t r_head = (16u - ((r_dst + out_mis) & 15u)) & 15u;
+                            if (r_head > r_len) r_head = r_len;
+                            const uint32_t r_nvec = (r_len - r_head) >> 4;
+                            const uint32_t r_units = r_head + r_nvec + ((r_len - r_head) & 15u);
+                            const uint32_t ul = u - (r_end - r_units);         // unit index inside the record
+                            uint32_t off;                                      // byte offset inside the record
+                            bool vec = false;
+                            if (ul < r_head) off = ul;
+                            else if (ul < r_head + r_nvec) { off = r_head + 16u * (ul - r_head); vec = true; }
+                            else off = r_head + 16u * r_nvec + (ul - r_head - r_nvec);
+                            const uint8_t* src = r_kind == BRO_REC_STORED ? in + r_a + off : out + (r_dst - r_a) + off;
+                            m_dp[r] = r_dst + off;
+                            if (vec) {
+                                const uintptr_t sa = (uintptr_t)src;
+                                const uint32_t sh = (uint32_t)(sa & 15u);
+                                const uint32_t slot = stage_base + (uint32_t)(r * 32 + (int)lane) * 32u;
+                                bro_cp_async16(slot, (const void*)(sa & ~(uintptr_t)15));
+                                if (sh) bro_cp_async16(slot + 16u, (const void*)((sa & ~(uintptr_t)15) + 16u));
+                                m_info[r] = 2u | (sh << 8);
+                            } else { m_info[r] = 1u; m_byte[r] = *src; }
+                        }
                     }
-                    const int ks = (int)(k & 31u);
-                    const uint32_t r_dst = __shfl_sync(0xffffffffu, dst, ks), r_lk = __shfl_sync(0xffffffffu, lk, ks);
-                    const uint32_t r_a = __shfl_sync(0xffffffffu, a, ks), r_end = __shfl_sync(0xffffffffu, incl, ks);
-                    if (u < total) {
-                        const uint32_t r_len = r_lk & BRO_REC_LEN_MASK, r_kind = r_lk >> BRO_REC_KIND_SHIFT;
-                        uint32_t r_head = (16u - ((r_dst + out_mis) & 15u)) & 15u;
-                        if (r_head > r_len) r_head = r_len;
-                        const uint32_t r_nvec = (r_len - r_head) >> 4;
-                        const uint32_t r_units = r_head + r_nvec + ((r_len - r_head) & 15u);
-                        const uint32_t ul = u - (r_end - r_units);         // unit index inside the record
-                        uint32_t off;                                      // byte offset inside the record
-                        bool vec = false;
-                        if (ul < r_head) off = ul;
-                        else if (ul < r_head + r_nvec) { off = r_head + 16u * (ul - r_head); vec = true; }
-                        else off = r_head + 16u * r_nvec + (ul - r_head - r_nvec);
-                        const uint8_t* src = r_kind == BRO_REC_STORED ? in + r_a + off : out + (r_dst - r_a) + off;
-                        uint8_t* dp = out + r_dst + off;
-                        if (vec) *(uint4*)dp = bro_ldu16(src);
-                        else *dp = *src;
+                    bro_cp_async_wait_all();
+#pragma unroll
+                    for (int r = 0; r < BRO_COPY_DEPTH; r++) {
+                        const uint32_t info = m_info[r];
+                        if ((info & 3u) == 2u) {
+                            const uint32_t slot = stage_base + (uint32_t)(r * 32 + (int)lane) * 32u;
+                            const uint32_t sh = info >> 8;
+                            uint4 A = bro_lds128(slot);
+                            if (sh) {
+                                const uint4 B = bro_lds128(slot + 16u);
+                                uint32_t w0 = A.x, w1 = A.y, w2 = A.z, w3 = A.w, w4 = B.x, w5 = B.y, w6 = B.z, w7 = B.w;
+                                if (sh & 8u) { w0 = w2; w1 = w3; w2 = w4; w3 = w5; w4 = w6; w5 = w7; }
+                                if (sh & 4u) { w0 = w1; w1 = w2; w2 = w3; w3 = w4; w4 = w5; }
+                                const unsigned bs = 8u * (sh & 3u);
+                                A.x = __funnelshift_r(w0, w1, bs); A.y = __funnelshift_r(w1, w2, bs);
+                                A.z = __funnelshift_r(w2, w3, bs); A.w = __funnelshift_r(w3, w4, bs);
+                            }
+                            *(uint4*)(out + m_dp[r]) = A;
+                        } else if (info & 1u) out[m_dp[r]] = (uint8_t)m_byte[r];
                     }
                 }
                 j = e;

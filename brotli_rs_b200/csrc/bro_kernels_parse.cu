@@ -27,7 +27,6 @@
 #ifndef BRO_PARSE_PATIENCE
 #define BRO_PARSE_PATIENCE 1024u
 #endif
-#define BRO_SCRATCH_U16 ((sizeof(BroScratch) / 2u + 7u) & ~7u)
 // the stride is an odd number of 128-byte lines, so that the threads' root tables do not pile into a few cache sets
 #define BRO_THREAD_ARENA_STRIDE_U16 (BRO_THREAD_ARENA_U16 + 704u)
 
@@ -38,14 +37,18 @@ __global__ void __launch_bounds__(BRO_PARSE_BLOCK, BRO_PARSE_MIN_BLOCKS) bro_par
     BroDec d;
     BroParse ps;
     BroMbInfo mb;
+    // The scratch of the table reader lives in LOCAL memory: the lanes of a warp read their scratch at the same index
+    // at the same time (they enter headers together), which local memory's lane-interleaved layout turns into one
+    // cache line per warp access; in the arena every access would be a separate trip to L2 / HBM.
+    BroScratch sc;
     uint32_t stream = 0;
     uint32_t waited = 0;          // warp-uniform: trips since the first lane reached a boundary
     bool exhausted = false;       // warp-uniform: the queue is empty
     ps.kind = BRO_K_DONE; ps.st = -1;   // st < 0: no stream to report
-    d.sc = (BroScratch*)arena;
+    d.sc = &sc;
     d.arena = arena;
     d.arena_cap = BRO_THREAD_ARENA_U16;
-    d.arena_base = BRO_SCRATCH_U16;
+    d.arena_base = 0;
     d.dict = p.dict;
     d.quirk_spec = p.quirk_spec;
     for (;;) {
@@ -96,7 +99,7 @@ __global__ void __launch_bounds__(BRO_PARSE_BLOCK, BRO_PARSE_MIN_BLOCKS) bro_par
                 if (ps.kind == BRO_K_HEADER) bro_parse_header(d, ps, mb);
             }
         } else waited = 0;
-        if (ps.kind < BRO_K_HEADER) bro_parse_step(d, ps, mb);
+        bro_parse_round(d, ps, mb);
     }
 }
 
