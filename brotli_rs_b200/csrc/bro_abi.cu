@@ -28,6 +28,7 @@ struct bro_ctx {
     int grid_t;               // parse kernel: persistent CTAs
     uint32_t num_threads;
     uint16_t* d_arena_t;      // parse kernel: 64 KiB arena per thread
+    uint16_t* d_roots; size_t roots_bytes;   // parse kernel: compact per-thread literal tables (bro_parse.h)
     int grid_c;               // copy kernel: persistent CTAs
     uint8_t* d_dict;
     uint32_t* d_counter;      // queue heads: [0] parse kernel, [1] warp kernel, [3] copy kernel; [2] retry count;
@@ -75,13 +76,22 @@ extern "C" int bro_ctx_create(bro_ctx** out, int device) {
         bro_copy_kernel_occupancy(&per_sm_c) != 0 || per_sm_c < 1) { free(ctx); return BRO_ST_CudaError; }
     ctx->grid = ctx->num_sms * per_sm;
     ctx->num_warps = (uint32_t)ctx->grid * (uint32_t)bro_warp_kernel_warps_per_cta();
+    // The parse kernel is bound by the latency of its table look-ups, i.e. by how many streams' tables stay in L2:
+    // BRO_B200_PARSE_BLOCKS caps its resident CTAs per SM (tuning knob).
+    // Measured on B200 (profiles/r01_kernel_variants.md): 3 CTAs (384 streams) per SM is the optimum.
+    int pb_want = 3;
+    const char* pb = getenv("BRO_B200_PARSE_BLOCKS");
+    if (pb && atoi(pb) >= 1) pb_want = atoi(pb);
+    if (pb_want < per_sm_t) per_sm_t = pb_want;
     ctx->grid_t = ctx->num_sms * per_sm_t;
     ctx->num_threads = (uint32_t)ctx->grid_t * (uint32_t)bro_parse_kernel_block();
     ctx->grid_c = ctx->num_sms * per_sm_c;
     ctx->mode = BRO_MODE_AUTO;
-    // A warp per stream is the lowest latency for a few streams; once there are more streams than resident warps the
-    // two-phase path (32 streams per warp in the entropy decode, then bandwidth-bound copies) wins.
-    ctx->twophase_threshold = ctx->num_warps;
+    // A warp per stream is the lowest latency per stream; the two-phase path (32 streams per warp in the entropy decode,
+    // then copies at memory speed) has the higher throughput.  It pays once the fused kernel would need many waves of
+    // its resident warps: measured on B200 (profiles/r01_bench.md), batches of 10 k and 52 k mixed streams are bound by
+    // their longest streams and are as fast or faster fused, 100 k-stream batches are 1.8x faster two-phase.
+    ctx->twophase_threshold = 12u * ctx->num_warps;
     const char* env = getenv("BRO_B200_MODE");
     if (env && !strcmp(env, "warp")) ctx->mode = BRO_MODE_WARP;
     if (env && (!strcmp(env, "twophase") || !strcmp(env, "thread"))) ctx->mode = BRO_MODE_TWOPHASE;
@@ -103,7 +113,7 @@ extern "C" void bro_ctx_destroy(bro_ctx* ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     cudaFree(ctx->d_arena); cudaFree(ctx->d_arena_t); cudaFree(ctx->d_dict); cudaFree(ctx->d_counter);
-    cudaFree(ctx->d_order); cudaFree(ctx->d_order_scratch); cudaFree(ctx->d_rec);
+    cudaFree(ctx->d_order); cudaFree(ctx->d_order_scratch); cudaFree(ctx->d_rec); cudaFree(ctx->d_roots);
     cudaFree(ctx->d_in); cudaFree(ctx->d_out); cudaFree(ctx->d_meta);
     for (int k = 0; k < 5; k++) if (ctx->ev[k]) cudaEventDestroy(ctx->ev[k]);
     free(ctx);
@@ -197,8 +207,13 @@ extern "C" int bro_batch_decode(bro_ctx* ctx, const uint8_t* d_in, const uint64_
         // dictionary words go into the slots, copies become records.  PHASE TWO: one warp per stream executes the
         // records (bro_copy_kernel).  Streams phase one cannot decode are left for the fused kernel's retry pass.
         int st;
-        if (!ctx->d_arena_t)   // 64 KiB per resident thread, allocated on first use
+        if (!ctx->d_arena_t) {   // 64 KiB per resident thread, allocated on first use
             BRO_CUDA(ctx, cudaMalloc(&ctx->d_arena_t, (size_t)ctx->num_threads * bro_parse_kernel_arena_bytes()));
+            ctx->roots_bytes = (size_t)ctx->num_threads * bro_parse_kernel_roots_bytes();
+            if (ctx->roots_bytes) {
+                BRO_CUDA(ctx, cudaMalloc(&ctx->d_roots, ctx->roots_bytes));
+            }
+        }
         if ((st = bro_grow(ctx, (void**)&ctx->d_order, &ctx->d_order_cap, (size_t)n, 2 * sizeof(uint32_t)))) return st;
         // the record arena is sized from the compressed bytes of the batch: the caller's bound (bro_ctx_reserve), else
         // the two end offsets are read back (16 bytes, blocking on `s`)
@@ -223,7 +238,7 @@ extern "C" int bro_batch_decode(bro_ctx* ctx, const uint8_t* d_in, const uint64_
         const uint32_t tb = (uint32_t)bro_parse_kernel_block();
         int grid_t = ctx->grid_t;
         if ((uint32_t)grid_t > (n + tb - 1) / tb) grid_t = (int)((n + tb - 1) / tb);
-        p.arena = ctx->d_arena_t; p.counter = ctx->d_counter; p.order = d_order;
+        p.arena = ctx->d_arena_t; p.counter = ctx->d_counter; p.order = d_order; p.roots = ctx->d_roots;
         if (ctx->timing) BRO_CUDA(ctx, cudaEventRecord(ctx->ev[1], s));
         e = (cudaError_t)bro_parse_kernel_launch(&p, grid_t, s);
         if (e != cudaSuccess) return bro_fail(ctx, e, "bro_parse_kernel launch");

@@ -39,7 +39,9 @@
 #define BRO_SERIAL 1
 #define BRO_FN __device__ __forceinline__
 #define BRO_COLD static __device__ __noinline__
-#define BRO_TABLE_QUAL static __constant__ const
+// every lane indexes the format tables with its own stream's symbol: global memory (L1) serves 32 different addresses in
+// one access, the constant cache would replay the load once per distinct address
+#define BRO_TABLE_QUAL static __device__ const
 #else
 #if defined(BRO_GROUP_W)
 #define BRO_W BRO_GROUP_W   /* lanes that cooperate on one stream: 32 (a warp), 16, 8 or 4 (sub-warp groups) */
@@ -100,20 +102,22 @@ BRO_FN uint32_t bro_funnel_r(uint32_t lo, uint32_t hi, unsigned sh) { return __f
 // ------------------------------------------------------------------------------------------------------
 // memory layout of the per-warp table arena (HBM, L1/L2 resident while a stream is being decoded)
 // ------------------------------------------------------------------------------------------------------
-// A prefix-code table ("tree record"), in uint16 units:
-//   [0..255]   root: indexed by the next 8 stream bits; entry = symbol | len<<10 (len 1..8),
+// A prefix-code table ("tree record"), in uint16 units (R = 1 << BRO_ROOT_BITS):
+//   [0..R)     root: indexed by the next BRO_ROOT_BITS stream bits; entry = symbol | len<<10 (len 1..BRO_ROOT_BITS),
 //              0 = no code starts with these bits (hole), 1 = a longer code does (search by length)
-//   [256..271] limit[L]: left-justified 15-bit end of all codes of length <= L (canonical order)
-//   [272..287] base[L]:  (int16) index into sorted[] of the first code of length L minus its code value
-//   [288] single-symbol flag (decode consumes zero bits: src/huffman/tree/mod.rs:87-91)
-//   [289] the single symbol   [290] max code length   [291] reserved
-//   [292..]    sorted[]: symbols in canonical order (by length, then by position)
-#define BRO_T_LIMIT 256
-#define BRO_T_BASE 272
-#define BRO_T_SINGLE 288
-#define BRO_T_SINGLE_SYM 289
-#define BRO_T_MAXDEPTH 290
-#define BRO_T_SORTED 292
+//   [R..R+16)  limit[L]: left-justified 15-bit end of all codes of length <= L (canonical order)
+//   [R+16..R+32) base[L]: (int16) index into sorted[] of the first code of length L minus its code value
+//   [R+32] single-symbol flag (decode consumes zero bits: src/huffman/tree/mod.rs:87-91)
+//   [R+33] the single symbol   [R+34] max code length   [R+35] reserved
+//   [R+36..]   sorted[]: symbols in canonical order (by length, then by position)
+#define BRO_ROOT_BITS 8u
+#define BRO_ROOT_SIZE (1u << BRO_ROOT_BITS)
+#define BRO_T_LIMIT (BRO_ROOT_SIZE)
+#define BRO_T_BASE (BRO_ROOT_SIZE + 16u)
+#define BRO_T_SINGLE (BRO_ROOT_SIZE + 32u)
+#define BRO_T_SINGLE_SYM (BRO_ROOT_SIZE + 33u)
+#define BRO_T_MAXDEPTH (BRO_ROOT_SIZE + 34u)
+#define BRO_T_SORTED (BRO_ROOT_SIZE + 36u)
 #define BRO_TREE_U16(alphabet) (((BRO_T_SORTED + (alphabet)) + 7u) & ~7u)
 
 // largest output slot one stream may use: positions are 32-bit and one command may add up to 2 * (2^24 + 22594) bytes
@@ -163,6 +167,9 @@ struct BroBits {
     const uint8_t* lo;      // first loadable word address (stream start rounded down to 4)
     const uint8_t* end;     // one past the last byte of the stream
     uint32_t w0, w1;        // bit window: two consecutive little-endian words of the stream; next bit = bit `bp` of w0
+#if defined(BRO_THREAD_MODE)
+    uint32_t w2;            // the word after the window, loaded one slide ahead so that a slide never waits for memory
+#endif
     uint32_t bp;            // 0..31
     uint32_t avail;         // real stream bits in the window from `bp` on (the rest of w0/w1 is padding past the end)
     uint32_t rem;           // real stream BYTES not yet loaded into the window (a stream is < 4 GiB)
@@ -218,11 +225,21 @@ BRO_FN void bro_bits_seek(BroBits& s, const uint8_t* a) {
     uint32_t sh = (uint32_t)(ai & 3u);
     s.w0 = bro_next_word(s);
     s.w1 = bro_next_word(s);
+#if defined(BRO_THREAD_MODE)
+    s.w2 = bro_next_word(s);
+#endif
     s.bp = 8u * sh;
+#if defined(BRO_THREAD_MODE)
+    // one thread per stream: `avail` counts ALL real bits from `bp` to the end of the stream (streams of 256 MiB and
+    // more are left to the fused kernel), so that a slide needs no bookkeeping at all
+    s.avail = 8u * left;
+    s.rem = 0;
+#else
     uint32_t in_window = 8u - sh;                                 // bytes of [a, ...) the two words cover
     if (in_window > left) in_window = left;
     s.avail = 8u * in_window;
     s.rem = left - in_window;
+#endif
 }
 
 BRO_FN void bro_bits_init(BroBits& s, const uint8_t* start, const uint8_t* end) {
@@ -243,15 +260,13 @@ BRO_FN void bro_refill(BroBits& s) {
     // one thread per stream: branch-free, so that the lanes of a warp (different streams, different bit positions)
     // share these instructions instead of taking the slide one group of lanes at a time
     const bool need = s.bp >= 32u;
-    uint32_t wn = 0;
-    if (need && s.chunk < s.end) wn = __ldg((const uint32_t*)s.chunk);   // chunk >= lo always holds here
-    const uint32_t got = need ? (s.rem < 4u ? s.rem : 4u) : 0u;
+    uint32_t wn = s.w2;
+    if (need) { wn = 0; if (s.chunk < s.end) wn = __ldg((const uint32_t*)s.chunk); }   // chunk >= lo always holds here
     s.w0 = need ? s.w1 : s.w0;
-    s.w1 = need ? wn : s.w1;
+    s.w1 = need ? s.w2 : s.w1;
+    s.w2 = wn;                                                            // not looked at before the next slide
     s.bp -= need ? 32u : 0u;
     s.chunk += need ? 4 : 0;
-    s.avail += 8u * got;
-    s.rem -= got;
     return;
 #endif
     if (s.bp >= 32u) {
@@ -289,7 +304,9 @@ BRO_FN bool bro_read_byte_tail(BroBits& s, uint32_t& v) {
 
 // byte address of the next unread bit (valid when byte aligned)
 BRO_FN const uint8_t* bro_bits_addr(const BroBits& s) {
-#if defined(BRO_SERIAL)
+#if defined(BRO_THREAD_MODE)
+    return s.chunk - 12 + (s.bp >> 3);
+#elif defined(BRO_SERIAL)
     return s.chunk - 8 + (s.bp >> 3);
 #else
     return s.chunk + 4u * s.wi - 8 + (s.bp >> 3);
@@ -309,11 +326,11 @@ BRO_FN const uint8_t* bro_bits_addr(const BroBits& s) {
 // is therefore EOF, and a hole is EOF unless max_depth+1 real bits remain.
 // Codes longer than 8 bits, single-symbol tables and holes: out of line, and it does not touch the window.
 // Returns symbol | length << 16 | BRO_SYM_* << 24.
-BRO_COLD uint32_t bro_sym_slow(const uint16_t* T, uint32_t peek, uint32_t e, uint32_t avail) {
+BRO_COLD uint32_t bro_sym_slow(const uint16_t* T, uint32_t peek, uint32_t e, uint32_t avail, uint32_t root_bits = BRO_ROOT_BITS) {
     if (T[BRO_T_SINGLE]) return (uint32_t)T[BRO_T_SINGLE_SYM];
     if (e == 1u) {
         uint32_t x = bro_brev(peek) >> 17;   // next 15 bits, first bit read most significant
-        uint32_t L = 9;
+        uint32_t L = root_bits + 1u;        // no code of at most root_bits bits starts here
         while (L <= 15u && x >= T[BRO_T_LIMIT + L]) L++;
         if (L <= 15u) {
             if (L > avail) return (uint32_t)BRO_SYM_EOF << 24;
@@ -328,7 +345,7 @@ BRO_COLD uint32_t bro_sym_slow(const uint16_t* T, uint32_t peek, uint32_t e, uin
 BRO_FN int bro_decode_sym2(BroBits& s, const uint16_t* root, const uint16_t* T, uint32_t& sym) {
     bro_refill(s);
     uint32_t peek = bro_peek(s);
-    uint32_t e = root[peek & 0xffu];
+    uint32_t e = root[peek & (BRO_ROOT_SIZE - 1u)];
     uint32_t len = e >> 10;
     if (len != 0u) {
         if (len > bro_avail(s)) return BRO_SYM_EOF;
@@ -343,6 +360,33 @@ BRO_FN int bro_decode_sym2(BroBits& s, const uint16_t* root, const uint16_t* T, 
 }
 
 BRO_FN int bro_decode_sym(BroBits& s, const uint16_t* T, uint32_t& sym) { return bro_decode_sym2(s, T, T, sym); }
+
+// The same through a narrower copy of the root kept on chip by the caller (parse kernel: shared memory): `root` has
+// 1 << root_bits entries; an entry is a direct hit (symbol | len<<10, len <= root_bits) or 1 = search by length in T.
+BRO_FN int bro_decode_sym_r(BroBits& s, const uint16_t* root, uint32_t root_bits, const uint16_t* T, uint32_t& sym) {
+    bro_refill(s);
+    uint32_t peek = bro_peek(s);
+    uint32_t e = root[peek & ((1u << root_bits) - 1u)];
+    uint32_t len = e >> 10;
+    if (len != 0u) {
+        if (len > bro_avail(s)) return BRO_SYM_EOF;
+        bro_consume(s, len);
+        sym = e & 0x3ffu;
+        return BRO_SYM_OK;
+    }
+    uint32_t r = bro_sym_slow(T, peek, 1u, bro_avail(s), root_bits);
+    bro_consume(s, (r >> 16) & 0xffu);
+    sym = r & 0xffffu;
+    return (int)(r >> 24);
+}
+
+// Fill such a copy from the table's own 8-bit root.
+BRO_FN void bro_narrow_root(uint16_t* root, uint32_t root_bits, const uint16_t* T) {
+    for (uint32_t r = 0; r < (1u << root_bits); r++) {
+        const uint32_t e = T[r], l = e >> 10;
+        root[r] = (uint16_t)((l >= 1u && l <= root_bits) ? e : 1u);
+    }
+}
 
 // Build a tree record from n (length, symbol) pairs in sc.lens[] (and sc.syms[] when `explicit_syms`), in
 // the order the reference inserts them: src/huffman/mod.rs:19-43 assigns canonical codes per length in array
@@ -378,11 +422,11 @@ BRO_COLD void bro_build_tree(uint16_t* T, BroScratch& sc, uint32_t n, bool expli
     // >= 2 non-zero lengths
     T[BRO_T_SINGLE] = (nonzero <= 1u) ? 1 : 0;
     T[BRO_T_MAXDEPTH] = (uint16_t)maxdepth;
-    T[291] = 0;
+    T[BRO_T_MAXDEPTH + 1u] = 0;
 #if defined(BRO_HOSTSIM)
-    for (uint32_t r = 0; r < 256u; r++) T[r] = 0;
+    for (uint32_t r = 0; r < BRO_ROOT_SIZE; r++) T[r] = 0;
 #else
-    for (uint32_t r = 0; r < 32u; r++) ((uint4*)T)[r] = make_uint4(0u, 0u, 0u, 0u);     // records are 16-byte aligned
+    for (uint32_t r = 0; r < BRO_ROOT_SIZE / 8u; r++) ((uint4*)T)[r] = make_uint4(0u, 0u, 0u, 0u);     // records are 16-byte aligned
 #endif
     uint32_t single_sym = 0;
     for (uint32_t i = 0; i < n; i++) {
@@ -395,10 +439,10 @@ BRO_COLD void bro_build_tree(uint16_t* T, BroScratch& sc, uint32_t n, bool expli
         if (nonzero == 1u) single_sym = symv;
         if (nonzero >= 2u) {
             const uint32_t c = (uint32_t)((int)idx - base[L]);      // the canonical code of this symbol
-            if (L <= 8u) {
+            if (L <= BRO_ROOT_BITS) {
                 const uint32_t e = symv | (L << 10);
-                for (uint32_t r = bro_brev(c) >> (32u - L); r < 256u; r += 1u << L) T[r] = (uint16_t)e;
-            } else T[bro_brev(c >> (L - 8u)) >> 24] = 1;
+                for (uint32_t r = bro_brev(c) >> (32u - L); r < BRO_ROOT_SIZE; r += 1u << L) T[r] = (uint16_t)e;
+            } else T[bro_brev(c >> (L - BRO_ROOT_BITS)) >> (32u - BRO_ROOT_BITS)] = 1;
         }
     }
     T[BRO_T_SINGLE_SYM] = (uint16_t)single_sym;
@@ -443,7 +487,7 @@ BRO_COLD void bro_build_tree(uint16_t* T, BroScratch& sc, uint32_t n, bool expli
         bool single = (nonzero == 1u) || (nonzero == 0u);
         T[BRO_T_SINGLE] = single ? 1 : 0;
         T[BRO_T_MAXDEPTH] = (uint16_t)maxdepth;
-        T[291] = 0;
+        T[BRO_T_MAXDEPTH + 1u] = 0;
     }
     bro_syncwarp();
     // pass 2: stable placement into sorted[] (rank inside the 32-symbol group + running position per length)
@@ -509,16 +553,48 @@ struct BroDec {
     BroRec* rec;              // copy records of this stream (phase one of the two-phase path writes, phase two executes)
     uint32_t nrec, rec_cap;
     const uint8_t* in_base;   // first byte of the compressed stream (stored-block records hold offsets from it)
+    uint16_t* roots;          // symbols of the current literal code in canonical order (bro_parse.h; HBM / L2 in the parse kernel)
+    uint16_t* roots_cd;       // roots of the current literal, insert&copy and distance tables (shared memory)
+    const uint32_t* ic;       // bro_ic_insert / bro_ic_copy interleaved (shared memory)
+    uint32_t out_mis;         // (address of out) & 15: pieces are cut at 16-byte boundaries of the destination ADDRESS
 #endif
 };
 
 #if defined(BRO_PARSE)
-BRO_FN bool bro_rec_push(BroDec& d, uint32_t dst, uint32_t len, uint32_t kind, uint32_t a) {
+BRO_FN bool bro_rec_push1(BroDec& d, uint32_t dst, uint32_t len, uint32_t kind, uint32_t a) {
     if (d.nrec >= d.rec_cap) return false;
     BroRec r;
     r.dst = dst; r.len_kind = len | (kind << BRO_REC_KIND_SHIFT); r.a = a; r.b = 0;
+#if defined(BRO_THREAD_MODE)
+    // written once, read once by the next kernel: streaming store, so that records do not push the prefix tables
+    // (looked up for every symbol) out of L2
+    __stcs((uint4*)(d.rec + d.nrec), make_uint4(r.dst, r.len_kind, r.a, r.b));
+    d.nrec++;
+#else
     d.rec[d.nrec++] = r;
+#endif
     return true;
+}
+
+// A copy becomes one record per PIECE of at most BRO_REC_PIECE_VECS 16-byte vectors on 16-byte aligned destinations
+// (plus the ragged bytes before the first and after the last vector), so that one step of the copy kernel's warp moves
+// one piece whatever the copy's length.  Pieces keep the copy's distance: a piece may read what an earlier piece of
+// the same copy wrote, which the copy kernel's grouping handles like any other dependency.  Only a copy whose distance
+// is shorter than a piece (a periodic fill) stays whole.
+BRO_FN bool bro_rec_push(BroDec& d, uint32_t dst, uint32_t len, uint32_t kind, uint32_t a) {
+    if (kind == BRO_REC_LZ && a < len && a < 16u * BRO_REC_PIECE_VECS + 32u) return bro_rec_push1(d, dst, len, kind, a);
+    // first piece: up to the 16-byte boundary plus BRO_REC_PIECE_VECS vectors; then whole pieces; the last few bytes
+    // (< 16) ride along as the tail of the piece before them
+    uint32_t piece = ((16u - ((d.out_mis + dst) & 15u)) & 15u) + 16u * BRO_REC_PIECE_VECS;
+    bool ok = true;
+    while (ok && len != 0u) {
+        if (len < piece + 16u) piece = len;
+        ok = bro_rec_push1(d, dst, piece, kind, a);
+        dst += piece; len -= piece;
+        if (kind == BRO_REC_STORED) a += piece;
+        piece = 16u * BRO_REC_PIECE_VECS;
+    }
+    return ok;
 }
 #endif
 

@@ -29,12 +29,16 @@ extern "C" int bro_hostsim_parse_decode(const uint8_t* in, size_t in_len, uint8_
     d.arena_base = 0;
     d.dict = bro_dictionary_blob;
     d.out = out;
+    d.out_mis = (uint32_t)((uintptr_t)out & 15u);
     d.cap = cap > BRO_MAX_SLOT ? (uint32_t)BRO_MAX_SLOT : (uint32_t)cap;
     d.pos = 0;
     d.p1 = d.p2 = 0;
     d.d0 = 4; d.d1 = 11; d.d2 = 15; d.d3 = 16;
     d.quirk_spec = quirks;
-    d.rec = rec; d.nrec = 0; d.rec_cap = rec_cap; d.in_base = in;
+    uint16_t roots[BRO_ROOTS_U16], roots_cd[BRO_ROOTS_CD_U16];
+    static uint32_t ic[2 * 704];
+    for (unsigned i = 0; i < 704; i++) { ic[2 * i] = bro_ic_insert[i]; ic[2 * i + 1] = bro_ic_copy[i]; }
+    d.rec = rec; d.nrec = 0; d.rec_cap = rec_cap; d.in_base = in; d.roots = roots; d.roots_cd = roots_cd; d.ic = ic;
     bro_bits_init(d.in, in, in + in_len);
     BroParse ps;
     BroMbInfo mb;

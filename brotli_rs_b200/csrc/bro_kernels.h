@@ -28,6 +28,7 @@ struct BroLaunch {
     BroRec* rec;
     uint64_t rec_total;
     uint32_t* nrec;           // n: records written for stream i
+    uint16_t* roots;          // parse kernel: per-thread decode tables (bro_parse.h) when they live in HBM / L2
     unsigned long long* copy_stats;   // [0] bytes moved by records, [1] records executed (this batch)
 };
 
@@ -43,6 +44,7 @@ extern "C" int bro_warp_kernel_launch(const BroLaunch* p, int grid, cudaStream_t
 extern "C" int bro_parse_kernel_occupancy(int* blocks_per_sm);
 extern "C" int bro_parse_kernel_block();
 extern "C" size_t bro_parse_kernel_arena_bytes();
+extern "C" size_t bro_parse_kernel_roots_bytes();
 extern "C" int bro_parse_kernel_launch(const BroLaunch* p, int grid, cudaStream_t stream);
 // two-phase path, phase two: the copy kernel (one warp per stream) (bro_kernels_copy.cu)
 extern "C" int bro_copy_kernel_occupancy(int* blocks_per_sm);

@@ -6,11 +6,14 @@
 //
 // The records of a stream must take effect in order, but most neighbours do not depend on each other.  The warp loads
 // 32 records at a time (one per lane, coalesced) and splits them into GROUPS: a maximal run of records none of which
-// reads a byte that a record of the same run writes.  A group is executed as ONE segmented copy: the bytes of all its
-// records are cut into units (16-byte vector units on 16-byte aligned destinations, single bytes for the ragged
-// ends), the units are numbered by a warp prefix sum, and every lane takes every 32nd unit, finding its record by a
-// binary search over the prefix sums with shuffles.  All 32 lanes therefore move data in every step whatever the
-// record lengths are, all loads of a step are independent, and the only serialisation left is between groups.
+// reads a byte that a record of the same run writes.  Inside a group nothing has to be ordered:
+//   * a group of LONG records (phase one cuts every copy into pieces of at most 32 aligned 16-byte vectors) moves one
+//     piece per warp step -- lane t moves vector t plus the t-th ragged byte at each end -- with several pieces in
+//     flight: all loads are issued before the first store;
+//   * a group of SHORT records (text-like streams) is executed as ONE segmented copy: the bytes of all its records are
+//     cut into units (16-byte vectors on aligned destinations, single bytes for the ragged ends), the units are
+//     numbered by a warp prefix sum, and every lane takes every 32nd unit, finding its record by a binary search over
+//     the prefix sums with shuffles; the sources are staged through shared memory by cp.async, several rounds deep.
 // A record that overlaps its own source (distance < length, a periodic fill) is executed alone by doubling: each pass
 // copies the whole pattern laid down so far.
 //
@@ -26,7 +29,10 @@
 #define BRO_COPY_WARPS 8
 #endif
 #ifndef BRO_COPY_MIN_BLOCKS
-#define BRO_COPY_MIN_BLOCKS 6
+#define BRO_COPY_MIN_BLOCKS 3
+#endif
+#ifndef BRO_COPY_PIECES
+#define BRO_COPY_PIECES 4     // long records: pieces in flight per warp (their data is held in registers)
 #endif
 #ifndef BRO_COPY_DEPTH
 #define BRO_COPY_DEPTH 4      // rounds of 32 units in flight per warp; 1 KiB of staging per round and warp
@@ -133,6 +139,65 @@ __global__ void __launch_bounds__(WARPS * 32, BRO_COPY_MIN_BLOCKS) bro_copy_kern
                 uint32_t head = (16u - ((dst + out_mis) & 15u)) & 15u;
                 if (head > len) head = len;
                 const uint32_t nvec = (len - head) >> 4, tail = (len - head) & 15u;
+                // LONG records (phase one cuts copies into pieces of <= 32 vectors): one piece per warp step -- lane t
+                // moves vector t, lanes 0..15 the ragged bytes in front, lanes 16..31 those behind -- with
+                // BRO_COPY_PIECES pieces in flight (all loads are issued before the first store) and no search.
+                const uint32_t gsum = __reduce_add_sync(0xffffffffu, mine ? len : 0u);
+                if (gsum >= 192u * (e - j) && !__any_sync(0xffffffffu, mine && nvec > 32u)) {
+                    // per record (lane-local, broadcast per piece): source address and geometry
+                    const uint8_t* sp = kind == BRO_REC_STORED ? in + a : (const uint8_t*)out + (dst - a);
+                    const uint32_t sp_lo = (uint32_t)(uintptr_t)sp, sp_hi = (uint32_t)((uintptr_t)sp >> 32);
+                    const uint32_t geo = head | (nvec << 8) | (tail << 16) | (((sp_lo + head) & 15u) << 24) | 0x80000000u;
+                    const uint32_t bl = lane & 15u;
+                    const bool back = lane >= 16u;
+                    for (uint32_t k0 = j; k0 < e; k0 += BRO_COPY_PIECES) {
+                        uint4 A[BRO_COPY_PIECES], B[BRO_COPY_PIECES];
+                        uint32_t bv[BRO_COPY_PIECES], m_dst[BRO_COPY_PIECES], m_geo[BRO_COPY_PIECES];
+#pragma unroll
+                        for (int r = 0; r < BRO_COPY_PIECES; r++) {
+                            m_geo[r] = 0;
+                            if (k0 + r >= e) continue;                                   // warp-uniform
+                            const int k = (int)(k0 + r);
+                            const uint32_t g = __shfl_sync(0xffffffffu, geo, k);
+                            const uintptr_t s0 = (uintptr_t)__shfl_sync(0xffffffffu, sp_lo, k) |
+                                                 ((uintptr_t)__shfl_sync(0xffffffffu, sp_hi, k) << 32);
+                            m_dst[r] = __shfl_sync(0xffffffffu, dst, k);
+                            m_geo[r] = g;
+                            const uint32_t r_head = g & 0xffu, r_nvec = (g >> 8) & 0xffu, r_tail = (g >> 16) & 0xffu;
+                            const uint32_t vbase = r_head + 16u * lane;
+                            // ragged bytes: lanes 0..15 in front of the vectors, lanes 16..31 behind them
+                            if (bl < (back ? r_tail : r_head)) bv[r] = *(const uint8_t*)(s0 + (back ? r_head + 16u * r_nvec : 0u) + bl);
+                            if (lane < r_nvec) {
+                                const uint4* q = (const uint4*)((s0 + vbase) & ~(uintptr_t)15);
+                                A[r] = q[0];
+                                if (g & 0x0f000000u) B[r] = q[1];
+                            }
+                        }
+#pragma unroll
+                        for (int r = 0; r < BRO_COPY_PIECES; r++) {
+                            const uint32_t g = m_geo[r];
+                            if (g == 0u) continue;                                       // warp-uniform
+                            const uint32_t r_head = g & 0xffu, r_nvec = (g >> 8) & 0xffu, r_tail = (g >> 16) & 0xffu, sh = (g >> 24) & 15u;
+                            uint8_t* dp = out + m_dst[r];
+                            if (bl < (back ? r_tail : r_head)) dp[(back ? r_head + 16u * r_nvec : 0u) + bl] = (uint8_t)bv[r];
+                            if (lane < r_nvec) {
+                                uint4 v = A[r];
+                                if (sh) {
+                                    uint32_t w0 = v.x, w1 = v.y, w2 = v.z, w3 = v.w, w4 = B[r].x, w5 = B[r].y, w6 = B[r].z, w7 = B[r].w;
+                                    if (sh & 8u) { w0 = w2; w1 = w3; w2 = w4; w3 = w5; w4 = w6; w5 = w7; }
+                                    if (sh & 4u) { w0 = w1; w1 = w2; w2 = w3; w3 = w4; w4 = w5; }
+                                    const unsigned bs = 8u * (sh & 3u);
+                                    v.x = __funnelshift_r(w0, w1, bs); v.y = __funnelshift_r(w1, w2, bs);
+                                    v.z = __funnelshift_r(w2, w3, bs); v.w = __funnelshift_r(w3, w4, bs);
+                                }
+                                *(uint4*)(dp + r_head + 16u * lane) = v;
+                            }
+                        }
+                    }
+                    j = e;
+                    continue;
+                }
+                // SHORT records: one segmented copy over all units of the group
                 const uint32_t units = mine ? head + nvec + tail : 0u;
                 uint32_t incl = units;
 #pragma unroll

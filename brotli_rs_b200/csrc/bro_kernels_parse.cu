@@ -22,8 +22,13 @@
 #define BRO_PARSE_BLOCK 128
 #endif
 #ifndef BRO_PARSE_MIN_BLOCKS
+#if defined(BRO_PARSE_LIT_SMEM)
+#define BRO_PARSE_MIN_BLOCKS 2
+#else
 #define BRO_PARSE_MIN_BLOCKS 4
 #endif
+#endif
+#define BRO_PARSE_SMEM (BRO_PARSE_BLOCK * BRO_ROOTS_CD_U16 * 2u)     // 32 KiB, or 96 KiB with the literal root (2 CTAs per SM)
 #ifndef BRO_PARSE_PATIENCE
 #define BRO_PARSE_PATIENCE 1024u
 #endif
@@ -41,11 +46,21 @@ __global__ void __launch_bounds__(BRO_PARSE_BLOCK, BRO_PARSE_MIN_BLOCKS) bro_par
     // at the same time (they enter headers together), which local memory's lane-interleaved layout turns into one
     // cache line per warp access; in the arena every access would be a separate trip to L2 / HBM.
     BroScratch sc;
+    // shared memory: per thread the roots of its current insert&copy and distance tables (256 B) [and of its literal
+    // table, 512 B], per CTA the insert/copy length table; the rest of a thread's literal table is in the compact HBM
+    // array p.roots (bro_parse.h)
+    extern __shared__ __align__(16) uint16_t s_roots_cd[];
+    __shared__ uint32_t s_ic[2 * 704];
+    for (unsigned i = threadIdx.x; i < 704u; i += BRO_PARSE_BLOCK) { s_ic[2 * i] = bro_ic_insert[i]; s_ic[2 * i + 1] = bro_ic_copy[i]; }
+    __syncthreads();
     uint32_t stream = 0;
     uint32_t waited = 0;          // warp-uniform: trips since the first lane reached a boundary
     bool exhausted = false;       // warp-uniform: the queue is empty
     ps.kind = BRO_K_DONE; ps.st = -1;   // st < 0: no stream to report
     d.sc = &sc;
+    d.roots = p.roots + (size_t)t * BRO_ROOTS_U16;
+    d.roots_cd = s_roots_cd + (size_t)threadIdx.x * BRO_ROOTS_CD_U16;
+    d.ic = s_ic;
     d.arena = arena;
     d.arena_cap = BRO_THREAD_ARENA_U16;
     d.arena_base = 0;
@@ -79,6 +94,7 @@ __global__ void __launch_bounds__(BRO_PARSE_BLOCK, BRO_PARSE_MIN_BLOCKS) bro_par
                             const uint64_t in_b = p.in_off[stream], in_e = p.in_off[stream + 1];
                             const uint64_t out_b = p.out_off[stream], out_e = p.out_off[stream + 1];
                             d.out = p.out + out_b;
+                            d.out_mis = (uint32_t)((uintptr_t)d.out & 15u);
                             const uint64_t cap = out_e - out_b;
                             d.cap = cap > BRO_MAX_SLOT ? (uint32_t)BRO_MAX_SLOT : (uint32_t)cap;
                             d.pos = 0;
@@ -92,6 +108,7 @@ __global__ void __launch_bounds__(BRO_PARSE_BLOCK, BRO_PARSE_MIN_BLOCKS) bro_par
                             bro_bits_init(d.in, p.in + in_b, p.in + in_e);
                             bro_parse_begin(ps);
                             if (rec_b + rec_n > p.rec_total) bro_parse_finish(ps, BRO_ST_RecordsFull);
+                            if (in_e - in_b >= (1ull << 28)) bro_parse_finish(ps, BRO_ST_NeedFused);   // 32-bit bit counts
                         }
                     }
                 }
@@ -145,12 +162,15 @@ extern "C" int bro_order_launch(const uint64_t* in_off, uint32_t n, uint32_t* or
 }
 
 extern "C" int bro_parse_kernel_occupancy(int* blocks_per_sm) {
-    return (int)cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, bro_parse_kernel, BRO_PARSE_BLOCK, 0);
+    cudaError_t e = cudaFuncSetAttribute(bro_parse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BRO_PARSE_SMEM);
+    if (e != cudaSuccess) return (int)e;
+    return (int)cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, bro_parse_kernel, BRO_PARSE_BLOCK, BRO_PARSE_SMEM);
 }
 extern "C" int bro_parse_kernel_block() { return BRO_PARSE_BLOCK; }
 extern "C" size_t bro_parse_kernel_arena_bytes() { return 2u * (size_t)BRO_THREAD_ARENA_STRIDE_U16; }
+extern "C" size_t bro_parse_kernel_roots_bytes() { return 2u * (size_t)BRO_ROOTS_U16; }   // per thread, in HBM
 
 extern "C" int bro_parse_kernel_launch(const BroLaunch* p, int grid, cudaStream_t stream) {
-    bro_parse_kernel<<<grid, BRO_PARSE_BLOCK, 0, stream>>>(*p);
+    bro_parse_kernel<<<grid, BRO_PARSE_BLOCK, BRO_PARSE_SMEM, stream>>>(*p);
     return (int)cudaGetLastError();
 }

@@ -29,7 +29,39 @@
 #define BRO_K_COPY 3u      // next: distance resolution and the copy itself  (src/lib.rs:1412-1542)
 #define BRO_K_HEADER 6u    // at a meta-block boundary (or before the stream header): structured code
 #define BRO_K_DONE 7u      // no stream
-#define BRO_PARSE_LITS_PER_ROUND 4
+#ifndef BRO_PARSE_LITS_PER_ROUND
+#define BRO_PARSE_LITS_PER_ROUND 8
+#endif
+
+// What bounds this kernel is not instruction issue but the number of L2 / HBM round trips on a lane's critical path:
+// one per look-up in a table of the arena, one per access to a spilled variable (the threads' stacks do not fit L1).
+// So everything a round touches is kept close: the state below in registers (the canonical limits and bases of the
+// literal code included); the 8-bit root of the current literal table, 6-bit roots of the current insert&copy and
+// distance tables (their alphabets are skewed: the codes that matter are short; longer ones take the search in the HBM
+// table) and the insert/copy length table in shared memory; the symbols of the literal code in canonical order, needed
+// only for codes longer than 8 bits, in a compact HBM array.
+#define BRO_RB_LIT 8u
+#define BRO_RB_CMD 6u
+#define BRO_RB_DIST 6u
+// Two placements of the literal root, both measured on B200 (profiles/r01_kernel_variants.md):
+//   default: in the thread's compact HBM array (an L2 round trip per literal) -- 256 B of shared memory per thread
+//            (insert&copy and distance roots), 384 streams per SM: best on the headline high-ratio workload;
+//   BRO_PARSE_LIT_SMEM: in shared memory -- 768 B per thread, 256 streams per SM: best on literal-heavy streams.
+// d.roots (HBM, L2): the 256 symbols of the literal code in canonical order, one byte each (looked up only for a code
+// longer than 8 bits) [, the 8-bit literal root]
+#define BRO_ROOTS_LIT_SORTED 0u
+#if defined(BRO_PARSE_LIT_SMEM)
+#define BRO_ROOTS_U16 128u
+#define BRO_LIT_ROOT(d) ((d).roots_cd + BRO_ROOTS_CMD + (1u << BRO_RB_CMD) + (1u << BRO_RB_DIST))
+#define BRO_ROOTS_CD_U16 ((1u << BRO_RB_CMD) + (1u << BRO_RB_DIST) + (1u << BRO_RB_LIT))
+#else
+#define BRO_ROOTS_U16 (128u + (1u << BRO_RB_LIT))
+#define BRO_LIT_ROOT(d) ((d).roots + 128u)
+#define BRO_ROOTS_CD_U16 ((1u << BRO_RB_CMD) + (1u << BRO_RB_DIST))
+#endif
+// d.roots_cd (shared memory): 6-bit roots of the insert&copy and the distance table [, the 8-bit literal root]
+#define BRO_ROOTS_CMD 0u
+#define BRO_ROOTS_DIST (1u << BRO_RB_CMD)
 
 #if defined(BRO_HOSTSIM)
 BRO_FN bool bro_any(bool p) { return p; }
@@ -47,18 +79,73 @@ struct BroParse {
     uint32_t need_dist;       // the command carries an explicit distance code (symbol >= 128)
     uint32_t mb_begin, mlen;  // meta-block: output position at its start, MLEN
     uint32_t blen0, blen1, blen2;   // symbols left in the current block per category (valid when the category has >= 2 types)
-    uint32_t multi;           // bit c: category c has >= 2 block types
+    uint32_t multi;           // bit c: category c has >= 2 block types; bit 3: one distance table (its root is on chip)
     uint32_t is_last;         // ISLAST of the current meta-block
     uint32_t started;         // the stream header has been read
+    uint32_t npostfix, ndirect, o_dist;   // of the current meta-block (copies of BroMbInfo fields, which lives on the stack)
+    // the current literal code beyond its root: limit[9..15] and base[9..15] (two per word), maximum length, single symbol
+    uint32_t lit_lim[4], lit_base[4], lit_misc;   // lit_misc = max length | single flag << 8 | single symbol << 16
     int st;                   // final status once kind == BRO_K_DONE
 };
 
 BRO_FN void bro_parse_begin(BroParse& ps) {
     ps.kind = BRO_K_HEADER; ps.toff_cmd = 0; ps.toff_lit = 0; ps.ins_rem = 0; ps.copy_len = 0; ps.dcode = 0; ps.need_dist = 0;
     ps.mb_begin = 0; ps.mlen = 0; ps.blen0 = ps.blen1 = ps.blen2 = 0; ps.multi = 0; ps.is_last = 0; ps.started = 0; ps.st = 0;
+    ps.npostfix = 0; ps.ndirect = 0; ps.o_dist = 0; ps.lit_misc = 0;
+    for (int i = 0; i < 4; i++) { ps.lit_lim[i] = 0; ps.lit_base[i] = 0; }
 }
 
 BRO_FN void bro_parse_finish(BroParse& ps, int st) { ps.st = st; ps.kind = BRO_K_DONE; }
+
+// Make T the current literal table: root and canonical-order symbols into the thread's compact array, limits and bases
+// of the long codes into registers.
+BRO_FN void bro_parse_load_lit(BroParse& ps, uint16_t* roots, uint16_t* lit_root, const uint16_t* T) {
+    bro_narrow_root(lit_root, BRO_RB_LIT, T);
+#pragma unroll
+    for (uint32_t k = 0; k < 4u; k++) {
+        // word k holds lengths 9 + 2k (low half) and 10 + 2k (high half); length 16 does not exist: limit 0xffff
+        const uint32_t L0 = 9u + 2u * k, L1 = 10u + 2u * k;
+        ps.lit_lim[k] = (uint32_t)T[BRO_T_LIMIT + L0] | ((L1 <= 15u ? (uint32_t)T[BRO_T_LIMIT + L1] : 0xffffu) << 16);
+        ps.lit_base[k] = (uint32_t)T[BRO_T_BASE + L0] | ((L1 <= 15u ? (uint32_t)T[BRO_T_BASE + L1] : 0u) << 16);
+    }
+    ps.lit_misc = (uint32_t)T[BRO_T_MAXDEPTH] | (T[BRO_T_SINGLE] ? 0x100u : 0u) | ((uint32_t)T[BRO_T_SINGLE_SYM] << 16);
+    uint8_t* sorted = (uint8_t*)(roots + BRO_ROOTS_LIT_SORTED);
+    for (uint32_t i = 0; i < 256u; i++) sorted[i] = (uint8_t)T[BRO_T_SORTED + i];
+}
+
+// One literal (same results as bro_decode_sym on the table; src/huffman/tree/mod.rs:63-92): one look-up in the root,
+// and for a code longer than 8 bits a search of the limits held in registers and one look-up of the symbol.
+BRO_FN int bro_parse_decode_lit(BroBits& s, const BroParse& ps, const uint16_t* roots, const uint16_t* lit_root, uint32_t& sym) {
+    bro_refill(s);
+    const uint32_t peek = bro_peek(s), avail = bro_avail(s);
+    const uint32_t e = lit_root[peek & 0xffu];
+    uint32_t len = e >> 10;
+    int r = BRO_SYM_OK;
+    sym = e & 0x3ffu;
+    if (len == 0u) {
+        if (ps.lit_misc & 0x100u) sym = ps.lit_misc >> 16;                    // one symbol: zero bits
+        else {
+            const uint32_t x = bro_brev(peek) >> 17;                           // next 15 bits, first bit read most significant
+            // smallest L in 9..15 with x < limit[L] (limits grow with L)
+            uint32_t L = 16u, base = 0;
+#pragma unroll
+            for (int k = 3; k >= 0; k--) {
+                const uint32_t lo = ps.lit_lim[k] & 0xffffu, hi = ps.lit_lim[k] >> 16;
+                if (k < 3 && x < hi) { L = 10u + 2u * (uint32_t)k; base = ps.lit_base[k] >> 16; }
+                if (x < lo) { L = 9u + 2u * (uint32_t)k; base = ps.lit_base[k] & 0xffffu; }
+            }
+            if (L <= 15u) {
+                len = L;
+                sym = ((const uint8_t*)(roots + BRO_ROOTS_LIT_SORTED))[((int)(int16_t)base + (int)(x >> (15u - L))) & 255];
+            } else r = (avail >= (ps.lit_misc & 0xffu) + 1u) ? BRO_SYM_HOLE : BRO_SYM_EOF;
+        }
+    }
+    if (r == BRO_SYM_OK) {
+        if (len > avail) r = BRO_SYM_EOF;
+        else bro_consume(s, len);
+    }
+    return r;
+}
 
 // Table of a symbol of category c (0 literal, 1 insert&copy, 2 distance) under the current block types.
 BRO_FN uint32_t bro_parse_table(const BroDec& d, const BroParse& ps, const BroMbInfo& mb, uint32_t c) {
@@ -90,8 +177,8 @@ BRO_FN bool bro_parse_block_step(BroDec& d, BroParse& ps, BroMbInfo& mb, uint32_
         mb.cat[c] = tc;
         if (st) { bro_parse_finish(ps, st); return false; }
         bl = tc.blen + 1u;
-        if (c == 0u) ps.toff_lit = bro_parse_table(d, ps, mb, 0u);
-        else if (c == 1u) ps.toff_cmd = bro_parse_table(d, ps, mb, 1u);
+        if (c == 0u) { ps.toff_lit = bro_parse_table(d, ps, mb, 0u); bro_parse_load_lit(ps, d.roots, BRO_LIT_ROOT(d), d.arena + ps.toff_lit); }
+        else if (c == 1u) { ps.toff_cmd = bro_parse_table(d, ps, mb, 1u); bro_narrow_root(d.roots_cd + BRO_ROOTS_CMD, BRO_RB_CMD, d.arena + ps.toff_cmd); }
     }
     bl -= 1u;
     if (c == 0u) ps.blen0 = bl; else if (c == 1u) ps.blen1 = bl; else ps.blen2 = bl;
@@ -124,6 +211,10 @@ BRO_FN void bro_parse_header(BroDec& d, BroParse& ps, BroMbInfo& mb) {
             ps.blen0 = mb.cat[0].blen; ps.blen1 = mb.cat[1].blen; ps.blen2 = mb.cat[2].blen;
             ps.toff_cmd = bro_parse_table(d, ps, mb, 1u);
             ps.toff_lit = bro_parse_table(d, ps, mb, 0u);
+            bro_parse_load_lit(ps, d.roots, BRO_LIT_ROOT(d), d.arena + ps.toff_lit);
+            bro_narrow_root(d.roots_cd + BRO_ROOTS_CMD, BRO_RB_CMD, d.arena + ps.toff_cmd);
+            if (mb.ntd == 1u) { ps.multi |= 8u; bro_narrow_root(d.roots_cd + BRO_ROOTS_DIST, BRO_RB_DIST, d.arena + mb.o_dist); }
+            ps.npostfix = mb.npostfix; ps.ndirect = mb.ndirect; ps.o_dist = mb.o_dist;
             ps.kind = BRO_K_CMD;
             return;
         }
@@ -139,12 +230,20 @@ BRO_FN void bro_parse_round(BroDec& d, BroParse& ps, BroMbInfo& mb) {
     // ---- step 1: insert&copy command symbol and its extra bits ----
     if (ps.kind == BRO_K_CMD && bro_parse_block_step(d, ps, mb, 1u)) {
         uint32_t sym = 0;
-        const int r = bro_decode_sym(d.in, d.arena + ps.toff_cmd, sym);
+        const int r = bro_decode_sym_r(d.in, d.roots_cd + BRO_ROOTS_CMD, BRO_RB_CMD, d.arena + ps.toff_cmd, sym);
         if (r != BRO_SYM_OK) bro_parse_finish(ps, r == BRO_SYM_HOLE ? BRO_ST_ParseErrorInsertAndCopyLength : BRO_ST_UnexpectedEOF);
         else {
-            const uint32_t ie = bro_ic_insert[sym], ce = bro_ic_copy[sym];
+            const uint32_t ie = d.ic[2u * sym], ce = d.ic[2u * sym + 1u];        // bro_ic_insert / bro_ic_copy, interleaved on chip
             uint32_t insert_len = ie & 0xffffu, copy_len = ce & 0xffffu, extra = 0, extra2 = 0;
-            const bool ok = bro_read_bits(d.in, ie >> 16, extra) && bro_read_bits(d.in, ce >> 16, extra2);   // insert extra bits first
+            const uint32_t ib = ie >> 16, cb = ce >> 16;                   // insert extra bits come first
+            bool ok;
+            if (ib + cb <= 25u) {
+                // both fields from one window read (the common case: short lengths carry few extra bits)
+                uint32_t v = 0;
+                ok = bro_read_bits(d.in, ib + cb, v);
+                extra = v & ((1u << ib) - 1u);
+                extra2 = v >> ib;
+            } else ok = bro_read_bits(d.in, ib, extra) && bro_read_bits(d.in, cb, extra2);
             insert_len += extra;
             copy_len += extra2;
             if (!ok) bro_parse_finish(ps, BRO_ST_UnexpectedEOF);
@@ -162,7 +261,7 @@ BRO_FN void bro_parse_round(BroDec& d, BroParse& ps, BroMbInfo& mb) {
         if (!bro_any(ps.kind == BRO_K_LIT)) break;
         if (ps.kind == BRO_K_LIT && bro_parse_block_step(d, ps, mb, 0u)) {
             uint32_t sym = 0;
-            const int r = bro_decode_sym(d.in, d.arena + ps.toff_lit, sym);
+            const int r = bro_parse_decode_lit(d.in, ps, d.roots, BRO_LIT_ROOT(d), sym);
             if (r != BRO_SYM_OK) bro_parse_finish(ps, r == BRO_SYM_HOLE ? BRO_ST_ParseErrorInsertLiterals : BRO_ST_UnexpectedEOF);
             else {
                 // a run that does not fit the slot is still decoded: a decode error inside it wins over OutputTooSmall
@@ -175,14 +274,15 @@ BRO_FN void bro_parse_round(BroDec& d, BroParse& ps, BroMbInfo& mb) {
     // ---- step 3: distance code ----
     if (ps.kind == BRO_K_DIST && bro_parse_block_step(d, ps, mb, 2u)) {
         uint32_t sym = 0;
-        const int r = bro_decode_sym(d.in, d.arena + bro_parse_table(d, ps, mb, 2u), sym);
+        const int r = (ps.multi & 8u) ? bro_decode_sym_r(d.in, d.roots_cd + BRO_ROOTS_DIST, BRO_RB_DIST, d.arena + ps.o_dist, sym)
+                                      : bro_decode_sym(d.in, d.arena + bro_parse_table(d, ps, mb, 2u), sym);
         if (r != BRO_SYM_OK) bro_parse_finish(ps, r == BRO_SYM_HOLE ? BRO_ST_ParseErrorDistanceCode : BRO_ST_UnexpectedEOF);
         else { ps.dcode = sym; ps.kind = BRO_K_COPY; }
     }
     // ---- step 4: distance, then the copy: a record for phase two, or a dictionary word emitted here ----
     if (ps.kind == BRO_K_COPY) {
         uint32_t distance = 0, max_allowed = 0;
-        int st = bro_resolve_distance(d, ps.dcode, mb.npostfix, mb.ndirect, distance, max_allowed);
+        int st = bro_resolve_distance(d, ps.dcode, ps.npostfix, ps.ndirect, distance, max_allowed);
         const uint32_t mb_out = d.pos - ps.mb_begin, copy_len = ps.copy_len;
         if (!st) {
             if (distance <= max_allowed) {

@@ -15,6 +15,8 @@ struct alignas(16) BroRec {
 #define BRO_REC_LEN_MASK 0x0fffffffu
 #define BRO_REC_LZ 0u
 #define BRO_REC_STORED 1u
+#define BRO_REC_PIECE_VECS 32u    /* a record moves at most this many aligned 16-byte vectors (+ < 16 ragged bytes at each end),
+                                    unless it is a periodic fill (distance < length, distance shorter than a piece) */
 
 // Stream i owns records [BRO_REC_BASE(in_off, i), BRO_REC_BASE(in_off, i + 1)) of the record arena: one record per 2
 // compressed bytes + 32.  A stream that needs more is handed to the fused kernel (BRO_ST_RecordsFull).
