@@ -88,10 +88,10 @@ extern "C" int bro_ctx_create(bro_ctx** out, int device) {
     ctx->grid_c = ctx->num_sms * per_sm_c;
     ctx->mode = BRO_MODE_AUTO;
     // A warp per stream is the lowest latency per stream; the two-phase path (32 streams per warp in the entropy decode,
-    // then copies at memory speed) has the higher throughput.  It pays once the fused kernel would need many waves of
-    // its resident warps: measured on B200 (profiles/r01_bench.md), batches of 10 k and 52 k mixed streams are bound by
-    // their longest streams and are as fast or faster fused, 100 k-stream batches are 1.8x faster two-phase.
-    ctx->twophase_threshold = 12u * ctx->num_warps;
+    // then copies at memory speed) has the higher throughput.  It pays once the fused kernel would need several waves
+    // of its resident warps; measured on B200 with the headline streams (profiles/r01_kernel_variants.md) the break-even
+    // is near 4 waves.
+    ctx->twophase_threshold = 5u * ctx->num_warps;
     const char* env = getenv("BRO_B200_MODE");
     if (env && !strcmp(env, "warp")) ctx->mode = BRO_MODE_WARP;
     if (env && (!strcmp(env, "twophase") || !strcmp(env, "thread"))) ctx->mode = BRO_MODE_TWOPHASE;

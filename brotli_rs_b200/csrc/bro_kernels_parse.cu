@@ -19,10 +19,16 @@
 #include "bro_kernels.h"
 
 #ifndef BRO_PARSE_BLOCK
+#if defined(BRO_PARSE_ALL_SMEM)
+#define BRO_PARSE_BLOCK 192
+#else
 #define BRO_PARSE_BLOCK 128
 #endif
+#endif
 #ifndef BRO_PARSE_MIN_BLOCKS
-#if defined(BRO_PARSE_LIT_SMEM)
+#if defined(BRO_PARSE_ALL_SMEM)
+#define BRO_PARSE_MIN_BLOCKS 1
+#elif defined(BRO_PARSE_LIT_SMEM)
 #define BRO_PARSE_MIN_BLOCKS 2
 #else
 #define BRO_PARSE_MIN_BLOCKS 4

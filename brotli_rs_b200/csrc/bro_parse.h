@@ -49,14 +49,21 @@
 //   BRO_PARSE_LIT_SMEM: in shared memory -- 768 B per thread, 256 streams per SM: best on literal-heavy streams.
 // d.roots (HBM, L2): the 256 symbols of the literal code in canonical order, one byte each (looked up only for a code
 // longer than 8 bits) [, the 8-bit literal root]
-#define BRO_ROOTS_LIT_SORTED 0u
-#if defined(BRO_PARSE_LIT_SMEM)
+#if defined(BRO_PARSE_ALL_SMEM)
+//   BRO_PARSE_ALL_SMEM: root and symbols in shared memory -- 1,024 B per thread, one CTA of 192 streams per SM.
+#define BRO_ROOTS_U16 8u
+#define BRO_LIT_ROOT(d) ((d).roots_cd + BRO_ROOTS_CMD + (1u << BRO_RB_CMD) + (1u << BRO_RB_DIST))
+#define BRO_LIT_SORTED(d) ((d).roots_cd + BRO_ROOTS_CMD + (1u << BRO_RB_CMD) + (1u << BRO_RB_DIST) + (1u << BRO_RB_LIT))
+#define BRO_ROOTS_CD_U16 ((1u << BRO_RB_CMD) + (1u << BRO_RB_DIST) + (1u << BRO_RB_LIT) + 128u)
+#elif defined(BRO_PARSE_LIT_SMEM)
 #define BRO_ROOTS_U16 128u
 #define BRO_LIT_ROOT(d) ((d).roots_cd + BRO_ROOTS_CMD + (1u << BRO_RB_CMD) + (1u << BRO_RB_DIST))
+#define BRO_LIT_SORTED(d) ((d).roots)
 #define BRO_ROOTS_CD_U16 ((1u << BRO_RB_CMD) + (1u << BRO_RB_DIST) + (1u << BRO_RB_LIT))
 #else
 #define BRO_ROOTS_U16 (128u + (1u << BRO_RB_LIT))
 #define BRO_LIT_ROOT(d) ((d).roots + 128u)
+#define BRO_LIT_SORTED(d) ((d).roots)
 #define BRO_ROOTS_CD_U16 ((1u << BRO_RB_CMD) + (1u << BRO_RB_DIST))
 #endif
 // d.roots_cd (shared memory): 6-bit roots of the insert&copy and the distance table [, the 8-bit literal root]
@@ -99,7 +106,7 @@ BRO_FN void bro_parse_finish(BroParse& ps, int st) { ps.st = st; ps.kind = BRO_K
 
 // Make T the current literal table: root and canonical-order symbols into the thread's compact array, limits and bases
 // of the long codes into registers.
-BRO_FN void bro_parse_load_lit(BroParse& ps, uint16_t* roots, uint16_t* lit_root, const uint16_t* T) {
+BRO_FN void bro_parse_load_lit(BroParse& ps, uint16_t* lit_sorted, uint16_t* lit_root, const uint16_t* T) {
     bro_narrow_root(lit_root, BRO_RB_LIT, T);
 #pragma unroll
     for (uint32_t k = 0; k < 4u; k++) {
@@ -109,13 +116,13 @@ BRO_FN void bro_parse_load_lit(BroParse& ps, uint16_t* roots, uint16_t* lit_root
         ps.lit_base[k] = (uint32_t)T[BRO_T_BASE + L0] | ((L1 <= 15u ? (uint32_t)T[BRO_T_BASE + L1] : 0u) << 16);
     }
     ps.lit_misc = (uint32_t)T[BRO_T_MAXDEPTH] | (T[BRO_T_SINGLE] ? 0x100u : 0u) | ((uint32_t)T[BRO_T_SINGLE_SYM] << 16);
-    uint8_t* sorted = (uint8_t*)(roots + BRO_ROOTS_LIT_SORTED);
+    uint8_t* sorted = (uint8_t*)lit_sorted;
     for (uint32_t i = 0; i < 256u; i++) sorted[i] = (uint8_t)T[BRO_T_SORTED + i];
 }
 
 // One literal (same results as bro_decode_sym on the table; src/huffman/tree/mod.rs:63-92): one look-up in the root,
 // and for a code longer than 8 bits a search of the limits held in registers and one look-up of the symbol.
-BRO_FN int bro_parse_decode_lit(BroBits& s, const BroParse& ps, const uint16_t* roots, const uint16_t* lit_root, uint32_t& sym) {
+BRO_FN int bro_parse_decode_lit(BroBits& s, const BroParse& ps, const uint16_t* lit_sorted, const uint16_t* lit_root, uint32_t& sym) {
     bro_refill(s);
     const uint32_t peek = bro_peek(s), avail = bro_avail(s);
     const uint32_t e = lit_root[peek & 0xffu];
@@ -136,7 +143,7 @@ BRO_FN int bro_parse_decode_lit(BroBits& s, const BroParse& ps, const uint16_t* 
             }
             if (L <= 15u) {
                 len = L;
-                sym = ((const uint8_t*)(roots + BRO_ROOTS_LIT_SORTED))[((int)(int16_t)base + (int)(x >> (15u - L))) & 255];
+                sym = ((const uint8_t*)lit_sorted)[((int)(int16_t)base + (int)(x >> (15u - L))) & 255];
             } else r = (avail >= (ps.lit_misc & 0xffu) + 1u) ? BRO_SYM_HOLE : BRO_SYM_EOF;
         }
     }
@@ -177,7 +184,7 @@ BRO_FN bool bro_parse_block_step(BroDec& d, BroParse& ps, BroMbInfo& mb, uint32_
         mb.cat[c] = tc;
         if (st) { bro_parse_finish(ps, st); return false; }
         bl = tc.blen + 1u;
-        if (c == 0u) { ps.toff_lit = bro_parse_table(d, ps, mb, 0u); bro_parse_load_lit(ps, d.roots, BRO_LIT_ROOT(d), d.arena + ps.toff_lit); }
+        if (c == 0u) { ps.toff_lit = bro_parse_table(d, ps, mb, 0u); bro_parse_load_lit(ps, BRO_LIT_SORTED(d), BRO_LIT_ROOT(d), d.arena + ps.toff_lit); }
         else if (c == 1u) { ps.toff_cmd = bro_parse_table(d, ps, mb, 1u); bro_narrow_root(d.roots_cd + BRO_ROOTS_CMD, BRO_RB_CMD, d.arena + ps.toff_cmd); }
     }
     bl -= 1u;
@@ -211,7 +218,7 @@ BRO_FN void bro_parse_header(BroDec& d, BroParse& ps, BroMbInfo& mb) {
             ps.blen0 = mb.cat[0].blen; ps.blen1 = mb.cat[1].blen; ps.blen2 = mb.cat[2].blen;
             ps.toff_cmd = bro_parse_table(d, ps, mb, 1u);
             ps.toff_lit = bro_parse_table(d, ps, mb, 0u);
-            bro_parse_load_lit(ps, d.roots, BRO_LIT_ROOT(d), d.arena + ps.toff_lit);
+            bro_parse_load_lit(ps, BRO_LIT_SORTED(d), BRO_LIT_ROOT(d), d.arena + ps.toff_lit);
             bro_narrow_root(d.roots_cd + BRO_ROOTS_CMD, BRO_RB_CMD, d.arena + ps.toff_cmd);
             if (mb.ntd == 1u) { ps.multi |= 8u; bro_narrow_root(d.roots_cd + BRO_ROOTS_DIST, BRO_RB_DIST, d.arena + mb.o_dist); }
             ps.npostfix = mb.npostfix; ps.ndirect = mb.ndirect; ps.o_dist = mb.o_dist;
@@ -256,12 +263,50 @@ BRO_FN void bro_parse_round(BroDec& d, BroParse& ps, BroMbInfo& mb) {
         }
     }
     // ---- step 2: literals ----
+    // Fast loop: when the next `fast` literals of a lane can neither overflow its slot nor run into the end of its
+    // input (a literal code has at most 15 bits) and no block switch is due, they need no checks at all.  This loop is
+    // the critical path of a literal-heavy stream: every instruction in it is paid in full by a single lane.
+    {
+        uint32_t fast = 0;
+        if (ps.kind == BRO_K_LIT) {
+            uint32_t n = ps.ins_rem < BRO_PARSE_LITS_PER_ROUND ? ps.ins_rem : (uint32_t)BRO_PARSE_LITS_PER_ROUND;
+            if ((ps.multi & 1u) && ps.blen0 < n) n = ps.blen0;     // literals left in the current block (0: a switch is due)
+            if (d.pos <= d.cap && n <= d.cap - d.pos && bro_avail(d.in) >= 16u * n) fast = n;
+        }
+        const uint16_t* const lit_root = BRO_LIT_ROOT(d);
+        uint8_t* op = d.out + d.pos;
+        uint32_t done = 0;
+#pragma unroll 1
+        for (uint32_t u = 0; u < BRO_PARSE_LITS_PER_ROUND; u++) {
+            if (!bro_any(u < fast)) break;
+            if (u < fast) {
+                bro_refill(d.in);
+                const uint32_t peek = bro_peek(d.in);
+                const uint32_t e = lit_root[peek & 0xffu];
+                uint32_t len = e >> 10, sym = e;
+                if (len == 0u) {
+                    // a code longer than 8 bits, a one-symbol code, or no code at all: the general decoder
+                    const int r = bro_parse_decode_lit(d.in, ps, BRO_LIT_SORTED(d), lit_root, sym);
+                    if (r != BRO_SYM_OK) { bro_parse_finish(ps, r == BRO_SYM_HOLE ? BRO_ST_ParseErrorInsertLiterals : BRO_ST_UnexpectedEOF); fast = 0; }
+                } else bro_consume(d.in, len);
+                if (fast) { op[u] = (uint8_t)sym; done = u + 1u; }
+            }
+        }
+        if (done != 0u && ps.kind == BRO_K_LIT) {
+            d.pos += done;
+            ps.ins_rem -= done;
+            if (ps.multi & 1u) ps.blen0 -= done;
+            if (ps.ins_rem == 0u) bro_parse_after_literals(d, ps);
+        }
+    }
+    // General loop: the lanes the fast loop could not take (near the end of the slot or of the input, block switches)
 #pragma unroll 1
     for (int u = 0; u < BRO_PARSE_LITS_PER_ROUND; u++) {
-        if (!bro_any(ps.kind == BRO_K_LIT)) break;
-        if (ps.kind == BRO_K_LIT && bro_parse_block_step(d, ps, mb, 0u)) {
+        const bool slow = ps.kind == BRO_K_LIT && (((ps.multi & 1u) && ps.blen0 == 0u) || d.pos > d.cap || ps.ins_rem > d.cap - d.pos || bro_avail(d.in) < 16u * BRO_PARSE_LITS_PER_ROUND);
+        if (!bro_any(slow)) break;
+        if (slow && bro_parse_block_step(d, ps, mb, 0u)) {
             uint32_t sym = 0;
-            const int r = bro_parse_decode_lit(d.in, ps, d.roots, BRO_LIT_ROOT(d), sym);
+            const int r = bro_parse_decode_lit(d.in, ps, BRO_LIT_SORTED(d), BRO_LIT_ROOT(d), sym);
             if (r != BRO_SYM_OK) bro_parse_finish(ps, r == BRO_SYM_HOLE ? BRO_ST_ParseErrorInsertLiterals : BRO_ST_UnexpectedEOF);
             else {
                 // a run that does not fit the slot is still decoded: a decode error inside it wins over OutputTooSmall

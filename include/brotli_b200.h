@@ -57,8 +57,8 @@ int bro_ctx_set_quirks(bro_ctx* ctx, int quirks);
  *             every LZ77 copy into a record; phase two executes the records with one warp per stream at memory speed.
  *             Streams phase one cannot decode (literal context modelling, libbrotli quality >= 10) are re-run by the
  *             fused kernel inside the same call.
- *   AUTO (default): TWOPHASE for batches of at least 12 x bro_ctx_num_warps streams (the fused kernel would need a
- *             dozen waves of its resident warps), WARP below.
+ *   AUTO (default): TWOPHASE for batches of at least 5 x bro_ctx_num_warps streams (the fused kernel would need that
+ *             many waves of its resident warps), WARP below.
  * The environment variable BRO_B200_MODE=warp|twophase sets the initial mode. */
 #define BRO_MODE_AUTO 0
 #define BRO_MODE_WARP 1

@@ -322,11 +322,11 @@ def test_auto_mode_launch_counts():
     streams = [c for _, c, _ in files] * 100
     exps = [e for _, _, e in files] * 100
     probe = BatchDecoder(0)
-    many = -(-12 * probe.num_warps // len(streams))          # AUTO takes the two-phase path from 12 x num_warps streams
+    many = -(-5 * probe.num_warps // len(streams))           # AUTO takes the two-phase path from 5 x num_warps streams
     probe.close()
     for mode, reps, want in ((None, 1, 1), (BatchDecoder.MODE_TWOPHASE, 1, 6), (None, many, 6)):
         d = BatchDecoder(0, mode=mode)
-        assert len(streams) < 12 * d.num_warps <= len(streams) * many
+        assert len(streams) < 5 * d.num_warps <= len(streams) * many
         before = d.launch_count
         res = d.decode_streams(streams * reps, [len(e) for e in exps] * reps)
         assert d.launch_count - before == want

@@ -1,6 +1,7 @@
 #!/usr/bin/env python3
 """Summarise ncu captures brought back in gpurun_out/ into profiles/ (tracked).
-usage: python tools/ncu_summary.py <round tag> <name>=<file.ncu-rep>:<algorithmic bytes of that launch> ...  [launches.csv]"""
+usage: python tools/ncu_summary.py <round tag> <name>=<file.ncu-rep>:<log of the bench run under ncu> ...  [launches.csv]
+The bench log's JSON line supplies the algorithmic bytes per kernel (roofline.kernels) of the very batch that was captured."""
 import csv
 import io
 import json
@@ -49,10 +50,12 @@ def main():
         if "=" not in arg:
             continue
         name, rest = arg.split("=", 1)
-        rep, algo = rest.rsplit(":", 1)
-        algo = float(algo)
+        rep, benchlog = rest.rsplit(":", 1)
+        line = [l for l in open(benchlog).read().splitlines() if l.startswith("{")][-1]
+        kern_algo = {k.split(" ")[0].split("_kernel")[0]: v["algorithmic_bytes"] for k, v in json.loads(line)["roofline"]["kernels"].items()}
         launches = raw(rep)
         lines.append("## %s (`%s`, %d launch(es) captured)\n" % (name, os.path.basename(rep), len(launches)))
+        per_kernel = {}
         for L in launches:
             kn = L["Kernel Name"][0]
             lines.append("kernel `%s`\n" % kn)
@@ -62,17 +65,21 @@ def main():
                     v, u = L[m]
                     lines.append("| %s | %s | %s |" % (m, v, u))
             lines.append("")
-        L = launches[0]
 
-        def num(m):
-            v, u = L[m]
-            f = float(v.replace(",", ""))
-            return f * {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1, "Tbyte": 1e12}.get(u, 1)
-        dram = num("dram__bytes_read.sum") + num("dram__bytes_write.sum")
-        lines.append("algorithmic bytes of this launch: %.0f; DRAM traffic (read+write): %.0f; traffic / algorithmic = %.3f\n" % (algo, dram, dram / algo))
-        traffic[name] = {"dram_bytes_per_algorithmic_byte": dram / algo, "dram_read": num("dram__bytes_read.sum"),
-                         "dram_write": num("dram__bytes_write.sum"), "algorithmic_bytes": algo, "round": tag,
-                         "report": os.path.basename(rep)}
+            def num(m):
+                v, u = L[m]
+                f = float(v.replace(",", ""))
+                return f * {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1, "Tbyte": 1e12}.get(u, 1)
+            key = kn.replace("void ", "").split("<")[0].split("(")[0].split("_kernel")[0]
+            algo = kern_algo.get(key)
+            dram = num("dram__bytes_read.sum") + num("dram__bytes_write.sum")
+            if algo:
+                lines.append("algorithmic bytes of this launch: %.0f; DRAM traffic (read+write): %.0f; traffic / algorithmic = %.3f\n" % (algo, dram, dram / algo))
+                per_kernel[key + "_kernel"] = {"dram_bytes_per_algorithmic_byte": dram / algo, "dram_read": num("dram__bytes_read.sum"),
+                                               "dram_write": num("dram__bytes_write.sum"), "algorithmic_bytes": algo}
+            else:
+                lines.append("DRAM traffic (read+write): %.0f\n" % dram)
+        traffic[name] = {"kernels": per_kernel, "round": tag, "report": os.path.basename(rep)}
     with open(os.path.join(ROOT, "profiles", "%s_ncu_summary.md" % tag), "w") as f:
         f.write("\n".join(lines))
     json.dump(traffic, open(traffic_path, "w"), indent=1)
