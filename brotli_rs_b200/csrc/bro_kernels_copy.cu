@@ -89,17 +89,26 @@ __global__ void __launch_bounds__(WARPS * 32, BRO_COPY_MIN_BLOCKS) bro_copy_kern
     // unit's 16 source bytes)
     __shared__ __align__(16) uint8_t stage[WARPS * BRO_COPY_DEPTH * 32 * 32];
     const uint32_t stage_base = (uint32_t)__cvta_generic_to_shared(stage) + (threadIdx.x >> 5) * (BRO_COPY_DEPTH * 32u * 32u);
+    // The queue is read one stream ahead and a stream's descriptors (status, record count, offsets) are fetched by
+    // four lanes at once: a short stream costs three memory round trips before its first copy, not six.
+    const uint64_t in_off0 = p.in_off[0];
+    uint32_t i_next = 0;
+    if (lane == 0) i_next = atomicAdd(p.counter, 1u);
     for (;;) {
-        uint32_t i = 0;
-        if (lane == 0) i = atomicAdd(p.counter, 1u);
-        i = __shfl_sync(0xffffffffu, i, 0);
+        const uint32_t i = __shfl_sync(0xffffffffu, i_next, 0);
         if (i >= p.n) break;
-        if (p.status[i] != BRO_ST_OK) continue;       // bytes of a failed stream are not part of the contract
-        const uint32_t n = p.nrec[i];
+        if (lane == 0) i_next = atomicAdd(p.counter, 1u);
+        uint64_t meta = 0;
+        if (lane == 0) meta = (uint64_t)(uint32_t)p.status[i];
+        else if (lane == 1) meta = p.nrec[i];
+        else if (lane == 2) meta = p.in_off[i];
+        else if (lane == 3) meta = p.out_off[i];
+        if (__shfl_sync(0xffffffffu, (uint32_t)meta, 0) != (uint32_t)BRO_ST_OK) continue;   // bytes of a failed stream are not part of the contract
+        const uint32_t n = __shfl_sync(0xffffffffu, (uint32_t)meta, 1);
         if (n == 0u) continue;
-        const uint64_t in_b = p.in_off[i];
-        const BroRec* recs = p.rec + BRO_REC_BASE(p.in_off, i);
-        uint8_t* const out = p.out + p.out_off[i];
+        const uint64_t in_b = __shfl_sync(0xffffffffu, meta, 2);
+        const BroRec* recs = p.rec + (((in_b - in_off0) >> 1) + 32ull * i);      // BRO_REC_BASE
+        uint8_t* const out = p.out + __shfl_sync(0xffffffffu, meta, 3);
         const uint8_t* const in = p.in + in_b;
         const uint32_t out_mis = (uint32_t)((uintptr_t)out & 15u);   // destination alignment is that of the address
         unsigned long long moved = 0;                                // bytes this lane's records move (measurement)

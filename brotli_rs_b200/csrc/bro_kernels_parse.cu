@@ -134,9 +134,13 @@ __device__ __forceinline__ uint32_t bro_size_class(uint64_t len) {
     return 255u - (b * 8u + sub);
 }
 
+// Batches are made of few size classes (replicas, similar streams): the lanes of a warp that hit the same class are
+// counted by one atomic of their leader (match_any) instead of serialising on one address.
 __global__ void bro_order_hist_kernel(const uint64_t* in_off, uint32_t n, uint32_t* hist) {
-    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) atomicAdd(&hist[bro_size_class(in_off[i + 1] - in_off[i])], 1u);
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t c = i < n ? bro_size_class(in_off[i + 1] - in_off[i]) : 0xffffffffu;
+    const uint32_t peers = __match_any_sync(0xffffffffu, c);
+    if (i < n && (peers & ((1u << (threadIdx.x & 31u)) - 1u)) == 0u) atomicAdd(&hist[c], (uint32_t)__popc(peers));
 }
 
 __global__ void bro_order_scan_kernel(const uint32_t* hist, uint32_t* cursor) {
@@ -153,8 +157,15 @@ __global__ void bro_order_scan_kernel(const uint32_t* hist, uint32_t* cursor) {
 }
 
 __global__ void bro_order_scatter_kernel(const uint64_t* in_off, uint32_t n, uint32_t* cursor, uint32_t* order) {
-    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) order[atomicAdd(&cursor[bro_size_class(in_off[i + 1] - in_off[i])], 1u)] = i;
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t c = i < n ? bro_size_class(in_off[i + 1] - in_off[i]) : 0xffffffffu;
+    const uint32_t peers = __match_any_sync(0xffffffffu, c);
+    const int leader = __ffs(peers) - 1;
+    uint32_t base = 0;
+    if (i < n && (int)lane == leader) base = atomicAdd(&cursor[c], (uint32_t)__popc(peers));
+    base = __shfl_sync(0xffffffffu, base, leader);
+    if (i < n) order[base + (uint32_t)__popc(peers & ((1u << lane) - 1u))] = i;
 }
 
 extern "C" int bro_order_launch(const uint64_t* in_off, uint32_t n, uint32_t* order, uint32_t* scratch, cudaStream_t stream) {

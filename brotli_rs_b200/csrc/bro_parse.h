@@ -120,38 +120,42 @@ BRO_FN void bro_parse_load_lit(BroParse& ps, uint16_t* lit_sorted, uint16_t* lit
     for (uint32_t i = 0; i < 256u; i++) sorted[i] = (uint8_t)T[BRO_T_SORTED + i];
 }
 
-// One literal (same results as bro_decode_sym on the table; src/huffman/tree/mod.rs:63-92): one look-up in the root,
-// and for a code longer than 8 bits a search of the limits held in registers and one look-up of the symbol.
+// The part of a literal decode behind a root miss (entry without a length): a code longer than 8 bits -- a search of the
+// limits held in registers and ONE look-up of the symbol --, a one-symbol code, or no code at all.  Consumes the bits.
+BRO_FN int bro_parse_lit_long(BroBits& s, const BroParse& ps, const uint16_t* lit_sorted, uint32_t peek, uint32_t& sym) {
+    const uint32_t avail = bro_avail(s);
+    uint32_t len = 0;
+    if (ps.lit_misc & 0x100u) sym = ps.lit_misc >> 16;                        // one symbol: zero bits
+    else {
+        const uint32_t x = bro_brev(peek) >> 17;                               // next 15 bits, first bit read most significant
+        // smallest L in 9..15 with x < limit[L] (limits grow with L)
+        uint32_t L = 16u, base = 0;
+#pragma unroll
+        for (int k = 3; k >= 0; k--) {
+            const uint32_t lo = ps.lit_lim[k] & 0xffffu, hi = ps.lit_lim[k] >> 16;
+            if (k < 3 && x < hi) { L = 10u + 2u * (uint32_t)k; base = ps.lit_base[k] >> 16; }
+            if (x < lo) { L = 9u + 2u * (uint32_t)k; base = ps.lit_base[k] & 0xffffu; }
+        }
+        if (L > 15u) return (avail >= (ps.lit_misc & 0xffu) + 1u) ? BRO_SYM_HOLE : BRO_SYM_EOF;
+        len = L;
+        sym = ((const uint8_t*)lit_sorted)[((int)(int16_t)base + (int)(x >> (15u - L))) & 255];
+    }
+    if (len > avail) return BRO_SYM_EOF;
+    bro_consume(s, len);
+    return BRO_SYM_OK;
+}
+
+// One literal (same results as bro_decode_sym on the table; src/huffman/tree/mod.rs:63-92).
 BRO_FN int bro_parse_decode_lit(BroBits& s, const BroParse& ps, const uint16_t* lit_sorted, const uint16_t* lit_root, uint32_t& sym) {
     bro_refill(s);
-    const uint32_t peek = bro_peek(s), avail = bro_avail(s);
+    const uint32_t peek = bro_peek(s);
     const uint32_t e = lit_root[peek & 0xffu];
-    uint32_t len = e >> 10;
-    int r = BRO_SYM_OK;
+    const uint32_t len = e >> 10;
     sym = e & 0x3ffu;
-    if (len == 0u) {
-        if (ps.lit_misc & 0x100u) sym = ps.lit_misc >> 16;                    // one symbol: zero bits
-        else {
-            const uint32_t x = bro_brev(peek) >> 17;                           // next 15 bits, first bit read most significant
-            // smallest L in 9..15 with x < limit[L] (limits grow with L)
-            uint32_t L = 16u, base = 0;
-#pragma unroll
-            for (int k = 3; k >= 0; k--) {
-                const uint32_t lo = ps.lit_lim[k] & 0xffffu, hi = ps.lit_lim[k] >> 16;
-                if (k < 3 && x < hi) { L = 10u + 2u * (uint32_t)k; base = ps.lit_base[k] >> 16; }
-                if (x < lo) { L = 9u + 2u * (uint32_t)k; base = ps.lit_base[k] & 0xffffu; }
-            }
-            if (L <= 15u) {
-                len = L;
-                sym = ((const uint8_t*)lit_sorted)[((int)(int16_t)base + (int)(x >> (15u - L))) & 255];
-            } else r = (avail >= (ps.lit_misc & 0xffu) + 1u) ? BRO_SYM_HOLE : BRO_SYM_EOF;
-        }
-    }
-    if (r == BRO_SYM_OK) {
-        if (len > avail) r = BRO_SYM_EOF;
-        else bro_consume(s, len);
-    }
-    return r;
+    if (len == 0u) return bro_parse_lit_long(s, ps, lit_sorted, peek, sym);
+    if (len > bro_avail(s)) return BRO_SYM_EOF;
+    bro_consume(s, len);
+    return BRO_SYM_OK;
 }
 
 // Table of a symbol of category c (0 literal, 1 insert&copy, 2 distance) under the current block types.
@@ -286,7 +290,7 @@ BRO_FN void bro_parse_round(BroDec& d, BroParse& ps, BroMbInfo& mb) {
                 uint32_t len = e >> 10, sym = e;
                 if (len == 0u) {
                     // a code longer than 8 bits, a one-symbol code, or no code at all: the general decoder
-                    const int r = bro_parse_decode_lit(d.in, ps, BRO_LIT_SORTED(d), lit_root, sym);
+                    const int r = bro_parse_lit_long(d.in, ps, BRO_LIT_SORTED(d), peek, sym);
                     if (r != BRO_SYM_OK) { bro_parse_finish(ps, r == BRO_SYM_HOLE ? BRO_ST_ParseErrorInsertLiterals : BRO_ST_UnexpectedEOF); fast = 0; }
                 } else bro_consume(d.in, len);
                 if (fast) { op[u] = (uint8_t)sym; done = u + 1u; }
