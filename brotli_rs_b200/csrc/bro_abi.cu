@@ -33,9 +33,13 @@ struct bro_ctx {
     uint8_t* d_dict;
     uint32_t* d_counter;      // queue heads: [0] parse kernel, [1] warp kernel, [3] copy kernel; [2] retry count;
                               // [4..7] as two uint64: bytes moved / records executed by the copy kernel (last batch)
-    uint32_t* d_order; size_t d_order_cap;   // size-class order of the current batch | records per stream (2 * cap)
+    uint32_t* d_order; size_t d_order_cap;   // size-class order of the batch | records per stream | completion queue (3 * cap)
     uint32_t* d_order_scratch;               // 512 counters
     BroRec* d_rec; size_t d_rec_cap;         // copy records (in records)
+    cudaStream_t side;        // the copy kernel runs here, next to the parse kernel on the caller's stream
+    cudaEvent_t ev_fork, ev_join;
+    int overlap;              // 1: parse and copy kernels side by side (BRO_B200_OVERLAP=1); 0 (default): one after the other
+                              // (always while timing is on, so that bro_ctx_last_kernel_ms reports each kernel alone)
     int timing;               // bro_ctx_set_timing: record CUDA events around the kernels of a batch
     cudaEvent_t ev[5];        // before ordering | before parse | before copy | before fused | after fused
     int ev_valid;             // the last batch recorded ev[] (two_phase: all five, else ev[3], ev[4])
@@ -87,6 +91,14 @@ extern "C" int bro_ctx_create(bro_ctx** out, int device) {
     ctx->num_threads = (uint32_t)ctx->grid_t * (uint32_t)bro_parse_kernel_block();
     ctx->grid_c = ctx->num_sms * per_sm_c;
     ctx->mode = BRO_MODE_AUTO;
+    // Measured on B200 (profiles/r01_kernel_variants.md): side by side the two kernels compete for the register file (the
+    // parse kernel's three CTAs leave room for one 64-register copy CTA per SM) and the streams of a batch finish in
+    // bursts, so the overlap buys 5 % at best and costs the copy kernel its best configuration: off unless asked for.
+    ctx->overlap = 0;
+    { const char* ov = getenv("BRO_B200_OVERLAP"); if (ov && ov[0] == '1') ctx->overlap = 1; }
+    if (cudaStreamCreateWithFlags(&ctx->side, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming) != cudaSuccess) { ctx->side = NULL; cudaGetLastError(); }
     // A warp per stream is the lowest latency per stream; the two-phase path (32 streams per warp in the entropy decode,
     // then copies at memory speed) has the higher throughput.  It pays once the fused kernel would need several waves
     // of its resident warps; measured on B200 with the headline streams (profiles/r01_kernel_variants.md) the break-even
@@ -98,7 +110,7 @@ extern "C" int bro_ctx_create(bro_ctx** out, int device) {
     size_t arena = (size_t)ctx->num_warps * bro_warp_kernel_arena_bytes();
     if ((e = cudaMalloc(&ctx->d_arena, arena)) != cudaSuccess ||
         (e = cudaMalloc(&ctx->d_dict, BRO_DICT_BYTES)) != cudaSuccess ||
-        (e = cudaMalloc(&ctx->d_counter, 8 * sizeof(uint32_t))) != cudaSuccess ||
+        (e = cudaMalloc(&ctx->d_counter, 16 * sizeof(uint32_t))) != cudaSuccess ||
         (e = cudaMalloc(&ctx->d_order_scratch, 512 * sizeof(uint32_t))) != cudaSuccess ||
         (e = cudaMemcpy(ctx->d_dict, bro_dictionary_blob, BRO_DICT_BYTES, cudaMemcpyHostToDevice)) != cudaSuccess) {
         cudaFree(ctx->d_arena); cudaFree(ctx->d_arena_t); cudaFree(ctx->d_dict); cudaFree(ctx->d_counter); cudaFree(ctx->d_order_scratch);
@@ -116,6 +128,9 @@ extern "C" void bro_ctx_destroy(bro_ctx* ctx) {
     cudaFree(ctx->d_order); cudaFree(ctx->d_order_scratch); cudaFree(ctx->d_rec); cudaFree(ctx->d_roots);
     cudaFree(ctx->d_in); cudaFree(ctx->d_out); cudaFree(ctx->d_meta);
     for (int k = 0; k < 5; k++) if (ctx->ev[k]) cudaEventDestroy(ctx->ev[k]);
+    if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
+    if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
+    if (ctx->side) cudaStreamDestroy(ctx->side);
     free(ctx);
 }
 
@@ -190,7 +205,7 @@ extern "C" int bro_batch_decode(bro_ctx* ctx, const uint8_t* d_in, const uint64_
     if (n == 0) return BRO_ST_OK;
     if (!d_in_off || !d_out_off || !d_out_len || !d_status) return BRO_ST_InvalidArgument;
     cudaStream_t s = (cudaStream_t)stream;
-    BRO_CUDA(ctx, cudaMemsetAsync(ctx->d_counter, 0, 8 * sizeof(uint32_t), s));
+    BRO_CUDA(ctx, cudaMemsetAsync(ctx->d_counter, 0, 16 * sizeof(uint32_t), s));
     BroLaunch p;
     memset(&p, 0, sizeof(p));
     p.in = d_in; p.in_off = d_in_off; p.out = d_out; p.out_off = d_out_off;
@@ -214,7 +229,7 @@ extern "C" int bro_batch_decode(bro_ctx* ctx, const uint8_t* d_in, const uint64_
                 BRO_CUDA(ctx, cudaMalloc(&ctx->d_roots, ctx->roots_bytes));
             }
         }
-        if ((st = bro_grow(ctx, (void**)&ctx->d_order, &ctx->d_order_cap, (size_t)n, 2 * sizeof(uint32_t)))) return st;
+        if ((st = bro_grow(ctx, (void**)&ctx->d_order, &ctx->d_order_cap, (size_t)n, 3 * sizeof(uint32_t)))) return st;
         // the record arena is sized from the compressed bytes of the batch: the caller's bound (bro_ctx_reserve), else
         // the two end offsets are read back (16 bytes, blocking on `s`)
         uint64_t total_in = ctx->reserved_in;
@@ -231,6 +246,9 @@ extern "C" int bro_batch_decode(bro_ctx* ctx, const uint8_t* d_in, const uint64_
         uint32_t* d_order = ctx->d_order;
         if (ctx->timing) BRO_CUDA(ctx, cudaEventRecord(ctx->ev[0], s));
         p.nrec = ctx->d_order + ctx->d_order_cap;
+        p.done_q = ctx->d_order + 2 * ctx->d_order_cap;
+        p.done_tail = ctx->d_counter + 8;
+        BRO_CUDA(ctx, cudaMemsetAsync(p.done_q, 0xff, (size_t)n * sizeof(uint32_t), s));
         p.rec = ctx->d_rec; p.rec_total = ctx->d_rec_cap;
         e = (cudaError_t)bro_order_launch(d_in_off, n, d_order, ctx->d_order_scratch, s);
         if (e != cudaSuccess) return bro_fail(ctx, e, "bro_order kernels launch");
@@ -238,20 +256,33 @@ extern "C" int bro_batch_decode(bro_ctx* ctx, const uint8_t* d_in, const uint64_
         const uint32_t tb = (uint32_t)bro_parse_kernel_block();
         int grid_t = ctx->grid_t;
         if ((uint32_t)grid_t > (n + tb - 1) / tb) grid_t = (int)((n + tb - 1) / tb);
+        const uint32_t cw = (uint32_t)bro_copy_kernel_warps_per_cta();
+        p.counter = ctx->d_counter + 3; p.order = NULL;
+        p.copy_stats = (unsigned long long*)(ctx->d_counter + 4);
+        const bool overlap = ctx->overlap && !ctx->timing && ctx->side;
+        if (overlap) {
+            // The copy kernel follows the parse kernel through the completion queue: launched on the side stream while
+            // the parse kernel runs on the caller's, one CTA per SM (what fits next to the parse kernel's three).  The
+            // parse kernel never waits for it, so whatever the block scheduler does there is no cycle to deadlock on.
+            BRO_CUDA(ctx, cudaEventRecord(ctx->ev_fork, s));
+            BRO_CUDA(ctx, cudaStreamWaitEvent(ctx->side, ctx->ev_fork, 0));
+        }
         p.arena = ctx->d_arena_t; p.counter = ctx->d_counter; p.order = d_order; p.roots = ctx->d_roots;
         if (ctx->timing) BRO_CUDA(ctx, cudaEventRecord(ctx->ev[1], s));
         e = (cudaError_t)bro_parse_kernel_launch(&p, grid_t, s);
         if (e != cudaSuccess) return bro_fail(ctx, e, "bro_parse_kernel launch");
         ctx->launches += 1;
-        const uint32_t cw = (uint32_t)bro_copy_kernel_warps_per_cta();
-        int grid_c = ctx->grid_c;
-        if ((uint32_t)grid_c > (n + cw - 1) / cw) grid_c = (int)((n + cw - 1) / cw);
         p.counter = ctx->d_counter + 3; p.order = NULL;
-        p.copy_stats = (unsigned long long*)(ctx->d_counter + 4);
+        int grid_c = ctx->grid_c;      // side by side, one CTA per SM fits next to the parse kernel; the others start as its CTAs exit
+        if ((uint32_t)grid_c > (n + cw - 1) / cw) grid_c = (int)((n + cw - 1) / cw);
         if (ctx->timing) BRO_CUDA(ctx, cudaEventRecord(ctx->ev[2], s));
-        e = (cudaError_t)bro_copy_kernel_launch(&p, grid_c, s);
+        e = (cudaError_t)bro_copy_kernel_launch(&p, grid_c, overlap ? ctx->side : s);
         if (e != cudaSuccess) return bro_fail(ctx, e, "bro_copy_kernel launch");
         ctx->launches += 1;
+        if (overlap) {
+            BRO_CUDA(ctx, cudaEventRecord(ctx->ev_join, ctx->side));
+            BRO_CUDA(ctx, cudaStreamWaitEvent(s, ctx->ev_join, 0));
+        }
         p.retry_mode = 1;
     }
     p.arena = ctx->d_arena; p.counter = ctx->d_counter + 1;

@@ -28,6 +28,11 @@ struct BroLaunch {
     BroRec* rec;
     uint64_t rec_total;
     uint32_t* nrec;           // n: records written for stream i
+    // two-phase path: the parse kernel announces every stream it has finished (whatever its status) in done_q, in
+    // completion order; the copy kernel takes tickets from counter[] and waits for its slot to be filled, so that the two
+    // kernels can run side by side.  done_q is all-ones before the batch.
+    uint32_t* done_q;
+    uint32_t* done_tail;
     uint16_t* roots;          // parse kernel: per-thread decode tables (bro_parse.h) when they live in HBM / L2
     unsigned long long* copy_stats;   // [0] bytes moved by records, [1] records executed (this batch)
 };

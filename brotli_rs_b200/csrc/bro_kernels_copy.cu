@@ -89,15 +89,28 @@ __global__ void __launch_bounds__(WARPS * 32, BRO_COPY_MIN_BLOCKS) bro_copy_kern
     // unit's 16 source bytes)
     __shared__ __align__(16) uint8_t stage[WARPS * BRO_COPY_DEPTH * 32 * 32];
     const uint32_t stage_base = (uint32_t)__cvta_generic_to_shared(stage) + (threadIdx.x >> 5) * (BRO_COPY_DEPTH * 32u * 32u);
-    // The queue is read one stream ahead and a stream's descriptors (status, record count, offsets) are fetched by
-    // four lanes at once: a short stream costs three memory round trips before its first copy, not six.
+    // Streams come from the parse kernel's completion queue: a warp takes a ticket (one ahead of the stream it works on)
+    // and waits until the slot of that ticket holds a stream index -- immediately, when the parse kernel has already
+    // ended; with the two kernels side by side this is where the copy kernel follows the parse kernel's progress.  A
+    // stream's descriptors (status, record count, offsets) are then fetched by four lanes at once.
     const uint64_t in_off0 = p.in_off[0];
-    uint32_t i_next = 0;
-    if (lane == 0) i_next = atomicAdd(p.counter, 1u);
+    uint32_t t_next = 0;
+    if (lane == 0) t_next = atomicAdd(p.counter, 1u);
     for (;;) {
-        const uint32_t i = __shfl_sync(0xffffffffu, i_next, 0);
-        if (i >= p.n) break;
-        if (lane == 0) i_next = atomicAdd(p.counter, 1u);
+        const uint32_t ticket = __shfl_sync(0xffffffffu, t_next, 0);
+        if (ticket >= p.n) break;
+        uint32_t i = 0xffffffffu;
+        if (lane == 0) {
+            t_next = atomicAdd(p.counter, 1u);
+            const long long t0 = clock64();
+            while ((i = ((volatile uint32_t*)p.done_q)[ticket]) == 0xffffffffu) {
+                __nanosleep(500);
+                if (clock64() - t0 > (1ll << 33)) break;      // watchdog (seconds): never spin forever
+            }
+            __threadfence();
+        }
+        i = __shfl_sync(0xffffffffu, i, 0);
+        if (i >= p.n) break;                                  // watchdog fired: give up (the streams left fail parity loudly)
         uint64_t meta = 0;
         if (lane == 0) meta = (uint64_t)(uint32_t)p.status[i];
         else if (lane == 1) meta = p.nrec[i];

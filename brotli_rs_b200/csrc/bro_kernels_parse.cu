@@ -85,6 +85,10 @@ __global__ void __launch_bounds__(BRO_PARSE_BLOCK, BRO_PARSE_MIN_BLOCKS) bro_par
                     p.nrec[stream] = d.nrec;
                     if (BRO_ST_IS_RETRY(ps.st)) atomicAdd(p.retry_count, 1u);
                     ps.st = -1;
+                    // announce the stream to the copy kernel: everything this thread wrote for it (literals, dictionary
+                    // words, records, the three values above) is visible before its index appears in the queue
+                    __threadfence();
+                    ((volatile uint32_t*)p.done_q)[atomicAdd(p.done_tail, 1u)] = stream;
                 }
                 const uint32_t idle = __ballot_sync(0xffffffffu, ps.kind == BRO_K_DONE);
                 if (idle != 0u && !exhausted) {
