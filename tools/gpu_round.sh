@@ -10,7 +10,7 @@ timeout 900 python bench.py --mode warp --steps 10 --warmup 3 --no-e2e --no-cpu-
 for w in c2_quickfox_x10k c3_corpus_x1000 c5_stored_10k c5b_literals_10k; do
   timeout 900 python bench.py --workload $w --steps 10 --warmup 3 --no-e2e > gpurun_out/bench_$w.json 2> gpurun_out/bench_$w.err
 done
-timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 80 --csv --log-file gpurun_out/launches.csv \
+timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:bro_ -c 60 --csv --log-file gpurun_out/launches.csv \
     python bench.py --steps 3 --warmup 1 --no-e2e --no-cpu-baseline > gpurun_out/bench_under_ncu.log 2>&1
 # one full capture per kernel of the headline step (launches 1.. of the warm-up call: parse, copy, fused retry)
 timeout 1200 ncu --set full --clock-control none --import-source on -k regex:"bro_parse_kernel|bro_copy_kernel" -s 2 -c 2 -f -o gpurun_out/prof_c4_highratio_w16 \
