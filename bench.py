@@ -328,7 +328,7 @@ def main():
     # algorithmic bytes per launch: fused = compressed read + uncompressed written; copy = bytes
     # written by copy records + 16 B per record read; parse = compressed read + bytes it writes itself (literals,
     # dictionary words) + 16 B per record written
-    two_phase = kms["parse"] > 0.0
+    two_phase = kms["parse"] > 0.0 and not stats.get("gated_to_fused")
     rec_bytes = 16.0 * stats["copy_records"]
     if two_phase:
         retried = stats["retried_streams"]
@@ -337,6 +337,7 @@ def main():
                 "fused": (comp_bytes + uncomp_bytes) if retried == n else None, "order": 8.0 * (n + 1) * 2}
     else:
         algo = {"fused": comp_bytes + uncomp_bytes}
+        kms = {k: (v if k == "fused" or v > 0.05 else 0.0) for k, v in kms.items()}   # gated batch: the other kernels returned at once
     names = {"order": "bro_order_*_kernel (3)", "parse": "bro_parse_kernel", "copy": "bro_copy_kernel", "fused": "bro_decode_warp_kernel"}
     kernels = {}
     for k, ms in kms.items():

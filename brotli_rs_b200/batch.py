@@ -88,10 +88,10 @@ class BatchDecoder:
         return {"order": float(ms[0]), "parse": float(ms[1]), "copy": float(ms[2]), "fused": float(ms[3])}
 
     def last_batch_stats(self):
-        """-> dict(copy_bytes, copy_records, retried_streams) of the last batch; synchronises the device."""
+        """-> dict(copy_bytes, copy_records, retried_streams, gated_to_fused) of the last batch; synchronises the device."""
         st = (ctypes.c_uint64 * 4)()
         self._check(self._lib.bro_ctx_last_batch_stats(self._ctx, st))
-        return {"copy_bytes": int(st[0]), "copy_records": int(st[1]), "retried_streams": int(st[2])}
+        return {"copy_bytes": int(st[0]), "copy_records": int(st[1]), "retried_streams": int(st[2]), "gated_to_fused": int(st[3])}
 
     @property
     def num_warps(self):

@@ -171,14 +171,14 @@ extern "C" int bro_ctx_last_kernel_ms(bro_ctx* ctx, float* ms4) {
 
 extern "C" int bro_ctx_last_batch_stats(bro_ctx* ctx, uint64_t* stats4) {
     if (!ctx || !stats4) return BRO_ST_InvalidArgument;
-    uint32_t h[8];
+    uint32_t h[16];
     BRO_CUDA(ctx, cudaSetDevice(ctx->device));
     BRO_CUDA(ctx, cudaDeviceSynchronize());
     BRO_CUDA(ctx, cudaMemcpy(h, ctx->d_counter, sizeof(h), cudaMemcpyDeviceToHost));
     stats4[0] = (uint64_t)h[4] | ((uint64_t)h[5] << 32);     // bytes moved by copy records
     stats4[1] = (uint64_t)h[6] | ((uint64_t)h[7] << 32);     // copy records executed
     stats4[2] = h[2];                                        // streams handed to the fused kernel's retry pass
-    stats4[3] = 0;
+    stats4[3] = h[10];                                       // 1: AUTO's gate sent the whole batch to the fused kernel
     return BRO_ST_OK;
 }
 
@@ -250,7 +250,10 @@ extern "C" int bro_batch_decode(bro_ctx* ctx, const uint8_t* d_in, const uint64_
         p.done_tail = ctx->d_counter + 8;
         BRO_CUDA(ctx, cudaMemsetAsync(p.done_q, 0xff, (size_t)n * sizeof(uint32_t), s));
         p.rec = ctx->d_rec; p.rec_total = ctx->d_rec_cap;
-        e = (cudaError_t)bro_order_launch(d_in_off, n, d_order, ctx->d_order_scratch, s);
+        // AUTO: the ordering kernels also find the longest stream and decide on the device whether the batch is bound by
+        // it; an explicit TWOPHASE is not second-guessed
+        p.gate = ctx->mode == BRO_MODE_AUTO ? ctx->d_counter + 9 : NULL;
+        e = (cudaError_t)bro_order_launch(d_in_off, n, d_order, ctx->d_order_scratch, p.gate, s);
         if (e != cudaSuccess) return bro_fail(ctx, e, "bro_order kernels launch");
         ctx->launches += 3;
         const uint32_t tb = (uint32_t)bro_parse_kernel_block();

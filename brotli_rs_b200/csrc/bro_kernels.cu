@@ -26,13 +26,16 @@ __global__ void __launch_bounds__(WARPS * 32, BRO_MIN_BLOCKS) bro_decode_warp_ke
     __shared__ BroScratch scratch[WARPS * BRO_GROUPS_PER_WARP];
     const unsigned warp = threadIdx.x / BRO_W, lane = bro_lane();     // "warp" = group of BRO_W lanes
     const unsigned gwarp = blockIdx.x * (WARPS * BRO_GROUPS_PER_WARP) + warp;
-    if (p.retry_mode && *p.retry_count == 0u) return;
+    // retry pass of the two-phase path: only the streams the parse kernel handed over -- unless AUTO's gate sent the
+    // whole batch here
+    const bool retry = p.retry_mode && !(p.gate && p.gate[1]);
+    if (retry && *p.retry_count == 0u) return;
     for (;;) {
         uint32_t i = 0;
         if (lane == 0) i = atomicAdd(p.counter, 1u);
         i = bro_shfl(i, 0);
         if (i >= p.n) break;
-        if (p.retry_mode && !BRO_ST_IS_RETRY(p.status[i])) continue;
+        if (retry && !BRO_ST_IS_RETRY(p.status[i])) continue;
         const uint64_t in_b = p.in_off[i], in_e = p.in_off[i + 1];
         const uint64_t out_b = p.out_off[i], out_e = p.out_off[i + 1];
         BroDec d;

@@ -32,6 +32,9 @@ struct BroLaunch {
     // completion order; the copy kernel takes tickets from counter[] and waits for its slot to be filled, so that the two
     // kernels can run side by side.  done_q is all-ones before the batch.
     uint32_t* done_q;
+    // AUTO mode: [0] longest compressed stream of the batch (bytes, saturated), [1] 1 = the batch is bound by its longest
+    // stream: the parse and copy kernels return at once and the fused kernel decodes everything.  NULL = no gating.
+    uint32_t* gate;
     uint32_t* done_tail;
     uint16_t* roots;          // parse kernel: per-thread decode tables (bro_parse.h) when they live in HBM / L2
     unsigned long long* copy_stats;   // [0] bytes moved by records, [1] records executed (this batch)
@@ -56,4 +59,4 @@ extern "C" int bro_copy_kernel_occupancy(int* blocks_per_sm);
 extern "C" int bro_copy_kernel_warps_per_cta();
 extern "C" int bro_copy_kernel_launch(const BroLaunch* p, int grid, cudaStream_t stream);
 // order[] <- stream indices grouped by compressed-size class, largest first.  scratch: 512 uint32.
-extern "C" int bro_order_launch(const uint64_t* in_off, uint32_t n, uint32_t* order, uint32_t* scratch, cudaStream_t stream);
+extern "C" int bro_order_launch(const uint64_t* in_off, uint32_t n, uint32_t* order, uint32_t* scratch, uint32_t* gate, cudaStream_t stream);

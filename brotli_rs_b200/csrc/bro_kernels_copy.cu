@@ -84,6 +84,7 @@ __device__ __forceinline__ void bro_warp_copy(uint8_t* dst, const uint8_t* src, 
 
 template <int WARPS>
 __global__ void __launch_bounds__(WARPS * 32, BRO_COPY_MIN_BLOCKS) bro_copy_kernel(BroLaunch p) {
+    if (p.gate && p.gate[1]) return;       // AUTO: this batch goes to the fused kernel as a whole
     const unsigned lane = threadIdx.x & 31u;
     // staging: per warp BRO_COPY_DEPTH rounds x 32 lanes x 32 bytes (the two aligned 16-byte granules that hold a
     // unit's 16 source bytes)

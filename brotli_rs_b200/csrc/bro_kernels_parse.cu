@@ -42,6 +42,7 @@
 #define BRO_THREAD_ARENA_STRIDE_U16 (BRO_THREAD_ARENA_U16 + 704u)
 
 __global__ void __launch_bounds__(BRO_PARSE_BLOCK, BRO_PARSE_MIN_BLOCKS) bro_parse_kernel(BroLaunch p) {
+    if (p.gate && p.gate[1]) return;       // AUTO: this batch goes to the fused kernel as a whole
     const unsigned t = blockIdx.x * BRO_PARSE_BLOCK + threadIdx.x;
     const unsigned lane = threadIdx.x & 31u;
     uint16_t* const arena = p.arena + (size_t)t * BRO_THREAD_ARENA_STRIDE_U16;
@@ -140,16 +141,29 @@ __device__ __forceinline__ uint32_t bro_size_class(uint64_t len) {
 
 // Batches are made of few size classes (replicas, similar streams): the lanes of a warp that hit the same class are
 // counted by one atomic of their leader (match_any) instead of serialising on one address.
-__global__ void bro_order_hist_kernel(const uint64_t* in_off, uint32_t n, uint32_t* hist) {
+__global__ void bro_order_hist_kernel(const uint64_t* in_off, uint32_t n, uint32_t* hist, uint32_t* gate) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    const uint32_t c = i < n ? bro_size_class(in_off[i + 1] - in_off[i]) : 0xffffffffu;
+    const uint64_t len = i < n ? in_off[i + 1] - in_off[i] : 0;
+    const uint32_t c = i < n ? bro_size_class(len) : 0xffffffffu;
     const uint32_t peers = __match_any_sync(0xffffffffu, c);
     if (i < n && (peers & ((1u << (threadIdx.x & 31u)) - 1u)) == 0u) atomicAdd(&hist[c], (uint32_t)__popc(peers));
+    if (gate) {
+        // longest compressed stream of the batch (one atomic per warp)
+        const uint32_t m = __reduce_max_sync(0xffffffffu, len > 0xffffffffull ? 0xffffffffu : (uint32_t)len);
+        if ((threadIdx.x & 31u) == 0u && m) atomicMax(&gate[0], m);
+    }
 }
 
-__global__ void bro_order_scan_kernel(const uint32_t* hist, uint32_t* cursor) {
+// BRO_GATE_RATIO: throughput of the fused kernel over the decode rate of a single stream (both in compressed bytes
+// per second, measured on B200: ~10 GB/s over ~1 MB/s).  A batch whose longest stream, decoded alone, takes longer
+// than the whole batch would take at full throughput is bound by that stream on either path, and then the two-phase
+// path only adds the serial tails of its phases: the fused kernel takes the whole batch.
+#define BRO_GATE_RATIO 10000ull
+
+__global__ void bro_order_scan_kernel(const uint32_t* hist, uint32_t* cursor, const uint64_t* in_off, uint32_t n, uint32_t* gate) {
     __shared__ uint32_t s[256];
     uint32_t t = threadIdx.x;
+    if (gate && t == 0) gate[1] = ((uint64_t)gate[0] * BRO_GATE_RATIO > in_off[n] - in_off[0]) ? 1u : 0u;
     s[t] = hist[t];
     __syncthreads();
     if (t == 0) {
@@ -172,12 +186,12 @@ __global__ void bro_order_scatter_kernel(const uint64_t* in_off, uint32_t n, uin
     if (i < n) order[base + (uint32_t)__popc(peers & ((1u << lane) - 1u))] = i;
 }
 
-extern "C" int bro_order_launch(const uint64_t* in_off, uint32_t n, uint32_t* order, uint32_t* scratch, cudaStream_t stream) {
+extern "C" int bro_order_launch(const uint64_t* in_off, uint32_t n, uint32_t* order, uint32_t* scratch, uint32_t* gate, cudaStream_t stream) {
     cudaError_t e = cudaMemsetAsync(scratch, 0, 512 * sizeof(uint32_t), stream);
     if (e != cudaSuccess) return (int)e;
     uint32_t blocks = (n + 255u) / 256u;
-    bro_order_hist_kernel<<<blocks, 256, 0, stream>>>(in_off, n, scratch);
-    bro_order_scan_kernel<<<1, 256, 0, stream>>>(scratch, scratch + 256);
+    bro_order_hist_kernel<<<blocks, 256, 0, stream>>>(in_off, n, scratch, gate);
+    bro_order_scan_kernel<<<1, 256, 0, stream>>>(scratch, scratch + 256, in_off, n, gate);
     bro_order_scatter_kernel<<<blocks, 256, 0, stream>>>(in_off, n, scratch + 256, order);
     return (int)cudaGetLastError();
 }

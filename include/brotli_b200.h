@@ -58,7 +58,8 @@ int bro_ctx_set_quirks(bro_ctx* ctx, int quirks);
  *             Streams phase one cannot decode (literal context modelling, libbrotli quality >= 10) are re-run by the
  *             fused kernel inside the same call.
  *   AUTO (default): TWOPHASE for batches of at least 5 x bro_ctx_num_warps streams (the fused kernel would need that
- *             many waves of its resident warps), WARP below.
+ *             many waves of its resident warps), WARP below -- and also for a large batch that is bound by its longest
+ *             stream (decided on the device from the compressed sizes: the two-phase kernels return at once).
  * The environment variable BRO_B200_MODE=warp|twophase sets the initial mode. */
 #define BRO_MODE_AUTO 0
 #define BRO_MODE_WARP 1
@@ -76,7 +77,7 @@ uint32_t bro_ctx_num_warps(const bro_ctx* ctx);
 int bro_ctx_set_timing(bro_ctx* ctx, int on);
 int bro_ctx_last_kernel_ms(bro_ctx* ctx, float* ms4);
 /* Counters of the last batch (synchronises the device): {bytes moved by copy records, copy records executed, streams
- * handed to the fused kernel's retry pass, reserved}. */
+ * handed to the fused kernel's retry pass, 1 if AUTO's gate sent the whole batch to the fused kernel}. */
 int bro_ctx_last_batch_stats(bro_ctx* ctx, uint64_t* stats4);
 
 /* Optional: an upper bound on the compressed bytes (d_in_off[n] - d_in_off[0]) of the batches that follow, until changed
