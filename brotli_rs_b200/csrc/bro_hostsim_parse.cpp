@@ -13,6 +13,12 @@ extern "C" const uint8_t bro_dictionary_blob[];
 
 // Returns the status phase one leaves (BRO_ST_NeedFused etc. included).  *n_rec = records written, *n_steps = rounds of
 // the machine.  rec_cap = 0 selects the product's share: one record per 2 compressed bytes + 32.
+static uint32_t* g_rec_out = 0;       // when set: the records of the next decode are copied here (4 words each)
+static unsigned g_rec_out_cap = 0;
+
+// Ask the next bro_hostsim_parse_decode to export its records (tests of the piece geometry).
+extern "C" void bro_hostsim_parse_export_records(uint32_t* words, unsigned max_records) { g_rec_out = words; g_rec_out_cap = max_records; }
+
 extern "C" int bro_hostsim_parse_decode(const uint8_t* in, size_t in_len, uint8_t* out, size_t cap, size_t* out_len,
                                         int quirks, unsigned arena_u16, unsigned rec_cap, unsigned* n_rec, unsigned* n_steps) {
     if (arena_u16 == 0) arena_u16 = BRO_THREAD_ARENA_U16;
@@ -57,6 +63,12 @@ extern "C" int bro_hostsim_parse_decode(const uint8_t* in, size_t in_len, uint8_
             if (kind == BRO_REC_STORED) memcpy(out + r.dst, in + r.a, len);
             else for (uint32_t i = 0; i < len; i++) out[r.dst + i] = out[r.dst + i - r.a];
         }
+    }
+    if (g_rec_out) {
+        for (uint32_t k = 0; k < d.nrec && k < g_rec_out_cap; k++) {
+            g_rec_out[4 * k] = rec[k].dst; g_rec_out[4 * k + 1] = rec[k].len_kind; g_rec_out[4 * k + 2] = rec[k].a; g_rec_out[4 * k + 3] = d.out_mis;
+        }
+        g_rec_out = 0;
     }
     *out_len = d.pos;
     if (n_rec) *n_rec = d.nrec;

@@ -71,3 +71,18 @@ def parse_decode(data: bytes, cap: int = 1 << 20, quirks: int = 0, arena_u16: in
     st = lib(asan).bro_hostsim_parse_decode(data, len(data), out, cap, ctypes.byref(n), quirks, arena_u16, rec_cap,
                                             ctypes.byref(nrec), ctypes.byref(steps))
     return st, out.raw[: n.value], nrec.value, steps.value
+
+
+def parse_records(data: bytes, cap: int = 1 << 20):
+    """The copy records phase one writes for a stream: -> (status, [(dst, len, kind, a)], out_mis) where out_mis is the
+    alignment (address & 15) of the output buffer the pieces were cut for."""
+    import numpy as np
+    L = lib()
+    L.bro_hostsim_parse_export_records.restype = None
+    L.bro_hostsim_parse_export_records.argtypes = [ctypes.c_void_p, ctypes.c_uint]
+    max_rec = len(data) // 2 + 32
+    words = np.zeros(4 * max_rec, dtype=np.uint32)
+    L.bro_hostsim_parse_export_records(words.ctypes.data, max_rec)
+    st, out, nrec, _ = parse_decode(data, cap=cap)
+    recs = [(int(words[4 * k]), int(words[4 * k + 1]) & 0x0fffffff, int(words[4 * k + 1]) >> 28, int(words[4 * k + 2])) for k in range(nrec)]
+    return st, recs, (int(words[3]) if nrec else 0), out

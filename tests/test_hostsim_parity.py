@@ -141,3 +141,36 @@ def test_parse_record_arena_overflow():
     assert (st, out) == (0, raw) and nrec > 8
     st, _, _, _ = hostsim.parse_decode(comp, cap=len(raw), rec_cap=8)
     assert st == hostsim.RECORDS_FULL
+
+
+def test_parse_piece_geometry():
+    """every copy record is a piece of at most 32 aligned 16-byte vectors (+ < 16 ragged bytes at each end) unless it is
+    a periodic fill; records are in stream order, do not overlap, stay inside the slot and, together with the literals,
+    tile the output"""
+    enc = fuzzgen.libbrotli_enc()
+    if enc is None:
+        pytest.skip("system libbrotlienc not present")
+    seen_fill = seen_split = seen_stored = 0
+    for kind, q, lgwin, size in (("repeat2k", 5, 16, 262144), ("runs", 5, 16, 90000), ("random", 5, 16, 10000), ("words", 5, 18, 50000),
+                                 ("small_alpha", 9, 22, 30000), ("skewed", 1, 16, 40000)):
+        raw = fuzzgen.synthetic_raw(kind, 900, size)
+        st, recs, out_mis, out = hostsim.parse_records(fuzzgen.compress(enc, raw, q, lgwin), cap=len(raw))
+        if st in hostsim.RETRY:
+            continue
+        assert (st, out) == (0, raw), kind
+        end = 0
+        for dst, ln, rk, a in recs:
+            assert dst >= end and ln >= 1 and dst + ln <= len(raw), (kind, dst, ln)
+            end = dst + ln
+            fill = rk == 0 and a < ln and a < 16 * 32 + 32
+            if fill:
+                seen_fill += 1
+                continue
+            head = (16 - ((dst + out_mis) & 15)) & 15
+            head = min(head, ln)
+            assert (ln - head) >> 4 <= 32, (kind, dst, ln, a)
+            seen_stored += rk == 1
+            seen_split += ln >= 512
+            if rk == 0:
+                assert a <= dst      # a back-reference never reaches before the stream (max_allowed = min(window, pos))
+    assert seen_fill and seen_split and seen_stored
