@@ -6,8 +6,10 @@
     python bench.py --impl reference ...                                              (the CPU arm)
 
 A "step" is one pass of the hot path (one bro_batch_decode call per rank: ordering, parse, copy and fused-retry
-kernels for a large batch, the fused kernel alone for a small one) over the whole batch.  The batch is fixed
-(strong scaling): at N ranks every rank decodes 1/N of the streams, no data-path collective.
+kernels for a large batch, the fused kernel alone for a small one) over the whole batch.  Streams are independent: the
+job is sharded by stream with no data-path collective.  --scaling weak (default, what the contract asks of a path that
+partitions): every rank decodes its own BASELINE-size batch (100,000 streams per GPU; the job is N such shards).
+--scaling strong: one BASELINE-size batch split over the N ranks (profiles/r01b_scaling.md has both).
 
   value   whole-job uncompressed GB/s with inputs and outputs resident in HBM (CUDA events, max over ranks)
   e2e     the same metric through the reference-facing C ABI call bro_batch_decode_host with pinned HOST buffers:
@@ -43,6 +45,8 @@ def parse_args():
     ap.add_argument("--workload", default="c4_highratio_w16")
     ap.add_argument("--streams", type=int, default=None, help="batch size (default: the workload's BASELINE size)")
     ap.add_argument("--e2e-steps", type=int, default=None, help="timed end-to-end steps (default: min(steps, 5))")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="weak: --streams per rank (the job is N shards of that size); strong: --streams split over the ranks")
     ap.add_argument("--mode", default="auto", choices=["auto", "warp", "twophase"],
                     help="decode path (bro_ctx_set_mode); auto = the library's default policy")
     ap.add_argument("--no-e2e", action="store_true")
@@ -179,7 +183,8 @@ def run_reference(args):
     if rank != 0:
         return 0
     cores = os.cpu_count() or 1
-    n_streams = args.streams or DEFAULT_STREAMS[args.workload]
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    n_streams = (args.streams or DEFAULT_STREAMS[args.workload]) * (world if args.scaling == "weak" else 1)
     wl = build_workload(args.workload, n_streams)
     desc = wl["desc"]
     sample = args.cpu_sample_streams or cpu_sample_size(wl, cores, 1.5, n_streams)
@@ -192,7 +197,7 @@ def run_reference(args):
     line = {
         "impl": "reference", "metric": "uncompressed GB/s (many-stream batch)", "value": val, "unit": "GB/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total_t / args.steps,
-        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+        "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "u8", "data": "synthetic",
         "config": {"workload": args.workload, "description": desc, "streams": n_streams,
                    "sample": "%d streams per step" % sample},
         "cpu_baseline": {"value": val, "unit": "GB/s", "cores": cores, "kind": "port",
@@ -243,14 +248,18 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.SUM)
         return float(t.item())
 
-    # ---- workload: N_UNIQUE distinct streams tiled to the batch; this rank's shard (strong scaling) ----
-    n_streams = args.streams or DEFAULT_STREAMS[args.workload]
+    # ---- workload: N_UNIQUE distinct streams tiled to the job's batch; this rank's shard ----
+    per_rank = args.streams or DEFAULT_STREAMS[args.workload]
+    n_streams = per_rank * world if args.scaling == "weak" else per_rank
     wl = build_workload(args.workload, n_streams)
     streams, raws, desc, gidx = wl["streams"], wl["raws"], wl["desc"], wl["gidx"]
     ulen_in = np.array([len(s) for s in streams], dtype=np.int64)
     ulen_out = np.array([len(r) if r is not None else 0 for r in raws], dtype=np.int64)
     ucap = np.array([len(r) if r is not None else 70000 for r in raws], dtype=np.int64)
-    mine = shard_streams(ulen_in[gidx], ucap[gidx], world, rank)
+    if args.scaling == "weak":
+        mine = np.arange(rank * per_rank, (rank + 1) * per_rank)      # every rank: one BASELINE-size shard of the job
+    else:
+        mine = shard_streams(ulen_in[gidx], ucap[gidx], world, rank)
     uidx = gidx[mine]
     n = len(uidx)
     in_off = np.concatenate([[0], np.cumsum(ulen_in[uidx])]).astype(np.int64)
@@ -362,11 +371,15 @@ def main():
     e2e = None
     if not args.no_e2e:
         e2e_steps = args.e2e_steps or min(args.steps, 5)
-        h_in = torch.empty(int(in_off[-1]), dtype=torch.uint8).pin_memory()
-        h_in.copy_(d_in)
-        h_out = torch.empty(int(out_off[-1]), dtype=torch.uint8).pin_memory()
+        # Host memory for the end-to-end leg is bounded per BOX: with N ranks each pins 1/N of a BASELINE-size batch (at
+        # weak scaling the first 1/N of its shard), so that N = 8 does not pin 8 x 26 GB.
+        ne = n if (world == 1 or args.scaling == "strong") else max(1, n // world)
+        e_in, e_out = int(in_off[ne]), int(out_off[ne])
+        h_in = torch.empty(e_in, dtype=torch.uint8).pin_memory()
+        h_in.copy_(d_in[:e_in])
+        h_out = torch.empty(e_out, dtype=torch.uint8).pin_memory()
         hin_np, hout_np = h_in.numpy(), h_out.numpy()
-        in_off_u, out_off_u = in_off.astype(np.uint64), out_off.astype(np.uint64)
+        in_off_u, out_off_u = in_off[: ne + 1].astype(np.uint64), out_off[: ne + 1].astype(np.uint64)
         dec.decode_host(hin_np, in_off_u, out_off_u, out=hout_np)        # warm-up (also sizes the device staging)
         barrier()
         t0 = time.perf_counter()
@@ -374,15 +387,16 @@ def main():
             _, out_len, status = dec.decode_host(hin_np, in_off_u, out_off_u, out=hout_np)
         torch.cuda.synchronize()
         t1 = time.perf_counter()
-        assert (status == wl["status"][uidx]).all() and float(out_len[status == 0].sum()) == uncomp_bytes
-        for k in check[-8:]:
+        e_uncomp = float(ulen_out[uidx[:ne]].sum())
+        assert (status == wl["status"][uidx[:ne]]).all() and float(out_len[status == 0].sum()) == e_uncomp
+        for k in check[check < ne][-8:]:
             u = int(uidx[k])
             if raws[u] is not None:
                 assert hout_np[int(out_off[k]): int(out_off[k]) + int(ulen_out[u])].tobytes() == raws[u]
         e2e_t = max_over_ranks(t1 - t0)
-        e2e = {"value": all_uncomp * e2e_steps / e2e_t / 1e9, "unit": "GB/s",
-               "h2d_bytes_per_step": int(comp_bytes + 2 * 8 * (n + 1)), "d2h_bytes_per_step": int(out_off[-1] + 12 * n),
-               "steps": e2e_steps, "api": "bro_batch_decode_host (pinned host buffers, per rank)"}
+        e2e = {"value": sum_over_ranks(e_uncomp) * e2e_steps / e2e_t / 1e9, "unit": "GB/s",
+               "h2d_bytes_per_step": int(e_in + 2 * 8 * (ne + 1)), "d2h_bytes_per_step": int(e_out + 12 * ne),
+               "steps": e2e_steps, "streams_per_rank": int(ne), "api": "bro_batch_decode_host (pinned host buffers, per rank)"}
         del h_in, h_out
 
     # ---- CPU baseline (rank 0, N = 1 only): the oracle port on the host cores, bounded sample ----
@@ -399,12 +413,14 @@ def main():
         line = {
             "metric": "uncompressed GB/s (many-stream batch)", "value": value, "unit": "GB/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": total_ms_max / args.steps,
-            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+            "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "u8", "data": "synthetic",
             "config": {"workload": args.workload, "description": desc, "streams": n_streams,
                        "unique_streams": len(streams), "streams_per_rank": n, "mode": args.mode,
                        "compressed_bytes": all_comp, "uncompressed_bytes": all_uncomp,
                        "l2_policy": "inputs and outputs far larger than L2 (no flush needed)",
-                       "parallelism": "streams sharded over %d rank(s), no data-path collective" % world},
+                       "parallelism": ("%d rank(s), one %d-stream shard each (weak scaling), no data-path collective" % (world, n))
+                                      if args.scaling == "weak" else
+                                      ("one batch split over %d rank(s) (strong scaling), no data-path collective" % world)},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
         }
         print(json.dumps(line))

@@ -47,23 +47,26 @@ for j in rows:
 md.append("\n`value` is kernel-only (inputs and outputs resident in HBM), `e2e` goes through bro_batch_decode_host with pinned host "
           "buffers. The roofline peak is MEASURED_PEAKS.json's hbm_gbs. Full lines: `%s_bench_lines.jsonl`." % tag)
 open(os.path.join(ROOT, "profiles", "%s_bench.md" % tag), "w").write("\n".join(md) + "\n")
-sc = []
-for f in sorted(glob.glob(os.path.join(out, "scale_n*.json"))):
-    j = last_json(f)
-    if j:
-        sc.append(j)
-if sc:
+md, all_sc = ["# Scaling, round %s (gpurun --gpus N, one box; tools/scale_round.sh; torchrun, NCCL for barrier + reductions only)\n" % tag], []
+for mode, what in (("weak", "every rank decodes its own 100,000-stream shard (the job is N x 100,000 streams)"),
+                   ("strong", "one 100,000-stream batch split over the ranks")):
+    sc = [j for j in (last_json(f) for f in sorted(glob.glob(os.path.join(out, "scale_%s_n*.json" % mode)))) if j]
+    if not sc:
+        continue
     sc.sort(key=lambda j: j["n_gpus"])
-    base = sc[0]["value"]
-    md = ["# Scaling, round %s (gpurun --gpus N, one box; tools/scale_round.sh; torchrun, NCCL for barrier + reductions only)\n" % tag,
-          "| N | value GB/s | ms/step | e2e GB/s | streams/rank | path | speed-up vs N=1 |", "|---|---|---|---|---|---|---|"]
+    all_sc += sc
+    base = sc[0]["value"] / sc[0]["n_gpus"]
+    md += ["## %s scaling: %s\n" % (mode, what),
+           "| N | value GB/s | ms/step | e2e GB/s | streams/rank | dominant kernel | value / (N=1 value) |", "|---|---|---|---|---|---|---|"]
     for j in sc:
         md.append("| %d | %.1f | %.3f | %s | %d | %s | %.2f |" % (j["n_gpus"], j["value"], j["ms_per_step"], ("%.1f" % j["e2e"]["value"]) if j.get("e2e") else "-",
                                                                  j["config"]["streams_per_rank"], j["roofline"]["kernel"], j["value"] / base))
-    for f in sorted(glob.glob(os.path.join(out, "scale_ref_n*.json"))):
-        j = last_json(f)
-        if j:
-            md.append("\nreference arm at N=%d (rank 0 only, oracle port on %d host threads): %.2f GB/s" % (j["n_gpus"], j["cpu_baseline"]["cores"], j["value"]))
+    md.append("")
+for f in sorted(glob.glob(os.path.join(out, "scale_ref_n*.json"))):
+    j = last_json(f)
+    if j:
+        md.append("reference arm at N=%d (rank 0 only, oracle port on %d host threads): %.2f GB/s\n" % (j["n_gpus"], j["cpu_baseline"]["cores"], j["value"]))
+if all_sc:
     open(os.path.join(ROOT, "profiles", "%s_scaling.md" % tag), "w").write("\n".join(md) + "\n")
-    open(os.path.join(ROOT, "profiles", "%s_scaling_lines.jsonl" % tag), "w").write("\n".join(json.dumps(j) for j in sc) + "\n")
+    open(os.path.join(ROOT, "profiles", "%s_scaling_lines.jsonl" % tag), "w").write("\n".join(json.dumps(j) for j in all_sc) + "\n")
 print(open(os.path.join(ROOT, "profiles", "%s_bench.md" % tag)).read())
