@@ -106,7 +106,7 @@ __global__ void __launch_bounds__(WARPS * 32, BRO_COPY_MIN_BLOCKS) bro_copy_kern
             const long long t0 = clock64();
             while ((i = ((volatile uint32_t*)p.done_q)[ticket]) == 0xffffffffu) {
                 __nanosleep(500);
-                if (clock64() - t0 > (1ll << 33)) break;      // watchdog (seconds): never spin forever
+                if (clock64() - t0 > (1ll << 36)) break;      // watchdog (about half a minute): never spin forever
             }
             __threadfence();
         }

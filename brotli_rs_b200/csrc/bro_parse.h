@@ -41,8 +41,12 @@
 // table) and the insert/copy length table in shared memory; the symbols of the literal code in canonical order, needed
 // only for codes longer than 8 bits, in a compact HBM array.
 #define BRO_RB_LIT 8u
+#ifndef BRO_RB_CMD
 #define BRO_RB_CMD 6u
+#endif
+#ifndef BRO_RB_DIST
 #define BRO_RB_DIST 6u
+#endif
 // Two placements of the literal root, both measured on B200 (profiles/r01_kernel_variants.md):
 //   default: in the thread's compact HBM array (an L2 round trip per literal) -- 256 B of shared memory per thread
 //            (insert&copy and distance roots), 384 streams per SM: best on the headline high-ratio workload;

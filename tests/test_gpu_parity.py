@@ -367,3 +367,22 @@ def test_device_path_without_reservation():
         for i, r in enumerate(raws):
             assert out[int(out_off[i]): int(out_off[i]) + len(r)].tobytes() == r, (bound, i)
     d.close()
+
+
+def test_parse_and_copy_side_by_side(monkeypatch):
+    """BRO_B200_OVERLAP=1: the copy kernel runs on a side stream next to the parse kernel and follows it through the
+    completion queue -- same results as one after the other"""
+    from brotli_rs_b200 import BatchDecoder
+    enc = fuzzgen.libbrotli_enc()
+    if enc is None:
+        pytest.skip("system libbrotlienc not present")
+    raws = [fuzzgen.synthetic_raw(kind, 70 + i, size) for i, (kind, size) in
+            enumerate([("repeat2k", 262144), ("runs", 50000), ("random", 10000), ("skewed", 10000), ("words", 30000)] * 40)]
+    streams = [fuzzgen.compress(enc, r, 5, 16) for r in raws]
+    monkeypatch.setenv("BRO_B200_OVERLAP", "1")
+    d = BatchDecoder(0, mode=BatchDecoder.MODE_TWOPHASE)
+    for _ in range(3):
+        res = d.decode_streams(streams, [len(r) for r in raws])
+        for i, ((st, out), r) in enumerate(zip(res, raws)):
+            assert st == 0 and out == r, i
+    d.close()

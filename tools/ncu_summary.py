@@ -44,7 +44,7 @@ def main():
     traffic = json.load(open(traffic_path)) if os.path.exists(traffic_path) else {}
     lines = ["# ncu summaries, round %s\n" % tag,
              "Captured with `ncu --set full --clock-control none --import-source on -k regex:bro_` under gpurun",
-             "(see tools/ncu_round.sh); per-launch values of the FIRST captured launch of each report. Times under ncu are",
+             "(see tools/gpu_round.sh); per-launch values of every captured launch of each report. Times under ncu are",
              "cold-cache and serialised: use them for shares and counters, never as bench values.\n"]
     for arg in sys.argv[2:]:
         if "=" not in arg:
