@@ -374,7 +374,17 @@ BRO_FN int bro_decode_sym_r(BroBits& s, const uint16_t* root, uint32_t root_bits
         sym = e & 0x3ffu;
         return BRO_SYM_OK;
     }
-    uint32_t r = bro_sym_slow(T, peek, 1u, bro_avail(s), root_bits);
+    // not in the narrow copy: the table's own 8-bit root settles codes of up to 8 bits with one look-up; only what is
+    // longer takes the canonical search (four dependent look-ups)
+    e = T[peek & (BRO_ROOT_SIZE - 1u)];
+    len = e >> 10;
+    if (len != 0u) {
+        if (len > bro_avail(s)) return BRO_SYM_EOF;
+        bro_consume(s, len);
+        sym = e & 0x3ffu;
+        return BRO_SYM_OK;
+    }
+    uint32_t r = bro_sym_slow(T, peek, e, bro_avail(s));
     bro_consume(s, (r >> 16) & 0xffu);
     sym = r & 0xffffu;
     return (int)(r >> 24);
