@@ -121,6 +121,7 @@ BRO_FN void bro_parse_load_lit(BroParse& ps, uint16_t* lit_sorted, uint16_t* lit
     }
     ps.lit_misc = (uint32_t)T[BRO_T_MAXDEPTH] | (T[BRO_T_SINGLE] ? 0x100u : 0u) | ((uint32_t)T[BRO_T_SINGLE_SYM] << 16);
     uint8_t* sorted = (uint8_t*)lit_sorted;
+#pragma unroll 8
     for (uint32_t i = 0; i < 256u; i++) sorted[i] = (uint8_t)T[BRO_T_SORTED + i];
 }
 
