@@ -366,6 +366,9 @@ def main():
                 "whole_step": {"ms": float(np.mean(step_ms)), "algorithmic_bytes": comp_bytes + uncomp_bytes,
                                "frac": (comp_bytes + uncomp_bytes) / (float(np.mean(step_ms)) * 1e-3) / 1e9 / peak},
                 "batch_stats": stats}
+    if dom == "parse":
+        roofline["note"] = ("bro_parse_kernel (entropy decode, one thread per stream) moves few bytes and is latency-bound, not "
+                            "HBM-bound (DESIGN.md 3.3); the HBM-bound kernel of the step is bro_copy_kernel, see kernels")
 
     # ---- end to end through the C ABI with pinned host buffers ----
     e2e = None
