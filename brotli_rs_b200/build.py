@@ -64,7 +64,7 @@ def _build(force, verbose, defines):
     if res.returncode != 0:
         raise RuntimeError("nvcc failed building libbrotli_b200.so")
     with open(os.path.join(LIBDIR, os.path.basename(LIB) + ".ptxas_info.txt"), "w") as f:
-        f.write(res.stderr)
+        f.write("".join(l for l in res.stderr.splitlines(True) if "Compile time" not in l))   # stable across builds
     return LIB
 
 
