@@ -10,11 +10,12 @@ UNEXPECTED_EOF = 24
 OUTPUT_TOO_SMALL = 100
 CUDA_ERROR = 101
 PANIC_UPPERCASE_ZERO = 102
+SIZE_UNKNOWN = 103
 
 # every symbol include/brotli_b200.h declares
 ABI_SYMBOLS = [
     "bro_ctx_create", "bro_ctx_destroy", "bro_ctx_set_quirks", "bro_ctx_set_mode", "bro_ctx_last_cuda_error", "bro_ctx_launch_count",
-    "bro_ctx_num_warps", "bro_ctx_reserve", "bro_ctx_set_timing", "bro_ctx_last_kernel_ms", "bro_ctx_last_batch_stats", "bro_batch_decode", "bro_batch_decode_host", "bro_status_description",
+    "bro_ctx_num_warps", "bro_ctx_reserve", "bro_ctx_set_timing", "bro_ctx_last_kernel_ms", "bro_ctx_last_batch_stats", "bro_batch_decode", "bro_batch_decode_host", "bro_batch_sizes", "bro_batch_decode_unsized_host", "bro_free", "bro_status_description",
     "bro_reader_new", "bro_reader_read", "bro_reader_status", "bro_reader_free",
 ]
 
@@ -72,6 +73,12 @@ def load_library():
     L.bro_batch_decode.argtypes = [vp, vp, vp, vp, vp, vp, vp, u32, vp]
     L.bro_batch_decode_host.restype = ctypes.c_int
     L.bro_batch_decode_host.argtypes = [vp, vp, vp, vp, vp, vp, vp, u32]
+    L.bro_batch_sizes.restype = ctypes.c_int
+    L.bro_batch_sizes.argtypes = [vp, vp, vp, vp, vp, u32, vp]
+    L.bro_batch_decode_unsized_host.restype = ctypes.c_int
+    L.bro_batch_decode_unsized_host.argtypes = [vp, vp, vp, u32, ctypes.POINTER(vp), vp, vp, vp]
+    L.bro_free.restype = None
+    L.bro_free.argtypes = [vp]
     L.bro_status_description.restype = ctypes.c_char_p
     L.bro_status_description.argtypes = [ctypes.c_int]
     L.bro_reader_new.restype = vp

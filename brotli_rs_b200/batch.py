@@ -140,6 +140,39 @@ class BatchDecoder:
         self._check(st)
         return out, out_len, status
 
+    def sizes_device(self, d_in, d_in_off, stream=None):
+        """bro_batch_sizes on torch CUDA tensors: measure the streams without writing a byte (asynchronous).
+        Returns (d_out_len, d_status); status 103 (SIZE_UNKNOWN) = only a real decode tells this stream's size."""
+        import torch
+        n = d_in_off.numel() - 1
+        d_out_len = torch.empty(n, dtype=torch.int64, device=d_in.device)
+        d_status = torch.empty(n, dtype=torch.int32, device=d_in.device)
+        s = stream if stream is not None else torch.cuda.current_stream(d_in.device)
+        self._check(self._lib.bro_batch_sizes(self._ctx, d_in.data_ptr(), d_in_off.data_ptr(), d_out_len.data_ptr(),
+                                              d_status.data_ptr(), n, ctypes.c_void_p(s.cuda_stream)))
+        return d_out_len, d_status
+
+    def decode_unsized(self, streams):
+        """bro_batch_decode_unsized_host: list of byte strings, NO size hints -> list of (status, bytes).  The library
+        measures the streams, sizes the slots itself and returns one buffer."""
+        in_buf, in_off = pack_streams(streams)
+        n = len(streams)
+        out_off = np.zeros(n + 1, dtype=np.uint64)
+        out_len = np.zeros(n, dtype=np.uint64)
+        status = np.zeros(n, dtype=np.int32)
+        h_out = ctypes.c_void_p()
+        st = self._lib.bro_batch_decode_unsized_host(self._ctx, in_buf.ctypes.data if len(in_buf) else None, in_off.ctypes.data, n,
+                                                     ctypes.byref(h_out), out_off.ctypes.data, out_len.ctypes.data, status.ctypes.data)
+        self._check(st)
+        try:
+            total = int(out_off[-1])
+            buf = (ctypes.c_uint8 * max(total, 1)).from_address(h_out.value) if h_out.value else None
+            mv = memoryview(buf) if buf is not None else memoryview(b"")
+            return [(int(status[i]), bytes(mv[int(out_off[i]): int(out_off[i]) + int(out_len[i])])) for i in range(n)]
+        finally:
+            if h_out.value:
+                self._lib.bro_free(h_out)
+
     def decode_streams(self, streams, capacities):
         """Convenience: list of byte strings + per-stream output capacities -> list of (status, bytes)."""
         in_buf, in_off = pack_streams(streams)

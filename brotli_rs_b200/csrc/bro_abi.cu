@@ -300,6 +300,44 @@ extern "C" int bro_batch_decode(bro_ctx* ctx, const uint8_t* d_in, const uint64_
     return BRO_ST_OK;
 }
 
+extern "C" int bro_batch_sizes(bro_ctx* ctx, const uint8_t* d_in, const uint64_t* d_in_off, uint64_t* d_out_len,
+                               int32_t* d_status, uint32_t n, void* stream) {
+    if (!ctx) return BRO_ST_InvalidArgument;
+    if (n == 0) return BRO_ST_OK;
+    if (!d_in_off || !d_out_len || !d_status) return BRO_ST_InvalidArgument;
+    cudaStream_t s = (cudaStream_t)stream;
+    int st;
+    if (!ctx->d_arena_t) {
+        BRO_CUDA(ctx, cudaMalloc(&ctx->d_arena_t, (size_t)ctx->num_threads * bro_parse_kernel_arena_bytes()));
+        ctx->roots_bytes = (size_t)ctx->num_threads * bro_parse_kernel_roots_bytes();
+        if (ctx->roots_bytes) BRO_CUDA(ctx, cudaMalloc(&ctx->d_roots, ctx->roots_bytes));
+    }
+    if ((st = bro_grow(ctx, (void**)&ctx->d_order, &ctx->d_order_cap, (size_t)n, 3 * sizeof(uint32_t)))) return st;
+    BRO_CUDA(ctx, cudaMemsetAsync(ctx->d_counter, 0, 16 * sizeof(uint32_t), s));
+    BroLaunch p;
+    memset(&p, 0, sizeof(p));
+    p.in = d_in; p.in_off = d_in_off; p.out_len = d_out_len; p.status = d_status; p.n = n;
+    p.dict = ctx->d_dict; p.quirk_spec = ctx->quirks;
+    p.retry_count = ctx->d_counter + 2;
+    p.sizing = 1;
+    cudaError_t e = (cudaError_t)bro_order_launch(d_in_off, n, ctx->d_order, ctx->d_order_scratch, NULL, s);
+    if (e != cudaSuccess) return bro_fail(ctx, e, "bro_order kernels launch");
+    ctx->launches += 3;
+    const uint32_t tb = (uint32_t)bro_parse_kernel_block();
+    int grid_t = ctx->grid_t;
+    if ((uint32_t)grid_t > (n + tb - 1) / tb) grid_t = (int)((n + tb - 1) / tb);
+    p.arena = ctx->d_arena_t; p.counter = ctx->d_counter; p.order = ctx->d_order; p.roots = ctx->d_roots;
+    e = (cudaError_t)bro_parse_kernel_launch(&p, grid_t, s);
+    if (e != cudaSuccess) return bro_fail(ctx, e, "bro_parse_kernel launch");
+    ctx->launches += 1;
+    e = (cudaError_t)bro_sizes_finish_launch(d_status, n, s);          // internal hand-over statuses -> BRO_SIZE_UNKNOWN
+    if (e != cudaSuccess) return bro_fail(ctx, e, "bro_sizes_finish_kernel launch");
+    ctx->launches += 1;
+    return BRO_ST_OK;
+}
+
+extern "C" void bro_free(void* p) { free(p); }
+
 static int bro_reserve(bro_ctx* ctx, void** p, size_t* cap, size_t need) {
     if (*cap >= need) return BRO_ST_OK;
     if (*p) { BRO_CUDA(ctx, cudaFree(*p)); *p = NULL; *cap = 0; }
@@ -345,6 +383,108 @@ extern "C" int bro_batch_decode_host(bro_ctx* ctx, const uint8_t* h_in, const ui
     return BRO_ST_OK;
 }
 
+extern "C" int bro_batch_decode_unsized_host(bro_ctx* ctx, const uint8_t* h_in, const uint64_t* h_in_off, uint32_t n,
+                                             uint8_t** h_out, uint64_t* h_out_off, uint64_t* h_out_len, int32_t* h_status) {
+    if (!ctx || !h_out) return BRO_ST_InvalidArgument;
+    *h_out = NULL;
+    if (n == 0) { if (h_out_off) h_out_off[0] = 0; return BRO_ST_OK; }
+    if (!h_in_off || !h_out_off || !h_out_len || !h_status) return BRO_ST_InvalidArgument;
+    BRO_CUDA(ctx, cudaSetDevice(ctx->device));
+    const uint64_t in_lo = h_in_off[0], in_hi = h_in_off[n];
+    if (in_hi < in_lo) return BRO_ST_InvalidArgument;
+    const size_t in_bytes = (size_t)(in_hi - in_lo), off_bytes = (size_t)(n + 1) * sizeof(uint64_t);
+    const size_t meta_bytes = 2 * off_bytes + (size_t)n * sizeof(uint64_t) + (size_t)n * sizeof(int32_t);
+    int st;
+    if ((st = bro_reserve(ctx, (void**)&ctx->d_in, &ctx->d_in_cap, in_bytes + 16))) return st;
+    if ((st = bro_reserve(ctx, (void**)&ctx->d_meta, &ctx->d_meta_cap, meta_bytes))) return st;
+    uint64_t* d_in_off = ctx->d_meta;
+    uint64_t* d_out_off = d_in_off + (n + 1);
+    uint64_t* d_out_len = d_out_off + (n + 1);
+    int32_t* d_status = (int32_t*)(d_out_len + n);
+    cudaStream_t s = 0;
+    try {
+        // 1. measure (no output is written); the compressed batch stays on the device for the decode
+        if (in_bytes) BRO_CUDA(ctx, cudaMemcpyAsync(ctx->d_in, h_in + in_lo, in_bytes, cudaMemcpyHostToDevice, s));
+        BRO_CUDA(ctx, cudaMemcpyAsync(d_in_off, h_in_off, off_bytes, cudaMemcpyHostToDevice, s));
+        if ((st = bro_batch_sizes(ctx, ctx->d_in - in_lo, d_in_off, d_out_len, d_status, n, s))) return st;
+        BRO_CUDA(ctx, cudaMemcpyAsync(h_out_len, d_out_len, (size_t)n * sizeof(uint64_t), cudaMemcpyDeviceToHost, s));
+        BRO_CUDA(ctx, cudaMemcpyAsync(h_status, d_status, (size_t)n * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+        BRO_CUDA(ctx, cudaStreamSynchronize(s));
+        // 2. slots: exact where the size is known, a guess (grown while the stream answers OutputTooSmall) elsewhere;
+        //    invalid streams keep the status the measurement found and get an empty slot
+        std::vector<uint64_t> cap(n), slot_off(n + 1);
+        std::vector<uint32_t> todo;            // streams still to decode
+        for (uint32_t i = 0; i < n; i++) {
+            if (h_status[i] == BRO_ST_OK) { cap[i] = h_out_len[i]; todo.push_back(i); }
+            else if (h_status[i] == BRO_ST_SizeUnknown) { cap[i] = 8 * (h_in_off[i + 1] - h_in_off[i]) + 4096; todo.push_back(i); }
+            else { cap[i] = 0; h_out_len[i] = 0; }
+        }
+        std::vector<std::vector<uint8_t> > grown(n);     // final bytes of the streams that needed a second attempt
+        std::vector<uint8_t> first;                      // slots of the first attempt
+        std::vector<uint64_t> first_off(n + 1, 0);
+        std::vector<int32_t> st_tmp;
+        std::vector<uint64_t> len_tmp, off_in, off_out;
+        for (int attempt = 0; !todo.empty(); attempt++) {
+            const uint32_t m = (uint32_t)todo.size();
+            off_in.assign(m + 1, 0); off_out.assign(m + 1, 0); len_tmp.assign(m, 0); st_tmp.assign(m, 0);
+            // the sub-batch: compressed streams gathered on the host (first attempt: the batch as it is)
+            std::vector<uint8_t> sub_in;
+            const uint8_t* in_ptr = h_in;
+            if (m == n) { for (uint32_t k = 0; k <= n; k++) off_in[k] = h_in_off[k]; }
+            else {
+                size_t tot = 0;
+                for (uint32_t k = 0; k < m; k++) tot += (size_t)(h_in_off[todo[k] + 1] - h_in_off[todo[k]]);
+                sub_in.resize(tot ? tot : 1);
+                size_t o = 0;
+                for (uint32_t k = 0; k < m; k++) {
+                    const size_t len = (size_t)(h_in_off[todo[k] + 1] - h_in_off[todo[k]]);
+                    if (len) memcpy(sub_in.data() + o, h_in + h_in_off[todo[k]], len);
+                    off_in[k] = o; o += len;
+                }
+                off_in[m] = o;
+                in_ptr = sub_in.data();
+            }
+            for (uint32_t k = 0; k < m; k++) off_out[k + 1] = off_out[k] + ((cap[todo[k]] + 15) & ~(uint64_t)15);
+            std::vector<uint8_t> sub_out((size_t)off_out[m] ? (size_t)off_out[m] : 1);
+            // bro_batch_decode_host takes slot i as [off[i], off[i+1]): the padding to 16 bytes belongs to the slot, which
+            // is harmless (a stream that fits its exact size fits the padded slot)
+            if ((st = bro_batch_decode_host(ctx, in_ptr, off_in.data(), sub_out.data(), off_out.data(), len_tmp.data(), st_tmp.data(), m))) return st;
+            std::vector<uint32_t> again;
+            for (uint32_t k = 0; k < m; k++) {
+                const uint32_t i = todo[k];
+                if (st_tmp[k] == BRO_ST_OutputTooSmall && cap[i] < 0xf0000000ull && attempt < 12) {
+                    cap[i] = cap[i] * 4 < 0xf0000000ull ? cap[i] * 4 : 0xf0000000ull;
+                    again.push_back(i);
+                    continue;
+                }
+                h_status[i] = st_tmp[k];
+                h_out_len[i] = st_tmp[k] == BRO_ST_OK ? len_tmp[k] : 0;
+                if (attempt == 0) continue;            // first-attempt bytes stay in `first`
+                grown[i].assign(sub_out.begin() + (size_t)off_out[k], sub_out.begin() + (size_t)off_out[k] + (size_t)h_out_len[i]);
+            }
+            if (attempt == 0) {
+                first.swap(sub_out);
+                for (uint32_t k = 0; k < m; k++) first_off[todo[k]] = off_out[k];
+            }
+            todo.swap(again);
+        }
+        // 3. one buffer, streams back to back (16-byte aligned starts)
+        h_out_off[0] = 0;
+        for (uint32_t i = 0; i < n; i++) h_out_off[i + 1] = h_out_off[i] + ((h_out_len[i] + 15) & ~(uint64_t)15);
+        uint8_t* out = (uint8_t*)malloc((size_t)h_out_off[n] ? (size_t)h_out_off[n] : 1);
+        if (!out) return BRO_ST_InvalidArgument;
+        for (uint32_t i = 0; i < n; i++) {
+            if (!h_out_len[i]) continue;
+            const uint8_t* src = grown[i].empty() ? first.data() + (size_t)first_off[i] : grown[i].data();
+            memcpy(out + h_out_off[i], src, (size_t)h_out_len[i]);
+        }
+        *h_out = out;
+    } catch (...) {
+        return BRO_ST_InvalidArgument;
+    }
+    return BRO_ST_OK;
+}
+
 // src/lib.rs:331-354 -- the strings are the observable error payload of the reference (io::Error description)
 extern "C" const char* bro_status_description(int st) {
     switch (st) {
@@ -376,6 +516,7 @@ extern "C" const char* bro_status_description(int st) {
     case BRO_ST_OutputTooSmall: return "output slot too small for the decoded stream";
     case BRO_ST_CudaError: return "CUDA error";
     case BRO_ST_PanicUppercaseZero: return "reference panics: uppercase_first on a dictionary word starting with 0x00";
+    case BRO_ST_SizeUnknown: return "the size of the stream is known only after decoding it";
     case BRO_ST_InvalidArgument: return "invalid argument";
     default: return "unknown status";
     }

@@ -568,6 +568,7 @@ struct BroDec {
     uint16_t* roots_cd;       // roots of the current literal, insert&copy and distance tables (shared memory)
     const uint32_t* ic;       // bro_ic_insert / bro_ic_copy interleaved (shared memory)
     uint32_t out_mis;         // (address of out) & 15: pieces are cut at 16-byte boundaries of the destination ADDRESS
+    uint32_t sizing;          // 1: only measure the stream (bro_batch_sizes): nothing is written, the slot is unbounded
 #endif
 };
 
@@ -593,6 +594,7 @@ BRO_FN bool bro_rec_push1(BroDec& d, uint32_t dst, uint32_t len, uint32_t kind, 
 // the same copy wrote, which the copy kernel's grouping handles like any other dependency.  Only a copy whose distance
 // is shorter than a piece (a periodic fill) stays whole.
 BRO_FN bool bro_rec_push(BroDec& d, uint32_t dst, uint32_t len, uint32_t kind, uint32_t a) {
+    if (d.sizing) return true;
     if (kind == BRO_REC_LZ && a < len && a < 16u * BRO_REC_PIECE_VECS + 32u) return bro_rec_push1(d, dst, len, kind, a);
     // first piece: up to the 16-byte boundary plus BRO_REC_PIECE_VECS vectors; then whole pieces; the last few bytes
     // (< 16) ride along as the tail of the piece before them

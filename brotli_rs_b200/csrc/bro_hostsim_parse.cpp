@@ -13,6 +13,9 @@ extern "C" const uint8_t bro_dictionary_blob[];
 
 // Returns the status phase one leaves (BRO_ST_NeedFused etc. included).  *n_rec = records written, *n_steps = rounds of
 // the machine.  rec_cap = 0 selects the product's share: one record per 2 compressed bytes + 32.
+static uint32_t g_sizing = 0;         // next decodes only measure (bro_batch_sizes' mode): no output, unbounded slot
+extern "C" void bro_hostsim_parse_set_sizing(unsigned on) { g_sizing = on; }
+
 static uint32_t* g_rec_out = 0;       // when set: the records of the next decode are copied here (4 words each)
 static unsigned g_rec_out_cap = 0;
 
@@ -36,7 +39,8 @@ extern "C" int bro_hostsim_parse_decode(const uint8_t* in, size_t in_len, uint8_
     d.dict = bro_dictionary_blob;
     d.out = out;
     d.out_mis = (uint32_t)((uintptr_t)out & 15u);
-    d.cap = cap > BRO_MAX_SLOT ? (uint32_t)BRO_MAX_SLOT : (uint32_t)cap;
+    d.sizing = g_sizing;
+    d.cap = (cap > BRO_MAX_SLOT || g_sizing) ? (uint32_t)BRO_MAX_SLOT : (uint32_t)cap;
     d.pos = 0;
     d.p1 = d.p2 = 0;
     d.d0 = 4; d.d1 = 11; d.d2 = 15; d.d3 = 16;
@@ -56,7 +60,7 @@ extern "C" int bro_hostsim_parse_decode(const uint8_t* in, size_t in_len, uint8_
         else { bro_parse_round(d, ps, mb); steps++; }
     }
     // phase two, the obvious way
-    if (ps.st == BRO_ST_OK) {
+    if (ps.st == BRO_ST_OK && !g_sizing) {
         for (uint32_t k = 0; k < d.nrec; k++) {
             const BroRec r = rec[k];
             const uint32_t len = r.len_kind & BRO_REC_LEN_MASK, kind = r.len_kind >> BRO_REC_KIND_SHIFT;

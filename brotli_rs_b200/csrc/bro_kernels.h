@@ -35,6 +35,7 @@ struct BroLaunch {
     // AUTO mode: [0] longest compressed stream of the batch (bytes, saturated), [1] 1 = the batch is bound by its longest
     // stream: the parse and copy kernels return at once and the fused kernel decodes everything.  NULL = no gating.
     uint32_t* gate;
+    int sizing;               // parse kernel: only measure the streams (bro_batch_sizes): out_len = decoded size, nothing written
     uint32_t* done_tail;
     uint16_t* roots;          // parse kernel: per-thread decode tables (bro_parse.h) when they live in HBM / L2
     unsigned long long* copy_stats;   // [0] bytes moved by records, [1] records executed (this batch)
@@ -54,6 +55,8 @@ extern "C" int bro_parse_kernel_block();
 extern "C" size_t bro_parse_kernel_arena_bytes();
 extern "C" size_t bro_parse_kernel_roots_bytes();
 extern "C" int bro_parse_kernel_launch(const BroLaunch* p, int grid, cudaStream_t stream);
+// bro_batch_sizes: turn the internal hand-over statuses into BRO_ST_SizeUnknown
+extern "C" int bro_sizes_finish_launch(int32_t* status, uint32_t n, cudaStream_t stream);
 // two-phase path, phase two: the copy kernel (one warp per stream) (bro_kernels_copy.cu)
 extern "C" int bro_copy_kernel_occupancy(int* blocks_per_sm);
 extern "C" int bro_copy_kernel_warps_per_cta();

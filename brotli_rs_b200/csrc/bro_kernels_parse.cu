@@ -1,14 +1,15 @@
 // bro_kernels_parse.cu -- PHASE ONE of the two-phase path for sm_100a: the parse kernel (one THREAD per stream) and
 // the size-class ordering kernels that feed it.
 //
-// Every lane of a warp owns a different stream and runs the flat state machine of bro_parse.h: one trip decodes one
-// prefix-code symbol of whatever kind the lane needs next, so 32 streams advance per warp instruction on the
-// expensive part of the decode.  Literals and dictionary words go straight into the output slots; LZ77
-// back-references and stored meta-blocks become BroRec records for the copy kernel (bro_kernels_copy.cu).
+// Every lane of a warp owns a different stream and runs the lockstep rounds of bro_parse.h (insert&copy symbol, a few
+// literals, distance code, copy), so 32 streams advance per warp instruction on the expensive part of the decode.
+// Literals and dictionary words go straight into the output slots; LZ77 back-references and stored meta-blocks become
+// BroRec records for the copy kernel (bro_kernels_copy.cu).  In sizing mode (bro_batch_sizes) nothing is written at all:
+// the kernel only reports every stream's decoded size.
 //
 // Meta-block headers (prefix codes, context maps: long structured code, bro_decoder_core.h with a 1-lane "warp") are
 // entered by the lanes of a warp TOGETHER: a lane that reaches a meta-block boundary waits (up to BRO_PARSE_PATIENCE
-// trips of the others) until every lane is at a boundary, and lanes whose stream ended pull their next stream at the
+// rounds of the others) until every lane is at a boundary, and lanes whose stream ended pull their next stream at the
 // same moment.  Streams are handed out by compressed-size class, so the lanes of a warp hold similar streams.
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -73,6 +74,7 @@ __global__ void __launch_bounds__(BRO_PARSE_BLOCK, BRO_PARSE_MIN_BLOCKS) bro_par
     d.arena_base = 0;
     d.dict = p.dict;
     d.quirk_spec = p.quirk_spec;
+    d.sizing = p.sizing ? 1u : 0u;
     for (;;) {
         const uint32_t at_boundary = __ballot_sync(0xffffffffu, ps.kind >= BRO_K_HEADER);
         if (at_boundary != 0u) {
@@ -83,13 +85,13 @@ __global__ void __launch_bounds__(BRO_PARSE_BLOCK, BRO_PARSE_MIN_BLOCKS) bro_par
                 if (ps.kind == BRO_K_DONE && ps.st >= 0) {
                     p.status[stream] = ps.st;
                     p.out_len[stream] = d.pos;
-                    p.nrec[stream] = d.nrec;
+                    if (p.nrec) p.nrec[stream] = d.nrec;
                     if (BRO_ST_IS_RETRY(ps.st)) atomicAdd(p.retry_count, 1u);
                     ps.st = -1;
                     // announce the stream to the copy kernel: everything this thread wrote for it (literals, dictionary
                     // words, records, the three values above) is visible before its index appears in the queue
                     __threadfence();
-                    ((volatile uint32_t*)p.done_q)[atomicAdd(p.done_tail, 1u)] = stream;
+                    if (p.done_q) ((volatile uint32_t*)p.done_q)[atomicAdd(p.done_tail, 1u)] = stream;
                 }
                 const uint32_t idle = __ballot_sync(0xffffffffu, ps.kind == BRO_K_DONE);
                 if (idle != 0u && !exhausted) {
@@ -103,11 +105,11 @@ __global__ void __launch_bounds__(BRO_PARSE_BLOCK, BRO_PARSE_MIN_BLOCKS) bro_par
                         if (k < p.n) {
                             stream = p.order ? p.order[k] : k;
                             const uint64_t in_b = p.in_off[stream], in_e = p.in_off[stream + 1];
-                            const uint64_t out_b = p.out_off[stream], out_e = p.out_off[stream + 1];
+                            const uint64_t out_b = p.sizing ? 0 : p.out_off[stream], out_e = p.sizing ? 0 : p.out_off[stream + 1];
                             d.out = p.out + out_b;
                             d.out_mis = (uint32_t)((uintptr_t)d.out & 15u);
                             const uint64_t cap = out_e - out_b;
-                            d.cap = cap > BRO_MAX_SLOT ? (uint32_t)BRO_MAX_SLOT : (uint32_t)cap;
+                            d.cap = (cap > BRO_MAX_SLOT || p.sizing) ? (uint32_t)BRO_MAX_SLOT : (uint32_t)cap;
                             d.pos = 0;
                             d.p1 = 0; d.p2 = 0;
                             d.d0 = 4; d.d1 = 11; d.d2 = 15; d.d3 = 16;   // src/lib.rs:407-408
@@ -118,7 +120,7 @@ __global__ void __launch_bounds__(BRO_PARSE_BLOCK, BRO_PARSE_MIN_BLOCKS) bro_par
                             d.rec_cap = rec_n > 0x0fffffffull ? 0x0fffffffu : (uint32_t)rec_n;
                             bro_bits_init(d.in, p.in + in_b, p.in + in_e);
                             bro_parse_begin(ps);
-                            if (rec_b + rec_n > p.rec_total) bro_parse_finish(ps, BRO_ST_RecordsFull);
+                            if (!p.sizing && rec_b + rec_n > p.rec_total) bro_parse_finish(ps, BRO_ST_RecordsFull);
                             if (in_e - in_b >= (1ull << 28)) bro_parse_finish(ps, BRO_ST_NeedFused);   // 32-bit bit counts
                         }
                     }
@@ -193,6 +195,16 @@ extern "C" int bro_order_launch(const uint64_t* in_off, uint32_t n, uint32_t* or
     bro_order_hist_kernel<<<blocks, 256, 0, stream>>>(in_off, n, scratch, gate);
     bro_order_scan_kernel<<<1, 256, 0, stream>>>(scratch, scratch + 256, in_off, n, gate);
     bro_order_scatter_kernel<<<blocks, 256, 0, stream>>>(in_off, n, scratch + 256, order);
+    return (int)cudaGetLastError();
+}
+
+__global__ void bro_sizes_finish_kernel(int32_t* status, uint32_t n) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n && BRO_ST_IS_RETRY(status[i])) status[i] = BRO_ST_SizeUnknown;
+}
+
+extern "C" int bro_sizes_finish_launch(int32_t* status, uint32_t n, cudaStream_t stream) {
+    bro_sizes_finish_kernel<<<(n + 255u) / 256u, 256, 0, stream>>>(status, n);
     return (int)cudaGetLastError();
 }
 

@@ -298,7 +298,7 @@ BRO_FN void bro_parse_round(BroDec& d, BroParse& ps, BroMbInfo& mb) {
                     const int r = bro_parse_lit_long(d.in, ps, BRO_LIT_SORTED(d), peek, sym);
                     if (r != BRO_SYM_OK) { bro_parse_finish(ps, r == BRO_SYM_HOLE ? BRO_ST_ParseErrorInsertLiterals : BRO_ST_UnexpectedEOF); fast = 0; }
                 } else bro_consume(d.in, len);
-                if (fast) { op[u] = (uint8_t)sym; done = u + 1u; }
+                if (fast) { if (!d.sizing) op[u] = (uint8_t)sym; done = u + 1u; }
             }
         }
         if (done != 0u && ps.kind == BRO_K_LIT) {
@@ -319,7 +319,7 @@ BRO_FN void bro_parse_round(BroDec& d, BroParse& ps, BroMbInfo& mb) {
             if (r != BRO_SYM_OK) bro_parse_finish(ps, r == BRO_SYM_HOLE ? BRO_ST_ParseErrorInsertLiterals : BRO_ST_UnexpectedEOF);
             else {
                 // a run that does not fit the slot is still decoded: a decode error inside it wins over OutputTooSmall
-                if (d.pos < d.cap) d.out[d.pos] = (uint8_t)sym;
+                if (d.pos < d.cap && !d.sizing) d.out[d.pos] = (uint8_t)sym;
                 d.pos += 1;
                 if (--ps.ins_rem == 0u) bro_parse_after_literals(d, ps);
             }
@@ -358,7 +358,7 @@ BRO_FN void bro_parse_round(BroDec& d, BroParse& ps, BroMbInfo& mb) {
                     else if (ps.mlen < mb_out + (uint32_t)n) st = BRO_ST_ExceededExpectedBytes;                  // after the transform (Q10)
                     else if ((uint32_t)n > d.cap - d.pos) st = BRO_ST_OutputTooSmall;
                     else {
-                        for (uint32_t i = 0; i < (uint32_t)n; i++) d.out[d.pos + i] = d.sc->word[i];
+                        if (!d.sizing) for (uint32_t i = 0; i < (uint32_t)n; i++) d.out[d.pos + i] = d.sc->word[i];
                         d.pos += (uint32_t)n;
                     }
                 }

@@ -32,6 +32,7 @@
 #define BRO_ST_CudaError 101           /* a CUDA runtime call failed (host-side entry points only) */
 #define BRO_ST_PanicUppercaseZero 102  /* the reference reaches unreachable!() at src/transformation/mod.rs:78 */
 #define BRO_ST_InvalidArgument 104
+#define BRO_ST_SizeUnknown 103        /* bro_batch_sizes: the stream's size is only known after decoding it (literal context modelling) */
 /* internal: set by the two-phase path (parse kernel) for streams it hands to the fused warp kernel's retry pass; never
  * visible to a caller */
 #define BRO_ST_ArenaTooSmall 105      /* meta-block needs more table space than a parse-thread arena */

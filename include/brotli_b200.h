@@ -35,6 +35,7 @@ extern "C" {
 #define BRO_OUTPUT_TOO_SMALL 100      /* the stream decodes to more bytes than its output slot holds */
 #define BRO_CUDA_ERROR 101            /* a CUDA call failed; bro_ctx_last_cuda_error() has the text */
 #define BRO_PANIC_UPPERCASE_ZERO 102  /* the reference panics here (src/transformation/mod.rs:78) */
+#define BRO_SIZE_UNKNOWN 103          /* bro_batch_sizes only: the size is known only after decoding the stream */
 #define BRO_INVALID_ARGUMENT 104
 
 typedef struct bro_ctx bro_ctx;       /* one GPU, one CUDA stream's worth of scratch; not thread safe */
@@ -102,6 +103,24 @@ int bro_batch_decode(bro_ctx* ctx, const uint8_t* d_in, const uint64_t* d_in_off
  * slots, lengths and statuses back, and synchronises.  This is the end-to-end path a host-language caller uses. */
 int bro_batch_decode_host(bro_ctx* ctx, const uint8_t* h_in, const uint64_t* h_in_off, uint8_t* h_out,
                           const uint64_t* h_out_off, uint64_t* h_out_len, int32_t* h_status, uint32_t n);
+
+/* ---- decoding without knowing the uncompressed sizes (a Brotli stream does not state its size: MLEN is per meta-block,
+ * src/lib.rs:469-483; the reference grows a Vec as it goes, src/lib.rs:2183-2189) ----
+ *
+ * bro_batch_sizes: measure n streams without writing a byte (the entropy decode of the two-phase path, copies counted
+ * but not made).  d_out_len[i] = decoded size and d_status[i] = BRO_OK or the stream's error -- final, the stream need
+ * not be decoded again to learn it -- or BRO_SIZE_UNKNOWN for a stream whose size only a real decode tells (literal
+ * context modelling, libbrotli quality >= 10).  Asynchronous on `stream`. */
+int bro_batch_sizes(bro_ctx* ctx, const uint8_t* d_in, const uint64_t* d_in_off, uint64_t* d_out_len, int32_t* d_status,
+                    uint32_t n, void* stream);
+
+/* bro_batch_decode_unsized_host: bro_batch_decode_host for a caller who does not know the sizes.  Measures the streams,
+ * gives every stream an exact slot (a geometrically growing one for BRO_SIZE_UNKNOWN streams, retried while they answer
+ * BRO_OUTPUT_TOO_SMALL), decodes, and returns ONE buffer allocated by the library: *h_out (release with bro_free),
+ * stream i at [h_out_off[i], h_out_off[i] + h_out_len[i]).  h_out_off (n + 1), h_out_len (n), h_status (n) are the caller's. */
+int bro_batch_decode_unsized_host(bro_ctx* ctx, const uint8_t* h_in, const uint64_t* h_in_off, uint32_t n, uint8_t** h_out,
+                                  uint64_t* h_out_off, uint64_t* h_out_len, int32_t* h_status);
+void bro_free(void* p);
 
 /* The reference's error strings, byte-identical (src/lib.rs:331-354; typos included). */
 const char* bro_status_description(int status);

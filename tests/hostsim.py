@@ -86,3 +86,19 @@ def parse_records(data: bytes, cap: int = 1 << 20):
     st, out, nrec, _ = parse_decode(data, cap=cap)
     recs = [(int(words[4 * k]), int(words[4 * k + 1]) & 0x0fffffff, int(words[4 * k + 1]) >> 28, int(words[4 * k + 2])) for k in range(nrec)]
     return st, recs, (int(words[3]) if nrec else 0), out
+
+
+def parse_size(data: bytes, quirks: int = 0):
+    """bro_batch_sizes' mode of phase one: measure without writing.  -> (status, decoded size)"""
+    L = lib()
+    L.bro_hostsim_parse_set_sizing.restype = None
+    L.bro_hostsim_parse_set_sizing.argtypes = [ctypes.c_uint]
+    L.bro_hostsim_parse_set_sizing(1)
+    try:
+        out = ctypes.create_string_buffer(1)
+        n = ctypes.c_size_t()
+        nrec, steps = ctypes.c_uint(), ctypes.c_uint()
+        st = L.bro_hostsim_parse_decode(data, len(data), out, 0, ctypes.byref(n), quirks, 0, 0, ctypes.byref(nrec), ctypes.byref(steps))
+        return st, n.value
+    finally:
+        L.bro_hostsim_parse_set_sizing(0)

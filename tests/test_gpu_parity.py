@@ -386,3 +386,33 @@ def test_parse_and_copy_side_by_side(monkeypatch):
         for i, ((st, out), r) in enumerate(zip(res, raws)):
             assert st == 0 and out == r, i
     d.close()
+
+
+def test_decode_without_size_hints():
+    """bro_batch_sizes / bro_batch_decode_unsized_host: the caller knows no uncompressed size (the reference's
+    Decompressor does not either: src/lib.rs:2183-2189 grows a Vec)"""
+    import torch
+    from brotli_rs_b200 import BatchDecoder
+    from brotli_rs_b200.batch import pack_streams
+    files = corpus_files()
+    streams = [c for _, c, _ in files] + list(fuzzgen.mutations([c for _, c, _ in files], seed=31, count=400))
+    want = [oracle.decode(s) for s in streams]
+    d = BatchDecoder(0)
+    # measuring alone: exact sizes and final statuses wherever the size is knowable without a decode
+    in_buf, in_off = pack_streams(streams)
+    d_len, d_st = d.sizes_device(torch.from_numpy(in_buf.copy()).cuda(), torch.from_numpy(in_off.astype(np.int64)).cuda())
+    torch.cuda.synchronize()
+    ln, st = d_len.cpu().numpy(), d_st.cpu().numpy()
+    known = 0
+    for i, (wst, wout) in enumerate(want):
+        if int(st[i]) == 103:
+            continue
+        known += 1
+        assert int(st[i]) == wst and (wst != 0 or int(ln[i]) == len(wout)), (i, int(st[i]), wst)
+    assert known >= len(streams) // 2
+    # decoding without hints: bytes and statuses as with exact slots
+    res = d.decode_unsized(streams)
+    for i, ((gst, gout), (wst, wout)) in enumerate(zip(res, want)):
+        assert gst == wst and (wst != 0 or gout == wout), (i, gst, wst, len(gout), len(wout))
+    assert d.decode_unsized([]) == []
+    d.close()

@@ -174,3 +174,17 @@ def test_parse_piece_geometry():
             if rk == 0:
                 assert a <= dst      # a back-reference never reaches before the stream (max_allowed = min(window, pos))
     assert seen_fill and seen_split and seen_stored
+
+
+def test_parse_sizing_mode():
+    """bro_batch_sizes' mode of phase one: the decoded size (or the stream's error) without writing a byte"""
+    corpus = [c for _, c, _ in corpus_files()]
+    known = 0
+    for m in list(fuzzgen.mutations(corpus, seed=12, count=1500)) + corpus:
+        st, out = oracle.decode(m)
+        st1, size = hostsim.parse_size(m)
+        if st1 in hostsim.RETRY:
+            continue
+        known += 1
+        assert st1 == st and (st != 0 or size == len(out)), (st, st1, size, len(out), m[:12].hex())
+    assert known >= 600
