@@ -10,8 +10,10 @@
 //
 // What phase one produces:
 //   * literals and static-dictionary words (with their transforms) are written straight into the output slot,
-//   * every LZ77 back-reference and every stored meta-block becomes one BroRec {dst, len, distance | source offset};
-//     phase two (bro_kernels_copy.cu) executes the records of a stream in order, one warp per stream.
+//   * every LZ77 back-reference and every stored meta-block becomes BroRec records {dst, len, distance | source offset},
+//     one per piece of at most 32 aligned 16-byte vectors (bro_rec_push); phase two (bro_kernels_copy.cu) executes the
+//     records of a stream in order, one warp per stream;
+//   * in sizing mode (bro_batch_sizes) nothing at all: only the decoded size of every stream.
 // Copies are never materialised here, so a meta-block whose literal context map really depends on the two previous
 // bytes (libbrotli quality >= 10) cannot be decoded by this path: the stream is handed to the fused warp kernel's
 // retry pass with BRO_ST_NeedFused (as are streams that outgrow the thread arena or their share of the record arena).
@@ -36,10 +38,11 @@
 // What bounds this kernel is not instruction issue but the number of L2 / HBM round trips on a lane's critical path:
 // one per look-up in a table of the arena, one per access to a spilled variable (the threads' stacks do not fit L1).
 // So everything a round touches is kept close: the state below in registers (the canonical limits and bases of the
-// literal code included); the 8-bit root of the current literal table, 6-bit roots of the current insert&copy and
-// distance tables (their alphabets are skewed: the codes that matter are short; longer ones take the search in the HBM
-// table) and the insert/copy length table in shared memory; the symbols of the literal code in canonical order, needed
-// only for codes longer than 8 bits, in a compact HBM array.
+// literal code included); 6-bit roots of the current insert&copy and distance tables (their alphabets are skewed: the
+// codes that matter are short; a miss is settled by the table's own 8-bit root in HBM, one round trip, and only then by
+// the canonical search, four) and the insert/copy length table in shared memory; the literal table -- the one table
+// too big to keep on chip for 384 streams per SM -- as 8-bit root plus symbols in canonical order in a compact HBM
+// array: one round trip per literal, two for a code longer than 8 bits.
 #define BRO_RB_LIT 8u
 #ifndef BRO_RB_CMD
 #define BRO_RB_CMD 6u
