@@ -1,5 +1,3 @@
 #!/bin/bash
 mkdir -p gpurun_out
-timeout 300 python tools/fuzz_gpu.py --count 3000 --seed 5 > gpurun_out/fuzz_gpu.log 2>&1; tail -4 gpurun_out/fuzz_gpu.log
-timeout 700 compute-sanitizer --tool memcheck --print-limit 20 python tools/fuzz_gpu.py --count 600 --seed 9 > gpurun_out/fuzz_memcheck.log 2>&1
-grep "ERROR SUMMARY\|fuzz_gpu:\|Invalid" gpurun_out/fuzz_memcheck.log | head -8
+BRO_BENCH_MODE=twophase BRO_WORKLOADS=c4_highratio_w16,c5_stored_10k timeout 1200 python tools/quick_perf.py lib_c6.so lib_c2.so 2>&1 | tee -a gpurun_out/quick_variants.log
