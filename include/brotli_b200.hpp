@@ -102,4 +102,32 @@ private:
     bro_reader* h_;
 };
 
+// Many streams at once (no counterpart in the reference, which has one stream per Decompressor): the batch entry
+// point a host program would use, without size hints (bro_batch_decode_unsized_host).  Element i = {status, bytes};
+// status is the DecompressorError number of src/lib.rs:294-319 (0 = valid stream).
+struct BatchItem {
+    int status;
+    std::vector<uint8_t> bytes;
+};
+
+inline std::vector<BatchItem> decode_batch(bro_ctx* ctx, const std::vector<std::vector<uint8_t>>& streams) {
+    const uint32_t n = static_cast<uint32_t>(streams.size());
+    std::vector<uint64_t> in_off(n + 1, 0), out_off(n + 1, 0), out_len(n, 0);
+    std::vector<int32_t> status(n, 0);
+    for (uint32_t i = 0; i < n; i++) in_off[i + 1] = in_off[i] + streams[i].size();
+    std::vector<uint8_t> in(in_off[n] ? in_off[n] : 1);
+    for (uint32_t i = 0; i < n; i++)
+        for (size_t k = 0; k < streams[i].size(); k++) in[in_off[i] + k] = streams[i][k];
+    uint8_t* out = nullptr;
+    const int st = bro_batch_decode_unsized_host(ctx, in.data(), in_off.data(), n, &out, out_off.data(), out_len.data(), status.data());
+    if (st != BRO_OK) throw Error(st);
+    std::vector<BatchItem> res(n);
+    for (uint32_t i = 0; i < n; i++) {
+        res[i].status = status[i];
+        if (out_len[i]) res[i].bytes.assign(out + out_off[i], out + out_off[i] + out_len[i]);
+    }
+    bro_free(out);
+    return res;
+}
+
 }  // namespace brotli

@@ -13,7 +13,21 @@ SRC = r'''
 #include <fstream>
 #include <vector>
 #include "brotli_b200.hpp"
+static std::vector<uint8_t> slurp(const char* path) {
+    std::ifstream g(path, std::ios::binary);
+    return std::vector<uint8_t>((std::istreambuf_iterator<char>(g)), std::istreambuf_iterator<char>());
+}
 int main(int argc, char** argv) {
+    if (argc > 3 && !std::strcmp(argv[1], "batch")) {
+        // batch mode: argv[2..] = compressed files; prints "status size" per stream (no size hints given)
+        bro_ctx* ctx = nullptr;
+        if (bro_ctx_create(&ctx, -1) != BRO_OK) return 4;
+        std::vector<std::vector<uint8_t>> streams;
+        for (int i = 2; i < argc; i++) streams.push_back(slurp(argv[i]));
+        for (const auto& it : brotli::decode_batch(ctx, streams)) std::printf("%d %zu\n", it.status, it.bytes.size());
+        bro_ctx_destroy(ctx);
+        return 0;
+    }
     std::ifstream f(argv[1], std::ios::binary);
     brotli::Decompressor<brotli::IstreamReader> d{brotli::IstreamReader(f)};
     std::vector<uint8_t> out;
@@ -52,3 +66,9 @@ def test_cpp_twin_doctest_and_error(tmp_path):
     assert r.returncode == 0 and r.stdout.startswith("EQUAL 152089"), r.stdout + r.stderr
     r = subprocess.run([exe, os.path.join(DATA, "frewsxcv_06.compressed"), os.path.join(DATA, "64x")], capture_output=True, text=True)
     assert r.returncode == 3 and "ERR 23 Run length excceeded" in r.stdout, r.stdout + r.stderr
+    # brotli::decode_batch: several streams, no size hints
+    names = ["64x", "alice29.txt", "quickfox_repeated", "random_org_10k.bin", "empty"]
+    r = subprocess.run([exe, "batch"] + [os.path.join(DATA, n + ".compressed") for n in names] + [os.path.join(DATA, "frewsxcv_06.compressed")],
+                       capture_output=True, text=True)
+    want = ["0 %d" % os.path.getsize(os.path.join(DATA, n)) for n in names] + ["23 0"]
+    assert r.returncode == 0 and r.stdout.split("\n")[:6] == want, r.stdout + r.stderr
