@@ -1,0 +1,106 @@
+// bro_copy_piece.h -- the lane-local half of the copy kernel's LONG-record path (bro_kernels_copy.cu): what ONE lane
+// loads and stores for the piece its lane group works on.  No warp intrinsics in here, so the very same code is run
+// lane by lane on the host by the CPU test-suite (bro_hostsim_copy.cpp; never part of the product library).
+//
+// A piece is a copy record of at most 32 destination-aligned 16-byte vectors with fewer than 16 ragged bytes in front
+// (head) and behind (tail); phase one cuts every LZ77 back-reference (src/lib.rs:1483-1505) and every stored
+// meta-block (src/lib.rs:1701-1734) into such pieces.  G lanes (32, 16 or 8: a warp, half or quarter of one) move one
+// piece: lane bl of the group takes the vectors bl, bl + G, ... and the ragged byte slots bl, bl + G, ... (slots 0..15 are
+// the head bytes, 16..31 the tail bytes).  Loading and storing are separate calls so that the caller can issue the
+// loads of several pieces before the first store.
+#pragma once
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define BRO_PIECE_FN __device__ __forceinline__
+typedef uint4 bro_v16;
+BRO_PIECE_FN uint32_t bro_piece_funnel(uint32_t lo, uint32_t hi, unsigned s) { return __funnelshift_r(lo, hi, s); }
+#else
+#define BRO_PIECE_FN static inline
+struct alignas(16) bro_v16 { uint32_t x, y, z, w; };
+BRO_PIECE_FN uint32_t bro_piece_funnel(uint32_t lo, uint32_t hi, unsigned s) {
+    return s ? (lo >> s) | (hi << (32u - s)) : lo;
+}
+#endif
+
+// Geometry word of a piece (computed once per record by the lane that holds the record, broadcast per piece):
+// head | vectors << 8 | tail << 16 | (source address of the first vector & 15) << 24 | 1 << 31.
+// dst_addr_lo / src_addr_lo: low bits of the addresses of the record's first destination / source byte.
+BRO_PIECE_FN uint32_t bro_piece_geo(uint32_t dst_addr_lo, uint32_t src_addr_lo, uint32_t len) {
+    uint32_t head = (16u - (dst_addr_lo & 15u)) & 15u;
+    if (head > len) head = len;
+    const uint32_t nvec = (len - head) >> 4, tail = (len - head) & 15u;
+    return head | (nvec << 8) | (tail << 16) | (((src_addr_lo + head) & 15u) << 24) | 0x80000000u;
+}
+#define BRO_GEO_HEAD(g) ((g) & 0xffu)
+#define BRO_GEO_NVEC(g) (((g) >> 8) & 0xffu)
+#define BRO_GEO_TAIL(g) (((g) >> 16) & 0xffu)
+#define BRO_GEO_SHIFT(g) (((g) >> 24) & 15u)
+
+// 16 bytes that start 4 * WS + bs / 8 bytes into the 32 bytes A | B (WS = 0..3 whole words, bs = 0, 8, 16 or 24 bits)
+template <int WS>
+BRO_PIECE_FN bro_v16 bro_funnel16(const bro_v16& A, const bro_v16& B, unsigned bs) {
+    const uint32_t w[8] = {A.x, A.y, A.z, A.w, B.x, B.y, B.z, B.w};
+    bro_v16 r;
+    r.x = bro_piece_funnel(w[WS], w[WS + 1], bs); r.y = bro_piece_funnel(w[WS + 1], w[WS + 2], bs);
+    r.z = bro_piece_funnel(w[WS + 2], w[WS + 3], bs); r.w = bro_piece_funnel(w[WS + 3], w[WS + 4], bs);
+    return r;
+}
+
+// What a lane holds of one piece between load and store
+template <int G>
+struct BroPieceData {
+    bro_v16 A[32 / G], B[32 / G];      // the two aligned 16-byte granules that hold vector bl + G * i of the source
+    uint32_t rb[32 / G];               // ragged byte slot bl + G * i
+};
+
+// s0: address of the piece's first source byte; g: its geometry word (0 = this lane group has no piece: nothing is
+// touched); bl: lane index inside the group.
+template <int G>
+BRO_PIECE_FN void bro_piece_load(BroPieceData<G>& d, const uint8_t* s0, uint32_t g, uint32_t bl) {
+    const uint32_t head = BRO_GEO_HEAD(g), nvec = BRO_GEO_NVEC(g), tail = BRO_GEO_TAIL(g);
+#pragma unroll
+    for (int i = 0; i < 32 / G; i++) {
+        const uint32_t slot = bl + (uint32_t)(G * i);
+        const bool back = slot >= 16u;                                   // compile-time for G <= 16
+        const uint32_t b = slot & 15u;
+        if (b < (back ? tail : head)) d.rb[i] = s0[(back ? head + 16u * nvec : 0u) + b];
+    }
+    // the aligned granule that holds the first source byte of this lane's first vector; the others follow at G * 16 bytes
+    const bro_v16* q = (const bro_v16*)(((uintptr_t)s0 + head) & ~(uintptr_t)15) + bl;
+#pragma unroll
+    for (int i = 0; i < 32 / G; i++) {
+        if (bl + (uint32_t)(G * i) < nvec) {
+            d.A[i] = q[G * i];
+            if (g & 0x0f000000u) d.B[i] = q[G * i + 1];   // never read past the granule of the piece's last source byte
+        }
+    }
+}
+
+// dp: address of the piece's first destination byte
+template <int G>
+BRO_PIECE_FN void bro_piece_store(const BroPieceData<G>& d, uint8_t* dp, uint32_t g, uint32_t bl) {
+    const uint32_t head = BRO_GEO_HEAD(g), nvec = BRO_GEO_NVEC(g), tail = BRO_GEO_TAIL(g), sh = BRO_GEO_SHIFT(g);
+#pragma unroll
+    for (int i = 0; i < 32 / G; i++) {
+        const uint32_t slot = bl + (uint32_t)(G * i);
+        const bool back = slot >= 16u;
+        const uint32_t b = slot & 15u;
+        if (b < (back ? tail : head)) dp[(back ? head + 16u * nvec : 0u) + b] = (uint8_t)d.rb[i];
+    }
+    // The source shift is the same for every vector of the piece (all lanes of the group): branch once on its whole
+    // words, so that each case is four funnel shifts straight from the right registers.
+    bro_v16* const dv = (bro_v16*)(dp + head) + bl;
+    const unsigned bs = 8u * (sh & 3u);
+#define BRO_PIECE_VECTORS(EXPR)                                             \
+    _Pragma("unroll") for (int i = 0; i < 32 / G; i++)                      \
+        if (bl + (uint32_t)(G * i) < nvec) dv[G * i] = (EXPR);
+    if (sh == 0u) { BRO_PIECE_VECTORS(d.A[i]) }
+    else switch (sh >> 2) {
+        case 0: BRO_PIECE_VECTORS(bro_funnel16<0>(d.A[i], d.B[i], bs)) break;
+        case 1: BRO_PIECE_VECTORS(bro_funnel16<1>(d.A[i], d.B[i], bs)) break;
+        case 2: BRO_PIECE_VECTORS(bro_funnel16<2>(d.A[i], d.B[i], bs)) break;
+        default: BRO_PIECE_VECTORS(bro_funnel16<3>(d.A[i], d.B[i], bs)) break;
+    }
+#undef BRO_PIECE_VECTORS
+}

@@ -1,0 +1,110 @@
+// Host simulation of PHASE TWO of the two-phase path -- CPU TEST-SUITE ONLY (tests/_build/libbro_hostsim.so, built by
+// tests/hostsim.py; never part of libbrotli_b200.so).
+//
+// It executes a stream's copy records the way bro_copy_kernel (bro_kernels_copy.cu) does: 32 records at a time, split
+// into groups of records none of which reads what a record of the group writes; a group of long records goes piece by
+// piece through the VERY lane code of the kernel (bro_copy_piece.h: bro_piece_geo / bro_piece_load / bro_piece_store,
+// run here lane by lane for G = 32, 16 or 8 lanes per piece, all loads of a step before its first store); a group of
+// short records and a periodic fill are restated as byte loops (their kernel code is warp-wide).  What the CPU
+// test-suite gets from this: the piece geometry and realignment of the kernel, and the claim that the records of a group
+// may be executed in any order, checked against the oracle without a GPU.
+#include <stdint.h>
+#include <string.h>
+
+#include "bro_copy_piece.h"
+#include "bro_records.h"
+
+#ifndef BRO_COPY_PIECES
+#define BRO_COPY_PIECES 4      // as in bro_kernels_copy.cu
+#endif
+
+namespace {
+
+struct Rec { uint32_t dst, len, kind, a; };
+
+template <int G>
+void run_pieces(uint8_t* out, const uint8_t* in, const Rec* r, const uint32_t* geo, const uint8_t* const* sp, uint32_t j, uint32_t e) {
+    constexpr int PP = 32 / G, ROUNDS = (BRO_COPY_PIECES + PP - 1) / PP;
+    (void)in;
+    for (uint32_t k0 = j; k0 < e; k0 += (uint32_t)(PP * ROUNDS)) {
+        static BroPieceData<G> D[ROUNDS][32];      // [round][lane]
+        uint32_t m_geo[ROUNDS][32], m_dst[ROUNDS][32];
+        for (int rd = 0; rd < ROUNDS; rd++)
+            for (uint32_t lane = 0; lane < 32u; lane++) {
+                m_geo[rd][lane] = 0;
+                if (k0 + (uint32_t)(PP * rd) >= e) continue;
+                const uint32_t bl = lane & (uint32_t)(G - 1), sub = lane / (uint32_t)G;
+                const uint32_t k = k0 + (uint32_t)(PP * rd) + sub;
+                const uint32_t ks = k & 31u;
+                uint32_t g = geo[ks];
+                if (PP > 1 && k >= e) g = 0;
+                m_geo[rd][lane] = g;
+                m_dst[rd][lane] = r[ks].dst;
+                bro_piece_load<G>(D[rd][lane], sp[ks], g, bl);
+            }
+        for (int rd = 0; rd < ROUNDS; rd++)
+            for (uint32_t lane = 0; lane < 32u; lane++) {
+                if (k0 + (uint32_t)(PP * rd) >= e) continue;
+                bro_piece_store<G>(D[rd][lane], out + m_dst[rd][lane], m_geo[rd][lane], lane & (uint32_t)(G - 1));
+            }
+    }
+}
+
+}  // namespace
+
+// words: the records as phase one wrote them (4 x uint32 each).  group = lanes per piece (32, 16, 8).
+// stats (optional, 3 words): groups executed by the piece path / as short records / periodic fills.
+extern "C" void bro_hostsim_copy_exec(uint8_t* out, const uint8_t* in, const uint32_t* words, uint32_t nrec, int group, uint32_t* stats) {
+    const uint32_t out_mis = (uint32_t)((uintptr_t)out & 15u);
+    uint32_t st[3] = {0, 0, 0};
+    for (uint32_t b = 0; b < nrec; b += 32u) {
+        const uint32_t cnt = nrec - b < 32u ? nrec - b : 32u;
+        Rec r[32];
+        uint32_t geo[32];
+        const uint8_t* sp[32];
+        memset(r, 0, sizeof(r));
+        for (uint32_t l = 0; l < cnt; l++) {
+            const uint32_t* w = words + 4u * (b + l);
+            r[l].dst = w[0]; r[l].len = w[1] & BRO_REC_LEN_MASK; r[l].kind = w[1] >> BRO_REC_KIND_SHIFT; r[l].a = w[2];
+        }
+        uint32_t j = 0;
+        while (j < cnt) {
+            uint32_t e = j;
+            while (e < cnt && (r[e].kind == BRO_REC_STORED || (r[e].dst - r[e].a) + r[e].len <= r[j].dst)) e++;
+            if (e == j) {      // a record that overlaps its own source: the kernel fills by doubling; byte order is the definition
+                for (uint32_t i = 0; i < r[j].len; i++) out[r[j].dst + i] = out[r[j].dst + i - r[j].a];
+                st[2]++;
+                j++;
+                continue;
+            }
+            uint32_t gsum = 0;
+            bool too_long = false;
+            for (uint32_t l = j; l < e; l++) {
+                gsum += r[l].len;
+                uint32_t head = (16u - ((r[l].dst + out_mis) & 15u)) & 15u;
+                if (head > r[l].len) head = r[l].len;
+                too_long |= ((r[l].len - head) >> 4) > BRO_REC_PIECE_VECS;
+            }
+            if (gsum >= 192u * (e - j) && !too_long) {
+                for (uint32_t l = 0; l < 32u; l++) {
+                    sp[l] = r[l].kind == BRO_REC_STORED ? in + r[l].a : (const uint8_t*)out + (r[l].dst - r[l].a);
+                    geo[l] = bro_piece_geo(r[l].dst + out_mis, (uint32_t)(uintptr_t)sp[l], r[l].len);
+                }
+                if (group == 8) run_pieces<8>(out, in, r, geo, sp, j, e);
+                else if (group == 16) run_pieces<16>(out, in, r, geo, sp, j, e);
+                else run_pieces<32>(out, in, r, geo, sp, j, e);
+                st[0]++;
+            } else {
+                // short records: the kernel's segmented copy moves the units of all records of the group in one sweep;
+                // executing the records LAST TO FIRST checks that their order does not matter
+                for (uint32_t l = e; l-- > j;) {
+                    const uint8_t* s = r[l].kind == BRO_REC_STORED ? in + r[l].a : out + (r[l].dst - r[l].a);
+                    memmove(out + r[l].dst, s, r[l].len);
+                }
+                st[1]++;
+            }
+            j = e;
+        }
+    }
+    if (stats) { stats[0] = st[0]; stats[1] = st[1]; stats[2] = st[2]; }
+}

@@ -16,6 +16,14 @@ extern "C" const uint8_t bro_dictionary_blob[];
 static uint32_t g_sizing = 0;         // next decodes only measure (bro_batch_sizes' mode): no output, unbounded slot
 extern "C" void bro_hostsim_parse_set_sizing(unsigned on) { g_sizing = on; }
 
+// phase two of the next decodes: 0 = the obvious byte loop over the records; 32, 16, 8 = the copy kernel's grouping and
+// piece code with that many lanes per piece (bro_hostsim_copy.cpp)
+static int g_copy_group = 0;
+static uint32_t g_copy_stats[3];
+extern "C" void bro_hostsim_parse_set_copy_group(int group) { g_copy_group = group; }
+extern "C" void bro_hostsim_parse_copy_stats(uint32_t* stats3) { memcpy(stats3, g_copy_stats, sizeof(g_copy_stats)); }
+extern "C" void bro_hostsim_copy_exec(uint8_t* out, const uint8_t* in, const uint32_t* words, uint32_t nrec, int group, uint32_t* stats);
+
 static uint32_t* g_rec_out = 0;       // when set: the records of the next decode are copied here (4 words each)
 static unsigned g_rec_out_cap = 0;
 
@@ -60,7 +68,10 @@ extern "C" int bro_hostsim_parse_decode(const uint8_t* in, size_t in_len, uint8_
         else { bro_parse_round(d, ps, mb); steps++; }
     }
     // phase two, the obvious way
-    if (ps.st == BRO_ST_OK && !g_sizing) {
+    if (ps.st == BRO_ST_OK && !g_sizing && g_copy_group) {
+        static_assert(sizeof(BroRec) == 16, "a record is four words");
+        bro_hostsim_copy_exec(out, in, (const uint32_t*)rec, d.nrec, g_copy_group, g_copy_stats);
+    } else if (ps.st == BRO_ST_OK && !g_sizing) {
         for (uint32_t k = 0; k < d.nrec; k++) {
             const BroRec r = rec[k];
             const uint32_t len = r.len_kind & BRO_REC_LEN_MASK, kind = r.len_kind >> BRO_REC_KIND_SHIFT;

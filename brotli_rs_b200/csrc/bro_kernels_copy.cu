@@ -22,6 +22,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include "bro_copy_piece.h"
 #include "bro_decoder_core.h"
 #include "bro_kernels.h"
 
@@ -33,6 +34,9 @@
 #endif
 #ifndef BRO_COPY_PIECES
 #define BRO_COPY_PIECES 4     // long records: pieces in flight per warp (their data is held in registers)
+#endif
+#ifndef BRO_COPY_GROUP
+#define BRO_COPY_GROUP 32     // long records: lanes that move one piece (32, 16 or 8): 32 / GROUP pieces per warp step
 #endif
 #ifndef BRO_COPY_DEPTH
 #define BRO_COPY_DEPTH 4      // rounds of 32 units in flight per warp; 1 KiB of staging per round and warp
@@ -170,51 +174,31 @@ __global__ void __launch_bounds__(WARPS * 32, BRO_COPY_MIN_BLOCKS) bro_copy_kern
                     // per record (lane-local, broadcast per piece): source address and geometry
                     const uint8_t* sp = kind == BRO_REC_STORED ? in + a : (const uint8_t*)out + (dst - a);
                     const uint32_t sp_lo = (uint32_t)(uintptr_t)sp, sp_hi = (uint32_t)((uintptr_t)sp >> 32);
-                    const uint32_t geo = head | (nvec << 8) | (tail << 16) | (((sp_lo + head) & 15u) << 24) | 0x80000000u;
-                    const uint32_t bl = lane & 15u;
-                    const bool back = lane >= 16u;
-                    for (uint32_t k0 = j; k0 < e; k0 += BRO_COPY_PIECES) {
-                        uint4 A[BRO_COPY_PIECES], B[BRO_COPY_PIECES];
-                        uint32_t bv[BRO_COPY_PIECES], m_dst[BRO_COPY_PIECES], m_geo[BRO_COPY_PIECES];
+                    const uint32_t geo = bro_piece_geo(dst + out_mis, sp_lo, len);
+                    // BRO_COPY_GROUP lanes per piece: the warp moves PP pieces per step, ROUNDS steps in flight
+                    constexpr int G = BRO_COPY_GROUP, PP = 32 / G, ROUNDS = (BRO_COPY_PIECES + PP - 1) / PP;
+                    const uint32_t bl = lane & (uint32_t)(G - 1), sub = lane / (uint32_t)G;
+                    for (uint32_t k0 = j; k0 < e; k0 += (uint32_t)(PP * ROUNDS)) {
+                        BroPieceData<G> D[ROUNDS];
+                        uint32_t m_dst[ROUNDS], m_geo[ROUNDS];
 #pragma unroll
-                        for (int r = 0; r < BRO_COPY_PIECES; r++) {
+                        for (int r = 0; r < ROUNDS; r++) {
                             m_geo[r] = 0;
-                            if (k0 + r >= e) continue;                                   // warp-uniform
-                            const int k = (int)(k0 + r);
-                            const uint32_t g = __shfl_sync(0xffffffffu, geo, k);
-                            const uintptr_t s0 = (uintptr_t)__shfl_sync(0xffffffffu, sp_lo, k) |
-                                                 ((uintptr_t)__shfl_sync(0xffffffffu, sp_hi, k) << 32);
-                            m_dst[r] = __shfl_sync(0xffffffffu, dst, k);
+                            if (k0 + (uint32_t)(PP * r) >= e) continue;                  // warp-uniform
+                            const uint32_t k = k0 + (uint32_t)(PP * r) + sub;            // this lane group's piece
+                            const int ks = (int)(k & 31u);
+                            uint32_t g = __shfl_sync(0xffffffffu, geo, ks);
+                            const uintptr_t s0 = (uintptr_t)__shfl_sync(0xffffffffu, sp_lo, ks) |
+                                                 ((uintptr_t)__shfl_sync(0xffffffffu, sp_hi, ks) << 32);
+                            m_dst[r] = __shfl_sync(0xffffffffu, dst, ks);
+                            if (PP > 1 && k >= e) g = 0;                                 // the group ends inside this step
                             m_geo[r] = g;
-                            const uint32_t r_head = g & 0xffu, r_nvec = (g >> 8) & 0xffu, r_tail = (g >> 16) & 0xffu;
-                            const uint32_t vbase = r_head + 16u * lane;
-                            // ragged bytes: lanes 0..15 in front of the vectors, lanes 16..31 behind them
-                            if (bl < (back ? r_tail : r_head)) bv[r] = *(const uint8_t*)(s0 + (back ? r_head + 16u * r_nvec : 0u) + bl);
-                            if (lane < r_nvec) {
-                                const uint4* q = (const uint4*)((s0 + vbase) & ~(uintptr_t)15);
-                                A[r] = q[0];
-                                if (g & 0x0f000000u) B[r] = q[1];
-                            }
+                            bro_piece_load<G>(D[r], (const uint8_t*)s0, g, bl);
                         }
 #pragma unroll
-                        for (int r = 0; r < BRO_COPY_PIECES; r++) {
-                            const uint32_t g = m_geo[r];
-                            if (g == 0u) continue;                                       // warp-uniform
-                            const uint32_t r_head = g & 0xffu, r_nvec = (g >> 8) & 0xffu, r_tail = (g >> 16) & 0xffu, sh = (g >> 24) & 15u;
-                            uint8_t* dp = out + m_dst[r];
-                            if (bl < (back ? r_tail : r_head)) dp[(back ? r_head + 16u * r_nvec : 0u) + bl] = (uint8_t)bv[r];
-                            if (lane < r_nvec) {
-                                uint4 v = A[r];
-                                if (sh) {
-                                    uint32_t w0 = v.x, w1 = v.y, w2 = v.z, w3 = v.w, w4 = B[r].x, w5 = B[r].y, w6 = B[r].z, w7 = B[r].w;
-                                    if (sh & 8u) { w0 = w2; w1 = w3; w2 = w4; w3 = w5; w4 = w6; w5 = w7; }
-                                    if (sh & 4u) { w0 = w1; w1 = w2; w2 = w3; w3 = w4; w4 = w5; }
-                                    const unsigned bs = 8u * (sh & 3u);
-                                    v.x = __funnelshift_r(w0, w1, bs); v.y = __funnelshift_r(w1, w2, bs);
-                                    v.z = __funnelshift_r(w2, w3, bs); v.w = __funnelshift_r(w3, w4, bs);
-                                }
-                                *(uint4*)(dp + r_head + 16u * lane) = v;
-                            }
+                        for (int r = 0; r < ROUNDS; r++) {
+                            if (k0 + (uint32_t)(PP * r) >= e) continue;                  // warp-uniform
+                            bro_piece_store<G>(D[r], out + m_dst[r], m_geo[r], bl);
                         }
                     }
                     j = e;

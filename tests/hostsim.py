@@ -17,9 +17,9 @@ _LIBS = {}
 def _build(asan):
     os.makedirs(BUILD, exist_ok=True)
     so = os.path.join(BUILD, "libbro_hostsim_asan.so" if asan else "libbro_hostsim.so")
-    srcs = [os.path.join(CSRC, "bro_hostsim.cpp"), os.path.join(CSRC, "bro_hostsim_parse.cpp"),
+    srcs = [os.path.join(CSRC, "bro_hostsim.cpp"), os.path.join(CSRC, "bro_hostsim_parse.cpp"), os.path.join(CSRC, "bro_hostsim_copy.cpp"),
             os.path.join(ROOT, "oracle", "dict_blob.c")]
-    deps = srcs + [os.path.join(CSRC, f) for f in ("bro_decoder_core.h", "bro_parse.h", "bro_records.h", "bro_status.h", "bro_tables_generated.h")]
+    deps = srcs + [os.path.join(CSRC, f) for f in ("bro_decoder_core.h", "bro_parse.h", "bro_records.h", "bro_copy_piece.h", "bro_status.h", "bro_tables_generated.h")]
     if os.path.exists(so) and all(os.path.getmtime(so) >= os.path.getmtime(d) for d in deps):
         return so
     flags = ["-O1", "-g", "-fsanitize=address,undefined", "-fno-sanitize-recover=undefined"] if asan else ["-O2"]
@@ -36,7 +36,7 @@ def lib(asan=False):
         L.bro_hostsim_decode.argtypes = [ctypes.c_char_p, ctypes.c_size_t, ctypes.c_char_p, ctypes.c_size_t,
                                          ctypes.POINTER(ctypes.c_size_t), ctypes.c_int, ctypes.c_uint]
         L.bro_hostsim_parse_decode.restype = ctypes.c_int
-        L.bro_hostsim_parse_decode.argtypes = [ctypes.c_char_p, ctypes.c_size_t, ctypes.c_char_p, ctypes.c_size_t,
+        L.bro_hostsim_parse_decode.argtypes = [ctypes.c_char_p, ctypes.c_size_t, ctypes.c_void_p, ctypes.c_size_t,
                                                ctypes.POINTER(ctypes.c_size_t), ctypes.c_int, ctypes.c_uint, ctypes.c_uint,
                                                ctypes.POINTER(ctypes.c_uint), ctypes.POINTER(ctypes.c_uint)]
         _LIBS[asan] = L
@@ -61,16 +61,40 @@ def thread_arena_u16():
     return lib().bro_hostsim_thread_arena_u16()
 
 
-def parse_decode(data: bytes, cap: int = 1 << 20, quirks: int = 0, arena_u16: int = 0, rec_cap: int = 0, asan=False):
+def parse_decode(data: bytes, cap: int = 1 << 20, quirks: int = 0, arena_u16: int = 0, rec_cap: int = 0, asan=False, mis=None):
     """The two-phase path: phase one = the parse kernel's per-lane code (flat state machine), phase two = a byte loop
     over its copy records.  -> (status, bytes, records, machine trips); status may be one of RETRY, which the product
-    answers by re-running the stream with the fused warp kernel."""
-    out = ctypes.create_string_buffer(max(cap, 1))
+    answers by re-running the stream with the fused warp kernel.  mis = 0..15: the output slot starts at an address with
+    (address & 15) == mis (the pieces of the copy records are cut for the slot's alignment)."""
+    buf = ctypes.create_string_buffer(max(cap, 1) + 48)
+    base = ctypes.addressof(buf)
+    off = ((-base) % 16 + 16 + mis) if mis is not None else 0
     n = ctypes.c_size_t()
     nrec, steps = ctypes.c_uint(), ctypes.c_uint()
-    st = lib(asan).bro_hostsim_parse_decode(data, len(data), out, cap, ctypes.byref(n), quirks, arena_u16, rec_cap,
+    st = lib(asan).bro_hostsim_parse_decode(data, len(data), base + off, cap, ctypes.byref(n), quirks, arena_u16, rec_cap,
                                             ctypes.byref(nrec), ctypes.byref(steps))
-    return st, out.raw[: n.value], nrec.value, steps.value
+    return st, buf.raw[off: off + n.value], nrec.value, steps.value
+
+
+class copy_group:
+    """with copy_group(G): parse_decode executes the records as the copy kernel does -- grouping, and for long records the
+    kernel's own lane code with G (32, 16, 8) lanes per piece -- instead of the byte loop.  .stats() -> groups executed
+    by the piece path, as short records, periodic fills (accumulated over the last decode)."""
+
+    def __init__(self, group, asan=False):
+        self.group, self.L = group, lib(asan)
+
+    def __enter__(self):
+        self.L.bro_hostsim_parse_set_copy_group(self.group)
+        return self
+
+    def __exit__(self, *exc):
+        self.L.bro_hostsim_parse_set_copy_group(0)
+
+    def stats(self):
+        st = (ctypes.c_uint * 3)()
+        self.L.bro_hostsim_parse_copy_stats(st)
+        return tuple(st)
 
 
 def parse_records(data: bytes, cap: int = 1 << 20):
@@ -98,7 +122,7 @@ def parse_size(data: bytes, quirks: int = 0):
         out = ctypes.create_string_buffer(1)
         n = ctypes.c_size_t()
         nrec, steps = ctypes.c_uint(), ctypes.c_uint()
-        st = L.bro_hostsim_parse_decode(data, len(data), out, 0, ctypes.byref(n), quirks, 0, 0, ctypes.byref(nrec), ctypes.byref(steps))
+        st = L.bro_hostsim_parse_decode(data, len(data), ctypes.addressof(out), 0, ctypes.byref(n), quirks, 0, 0, ctypes.byref(nrec), ctypes.byref(steps))
         return st, n.value
     finally:
         L.bro_hostsim_parse_set_sizing(0)

@@ -72,3 +72,43 @@ def test_cpp_twin_doctest_and_error(tmp_path):
                        capture_output=True, text=True)
     want = ["0 %d" % os.path.getsize(os.path.join(DATA, n)) for n in names] + ["23 0"]
     assert r.returncode == 0 and r.stdout.split("\n")[:6] == want, r.stdout + r.stderr
+
+
+# ---- tools/corpus_driver.cpp: the reference's command-line driver (src/main.rs:49-70) ----
+
+def _build_driver(tmp):
+    from brotli_rs_b200 import _lib, build
+    if not os.path.exists(_lib.library_path()):
+        build.build()
+    exe = os.path.join(tmp, "corpus_driver")
+    libdir = os.path.dirname(_lib.library_path())
+    subprocess.check_call(["g++", "-std=c++17", "-O1", "-I", os.path.join(ROOT, "include"), os.path.join(ROOT, "tools", "corpus_driver.cpp"),
+                           "-o", exe, "-L" + libdir, "-lbrotli_b200", "-Wl,-rpath," + libdir])
+    return exe
+
+
+def test_corpus_driver_compiles_and_fails_loudly_without_gpu(tmp_path):
+    import torch
+    exe = _build_driver(str(tmp_path))
+    if not torch.cuda.is_available():
+        r = subprocess.run([exe, DATA], capture_output=True, text=True)
+        assert r.returncode == 3 and "no CPU decode path" in r.stderr and r.stdout == ""
+
+
+@pytest.mark.gpu
+def test_corpus_driver_matches_oracle(tmp_path):
+    """every *compressed file of the corpus, per file (the reference's call shape) and as one batch: the three lines the
+    reference prints per file, with the oracle's length and error text"""
+    from brotli_rs_b200 import _lib
+    from oracle import oracle
+    exe = _build_driver(str(tmp_path))
+    names = sorted(fn for fn in os.listdir(DATA) if fn.endswith("compressed"))
+    want = ""
+    for fn in names:
+        st, out = oracle.decode(open(os.path.join(DATA, fn), "rb").read())
+        res = "Ok(%d)" % len(out) if st == 0 else 'Err(Custom { kind: InvalidData, error: "%s" })' % _lib.status_description(st)
+        want += '"%s":\noutput length = %d\nres = %s\n===========\n\n' % (os.path.join(DATA, fn), len(out) if st == 0 else 0, res)
+    assert len(names) >= 30
+    for args in ([], ["--batch"]):
+        r = subprocess.run([exe] + args + [DATA], capture_output=True, text=True)
+        assert r.returncode == 0 and r.stdout == want, (args, r.stdout[:600], r.stderr[-300:])

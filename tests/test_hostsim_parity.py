@@ -67,8 +67,8 @@ def test_quirk_vectors():
 
 # ---- the two-phase path: phase one's flat state machine (bro_parse.h) + a byte loop over its copy records ----
 
-def _parse_check(stream, cap, want_st, want_out, label):
-    st1, out1, nrec, steps = hostsim.parse_decode(stream, cap=cap)
+def _parse_check(stream, cap, want_st, want_out, label, mis=None):
+    st1, out1, nrec, steps = hostsim.parse_decode(stream, cap=cap, mis=mis)
     if st1 in hostsim.RETRY:
         return False           # the product re-runs such a stream with the fused warp kernel
     assert st1 == want_st and (want_st != 0 or out1 == want_out), (label, want_st, st1, nrec, steps)
@@ -188,3 +188,34 @@ def test_parse_sizing_mode():
         known += 1
         assert st1 == st and (st != 0 or size == len(out)), (st, st1, size, len(out), m[:12].hex())
     assert known >= 600
+
+
+@pytest.mark.parametrize("group", [32, 16, 8])
+def test_copy_phase_lane_code(group):
+    """phase two as the copy kernel executes it: 32 records at a time, groups of independent records, long records piece
+    by piece through the kernel's own lane code (bro_copy_piece.h) with `group` lanes per piece, all loads of a step
+    before its first store; short groups last record first.  Bytes must equal the oracle's."""
+    enc = fuzzgen.libbrotli_enc()
+    if enc is None:
+        pytest.skip("system libbrotlienc not present")
+    pieces = shorts = fills = handled = 0
+    with hostsim.copy_group(group) as cg:
+        for name, comp, _ in corpus_files():
+            st, out = oracle.decode(comp)
+            if st == 0:
+                handled += _parse_check(comp, len(out), st, out, name, mis=len(comp) % 16)
+                p, s, f = cg.stats()
+                pieces, shorts, fills = pieces + p, shorts + s, fills + f
+        k = 0
+        for kind, q, lgwin, size in (("repeat2k", 5, 16, 262144), ("repeat2k", 1, 18, 150001), ("runs", 5, 16, 90000),
+                                     ("random", 5, 16, 10000), ("random", 5, 16, 70001), ("words", 5, 18, 50000),
+                                     ("small_alpha", 9, 22, 30000), ("skewed", 1, 16, 40000), ("repeat2k", 9, 22, 400000)):
+            for seed in range(3):
+                raw = fuzzgen.synthetic_raw(kind, 700 + k, size + 13 * seed)
+                k += 1
+                comp = fuzzgen.compress(enc, raw, q, lgwin)
+                # destination alignments 0..15: the slot starts at an address with (address & 15) == mis
+                handled += _parse_check(comp, len(raw), 0, raw, (kind, q, lgwin, seed), mis=(5 * k + 3) % 16)
+                p, s, f = cg.stats()
+                pieces, shorts, fills = pieces + p, shorts + s, fills + f
+    assert handled >= 40 and pieces >= 100 and shorts >= 100 and fills >= 10, (handled, pieces, shorts, fills)
