@@ -313,6 +313,18 @@ BRO_FN const uint8_t* bro_bits_addr(const BroBits& s) {
 #endif
 }
 
+// bits consumed since byte address `start` (any state of the window)
+BRO_FN uint64_t bro_bits_position(const BroBits& s, const uint8_t* start) {
+#if defined(BRO_THREAD_MODE)
+    const uint8_t* w0 = s.chunk - 12;
+#elif defined(BRO_SERIAL)
+    const uint8_t* w0 = s.chunk - 8;
+#else
+    const uint8_t* w0 = s.chunk + 4u * s.wi - 8;
+#endif
+    return (uint64_t)((int64_t)(w0 - start) * 8 + (int64_t)s.bp);
+}
+
 // ------------------------------------------------------------------------------------------------------
 // prefix code tables
 // ------------------------------------------------------------------------------------------------------
@@ -1540,10 +1552,27 @@ BRO_FN int bro_stream_header(BroDec& d) {
 // Advance to the next compressed meta-block: consumes meta-block headers, skips metadata blocks and copies stored
 // blocks on the way (src/lib.rs:1572-1734), and runs the end-of-stream checks (2155-2167) when the stream ends.
 // after_last: the meta-block just decoded had ISLAST set.  Returns BRO_MB_COMPRESSED, BRO_MB_END or an error status.
-BRO_FN int bro_next_metablock(BroDec& d, bool after_last, uint32_t& is_last, uint32_t& mlen) {
+#if !defined(BRO_PARSE)
+// Resume point in front of the next meta-block header (bro_records.h)
+BRO_FN void bro_checkpoint(const BroDec& d, BroResume* ck, const uint8_t* in_start, uint32_t flags) {
+    const uint64_t bits = bro_bits_position(d.in, in_start);
+    if (bro_lane() == 0) {
+        ck->in_bits = bits; ck->pos = d.pos; ck->window = d.window;
+        ck->dist[0] = d.d0; ck->dist[1] = d.d1; ck->dist[2] = d.d2; ck->dist[3] = d.d3;
+        ck->p1 = d.p1; ck->p2 = d.p2; ck->flags = flags; ck->reserved = 0;
+    }
+}
+#endif
+
+// CK (resumable decode only): write a resume point to `ck` in front of every meta-block header.
+template <bool CK = false>
+BRO_FN int bro_next_metablock(BroDec& d, bool after_last, uint32_t& is_last, uint32_t& mlen, BroResume* ck = 0, const uint8_t* in_start = 0) {
     uint32_t b, n, v;
     bool ended = after_last;
     while (!ended) {
+#if !defined(BRO_PARSE)
+        if (CK) bro_checkpoint(d, ck, in_start, BRO_RESUME_HEADER);
+#endif
         if (!bro_read_bits(d.in, 1, is_last)) return BRO_ST_UnexpectedEOF;
         if (is_last) {
             if (!bro_read_bits(d.in, 1, b)) return BRO_ST_UnexpectedEOF;
@@ -1621,6 +1650,48 @@ BRO_FN int bro_decode_stream(BroDec& d) {
     for (;;) {
         st = bro_next_metablock(d, after_last, is_last, mlen);
         if (st == BRO_MB_END) return BRO_ST_OK;
+        if (st != BRO_MB_COMPRESSED) return st;
+        st = bro_decode_compressed_metablock(d, mlen);
+        if (st) return st;
+        after_last = is_last != 0u;
+    }
+}
+
+// The same, from and to a resume point (bro_records.h): start where `ck` says (all-zero = start of stream), write a
+// resume point in front of every meta-block header, and at the clean end of the stream.  The status of a call that ran
+// out of input (UnexpectedEOF) or room (OutputTooSmall) inside a meta-block describes the attempt, `ck` the last
+// boundary it passed.  in_start / in_end: the input of THIS call (ck->in_bits counts from in_start).
+BRO_FN int bro_decode_stream_resume(BroDec& d, BroResume* ck, const uint8_t* in_start, const uint8_t* in_end) {
+    const BroResume r = *ck;
+    bro_syncwarp();                                     // every lane has read the resume point before lane 0 rewrites it
+    d.pos = r.pos; d.p1 = r.p1; d.p2 = r.p2;
+    bro_bits_init(d.in, in_start, in_end);
+    int st;
+    if (r.flags & BRO_RESUME_HEADER) {
+        d.window = r.window;
+        d.d0 = r.dist[0]; d.d1 = r.dist[1]; d.d2 = r.dist[2]; d.d3 = r.dist[3];
+        const uint64_t byte = r.in_bits >> 3;
+        if (byte > (uint64_t)(in_end - in_start)) return BRO_ST_UnexpectedEOF;
+        bro_bits_seek(d.in, in_start + byte);
+        const uint32_t bit = (uint32_t)(r.in_bits & 7u);
+        if (bit) {
+            if (bro_avail(d.in) < bit) return BRO_ST_UnexpectedEOF;
+            bro_consume(d.in, bit);
+        }
+    } else {
+        d.d0 = 4; d.d1 = 11; d.d2 = 15; d.d3 = 16;      // src/lib.rs:407-408
+        st = bro_stream_header(d);
+        if (st) return st;
+    }
+    uint32_t is_last = 0, mlen = 0;
+    bool after_last = (r.flags & BRO_RESUME_LAST) != 0u;
+    for (;;) {
+        if (after_last) bro_checkpoint(d, ck, in_start, BRO_RESUME_HEADER | BRO_RESUME_LAST);
+        st = bro_next_metablock<true>(d, after_last, is_last, mlen, ck, in_start);
+        if (st == BRO_MB_END) {
+            bro_checkpoint(d, ck, in_start, BRO_RESUME_HEADER | BRO_RESUME_LAST | BRO_RESUME_ENDED);
+            return BRO_ST_OK;
+        }
         if (st != BRO_MB_COMPRESSED) return st;
         st = bro_decode_compressed_metablock(d, mlen);
         if (st) return st;

@@ -38,3 +38,28 @@ extern "C" int bro_hostsim_decode(const uint8_t* in, size_t in_len, uint8_t* out
 }
 
 extern "C" unsigned bro_hostsim_thread_arena_u16() { return BRO_THREAD_ARENA_U16; }
+
+// The resumable decode (bro_decode_stream_resume, the device side of the streaming reader): one call over the input and
+// output the caller has at hand, from and to the resume point *ck.  out[0 .. ck->pos) must hold the history (the last
+// min(window, bytes so far) bytes of output).  *out_len = bytes in the slot when the call stopped (only those in front
+// of the new ck->pos are final).
+extern "C" int bro_hostsim_decode_resume(const uint8_t* in, size_t in_len, uint8_t* out, size_t cap, size_t* out_len, int quirks,
+                                         BroResume* ck) {
+    BroDec d;
+    memset(&d, 0, sizeof(d));
+    BroScratch* sc = (BroScratch*)calloc(1, sizeof(BroScratch));
+    uint16_t* arena = (uint16_t*)malloc(2u * (size_t)BRO_ARENA_U16_MAX);
+    d.sc = sc;
+    d.arena = arena;
+    d.arena_cap = BRO_ARENA_U16_MAX;
+    d.arena_base = 0;
+    d.dict = bro_dictionary_blob;
+    d.out = out;
+    d.cap = cap > BRO_MAX_SLOT ? (uint32_t)BRO_MAX_SLOT : (uint32_t)cap;
+    d.quirk_spec = quirks;
+    int st = bro_decode_stream_resume(d, ck, in, in + in_len);
+    *out_len = d.pos;
+    free(sc);
+    free(arena);
+    return st;
+}

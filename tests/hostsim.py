@@ -126,3 +126,69 @@ def parse_size(data: bytes, quirks: int = 0):
         return st, n.value
     finally:
         L.bro_hostsim_parse_set_sizing(0)
+
+
+class Resume(ctypes.Structure):
+    """BroResume (brotli_rs_b200/csrc/bro_records.h)"""
+    _fields_ = [("in_bits", ctypes.c_uint64), ("pos", ctypes.c_uint32), ("window", ctypes.c_uint32), ("dist", ctypes.c_uint32 * 4),
+                ("p1", ctypes.c_uint32), ("p2", ctypes.c_uint32), ("flags", ctypes.c_uint32), ("reserved", ctypes.c_uint32)]
+
+
+RESUME_HEADER, RESUME_LAST, RESUME_ENDED = 1, 2, 4
+UNEXPECTED_EOF, EXPECTED_END_OF_STREAM, OUTPUT_TOO_SMALL = 24, 2, 100
+
+
+def stream_decode(data: bytes, chunk_sizes, out_cap=1 << 16, quirks=0, max_calls=100000):
+    """The streaming reader's loop (bro_reader_* in bro_abi.cu) over the host simulation of the resumable decode: the
+    input arrives in pieces of chunk_sizes (cycled), the output buffer holds the history (at most a window) plus what one
+    call produces.  -> (final status, bytes served before it, calls, largest input buffer, largest output buffer)."""
+    L = lib()
+    L.bro_hostsim_decode_resume.restype = ctypes.c_int
+    L.bro_hostsim_decode_resume.argtypes = [ctypes.c_char_p, ctypes.c_size_t, ctypes.c_void_p, ctypes.c_size_t,
+                                            ctypes.POINTER(ctypes.c_size_t), ctypes.c_int, ctypes.POINTER(Resume)]
+    ck = Resume()
+    served = bytearray()
+    fed, k = 0, 0                       # bytes of `data` handed over so far; index into chunk_sizes
+    buf = b""                           # unconsumed input
+    out = ctypes.create_string_buffer(out_cap)
+    hist = 0                            # history bytes at the start of `out`
+    want = 0                            # read more input until the buffer holds this much
+    calls = max_in = 0
+    max_out = out_cap
+    while True:
+        while fed < len(data) and (len(buf) < max(want, 1)):
+            n = chunk_sizes[k % len(chunk_sizes)]
+            k += 1
+            buf += data[fed: fed + n]
+            fed += n
+        eof = fed >= len(data)
+        max_in = max(max_in, len(buf))
+        n_out = ctypes.c_size_t()
+        before = (ck.in_bits, ck.pos, ck.flags)
+        st = L.bro_hostsim_decode_resume(buf, len(buf), ctypes.addressof(out), len(out), ctypes.byref(n_out), quirks, ctypes.byref(ck))
+        calls += 1
+        assert calls <= max_calls, "the streaming loop does not terminate"
+        progress = (ck.in_bits, ck.pos, ck.flags) != before
+        final_pos = n_out.value if st == 0 else ck.pos      # bytes behind the last resume point are not final
+        served += out.raw[hist: final_pos]
+        if st == 0:
+            if not eof:                  # the device saw the end of ITS input; bytes still to come are trailing garbage
+                return EXPECTED_END_OF_STREAM, bytes(served), calls, max_in, max_out
+            return 0, bytes(served), calls, max_in, max_out
+        # consumed input goes, the history slides to the front
+        drop = ck.in_bits >> 3
+        buf = buf[drop:]
+        ck.in_bits &= 7
+        keep = min(ck.pos, ck.window) if ck.flags & RESUME_HEADER else 0
+        raw = out.raw
+        if st == OUTPUT_TOO_SMALL and not progress:
+            out = ctypes.create_string_buffer(2 * len(out))
+            max_out = max(max_out, len(out))
+        ctypes.memmove(out, raw[ck.pos - keep: ck.pos], keep)
+        ck.pos = hist = keep
+        if st == UNEXPECTED_EOF and not eof:
+            want = len(buf) + 1 if progress else 2 * len(buf) + 1      # no progress: this meta-block needs more input at once
+            continue
+        if st == OUTPUT_TOO_SMALL:
+            continue
+        return st, bytes(served), calls, max_in, max_out

@@ -219,3 +219,67 @@ def test_copy_phase_lane_code(group):
                 p, s, f = cg.stats()
                 pieces, shorts, fills = pieces + p, shorts + s, fills + f
     assert handled >= 40 and pieces >= 100 and shorts >= 100 and fills >= 10, (handled, pieces, shorts, fills)
+
+
+# ---- the resumable decode behind the streaming reader (bro_decode_stream_resume + the reader's loop, tests/hostsim.py) ----
+
+def _stream_check(stream, chunks, label, out_cap=1 << 16):
+    st, out = oracle.decode(stream)
+    st1, served, calls, max_in, max_out = hostsim.stream_decode(stream, chunks, out_cap=out_cap)
+    assert st1 == st, (label, chunks[:4], st, st1)
+    if st == 0:
+        assert served == out, (label, chunks[:4], len(served), len(out))
+    else:
+        # what was served before the error are whole meta-blocks the reference decoded too
+        assert out.startswith(served), (label, chunks[:4], st, len(served), len(out))
+    return calls, max_in, max_out
+
+
+def test_stream_resume_corpus():
+    """input in pieces of 1 byte .. the whole stream: status and bytes equal the oracle's for every corpus file and test
+    vector, with the input and output buffers bounded by one meta-block (+ window), not by the stream"""
+    rng = np.random.default_rng(3)
+    for name, comp, _ in corpus_files():
+        for chunks in ([1], [7], [4096], [len(comp) + 1], [int(x) for x in rng.integers(1, 3000, 16)]):
+            if chunks == [1] and len(comp) > 60000:
+                continue
+            _stream_check(comp, chunks, name)
+    for name, inp, _, _ in stream_vectors():
+        _stream_check(inp, [3], name)
+        _stream_check(inp, [len(inp) + 1], name)
+    # bounded memory: 106 meta-blocks, 405,808 -> 912,868 bytes, window 2^22: neither buffer ever holds the stream
+    comp = [c for n, c, _ in corpus_files() if n == "metablock_reset.compressed"][0]
+    calls, max_in, max_out = _stream_check(comp, [2048], "metablock_reset", out_cap=1 << 14)
+    assert max_in < len(comp) // 2 and max_out <= 1 << 18 and calls >= 20, (calls, max_in, max_out)
+    # 65,537 empty meta-blocks: progress without output
+    comp = [c for n, c, _ in corpus_files() if n == "empty.compressed.18"][0]
+    calls, max_in, max_out = _stream_check(comp, [1000], "empty.18")
+    assert max_in <= 2100, max_in
+
+
+def test_stream_resume_fuzz():
+    corpus = [c for _, c, _ in corpus_files()]
+    rng = np.random.default_rng(41)
+    seen = set()
+    for m in fuzzgen.mutations(corpus, seed=8, count=2500):
+        chunks = [int(x) for x in rng.integers(1, max(2, len(m)), 5)] if rng.random() < 0.7 else [int(rng.integers(1, 64))]
+        if chunks == [1] and len(m) > 20000:
+            chunks = [977]
+        _stream_check(m, chunks, m[:16].hex())
+        seen.add(oracle.decode(m)[0])
+    assert len(seen) >= 15
+
+
+def test_stream_resume_fresh_streams():
+    """streams with small windows (the history slides many times) and many meta-blocks, all qualities"""
+    enc = fuzzgen.libbrotli_enc()
+    if enc is None:
+        pytest.skip("system libbrotlienc not present")
+    k = 0
+    for kind in ("random", "skewed", "repeat2k", "runs", "words", "small_alpha"):
+        for q, lgwin, size in ((1, 10, 60000), (5, 16, 300000), (9, 10, 50000), (11, 12, 40000), (5, 22, 500000)):
+            raw = fuzzgen.synthetic_raw(kind, 500 + k, size)
+            k += 1
+            comp = fuzzgen.compress(enc, raw, q, lgwin)
+            st, served, calls, max_in, max_out = hostsim.stream_decode(comp, [1500], out_cap=1 << 12)
+            assert (st, served) == (0, raw), (kind, q, lgwin, st, len(served))
