@@ -15,7 +15,7 @@ SIZE_UNKNOWN = 103
 # every symbol include/brotli_b200.h declares
 ABI_SYMBOLS = [
     "bro_ctx_create", "bro_ctx_destroy", "bro_ctx_set_quirks", "bro_ctx_set_mode", "bro_ctx_last_cuda_error", "bro_ctx_launch_count",
-    "bro_ctx_num_warps", "bro_ctx_reserve", "bro_ctx_set_timing", "bro_ctx_last_kernel_ms", "bro_ctx_last_batch_stats", "bro_batch_decode", "bro_batch_decode_host", "bro_batch_sizes", "bro_batch_decode_unsized_host", "bro_free", "bro_status_description",
+    "bro_ctx_num_warps", "bro_ctx_reserve", "bro_ctx_set_timing", "bro_ctx_last_kernel_ms", "bro_ctx_last_batch_stats", "bro_batch_decode", "bro_batch_decode_host", "bro_batch_sizes", "bro_batch_decode_unsized_host", "bro_batch_decode_resume", "bro_reader_new_streaming", "bro_free", "bro_status_description",
     "bro_reader_new", "bro_reader_read", "bro_reader_status", "bro_reader_free",
 ]
 
@@ -83,6 +83,10 @@ def load_library():
     L.bro_status_description.argtypes = [ctypes.c_int]
     L.bro_reader_new.restype = vp
     L.bro_reader_new.argtypes = [vp, READ_CB, vp]
+    L.bro_reader_new_streaming.restype = vp
+    L.bro_reader_new_streaming.argtypes = [vp, READ_CB, vp, ctypes.c_size_t]
+    L.bro_batch_decode_resume.restype = ctypes.c_int
+    L.bro_batch_decode_resume.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, u32, vp]
     L.bro_reader_read.restype = ctypes.c_ssize_t
     L.bro_reader_read.argtypes = [vp, vp, ctypes.c_size_t]
     L.bro_reader_status.restype = ctypes.c_int

@@ -124,6 +124,27 @@ class BatchDecoder:
         self._check(st)
         return d_out_len, d_status
 
+    RESUME_DTYPE = np.dtype([("in_bits", "<u8"), ("pos", "<u4"), ("window", "<u4"), ("dist", "<u4", 4), ("p1", "<u4"),
+                             ("p2", "<u4"), ("flags", "<u4"), ("reserved", "<u4")])      # bro_resume (include/brotli_b200.h)
+
+    def decode_resume_device(self, d_in, d_in_off, d_out, d_out_off, d_resume, d_out_len=None, d_status=None, stream=None):
+        """bro_batch_decode_resume on torch CUDA tensors: decode from and to the resume points in d_resume (uint8
+        tensor of n * 40 bytes, RESUME_DTYPE records; zeros = start of stream).  Returns (d_out_len, d_status)."""
+        import torch
+        n = d_in_off.numel() - 1
+        assert d_out_off.numel() == n + 1 and d_resume.numel() * d_resume.element_size() == n * self.RESUME_DTYPE.itemsize
+        for t in (d_in, d_in_off, d_out, d_out_off, d_resume):
+            assert t.is_cuda and t.is_contiguous()
+        if d_out_len is None:
+            d_out_len = torch.empty(n, dtype=torch.int64, device=d_in.device)
+        if d_status is None:
+            d_status = torch.empty(n, dtype=torch.int32, device=d_in.device)
+        s = stream if stream is not None else torch.cuda.current_stream(d_in.device)
+        self._check(self._lib.bro_batch_decode_resume(self._ctx, d_in.data_ptr(), d_in_off.data_ptr(), d_out.data_ptr(),
+                                                      d_out_off.data_ptr(), d_out_len.data_ptr(), d_status.data_ptr(),
+                                                      d_resume.data_ptr(), n, ctypes.c_void_p(s.cuda_stream)))
+        return d_out_len, d_status
+
     def decode_host(self, in_buf, in_off, out_off, out=None):
         """bro_batch_decode_host on numpy arrays (or anything exposing a writable buffer, e.g. pinned torch tensors
         via .numpy()).  Returns (out, out_len, status)."""

@@ -14,7 +14,7 @@ CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIBDIR, "libbrotli_b200.so")
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
-SOURCES = ["bro_kernels.cu", "bro_kernels_parse.cu", "bro_kernels_copy.cu", "bro_abi.cu"]
+SOURCES = ["bro_kernels.cu", "bro_kernels_parse.cu", "bro_kernels_copy.cu", "bro_kernels_resume.cu", "bro_abi.cu"]
 BLOB = "dict_blob.c"
 HEADERS = ["bro_decoder_core.h", "bro_parse.h", "bro_records.h", "bro_copy_piece.h", "bro_kernels.h", "bro_status.h", "bro_tables_generated.h"]
 

@@ -300,6 +300,34 @@ extern "C" int bro_batch_decode(bro_ctx* ctx, const uint8_t* d_in, const uint64_
     return BRO_ST_OK;
 }
 
+static_assert(sizeof(bro_resume) == sizeof(BroResume), "bro_resume (include/brotli_b200.h) mirrors BroResume (bro_records.h)");
+
+// The resumable decode: the fused warp-per-stream kernel from and to a resume point per stream (bro_kernels_resume.cu).
+extern "C" int bro_batch_decode_resume(bro_ctx* ctx, const uint8_t* d_in, const uint64_t* d_in_off, uint8_t* d_out,
+                                       const uint64_t* d_out_off, uint64_t* d_out_len, int32_t* d_status, bro_resume* d_resume,
+                                       uint32_t n, void* stream) {
+    if (!ctx) return BRO_ST_InvalidArgument;
+    if (n == 0) return BRO_ST_OK;
+    if (!d_in_off || !d_out_off || !d_out_len || !d_status || !d_resume) return BRO_ST_InvalidArgument;
+    cudaStream_t s = (cudaStream_t)stream;
+    BRO_CUDA(ctx, cudaMemsetAsync(ctx->d_counter, 0, 16 * sizeof(uint32_t), s));
+    BroLaunch p;
+    memset(&p, 0, sizeof(p));
+    p.in = d_in; p.in_off = d_in_off; p.out = d_out; p.out_off = d_out_off;
+    p.out_len = d_out_len; p.status = d_status; p.n = n;
+    p.dict = ctx->d_dict; p.quirk_spec = ctx->quirks;
+    p.arena = ctx->d_arena; p.counter = ctx->d_counter + 1;
+    p.resume = (BroResume*)d_resume;
+    // the resume kernel has the warp kernel's CTA shape and arena layout: never more warps than the arena has shares
+    const uint32_t wpc = (uint32_t)bro_resume_kernel_warps_per_cta();
+    int grid = (int)(ctx->num_warps / wpc);
+    if ((uint32_t)grid > (n + wpc - 1) / wpc) grid = (int)((n + wpc - 1) / wpc);
+    cudaError_t e = (cudaError_t)bro_resume_kernel_launch(&p, grid, s);
+    if (e != cudaSuccess) return bro_fail(ctx, e, "bro_decode_resume_kernel launch");
+    ctx->launches += 1;
+    return BRO_ST_OK;
+}
+
 extern "C" int bro_batch_sizes(bro_ctx* ctx, const uint8_t* d_in, const uint64_t* d_in_off, uint64_t* d_out_len,
                                int32_t* d_status, uint32_t n, void* stream) {
     if (!ctx) return BRO_ST_InvalidArgument;
@@ -530,19 +558,46 @@ struct bro_reader {
     bool own_ctx;
     bro_read_cb cb;
     void* user;
-    bool decoded;
+    bool decoded;             // whole-stream mode: the stream has been decoded; streaming mode: no call can add anything
     int status;
-    std::vector<uint8_t> out;
+    std::vector<uint8_t> out; // decoded bytes not yet served (whole-stream mode: all of them)
     size_t served;
+    // ---- streaming mode (bro_reader_new_streaming) ----
+    bool streaming;
+    size_t chunk;             // bytes asked of `cb` at a time
+    std::vector<uint8_t> in;  // compressed bytes not yet consumed
+    bool in_eof;
+    size_t want;              // top `in` up to this many bytes before the next call
+    BroResume ck;             // resume point (host copy)
+    uint8_t* d_in; size_t d_in_cap;
+    uint8_t* d_out[2]; size_t d_out_cap;      // ping-pong: the history moves to the other buffer between calls
+    int cur;
+    uint64_t* d_meta;         // in_off[2] | out_off[2] | out_len | status (+ pad) | BroResume
 };
 
-extern "C" bro_reader* bro_reader_new(bro_ctx* ctx, bro_read_cb cb, void* user) {
+static bro_reader* bro_reader_alloc(bro_ctx* ctx, bro_read_cb cb, void* user) {
     if (!cb) return NULL;
     bro_reader* r = new (std::nothrow) bro_reader();
     if (!r) return NULL;
     r->ctx = ctx; r->own_ctx = false; r->cb = cb; r->user = user;
     r->decoded = false; r->status = BRO_ST_OK; r->served = 0;
-    return r;                                        // like Decompressor::new: no I/O yet (src/lib.rs:398-410)
+    r->streaming = false; r->chunk = 0; r->in_eof = false; r->want = 0;
+    memset(&r->ck, 0, sizeof(r->ck));
+    r->d_in = NULL; r->d_in_cap = 0; r->d_out[0] = r->d_out[1] = NULL; r->d_out_cap = 0; r->cur = 0; r->d_meta = NULL;
+    return r;
+}
+
+extern "C" bro_reader* bro_reader_new(bro_ctx* ctx, bro_read_cb cb, void* user) {
+    return bro_reader_alloc(ctx, cb, user);          // like Decompressor::new: no I/O yet (src/lib.rs:398-410)
+}
+
+extern "C" bro_reader* bro_reader_new_streaming(bro_ctx* ctx, bro_read_cb cb, void* user, size_t in_chunk) {
+    bro_reader* r = bro_reader_alloc(ctx, cb, user);
+    if (!r) return NULL;
+    r->streaming = true;
+    r->chunk = in_chunk ? in_chunk : (size_t)1 << 20;
+    r->want = r->chunk;
+    return r;
 }
 
 static void bro_reader_decode(bro_reader* r) {
@@ -585,8 +640,145 @@ static void bro_reader_decode(bro_reader* r) {
     }
 }
 
+// ---- streaming mode: incremental input, bounded memory, resume at meta-block boundaries ----
+//
+// One step = top the input buffer up from R, one call of the resumable decode over (unconsumed input, history + room),
+// then: the bytes in front of the new resume point are final and go to the caller; consumed input is dropped; the last
+// min(window, bytes so far) bytes of output move to the front of the other output buffer as the next call's history.
+// A call that ends inside a meta-block for lack of input (UnexpectedEOF while R has more) or room (OutputTooSmall) is
+// repeated from the resume point with more of it -- twice as much when the call made no progress at all, which bounds
+// both buffers by the largest meta-block (+ a window of history), not by the stream.
+
+static int bro_reader_fail(bro_reader* r, int st) {
+    r->status = st; r->decoded = true;
+    return st;
+}
+
+#define BRO_RCUDA(r, call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { bro_fail((r)->ctx, e_, #call); return bro_reader_fail(r, BRO_ST_CudaError); } } while (0)
+
+static int bro_reader_out_reserve(bro_reader* r, size_t cap, size_t keep_from, size_t keep) {
+    // both output buffers get capacity `cap`; bytes [keep_from, keep_from + keep) of the current one become [0, keep) of
+    // the (new) current one
+    uint8_t* nb[2] = {NULL, NULL};
+    BRO_RCUDA(r, cudaMalloc(&nb[0], cap));
+    if (cudaMalloc(&nb[1], cap) != cudaSuccess) { cudaFree(nb[0]); return bro_reader_fail(r, BRO_ST_CudaError); }
+    if (keep) BRO_RCUDA(r, cudaMemcpy(nb[0], r->d_out[r->cur] + keep_from, keep, cudaMemcpyDeviceToDevice));
+    cudaFree(r->d_out[0]); cudaFree(r->d_out[1]);
+    r->d_out[0] = nb[0]; r->d_out[1] = nb[1]; r->d_out_cap = cap; r->cur = 0;
+    return BRO_ST_OK;
+}
+
+// One step.  Returns BRO_ST_OK when the step may have added bytes to r->out or ended the stream (r->decoded).
+static int bro_reader_step(bro_reader* r) {
+    if (!r->ctx) {
+        int st = bro_ctx_create(&r->ctx, -1);
+        if (st) return bro_reader_fail(r, st);
+        r->own_ctx = true;
+    }
+    cudaSetDevice(r->ctx->device);
+    // top up the input
+    while (!r->in_eof && r->in.size() < r->want) {
+        const size_t old = r->in.size();
+        r->in.resize(old + r->chunk);
+        const intptr_t got = r->cb(r->user, r->in.data() + old, r->chunk);
+        r->in.resize(old + (got > 0 ? (size_t)got : 0));
+        if (got <= 0) r->in_eof = true;               // an I/O error ends the input (src/bitreader/mod.rs:78-82)
+    }
+    if (!r->d_meta) BRO_RCUDA(r, cudaMalloc(&r->d_meta, 8 * sizeof(uint64_t) + sizeof(BroResume)));
+    if (!r->d_out[0]) {
+        size_t cap = 4 * r->chunk;
+        if (cap < ((size_t)1 << 16)) cap = (size_t)1 << 16;
+        int st = bro_reader_out_reserve(r, cap, 0, 0);
+        if (st) return st;
+    }
+    if (r->in.size() > r->d_in_cap) {
+        cudaFree(r->d_in); r->d_in = NULL; r->d_in_cap = 0;
+        const size_t cap = r->in.size() + r->in.size() / 2 + 64;
+        BRO_RCUDA(r, cudaMalloc(&r->d_in, cap));
+        r->d_in_cap = cap;
+    }
+    if (!r->d_in) { BRO_RCUDA(r, cudaMalloc(&r->d_in, 64)); r->d_in_cap = 64; }
+    uint64_t meta[8] = {0, (uint64_t)r->in.size(), 0, (uint64_t)r->d_out_cap, 0, 0, 0, 0};
+    BroResume* d_ck = (BroResume*)(r->d_meta + 8);
+    if (!r->in.empty()) BRO_RCUDA(r, cudaMemcpy(r->d_in, r->in.data(), r->in.size(), cudaMemcpyHostToDevice));
+    BRO_RCUDA(r, cudaMemcpy(r->d_meta, meta, sizeof(meta), cudaMemcpyHostToDevice));
+    BRO_RCUDA(r, cudaMemcpy(d_ck, &r->ck, sizeof(BroResume), cudaMemcpyHostToDevice));
+    const BroResume before = r->ck;
+    const uint32_t hist = r->ck.pos;
+    int st = bro_batch_decode_resume(r->ctx, r->d_in, r->d_meta, r->d_out[r->cur], r->d_meta + 2, r->d_meta + 4, (int32_t*)(r->d_meta + 5),
+                                     (bro_resume*)d_ck, 1, NULL);
+    if (st) return bro_reader_fail(r, st);
+    BRO_RCUDA(r, cudaMemcpy(meta, r->d_meta, sizeof(meta), cudaMemcpyDeviceToHost));
+    BRO_RCUDA(r, cudaMemcpy(&r->ck, d_ck, sizeof(BroResume), cudaMemcpyDeviceToHost));
+    const int32_t status = *(const int32_t*)&meta[5];
+    const bool progress = r->ck.in_bits != before.in_bits || r->ck.pos != before.pos || r->ck.flags != before.flags;
+    // bytes behind the last resume point belong to an unfinished meta-block and are decoded again
+    const size_t final_pos = status == BRO_ST_OK ? (size_t)meta[4] : (size_t)r->ck.pos;
+    if (final_pos > hist) {
+        const size_t old = r->out.size();
+        r->out.resize(old + (final_pos - hist));
+        BRO_RCUDA(r, cudaMemcpy(r->out.data() + old, r->d_out[r->cur] + hist, final_pos - hist, cudaMemcpyDeviceToHost));
+    }
+    if (status == BRO_ST_OK) {
+        // the device saw the end of ITS input behind the stream; bytes R still holds are trailing garbage (src/lib.rs:2160-2166)
+        if (!r->in_eof) {
+            uint8_t probe[64];
+            const intptr_t got = r->cb(r->user, probe, sizeof(probe));
+            if (got > 0) { r->status = BRO_ST_ExpectedEndOfStream; r->decoded = true; return BRO_ST_OK; }
+            r->in_eof = true;
+        }
+        r->decoded = true;
+        return BRO_ST_OK;
+    }
+    // consumed input goes; the history slides to the front of the other buffer
+    const size_t drop = (size_t)(r->ck.in_bits >> 3);
+    if (drop) r->in.erase(r->in.begin(), r->in.begin() + (drop < r->in.size() ? drop : r->in.size()));
+    r->ck.in_bits &= 7u;
+    size_t keep = 0;
+    if (r->ck.flags & BRO_RESUME_HEADER) keep = r->ck.pos < r->ck.window ? r->ck.pos : r->ck.window;
+    const size_t keep_from = (size_t)r->ck.pos - keep;
+    if (status == BRO_ST_OutputTooSmall && !progress) {
+        if (r->d_out_cap >= ((size_t)1 << 31)) { r->status = status; r->decoded = true; return BRO_ST_OK; }
+        int st2 = bro_reader_out_reserve(r, 2 * r->d_out_cap, keep_from, keep);
+        if (st2) return st2;
+    } else if (keep_from != 0) {
+        if (keep) BRO_RCUDA(r, cudaMemcpy(r->d_out[1 - r->cur], r->d_out[r->cur] + keep_from, keep, cudaMemcpyDeviceToDevice));
+        r->cur = 1 - r->cur;
+    }
+    r->ck.pos = (uint32_t)keep;
+    if (status == BRO_ST_UnexpectedEOF && !r->in_eof) {
+        r->want = progress ? r->in.size() + 1 : 2 * r->in.size() + 1;     // no progress: this meta-block needs more at once
+        if (r->want < r->chunk) r->want = r->chunk;
+        return BRO_ST_OK;
+    }
+    if (status == BRO_ST_OutputTooSmall) return BRO_ST_OK;
+    r->status = status;                               // an invalid stream (or one that ends early): final
+    r->decoded = true;
+    return BRO_ST_OK;
+}
+
 extern "C" intptr_t bro_reader_read(bro_reader* r, uint8_t* buf, size_t len) {
     if (!r || (!buf && len)) return -(intptr_t)BRO_ST_InvalidArgument;
+    if (r->streaming) {
+        // like Read::read of the reference (src/lib.rs:2174-2192): fill `buf` while the stream has data; bytes decoded
+        // before an error are delivered first, the error by the read that finds nothing in front of it
+        size_t done = 0;
+        try {
+            for (;;) {
+                const size_t left = r->out.size() - r->served;
+                const size_t k = len - done < left ? len - done : left;
+                if (k) { memcpy(buf + done, r->out.data() + r->served, k); r->served += k; done += k; }
+                if (r->served == r->out.size()) { r->out.clear(); r->served = 0; }
+                if (done == len || r->decoded) break;
+                if (bro_reader_step(r) != BRO_ST_OK) break;
+            }
+        } catch (...) {
+            bro_reader_fail(r, BRO_ST_InvalidArgument);
+        }
+        if (done) return (intptr_t)done;
+        if (r->status != BRO_ST_OK) return -(intptr_t)r->status;
+        return 0;
+    }
     if (!r->decoded) bro_reader_decode(r);
     if (r->status != BRO_ST_OK) return -(intptr_t)r->status;   // io::Error(InvalidData, description), src/lib.rs:2177
     size_t left = r->out.size() - r->served;
@@ -600,6 +792,10 @@ extern "C" int bro_reader_status(const bro_reader* r) { return r ? r->status : B
 
 extern "C" void bro_reader_free(bro_reader* r) {
     if (!r) return;
+    if (r->d_in || r->d_out[0] || r->d_meta) {
+        if (r->ctx) cudaSetDevice(r->ctx->device);
+        cudaFree(r->d_in); cudaFree(r->d_out[0]); cudaFree(r->d_out[1]); cudaFree(r->d_meta);
+    }
     if (r->own_ctx) bro_ctx_destroy(r->ctx);
     delete r;
 }

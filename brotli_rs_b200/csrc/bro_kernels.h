@@ -39,6 +39,7 @@ struct BroLaunch {
     uint32_t* done_tail;
     uint16_t* roots;          // parse kernel: per-thread decode tables (bro_parse.h) when they live in HBM / L2
     unsigned long long* copy_stats;   // [0] bytes moved by records, [1] records executed (this batch)
+    BroResume* resume;        // resumable decode (bro_kernels_resume.cu): n resume points, read at the start and rewritten
 };
 
 
@@ -47,6 +48,10 @@ extern "C" int bro_warp_kernel_occupancy(int* blocks_per_sm);
 extern "C" int bro_warp_kernel_warps_per_cta();
 extern "C" size_t bro_warp_kernel_arena_bytes();
 extern "C" int bro_warp_kernel_launch(const BroLaunch* p, int grid, cudaStream_t stream);
+
+// resumable warp-per-stream kernel (bro_kernels_resume.cu); same arenas and grid as the warp kernel
+extern "C" int bro_resume_kernel_warps_per_cta();
+extern "C" int bro_resume_kernel_launch(const BroLaunch* p, int grid, cudaStream_t stream);
 
 // two-phase path, phase one: the parse kernel (one thread per stream) and the size-class ordering kernels
 // (bro_kernels_parse.cu)

@@ -7,6 +7,10 @@
 `Decompressor(r)` performs no I/O (like Decompressor::new); the first `read` drains `r`, decodes the stream on the
 GPU and serves bytes from a host buffer.  An invalid stream raises BroError whose message is the reference's
 error description (io::Error::new(InvalidData, description), src/lib.rs:2177).
+
+`Decompressor(r, streaming=True)` (or streaming=<bytes asked of r at a time>) has the reference's memory behaviour
+instead: input is read as it is needed and decoded meta-block by meta-block (bro_reader_new_streaming), the buffers are
+bounded by the largest meta-block plus a window, and bytes decoded before an error are delivered before it is raised.
 """
 import ctypes
 import io
@@ -15,7 +19,7 @@ from . import _lib
 
 
 class Decompressor(io.RawIOBase):
-    def __init__(self, r, decoder=None):
+    def __init__(self, r, decoder=None, streaming=False):
         """r: a readable binary file-like object (or bytes).  decoder: an optional BatchDecoder whose context is
         shared; otherwise the reader creates its own context on the current device."""
         super().__init__()
@@ -38,7 +42,10 @@ class Decompressor(io.RawIOBase):
 
         self._cb = _lib.READ_CB(_cb)        # keep the trampoline alive as long as the reader
         ctx = decoder._ctx if decoder is not None else None
-        self._h = self._lib.bro_reader_new(ctx, self._cb, None)
+        if streaming:
+            self._h = self._lib.bro_reader_new_streaming(ctx, self._cb, None, 0 if streaming is True else int(streaming))
+        else:
+            self._h = self._lib.bro_reader_new(ctx, self._cb, None)
         if not self._h:
             raise MemoryError("bro_reader_new failed")
 

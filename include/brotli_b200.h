@@ -104,6 +104,37 @@ int bro_batch_decode(bro_ctx* ctx, const uint8_t* d_in, const uint64_t* d_in_off
 int bro_batch_decode_host(bro_ctx* ctx, const uint8_t* h_in, const uint64_t* h_in_off, uint8_t* h_out,
                           const uint64_t* h_out_off, uint64_t* h_out_len, int32_t* h_status, uint32_t n);
 
+/* ---- resumable decode: the building block of streaming (incremental input, bounded memory) ----
+ *
+ * The reference decodes incrementally: its `State` and decoder fields survive between read() calls (src/lib.rs:245-291,
+ * 378-394), input is pulled as needed and only a window of output is kept (src/ringbuffer/mod.rs:8-73).  Here a stream's
+ * state between two calls is a RESUME POINT, written by the decoder in front of every meta-block header (stored and
+ * metadata blocks included) and at the clean end of the stream.  All-zero = start of stream. */
+typedef struct bro_resume {
+    uint64_t in_bits;    /* bits consumed, counted from the first byte of the input given to the call that wrote it */
+    uint32_t pos;        /* bytes in the output slot in front of the resume point, history included */
+    uint32_t window;     /* (1 << WBITS) - 16 once BRO_RESUME_HEADER is set (src/lib.rs:1562) */
+    uint32_t dist[4];    /* distance ring, last distance first (src/lib.rs:393) */
+    uint32_t p1, p2;     /* the two bytes in front of the resume point (src/lib.rs:389) */
+    uint32_t flags;      /* BRO_RESUME_* */
+    uint32_t reserved;
+} bro_resume;
+#define BRO_RESUME_HEADER 1u  /* the stream header has been consumed */
+#define BRO_RESUME_LAST 2u    /* the ISLAST meta-block has been decoded: only the end-of-stream checks remain */
+#define BRO_RESUME_ENDED 4u   /* the stream ended cleanly */
+
+/* bro_batch_decode_resume: bro_batch_decode from and to d_resume[i] (device memory, n resume points).  Stream i's input
+ * [d_in_off[i], d_in_off[i+1]) starts at the byte that holds bit d_resume[i].in_bits; its slot must start with the
+ * history -- the last min(window, bytes produced so far) bytes of output -- in [0, d_resume[i].pos).  The call decodes
+ * whole meta-blocks while input and slot last.  d_status[i]: BRO_OK = the stream ended cleanly (d_out_len[i] = bytes in
+ * the slot); BRO_UNEXPECTED_EOF / BRO_OUTPUT_TOO_SMALL = the input / the slot ended inside a meta-block: the bytes in front
+ * of the NEW d_resume[i].pos are final, and the call may be repeated from it with more input / room (the caller drops
+ * in_bits / 8 input bytes, keeps in_bits % 8, and moves the history to the front of the slot); any other status = the
+ * stream is invalid.  Always the fused warp-per-stream kernel.  Asynchronous on `stream`. */
+int bro_batch_decode_resume(bro_ctx* ctx, const uint8_t* d_in, const uint64_t* d_in_off, uint8_t* d_out,
+                            const uint64_t* d_out_off, uint64_t* d_out_len, int32_t* d_status, bro_resume* d_resume,
+                            uint32_t n, void* stream);
+
 /* ---- decoding without knowing the uncompressed sizes (a Brotli stream does not state its size: MLEN is per meta-block,
  * src/lib.rs:469-483; the reference grows a Vec as it goes, src/lib.rs:2183-2189) ----
  *
@@ -137,6 +168,13 @@ bro_reader* bro_reader_new(bro_ctx* ctx, bro_read_cb cb, void* user);
 intptr_t bro_reader_read(bro_reader* r, uint8_t* buf, size_t len);
 int bro_reader_status(const bro_reader* r);
 void bro_reader_free(bro_reader* r);
+
+/* The same Read-struct with the reference's memory behaviour (src/lib.rs:2174-2192: input is read as it is needed, the
+ * decoder keeps a window of output): `cb` is asked for `in_chunk` bytes at a time (0 = 1 MiB), every step decodes the
+ * whole meta-blocks the buffered input holds (bro_batch_decode_resume, one-stream batch) and hands their bytes out, and
+ * the buffers are bounded by the largest meta-block plus one window, not by the stream.  bro_reader_read fills `buf`
+ * while the stream has data; bytes decoded before an error are delivered first, then -(status). */
+bro_reader* bro_reader_new_streaming(bro_ctx* ctx, bro_read_cb cb, void* user, size_t in_chunk);
 
 #ifdef __cplusplus
 }

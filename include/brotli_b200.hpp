@@ -65,6 +65,13 @@ public:
     explicit Decompressor(R r, bro_ctx* ctx = nullptr) : r_(std::move(r)), h_(bro_reader_new(ctx, &trampoline, this)) {
         if (!h_) throw std::bad_alloc();
     }
+    // The same with the reference's memory behaviour (bro_reader_new_streaming): `r` is asked for in_chunk bytes at a
+    // time (0 = 1 MiB) and decoded meta-block by meta-block; buffers are bounded by a meta-block plus a window.
+    struct Streaming { size_t in_chunk; };
+    Decompressor(R r, Streaming s, bro_ctx* ctx = nullptr)
+        : r_(std::move(r)), h_(bro_reader_new_streaming(ctx, &trampoline, this, s.in_chunk)) {
+        if (!h_) throw std::bad_alloc();
+    }
     Decompressor(const Decompressor&) = delete;
     Decompressor& operator=(const Decompressor&) = delete;
     ~Decompressor() { bro_reader_free(h_); }

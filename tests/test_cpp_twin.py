@@ -9,6 +9,7 @@ from conftest import DATA, ROOT
 
 SRC = r'''
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <fstream>
 #include <vector>
@@ -27,6 +28,16 @@ int main(int argc, char** argv) {
         for (const auto& it : brotli::decode_batch(ctx, streams)) std::printf("%d %zu\n", it.status, it.bytes.size());
         bro_ctx_destroy(ctx);
         return 0;
+    }
+    if (argc > 4 && !std::strcmp(argv[1], "stream")) {
+        // streaming mode: argv[2] = compressed file, argv[3] = expected file, argv[4] = bytes asked of the file at a time
+        std::ifstream f(argv[2], std::ios::binary);
+        brotli::Decompressor<brotli::IstreamReader> d{brotli::IstreamReader(f), {static_cast<size_t>(std::atol(argv[4]))}};
+        std::vector<uint8_t> out;
+        try { d.read_to_end(out); } catch (const brotli::Error& e) { std::printf("ERR %d %s after %zu\n", e.status(), e.what(), out.size()); return 3; }
+        const std::vector<uint8_t> exp = slurp(argv[3]);
+        std::printf("%s %zu\n", out == exp ? "EQUAL" : "DIFFERENT", out.size());
+        return out == exp ? 0 : 2;
     }
     std::ifstream f(argv[1], std::ios::binary);
     brotli::Decompressor<brotli::IstreamReader> d{brotli::IstreamReader(f)};
@@ -65,6 +76,12 @@ def test_cpp_twin_doctest_and_error(tmp_path):
     r = subprocess.run([exe, os.path.join(DATA, "alice29.txt.compressed"), os.path.join(DATA, "alice29.txt")], capture_output=True, text=True)
     assert r.returncode == 0 and r.stdout.startswith("EQUAL 152089"), r.stdout + r.stderr
     r = subprocess.run([exe, os.path.join(DATA, "frewsxcv_06.compressed"), os.path.join(DATA, "64x")], capture_output=True, text=True)
+    assert r.returncode == 3 and "ERR 23 Run length excceeded" in r.stdout, r.stdout + r.stderr
+    # the streaming constructor (bro_reader_new_streaming): 2,000 bytes of input at a time
+    r = subprocess.run([exe, "stream", os.path.join(DATA, "metablock_reset.compressed"), os.path.join(DATA, "metablock_reset"), "2000"],
+                       capture_output=True, text=True)
+    assert r.returncode == 0 and r.stdout.startswith("EQUAL 912868"), r.stdout + r.stderr
+    r = subprocess.run([exe, "stream", os.path.join(DATA, "frewsxcv_06.compressed"), os.path.join(DATA, "64x"), "7"], capture_output=True, text=True)
     assert r.returncode == 3 and "ERR 23 Run length excceeded" in r.stdout, r.stdout + r.stderr
     # brotli::decode_batch: several streams, no size hints
     names = ["64x", "alice29.txt", "quickfox_repeated", "random_org_10k.bin", "empty"]

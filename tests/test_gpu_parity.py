@@ -416,3 +416,133 @@ def test_decode_without_size_hints():
         assert gst == wst and (wst != 0 or gout == wout), (i, gst, wst, len(gout), len(wout))
     assert d.decode_unsized([]) == []
     d.close()
+
+
+# ---- streaming: the resumable decode and the streaming Read-struct ----
+
+def test_streaming_reader_corpus():
+    """Decompressor(r, streaming=chunk): input pulled `chunk` bytes at a time, decoded meta-block by meta-block; bytes and
+    error class equal the oracle's for every corpus file, bytes decoded before an error come first"""
+    from brotli_rs_b200 import BatchDecoder, BroError, Decompressor
+    d = BatchDecoder(0)
+    try:
+        for name, comp, _ in corpus_files():
+            st, out = oracle.decode(comp)
+            for chunk in (True, 4096, 61):
+                if chunk == 61 and len(comp) > 60000:
+                    continue
+                r = Decompressor(comp, decoder=d, streaming=chunk)
+                got, err = bytearray(), 0
+                try:
+                    while True:
+                        b = bytearray(30011)
+                        n = r.readinto(b)
+                        if n == 0:
+                            break
+                        got += b[:n]
+                except BroError as e:
+                    err = e.status
+                assert err == st, (name, chunk, st, err)
+                if st == 0:
+                    assert bytes(got) == out and r.readinto(bytearray(8)) == 0, (name, chunk, len(got), len(out))
+                else:
+                    assert out.startswith(bytes(got)), (name, chunk)
+                r.close()
+        # trailing bytes behind a complete stream: every byte of the stream is delivered, then ExpectedEndOfStream
+        comp = open(os.path.join(DATA, "64x.compressed"), "rb").read()
+        r = Decompressor(comp + b"\x00" * 300, decoder=d, streaming=len(comp))
+        b = bytearray(100)
+        assert r.readinto(b) == 64 and bytes(b[:64]) == b"x" * 64
+        with pytest.raises(BroError) as ei:
+            r.readinto(b)
+        assert ei.value.status == 2
+        # a stream cut inside a meta-block: UnexpectedEOF once the input is exhausted
+        comp = open(os.path.join(DATA, "alice29.txt.compressed"), "rb").read()
+        with pytest.raises(BroError) as ei:
+            Decompressor(comp[:30000], decoder=d, streaming=1000).read()
+        assert ei.value.status == 24
+    finally:
+        d.close()
+
+
+def test_streaming_reader_fuzz_and_small_windows():
+    from brotli_rs_b200 import BatchDecoder, BroError, Decompressor
+    d = BatchDecoder(0)
+    rng = np.random.default_rng(17)
+    try:
+        corpus = [c for _, c, _ in corpus_files()]
+        seen = set()
+        for m in fuzzgen.mutations(corpus, seed=21, count=250, max_len=20000):
+            st, out = oracle.decode(m)
+            got, err = b"", 0
+            r = Decompressor(m, decoder=d, streaming=int(rng.integers(1, 3000)))
+            try:
+                got = r.read()
+            except BroError as e:
+                err = e.status
+            assert err == st and (st != 0 or got == out), (m[:16].hex(), st, err, len(got), len(out))
+            seen.add(st)
+            r.close()
+        assert len(seen) >= 8
+        enc = fuzzgen.libbrotli_enc()
+        if enc is not None:
+            for k, (kind, q, lgwin, size) in enumerate((("repeat2k", 5, 10, 200000), ("words", 11, 12, 60000), ("runs", 9, 10, 90000),
+                                                        ("skewed", 5, 16, 300000), ("random", 5, 16, 150000))):
+                raw = fuzzgen.synthetic_raw(kind, 800 + k, size)
+                comp = fuzzgen.compress(enc, raw, q, lgwin)
+                assert Decompressor(comp, decoder=d, streaming=1500).read() == raw, (kind, q, lgwin)
+    finally:
+        d.close()
+
+
+def test_batch_decode_resume_device():
+    """bro_batch_decode_resume on a batch: (1) from all-zero resume points with the whole input it is bro_batch_decode;
+    (2) with the input cut in two, the second call continues from the resume points of the first"""
+    import torch
+    from brotli_rs_b200 import BatchDecoder
+    from brotli_rs_b200.batch import pack_streams, slot_offsets
+    d = BatchDecoder(0)
+    try:
+        files = [(n, c, e) for n, c, e in corpus_files() if e is not None]
+        streams = [c for _, c, _ in files]
+        want = [e for _, _, e in files]
+        n = len(streams)
+        dev = torch.device("cuda", 0)
+        out_off = slot_offsets([len(e) + 64 for e in want])
+        d_out_off = torch.from_numpy(out_off.astype(np.int64)).to(dev)
+        d_out = torch.zeros(int(out_off[-1]), dtype=torch.uint8, device=dev)
+        rec = BatchDecoder.RESUME_DTYPE.itemsize
+
+        def run(parts, d_resume):
+            buf, off = pack_streams(parts)
+            d_in = torch.from_numpy(np.concatenate([buf, np.zeros(16, dtype=np.uint8)])).to(dev)
+            d_in_off = torch.from_numpy(off.astype(np.int64)).to(dev)
+            ln, st = d.decode_resume_device(d_in, d_in_off, d_out, d_out_off, d_resume)
+            torch.cuda.synchronize()
+            return ln.cpu().numpy(), st.cpu().numpy(), d_resume.cpu().numpy().view(BatchDecoder.RESUME_DTYPE)
+
+        ln, st, ck = run(streams, torch.zeros(n * rec, dtype=torch.uint8, device=dev))
+        host = d_out.cpu().numpy()
+        for i in range(n):
+            assert st[i] == 0 and ln[i] == len(want[i]) and ck["flags"][i] == 7, (files[i][0], st[i], ln[i], ck["flags"][i])
+            assert host[int(out_off[i]): int(out_off[i]) + len(want[i])].tobytes() == want[i], files[i][0]
+        # two calls: the first sees 60 % of every stream
+        d_out.zero_()
+        cut = [int(0.6 * len(s)) for s in streams]
+        d_resume = torch.zeros(n * rec, dtype=torch.uint8, device=dev)
+        ln1, st1, ck1 = run([s[:c] for s, c in zip(streams, cut)], d_resume)
+        assert set(st1.tolist()) <= {0, 24}
+        rest, ck2 = [], ck1.copy()
+        for i in range(n):
+            drop = int(ck1["in_bits"][i]) >> 3
+            rest.append(streams[i][drop:] if st1[i] != 0 else streams[i][len(streams[i]):])
+            ck2["in_bits"][i] &= 7
+        todo = [i for i in range(n) if st1[i] != 0]
+        assert len(todo) >= 8
+        ln2, st2, ck3 = run(rest, torch.from_numpy(ck2.view(np.uint8).copy()).to(dev))
+        host = d_out.cpu().numpy()
+        for i in todo:
+            assert st2[i] == 0 and ln2[i] == len(want[i]), (files[i][0], st2[i], ln2[i], len(want[i]))
+            assert host[int(out_off[i]): int(out_off[i]) + len(want[i])].tobytes() == want[i], files[i][0]
+    finally:
+        d.close()
