@@ -7,9 +7,10 @@
 // The records of a stream must take effect in order, but most neighbours do not depend on each other.  The warp loads
 // 32 records at a time (one per lane, coalesced) and splits them into GROUPS: a maximal run of records none of which
 // reads a byte that a record of the same run writes.  Inside a group nothing has to be ordered:
-//   * a group of LONG records (phase one cuts every copy into pieces of at most 32 aligned 16-byte vectors) moves one
-//     piece per warp step -- lane t moves vector t plus the t-th ragged byte at each end -- with several pieces in
-//     flight: all loads are issued before the first store;
+//   * a group of LONG records (phase one cuts every copy into pieces of at most 32 aligned 16-byte vectors) is moved
+//     piece by piece by groups of BRO_COPY_GROUP lanes (bro_copy_piece.h): lane t of a group moves the vectors t,
+//     t + GROUP, ... and the ragged bytes at both ends, so a warp step moves 32 / GROUP pieces -- with BRO_COPY_PIECES
+//     pieces in flight: all loads are issued before the first store;
 //   * a group of SHORT records (text-like streams) is executed as ONE segmented copy: the bytes of all its records are
 //     cut into units (16-byte vectors on aligned destinations, single bytes for the ragged ends), the units are
 //     numbered by a warp prefix sum, and every lane takes every 32nd unit, finding its record by a binary search over
@@ -36,7 +37,9 @@
 #define BRO_COPY_PIECES 4     // long records: pieces in flight per warp (their data is held in registers)
 #endif
 #ifndef BRO_COPY_GROUP
-#define BRO_COPY_GROUP 32     // long records: lanes that move one piece (32, 16 or 8): 32 / GROUP pieces per warp step
+#define BRO_COPY_GROUP 8      // long records: lanes that move one piece (32, 16 or 8): 32 / GROUP pieces per warp step.
+                              // Measured on B200 (profiles/r01c_kernel_variants.md): 8 lanes = 9.1 ms on the headline batch,
+                              // 16 = 9.7 ms, 32 = 11.3 ms; choosing per group between 8 and 32 spills and loses (12.7 ms)
 #endif
 #ifndef BRO_COPY_DEPTH
 #define BRO_COPY_DEPTH 4      // rounds of 32 units in flight per warp; 1 KiB of staging per round and warp
@@ -84,6 +87,39 @@ __device__ __forceinline__ void bro_warp_copy(uint8_t* dst, const uint8_t* src, 
     for (uint32_t v = lane; v < nv; v += 32u) *(uint4*)(dst + 16u * v) = bro_ldu16(src + 16u * v);
     const uint32_t done = nv << 4;
     if (done + lane < n) dst[done + lane] = src[done + lane];
+}
+
+// A group of LONG records [j, e) (lane k holds record k: destination offset, geometry word, source address): G lanes
+// move one piece, so the warp moves PP = 32 / G pieces per step, with ROUNDS steps in flight (all loads are issued
+// before the first store).  Nothing in a group is ordered.
+template <int G>
+__device__ __forceinline__ void bro_run_pieces(uint8_t* out, uint32_t dst, uint32_t geo, uint32_t sp_lo, uint32_t sp_hi,
+                                               unsigned lane, uint32_t j, uint32_t e) {
+    constexpr int PP = 32 / G, ROUNDS = (BRO_COPY_PIECES + PP - 1) / PP;
+    const uint32_t bl = lane & (uint32_t)(G - 1), sub = lane / (uint32_t)G;
+    for (uint32_t k0 = j; k0 < e; k0 += (uint32_t)(PP * ROUNDS)) {
+        BroPieceData<G> D[ROUNDS];
+        uint32_t m_dst[ROUNDS], m_geo[ROUNDS];
+#pragma unroll
+        for (int r = 0; r < ROUNDS; r++) {
+            m_geo[r] = 0;
+            if (k0 + (uint32_t)(PP * r) >= e) continue;                  // warp-uniform
+            const uint32_t k = k0 + (uint32_t)(PP * r) + sub;            // this lane group's piece
+            const int ks = (int)(k & 31u);
+            uint32_t g = __shfl_sync(0xffffffffu, geo, ks);
+            const uintptr_t s0 = (uintptr_t)__shfl_sync(0xffffffffu, sp_lo, ks) |
+                                 ((uintptr_t)__shfl_sync(0xffffffffu, sp_hi, ks) << 32);
+            m_dst[r] = __shfl_sync(0xffffffffu, dst, ks);
+            if (PP > 1 && k >= e) g = 0;                                 // the group ends inside this step
+            m_geo[r] = g;
+            bro_piece_load<G>(D[r], (const uint8_t*)s0, g, bl);
+        }
+#pragma unroll
+        for (int r = 0; r < ROUNDS; r++) {
+            if (k0 + (uint32_t)(PP * r) >= e) continue;                  // warp-uniform
+            bro_piece_store<G>(D[r], out + m_dst[r], m_geo[r], bl);
+        }
+    }
 }
 
 template <int WARPS>
@@ -175,32 +211,7 @@ __global__ void __launch_bounds__(WARPS * 32, BRO_COPY_MIN_BLOCKS) bro_copy_kern
                     const uint8_t* sp = kind == BRO_REC_STORED ? in + a : (const uint8_t*)out + (dst - a);
                     const uint32_t sp_lo = (uint32_t)(uintptr_t)sp, sp_hi = (uint32_t)((uintptr_t)sp >> 32);
                     const uint32_t geo = bro_piece_geo(dst + out_mis, sp_lo, len);
-                    // BRO_COPY_GROUP lanes per piece: the warp moves PP pieces per step, ROUNDS steps in flight
-                    constexpr int G = BRO_COPY_GROUP, PP = 32 / G, ROUNDS = (BRO_COPY_PIECES + PP - 1) / PP;
-                    const uint32_t bl = lane & (uint32_t)(G - 1), sub = lane / (uint32_t)G;
-                    for (uint32_t k0 = j; k0 < e; k0 += (uint32_t)(PP * ROUNDS)) {
-                        BroPieceData<G> D[ROUNDS];
-                        uint32_t m_dst[ROUNDS], m_geo[ROUNDS];
-#pragma unroll
-                        for (int r = 0; r < ROUNDS; r++) {
-                            m_geo[r] = 0;
-                            if (k0 + (uint32_t)(PP * r) >= e) continue;                  // warp-uniform
-                            const uint32_t k = k0 + (uint32_t)(PP * r) + sub;            // this lane group's piece
-                            const int ks = (int)(k & 31u);
-                            uint32_t g = __shfl_sync(0xffffffffu, geo, ks);
-                            const uintptr_t s0 = (uintptr_t)__shfl_sync(0xffffffffu, sp_lo, ks) |
-                                                 ((uintptr_t)__shfl_sync(0xffffffffu, sp_hi, ks) << 32);
-                            m_dst[r] = __shfl_sync(0xffffffffu, dst, ks);
-                            if (PP > 1 && k >= e) g = 0;                                 // the group ends inside this step
-                            m_geo[r] = g;
-                            bro_piece_load<G>(D[r], (const uint8_t*)s0, g, bl);
-                        }
-#pragma unroll
-                        for (int r = 0; r < ROUNDS; r++) {
-                            if (k0 + (uint32_t)(PP * r) >= e) continue;                  // warp-uniform
-                            bro_piece_store<G>(D[r], out + m_dst[r], m_geo[r], bl);
-                        }
-                    }
+                    bro_run_pieces<BRO_COPY_GROUP>(out, dst, geo, sp_lo, sp_hi, lane, j, e);
                     j = e;
                     continue;
                 }
