@@ -90,7 +90,8 @@ extern "C" void bro_hostsim_copy_exec(uint8_t* out, const uint8_t* in, const uin
                     sp[l] = r[l].kind == BRO_REC_STORED ? in + r[l].a : (const uint8_t*)out + (r[l].dst - r[l].a);
                     geo[l] = bro_piece_geo(r[l].dst + out_mis, (uint32_t)(uintptr_t)sp[l], r[l].len);
                 }
-                if (group == 8) run_pieces<8>(out, in, r, geo, sp, j, e);
+                if (group == 4) run_pieces<4>(out, in, r, geo, sp, j, e);
+                else if (group == 8) run_pieces<8>(out, in, r, geo, sp, j, e);
                 else if (group == 16) run_pieces<16>(out, in, r, geo, sp, j, e);
                 else run_pieces<32>(out, in, r, geo, sp, j, e);
                 st[0]++;

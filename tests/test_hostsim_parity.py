@@ -190,7 +190,7 @@ def test_parse_sizing_mode():
     assert known >= 600
 
 
-@pytest.mark.parametrize("group", [32, 16, 8])
+@pytest.mark.parametrize("group", [32, 16, 8, 4])
 def test_copy_phase_lane_code(group):
     """phase two as the copy kernel executes it: 32 records at a time, groups of independent records, long records piece
     by piece through the kernel's own lane code (bro_copy_piece.h) with `group` lanes per piece, all loads of a step
