@@ -67,12 +67,11 @@ extern "C" int bro_ctx_create(bro_ctx** out, int device) {
     *out = NULL;
     bro_ctx* ctx = (bro_ctx*)calloc(1, sizeof(bro_ctx));
     if (!ctx) return BRO_ST_InvalidArgument;
-    cudaError_t e;
-    if (device < 0) { if ((e = cudaGetDevice(&device)) != cudaSuccess) { free(ctx); return BRO_ST_CudaError; } }
-    if ((e = cudaSetDevice(device)) != cudaSuccess) { free(ctx); return BRO_ST_CudaError; }
+    if (device < 0 && cudaGetDevice(&device) != cudaSuccess) { free(ctx); return BRO_ST_CudaError; }
+    if (cudaSetDevice(device) != cudaSuccess) { free(ctx); return BRO_ST_CudaError; }
     ctx->device = device;
     cudaDeviceProp prop;
-    if ((e = cudaGetDeviceProperties(&prop, device)) != cudaSuccess) { free(ctx); return BRO_ST_CudaError; }
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) { free(ctx); return BRO_ST_CudaError; }
     ctx->num_sms = prop.multiProcessorCount;
     int per_sm = 0, per_sm_t = 0, per_sm_c = 0;
     if (bro_warp_kernel_occupancy(&per_sm) != 0 || per_sm < 1 ||
@@ -108,11 +107,11 @@ extern "C" int bro_ctx_create(bro_ctx** out, int device) {
     if (env && !strcmp(env, "warp")) ctx->mode = BRO_MODE_WARP;
     if (env && (!strcmp(env, "twophase") || !strcmp(env, "thread"))) ctx->mode = BRO_MODE_TWOPHASE;
     size_t arena = (size_t)ctx->num_warps * bro_warp_kernel_arena_bytes();
-    if ((e = cudaMalloc(&ctx->d_arena, arena)) != cudaSuccess ||
-        (e = cudaMalloc(&ctx->d_dict, BRO_DICT_BYTES)) != cudaSuccess ||
-        (e = cudaMalloc(&ctx->d_counter, 16 * sizeof(uint32_t))) != cudaSuccess ||
-        (e = cudaMalloc(&ctx->d_order_scratch, 512 * sizeof(uint32_t))) != cudaSuccess ||
-        (e = cudaMemcpy(ctx->d_dict, bro_dictionary_blob, BRO_DICT_BYTES, cudaMemcpyHostToDevice)) != cudaSuccess) {
+    if (cudaMalloc(&ctx->d_arena, arena) != cudaSuccess ||
+        cudaMalloc(&ctx->d_dict, BRO_DICT_BYTES) != cudaSuccess ||
+        cudaMalloc(&ctx->d_counter, 16 * sizeof(uint32_t)) != cudaSuccess ||
+        cudaMalloc(&ctx->d_order_scratch, 512 * sizeof(uint32_t)) != cudaSuccess ||
+        cudaMemcpy(ctx->d_dict, bro_dictionary_blob, BRO_DICT_BYTES, cudaMemcpyHostToDevice) != cudaSuccess) {
         cudaFree(ctx->d_arena); cudaFree(ctx->d_arena_t); cudaFree(ctx->d_dict); cudaFree(ctx->d_counter); cudaFree(ctx->d_order_scratch);
         free(ctx);
         return BRO_ST_CudaError;
@@ -289,6 +288,7 @@ extern "C" int bro_batch_decode(bro_ctx* ctx, const uint8_t* d_in, const uint64_
         p.retry_mode = 1;
     }
     p.arena = ctx->d_arena; p.counter = ctx->d_counter + 1;
+    p.order = two_phase ? ctx->d_order : NULL;       // size-class order of the batch (largest first) when it was computed
     if (ctx->timing) BRO_CUDA(ctx, cudaEventRecord(ctx->ev[3], s));
     e = (cudaError_t)bro_warp_kernel_launch(&p, grid_w, s);
     if (e != cudaSuccess) return bro_fail(ctx, e, "bro_decode_warp_kernel launch");

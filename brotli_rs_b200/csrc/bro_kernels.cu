@@ -32,7 +32,12 @@ __global__ void __launch_bounds__(WARPS * 32, BRO_MIN_BLOCKS) bro_decode_warp_ke
     if (retry && *p.retry_count == 0u) return;
     for (;;) {
         uint32_t i = 0;
-        if (lane == 0) i = atomicAdd(p.counter, 1u);
+        if (lane == 0) {
+            i = atomicAdd(p.counter, 1u);
+            // after the ordering kernels (two-phase path, AUTO's gate): longest streams first, so that the batch does not
+            // end on a 900 KB stream that was handed out last
+            if (p.order && i < p.n) i = p.order[i];
+        }
         i = bro_shfl(i, 0);
         if (i >= p.n) break;
         if (retry && !BRO_ST_IS_RETRY(p.status[i])) continue;
