@@ -58,6 +58,13 @@ def synthetic_raw(kind, seed, size):
     raise ValueError(kind)
 
 
+def far_reference_raw(seed=5, block=200000, gap=15_500_000):
+    """A payload whose second half repeats a random block `block + gap` bytes (15.7 MB) back: with lgwin = 24 (window
+    16 MiB - 16, the format's maximum) libbrotli at quality 9 encodes it as back-references at distance 15,700,000."""
+    blk = np.random.default_rng(seed).integers(0, 256, block, dtype=np.uint8).tobytes()
+    return blk + bytes(gap) + blk + blk[:5000]
+
+
 WORKLOADS = {
     # name: (payload kind, raw bytes per stream, seed base, quality, lgwin, description)
     "c4_highratio_w16": ("repeat2k", 262144, 1000, 5, 16,

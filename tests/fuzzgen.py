@@ -33,4 +33,4 @@ def mutations(corpus, seed, count, max_len=70000):
         yield bytes(base[:max_len])
 
 
-from brotli_rs_b200.workloads import compress, libbrotli_enc, synthetic_raw  # noqa: E402,F401
+from brotli_rs_b200.workloads import compress, far_reference_raw, libbrotli_enc, synthetic_raw  # noqa: E402,F401

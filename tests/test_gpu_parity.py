@@ -418,6 +418,18 @@ def test_decode_without_size_hints():
     d.close()
 
 
+def test_largest_window_far_reference(dec):
+    """WBITS = 24 with back-references 15,700,000 bytes back (the largest window), both paths,
+    next to small streams in the same batch"""
+    enc = fuzzgen.libbrotli_enc()
+    if enc is None:
+        pytest.skip("system libbrotlienc not present")
+    raw = fuzzgen.far_reference_raw()
+    comp = fuzzgen.compress(enc, raw, 9, 24)
+    small = open(os.path.join(DATA, "quickfox_repeated.compressed"), "rb").read()
+    check_batch(dec, [small, comp, small, comp], [176128, len(raw), 176128, len(raw)], "far reference")
+
+
 # ---- streaming: the resumable decode and the streaming Read-struct (SURVEY section 8 f.1) ----
 
 def test_streaming_reader_corpus():

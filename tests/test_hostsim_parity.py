@@ -283,3 +283,22 @@ def test_stream_resume_fresh_streams():
             comp = fuzzgen.compress(enc, raw, q, lgwin)
             st, served, calls, max_in, max_out = hostsim.stream_decode(comp, [1500], out_cap=1 << 12)
             assert (st, served) == (0, raw), (kind, q, lgwin, st, len(served))
+
+
+def test_largest_window_far_reference():
+    """WBITS = 24, back-references 15,700,000 bytes back (the window's limit is 16 MiB - 16): fused logic, phase one +
+    the copy kernel's lane code, and the streaming loop (whose history is then a whole window)"""
+    enc = fuzzgen.libbrotli_enc()
+    if enc is None:
+        pytest.skip("system libbrotlienc not present")
+    raw = fuzzgen.far_reference_raw()
+    comp = fuzzgen.compress(enc, raw, 9, 24)
+    assert oracle.decode(comp) == (0, raw)
+    assert hostsim.decode(comp, cap=len(raw)) == (0, raw)
+    st, recs, _, out = hostsim.parse_records(comp, cap=len(raw))
+    assert (st, out) == (0, raw) and max(a for _, _, k, a in recs if k == 0) == 15_700_000
+    with hostsim.copy_group(8):
+        st, out, _, _ = hostsim.parse_decode(comp, cap=len(raw), mis=9)
+    assert (st, out) == (0, raw)
+    st, served, calls, max_in, max_out = hostsim.stream_decode(comp, [1 << 16], out_cap=1 << 20)
+    assert (st, served) == (0, raw) and max_out <= 1 << 25
