@@ -104,3 +104,89 @@ BRO_PIECE_FN void bro_piece_store(const BroPieceData<G>& d, uint8_t* dp, uint32_
     }
 #undef BRO_PIECE_VECTORS
 }
+
+// ------------------------------------------------------------------------------------------------------
+// The STAGED form of the same piece (BRO_COPY_STAGED; not the shipped configuration -- see profiles/r01c_kernel_variants.md):
+// the source of a piece goes through a slot of shared memory instead of registers.  bro_piece_issue starts the copy of
+// every aligned 16-byte granule that holds a source byte of the piece into the slot (cp.async on the device: no
+// register holds the data, so a lane can have the granules of several pieces in flight); bro_piece_consume, once they
+// have landed, realigns from the slot and stores.  A slot holds BRO_STAGE_SLOT_BYTES: (15 + 15 + 512 + 15 + 15) / 16 = 35
+// granules at most, rounded to 36.
+// ------------------------------------------------------------------------------------------------------
+#define BRO_STAGE_SLOT_BYTES 576u
+
+#if defined(__CUDACC__)
+typedef uint32_t bro_stage_ptr;                        // shared-memory address
+BRO_PIECE_FN void bro_stage_fetch16(bro_stage_ptr dst, const void* src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(dst), "l"(src) : "memory");
+}
+BRO_PIECE_FN bro_v16 bro_stage_ld16(bro_stage_ptr a) {
+    bro_v16 v;
+    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a));
+    return v;
+}
+BRO_PIECE_FN uint32_t bro_stage_ld8(bro_stage_ptr a) {
+    uint32_t v;
+    asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(a));
+    return v;
+}
+#else
+typedef uint8_t* bro_stage_ptr;
+BRO_PIECE_FN void bro_stage_fetch16(bro_stage_ptr dst, const void* src) { *(bro_v16*)dst = *(const bro_v16*)src; }
+BRO_PIECE_FN bro_v16 bro_stage_ld16(bro_stage_ptr a) { return *(const bro_v16*)a; }
+BRO_PIECE_FN uint32_t bro_stage_ld8(bro_stage_ptr a) { return *a; }
+#endif
+
+// (address of the piece's first source byte) & 15, from the geometry word: sh = (s0 + head) & 15
+#define BRO_GEO_SRC_MIS(g) ((BRO_GEO_SHIFT(g) - BRO_GEO_HEAD(g)) & 15u)
+
+// Start fetching the granules of the piece into `slot` (16-byte aligned): lane bl of the group takes granules bl, bl + G, ...
+// Every granule fetched holds at least one source byte of the piece, i.e. lies inside the allocation of the source.
+template <int G>
+BRO_PIECE_FN void bro_piece_issue(bro_stage_ptr slot, const uint8_t* s0, uint32_t g, uint32_t bl) {
+    if (g == 0u) return;
+    const uint32_t len = BRO_GEO_HEAD(g) + 16u * BRO_GEO_NVEC(g) + BRO_GEO_TAIL(g);
+    const uint32_t granules = (BRO_GEO_SRC_MIS(g) + len + 15u) >> 4;
+    const uint8_t* gb = (const uint8_t*)((uintptr_t)s0 & ~(uintptr_t)15);
+#pragma unroll
+    for (int i = 0; i < (36 + G - 1) / G; i++) {
+        const uint32_t k = bl + (uint32_t)(G * i);
+        if (k < granules) bro_stage_fetch16(slot + 16u * k, gb + 16u * k);
+    }
+}
+
+// The slot holds the piece's source bytes from offset BRO_GEO_SRC_MIS(g) on.  dp: address of the first destination byte.
+template <int G>
+BRO_PIECE_FN void bro_piece_consume(bro_stage_ptr slot, uint8_t* dp, uint32_t g, uint32_t bl) {
+    const uint32_t head = BRO_GEO_HEAD(g), nvec = BRO_GEO_NVEC(g), tail = BRO_GEO_TAIL(g), sh = BRO_GEO_SHIFT(g);
+    const uint32_t mis = BRO_GEO_SRC_MIS(g);
+#pragma unroll
+    for (int i = 0; i < 32 / G; i++) {
+        const uint32_t rs = bl + (uint32_t)(G * i);
+        const bool back = rs >= 16u;
+        const uint32_t b = rs & 15u;
+        if (b < (back ? tail : head)) {
+            const uint32_t o = (back ? head + 16u * nvec : 0u) + b;
+            dp[o] = (uint8_t)bro_stage_ld8(slot + mis + o);
+        }
+    }
+    // vector v lies `sh` bytes into granule (mis + head) / 16 + v of the slot
+    const bro_stage_ptr base = slot + 16u * ((mis + head) >> 4) + 16u * bl;
+    bro_v16* const dv = (bro_v16*)(dp + head) + bl;
+    const unsigned bs = 8u * (sh & 3u);
+#define BRO_PIECE_VECTORS(EXPR)                                                         \
+    _Pragma("unroll") for (int i = 0; i < 32 / G; i++)                                  \
+        if (bl + (uint32_t)(G * i) < nvec) {                                            \
+            const bro_v16 A = bro_stage_ld16(base + 16u * (uint32_t)(G * i));           \
+            const bro_v16 B = sh ? bro_stage_ld16(base + 16u * (uint32_t)(G * i) + 16u) : A;   \
+            dv[G * i] = (EXPR);                                                         \
+        }
+    if (sh == 0u) { BRO_PIECE_VECTORS(A) }
+    else switch (sh >> 2) {
+        case 0: BRO_PIECE_VECTORS(bro_funnel16<0>(A, B, bs)) break;
+        case 1: BRO_PIECE_VECTORS(bro_funnel16<1>(A, B, bs)) break;
+        case 2: BRO_PIECE_VECTORS(bro_funnel16<2>(A, B, bs)) break;
+        default: BRO_PIECE_VECTORS(bro_funnel16<3>(A, B, bs)) break;
+    }
+#undef BRO_PIECE_VECTORS
+}

@@ -50,9 +50,39 @@ void run_pieces(uint8_t* out, const uint8_t* in, const Rec* r, const uint32_t* g
     }
 }
 
+#ifndef BRO_COPY_QUADS
+#define BRO_COPY_QUADS 2       // as in bro_kernels_copy.cu
+#endif
+
+// bro_run_pieces_staged of bro_kernels_copy.cu, trip by trip: issue step q (every lane), then consume step q - (NQ - 1)
+template <int G>
+void run_pieces_staged(uint8_t* out, const Rec* r, const uint32_t* geo, const uint8_t* const* sp, uint32_t j, uint32_t e) {
+    constexpr int PP = 32 / G, NQ = BRO_COPY_QUADS;
+    alignas(16) static uint8_t stage[NQ * PP * BRO_STAGE_SLOT_BYTES];
+    const uint32_t nq = (e - j + (uint32_t)PP - 1u) / (uint32_t)PP;
+    for (uint32_t q = 0; q < nq + (uint32_t)(NQ - 1); q++) {
+        if (q < nq)
+            for (uint32_t lane = 0; lane < 32u; lane++) {
+                const uint32_t bl = lane & (uint32_t)(G - 1), sub = lane / (uint32_t)G;
+                const uint32_t k = j + q * (uint32_t)PP + sub, ks = k & 31u;
+                const uint32_t g = k >= e ? 0u : geo[ks];
+                bro_piece_issue<G>(stage + ((q % (uint32_t)NQ) * (uint32_t)PP + sub) * BRO_STAGE_SLOT_BYTES, sp[ks], g, bl);
+            }
+        if (q + 1u < (uint32_t)NQ) continue;
+        const uint32_t c = q - (uint32_t)(NQ - 1);
+        for (uint32_t lane = 0; lane < 32u; lane++) {
+            const uint32_t bl = lane & (uint32_t)(G - 1), sub = lane / (uint32_t)G;
+            const uint32_t k = j + c * (uint32_t)PP + sub, ks = k & 31u;
+            const uint32_t g = k >= e ? 0u : geo[ks];
+            bro_piece_consume<G>(stage + ((c % (uint32_t)NQ) * (uint32_t)PP + sub) * BRO_STAGE_SLOT_BYTES, out + r[ks].dst, g, bl);
+        }
+    }
+}
+
 }  // namespace
 
-// words: the records as phase one wrote them (4 x uint32 each).  group = lanes per piece (32, 16, 8).
+// words: the records as phase one wrote them (4 x uint32 each).  group = lanes per piece (32, 16, 8, 4); + 100 = the staged
+// form of the long-record path (BRO_COPY_STAGED) with that many lanes per piece.
 // stats (optional, 3 words): groups executed by the piece path / as short records / periodic fills.
 extern "C" void bro_hostsim_copy_exec(uint8_t* out, const uint8_t* in, const uint32_t* words, uint32_t nrec, int group, uint32_t* stats) {
     const uint32_t out_mis = (uint32_t)((uintptr_t)out & 15u);
@@ -90,7 +120,10 @@ extern "C" void bro_hostsim_copy_exec(uint8_t* out, const uint8_t* in, const uin
                     sp[l] = r[l].kind == BRO_REC_STORED ? in + r[l].a : (const uint8_t*)out + (r[l].dst - r[l].a);
                     geo[l] = bro_piece_geo(r[l].dst + out_mis, (uint32_t)(uintptr_t)sp[l], r[l].len);
                 }
-                if (group == 4) run_pieces<4>(out, in, r, geo, sp, j, e);
+                if (group == 108) run_pieces_staged<8>(out, r, geo, sp, j, e);
+                else if (group == 116) run_pieces_staged<16>(out, r, geo, sp, j, e);
+                else if (group == 132) run_pieces_staged<32>(out, r, geo, sp, j, e);
+                else if (group == 4) run_pieces<4>(out, in, r, geo, sp, j, e);
                 else if (group == 8) run_pieces<8>(out, in, r, geo, sp, j, e);
                 else if (group == 16) run_pieces<16>(out, in, r, geo, sp, j, e);
                 else run_pieces<32>(out, in, r, geo, sp, j, e);

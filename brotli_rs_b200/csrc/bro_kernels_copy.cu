@@ -41,6 +41,12 @@
                               // Measured on B200 (profiles/r01c_kernel_variants.md): 8 lanes = 9.1 ms on the headline batch,
                               // 16 = 9.7 ms, 32 = 11.3 ms; choosing per group between 8 and 32 spills and loses (12.7 ms)
 #endif
+#ifndef BRO_COPY_STAGED
+#define BRO_COPY_STAGED 0     // 1: long records go through shared memory (bro_run_pieces_staged) -- prepared, NOT measured yet
+#endif
+#ifndef BRO_COPY_QUADS
+#define BRO_COPY_QUADS 2      // staged path: warp steps (of 32 / GROUP pieces) in flight
+#endif
 #ifndef BRO_COPY_DEPTH
 #define BRO_COPY_DEPTH 4      // rounds of 32 units in flight per warp; 1 KiB of staging per round and warp
 #endif
@@ -122,14 +128,57 @@ __device__ __forceinline__ void bro_run_pieces(uint8_t* out, uint32_t dst, uint3
     }
 }
 
+// The same group through shared memory (BRO_COPY_STAGED): no register holds a piece's data between its loads and its
+// stores, so the granules of BRO_COPY_QUADS warp steps are in flight at once -- step q + QUADS - 1 is issued before step q
+// is consumed -- and the kernel needs far fewer registers.  stage: this warp's QUADS * (32 / G) slots.
+__device__ __forceinline__ void bro_cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void bro_cp_async_wait_group() { asm volatile("cp.async.wait_group %0;" :: "n"(N) : "memory"); }
+
+template <int G>
+__device__ __forceinline__ void bro_run_pieces_staged(uint8_t* out, uint32_t dst, uint32_t geo, uint32_t sp_lo, uint32_t sp_hi,
+                                                      unsigned lane, uint32_t j, uint32_t e, uint32_t stage) {
+    constexpr int PP = 32 / G, NQ = BRO_COPY_QUADS;
+    const uint32_t bl = lane & (uint32_t)(G - 1), sub = lane / (uint32_t)G;
+    const uint32_t nq = (e - j + (uint32_t)PP - 1u) / (uint32_t)PP;
+    for (uint32_t q = 0; q < nq + (uint32_t)(NQ - 1); q++) {
+        if (q < nq) {                                                    // warp-uniform: issue step q
+            const uint32_t k = j + q * (uint32_t)PP + sub;
+            const int ks = (int)(k & 31u);
+            uint32_t g = __shfl_sync(0xffffffffu, geo, ks);
+            const uintptr_t s0 = (uintptr_t)__shfl_sync(0xffffffffu, sp_lo, ks) |
+                                 ((uintptr_t)__shfl_sync(0xffffffffu, sp_hi, ks) << 32);
+            if (k >= e) g = 0;
+            bro_piece_issue<G>(stage + ((q % (uint32_t)NQ) * (uint32_t)PP + sub) * BRO_STAGE_SLOT_BYTES, (const uint8_t*)s0, g, bl);
+        }
+        bro_cp_async_commit();                                           // one group per trip (an empty one behind the last step)
+        if (q + 1u < (uint32_t)NQ) continue;                             // warp-uniform: the pipeline is filling
+        const uint32_t c = q - (uint32_t)(NQ - 1);                       // consume step c: everything but the NQ - 1 youngest groups has landed
+        bro_cp_async_wait_group<NQ - 1>();
+        __syncwarp();                                                    // ... for every lane of the warp
+        const uint32_t k = j + c * (uint32_t)PP + sub;
+        const int ks = (int)(k & 31u);
+        uint32_t g = __shfl_sync(0xffffffffu, geo, ks);
+        const uint32_t d = __shfl_sync(0xffffffffu, dst, ks);
+        if (k >= e) g = 0;
+        bro_piece_consume<G>(stage + ((c % (uint32_t)NQ) * (uint32_t)PP + sub) * BRO_STAGE_SLOT_BYTES, out + d, g, bl);
+        __syncwarp();                                                    // the slots of step c are free for step c + NQ
+    }
+}
+
 template <int WARPS>
 __global__ void __launch_bounds__(WARPS * 32, BRO_COPY_MIN_BLOCKS) bro_copy_kernel(BroLaunch p) {
     if (p.gate && p.gate[1]) return;       // AUTO: this batch goes to the fused kernel as a whole
     const unsigned lane = threadIdx.x & 31u;
     // staging: per warp BRO_COPY_DEPTH rounds x 32 lanes x 32 bytes (the two aligned 16-byte granules that hold a
     // unit's 16 source bytes)
-    __shared__ __align__(16) uint8_t stage[WARPS * BRO_COPY_DEPTH * 32 * 32];
-    const uint32_t stage_base = (uint32_t)__cvta_generic_to_shared(stage) + (threadIdx.x >> 5) * (BRO_COPY_DEPTH * 32u * 32u);
+    // (the staged long-record path uses the same bytes as BRO_COPY_QUADS * (32 / GROUP) piece slots; a warp is in one
+    // path at a time)
+    constexpr uint32_t STAGE_SHORT = BRO_COPY_DEPTH * 32u * 32u;
+    constexpr uint32_t STAGE_LONG = BRO_COPY_STAGED ? BRO_COPY_QUADS * (32u / BRO_COPY_GROUP) * BRO_STAGE_SLOT_BYTES : 0u;
+    constexpr uint32_t STAGE_WARP = STAGE_SHORT > STAGE_LONG ? STAGE_SHORT : STAGE_LONG;
+    __shared__ __align__(16) uint8_t stage[WARPS * STAGE_WARP];
+    const uint32_t stage_base = (uint32_t)__cvta_generic_to_shared(stage) + (threadIdx.x >> 5) * STAGE_WARP;
     // Streams come from the parse kernel's completion queue: a warp takes a ticket (one ahead of the stream it works on)
     // and waits until the slot of that ticket holds a stream index -- immediately, when the parse kernel has already
     // ended; with the two kernels side by side this is where the copy kernel follows the parse kernel's progress.  A
@@ -211,7 +260,11 @@ __global__ void __launch_bounds__(WARPS * 32, BRO_COPY_MIN_BLOCKS) bro_copy_kern
                     const uint8_t* sp = kind == BRO_REC_STORED ? in + a : (const uint8_t*)out + (dst - a);
                     const uint32_t sp_lo = (uint32_t)(uintptr_t)sp, sp_hi = (uint32_t)((uintptr_t)sp >> 32);
                     const uint32_t geo = bro_piece_geo(dst + out_mis, sp_lo, len);
+#if BRO_COPY_STAGED
+                    bro_run_pieces_staged<BRO_COPY_GROUP>(out, dst, geo, sp_lo, sp_hi, lane, j, e, stage_base);
+#else
                     bro_run_pieces<BRO_COPY_GROUP>(out, dst, geo, sp_lo, sp_hi, lane, j, e);
+#endif
                     j = e;
                     continue;
                 }

@@ -190,11 +190,12 @@ def test_parse_sizing_mode():
     assert known >= 600
 
 
-@pytest.mark.parametrize("group", [32, 16, 8, 4])
+@pytest.mark.parametrize("group", [32, 16, 8, 4, 108, 116, 132])
 def test_copy_phase_lane_code(group):
     """phase two as the copy kernel executes it: 32 records at a time, groups of independent records, long records piece
     by piece through the kernel's own lane code (bro_copy_piece.h) with `group` lanes per piece, all loads of a step
-    before its first store; short groups last record first.  Bytes must equal the oracle's."""
+    before its first store (group > 100: the staged form, issue / consume through slots with two steps in flight); short
+    groups last record first.  Bytes must equal the oracle's."""
     enc = fuzzgen.libbrotli_enc()
     if enc is None:
         pytest.skip("system libbrotlienc not present")
