@@ -129,3 +129,60 @@ def test_corpus_driver_matches_oracle(tmp_path):
     for args in ([], ["--batch"]):
         r = subprocess.run([exe] + args + [DATA], capture_output=True, text=True)
         assert r.returncode == 0 and r.stdout == want, (args, r.stdout[:600], r.stderr[-300:])
+
+
+# ---- the host-side C++ code on CPU, against tests/mock_abi.c (the oracle stands in for the device library) ----
+
+def _build_mock(tmp):
+    """-> directory holding a libbrotli_b200.so that is the mock (CPU test-suite only; see tests/mock_abi.c)"""
+    from oracle import oracle
+    oracle.lib()
+    d = os.path.join(tmp, "mock")
+    os.makedirs(d, exist_ok=True)
+    odir = os.path.join(ROOT, "oracle")
+    subprocess.check_call(["gcc", "-O1", "-shared", "-fPIC", os.path.join(ROOT, "tests", "mock_abi.c"), "-o",
+                           os.path.join(d, "libbrotli_b200.so"), "-L" + odir, "-l:liboracle.so", "-Wl,-rpath," + odir])
+    return d
+
+
+def _want_driver_output(names):
+    from oracle import oracle
+    want = ""
+    for fn in names:
+        st, out = oracle.decode(open(os.path.join(DATA, fn), "rb").read())
+        res = "Ok(%d)" % len(out) if st == 0 else 'Err(Custom { kind: InvalidData, error: "%s" })' % oracle.lib().bro_oracle_status_description(st).decode()
+        want += '"%s":\noutput length = %d\nres = %s\n===========\n\n' % (os.path.join(DATA, fn), len(out) if st == 0 else 0, res)
+    return want
+
+
+def test_host_code_against_mock_library(tmp_path):
+    """brotli::Decompressor (whole-stream and streaming constructors), read_to_end, brotli::decode_batch and the corpus
+    driver, compiled against the mock: the text the driver prints for the corpus (per file and --batch) is the
+    reference's three lines per file with the oracle's lengths and error strings"""
+    mock = _build_mock(str(tmp_path))
+    inc = os.path.join(ROOT, "include")
+    drv = os.path.join(str(tmp_path), "corpus_driver_mock")
+    subprocess.check_call(["g++", "-std=c++17", "-O1", "-I", inc, os.path.join(ROOT, "tools", "corpus_driver.cpp"), "-o", drv,
+                           "-L" + mock, "-lbrotli_b200", "-Wl,-rpath," + mock])
+    names = sorted(fn for fn in os.listdir(DATA) if fn.endswith("compressed"))
+    want = _want_driver_output(names)
+    for args in ([], ["--batch"]):
+        r = subprocess.run([drv] + args + [DATA], capture_output=True, text=True)
+        assert r.returncode == 0 and r.stdout == want, (args, r.stdout[:400], r.stderr[-300:])
+    r = subprocess.run([drv, os.path.join(DATA, "no_such_dir")], capture_output=True, text=True)
+    assert r.returncode == 2
+    # the twin program of this file: doc-test, error text, streaming constructor, batch
+    src, exe = os.path.join(str(tmp_path), "twin_mock.cpp"), os.path.join(str(tmp_path), "twin_mock")
+    open(src, "w").write(SRC)
+    subprocess.check_call(["g++", "-std=c++17", "-O1", "-I", inc, src, "-o", exe, "-L" + mock, "-lbrotli_b200", "-Wl,-rpath," + mock])
+    r = subprocess.run([exe, os.path.join(DATA, "64x.compressed"), os.path.join(DATA, "64x")], capture_output=True, text=True)
+    assert r.returncode == 0 and r.stdout.startswith("EQUAL 64"), r.stdout + r.stderr
+    r = subprocess.run([exe, os.path.join(DATA, "frewsxcv_06.compressed"), os.path.join(DATA, "64x")], capture_output=True, text=True)
+    assert r.returncode == 3 and "ERR 23 Run length excceeded" in r.stdout, r.stdout + r.stderr
+    r = subprocess.run([exe, "stream", os.path.join(DATA, "metablock_reset.compressed"), os.path.join(DATA, "metablock_reset"), "2000"],
+                       capture_output=True, text=True)
+    assert r.returncode == 0 and r.stdout.startswith("EQUAL 912868"), r.stdout + r.stderr
+    bn = ["64x", "alice29.txt", "quickfox_repeated", "random_org_10k.bin", "empty"]
+    r = subprocess.run([exe, "batch"] + [os.path.join(DATA, n + ".compressed") for n in bn] + [os.path.join(DATA, "frewsxcv_06.compressed")],
+                       capture_output=True, text=True)
+    assert r.returncode == 0 and r.stdout.split("\n")[:6] == ["0 %d" % os.path.getsize(os.path.join(DATA, n)) for n in bn] + ["23 0"], r.stdout + r.stderr
