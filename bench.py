@@ -130,7 +130,7 @@ class ClockSampler:
 
 
 DEFAULT_STREAMS = {"c4_highratio_w16": 100000, "c5_stored_10k": 100000, "c5b_literals_10k": 100000,
-                   "c2_quickfox_x10k": 10000, "c3_corpus_x1000": 52000}
+                   "c2_quickfox_x10k": 10000, "c3_corpus_x1000": 52000, "c1_alice29_single": 1}
 
 
 def build_workload(name, n_streams):
@@ -138,7 +138,12 @@ def build_workload(name, n_streams):
     expected status, and the tiling of the distinct streams into the batch."""
     from brotli_rs_b200 import workloads as w
     data = os.path.join(ROOT, "tests", "golden", "data")
-    if name == "c2_quickfox_x10k":
+    if name == "c1_alice29_single":
+        # BASELINE configs[0]: one stream, the reference's own CPU-runnable case (plumbing and single-stream latency)
+        _, streams, raws, status = w.corpus_workload(data, only={"alice29.txt.compressed"})
+        desc = "data/alice29.txt.compressed, one stream (50,096 B -> 152,089 B)"
+        gidx = np.zeros(n_streams, dtype=np.int64)
+    elif name == "c2_quickfox_x10k":
         _, streams, raws, status = w.corpus_workload(data, only={"quickfox_repeated.compressed"})
         desc = "copies of data/quickfox_repeated.compressed (58 B -> 176,128 B, one overlapping copy at distance 43)"
         gidx = np.zeros(n_streams, dtype=np.int64)
@@ -182,9 +187,9 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
-    cores = os.cpu_count() or 1
     world = int(os.environ.get("WORLD_SIZE", "1"))
     n_streams = (args.streams or DEFAULT_STREAMS[args.workload]) * (world if args.scaling == "weak" else 1)
+    cores = min(os.cpu_count() or 1, n_streams)          # a stream is decoded by one thread
     wl = build_workload(args.workload, n_streams)
     desc = wl["desc"]
     sample = args.cpu_sample_streams or cpu_sample_size(wl, cores, 1.5, n_streams)
@@ -405,7 +410,7 @@ def main():
     # ---- CPU baseline (rank 0, N = 1 only): the oracle port on the host cores, bounded sample ----
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
-        cores = os.cpu_count() or 1
+        cores = min(os.cpu_count() or 1, n_streams)      # a stream is decoded by one thread
         sample = args.cpu_sample_streams or cpu_sample_size(wl, cores, 12.0, n_streams)
         b, t = cpu_baseline_run(wl, cores, sample)
         cpu = {"value": b / t / 1e9, "unit": "GB/s", "cores": cores, "kind": "port",
