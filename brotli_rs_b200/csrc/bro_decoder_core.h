@@ -15,7 +15,8 @@
 //     small batches and as the general fallback (bro_kernels.cu: bro_decode_warp_kernel).
 //   * nvcc, sm_100a, BRO_THREAD_MODE: BRO_W = 1: ONE THREAD PER STREAM.  The same code with a 1-lane "warp": 32
 //     streams advance per warp instruction, so the serial entropy decode no longer wastes 31/32 of the issue
-//     slots.  Used for large batches (bro_kernels_thread.cu: bro_decode_thread_kernel).
+//     slots.  Used for large batches, with BRO_PARSE: phase one of the two-phase path (bro_parse.h,
+//     bro_kernels_parse.cu: bro_parse_kernel), which records copies instead of making them.
 //   * BRO_HOSTSIM:                   BRO_W = 1 on the host, plain C++ -- a simulation of the very same code used
 //     ONLY by the CPU test-suite (tests/_build/libbro_hostsim.so) to fuzz the decoder logic against the oracle
 //     without a GPU.  It is never linked into libbrotli_b200.so and nothing in the product can reach it.

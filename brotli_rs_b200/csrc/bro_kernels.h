@@ -1,4 +1,5 @@
-// Launch interface between the C ABI (bro_abi.cu) and the kernels (bro_kernels.cu, bro_kernels_thread.cu).
+// Launch interface between the C ABI (bro_abi.cu) and the kernels (bro_kernels.cu, bro_kernels_parse.cu,
+// bro_kernels_copy.cu, bro_kernels_resume.cu).
 #pragma once
 #include <cuda_runtime.h>
 #include <stddef.h>

@@ -62,7 +62,7 @@ def thread_arena_u16():
 
 
 def parse_decode(data: bytes, cap: int = 1 << 20, quirks: int = 0, arena_u16: int = 0, rec_cap: int = 0, asan=False, mis=None):
-    """The two-phase path: phase one = the parse kernel's per-lane code (flat state machine), phase two = a byte loop
+    """The two-phase path: phase one = the parse kernel's per-lane code (bro_parse.h: header step and lockstep rounds), phase two = a byte loop
     over its copy records.  -> (status, bytes, records, machine trips); status may be one of RETRY, which the product
     answers by re-running the stream with the fused warp kernel.  mis = 0..15: the output slot starts at an address with
     (address & 15) == mis (the pieces of the copy records are cut for the slot's alignment)."""

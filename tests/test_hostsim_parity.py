@@ -65,7 +65,7 @@ def test_quirk_vectors():
             assert st1 == st and (st != 0 or out1 == out), (hx, quirks, st, st1)
 
 
-# ---- the two-phase path: phase one's flat state machine (bro_parse.h) + a byte loop over its copy records ----
+# ---- the two-phase path: phase one (bro_parse.h, the parse kernel's per-lane code) + a byte loop over its copy records ----
 
 def _parse_check(stream, cap, want_st, want_out, label, mis=None):
     st1, out1, nrec, steps = hostsim.parse_decode(stream, cap=cap, mis=mis)
