@@ -1,6 +1,7 @@
 #!/usr/bin/env python3
 """Fuzz harness standing in for the reference's AFL workflow (docs/notes_afl.txt, src/main.rs:49-70): mutated corpus
-streams are decoded on the GPU by both paths and compared with the oracle (status class and bytes).
+streams are decoded on the GPU by both paths, without size hints, and (--streaming N: the first N of them) through the
+streaming Read-struct, and compared with the oracle (status class and bytes).
 
     python tools/fuzz_gpu.py [--count 4000] [--seed 1] [--slack exact|tight|generous]
     compute-sanitizer --tool memcheck python tools/fuzz_gpu.py --count 600      (memory safety of the kernels)
@@ -22,6 +23,7 @@ def main():
     ap.add_argument("--count", type=int, default=4000)
     ap.add_argument("--seed", type=int, default=1)
     ap.add_argument("--slack", default="tight", choices=["exact", "tight", "generous"])
+    ap.add_argument("--streaming", type=int, default=200, help="streams also decoded through Decompressor(streaming=...) (resumable kernel)")
     args = ap.parse_args()
     import fuzzgen
     from brotli_rs_b200 import BatchDecoder
@@ -55,6 +57,24 @@ def main():
                 print("MISMATCH %s unsized stream %d: status %d vs %d" % (name, i, st, wst))
         dec.close()
         print("%s: %d streams, %d status classes" % (name, len(streams), len(set(int(x) for x in status))), flush=True)
+    if args.streaming:
+        from brotli_rs_b200 import BroError, Decompressor
+        dec = BatchDecoder(0)
+        k = min(args.streaming, len(streams))
+        for i in range(k):
+            wst, wout = oracle.decode(streams[i])
+            got, st = b"", 0
+            r = Decompressor(streams[i], decoder=dec, streaming=int(rng.integers(1, 4000)))
+            try:
+                got = r.read()
+            except BroError as e:
+                st = e.status
+            r.close()
+            if st != wst or (st == 0 and got != wout):
+                bad += 1
+                print("MISMATCH streaming stream %d: status %d vs %d; %s" % (i, st, wst, streams[i][:16].hex()))
+        dec.close()
+        print("streaming reader: %d streams" % k, flush=True)
     print("fuzz_gpu: %d streams x 2 paths, %d mismatches" % (len(streams), bad))
     return 1 if bad else 0
 
