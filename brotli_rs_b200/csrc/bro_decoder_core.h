@@ -33,12 +33,14 @@
 #define BRO_W 1u
 #define BRO_SERIAL 1
 #define BRO_FN static inline
+#define BRO_MFN inline
 #define BRO_COLD static
 #define BRO_TABLE_QUAL static const
 #elif defined(BRO_THREAD_MODE)
 #define BRO_W 1u
 #define BRO_SERIAL 1
 #define BRO_FN __device__ __forceinline__
+#define BRO_MFN __device__ __forceinline__
 #define BRO_COLD static __device__ __noinline__
 // every lane indexes the format tables with its own stream's symbol: global memory (L1) serves 32 different addresses in
 // one access, the constant cache would replay the load once per distinct address
@@ -50,6 +52,7 @@
 #define BRO_W 32u
 #endif
 #define BRO_FN __device__ __forceinline__
+#define BRO_MFN __device__ __forceinline__
 #define BRO_COLD static __device__ __noinline__
 #define BRO_TABLE_QUAL static __constant__ const
 #endif
@@ -141,6 +144,121 @@ BRO_FN uint32_t bro_funnel_r(uint32_t lo, uint32_t hi, unsigned sh) { return __f
 // tables; larger meta-blocks fall back to the warp kernel.  The thread's BroScratch sits at its start.
 #define BRO_THREAD_ARENA_U16 32768u
 
+#if defined(BRO_SERIAL)
+// ------------------------------------------------------------------------------------------------------
+// One decoder per THREAD: its on-chip storage is a block of BRO_TL_BYTES of shared memory, interleaved WORD BY WORD
+// with the blocks of the other 31 lanes of its warp: word w of lane l sits at warp_block + (32 * w + l) * 4.  Whatever
+// index a lane looks up, it touches bank l and no other lane does -- the 32 unrelated streams of a warp never
+// conflict, and a warp access costs one pass (a per-thread contiguous block would put equal indices of all lanes on
+// one bank).  Everything a lane touches per symbol lives here or in registers; local memory (1,232 bytes of stack per
+// thread in round 1: 470 KB per SM, i.e. an L2 round trip per access) is not used by the parse kernel any more.
+// The host simulation addresses a plain buffer with the very same interleave.
+// ------------------------------------------------------------------------------------------------------
+struct BroTl {
+#if defined(BRO_HOSTSIM)
+    uint8_t* base;            // this lane's word 0
+#else
+    uint32_t base;            // shared-window address of this lane's word 0
+#endif
+};
+BRO_FN uint32_t bro_tl_off(uint32_t b) { return ((b & ~3u) << 5) | (b & 3u); }
+#if defined(BRO_HOSTSIM)
+BRO_FN uint32_t bro_tl_ld8(BroTl t, uint32_t b) { return t.base[bro_tl_off(b)]; }
+BRO_FN void bro_tl_st8(BroTl t, uint32_t b, uint32_t v) { t.base[bro_tl_off(b)] = (uint8_t)v; }
+BRO_FN uint32_t bro_tl_ld16(BroTl t, uint32_t b) { const uint8_t* p = t.base + bro_tl_off(b); return (uint32_t)p[0] | ((uint32_t)p[1] << 8); }
+BRO_FN void bro_tl_st16(BroTl t, uint32_t b, uint32_t v) { uint8_t* p = t.base + bro_tl_off(b); p[0] = (uint8_t)v; p[1] = (uint8_t)(v >> 8); }
+BRO_FN uint32_t bro_tl_ld32(BroTl t, uint32_t b) {
+    const uint8_t* p = t.base + bro_tl_off(b);
+    return (uint32_t)p[0] | ((uint32_t)p[1] << 8) | ((uint32_t)p[2] << 16) | ((uint32_t)p[3] << 24);
+}
+BRO_FN void bro_tl_st32(BroTl t, uint32_t b, uint32_t v) {
+    uint8_t* p = t.base + bro_tl_off(b);
+    p[0] = (uint8_t)v; p[1] = (uint8_t)(v >> 8); p[2] = (uint8_t)(v >> 16); p[3] = (uint8_t)(v >> 24);
+}
+#else
+BRO_FN uint32_t bro_tl_ld8(BroTl t, uint32_t b) { uint32_t v; asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(t.base + bro_tl_off(b))); return v; }
+BRO_FN void bro_tl_st8(BroTl t, uint32_t b, uint32_t v) { asm volatile("st.shared.u8 [%0], %1;" :: "r"(t.base + bro_tl_off(b)), "r"(v) : "memory"); }
+BRO_FN uint32_t bro_tl_ld16(BroTl t, uint32_t b) { uint16_t v; asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(t.base + bro_tl_off(b))); return v; }
+BRO_FN void bro_tl_st16(BroTl t, uint32_t b, uint32_t v) { asm volatile("st.shared.u16 [%0], %1;" :: "r"(t.base + bro_tl_off(b)), "h"((uint16_t)v) : "memory"); }
+BRO_FN uint32_t bro_tl_ld32(BroTl t, uint32_t b) { uint32_t v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(t.base + (b << 5))); return v; }
+BRO_FN void bro_tl_st32(BroTl t, uint32_t b, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" :: "r"(t.base + (b << 5)), "r"(v) : "memory"); }
+#endif
+
+// arrays inside the block: sc.cnt[L] reads and sc.cnt[L] = v writes go through the interleave
+template <typename T, uint32_t OFF>
+struct BroTlArray {
+    BroTl t;
+    struct Ref {
+        BroTl t; uint32_t b;
+        BRO_MFN operator T() const {
+            return sizeof(T) == 1 ? (T)bro_tl_ld8(t, b) : sizeof(T) == 2 ? (T)(uint16_t)bro_tl_ld16(t, b) : (T)bro_tl_ld32(t, b);
+        }
+        BRO_MFN const Ref& operator=(T v) const {
+            if (sizeof(T) == 1) bro_tl_st8(t, b, (uint32_t)(uint8_t)v);
+            else if (sizeof(T) == 2) bro_tl_st16(t, b, (uint32_t)(uint16_t)v);
+            else bro_tl_st32(t, b, (uint32_t)v);
+            return *this;
+        }
+        BRO_MFN const Ref& operator=(const Ref& o) const { return *this = (T)o; }
+    };
+    BRO_MFN Ref operator[](uint32_t i) const { Ref r; r.t = t; r.b = OFF + i * (uint32_t)sizeof(T); return r; }
+};
+
+// Layout of a block.  While a meta-block HEADER is read it holds the table reader's scratch; inside a meta-block the
+// same bytes hold the decode tables of the current block types (bro_parse.h).  `word` is valid in both.
+#define BRO_TL_LENS 0u          // 704 code lengths, 4 bits each (bro_lens_*); the 256-byte IMTF list once they are dead
+#define BRO_TL_SYMS 352u        // uint16[4]
+#define BRO_TL_CNT 360u         // uint16[16]
+#define BRO_TL_LIMIT 392u       // uint16[16]
+#define BRO_TL_BASE 424u        // int16[16]
+#define BRO_TL_CLC 456u         // uint8[32]
+#define BRO_TL_CL 488u          // uint8[18] (+2)
+#define BRO_TL_WORD 512u        // uint8[64]
+#define BRO_TL_BYTES 576u
+struct BroScratch {
+    BroTl t;
+    BroTlArray<uint8_t, BRO_TL_LENS> mtf;      // 256-entry move-to-front list (the code lengths are dead by then)
+    BroTlArray<uint16_t, BRO_TL_SYMS> syms;    // explicit symbols of a simple code
+    BroTlArray<uint16_t, BRO_TL_CNT> cnt;      // per-length running positions
+    BroTlArray<uint16_t, BRO_TL_LIMIT> limit;
+    BroTlArray<int16_t, BRO_TL_BASE> base;
+    BroTlArray<uint8_t, BRO_TL_CLC> clc;       // code-length-code table: symbol | len<<5, indexed by 5 stream bits
+    BroTlArray<uint8_t, BRO_TL_CL> cl;         // lengths of the code-length code
+    BroTlArray<uint8_t, BRO_TL_WORD> word;     // dictionary word staging (<= 24 + 13 bytes)
+    uint16_t *root_lit, *root_cmd, *root_dist; // 256-entry root tables of the fused loops (host simulation only)
+};
+BRO_FN void bro_scratch_bind(BroScratch& sc, BroTl t) {
+    sc.t = t; sc.mtf.t = t; sc.syms.t = t; sc.cnt.t = t; sc.limit.t = t; sc.base.t = t; sc.clc.t = t; sc.cl.t = t; sc.word.t = t;
+    sc.root_lit = sc.root_cmd = sc.root_dist = 0;
+}
+// Out-of-line functions get the block's address by value and bind their own view of it (registers), and they work on
+// a register copy of the bit window: a struct passed by reference lives in LOCAL memory for its whole life, and with
+// hundreds of resident threads per SM every access to it would be an L2 round trip.
+#define BRO_SC_PARAM BroTl sc_tl_
+#define BRO_SC_BIND BroScratch sc; bro_scratch_bind(sc, sc_tl_)
+#define BRO_SC_PASS(sc) (sc).t
+#define BRO_CL(sc, i) (sc).cl[i]
+#define BRO_CL_DECL
+// code lengths (0..15), eight to a word
+BRO_FN uint32_t bro_lens_word(const BroScratch& sc, uint32_t w) { return bro_tl_ld32(sc.t, BRO_TL_LENS + 4u * w); }
+BRO_FN uint32_t bro_lens_get(const BroScratch& sc, uint32_t i) { return (bro_lens_word(sc, i >> 3) >> (4u * (i & 7u))) & 15u; }
+BRO_FN void bro_lens_put(const BroScratch& sc, uint32_t i, uint32_t v) {     // read-modify-write: the few explicit lengths of a simple code
+    const uint32_t sh = 4u * (i & 7u);
+    bro_tl_st32(sc.t, BRO_TL_LENS + 4u * (i >> 3), (bro_lens_word(sc, i >> 3) & ~(15u << sh)) | (v << sh));
+}
+// sequential writer: lengths arrive in ascending index order (with gaps that stay zero); a word is stored once
+struct BroLensWriter { uint32_t acc, w; };
+BRO_FN void bro_lens_begin(const BroScratch& sc, BroLensWriter& lw, uint32_t alphabet) {
+    for (uint32_t w = 0; w < (alphabet + 7u) >> 3; w++) bro_tl_st32(sc.t, BRO_TL_LENS + 4u * w, 0u);
+    lw.acc = 0; lw.w = 0;
+}
+BRO_FN void bro_lens_push(const BroScratch& sc, BroLensWriter& lw, uint32_t i, uint32_t v) {
+    const uint32_t w = i >> 3;
+    if (w != lw.w) { bro_tl_st32(sc.t, BRO_TL_LENS + 4u * lw.w, lw.acc); lw.acc = 0; lw.w = w; }
+    lw.acc |= v << (4u * (i & 7u));
+}
+BRO_FN void bro_lens_end(const BroScratch& sc, BroLensWriter& lw) { bro_tl_st32(sc.t, BRO_TL_LENS + 4u * lw.w, lw.acc); }
+#else
 // per-warp on-chip scratch (shared memory on the device)
 struct BroScratch {
     uint8_t lens[BRO_ALPHA_CMD];   // code lengths of the code being read; reused as the IMTF list
@@ -150,14 +268,20 @@ struct BroScratch {
     int16_t base[16];
     uint8_t clc[32];               // code-length-code table: symbol | len<<5, indexed by 5 stream bits
     uint8_t word[64];              // dictionary word staging (<= 24 + 13 bytes)
-#if !defined(BRO_PARSE)
     // on-chip copies of the root tables of the current meta-block's literal / insert&copy / distance code when the
     // meta-block has exactly one of that kind (true for every stream libbrotli produces at quality <= 9)
     uint16_t root_lit[256];
     uint16_t root_cmd[256];
     uint16_t root_dist[256];
-#endif
 };
+BRO_FN uint32_t bro_lens_get(const BroScratch& sc, uint32_t i) { return sc.lens[i]; }
+BRO_FN void bro_lens_put(BroScratch& sc, uint32_t i, uint32_t v) { sc.lens[i] = (uint8_t)v; }
+#define BRO_SC_PARAM BroScratch& sc
+#define BRO_SC_BIND
+#define BRO_SC_PASS(sc) (sc)
+#define BRO_CL(sc, i) cl_[i]
+#define BRO_CL_DECL uint32_t cl_[18]
+#endif
 
 // ------------------------------------------------------------------------------------------------------
 // bit stream: src/bitreader/mod.rs:21-304 restated as a 64-bit LSB-first window.  The warp loads the
@@ -169,7 +293,7 @@ struct BroBits {
     const uint8_t* end;     // one past the last byte of the stream
     uint32_t w0, w1;        // bit window: two consecutive little-endian words of the stream; next bit = bit `bp` of w0
 #if defined(BRO_THREAD_MODE)
-    uint32_t w2;            // the word after the window, loaded one slide ahead so that a slide never waits for memory
+    uint32_t w2, w3;        // the two words after the window, loaded two slides ahead so that a slide does not wait for L2
 #endif
     uint32_t bp;            // 0..31
     uint32_t avail;         // real stream bits in the window from `bp` on (the rest of w0/w1 is padding past the end)
@@ -228,6 +352,7 @@ BRO_FN void bro_bits_seek(BroBits& s, const uint8_t* a) {
     s.w1 = bro_next_word(s);
 #if defined(BRO_THREAD_MODE)
     s.w2 = bro_next_word(s);
+    s.w3 = bro_next_word(s);
 #endif
     s.bp = 8u * sh;
 #if defined(BRO_THREAD_MODE)
@@ -261,11 +386,18 @@ BRO_FN void bro_refill(BroBits& s) {
     // one thread per stream: branch-free, so that the lanes of a warp (different streams, different bit positions)
     // share these instructions instead of taking the slide one group of lanes at a time
     const bool need = s.bp >= 32u;
-    uint32_t wn = s.w2;
-    if (need) { wn = 0; if (s.chunk < s.end) wn = __ldg((const uint32_t*)s.chunk); }   // chunk >= lo always holds here
+    uint32_t wn = s.w3;
+    if (need) {
+        wn = 0;
+        if (s.chunk < s.end) wn = __ldg((const uint32_t*)s.chunk);       // chunk >= lo always holds here
+        // entering a new 32-byte sector: ask L2 for the sector after the next one (the stream is read strictly forward,
+        // so DRAM latency is paid two sectors ahead of the window and the loads above find their words in L2 / L1)
+        if (((uintptr_t)s.chunk & 31u) == 0u && s.chunk + 64 < s.end) asm volatile("prefetch.global.L2 [%0];" :: "l"(s.chunk + 64));
+    }
     s.w0 = need ? s.w1 : s.w0;
     s.w1 = need ? s.w2 : s.w1;
-    s.w2 = wn;                                                            // not looked at before the next slide
+    s.w2 = need ? s.w3 : s.w2;
+    s.w3 = wn;                                                            // not looked at before the slide after the next
     s.bp -= need ? 32u : 0u;
     s.chunk += need ? 4 : 0;
     return;
@@ -306,7 +438,7 @@ BRO_FN bool bro_read_byte_tail(BroBits& s, uint32_t& v) {
 // byte address of the next unread bit (valid when byte aligned)
 BRO_FN const uint8_t* bro_bits_addr(const BroBits& s) {
 #if defined(BRO_THREAD_MODE)
-    return s.chunk - 12 + (s.bp >> 3);
+    return s.chunk - 16 + (s.bp >> 3);
 #elif defined(BRO_SERIAL)
     return s.chunk - 8 + (s.bp >> 3);
 #else
@@ -317,7 +449,7 @@ BRO_FN const uint8_t* bro_bits_addr(const BroBits& s) {
 // bits consumed since byte address `start` (any state of the window)
 BRO_FN uint64_t bro_bits_position(const BroBits& s, const uint8_t* start) {
 #if defined(BRO_THREAD_MODE)
-    const uint8_t* w0 = s.chunk - 12;
+    const uint8_t* w0 = s.chunk - 16;
 #elif defined(BRO_SERIAL)
     const uint8_t* w0 = s.chunk - 8;
 #else
@@ -374,44 +506,6 @@ BRO_FN int bro_decode_sym2(BroBits& s, const uint16_t* root, const uint16_t* T, 
 
 BRO_FN int bro_decode_sym(BroBits& s, const uint16_t* T, uint32_t& sym) { return bro_decode_sym2(s, T, T, sym); }
 
-// The same through a narrower copy of the root kept on chip by the caller (parse kernel: shared memory): `root` has
-// 1 << root_bits entries; an entry is a direct hit (symbol | len<<10, len <= root_bits) or 1 = search by length in T.
-BRO_FN int bro_decode_sym_r(BroBits& s, const uint16_t* root, uint32_t root_bits, const uint16_t* T, uint32_t& sym) {
-    bro_refill(s);
-    uint32_t peek = bro_peek(s);
-    uint32_t e = root[peek & ((1u << root_bits) - 1u)];
-    uint32_t len = e >> 10;
-    if (len != 0u) {
-        if (len > bro_avail(s)) return BRO_SYM_EOF;
-        bro_consume(s, len);
-        sym = e & 0x3ffu;
-        return BRO_SYM_OK;
-    }
-    // not in the narrow copy: the table's own 8-bit root settles codes of up to 8 bits with one look-up; only what is
-    // longer takes the canonical search (four dependent look-ups)
-    e = T[peek & (BRO_ROOT_SIZE - 1u)];
-    len = e >> 10;
-    if (len != 0u) {
-        if (len > bro_avail(s)) return BRO_SYM_EOF;
-        bro_consume(s, len);
-        sym = e & 0x3ffu;
-        return BRO_SYM_OK;
-    }
-    uint32_t r = bro_sym_slow(T, peek, e, bro_avail(s));
-    bro_consume(s, (r >> 16) & 0xffu);
-    sym = r & 0xffffu;
-    return (int)(r >> 24);
-}
-
-// Fill such a copy from the table's own 8-bit root.
-BRO_FN void bro_narrow_root(uint16_t* root, uint32_t root_bits, const uint16_t* T) {
-#pragma unroll 8
-    for (uint32_t r = 0; r < (1u << root_bits); r++) {     // unrolled: eight table look-ups in flight, not one
-        const uint32_t e = T[r], l = e >> 10;
-        root[r] = (uint16_t)((l >= 1u && l <= root_bits) ? e : 1u);
-    }
-}
-
 // Build a tree record from n (length, symbol) pairs in sc.lens[] (and sc.syms[] when `explicit_syms`), in
 // the order the reference inserts them: src/huffman/mod.rs:19-43 assigns canonical codes per length in array
 // order; Tree::insert (src/huffman/tree/mod.rs:50-61) counts every insert, and a tree with exactly one
@@ -422,19 +516,29 @@ BRO_FN void bro_narrow_root(uint16_t* root, uint32_t root_bits, const uint16_t* 
 // in its own scratch (local memory on the device); the table itself is only written: the root is filled by
 // replication as every symbol is placed (its canonical code is known at that moment), so the build never waits for a
 // load from the table arena in HBM.
-BRO_COLD void bro_build_tree(uint16_t* T, BroScratch& sc, uint32_t n, bool explicit_syms) {
-    uint32_t cnt[16], next[16];
-    int base[16];               // canonical index of the first code of a length minus its code value
-    for (uint32_t L = 0; L < 16u; L++) cnt[L] = 0;
-    for (uint32_t i = 0; i < n; i++) cnt[sc.lens[i] & 15u]++;
+BRO_COLD void bro_build_tree(uint16_t* T, BRO_SC_PARAM, uint32_t n, bool explicit_syms) {
+    BRO_SC_BIND;
+    // pass 1: per-length counts (running positions later) in the thread's on-chip block; unused symbols -- most of the
+    // 704 insert&copy symbols of a typical code -- are skipped eight at a time
+    for (uint32_t L = 0; L < 16u; L++) sc.cnt[L] = 0;
+    const uint32_t nw = (n + 7u) >> 3;
+    for (uint32_t w = 0; w < nw; w++) {
+        uint32_t word = bro_lens_word(sc, w);
+        if (8u * w + 8u > n) word &= (1u << (4u * (n - 8u * w))) - 1u;         // lengths behind the alphabet are not part of the code
+        while (word) {
+            const uint32_t L = word & 15u;
+            word >>= 4;
+            if (L) sc.cnt[L] = (uint16_t)(sc.cnt[L] + 1u);
+        }
+    }
     uint32_t code = 0, off = 0, maxdepth = 0, nonzero = 0;
     T[BRO_T_LIMIT] = 0; T[BRO_T_BASE] = 0;
-    base[0] = 0; next[0] = 0;
     for (uint32_t L = 1; L <= 15u; L++) {
-        const uint32_t c = cnt[L];
-        next[L] = off;
-        base[L] = (int)off - (int)code;
-        T[BRO_T_BASE + L] = (uint16_t)(int16_t)base[L];
+        const uint32_t c = sc.cnt[L];
+        sc.cnt[L] = (uint16_t)off;                                            // next free position of this length in sorted[]
+        const int base = (int)off - (int)code;                                // canonical index of the first code of the length minus its code value
+        sc.base[L] = (int16_t)base;
+        T[BRO_T_BASE + L] = (uint16_t)(int16_t)base;
         code += c;
         T[BRO_T_LIMIT + L] = (uint16_t)(code << (15u - L));
         code <<= 1;
@@ -452,21 +556,27 @@ BRO_COLD void bro_build_tree(uint16_t* T, BroScratch& sc, uint32_t n, bool expli
 #else
     for (uint32_t r = 0; r < BRO_ROOT_SIZE / 8u; r++) ((uint4*)T)[r] = make_uint4(0u, 0u, 0u, 0u);     // records are 16-byte aligned
 #endif
-    uint32_t single_sym = 0;
-    for (uint32_t i = 0; i < n; i++) {
-        const uint32_t L = sc.lens[i] & 15u;
-        const uint32_t symv = explicit_syms ? sc.syms[i] : i;
-        if (nonzero == 0u && i == 0u) single_sym = symv;
-        if (L == 0u) continue;
-        const uint32_t idx = next[L]++;
-        T[BRO_T_SORTED + idx] = (uint16_t)symv;
-        if (nonzero == 1u) single_sym = symv;
-        if (nonzero >= 2u) {
-            const uint32_t c = (uint32_t)((int)idx - base[L]);      // the canonical code of this symbol
-            if (L <= BRO_ROOT_BITS) {
-                const uint32_t e = symv | (L << 10);
-                for (uint32_t r = bro_brev(c) >> (32u - L); r < BRO_ROOT_SIZE; r += 1u << L) T[r] = (uint16_t)e;
-            } else T[bro_brev(c >> (L - BRO_ROOT_BITS)) >> (32u - BRO_ROOT_BITS)] = 1;
+    // pass 2: place the symbols in canonical order (array order inside a length); the table itself is only written --
+    // the root is filled by replication as every symbol is placed (its canonical code is known at that moment)
+    uint32_t single_sym = explicit_syms ? (uint32_t)sc.syms[0] : 0u;          // nonzero == 0: the first pair
+    for (uint32_t w = 0; w < nw; w++) {
+        uint32_t word = bro_lens_word(sc, w);
+        if (8u * w + 8u > n) word &= (1u << (4u * (n - 8u * w))) - 1u;
+        for (uint32_t i = 8u * w; word; i++, word >>= 4) {
+            const uint32_t L = word & 15u;
+            if (L == 0u) continue;
+            const uint32_t symv = explicit_syms ? (uint32_t)sc.syms[i] : i;
+            const uint32_t idx = sc.cnt[L];
+            sc.cnt[L] = (uint16_t)(idx + 1u);
+            T[BRO_T_SORTED + idx] = (uint16_t)symv;
+            if (nonzero == 1u) single_sym = symv;
+            if (nonzero >= 2u) {
+                const uint32_t c = (uint32_t)((int)idx - (int)sc.base[L]);    // the canonical code of this symbol
+                if (L <= BRO_ROOT_BITS) {
+                    const uint32_t e = symv | (L << 10);
+                    for (uint32_t r = bro_brev(c) >> (32u - L); r < BRO_ROOT_SIZE; r += 1u << L) T[r] = (uint16_t)e;
+                } else T[bro_brev(c >> (L - BRO_ROOT_BITS)) >> (32u - BRO_ROOT_BITS)] = 1;
+            }
         }
     }
     T[BRO_T_SINGLE_SYM] = (uint16_t)single_sym;
@@ -570,15 +680,19 @@ struct BroDec {
     uint16_t* arena;          // table arena of this warp / thread (bump-allocated per meta-block)
     uint32_t arena_cap;       // its capacity in uint16 units
     uint32_t arena_base;      // first free uint16 (thread mode keeps its scratch below it)
-    BroScratch* sc;
+#if defined(BRO_SERIAL)
+    BroScratch scv;           // view of this thread's on-chip block (a few addresses, by value: registers)
+#define BRO_DSC(d) ((d).scv)
+#else
+    BroScratch* sc;           // this warp's scratch in shared memory
+#define BRO_DSC(d) (*(d).sc)
+#endif
     const uint8_t* dict;      // 122,784-byte static dictionary image
     int quirk_spec;
 #if defined(BRO_PARSE)
     BroRec* rec;              // copy records of this stream (phase one of the two-phase path writes, phase two executes)
     uint32_t nrec, rec_cap;
     const uint8_t* in_base;   // first byte of the compressed stream (stored-block records hold offsets from it)
-    uint16_t* roots;          // symbols of the current literal code in canonical order (bro_parse.h; HBM / L2 in the parse kernel)
-    uint16_t* roots_cd;       // roots of the current literal, insert&copy and distance tables (shared memory)
     const uint32_t* ic;       // bro_ic_insert / bro_ic_copy interleaved (shared memory)
     uint32_t out_mis;         // (address of out) & 15: pieces are cut at 16-byte boundaries of the destination ADDRESS
     uint32_t sizing;          // 1: only measure the stream (bro_batch_sizes): nothing is written, the slot is unbounded
@@ -636,27 +750,32 @@ BRO_FN int bro_read_nbltypes(BroBits& in, uint32_t& v) {
     return 0;
 }
 
-// The readers below only fill sc.lens[] (and sc.syms[]); the table is built by their caller afterwards.  In the
-// thread-per-stream kernel this matters: lanes leave the loops below at different trips, and they are converged again
-// only once the out-of-line function has returned -- the build then runs once for the whole warp.  For the same
+// The readers below only fill the scratch's code lengths (and sc.syms[]); the table is built by their caller afterwards.
+// In the thread-per-stream kernel this matters: lanes leave the loops below at different trips, and they are converged
+// again only once the out-of-line function has returned -- the build then runs once for the whole warp.  For the same
 // reason the loops have a single exit (errors break and are returned after the loop).
 
-// src/lib.rs:597-665.  -> number of (length, symbol) pairs in sc.lens[] / sc.syms[]
-BRO_COLD int bro_read_simple_code(BroBits& in, BroScratch& sc, uint32_t alphabet, uint32_t& n_out) {
+// src/lib.rs:597-665.  -> number of (length, symbol) pairs in the scratch's lengths / sc.syms[]
+BRO_FN int bro_read_simple_code(BroBits& in, BroScratch& sc, uint32_t alphabet, uint32_t& n_out) {
     uint32_t bit_width = 0;
     for (uint32_t a = alphabet - 1u; a; a >>= 1) bit_width++;   // 16 - leading_zeros(alphabet-1 as u16), src/lib.rs:598
     uint32_t nsym, s[4] = {0, 0, 0, 0};
     if (!bro_read_bits(in, 2, nsym)) return BRO_ST_UnexpectedEOF;
     nsym += 1;
     int st = 0;
-    for (uint32_t i = 0; i < nsym; i++) {
-        if (!bro_read_bits(in, bit_width, s[i])) { st = BRO_ST_UnexpectedEOF; break; }
-        if (s[i] >= alphabet) { st = BRO_ST_InvalidSymbol; break; }
+#pragma unroll
+    for (uint32_t i = 0; i < 4u; i++) {
+        if (i < nsym && !st) {
+            if (!bro_read_bits(in, bit_width, s[i])) st = BRO_ST_UnexpectedEOF;
+            else if (s[i] >= alphabet) st = BRO_ST_InvalidSymbol;
+        }
     }
     if (st) return st;
-    for (uint32_t i = 0; i + 1 < nsym; i++)
-        for (uint32_t j = i + 1; j < nsym; j++)
-            if (s[i] == s[j]) st = BRO_ST_InvalidSymbol;
+#pragma unroll
+    for (uint32_t i = 0; i < 3u; i++)
+#pragma unroll
+        for (uint32_t j = i + 1; j < 4u; j++)
+            if (j < nsym && s[i] == s[j]) st = BRO_ST_InvalidSymbol;
     if (st) return st;
     uint32_t L[4] = {0, 0, 0, 0};
 #define BRO_SWAP(a, b) do { if (s[a] > s[b]) { uint32_t t_ = s[a]; s[a] = s[b]; s[b] = t_; } } while (0)
@@ -672,19 +791,30 @@ BRO_COLD int bro_read_simple_code(BroBits& in, BroScratch& sc, uint32_t alphabet
     }
 #undef BRO_SWAP
     bro_syncwarp();
-    if (bro_lane() == 0) for (uint32_t i = 0; i < nsym; i++) { sc.lens[i] = (uint8_t)L[i]; sc.syms[i] = (uint16_t)s[i]; }
+    if (bro_lane() == 0) {
+#if defined(BRO_SERIAL)
+        bro_tl_st32(sc.t, BRO_TL_LENS, L[0] | (L[1] << 4) | (L[2] << 8) | (L[3] << 12));
+#endif
+#pragma unroll
+        for (uint32_t i = 0; i < 4u; i++) if (i < nsym) {
+#if !defined(BRO_SERIAL)
+            sc.lens[i] = (uint8_t)L[i];
+#endif
+            sc.syms[i] = (uint16_t)s[i];
+        }
+    }
     bro_syncwarp();
     n_out = nsym;
     return 0;
 }
 
-// src/lib.rs:667-875.  Fills sc.lens[0..alphabet).
-BRO_COLD int bro_read_complex_code(BroBits& in, BroScratch& sc, uint32_t hskip, uint32_t alphabet) {
+// src/lib.rs:667-875.  Fills the scratch's code lengths [0, alphabet).
+BRO_FN int bro_read_complex_code(BroBits& in, BroScratch& sc, uint32_t hskip, uint32_t alphabet) {
     const unsigned lane = bro_lane();
     // code lengths of the code-length code, transmitted in the order 1,2,3,4,0,5,17,6,16,7,8,...,15 with the fixed
     // code 00->0 01->3 10->4 110->2 1110->1 1111->5 (src/lib.rs:120-125, 669-704)
-    uint32_t cl[18];
-    for (int i = 0; i < 18; i++) cl[i] = 0;
+    BRO_CL_DECL;
+    for (uint32_t i = 0; i < 18u; i++) BRO_CL(sc, i) = 0;
     uint32_t sum = 0, nonzero = 0;
     int st = 0;
     for (uint32_t i = hskip; i < 18u; i++) {
@@ -701,9 +831,9 @@ BRO_COLD int bro_read_complex_code(BroBits& in, BroScratch& sc, uint32_t hskip, 
                 v = b ? 5 : 1;
             }
         }
-        // transmission slot i -> symbol
-        const uint8_t slot_sym[18] = {1, 2, 3, 4, 0, 5, 17, 6, 16, 7, 8, 9, 10, 11, 12, 13, 14, 15};
-        cl[slot_sym[i]] = v;
+        // transmission slot i -> symbol: 1, 2, 3, 4, 0, 5, 17, 6, 16, 7, 8, ..., 15 (one nibble / one bit per slot)
+        const uint32_t slot_sym = i < 16u ? (uint32_t)((0xdcba987061504321ull >> (4u * i)) & 15u) + ((0x0140u >> i) & 1u) * 16u : i - 2u;
+        BRO_CL(sc, slot_sym) = v;
         if (v > 0u) {
             sum += 32u >> v;
             nonzero += 1;
@@ -722,22 +852,31 @@ BRO_COLD int bro_read_complex_code(BroBits& in, BroScratch& sc, uint32_t hskip, 
         bro_syncwarp();
         for (uint32_t L = 1; L <= 5u; L++) {
             for (uint32_t sy = 0; sy < 18u; sy++) {
-                if (cl[sy] == L) {
+                if (BRO_CL(sc, sy) == L) {
                     uint32_t rev = bro_brev(code) >> (32u - L);
+#if defined(BRO_SERIAL)
+                    for (uint32_t r = rev; r < 32u; r += 1u << L) sc.clc[r] = (uint8_t)(sy | (L << 5));
+#else
                     for (uint32_t r = lane; r < 32u; r += BRO_W)
                         if ((r & ((1u << L) - 1u)) == rev) sc.clc[r] = (uint8_t)(sy | (L << 5));
+#endif
                     code++;
                 }
             }
             code <<= 1;
         }
-        if (nonzero == 1u) for (uint32_t sy = 0; sy < 18u; sy++) if (cl[sy]) clc_single = sy;
+        if (nonzero == 1u) for (uint32_t sy = 0; sy < 18u; sy++) if (BRO_CL(sc, sy)) clc_single = sy;
         bro_syncwarp();
     }
 
     // the symbol code lengths (src/lib.rs:730-864)
+#if defined(BRO_SERIAL)
+    BroLensWriter lw;
+    bro_lens_begin(sc, lw, alphabet);
+#else
     for (uint32_t i = lane; i < alphabet; i += BRO_W) sc.lens[i] = 0;
     bro_syncwarp();
+#endif
     uint32_t total = 0, last_symbol = 0xffu, last_repeat = 0, have_repeat = 0, last_nz = 8, i = 0, nz = 0;
     while (i < alphabet) {
         uint32_t c;
@@ -751,7 +890,11 @@ BRO_COLD int bro_read_complex_code(BroBits& in, BroScratch& sc, uint32_t hskip, 
             c = e & 31u;
         }
         if (c <= 15u) {
+#if defined(BRO_SERIAL)
+            bro_lens_push(sc, lw, i, c);
+#else
             if (lane == 0) sc.lens[i] = (uint8_t)c;
+#endif
             i += 1;
             last_symbol = c;
             have_repeat = 0;
@@ -774,7 +917,11 @@ BRO_COLD int bro_read_complex_code(BroBits& in, BroScratch& sc, uint32_t hskip, 
                 if (i + newrep > alphabet) { st = BRO_ST_ParseErrorComplexPrefixCodeLengths; break; }
                 count = newrep;
             }
+#if defined(BRO_SERIAL)
+            for (uint32_t k = 0; k < count; k++) bro_lens_push(sc, lw, i + k, last_nz);
+#else
             for (uint32_t k = lane; k < count; k += BRO_W) sc.lens[i + k] = (uint8_t)last_nz;
+#endif
             i += count;
             nz += count;
             total += count * (32768u >> last_nz);
@@ -799,6 +946,9 @@ BRO_COLD int bro_read_complex_code(BroBits& in, BroScratch& sc, uint32_t hskip, 
             last_symbol = 17;
         }
     }
+#if defined(BRO_SERIAL)
+    bro_lens_end(sc, lw);
+#endif
     if (st) return st;
     if (nz < 2u) return BRO_ST_LessThanTwoNonZeroCodeLengths;
     bro_syncwarp();
@@ -806,7 +956,7 @@ BRO_COLD int bro_read_complex_code(BroBits& in, BroScratch& sc, uint32_t hskip, 
 }
 
 // src/lib.rs:877-889.  -> the arguments of the table build that follows: n pairs, explicit symbols or not.
-BRO_COLD int bro_read_prefix_code_cold(BroBits& in, BroScratch& sc, uint32_t alphabet, uint32_t& n_out, bool& explicit_out) {
+BRO_FN int bro_read_prefix_code_body(BroBits& in, BroScratch& sc, uint32_t alphabet, uint32_t& n_out, bool& explicit_out) {
     uint32_t kind;
     if (!bro_read_bits(in, 2, kind)) return BRO_ST_UnexpectedEOF;
     explicit_out = kind == 1u;
@@ -816,14 +966,25 @@ BRO_COLD int bro_read_prefix_code_cold(BroBits& in, BroScratch& sc, uint32_t alp
 }
 
 // The out-of-line (cold) routines take the bit window by reference.  Callers hand them a COPY and copy it back, so
-// that the hot loops' own window never has its address taken and stays in registers.
+// that the hot loops' own window never has its address taken and stays in registers; the routines themselves work on
+// a register copy too (BRO_SC_PARAM above).
+BRO_COLD int bro_read_prefix_code_cold(BroBits& in_, BRO_SC_PARAM, uint32_t alphabet, uint32_t& n_out, bool& explicit_out) {
+    BRO_SC_BIND;
+    BroBits in = in_;
+    uint32_t n = 0;
+    bool ex = false;
+    const int st = bro_read_prefix_code_body(in, sc, alphabet, n, ex);
+    in_ = in; n_out = n; explicit_out = ex;
+    return st;
+}
+
 BRO_FN int bro_read_prefix_code(BroBits& in, BroScratch& sc, uint32_t alphabet, uint16_t* T) {
     BroBits t = in;
     uint32_t n = 0;
     bool explicit_syms = false;
-    int st = bro_read_prefix_code_cold(t, sc, alphabet, n, explicit_syms);
+    int st = bro_read_prefix_code_cold(t, BRO_SC_PASS(sc), alphabet, n, explicit_syms);
     in = t;
-    if (st == 0) bro_build_tree(T, sc, n, explicit_syms);
+    if (st == 0) bro_build_tree(T, BRO_SC_PASS(sc), n, explicit_syms);
     return st;
 }
 
@@ -840,7 +1001,7 @@ BRO_FN int bro_read_block_count(BroBits& in, const uint16_t* T, uint32_t& count)
 }
 
 // src/lib.rs:1226-1250 plus the caller's bookkeeping (e.g. 1296-1302)
-BRO_COLD int bro_block_switch_cold(BroBits& in, const uint16_t* arena, BroBlockCat& c) {
+BRO_FN int bro_block_switch_body(BroBits& in, const uint16_t* arena, BroBlockCat& c) {
     uint32_t code, count;
     int r = bro_decode_sym(in, arena + c.t_type, code);
     if (r == BRO_SYM_HOLE) return BRO_ST_InvalidBlockSwitchCommandCode;
@@ -853,6 +1014,13 @@ BRO_COLD int bro_block_switch_cold(BroBits& in, const uint16_t* arena, BroBlockC
     c.blen = count - 1u;
     return 0;
 }
+BRO_COLD int bro_block_switch_cold(BroBits& in_, const uint16_t* arena, BroBlockCat& c_) {
+    BroBits in = in_;
+    BroBlockCat c = c_;
+    const int st = bro_block_switch_body(in, arena, c);
+    in_ = in; c_ = c;
+    return st;
+}
 
 BRO_FN int bro_block_switch(BroBits& in, const uint16_t* arena, BroBlockCat& c) {
     BroBits t = in;
@@ -864,7 +1032,7 @@ BRO_FN int bro_block_switch(BroBits& in, const uint16_t* arena, BroBlockCat& c) 
 }
 
 // src/lib.rs:1070-1144 and the IMTF of 1164-1177
-BRO_COLD int bro_read_context_map_cold(BroBits& in, BroScratch& sc, uint16_t* T, uint32_t t_cap, uint32_t ntrees, uint32_t len, uint8_t* cmap) {
+BRO_FN int bro_read_context_map_body(BroBits& in, BroScratch& sc, uint16_t* T, uint32_t t_cap, uint32_t ntrees, uint32_t len, uint8_t* cmap) {
     const unsigned lane = bro_lane();
     uint32_t b, rlemax = 0;
     if (!bro_read_bits(in, 1, b)) return BRO_ST_UnexpectedEOF;
@@ -875,9 +1043,9 @@ BRO_COLD int bro_read_context_map_cold(BroBits& in, BroScratch& sc, uint16_t* T,
     if (BRO_TREE_U16(rlemax + ntrees) > t_cap) return BRO_ST_ArenaTooSmall;   // temporary table above the arena top
     uint32_t n_pairs = 0;
     bool explicit_syms = false;
-    int st = bro_read_prefix_code_cold(in, sc, rlemax + ntrees, n_pairs, explicit_syms);
+    int st = bro_read_prefix_code_body(in, sc, rlemax + ntrees, n_pairs, explicit_syms);
     if (st) return st;
-    bro_build_tree(T, sc, n_pairs, explicit_syms);
+    bro_build_tree(T, BRO_SC_PASS(sc), n_pairs, explicit_syms);
     uint32_t pushed = 0;
     while (pushed < len) {
         uint32_t s;
@@ -898,7 +1066,12 @@ BRO_COLD int bro_read_context_map_cold(BroBits& in, BroScratch& sc, uint16_t* T,
     }
     if (!bro_read_bits(in, 1, b)) return BRO_ST_UnexpectedEOF;
     if (b) {
-        uint8_t* mtf = sc.lens;   // 256-entry move-to-front list
+        // 256-entry move-to-front list (the code lengths are dead: their bytes are reused)
+#if defined(BRO_SERIAL)
+        const BroTlArray<uint8_t, BRO_TL_LENS>& mtf = sc.mtf;
+#else
+        uint8_t* mtf = sc.lens;
+#endif
         bro_syncwarp();
         for (uint32_t k = lane; k < 256u; k += BRO_W) mtf[k] = (uint8_t)k;
         bro_syncwarp();
@@ -907,7 +1080,7 @@ BRO_COLD int bro_read_context_map_cold(BroBits& in, BroScratch& sc, uint16_t* T,
                 uint32_t index = cmap[k];
                 uint8_t value = mtf[index];
                 cmap[k] = value;
-                for (uint32_t j = index; j >= 1u; j--) mtf[j] = mtf[j - 1];
+                for (uint32_t j = index; j >= 1u; j--) mtf[j] = (uint8_t)mtf[j - 1];
                 mtf[0] = value;
             }
         }
@@ -915,10 +1088,17 @@ BRO_COLD int bro_read_context_map_cold(BroBits& in, BroScratch& sc, uint16_t* T,
     bro_syncwarp();
     return 0;
 }
+BRO_COLD int bro_read_context_map_cold(BroBits& in_, BRO_SC_PARAM, uint16_t* T, uint32_t t_cap, uint32_t ntrees, uint32_t len, uint8_t* cmap) {
+    BRO_SC_BIND;
+    BroBits in = in_;
+    const int st = bro_read_context_map_body(in, sc, T, t_cap, ntrees, len, cmap);
+    in_ = in;
+    return st;
+}
 
 BRO_FN int bro_read_context_map(BroBits& in, BroScratch& sc, uint16_t* T, uint32_t t_cap, uint32_t ntrees, uint32_t len, uint8_t* cmap) {
     BroBits t = in;
-    int st = bro_read_context_map_cold(t, sc, T, t_cap, ntrees, len, cmap);
+    int st = bro_read_context_map_cold(t, BRO_SC_PASS(sc), T, t_cap, ntrees, len, cmap);
     in = t;
     return st;
 }
@@ -1027,7 +1207,8 @@ BRO_COPY_FN void bro_lz_copy(uint8_t* out, uint32_t pos, uint32_t dist, uint32_t
 
 // Static dictionary word + transform (src/lib.rs:1506-1540, src/transformation/mod.rs:84-209).  Returns the
 // transformed length, or -1 where the reference panics (uppercase_first on a 0x00 byte).
-BRO_COLD int bro_dict_word(BroScratch& sc, const uint8_t* dict, int quirk_spec, uint32_t copy_len, uint32_t index, uint32_t tid) {
+BRO_COLD int bro_dict_word(BRO_SC_PARAM, const uint8_t* dict, int quirk_spec, uint32_t copy_len, uint32_t index, uint32_t tid) {
+    BRO_SC_BIND;
     const unsigned lane = bro_lane();
     const uint8_t* w = dict + bro_dict_offsets[copy_len] + index * copy_len;
     uint32_t type = bro_xf_type[tid], plen = bro_xf_prefix_len[tid], slen = bro_xf_suffix_len[tid];
@@ -1051,13 +1232,12 @@ BRO_COLD int bro_dict_word(BroScratch& sc, const uint8_t* dict, int quirk_spec, 
         uint32_t c0 = sc.word[plen];
         if (type == 1u && c0 == 0u && !quirk_spec) ret = -1;
         else if (lane == 0) {
-            uint8_t* v = sc.word + plen;
-            uint32_t i = 0;
+            uint32_t i = 0;                     // position in the transformed word, which starts at sc.word[plen]
             do {
-                uint32_t c = v[i];
-                if (c < 192u) { if (c >= 97u && c <= 122u) v[i] ^= 32; i += 1; }
-                else if (c < 224u) { if (i + 1 < wl) v[i + 1] ^= 32; i += 2; }
-                else { if (i + 2 < wl) v[i + 2] ^= 5; i += 3; }
+                uint32_t c = sc.word[plen + i];
+                if (c < 192u) { if (c >= 97u && c <= 122u) sc.word[plen + i] = (uint8_t)(c ^ 32u); i += 1; }
+                else if (c < 224u) { if (i + 1 < wl) sc.word[plen + i + 1] = (uint8_t)((uint32_t)sc.word[plen + i + 1] ^ 32u); i += 2; }
+                else { if (i + 2 < wl) sc.word[plen + i + 2] = (uint8_t)((uint32_t)sc.word[plen + i + 2] ^ 5u); i += 3; }
             } while (type == 2u && i < wl);
         }
         bro_syncwarp();
@@ -1087,7 +1267,7 @@ BRO_FN int bro_emit_copy(BroDec& d, BroScratch& sc, uint32_t mlen, uint32_t mb_b
         uint32_t bits = bro_dict_size_bits[copy_len];
         uint32_t index = word_id & ((1u << bits) - 1u), tid = word_id >> bits;
         if (tid > 120u) return BRO_ST_InvalidTransformId;
-        int n = bro_dict_word(sc, d.dict, d.quirk_spec, copy_len, index, tid);
+        int n = bro_dict_word(BRO_SC_PASS(sc), d.dict, d.quirk_spec, copy_len, index, tid);
         if (n < 0) return BRO_ST_PanicUppercaseZero;
         if (mlen < mb_out + (uint32_t)n) return BRO_ST_ExceededExpectedBytes;  // checked after the transform (Q10)
         if ((uint32_t)n > d.cap - d.pos) return BRO_ST_OutputTooSmall;
@@ -1306,7 +1486,7 @@ BRO_FN int bro_metablock_tables(BroDec& d, BroMbInfo& mb) {
     const unsigned lane = bro_lane();
     uint16_t* A = d.arena;
     BroBlockCat (&cat)[3] = mb.cat;
-    BroScratch& sc = *d.sc;
+    BroScratch& sc = BRO_DSC(d);
     // Single exit: an error only sets `st` and the remaining steps are skipped, so that in the thread-per-stream kernel
     // the lanes of a warp meet again after every conditional part (a `return` inside would let the lanes that skip a
     // part run ahead of the others).
@@ -1515,7 +1695,7 @@ BRO_FN void bro_stage_roots(BroDec& d, BroScratch& sc, const BroMbInfo& mb) {
 // one compressed meta-block after MLEN / ISUNCOMPRESSED: src/lib.rs:1745-2141
 BRO_FN int bro_decode_compressed_metablock(BroDec& d, uint32_t mlen) {
     BroMbInfo mb;
-    BroScratch& sc = *d.sc;
+    BroScratch& sc = BRO_DSC(d);
     int st = bro_metablock_tables(d, mb);
     if (st) return st;
     bro_stage_roots(d, sc, mb);

@@ -9,6 +9,15 @@
 
 extern "C" const uint8_t bro_dictionary_blob[];
 
+// the decoder's on-chip block (lane 3 of 32, with the device's interleave: BroTl) and the three root tables behind it
+static void bro_hostsim_bind(BroDec& d, uint8_t* mem) {
+    BroTl tl;
+    tl.base = mem + 4u * 3u;
+    bro_scratch_bind(d.scv, tl);
+    uint16_t* roots = (uint16_t*)(mem + 32u * BRO_TL_BYTES);
+    d.scv.root_lit = roots; d.scv.root_cmd = roots + 256; d.scv.root_dist = roots + 512;
+}
+
 // arena_u16 = 0 selects the worst-case arena of the warp kernel; BRO_THREAD_ARENA_U16 simulates the thread kernel
 // (which may answer BRO_ST_ArenaTooSmall, upon which the product re-runs the stream with the warp kernel).
 extern "C" int bro_hostsim_decode(const uint8_t* in, size_t in_len, uint8_t* out, size_t cap, size_t* out_len, int quirks,
@@ -16,9 +25,9 @@ extern "C" int bro_hostsim_decode(const uint8_t* in, size_t in_len, uint8_t* out
     if (arena_u16 == 0) arena_u16 = BRO_ARENA_U16_MAX;
     BroDec d;
     memset(&d, 0, sizeof(d));
-    BroScratch* sc = (BroScratch*)calloc(1, sizeof(BroScratch));
+    uint8_t* sc = (uint8_t*)calloc(32u * BRO_TL_BYTES + 3u * 256u * sizeof(uint16_t), 1);
     uint16_t* arena = (uint16_t*)malloc(2u * (size_t)arena_u16);
-    d.sc = sc;
+    bro_hostsim_bind(d, sc);
     d.arena = arena;
     d.arena_cap = arena_u16;
     d.arena_base = 0;
@@ -47,9 +56,9 @@ extern "C" int bro_hostsim_decode_resume(const uint8_t* in, size_t in_len, uint8
                                          BroResume* ck) {
     BroDec d;
     memset(&d, 0, sizeof(d));
-    BroScratch* sc = (BroScratch*)calloc(1, sizeof(BroScratch));
+    uint8_t* sc = (uint8_t*)calloc(32u * BRO_TL_BYTES + 3u * 256u * sizeof(uint16_t), 1);
     uint16_t* arena = (uint16_t*)malloc(2u * (size_t)BRO_ARENA_U16_MAX);
-    d.sc = sc;
+    bro_hostsim_bind(d, sc);
     d.arena = arena;
     d.arena_cap = BRO_ARENA_U16_MAX;
     d.arena_base = 0;

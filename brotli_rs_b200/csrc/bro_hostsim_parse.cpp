@@ -38,9 +38,13 @@ extern "C" int bro_hostsim_parse_decode(const uint8_t* in, size_t in_len, uint8_
     memset(&d, 0, sizeof(d));
     uint16_t* arena = (uint16_t*)malloc(2u * (size_t)arena_u16);
     BroRec* rec = (BroRec*)malloc(sizeof(BroRec) * (size_t)rec_cap);
-    BroScratch sc;
-    memset(&sc, 0, sizeof(sc));
-    d.sc = &sc;
+    // the thread's on-chip block, with the device's interleave: lane 7 of 32 (bro_decoder_core.h, BroTl)
+    uint8_t* blocks = (uint8_t*)calloc(32u * BRO_TL_BYTES, 1);
+    {
+        BroTl tl;
+        tl.base = blocks + 4u * 7u;
+        bro_scratch_bind(d.scv, tl);
+    }
     d.arena = arena;
     d.arena_cap = arena_u16;
     d.arena_base = 0;
@@ -53,10 +57,9 @@ extern "C" int bro_hostsim_parse_decode(const uint8_t* in, size_t in_len, uint8_
     d.p1 = d.p2 = 0;
     d.d0 = 4; d.d1 = 11; d.d2 = 15; d.d3 = 16;
     d.quirk_spec = quirks;
-    uint16_t roots[BRO_ROOTS_U16], roots_cd[BRO_ROOTS_CD_U16];
     static uint32_t ic[2 * 704];
     for (unsigned i = 0; i < 704; i++) { ic[2 * i] = bro_ic_insert[i]; ic[2 * i + 1] = bro_ic_copy[i]; }
-    d.rec = rec; d.nrec = 0; d.rec_cap = rec_cap; d.in_base = in; d.roots = roots; d.roots_cd = roots_cd; d.ic = ic;
+    d.rec = rec; d.nrec = 0; d.rec_cap = rec_cap; d.in_base = in; d.ic = ic;
     bro_bits_init(d.in, in, in + in_len);
     BroParse ps;
     BroMbInfo mb;
@@ -90,5 +93,6 @@ extern "C" int bro_hostsim_parse_decode(const uint8_t* in, size_t in_len, uint8_
     if (n_steps) *n_steps = steps;
     free(rec);
     free(arena);
+    free(blocks);
     return ps.st;
 }

@@ -19,23 +19,13 @@
 #include "bro_parse.h"
 #include "bro_kernels.h"
 
+// One CTA per SM: BRO_PARSE_BLOCK threads, each with its lane-interleaved block of BRO_TL_BYTES of shared memory
+// (384 x 576 B = 216 KB) + the insert/copy length table (5.5 KB) = 222 KB of the SM's 227 KB.
 #ifndef BRO_PARSE_BLOCK
-#if defined(BRO_PARSE_ALL_SMEM)
-#define BRO_PARSE_BLOCK 192
-#else
-#define BRO_PARSE_BLOCK 128
+#define BRO_PARSE_BLOCK 384
 #endif
-#endif
-#ifndef BRO_PARSE_MIN_BLOCKS
-#if defined(BRO_PARSE_ALL_SMEM)
 #define BRO_PARSE_MIN_BLOCKS 1
-#elif defined(BRO_PARSE_LIT_SMEM)
-#define BRO_PARSE_MIN_BLOCKS 2
-#else
-#define BRO_PARSE_MIN_BLOCKS 4
-#endif
-#endif
-#define BRO_PARSE_SMEM (BRO_PARSE_BLOCK * BRO_ROOTS_CD_U16 * 2u)     // 32 KiB, or 96 KiB with the literal root (2 CTAs per SM)
+#define BRO_PARSE_SMEM (BRO_PARSE_BLOCK * BRO_TL_BYTES)
 #ifndef BRO_PARSE_PATIENCE
 #define BRO_PARSE_PATIENCE 1024u
 #endif
@@ -50,14 +40,10 @@ __global__ void __launch_bounds__(BRO_PARSE_BLOCK, BRO_PARSE_MIN_BLOCKS) bro_par
     BroDec d;
     BroParse ps;
     BroMbInfo mb;
-    // The scratch of the table reader lives in LOCAL memory: the lanes of a warp read their scratch at the same index
-    // at the same time (they enter headers together), which local memory's lane-interleaved layout turns into one
-    // cache line per warp access; in the arena every access would be a separate trip to L2 / HBM.
-    BroScratch sc;
-    // shared memory: per thread the roots of its current insert&copy and distance tables (256 B) [and of its literal
-    // table, 512 B], per CTA the insert/copy length table; the rest of a thread's literal table is in the compact HBM
-    // array p.roots (bro_parse.h)
-    extern __shared__ __align__(16) uint16_t s_roots_cd[];
+    // shared memory: per warp 32 lane-interleaved blocks (the table reader's scratch while a header is read, the decode
+    // tables of the current block types inside a meta-block: bro_decoder_core.h, bro_parse.h), per CTA the
+    // insert/copy length table.  Nothing of a thread's working set is in local memory.
+    extern __shared__ __align__(16) uint8_t s_blocks[];
     __shared__ uint32_t s_ic[2 * 704];
     for (unsigned i = threadIdx.x; i < 704u; i += BRO_PARSE_BLOCK) { s_ic[2 * i] = bro_ic_insert[i]; s_ic[2 * i + 1] = bro_ic_copy[i]; }
     __syncthreads();
@@ -65,9 +51,11 @@ __global__ void __launch_bounds__(BRO_PARSE_BLOCK, BRO_PARSE_MIN_BLOCKS) bro_par
     uint32_t waited = 0;          // warp-uniform: trips since the first lane reached a boundary
     bool exhausted = false;       // warp-uniform: the queue is empty
     ps.kind = BRO_K_DONE; ps.st = -1;   // st < 0: no stream to report
-    d.sc = &sc;
-    d.roots = p.roots + (size_t)t * BRO_ROOTS_U16;
-    d.roots_cd = s_roots_cd + (size_t)threadIdx.x * BRO_ROOTS_CD_U16;
+    {
+        BroTl tl;
+        tl.base = (uint32_t)__cvta_generic_to_shared(s_blocks) + (threadIdx.x >> 5) * (32u * BRO_TL_BYTES) + 4u * lane;
+        bro_scratch_bind(d.scv, tl);
+    }
     d.ic = s_ic;
     d.arena = arena;
     d.arena_cap = BRO_THREAD_ARENA_U16;
@@ -215,7 +203,7 @@ extern "C" int bro_parse_kernel_occupancy(int* blocks_per_sm) {
 }
 extern "C" int bro_parse_kernel_block() { return BRO_PARSE_BLOCK; }
 extern "C" size_t bro_parse_kernel_arena_bytes() { return 2u * (size_t)BRO_THREAD_ARENA_STRIDE_U16; }
-extern "C" size_t bro_parse_kernel_roots_bytes() { return 2u * (size_t)BRO_ROOTS_U16; }   // per thread, in HBM
+extern "C" size_t bro_parse_kernel_roots_bytes() { return 0; }   // (round 1 kept literal tables in HBM; everything is on chip now)
 
 extern "C" int bro_parse_kernel_launch(const BroLaunch* p, int grid, cudaStream_t stream) {
     bro_parse_kernel<<<grid, BRO_PARSE_BLOCK, BRO_PARSE_SMEM, stream>>>(*p);

@@ -35,47 +35,29 @@
 #define BRO_PARSE_LITS_PER_ROUND 8
 #endif
 
-// What bounds this kernel is not instruction issue but the number of L2 / HBM round trips on a lane's critical path:
-// one per look-up in a table of the arena, one per access to a spilled variable (the threads' stacks do not fit L1).
-// So everything a round touches is kept close: the state below in registers (the canonical limits and bases of the
-// literal code included); 6-bit roots of the current insert&copy and distance tables (their alphabets are skewed: the
-// codes that matter are short; a miss is settled by the table's own 8-bit root in HBM, one round trip, and only then by
-// the canonical search, four) and the insert/copy length table in shared memory; the literal table -- the one table
-// too big to keep on chip for 384 streams per SM -- as 8-bit root plus symbols in canonical order in a compact HBM
-// array: one round trip per literal, two for a code longer than 8 bits.
-#define BRO_RB_LIT 8u
+// What bounded this kernel in round 1 was not instruction issue but the L2 / HBM round trips on a lane's critical path
+// (one per look-up in a table of the arena, one per access to local memory: the threads' stacks did not fit L1), and a
+// warp pays for the slowest of its 32 lanes at every step.  So everything a round touches is on chip now, in the
+// thread's lane-interleaved block of shared memory (BroTl, bro_decoder_core.h) or in registers:
+//   * literals: CANONICAL decode, no root table -- the 15 left-justified limits of the code in registers, the 256
+//     symbols in canonical order as bytes in the block.  A literal of ANY length costs ~30 register instructions and
+//     ONE conflict-free shared-memory look-up, never a trip to L2 (an 8-bit root would take 512 bytes per stream and
+//     still send every longer code off chip: 8 % of the literals of the headline streams);
+//   * insert&copy and distance symbols: narrow roots in the block (their alphabets are skewed: the codes that matter
+//     are short); a miss is settled by the table's own 8-bit root in the arena (one round trip), and only then by the
+//     canonical search (four);
+//   * the insert/copy length table: shared memory, one copy per CTA.
 #ifndef BRO_RB_CMD
-#define BRO_RB_CMD 6u
+#define BRO_RB_CMD 7u
 #endif
 #ifndef BRO_RB_DIST
-#define BRO_RB_DIST 6u
+#define BRO_RB_DIST 5u
 #endif
-// Two placements of the literal root, both measured on B200 (profiles/r01_kernel_variants.md):
-//   default: in the thread's compact HBM array (an L2 round trip per literal) -- 256 B of shared memory per thread
-//            (insert&copy and distance roots), 384 streams per SM: best on the headline high-ratio workload;
-//   BRO_PARSE_LIT_SMEM: in shared memory -- 768 B per thread, 256 streams per SM: best on literal-heavy streams.
-// d.roots (HBM, L2): the 256 symbols of the literal code in canonical order, one byte each (looked up only for a code
-// longer than 8 bits) [, the 8-bit literal root]
-#if defined(BRO_PARSE_ALL_SMEM)
-//   BRO_PARSE_ALL_SMEM: root and symbols in shared memory -- 1,024 B per thread, one CTA of 192 streams per SM.
-#define BRO_ROOTS_U16 8u
-#define BRO_LIT_ROOT(d) ((d).roots_cd + BRO_ROOTS_CMD + (1u << BRO_RB_CMD) + (1u << BRO_RB_DIST))
-#define BRO_LIT_SORTED(d) ((d).roots_cd + BRO_ROOTS_CMD + (1u << BRO_RB_CMD) + (1u << BRO_RB_DIST) + (1u << BRO_RB_LIT))
-#define BRO_ROOTS_CD_U16 ((1u << BRO_RB_CMD) + (1u << BRO_RB_DIST) + (1u << BRO_RB_LIT) + 128u)
-#elif defined(BRO_PARSE_LIT_SMEM)
-#define BRO_ROOTS_U16 128u
-#define BRO_LIT_ROOT(d) ((d).roots_cd + BRO_ROOTS_CMD + (1u << BRO_RB_CMD) + (1u << BRO_RB_DIST))
-#define BRO_LIT_SORTED(d) ((d).roots)
-#define BRO_ROOTS_CD_U16 ((1u << BRO_RB_CMD) + (1u << BRO_RB_DIST) + (1u << BRO_RB_LIT))
-#else
-#define BRO_ROOTS_U16 (128u + (1u << BRO_RB_LIT))
-#define BRO_LIT_ROOT(d) ((d).roots + 128u)
-#define BRO_LIT_SORTED(d) ((d).roots)
-#define BRO_ROOTS_CD_U16 ((1u << BRO_RB_CMD) + (1u << BRO_RB_DIST))
-#endif
-// d.roots_cd (shared memory): 6-bit roots of the insert&copy and the distance table [, the 8-bit literal root]
-#define BRO_ROOTS_CMD 0u
-#define BRO_ROOTS_DIST (1u << BRO_RB_CMD)
+// the block while a meta-block is being decoded (bytes; the header's scratch uses the same bytes, BRO_TL_* )
+#define BRO_TLB_LIT 0u                                   // uint8[256]: symbols of the current literal code in canonical order
+#define BRO_TLB_CMD 256u                                 // uint16[1 << BRO_RB_CMD]: root of the current insert&copy code
+#define BRO_TLB_DIST (BRO_TLB_CMD + (2u << BRO_RB_CMD))  // uint16[1 << BRO_RB_DIST]: root of the distance code (when there is one)
+static_assert(BRO_TLB_DIST + (2u << BRO_RB_DIST) <= BRO_TL_BYTES, "the decode tables must fit the thread's block");
 
 #if defined(BRO_HOSTSIM)
 BRO_FN bool bro_any(bool p) { return p; }
@@ -97,8 +79,11 @@ struct BroParse {
     uint32_t is_last;         // ISLAST of the current meta-block
     uint32_t started;         // the stream header has been read
     uint32_t npostfix, ndirect, o_dist;   // of the current meta-block (copies of BroMbInfo fields, which lives on the stack)
-    // the current literal code beyond its root: limit[9..15] and base[9..15] (two per word), maximum length, single symbol
-    uint32_t lit_lim[4], lit_base[4], lit_misc;   // lit_misc = max length | single flag << 8 | single symbol << 16
+    // the current literal code: lit_lim[k] = left-justified 15-bit end of all codes of length <= k + 1; lit_dbb[k] =
+    // 65536 + base[k + 2] - base[k + 1] (base[L] = canonical index of the first code of length L minus its value), so
+    // that ONE sum over the limits the next 15 bits reach yields both the code's length and its base (bro_parse_lit)
+    uint32_t lit_lim[15], lit_dbb[15];
+    uint32_t lit_misc;        // max length | single flag << 8 | single symbol << 16
     int st;                   // final status once kind == BRO_K_DONE
 };
 
@@ -106,61 +91,109 @@ BRO_FN void bro_parse_begin(BroParse& ps) {
     ps.kind = BRO_K_HEADER; ps.toff_cmd = 0; ps.toff_lit = 0; ps.ins_rem = 0; ps.copy_len = 0; ps.dcode = 0; ps.need_dist = 0;
     ps.mb_begin = 0; ps.mlen = 0; ps.blen0 = ps.blen1 = ps.blen2 = 0; ps.multi = 0; ps.is_last = 0; ps.started = 0; ps.st = 0;
     ps.npostfix = 0; ps.ndirect = 0; ps.o_dist = 0; ps.lit_misc = 0;
-    for (int i = 0; i < 4; i++) { ps.lit_lim[i] = 0; ps.lit_base[i] = 0; }
+#pragma unroll
+    for (int i = 0; i < 15; i++) { ps.lit_lim[i] = 0; ps.lit_dbb[i] = 65536u; }
 }
 
 BRO_FN void bro_parse_finish(BroParse& ps, int st) { ps.st = st; ps.kind = BRO_K_DONE; }
 
-// Make T the current literal table: root and canonical-order symbols into the thread's compact array, limits and bases
-// of the long codes into registers.
-BRO_FN void bro_parse_load_lit(BroParse& ps, uint16_t* lit_sorted, uint16_t* lit_root, const uint16_t* T) {
-    bro_narrow_root(lit_root, BRO_RB_LIT, T);
-#pragma unroll
-    for (uint32_t k = 0; k < 4u; k++) {
-        // word k holds lengths 9 + 2k (low half) and 10 + 2k (high half); length 16 does not exist: limit 0xffff
-        const uint32_t L0 = 9u + 2u * k, L1 = 10u + 2u * k;
-        ps.lit_lim[k] = (uint32_t)T[BRO_T_LIMIT + L0] | ((L1 <= 15u ? (uint32_t)T[BRO_T_LIMIT + L1] : 0xffffu) << 16);
-        ps.lit_base[k] = (uint32_t)T[BRO_T_BASE + L0] | ((L1 <= 15u ? (uint32_t)T[BRO_T_BASE + L1] : 0u) << 16);
+// Narrow copy of a table's root in the thread's block: entry r is a direct hit (symbol | len<<10, len <= root_bits) or
+// 1 = settle it in the table itself.
+BRO_FN void bro_narrow_root_tl(BroTl t, uint32_t off, uint32_t root_bits, const uint16_t* T) {
+#pragma unroll 4
+    for (uint32_t r = 0; r < (1u << root_bits); r += 2u) {     // the table's root is 4-byte aligned: two entries per load, four loads in flight
+        const uint32_t ee = *(const uint32_t*)(T + r);
+        const uint32_t e0 = ee & 0xffffu, e1 = ee >> 16, l0 = e0 >> 10, l1 = e1 >> 10;
+        bro_tl_st32(t, off + 2u * r, ((l0 >= 1u && l0 <= root_bits) ? e0 : 1u) | (((l1 >= 1u && l1 <= root_bits) ? e1 : 1u) << 16));
     }
-    ps.lit_misc = (uint32_t)T[BRO_T_MAXDEPTH] | (T[BRO_T_SINGLE] ? 0x100u : 0u) | ((uint32_t)T[BRO_T_SINGLE_SYM] << 16);
-    uint8_t* sorted = (uint8_t*)lit_sorted;
-#pragma unroll 8
-    for (uint32_t i = 0; i < 256u; i++) sorted[i] = (uint8_t)T[BRO_T_SORTED + i];
 }
 
-// The part of a literal decode behind a root miss (entry without a length): a code longer than 8 bits -- a search of the
-// limits held in registers and ONE look-up of the symbol --, a one-symbol code, or no code at all.  Consumes the bits.
-BRO_FN int bro_parse_lit_long(BroBits& s, const BroParse& ps, const uint16_t* lit_sorted, uint32_t peek, uint32_t& sym) {
-    const uint32_t avail = bro_avail(s);
-    uint32_t len = 0;
-    if (ps.lit_misc & 0x100u) sym = ps.lit_misc >> 16;                        // one symbol: zero bits
-    else {
-        const uint32_t x = bro_brev(peek) >> 17;                               // next 15 bits, first bit read most significant
-        // smallest L in 9..15 with x < limit[L] (limits grow with L)
-        uint32_t L = 16u, base = 0;
-#pragma unroll
-        for (int k = 3; k >= 0; k--) {
-            const uint32_t lo = ps.lit_lim[k] & 0xffffu, hi = ps.lit_lim[k] >> 16;
-            if (k < 3 && x < hi) { L = 10u + 2u * (uint32_t)k; base = ps.lit_base[k] >> 16; }
-            if (x < lo) { L = 9u + 2u * (uint32_t)k; base = ps.lit_base[k] & 0xffffu; }
-        }
-        if (L > 15u) return (avail >= (ps.lit_misc & 0xffu) + 1u) ? BRO_SYM_HOLE : BRO_SYM_EOF;
-        len = L;
-        sym = ((const uint8_t*)lit_sorted)[((int)(int16_t)base + (int)(x >> (15u - L))) & 255];
+// One symbol through such a copy (same results as bro_decode_sym on the table).
+BRO_FN int bro_decode_sym_tl(BroBits& s, BroTl t, uint32_t off, uint32_t root_bits, const uint16_t* T, uint32_t& sym) {
+    bro_refill(s);
+    uint32_t peek = bro_peek(s);
+    uint32_t e = bro_tl_ld16(t, off + 2u * (peek & ((1u << root_bits) - 1u)));
+    uint32_t len = e >> 10;
+    if (len != 0u) {
+        if (len > bro_avail(s)) return BRO_SYM_EOF;
+        bro_consume(s, len);
+        sym = e & 0x3ffu;
+        return BRO_SYM_OK;
     }
-    if (len > avail) return BRO_SYM_EOF;
-    bro_consume(s, len);
+    // not in the narrow copy: the table's own 8-bit root settles codes of up to 8 bits with one look-up; only what is
+    // longer takes the canonical search (four dependent look-ups)
+    e = T[peek & (BRO_ROOT_SIZE - 1u)];
+    len = e >> 10;
+    if (len != 0u) {
+        if (len > bro_avail(s)) return BRO_SYM_EOF;
+        bro_consume(s, len);
+        sym = e & 0x3ffu;
+        return BRO_SYM_OK;
+    }
+    uint32_t r = bro_sym_slow(T, peek, e, bro_avail(s));
+    bro_consume(s, (r >> 16) & 0xffu);
+    sym = r & 0xffffu;
+    return (int)(r >> 24);
+}
+
+// Make T the current literal table: symbols in canonical order into the thread's block, limits and base differences
+// into registers.
+BRO_FN void bro_parse_load_lit(BroParse& ps, BroTl t, const uint16_t* T) {
+    int prev = (int)(int16_t)T[BRO_T_BASE + 1u];             // = 0: the first code of length 1 is code 0 at index 0
+#pragma unroll
+    for (uint32_t k = 0; k < 15u; k++) {
+        ps.lit_lim[k] = T[BRO_T_LIMIT + 1u + k];
+        const int next = k < 14u ? (int)(int16_t)T[BRO_T_BASE + 2u + k] : prev;
+        ps.lit_dbb[k] = (uint32_t)(65536 + next - prev);
+        prev = next;
+    }
+    ps.lit_misc = (uint32_t)T[BRO_T_MAXDEPTH] | (T[BRO_T_SINGLE] ? 0x100u : 0u) | ((uint32_t)T[BRO_T_SINGLE_SYM] << 16);
+    // sorted[] starts 8 bytes into a 16-byte granule of the table record: 64 loads of four symbols, eight in flight
+#pragma unroll 8
+    for (uint32_t i = 0; i < 64u; i++) {
+#if defined(__CUDACC__)
+        const uint2 v = ((const uint2*)(T + BRO_T_SORTED))[i];
+        const uint32_t vx = v.x, vy = v.y;
+#else
+        const uint32_t vx = ((const uint32_t*)(T + BRO_T_SORTED))[2u * i], vy = ((const uint32_t*)(T + BRO_T_SORTED))[2u * i + 1u];
+#endif
+        bro_tl_st32(t, BRO_TLB_LIT + 4u * i, (vx & 0xffu) | ((vx >> 8) & 0xff00u) | ((vy & 0xffu) << 16) | ((vy >> 16) << 24));
+    }
+}
+
+// One literal of the current code from the next bits `peek` (same results as bro_decode_sym on the table;
+// src/huffman/tree/mod.rs:63-92).  Canonical decode: the code's length is 1 + the number of limits the next 15 bits
+// (first bit most significant) reach, its symbol sits at base[length] + (bits >> (15 - length)) of the canonical order.
+// -> BRO_SYM_*; len = bits to consume (not consumed here: the caller knows whether `avail` must be checked).
+BRO_FN int bro_parse_lit(const BroParse& ps, BroTl t, uint32_t peek, uint32_t avail, uint32_t& sym, uint32_t& len) {
+    const uint32_t x = bro_brev(peek) >> 17;
+    uint32_t acc0 = 0, acc1 = 0, acc2 = 0;                   // three partial sums: a shorter dependency chain
+#pragma unroll
+    for (uint32_t k = 0; k < 15u; k += 3u) {
+        if (x >= ps.lit_lim[k]) acc0 += ps.lit_dbb[k];
+        if (x >= ps.lit_lim[k + 1u]) acc1 += ps.lit_dbb[k + 1u];
+        if (x >= ps.lit_lim[k + 2u]) acc2 += ps.lit_dbb[k + 2u];
+    }
+    const uint32_t acc = acc0 + acc1 + acc2;
+    const uint32_t count = (acc + 32768u) >> 16;             // limits reached (|base| < 32768)
+    if (count >= 15u) {
+        // no code starts with these bits: a one-symbol code (zero bits), or a hole / the end of the input
+        len = 0;
+        if (ps.lit_misc & 0x100u) { sym = ps.lit_misc >> 16; return BRO_SYM_OK; }
+        return (avail >= (ps.lit_misc & 0xffu) + 1u) ? BRO_SYM_HOLE : BRO_SYM_EOF;
+    }
+    len = count + 1u;
+    const int base = (int)(acc - (count << 16));
+    sym = bro_tl_ld8(t, BRO_TLB_LIT + ((uint32_t)(base + (int)(x >> (14u - count))) & 255u));
     return BRO_SYM_OK;
 }
 
-// One literal (same results as bro_decode_sym on the table; src/huffman/tree/mod.rs:63-92).
-BRO_FN int bro_parse_decode_lit(BroBits& s, const BroParse& ps, const uint16_t* lit_sorted, const uint16_t* lit_root, uint32_t& sym) {
+// The same with the end-of-input check, consuming the bits.
+BRO_FN int bro_parse_decode_lit(BroBits& s, const BroParse& ps, BroTl t, uint32_t& sym) {
     bro_refill(s);
-    const uint32_t peek = bro_peek(s);
-    const uint32_t e = lit_root[peek & 0xffu];
-    const uint32_t len = e >> 10;
-    sym = e & 0x3ffu;
-    if (len == 0u) return bro_parse_lit_long(s, ps, lit_sorted, peek, sym);
+    uint32_t len = 0;
+    const int r = bro_parse_lit(ps, t, bro_peek(s), bro_avail(s), sym, len);
+    if (r != BRO_SYM_OK) return r;
     if (len > bro_avail(s)) return BRO_SYM_EOF;
     bro_consume(s, len);
     return BRO_SYM_OK;
@@ -196,8 +229,8 @@ BRO_FN bool bro_parse_block_step(BroDec& d, BroParse& ps, BroMbInfo& mb, uint32_
         mb.cat[c] = tc;
         if (st) { bro_parse_finish(ps, st); return false; }
         bl = tc.blen + 1u;
-        if (c == 0u) { ps.toff_lit = bro_parse_table(d, ps, mb, 0u); bro_parse_load_lit(ps, BRO_LIT_SORTED(d), BRO_LIT_ROOT(d), d.arena + ps.toff_lit); }
-        else if (c == 1u) { ps.toff_cmd = bro_parse_table(d, ps, mb, 1u); bro_narrow_root(d.roots_cd + BRO_ROOTS_CMD, BRO_RB_CMD, d.arena + ps.toff_cmd); }
+        if (c == 0u) { ps.toff_lit = bro_parse_table(d, ps, mb, 0u); bro_parse_load_lit(ps, d.scv.t, d.arena + ps.toff_lit); }
+        else if (c == 1u) { ps.toff_cmd = bro_parse_table(d, ps, mb, 1u); bro_narrow_root_tl(d.scv.t, BRO_TLB_CMD, BRO_RB_CMD, d.arena + ps.toff_cmd); }
     }
     bl -= 1u;
     if (c == 0u) ps.blen0 = bl; else if (c == 1u) ps.blen1 = bl; else ps.blen2 = bl;
@@ -230,15 +263,61 @@ BRO_FN void bro_parse_header(BroDec& d, BroParse& ps, BroMbInfo& mb) {
             ps.blen0 = mb.cat[0].blen; ps.blen1 = mb.cat[1].blen; ps.blen2 = mb.cat[2].blen;
             ps.toff_cmd = bro_parse_table(d, ps, mb, 1u);
             ps.toff_lit = bro_parse_table(d, ps, mb, 0u);
-            bro_parse_load_lit(ps, BRO_LIT_SORTED(d), BRO_LIT_ROOT(d), d.arena + ps.toff_lit);
-            bro_narrow_root(d.roots_cd + BRO_ROOTS_CMD, BRO_RB_CMD, d.arena + ps.toff_cmd);
-            if (mb.ntd == 1u) { ps.multi |= 8u; bro_narrow_root(d.roots_cd + BRO_ROOTS_DIST, BRO_RB_DIST, d.arena + mb.o_dist); }
+            bro_parse_load_lit(ps, d.scv.t, d.arena + ps.toff_lit);
+            bro_narrow_root_tl(d.scv.t, BRO_TLB_CMD, BRO_RB_CMD, d.arena + ps.toff_cmd);
+            if (mb.ntd == 1u) { ps.multi |= 8u; bro_narrow_root_tl(d.scv.t, BRO_TLB_DIST, BRO_RB_DIST, d.arena + mb.o_dist); }
             ps.npostfix = mb.npostfix; ps.ndirect = mb.ndirect; ps.o_dist = mb.o_dist;
             ps.kind = BRO_K_CMD;
             return;
         }
     }
     bro_parse_finish(ps, st == BRO_MB_END ? BRO_ST_OK : st);
+}
+
+// Static dictionary word + transform (src/lib.rs:1506-1540, src/transformation/mod.rs:84-209) for one thread: the
+// geometry first (transformed length, or -1 where the reference panics: uppercase_first on a 0x00 byte), so
+// that the caller can run its checks; then the bytes straight into the output slot -- no staging buffer, the UTF-8 walk
+// of the uppercase transforms is applied as the bytes pass.  Same results as bro_dict_word.
+BRO_FN int bro_parse_dict_geometry(const uint8_t* dict, int quirk_spec, uint32_t copy_len, uint32_t index, uint32_t tid, uint32_t& from, uint32_t& wl) {
+    const uint32_t type = bro_xf_type[tid];
+    from = 0; wl = copy_len;
+    if (type >= 3u && type <= 11u) {            // OmitFirstN: base_word[min(N, len-1)..] (Q3) / spec: [min(N,len)..]
+        const uint32_t n = type - 2u;
+        from = quirk_spec ? (n < wl ? n : wl) : (n < wl - 1u ? n : wl - 1u);
+        wl -= from;
+    } else if (type >= 12u) {                   // OmitLastN: base_word[..max(N,len)-N]
+        const uint32_t n = type - 11u;
+        wl = (wl > n ? wl : n) - n;
+    }
+    if (type == 1u && !quirk_spec) {
+        // what the reference looks at is the byte behind the prefix: the word's first byte, or -- for an empty word,
+        // which uppercase_first cannot get -- nothing
+        if (dict[bro_dict_offsets[copy_len] + index * copy_len] == 0u) return -1;
+    }
+    return (int)(bro_xf_prefix_len[tid] + wl + bro_xf_suffix_len[tid]);
+}
+
+BRO_FN void bro_parse_dict_emit(uint8_t* o, const uint8_t* dict, uint32_t copy_len, uint32_t index, uint32_t tid, uint32_t from, uint32_t wl) {
+    const uint32_t type = bro_xf_type[tid], plen = bro_xf_prefix_len[tid], slen = bro_xf_suffix_len[tid];
+    const uint8_t* w = dict + bro_dict_offsets[copy_len] + index * copy_len + from;
+    for (uint32_t i = 0; i < plen; i++) o[i] = bro_xf_strings[bro_xf_prefix_off[tid] + i];
+    o += plen;
+    // uppercase_first (src/transformation/mod.rs:42-82) / uppercase_all (3-40): position `dec` decides -- an ASCII
+    // letter is flipped itself, a 2- / 3-byte UTF-8 lead flips bit 5 of the next / bits 0 and 2 of the byte after the
+    // next -- and the walk continues behind what it touched (uppercase_first: one decision only)
+    uint32_t dec = (type == 1u || type == 2u) ? 0u : 0xffffffffu, tpos = 0xffffffffu, txor = 0;
+    for (uint32_t i = 0; i < wl; i++) {
+        uint32_t c = w[i];
+        if (i == dec) {
+            if (c < 192u) { if (c >= 97u && c <= 122u) c ^= 32u; dec = i + 1u; }
+            else if (c < 224u) { tpos = i + 1u; txor = 32u; dec = i + 2u; }
+            else { tpos = i + 2u; txor = 5u; dec = i + 3u; }
+            if (type == 1u) dec = 0xffffffffu;
+        } else if (i == tpos) c ^= txor;
+        o[i] = (uint8_t)c;
+    }
+    o += wl;
+    for (uint32_t i = 0; i < slen; i++) o[i] = bro_xf_strings[bro_xf_suffix_off[tid] + i];
 }
 
 // One ROUND of the machine: every lane that is inside a meta-block advances by (at most) one command -- its
@@ -249,7 +328,7 @@ BRO_FN void bro_parse_round(BroDec& d, BroParse& ps, BroMbInfo& mb) {
     // ---- step 1: insert&copy command symbol and its extra bits ----
     if (ps.kind == BRO_K_CMD && bro_parse_block_step(d, ps, mb, 1u)) {
         uint32_t sym = 0;
-        const int r = bro_decode_sym_r(d.in, d.roots_cd + BRO_ROOTS_CMD, BRO_RB_CMD, d.arena + ps.toff_cmd, sym);
+        const int r = bro_decode_sym_tl(d.in, d.scv.t, BRO_TLB_CMD, BRO_RB_CMD, d.arena + ps.toff_cmd, sym);
         if (r != BRO_SYM_OK) bro_parse_finish(ps, r == BRO_SYM_HOLE ? BRO_ST_ParseErrorInsertAndCopyLength : BRO_ST_UnexpectedEOF);
         else {
             const uint32_t ie = d.ic[2u * sym], ce = d.ic[2u * sym + 1u];        // bro_ic_insert / bro_ic_copy, interleaved on chip
@@ -285,7 +364,7 @@ BRO_FN void bro_parse_round(BroDec& d, BroParse& ps, BroMbInfo& mb) {
             if ((ps.multi & 1u) && ps.blen0 < n) n = ps.blen0;     // literals left in the current block (0: a switch is due)
             if (d.pos <= d.cap && n <= d.cap - d.pos && bro_avail(d.in) >= 16u * n) fast = n;
         }
-        const uint16_t* const lit_root = BRO_LIT_ROOT(d);
+        const BroTl tl = d.scv.t;
         uint8_t* op = d.out + d.pos;
         uint32_t done = 0;
 #pragma unroll 1
@@ -293,15 +372,14 @@ BRO_FN void bro_parse_round(BroDec& d, BroParse& ps, BroMbInfo& mb) {
             if (!bro_any(u < fast)) break;
             if (u < fast) {
                 bro_refill(d.in);
-                const uint32_t peek = bro_peek(d.in);
-                const uint32_t e = lit_root[peek & 0xffu];
-                uint32_t len = e >> 10, sym = e;
-                if (len == 0u) {
-                    // a code longer than 8 bits, a one-symbol code, or no code at all: the general decoder
-                    const int r = bro_parse_lit_long(d.in, ps, BRO_LIT_SORTED(d), peek, sym);
-                    if (r != BRO_SYM_OK) { bro_parse_finish(ps, r == BRO_SYM_HOLE ? BRO_ST_ParseErrorInsertLiterals : BRO_ST_UnexpectedEOF); fast = 0; }
-                } else bro_consume(d.in, len);
-                if (fast) { if (!d.sizing) op[u] = (uint8_t)sym; done = u + 1u; }
+                uint32_t sym = 0, len = 0;
+                const int r = bro_parse_lit(ps, tl, bro_peek(d.in), bro_avail(d.in), sym, len);
+                if (r != BRO_SYM_OK) { bro_parse_finish(ps, r == BRO_SYM_HOLE ? BRO_ST_ParseErrorInsertLiterals : BRO_ST_UnexpectedEOF); fast = 0; }
+                else {
+                    bro_consume(d.in, len);
+                    if (!d.sizing) op[u] = (uint8_t)sym;
+                    done = u + 1u;
+                }
             }
         }
         if (done != 0u && ps.kind == BRO_K_LIT) {
@@ -318,7 +396,7 @@ BRO_FN void bro_parse_round(BroDec& d, BroParse& ps, BroMbInfo& mb) {
         if (!bro_any(slow)) break;
         if (slow && bro_parse_block_step(d, ps, mb, 0u)) {
             uint32_t sym = 0;
-            const int r = bro_parse_decode_lit(d.in, ps, BRO_LIT_SORTED(d), BRO_LIT_ROOT(d), sym);
+            const int r = bro_parse_decode_lit(d.in, ps, d.scv.t, sym);
             if (r != BRO_SYM_OK) bro_parse_finish(ps, r == BRO_SYM_HOLE ? BRO_ST_ParseErrorInsertLiterals : BRO_ST_UnexpectedEOF);
             else {
                 // a run that does not fit the slot is still decoded: a decode error inside it wins over OutputTooSmall
@@ -331,7 +409,7 @@ BRO_FN void bro_parse_round(BroDec& d, BroParse& ps, BroMbInfo& mb) {
     // ---- step 3: distance code ----
     if (ps.kind == BRO_K_DIST && bro_parse_block_step(d, ps, mb, 2u)) {
         uint32_t sym = 0;
-        const int r = (ps.multi & 8u) ? bro_decode_sym_r(d.in, d.roots_cd + BRO_ROOTS_DIST, BRO_RB_DIST, d.arena + ps.o_dist, sym)
+        const int r = (ps.multi & 8u) ? bro_decode_sym_tl(d.in, d.scv.t, BRO_TLB_DIST, BRO_RB_DIST, d.arena + ps.o_dist, sym)
                                       : bro_decode_sym(d.in, d.arena + bro_parse_table(d, ps, mb, 2u), sym);
         if (r != BRO_SYM_OK) bro_parse_finish(ps, r == BRO_SYM_HOLE ? BRO_ST_ParseErrorDistanceCode : BRO_ST_UnexpectedEOF);
         else { ps.dcode = sym; ps.kind = BRO_K_COPY; }
@@ -356,12 +434,13 @@ BRO_FN void bro_parse_round(BroDec& d, BroParse& ps, BroMbInfo& mb) {
                 const uint32_t index = word_id & ((1u << bits) - 1u), tid = word_id >> bits;
                 if (tid > 120u) st = BRO_ST_InvalidTransformId;
                 else {
-                    const int n = bro_dict_word(*d.sc, d.dict, d.quirk_spec, copy_len, index, tid);
+                    uint32_t from = 0, wl = 0;
+                    const int n = bro_parse_dict_geometry(d.dict, d.quirk_spec, copy_len, index, tid, from, wl);
                     if (n < 0) st = BRO_ST_PanicUppercaseZero;
                     else if (ps.mlen < mb_out + (uint32_t)n) st = BRO_ST_ExceededExpectedBytes;                  // after the transform (Q10)
                     else if ((uint32_t)n > d.cap - d.pos) st = BRO_ST_OutputTooSmall;
                     else {
-                        if (!d.sizing) for (uint32_t i = 0; i < (uint32_t)n; i++) d.out[d.pos + i] = d.sc->word[i];
+                        if (!d.sizing) bro_parse_dict_emit(d.out + d.pos, d.dict, copy_len, index, tid, from, wl);
                         d.pos += (uint32_t)n;
                     }
                 }
