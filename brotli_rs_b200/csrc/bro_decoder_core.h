@@ -204,6 +204,9 @@ struct BroTlArray {
     BRO_MFN Ref operator[](uint32_t i) const { Ref r; r.t = t; r.b = OFF + i * (uint32_t)sizeof(T); return r; }
 };
 
+#ifndef BRO_RING_WORDS
+#define BRO_RING_WORDS 6u
+#endif
 // Layout of a block.  While a meta-block HEADER is read it holds the table reader's scratch; inside a meta-block the
 // same bytes hold the decode tables of the current block types (bro_parse.h).  `word` is valid in both.
 #define BRO_TL_LENS 0u          // 704 code lengths, 4 bits each (bro_lens_*); the 256-byte IMTF list once they are dead
@@ -214,7 +217,8 @@ struct BroTlArray {
 #define BRO_TL_CLC 456u         // uint8[32]
 #define BRO_TL_CL 488u          // uint8[18] (+2)
 #define BRO_TL_WORD 512u        // uint8[64]
-#define BRO_TL_BYTES 576u
+#define BRO_TL_RING 576u        // uint32[BRO_RING_WORDS]: the compressed words behind the bit window (BroBits), always live
+#define BRO_TL_BYTES (576u + 4u * BRO_RING_WORDS)
 struct BroScratch {
     BroTl t;
     BroTlArray<uint8_t, BRO_TL_LENS> mtf;      // 256-entry move-to-front list (the code lengths are dead by then)
@@ -284,46 +288,151 @@ BRO_FN void bro_lens_put(BroScratch& sc, uint32_t i, uint32_t v) { sc.lens[i] = 
 #endif
 
 // ------------------------------------------------------------------------------------------------------
-// bit stream: src/bitreader/mod.rs:21-304 restated as a 64-bit LSB-first window.  The warp loads the
-// compressed bytes 128 B at a time (lane i holds word i) and feeds the window by shuffle.
+// bit stream: src/bitreader/mod.rs:21-304 restated as a 64-bit LSB-first window (w0, w1; the next bit is bit `bp` of w0).
 // ------------------------------------------------------------------------------------------------------
+#if defined(BRO_SERIAL)
+// ONE THREAD PER STREAM (and the host simulation of it).  The words behind the window wait in a small RING in the
+// thread's on-chip block (BRO_TL_RING), filled by asynchronous copies global -> shared (cp.async, 4 bytes): a slide takes
+// its word from the ring (a shared-memory load) and requests the word BRO_RING_WORDS positions ahead into the slot it
+// freed.  No register ever holds data in flight -- in round 1 (one word of lookahead in a register) 17 % of the parse
+// kernel's stall samples sat on register moves of words that had not arrived, and with 32 unrelated streams per warp
+// some lane slides in nearly every step, so whatever a slide costs is paid all the time: it has to be cheap, uniform
+// (predicated, no branch) and never exposed to memory latency.  The sector two ahead is asked of DRAM at the same
+// time (prefetch.global.L2).  `avail` counts ALL real bits from `bp` to the end of the stream (streams of 256 MiB
+// and more are left to the fused kernel), so that a slide needs no bookkeeping.
 struct BroBits {
-    const uint8_t* chunk;   // warp/group modes: aligned address of the chunk held in `cur`; 1-lane modes: next word address
+    const uint8_t* base;    // 4-byte aligned address at or below the first byte of the stream
+    const uint8_t* end;     // one past the last byte of the stream
+#if defined(BRO_HOSTSIM)
+    const uint8_t* lo;      // first byte of the stream (host buffers are neither padded nor aligned)
+#endif
+    BroTl ring;             // the thread's block (set once per thread, before bro_bits_init)
+    uint32_t elen;          // end - base
+    uint32_t last;          // offset of the word that holds the stream's last byte
+    uint32_t pos;           // offset (from base) of the word that will be requested next; the ring holds the BRO_RING_WORDS words before it
+    uint32_t ri;            // ring slot of the word that follows w1
+    uint32_t w0, w1;
+    uint32_t bp;            // 0..31 after bro_refill
+    uint32_t avail;
+};
+
+// word at offset o, clamped to the word that holds the stream's last byte: nothing behind that word is ever read.
+// What a word holds behind the end of the stream (neighbouring bytes of the same buffer, or a repeat of the last
+// word) never matters: `avail` keeps every decision on real bits.
+BRO_FN uint32_t bro_word_offset(const BroBits& s, uint32_t o) { return o < s.last ? o : s.last; }
+BRO_FN uint32_t bro_load_word(const BroBits& s, uint32_t o) {
+#if defined(BRO_HOSTSIM)
+    uint32_t w = 0;
+    o = bro_word_offset(s, o);
+    for (uint32_t i = 0; i < 4u; i++) {
+        const uint8_t* p = s.base + o + i;
+        if (p >= s.lo && p < s.end) w |= (uint32_t)*p << (8u * i);
+    }
+    return w;
+#else
+    return __ldg((const uint32_t*)(s.base + bro_word_offset(s, o)));
+#endif
+}
+
+// position the window at byte address `a` (start of stream, or after a stored / metadata block)
+BRO_FN void bro_bits_seek(BroBits& s, const uint8_t* a) {
+    const uint32_t off = (uint32_t)(a - s.base), wo = off & ~3u;
+    s.ri = 0;
+    s.pos = wo + 8u + 4u * BRO_RING_WORDS;
+    s.bp = 8u * (off & 3u);
+    s.avail = a < s.end ? 8u * (uint32_t)(s.end - a) : 0u;
+    if (s.elen == 0u) { s.w0 = s.w1 = 0; return; }            // an empty stream: nothing to read, and nothing is ever consumed
+#if !defined(BRO_HOSTSIM)
+    asm volatile("cp.async.wait_all;");                         // no request of the old position may land in a slot later
+#endif
+    s.w0 = bro_load_word(s, wo);
+    s.w1 = bro_load_word(s, wo + 4u);
+    for (uint32_t j = 0; j < BRO_RING_WORDS; j++) {
+#if defined(BRO_HOSTSIM)
+        bro_tl_st32(s.ring, BRO_TL_RING + 4u * j, bro_load_word(s, wo + 8u + 4u * j));
+#else
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n\tcp.async.commit_group;"
+                     :: "r"(s.ring.base + ((BRO_TL_RING + 4u * j) << 5)), "l"(s.base + bro_word_offset(s, wo + 8u + 4u * j)));
+#endif
+    }
+}
+
+BRO_FN void bro_bits_init(BroBits& s, const uint8_t* start, const uint8_t* end) {
+#if defined(BRO_HOSTSIM)
+    s.lo = start;
+#endif
+    s.base = (const uint8_t*)((uintptr_t)start & ~(uintptr_t)3);
+    s.end = end;
+    s.elen = (uint32_t)(end - s.base);
+    s.last = (s.elen - 1u) & ~3u;
+    bro_bits_seek(s, start);
+}
+
+// Protocol: bro_refill() (slides the window so that bp < 32), then bro_peek() / bro_avail(), then bro_consume() of at
+// most 32 bits.  A lane slides at most once per call, and every call is one cp.async group (of the lanes that slid), so
+// the word a lane takes from the ring was requested at least BRO_RING_WORDS groups ago, however the hardware counts
+// groups (per thread or per warp): waiting for all but the BRO_RING_WORDS - 1 youngest is enough.  One predicated
+// block, no branch: wait, take the word, request the word BRO_RING_WORDS ahead into the freed slot.
+BRO_FN void bro_refill(BroBits& s) {
+#if defined(BRO_HOSTSIM)
+    if (s.bp >= 32u) {
+        s.w0 = s.w1;
+        s.w1 = bro_tl_ld32(s.ring, BRO_TL_RING + 4u * s.ri);
+        bro_tl_st32(s.ring, BRO_TL_RING + 4u * s.ri, bro_load_word(s, s.pos));
+        s.pos += 4u;
+        s.ri = s.ri + 1u == BRO_RING_WORDS ? 0u : s.ri + 1u;
+        s.bp -= 32u;
+    }
+#else
+    asm volatile("{\n\t"
+                 ".reg .pred p, w;\n\t"
+                 ".reg .u32 o, slot;\n\t"
+                 ".reg .u64 a;\n\t"
+                 "setp.ge.u32 p, %2, 32;\n\t"
+                 "mad.lo.u32 slot, %4, 128, %5;\n\t"            // the slot of word ri: interleaved, 128 bytes apart
+                 "min.u32 o, %3, %7;\n\t"
+                 "cvt.u64.u32 a, o;\n\t"
+                 "add.u64 a, a, %6;\n\t"
+                 "@p cp.async.wait_group %8;\n\t"
+                 "@p mov.u32 %0, %1;\n\t"
+                 "@p ld.shared.u32 %1, [slot];\n\t"
+                 "@p cp.async.ca.shared.global [slot], [a], 4;\n\t"
+                 "@p cp.async.commit_group;\n\t"
+                 "@p add.u32 %3, %3, 4;\n\t"
+                 "@p add.u32 %4, %4, 1;\n\t"
+                 "@p sub.u32 %2, %2, 32;\n\t"
+                 "setp.eq.and.u32 w, %4, %9, p;\n\t"
+                 "@w mov.u32 %4, 0;\n\t"
+                 "}"
+                 : "+r"(s.w0), "+r"(s.w1), "+r"(s.bp), "+r"(s.pos), "+r"(s.ri)
+                 : "r"(s.ring.base + (BRO_TL_RING << 5)), "l"(s.base), "r"(s.last), "n"(BRO_RING_WORDS - 1u), "n"(BRO_RING_WORDS));
+#endif
+}
+// byte offset (from base) of window word w0
+BRO_FN uint32_t bro_bits_w0(const BroBits& s) { return s.pos - 4u * BRO_RING_WORDS - 8u; }
+#else
+// ONE WARP (or lane group) PER STREAM: the group loads the compressed bytes 32 words at a time (lane i holds word i,
+// the next chunk is already in flight) and feeds the window by shuffle.
+struct BroBits {
+    const uint8_t* chunk;   // aligned address of the chunk held in `cur`
     const uint8_t* lo;      // first loadable word address (stream start rounded down to 4)
     const uint8_t* end;     // one past the last byte of the stream
     uint32_t w0, w1;        // bit window: two consecutive little-endian words of the stream; next bit = bit `bp` of w0
-#if defined(BRO_THREAD_MODE)
-    uint32_t w2, w3;        // the two words after the window, loaded two slides ahead so that a slide does not wait for L2
-#endif
     uint32_t bp;            // 0..31
     uint32_t avail;         // real stream bits in the window from `bp` on (the rest of w0/w1 is padding past the end)
     uint32_t rem;           // real stream BYTES not yet loaded into the window (a stream is < 4 GiB)
-#if !defined(BRO_SERIAL)
     uint32_t wi;            // next word of the chunk to hand out
     uint32_t cur, nxt;      // this lane's word of the current / next chunk
-#endif
 };
 
 BRO_FN uint32_t bro_load_word(const BroBits& s, const uint8_t* a) {
-#if defined(BRO_HOSTSIM)
-    // host buffers are neither padded nor aligned: assemble the word from the bytes that belong to the stream
-    uint32_t w = 0;
-    for (int i = 0; i < 4; i++) if (a + i >= s.lo && a + i < s.end) w |= (uint32_t)a[i] << (8 * i);
-    return w;
-#else
     // words entirely outside [lo, end) read as zero; words straddling the ends expose neighbouring bytes of the
     // same allocation, which the bit accounting below never lets a decision depend on
     if (a < s.lo || a >= s.end) return 0u;
     return __ldg((const uint32_t*)a);
-#endif
 }
 
 BRO_FN uint32_t bro_next_word(BroBits& s) {
-#if defined(BRO_SERIAL)
-    uint32_t w = bro_load_word(s, s.chunk);
-    s.chunk += 4;
-    return w;
-#else
     uint32_t w = bro_shfl(s.cur, s.wi);
     if (++s.wi == BRO_W) {
         s.cur = s.nxt;
@@ -332,48 +441,28 @@ BRO_FN uint32_t bro_next_word(BroBits& s) {
         s.wi = 0;
     }
     return w;
-#endif
 }
 
 // position the window at byte address `a` (start of stream, or after a stored / metadata block)
 BRO_FN void bro_bits_seek(BroBits& s, const uint8_t* a) {
     uintptr_t ai = (uintptr_t)a;
-#if defined(BRO_SERIAL)
-    s.chunk = (const uint8_t*)(ai & ~(uintptr_t)3);
-#else
     s.chunk = (const uint8_t*)(ai & ~(uintptr_t)(4u * BRO_W - 1u));
     s.wi = (uint32_t)(ai & (4u * BRO_W - 1u)) >> 2;
     s.cur = bro_load_word(s, s.chunk + 4u * bro_lane());
     s.nxt = bro_load_word(s, s.chunk + 4u * BRO_W + 4u * bro_lane());
-#endif
     uint32_t left = a < s.end ? (uint32_t)(s.end - a) : 0u;      // real bytes from `a` on
     uint32_t sh = (uint32_t)(ai & 3u);
     s.w0 = bro_next_word(s);
     s.w1 = bro_next_word(s);
-#if defined(BRO_THREAD_MODE)
-    s.w2 = bro_next_word(s);
-    s.w3 = bro_next_word(s);
-#endif
     s.bp = 8u * sh;
-#if defined(BRO_THREAD_MODE)
-    // one thread per stream: `avail` counts ALL real bits from `bp` to the end of the stream (streams of 256 MiB and
-    // more are left to the fused kernel), so that a slide needs no bookkeeping at all
-    s.avail = 8u * left;
-    s.rem = 0;
-#else
     uint32_t in_window = 8u - sh;                                 // bytes of [a, ...) the two words cover
     if (in_window > left) in_window = left;
     s.avail = 8u * in_window;
     s.rem = left - in_window;
-#endif
 }
 
 BRO_FN void bro_bits_init(BroBits& s, const uint8_t* start, const uint8_t* end) {
-#if defined(BRO_HOSTSIM)
-    s.lo = start;
-#else
     s.lo = (const uint8_t*)((uintptr_t)start & ~(uintptr_t)3);
-#endif
     s.end = end;
     bro_bits_seek(s, start);
 }
@@ -382,26 +471,6 @@ BRO_FN void bro_bits_init(BroBits& s, const uint8_t* start, const uint8_t* end) 
 // most 32 bits.  Keeping the slide in ONE place per read keeps the hot loops small (the I-cache is a first-order
 // limit for this kernel).
 BRO_FN void bro_refill(BroBits& s) {
-#if defined(BRO_THREAD_MODE)
-    // one thread per stream: branch-free, so that the lanes of a warp (different streams, different bit positions)
-    // share these instructions instead of taking the slide one group of lanes at a time
-    const bool need = s.bp >= 32u;
-    uint32_t wn = s.w3;
-    if (need) {
-        wn = 0;
-        if (s.chunk < s.end) wn = __ldg((const uint32_t*)s.chunk);       // chunk >= lo always holds here
-        // entering a new 32-byte sector: ask L2 for the sector after the next one (the stream is read strictly forward,
-        // so DRAM latency is paid two sectors ahead of the window and the loads above find their words in L2 / L1)
-        if (((uintptr_t)s.chunk & 31u) == 0u && s.chunk + 64 < s.end) asm volatile("prefetch.global.L2 [%0];" :: "l"(s.chunk + 64));
-    }
-    s.w0 = need ? s.w1 : s.w0;
-    s.w1 = need ? s.w2 : s.w1;
-    s.w2 = need ? s.w3 : s.w2;
-    s.w3 = wn;                                                            // not looked at before the slide after the next
-    s.bp -= need ? 32u : 0u;
-    s.chunk += need ? 4 : 0;
-    return;
-#endif
     if (s.bp >= 32u) {
         s.bp -= 32u;
         s.w0 = s.w1;
@@ -411,8 +480,14 @@ BRO_FN void bro_refill(BroBits& s) {
         s.rem -= got;
     }
 }
+#endif
 // The next 32 stream bits, first bit in bit 0 (after bro_refill the window holds more than 32 bits past `bp`).
 BRO_FN uint32_t bro_peek(const BroBits& s) { return bro_funnel_r(s.w0, s.w1, s.bp); }
+// The same when up to 17 bits have been consumed since bro_refill (bp < 49): at least 15 valid bits.
+BRO_FN uint32_t bro_peek_wide(const BroBits& s) {
+    const bool hi = s.bp >= 32u;
+    return bro_funnel_r(hi ? s.w1 : s.w0, hi ? 0u : s.w1, s.bp & 31u);
+}
 BRO_FN uint32_t bro_avail(const BroBits& s) { return s.avail; }
 BRO_FN void bro_consume(BroBits& s, uint32_t n) { s.bp += n; s.avail -= n; }   // n <= 32, n <= avail
 
@@ -437,10 +512,8 @@ BRO_FN bool bro_read_byte_tail(BroBits& s, uint32_t& v) {
 
 // byte address of the next unread bit (valid when byte aligned)
 BRO_FN const uint8_t* bro_bits_addr(const BroBits& s) {
-#if defined(BRO_THREAD_MODE)
-    return s.chunk - 16 + (s.bp >> 3);
-#elif defined(BRO_SERIAL)
-    return s.chunk - 8 + (s.bp >> 3);
+#if defined(BRO_SERIAL)
+    return s.base + (bro_bits_w0(s) + (s.bp >> 3));
 #else
     return s.chunk + 4u * s.wi - 8 + (s.bp >> 3);
 #endif
@@ -448,10 +521,8 @@ BRO_FN const uint8_t* bro_bits_addr(const BroBits& s) {
 
 // bits consumed since byte address `start` (any state of the window)
 BRO_FN uint64_t bro_bits_position(const BroBits& s, const uint8_t* start) {
-#if defined(BRO_THREAD_MODE)
-    const uint8_t* w0 = s.chunk - 16;
-#elif defined(BRO_SERIAL)
-    const uint8_t* w0 = s.chunk - 8;
+#if defined(BRO_SERIAL)
+    const uint8_t* w0 = s.base + (int32_t)bro_bits_w0(s);       // (below base right after a seek to the stream's first bytes)
 #else
     const uint8_t* w0 = s.chunk + 4u * s.wi - 8;
 #endif
@@ -516,7 +587,9 @@ BRO_FN int bro_decode_sym(BroBits& s, const uint16_t* T, uint32_t& sym) { return
 // in its own scratch (local memory on the device); the table itself is only written: the root is filled by
 // replication as every symbol is placed (its canonical code is known at that moment), so the build never waits for a
 // load from the table arena in HBM.
-BRO_COLD void bro_build_tree(uint16_t* T, BRO_SC_PARAM, uint32_t n, bool explicit_syms) {
+// want_root = false: the caller decodes this table canonically (limits, bases and sorted[] only): the 256-entry root
+// is neither cleared nor filled.
+BRO_COLD void bro_build_tree(uint16_t* T, BRO_SC_PARAM, uint32_t n, bool explicit_syms, bool want_root = true) {
     BRO_SC_BIND;
     // pass 1: per-length counts (running positions later) in the thread's on-chip block; unused symbols -- most of the
     // 704 insert&copy symbols of a typical code -- are skipped eight at a time
@@ -552,9 +625,9 @@ BRO_COLD void bro_build_tree(uint16_t* T, BRO_SC_PARAM, uint32_t n, bool explici
     T[BRO_T_MAXDEPTH] = (uint16_t)maxdepth;
     T[BRO_T_MAXDEPTH + 1u] = 0;
 #if defined(BRO_HOSTSIM)
-    for (uint32_t r = 0; r < BRO_ROOT_SIZE; r++) T[r] = 0;
+    if (want_root) for (uint32_t r = 0; r < BRO_ROOT_SIZE; r++) T[r] = 0;
 #else
-    for (uint32_t r = 0; r < BRO_ROOT_SIZE / 8u; r++) ((uint4*)T)[r] = make_uint4(0u, 0u, 0u, 0u);     // records are 16-byte aligned
+    if (want_root) for (uint32_t r = 0; r < BRO_ROOT_SIZE / 8u; r++) ((uint4*)T)[r] = make_uint4(0u, 0u, 0u, 0u);     // records are 16-byte aligned
 #endif
     // pass 2: place the symbols in canonical order (array order inside a length); the table itself is only written --
     // the root is filled by replication as every symbol is placed (its canonical code is known at that moment)
@@ -570,7 +643,7 @@ BRO_COLD void bro_build_tree(uint16_t* T, BRO_SC_PARAM, uint32_t n, bool explici
             sc.cnt[L] = (uint16_t)(idx + 1u);
             T[BRO_T_SORTED + idx] = (uint16_t)symv;
             if (nonzero == 1u) single_sym = symv;
-            if (nonzero >= 2u) {
+            if (nonzero >= 2u && want_root) {
                 const uint32_t c = (uint32_t)((int)idx - (int)sc.base[L]);    // the canonical code of this symbol
                 if (L <= BRO_ROOT_BITS) {
                     const uint32_t e = symv | (L << 10);
@@ -582,7 +655,7 @@ BRO_COLD void bro_build_tree(uint16_t* T, BRO_SC_PARAM, uint32_t n, bool explici
     T[BRO_T_SINGLE_SYM] = (uint16_t)single_sym;
 }
 #else
-BRO_COLD void bro_build_tree(uint16_t* T, BroScratch& sc, uint32_t n, bool explicit_syms) {
+BRO_COLD void bro_build_tree(uint16_t* T, BroScratch& sc, uint32_t n, bool explicit_syms, bool = true) {
     const unsigned lane = bro_lane();
     for (unsigned i = lane; i < 16u; i += BRO_W) sc.cnt[i] = 0;
     bro_syncwarp();
@@ -693,7 +766,7 @@ struct BroDec {
     BroRec* rec;              // copy records of this stream (phase one of the two-phase path writes, phase two executes)
     uint32_t nrec, rec_cap;
     const uint8_t* in_base;   // first byte of the compressed stream (stored-block records hold offsets from it)
-    const uint32_t* ic;       // bro_ic_insert / bro_ic_copy interleaved (shared memory)
+    const uint32_t* ic;       // insert / copy length codes -> base | extra bits << 16 (bro_ic_lookup; shared memory)
     uint32_t out_mis;         // (address of out) & 15: pieces are cut at 16-byte boundaries of the destination ADDRESS
     uint32_t sizing;          // 1: only measure the stream (bro_batch_sizes): nothing is written, the slot is unbounded
 #endif
@@ -978,13 +1051,13 @@ BRO_COLD int bro_read_prefix_code_cold(BroBits& in_, BRO_SC_PARAM, uint32_t alph
     return st;
 }
 
-BRO_FN int bro_read_prefix_code(BroBits& in, BroScratch& sc, uint32_t alphabet, uint16_t* T) {
+BRO_FN int bro_read_prefix_code(BroBits& in, BroScratch& sc, uint32_t alphabet, uint16_t* T, bool want_root = true) {
     BroBits t = in;
     uint32_t n = 0;
     bool explicit_syms = false;
     int st = bro_read_prefix_code_cold(t, BRO_SC_PASS(sc), alphabet, n, explicit_syms);
     in = t;
-    if (st == 0) bro_build_tree(T, BRO_SC_PASS(sc), n, explicit_syms);
+    if (st == 0) bro_build_tree(T, BRO_SC_PASS(sc), n, explicit_syms, want_root);
     return st;
 }
 
@@ -1565,7 +1638,11 @@ BRO_FN int bro_metablock_tables(BroDec& d, BroMbInfo& mb) {
             if (i < n_l) { alphabet = BRO_ALPHA_LIT; T = A + o_lit + i * BRO_TREE_U16(BRO_ALPHA_LIT); }
             else if (i < n_l + n_i) { alphabet = BRO_ALPHA_CMD; T = A + o_cmd + (i - n_l) * BRO_TREE_U16(BRO_ALPHA_CMD); }
             else { alphabet = dist_alphabet; T = A + o_dist + (i - n_l - n_i) * dist_stride; }
+#if defined(BRO_PARSE)
+            st = bro_read_prefix_code(d.in, sc, alphabet, T, i >= n_l);     // literal tables are decoded canonically (bro_parse.h)
+#else
             st = bro_read_prefix_code(d.in, sc, alphabet, T);
+#endif
         }
     }
 #undef BRO_TRY

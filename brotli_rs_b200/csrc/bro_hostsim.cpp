@@ -14,6 +14,7 @@ static void bro_hostsim_bind(BroDec& d, uint8_t* mem) {
     BroTl tl;
     tl.base = mem + 4u * 3u;
     bro_scratch_bind(d.scv, tl);
+    d.in.ring = tl;
     uint16_t* roots = (uint16_t*)(mem + 32u * BRO_TL_BYTES);
     d.scv.root_lit = roots; d.scv.root_cmd = roots + 256; d.scv.root_dist = roots + 512;
 }

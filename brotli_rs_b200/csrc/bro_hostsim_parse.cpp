@@ -24,6 +24,12 @@ extern "C" void bro_hostsim_parse_set_copy_group(int group) { g_copy_group = gro
 extern "C" void bro_hostsim_parse_copy_stats(uint32_t* stats3) { memcpy(stats3, g_copy_stats, sizeof(g_copy_stats)); }
 extern "C" void bro_hostsim_copy_exec(uint8_t* out, const uint8_t* in, const uint32_t* words, uint32_t nrec, int group, uint32_t* stats);
 
+// look-ups through the narrow insert&copy / distance roots since the last call: [cmd all, 8-bit root, search, dist all, ...]
+extern "C" void bro_hostsim_parse_root_stats(uint64_t* six) {
+    memcpy(six, bro_hostsim_root_stats, sizeof(bro_hostsim_root_stats));
+    memset(bro_hostsim_root_stats, 0, sizeof(bro_hostsim_root_stats));
+}
+
 static uint32_t* g_rec_out = 0;       // when set: the records of the next decode are copied here (4 words each)
 static unsigned g_rec_out_cap = 0;
 
@@ -44,6 +50,7 @@ extern "C" int bro_hostsim_parse_decode(const uint8_t* in, size_t in_len, uint8_
         BroTl tl;
         tl.base = blocks + 4u * 7u;
         bro_scratch_bind(d.scv, tl);
+        d.in.ring = tl;
     }
     d.arena = arena;
     d.arena_cap = arena_u16;
@@ -57,8 +64,13 @@ extern "C" int bro_hostsim_parse_decode(const uint8_t* in, size_t in_len, uint8_
     d.p1 = d.p2 = 0;
     d.d0 = 4; d.d1 = 11; d.d2 = 15; d.d3 = 16;
     d.quirk_spec = quirks;
-    static uint32_t ic[2 * 704];
-    for (unsigned i = 0; i < 704; i++) { ic[2 * i] = bro_ic_insert[i]; ic[2 * i + 1] = bro_ic_copy[i]; }
+    static uint32_t ic[48];
+    for (unsigned k = 0; k < 48; k++) bro_ic_compact_entry(k, ic[k]);
+    for (unsigned i = 0; i < 704; i++) {       // the compact form answers exactly what the reference's table holds
+        uint32_t ie, ce;
+        bro_ic_lookup(ic, i, ie, ce);
+        if (ie != bro_ic_insert[i] || ce != bro_ic_copy[i]) abort();
+    }
     d.rec = rec; d.nrec = 0; d.rec_cap = rec_cap; d.in_base = in; d.ic = ic;
     bro_bits_init(d.in, in, in + in_len);
     BroParse ps;

@@ -77,6 +77,7 @@ extern "C" int bro_warp_kernel_warps_per_cta() { return BRO_WARPS_PER_CTA * BRO_
 extern "C" size_t bro_warp_kernel_arena_bytes() { return 2u * (size_t)BRO_GROUP_ARENA_U16; }
 
 extern "C" int bro_warp_kernel_launch(const BroLaunch* p, int grid, cudaStream_t stream) {
+    (void)cudaGetLastError();      // a stale error of another library in this process (it is per thread) is not this launch's
     bro_decode_warp_kernel<BRO_WARPS_PER_CTA><<<grid, BRO_WARPS_PER_CTA * 32, 0, stream>>>(*p);
     return (int)cudaGetLastError();
 }

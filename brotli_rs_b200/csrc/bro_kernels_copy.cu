@@ -364,6 +364,7 @@ extern "C" int bro_copy_kernel_occupancy(int* blocks_per_sm) {
 extern "C" int bro_copy_kernel_warps_per_cta() { return BRO_COPY_WARPS; }
 
 extern "C" int bro_copy_kernel_launch(const BroLaunch* p, int grid, cudaStream_t stream) {
+    (void)cudaGetLastError();
     bro_copy_kernel<BRO_COPY_WARPS><<<grid, BRO_COPY_WARPS * 32, 0, stream>>>(*p);
     return (int)cudaGetLastError();
 }

@@ -20,7 +20,7 @@
 #include "bro_kernels.h"
 
 // One CTA per SM: BRO_PARSE_BLOCK threads, each with its lane-interleaved block of BRO_TL_BYTES of shared memory
-// (384 x 576 B = 216 KB) + the insert/copy length table (5.5 KB) = 222 KB of the SM's 227 KB.
+// (384 x 600 B = 225 KB of the SM's 227 KB).
 #ifndef BRO_PARSE_BLOCK
 #define BRO_PARSE_BLOCK 384
 #endif
@@ -44,8 +44,8 @@ __global__ void __launch_bounds__(BRO_PARSE_BLOCK, BRO_PARSE_MIN_BLOCKS) bro_par
     // tables of the current block types inside a meta-block: bro_decoder_core.h, bro_parse.h), per CTA the
     // insert/copy length table.  Nothing of a thread's working set is in local memory.
     extern __shared__ __align__(16) uint8_t s_blocks[];
-    __shared__ uint32_t s_ic[2 * 704];
-    for (unsigned i = threadIdx.x; i < 704u; i += BRO_PARSE_BLOCK) { s_ic[2 * i] = bro_ic_insert[i]; s_ic[2 * i + 1] = bro_ic_copy[i]; }
+    __shared__ uint32_t s_ic[48];
+    if (threadIdx.x < 48u) bro_ic_compact_entry(threadIdx.x, s_ic[threadIdx.x]);
     __syncthreads();
     uint32_t stream = 0;
     uint32_t waited = 0;          // warp-uniform: trips since the first lane reached a boundary
@@ -55,6 +55,7 @@ __global__ void __launch_bounds__(BRO_PARSE_BLOCK, BRO_PARSE_MIN_BLOCKS) bro_par
         BroTl tl;
         tl.base = (uint32_t)__cvta_generic_to_shared(s_blocks) + (threadIdx.x >> 5) * (32u * BRO_TL_BYTES) + 4u * lane;
         bro_scratch_bind(d.scv, tl);
+        d.in.ring = tl;
     }
     d.ic = s_ic;
     d.arena = arena;
@@ -180,6 +181,7 @@ extern "C" int bro_order_launch(const uint64_t* in_off, uint32_t n, uint32_t* or
     cudaError_t e = cudaMemsetAsync(scratch, 0, 512 * sizeof(uint32_t), stream);
     if (e != cudaSuccess) return (int)e;
     uint32_t blocks = (n + 255u) / 256u;
+    (void)cudaGetLastError();
     bro_order_hist_kernel<<<blocks, 256, 0, stream>>>(in_off, n, scratch, gate);
     bro_order_scan_kernel<<<1, 256, 0, stream>>>(scratch, scratch + 256, in_off, n, gate);
     bro_order_scatter_kernel<<<blocks, 256, 0, stream>>>(in_off, n, scratch + 256, order);
@@ -192,6 +194,7 @@ __global__ void bro_sizes_finish_kernel(int32_t* status, uint32_t n) {
 }
 
 extern "C" int bro_sizes_finish_launch(int32_t* status, uint32_t n, cudaStream_t stream) {
+    (void)cudaGetLastError();
     bro_sizes_finish_kernel<<<(n + 255u) / 256u, 256, 0, stream>>>(status, n);
     return (int)cudaGetLastError();
 }
@@ -206,6 +209,7 @@ extern "C" size_t bro_parse_kernel_arena_bytes() { return 2u * (size_t)BRO_THREA
 extern "C" size_t bro_parse_kernel_roots_bytes() { return 0; }   // (round 1 kept literal tables in HBM; everything is on chip now)
 
 extern "C" int bro_parse_kernel_launch(const BroLaunch* p, int grid, cudaStream_t stream) {
+    (void)cudaGetLastError();
     bro_parse_kernel<<<grid, BRO_PARSE_BLOCK, BRO_PARSE_SMEM, stream>>>(*p);
     return (int)cudaGetLastError();
 }

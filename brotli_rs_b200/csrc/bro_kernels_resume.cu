@@ -54,6 +54,7 @@ __global__ void __launch_bounds__(BRO_RESUME_WARPS * 32, 4) bro_decode_resume_ke
 extern "C" int bro_resume_kernel_warps_per_cta() { return BRO_RESUME_WARPS; }
 
 extern "C" int bro_resume_kernel_launch(const BroLaunch* p, int grid, cudaStream_t stream) {
+    (void)cudaGetLastError();
     bro_decode_resume_kernel<<<grid, BRO_RESUME_WARPS * 32, 0, stream>>>(*p);
     return (int)cudaGetLastError();
 }

@@ -59,6 +59,19 @@
 #define BRO_TLB_DIST (BRO_TLB_CMD + (2u << BRO_RB_CMD))  // uint16[1 << BRO_RB_DIST]: root of the distance code (when there is one)
 static_assert(BRO_TLB_DIST + (2u << BRO_RB_DIST) <= BRO_TL_BYTES, "the decode tables must fit the thread's block");
 
+// The insert&copy length table (src/lookuptable/mod.rs:123, 704 entries) in 48: a symbol's cell (symbol >> 6) gives the
+// high parts of its insert and copy length codes, bits 3..5 and 0..2 the low parts; tab[0..24) holds base | extra
+// bits << 16 per insert length code, tab[24..48) per copy length code (192 bytes per CTA instead of 5.5 KB).
+BRO_FN void bro_ic_compact_entry(uint32_t k, uint32_t& v) {      // k in [0, 48)
+    const uint32_t hi = (k % 24u) >> 3, lo = k & 7u;
+    v = k < 24u ? bro_ic_insert[(hi == 0u ? 0u : hi == 1u ? 4u : 7u) * 64u + lo * 8u] : bro_ic_copy[(hi == 0u ? 0u : hi == 1u ? 1u : 6u) * 64u + lo];
+}
+BRO_FN void bro_ic_lookup(const uint32_t* tab, uint32_t sym, uint32_t& ie, uint32_t& ce) {
+    const uint32_t cell2 = (sym >> 6) * 2u;
+    ie = tab[((0x298500u >> cell2) & 3u) * 8u + ((sym >> 3) & 7u)];
+    ce = tab[24u + ((0x262444u >> cell2) & 3u) * 8u + (sym & 7u)];
+}
+
 #if defined(BRO_HOSTSIM)
 BRO_FN bool bro_any(bool p) { return p; }
 #else
@@ -108,12 +121,21 @@ BRO_FN void bro_narrow_root_tl(BroTl t, uint32_t off, uint32_t root_bits, const 
     }
 }
 
+#if defined(BRO_HOSTSIM)
+// test-suite instrumentation: look-ups through a narrow root [category][0 all | 1 settled by the table's 8-bit root | 2 canonical search]
+static uint64_t bro_hostsim_root_stats[2][3];
+#define BRO_ROOT_STAT(off, k) (bro_hostsim_root_stats[(off) == BRO_TLB_CMD ? 0 : 1][k]++)
+#else
+#define BRO_ROOT_STAT(off, k)
+#endif
+
 // One symbol through such a copy (same results as bro_decode_sym on the table).
 BRO_FN int bro_decode_sym_tl(BroBits& s, BroTl t, uint32_t off, uint32_t root_bits, const uint16_t* T, uint32_t& sym) {
     bro_refill(s);
     uint32_t peek = bro_peek(s);
     uint32_t e = bro_tl_ld16(t, off + 2u * (peek & ((1u << root_bits) - 1u)));
     uint32_t len = e >> 10;
+    BRO_ROOT_STAT(off, 0);
     if (len != 0u) {
         if (len > bro_avail(s)) return BRO_SYM_EOF;
         bro_consume(s, len);
@@ -124,12 +146,14 @@ BRO_FN int bro_decode_sym_tl(BroBits& s, BroTl t, uint32_t off, uint32_t root_bi
     // longer takes the canonical search (four dependent look-ups)
     e = T[peek & (BRO_ROOT_SIZE - 1u)];
     len = e >> 10;
+    BRO_ROOT_STAT(off, 1);
     if (len != 0u) {
         if (len > bro_avail(s)) return BRO_SYM_EOF;
         bro_consume(s, len);
         sym = e & 0x3ffu;
         return BRO_SYM_OK;
     }
+    BRO_ROOT_STAT(off, 2);
     uint32_t r = bro_sym_slow(T, peek, e, bro_avail(s));
     bro_consume(s, (r >> 16) & 0xffu);
     sym = r & 0xffffu;
@@ -331,7 +355,8 @@ BRO_FN void bro_parse_round(BroDec& d, BroParse& ps, BroMbInfo& mb) {
         const int r = bro_decode_sym_tl(d.in, d.scv.t, BRO_TLB_CMD, BRO_RB_CMD, d.arena + ps.toff_cmd, sym);
         if (r != BRO_SYM_OK) bro_parse_finish(ps, r == BRO_SYM_HOLE ? BRO_ST_ParseErrorInsertAndCopyLength : BRO_ST_UnexpectedEOF);
         else {
-            const uint32_t ie = d.ic[2u * sym], ce = d.ic[2u * sym + 1u];        // bro_ic_insert / bro_ic_copy, interleaved on chip
+            uint32_t ie, ce;
+            bro_ic_lookup(d.ic, sym, ie, ce);
             uint32_t insert_len = ie & 0xffffu, copy_len = ce & 0xffffu, extra = 0, extra2 = 0;
             const uint32_t ib = ie >> 16, cb = ce >> 16;                   // insert extra bits come first
             bool ok;
@@ -367,19 +392,29 @@ BRO_FN void bro_parse_round(BroDec& d, BroParse& ps, BroMbInfo& mb) {
         const BroTl tl = d.scv.t;
         uint8_t* op = d.out + d.pos;
         uint32_t done = 0;
+        // two literals per slide of the window: after bro_refill the window holds 64 bits from a bit position < 32, and a
+        // literal code has at most 15 bits, so the second literal of a pair still finds its bits (bro_peek_wide)
 #pragma unroll 1
-        for (uint32_t u = 0; u < BRO_PARSE_LITS_PER_ROUND; u++) {
+        for (uint32_t u = 0; u < BRO_PARSE_LITS_PER_ROUND; u += 2u) {
             if (!bro_any(u < fast)) break;
             if (u < fast) {
                 bro_refill(d.in);
                 uint32_t sym = 0, len = 0;
-                const int r = bro_parse_lit(ps, tl, bro_peek(d.in), bro_avail(d.in), sym, len);
-                if (r != BRO_SYM_OK) { bro_parse_finish(ps, r == BRO_SYM_HOLE ? BRO_ST_ParseErrorInsertLiterals : BRO_ST_UnexpectedEOF); fast = 0; }
-                else {
+                int r = bro_parse_lit(ps, tl, bro_peek(d.in), bro_avail(d.in), sym, len);
+                if (r == BRO_SYM_OK) {
                     bro_consume(d.in, len);
                     if (!d.sizing) op[u] = (uint8_t)sym;
                     done = u + 1u;
+                    if (u + 1u < fast) {
+                        r = bro_parse_lit(ps, tl, bro_peek_wide(d.in), bro_avail(d.in), sym, len);
+                        if (r == BRO_SYM_OK) {
+                            bro_consume(d.in, len);
+                            if (!d.sizing) op[u + 1u] = (uint8_t)sym;
+                            done = u + 2u;
+                        }
+                    }
                 }
+                if (r != BRO_SYM_OK) { bro_parse_finish(ps, r == BRO_SYM_HOLE ? BRO_ST_ParseErrorInsertLiterals : BRO_ST_UnexpectedEOF); fast = 0; }
             }
         }
         if (done != 0u && ps.kind == BRO_K_LIT) {

@@ -60,7 +60,10 @@ class Decompressor(io.RawIOBase):
         buf = (ctypes.c_uint8 * len(mv)).from_buffer(mv)
         n = self._lib.bro_reader_read(self._h, buf, len(mv))
         if n < 0:
-            raise _lib.BroError(-n)
+            msg = None
+            if -n == _lib.CUDA_ERROR and self._decoder is not None:
+                msg = "CUDA error: " + self._lib.bro_ctx_last_cuda_error(self._decoder._ctx).decode()
+            raise _lib.BroError(-n, msg)
         return n
 
     @property

@@ -488,11 +488,12 @@ def test_streaming_reader_fuzz_and_small_windows():
             st, out = oracle.decode(m)
             got, err = b"", 0
             r = Decompressor(m, decoder=d, streaming=int(rng.integers(1, 3000)))
+            msg = ""
             try:
                 got = r.read()
             except BroError as e:
-                err = e.status
-            assert err == st and (st != 0 or got == out), (m[:16].hex(), st, err, len(got), len(out))
+                err, msg = e.status, str(e)
+            assert err == st and (st != 0 or got == out), (m[:16].hex(), st, err, len(got), len(out), msg)
             seen.add(st)
             r.close()
         assert len(seen) >= 8
