@@ -9,7 +9,9 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <mutex>
 #include <new>
+#include <thread>
 #include <vector>
 
 #include "../../include/brotli_b200.h"
@@ -24,7 +26,9 @@ struct bro_ctx {
     int num_sms;
     int grid;                 // warp kernel: persistent CTAs
     uint32_t num_warps;
-    uint16_t* d_arena;        // warp kernel: worst-case arena per warp
+    uint16_t* d_arena;        // warp kernel: worst-case arena per warp, for the first `arena_warps` warps of the grid
+    uint32_t arena_warps;     // (grow-only, sized by the grids actually launched: a one-stream reader needs 8 warps = 10 MB,
+                              // a full grid 4,736 warps = 5.9 GB)
     int grid_t;               // parse kernel: persistent CTAs
     uint32_t num_threads;
     uint16_t* d_arena_t;      // parse kernel: 64 KiB arena per thread
@@ -48,6 +52,8 @@ struct bro_ctx {
     int mode;                 // BRO_MODE_AUTO / WARP / TWOPHASE
     uint32_t twophase_threshold;   // AUTO: batches of at least this many streams take the two-phase path
     int quirks;
+    long long watchdog;       // copy kernel: cycles to wait for one completion-queue slot (about half a minute)
+    int debug_no_parse;       // BRO_B200_DEBUG_NO_PARSE=1 (test-suite): the parse kernel is not launched, so the copy kernel's watchdog must fire
     uint64_t launches;
     char err[256];
     // grow-only device staging for the host-buffer path
@@ -90,11 +96,11 @@ extern "C" int bro_ctx_create(bro_ctx** out, int device) {
     ctx->num_threads = (uint32_t)ctx->grid_t * (uint32_t)bro_parse_kernel_block();
     ctx->grid_c = ctx->num_sms * per_sm_c;
     ctx->mode = BRO_MODE_AUTO;
-    // Measured on B200 (profiles/r01_kernel_variants.md): side by side the two kernels compete for the register file (the
-    // parse kernel's three CTAs leave room for one 64-register copy CTA per SM) and the streams of a batch finish in
-    // bursts, so the overlap buys 5 % at best and costs the copy kernel its best configuration: off unless asked for.
+    // The two kernels of the two-phase path run one after the other: the parse kernel's CTA takes an SM's whole shared
+    // memory (round 1 could run them side by side through the completion queue; it bought 5 % at best).
     ctx->overlap = 0;
-    { const char* ov = getenv("BRO_B200_OVERLAP"); if (ov && ov[0] == '1') ctx->overlap = 1; }
+    ctx->watchdog = 1ll << 36;
+    { const char* dbg = getenv("BRO_B200_DEBUG_NO_PARSE"); if (dbg && dbg[0] == '1') { ctx->debug_no_parse = 1; ctx->watchdog = 1ll << 22; } }
     if (cudaStreamCreateWithFlags(&ctx->side, cudaStreamNonBlocking) != cudaSuccess ||
         cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming) != cudaSuccess) { ctx->side = NULL; cudaGetLastError(); }
@@ -106,9 +112,7 @@ extern "C" int bro_ctx_create(bro_ctx** out, int device) {
     const char* env = getenv("BRO_B200_MODE");
     if (env && !strcmp(env, "warp")) ctx->mode = BRO_MODE_WARP;
     if (env && (!strcmp(env, "twophase") || !strcmp(env, "thread"))) ctx->mode = BRO_MODE_TWOPHASE;
-    size_t arena = (size_t)ctx->num_warps * bro_warp_kernel_arena_bytes();
-    if (cudaMalloc(&ctx->d_arena, arena) != cudaSuccess ||
-        cudaMalloc(&ctx->d_dict, BRO_DICT_BYTES) != cudaSuccess ||
+    if (cudaMalloc(&ctx->d_dict, BRO_DICT_BYTES) != cudaSuccess ||
         cudaMalloc(&ctx->d_counter, 16 * sizeof(uint32_t)) != cudaSuccess ||
         cudaMalloc(&ctx->d_order_scratch, 512 * sizeof(uint32_t)) != cudaSuccess ||
         cudaMemcpy(ctx->d_dict, bro_dictionary_blob, BRO_DICT_BYTES, cudaMemcpyHostToDevice) != cudaSuccess) {
@@ -178,6 +182,10 @@ extern "C" int bro_ctx_last_batch_stats(bro_ctx* ctx, uint64_t* stats4) {
     stats4[1] = (uint64_t)h[6] | ((uint64_t)h[7] << 32);     // copy records executed
     stats4[2] = h[2];                                        // streams handed to the fused kernel's retry pass
     stats4[3] = h[10];                                       // 1: AUTO's gate sent the whole batch to the fused kernel
+    if (h[11]) {
+        snprintf(ctx->err, sizeof(ctx->err), "copy kernel watchdog: a stream of the batch was never announced by the parse kernel");
+        return BRO_ST_CudaError;
+    }
     return BRO_ST_OK;
 }
 
@@ -185,6 +193,29 @@ extern "C" int bro_ctx_reserve(bro_ctx* ctx, uint64_t total_in_bytes, uint32_t n
     if (!ctx) return BRO_ST_InvalidArgument;
     (void)n_streams;
     ctx->reserved_in = total_in_bytes;
+    return BRO_ST_OK;
+}
+
+// The device entry points run on the context's device whatever the caller's current device is, and leave the caller's
+// choice as they found it.
+struct BroDeviceGuard {
+    int prev, ok;
+    explicit BroDeviceGuard(int device) : prev(-1), ok(1) {
+        if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+        if (prev != device && cudaSetDevice(device) != cudaSuccess) ok = 0;
+    }
+    ~BroDeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+
+// Table arenas of the warp kernels for a grid of `warps` warps (grow-only; nothing is in flight on a larger grid than
+// the one that was allocated for, and growing synchronises the device)
+static int bro_ensure_arena(bro_ctx* ctx, uint32_t warps) {
+    if (warps <= ctx->arena_warps) return BRO_ST_OK;
+    if (ctx->d_arena) { BRO_CUDA(ctx, cudaDeviceSynchronize()); BRO_CUDA(ctx, cudaFree(ctx->d_arena)); ctx->d_arena = NULL; ctx->arena_warps = 0; }
+    uint32_t want = warps < 64u ? warps : (warps + 63u) & ~63u;
+    if (want > ctx->num_warps) want = ctx->num_warps;
+    BRO_CUDA(ctx, cudaMalloc(&ctx->d_arena, (size_t)want * bro_warp_kernel_arena_bytes()));
+    ctx->arena_warps = want;
     return BRO_ST_OK;
 }
 
@@ -203,6 +234,8 @@ extern "C" int bro_batch_decode(bro_ctx* ctx, const uint8_t* d_in, const uint64_
     if (!ctx) return BRO_ST_InvalidArgument;
     if (n == 0) return BRO_ST_OK;
     if (!d_in_off || !d_out_off || !d_out_len || !d_status) return BRO_ST_InvalidArgument;
+    BroDeviceGuard guard(ctx->device);
+    if (!guard.ok) return bro_fail(ctx, cudaErrorInvalidDevice, "cudaSetDevice(context's device)");
     cudaStream_t s = (cudaStream_t)stream;
     BRO_CUDA(ctx, cudaMemsetAsync(ctx->d_counter, 0, 16 * sizeof(uint32_t), s));
     BroLaunch p;
@@ -215,6 +248,7 @@ extern "C" int bro_batch_decode(bro_ctx* ctx, const uint8_t* d_in, const uint64_
     int grid_w = ctx->grid;
     if ((uint32_t)grid_w > (n + wpc - 1) / wpc) grid_w = (int)((n + wpc - 1) / wpc);
     const bool two_phase = ctx->mode == BRO_MODE_TWOPHASE || (ctx->mode == BRO_MODE_AUTO && n >= ctx->twophase_threshold);
+    { int st_a = bro_ensure_arena(ctx, (uint32_t)grid_w * wpc); if (st_a) return st_a; }       // before anything of this batch is in flight
     cudaError_t e;
     if (two_phase) {
         // PHASE ONE: one thread per stream (bro_parse_kernel), streams handed out by compressed-size class; literals and
@@ -271,10 +305,11 @@ extern "C" int bro_batch_decode(bro_ctx* ctx, const uint8_t* d_in, const uint64_
         }
         p.arena = ctx->d_arena_t; p.counter = ctx->d_counter; p.order = d_order; p.roots = ctx->d_roots;
         if (ctx->timing) BRO_CUDA(ctx, cudaEventRecord(ctx->ev[1], s));
-        e = (cudaError_t)bro_parse_kernel_launch(&p, grid_t, s);
+        e = ctx->debug_no_parse ? cudaSuccess : (cudaError_t)bro_parse_kernel_launch(&p, grid_t, s);
         if (e != cudaSuccess) return bro_fail(ctx, e, "bro_parse_kernel launch");
         ctx->launches += 1;
         p.counter = ctx->d_counter + 3; p.order = NULL;
+        p.fault = ctx->d_counter + 11; p.watchdog = ctx->watchdog;
         int grid_c = ctx->grid_c;      // side by side, one CTA per SM fits next to the parse kernel; the others start as its CTAs exit
         if ((uint32_t)grid_c > (n + cw - 1) / cw) grid_c = (int)((n + cw - 1) / cw);
         if (ctx->timing) BRO_CUDA(ctx, cudaEventRecord(ctx->ev[2], s));
@@ -309,6 +344,8 @@ extern "C" int bro_batch_decode_resume(bro_ctx* ctx, const uint8_t* d_in, const 
     if (!ctx) return BRO_ST_InvalidArgument;
     if (n == 0) return BRO_ST_OK;
     if (!d_in_off || !d_out_off || !d_out_len || !d_status || !d_resume) return BRO_ST_InvalidArgument;
+    BroDeviceGuard guard(ctx->device);
+    if (!guard.ok) return bro_fail(ctx, cudaErrorInvalidDevice, "cudaSetDevice(context's device)");
     cudaStream_t s = (cudaStream_t)stream;
     BRO_CUDA(ctx, cudaMemsetAsync(ctx->d_counter, 0, 16 * sizeof(uint32_t), s));
     BroLaunch p;
@@ -316,12 +353,14 @@ extern "C" int bro_batch_decode_resume(bro_ctx* ctx, const uint8_t* d_in, const 
     p.in = d_in; p.in_off = d_in_off; p.out = d_out; p.out_off = d_out_off;
     p.out_len = d_out_len; p.status = d_status; p.n = n;
     p.dict = ctx->d_dict; p.quirk_spec = ctx->quirks;
-    p.arena = ctx->d_arena; p.counter = ctx->d_counter + 1;
+    p.counter = ctx->d_counter + 1;
     p.resume = (BroResume*)d_resume;
     // the resume kernel has the warp kernel's CTA shape and arena layout: never more warps than the arena has shares
     const uint32_t wpc = (uint32_t)bro_resume_kernel_warps_per_cta();
     int grid = (int)(ctx->num_warps / wpc);
     if ((uint32_t)grid > (n + wpc - 1) / wpc) grid = (int)((n + wpc - 1) / wpc);
+    { int st_a = bro_ensure_arena(ctx, (uint32_t)grid * wpc); if (st_a) return st_a; }
+    p.arena = ctx->d_arena;
     cudaError_t e = (cudaError_t)bro_resume_kernel_launch(&p, grid, s);
     if (e != cudaSuccess) return bro_fail(ctx, e, "bro_decode_resume_kernel launch");
     ctx->launches += 1;
@@ -333,6 +372,8 @@ extern "C" int bro_batch_sizes(bro_ctx* ctx, const uint8_t* d_in, const uint64_t
     if (!ctx) return BRO_ST_InvalidArgument;
     if (n == 0) return BRO_ST_OK;
     if (!d_in_off || !d_out_len || !d_status) return BRO_ST_InvalidArgument;
+    BroDeviceGuard guard(ctx->device);
+    if (!guard.ok) return bro_fail(ctx, cudaErrorInvalidDevice, "cudaSetDevice(context's device)");
     cudaStream_t s = (cudaStream_t)stream;
     int st;
     if (!ctx->d_arena_t) {
@@ -407,7 +448,15 @@ extern "C" int bro_batch_decode_host(bro_ctx* ctx, const uint8_t* h_in, const ui
     if (out_bytes) BRO_CUDA(ctx, cudaMemcpyAsync(h_out + out_lo, ctx->d_out, out_bytes, cudaMemcpyDeviceToHost, s));
     BRO_CUDA(ctx, cudaMemcpyAsync(h_out_len, d_out_len, (size_t)n * sizeof(uint64_t), cudaMemcpyDeviceToHost, s));
     BRO_CUDA(ctx, cudaMemcpyAsync(h_status, d_status, (size_t)n * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+    uint32_t fault = 0;
+    BRO_CUDA(ctx, cudaMemcpyAsync(&fault, ctx->d_counter + 11, sizeof(fault), cudaMemcpyDeviceToHost, s));
     BRO_CUDA(ctx, cudaStreamSynchronize(s));
+    if (fault) {
+        // the copy kernel gave up waiting for the parse kernel: statuses say OK for streams whose copies were never made
+        snprintf(ctx->err, sizeof(ctx->err), "copy kernel watchdog: a stream of the batch was never announced by the parse kernel");
+        for (uint32_t i = 0; i < n; i++) { h_status[i] = BRO_ST_CudaError; h_out_len[i] = 0; }
+        return BRO_ST_CudaError;
+    }
     return BRO_ST_OK;
 }
 
@@ -553,9 +602,28 @@ extern "C" const char* bro_status_description(int st) {
 // ------------------------------------------------------------------------------------------------------
 // The Read-struct: brotli::Decompressor<R: Read>
 // ------------------------------------------------------------------------------------------------------
+// Readers created without a context (what a drop-in `Decompressor::new(r)` does: the reference's test-suite creates
+// dozens) share ONE lazily created context per device for the life of the process -- a few hundred KB of device memory
+// until something is decoded, 10 MB of table arenas for one-stream batches -- and take turns on it.
+#define BRO_MAX_DEVICES 64
+static std::recursive_mutex g_default_mu;     // guards the table below AND every use of a default context (recursive: a
+                                              // reader's callback may itself read from another default-context reader)
+static bro_ctx* g_default_ctx[BRO_MAX_DEVICES];
+
+static bro_ctx* bro_default_ctx(int* st) {    // call with g_default_mu held
+    int device = 0;
+    if (cudaGetDevice(&device) != cudaSuccess || device < 0 || device >= BRO_MAX_DEVICES) { *st = BRO_ST_CudaError; return NULL; }
+    if (!g_default_ctx[device]) {
+        *st = bro_ctx_create(&g_default_ctx[device], device);
+        if (*st) { g_default_ctx[device] = NULL; return NULL; }
+    }
+    *st = BRO_ST_OK;
+    return g_default_ctx[device];
+}
+
 struct bro_reader {
     bro_ctx* ctx;
-    bool own_ctx;
+    bool shared_ctx;          // ctx is the process-wide default context of its device: used under g_default_mu
     bro_read_cb cb;
     void* user;
     bool decoded;             // whole-stream mode: the stream has been decoded; streaming mode: no call can add anything
@@ -579,7 +647,7 @@ static bro_reader* bro_reader_alloc(bro_ctx* ctx, bro_read_cb cb, void* user) {
     if (!cb) return NULL;
     bro_reader* r = new (std::nothrow) bro_reader();
     if (!r) return NULL;
-    r->ctx = ctx; r->own_ctx = false; r->cb = cb; r->user = user;
+    r->ctx = ctx; r->shared_ctx = false; r->cb = cb; r->user = user;
     r->decoded = false; r->status = BRO_ST_OK; r->served = 0;
     r->streaming = false; r->chunk = 0; r->in_eof = false; r->want = 0;
     memset(&r->ck, 0, sizeof(r->ck));
@@ -615,10 +683,13 @@ static void bro_reader_decode(bro_reader* r) {
             in.resize(old + (size_t)got);
             if (chunk < (1u << 24)) chunk <<= 1;
         }
-        if (!r->ctx) {
-            int st = bro_ctx_create(&r->ctx, -1);
-            if (st) { r->status = st; return; }
-            r->own_ctx = true;
+        std::unique_lock<std::recursive_mutex> turn(g_default_mu, std::defer_lock);
+        if (!r->ctx || r->shared_ctx) {
+            turn.lock();
+            int st = BRO_ST_OK;
+            r->ctx = bro_default_ctx(&st);
+            if (!r->ctx) { r->status = st; return; }
+            r->shared_ctx = true;
         }
         size_t cap = in.size() * 6 + (1 << 16);
         for (;;) {
@@ -670,10 +741,13 @@ static int bro_reader_out_reserve(bro_reader* r, size_t cap, size_t keep_from, s
 
 // One step.  Returns BRO_ST_OK when the step may have added bytes to r->out or ended the stream (r->decoded).
 static int bro_reader_step(bro_reader* r) {
-    if (!r->ctx) {
-        int st = bro_ctx_create(&r->ctx, -1);
-        if (st) return bro_reader_fail(r, st);
-        r->own_ctx = true;
+    std::unique_lock<std::recursive_mutex> turn(g_default_mu, std::defer_lock);
+    if (!r->ctx || r->shared_ctx) {
+        turn.lock();
+        int st = BRO_ST_OK;
+        r->ctx = bro_default_ctx(&st);
+        if (!r->ctx) return bro_reader_fail(r, st);
+        r->shared_ctx = true;
     }
     cudaSetDevice(r->ctx->device);
     // top up the input
@@ -796,6 +870,95 @@ extern "C" void bro_reader_free(bro_reader* r) {
         if (r->ctx) cudaSetDevice(r->ctx->device);
         cudaFree(r->d_in); cudaFree(r->d_out[0]); cudaFree(r->d_out[1]); cudaFree(r->d_meta);
     }
-    if (r->own_ctx) bro_ctx_destroy(r->ctx);
-    delete r;
+    delete r;                                          // (a default context lives as long as the process)
+}
+
+// ------------------------------------------------------------------------------------------------------
+// Multi-GPU in one process: one context per device, the batch split by stream into one
+// contiguous range per device with (nearly) equal work, every range decoded by its own host thread through
+// bro_batch_decode_host.  Streams are independent: no byte crosses between GPUs.
+// ------------------------------------------------------------------------------------------------------
+struct bro_mg {
+    int n;
+    bro_ctx** ctx;
+};
+
+extern "C" int bro_mg_create(bro_mg** out, int ngpus) {
+    if (!out) return BRO_ST_InvalidArgument;
+    *out = NULL;
+    int have = 0;
+    if (cudaGetDeviceCount(&have) != cudaSuccess || have < 1) return BRO_ST_CudaError;
+    if (ngpus <= 0) ngpus = have;
+    if (ngpus > have) return BRO_ST_InvalidArgument;
+    int prev = -1;
+    cudaGetDevice(&prev);
+    bro_mg* mg = (bro_mg*)calloc(1, sizeof(bro_mg));
+    if (!mg) return BRO_ST_InvalidArgument;
+    mg->ctx = (bro_ctx**)calloc((size_t)ngpus, sizeof(bro_ctx*));
+    if (!mg->ctx) { free(mg); return BRO_ST_InvalidArgument; }
+    mg->n = ngpus;
+    int st = BRO_ST_OK;
+    for (int k = 0; k < ngpus && !st; k++) st = bro_ctx_create(&mg->ctx[k], k);
+    if (prev >= 0) cudaSetDevice(prev);
+    if (st) { bro_mg_destroy(mg); return st; }
+    *out = mg;
+    return BRO_ST_OK;
+}
+
+extern "C" void bro_mg_destroy(bro_mg* mg) {
+    if (!mg) return;
+    int prev = -1;
+    cudaGetDevice(&prev);
+    for (int k = 0; k < mg->n; k++) bro_ctx_destroy(mg->ctx[k]);
+    if (prev >= 0) cudaSetDevice(prev);
+    free(mg->ctx);
+    free(mg);
+}
+
+extern "C" int bro_mg_device_count(const bro_mg* mg) { return mg ? mg->n : 0; }
+extern "C" bro_ctx* bro_mg_ctx(bro_mg* mg, int k) { return (mg && k >= 0 && k < mg->n) ? mg->ctx[k] : NULL; }
+
+// first[k] .. first[k + 1]: the streams of device k.  Work of a stream = compressed bytes + slot bytes (what crosses
+// PCIe for it and, to first order, what its decode costs); the cut points are where the running sum passes k / ngpus of
+// the total.
+extern "C" int bro_mg_partition(const uint64_t* h_in_off, const uint64_t* h_out_off, uint32_t n, int ngpus, uint32_t* first) {
+    if (!h_in_off || !h_out_off || !first || ngpus < 1) return BRO_ST_InvalidArgument;
+    const long double total = (long double)(h_in_off[n] - h_in_off[0]) + (long double)(h_out_off[n] - h_out_off[0]);
+    uint32_t i = 0;
+    first[0] = 0;
+    for (int k = 1; k < ngpus; k++) {
+        const long double want = total * k / ngpus;
+        while (i < n && (long double)(h_in_off[i + 1] - h_in_off[0]) + (long double)(h_out_off[i + 1] - h_out_off[0]) <= want) i++;
+        first[k] = i;
+    }
+    first[ngpus] = n;
+    return BRO_ST_OK;
+}
+
+extern "C" int bro_mg_decode_host(bro_mg* mg, const uint8_t* h_in, const uint64_t* h_in_off, uint8_t* h_out,
+                                  const uint64_t* h_out_off, uint64_t* h_out_len, int32_t* h_status, uint32_t n) {
+    if (!mg) return BRO_ST_InvalidArgument;
+    if (n == 0) return BRO_ST_OK;
+    if (!h_in_off || !h_out_off || !h_out_len || !h_status) return BRO_ST_InvalidArgument;
+    try {
+        std::vector<uint32_t> first((size_t)mg->n + 1);
+        int st = bro_mg_partition(h_in_off, h_out_off, n, mg->n, first.data());
+        if (st) return st;
+        std::vector<int> rc((size_t)mg->n, BRO_ST_OK);
+        std::vector<std::thread> workers;
+        for (int k = 0; k < mg->n; k++) {
+            const uint32_t a = first[k], b = first[k + 1];
+            if (a == b) continue;
+            // bro_batch_decode_host takes offsets relative to the caller's buffers: a range of the batch is the same
+            // buffers with the offset arrays advanced
+            workers.emplace_back([=, &rc]() {
+                rc[k] = bro_batch_decode_host(mg->ctx[k], h_in, h_in_off + a, h_out, h_out_off + a, h_out_len + a, h_status + a, b - a);
+            });
+        }
+        for (auto& w : workers) w.join();
+        for (int k = 0; k < mg->n; k++) if (rc[k]) return rc[k];
+    } catch (...) {
+        return BRO_ST_InvalidArgument;
+    }
+    return BRO_ST_OK;
 }

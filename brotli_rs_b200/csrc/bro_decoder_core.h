@@ -1274,6 +1274,9 @@ BRO_COPY_FN void bro_lz_copy(uint8_t* out, uint32_t pos, uint32_t dist, uint32_t
     uint32_t n0 = (m - 1u) * dist;
     if (n0 > len) n0 = len;
     for (uint32_t i = lane; i < n0; i += BRO_W) dst[i] = src[i % dist];
+    // the lanes leave the loop above at different trips, and the head bytes of the copy below read what OTHER lanes have
+    // just written (m * dist >= 16 * BRO_W bytes back is inside the prefix): order the stores before those loads
+    bro_syncwarp();
     if (len > n0) bro_copy_far(dst + n0, dst + n0 - m * dist, len - n0);
 #endif
 }
@@ -1639,7 +1642,9 @@ BRO_FN int bro_metablock_tables(BroDec& d, BroMbInfo& mb) {
             else if (i < n_l + n_i) { alphabet = BRO_ALPHA_CMD; T = A + o_cmd + (i - n_l) * BRO_TREE_U16(BRO_ALPHA_CMD); }
             else { alphabet = dist_alphabet; T = A + o_dist + (i - n_l - n_i) * dist_stride; }
 #if defined(BRO_PARSE)
-            st = bro_read_prefix_code(d.in, sc, alphabet, T, i >= n_l);     // literal tables are decoded canonically (bro_parse.h)
+            // literal and insert&copy tables, and the distance table when there is one, are decoded canonically
+            // (bro_parse.h): no root
+            st = bro_read_prefix_code(d.in, sc, alphabet, T, i >= n_l + n_i && ntd >= 2u);
 #else
             st = bro_read_prefix_code(d.in, sc, alphabet, T);
 #endif

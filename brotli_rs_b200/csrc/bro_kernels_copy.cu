@@ -195,12 +195,12 @@ __global__ void __launch_bounds__(WARPS * 32, BRO_COPY_MIN_BLOCKS) bro_copy_kern
             const long long t0 = clock64();
             while ((i = ((volatile uint32_t*)p.done_q)[ticket]) == 0xffffffffu) {
                 __nanosleep(500);
-                if (clock64() - t0 > (1ll << 36)) break;      // watchdog (about half a minute): never spin forever
+                if (clock64() - t0 > p.watchdog) { atomicExch(p.fault, 1u); break; }     // watchdog: never spin forever
             }
             __threadfence();
         }
         i = __shfl_sync(0xffffffffu, i, 0);
-        if (i >= p.n) break;                                  // watchdog fired: give up (the streams left fail parity loudly)
+        if (i >= p.n) break;                                  // watchdog fired: give up; the fault flag fails the whole batch (bro_abi.cu)
         uint64_t meta = 0;
         if (lane == 0) meta = (uint64_t)(uint32_t)p.status[i];
         else if (lane == 1) meta = p.nrec[i];

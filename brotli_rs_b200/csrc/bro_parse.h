@@ -43,21 +43,21 @@
 //     symbols in canonical order as bytes in the block.  A literal of ANY length costs ~30 register instructions and
 //     ONE conflict-free shared-memory look-up, never a trip to L2 (an 8-bit root would take 512 bytes per stream and
 //     still send every longer code off chip: 8 % of the literals of the headline streams);
-//   * insert&copy and distance symbols: narrow roots in the block (their alphabets are skewed: the codes that matter
-//     are short); a miss is settled by the table's own 8-bit root in the arena (one round trip), and only then by the
-//     canonical search (four);
+//   * insert&copy and distance symbols: canonical decode too, from the block alone -- 15 (limit, base) pairs searched
+//     by bisection (four look-ups) and the symbols in canonical order, 10 bits each, as many as fit (120 / 24: the
+//     shortest codes, i.e. all that matter); only a symbol behind those is fetched from the table in the arena.  Round 1
+//     kept 6-bit roots here and settled a miss in the arena: 5 % of the look-ups, but with 32 streams per warp some
+//     lane missed in most steps and the whole warp waited for L2 (19 % of the kernel's stall samples);
 //   * the insert/copy length table: shared memory, one copy per CTA.
-#ifndef BRO_RB_CMD
-#define BRO_RB_CMD 7u
-#endif
-#ifndef BRO_RB_DIST
-#define BRO_RB_DIST 5u
-#endif
-// the block while a meta-block is being decoded (bytes; the header's scratch uses the same bytes, BRO_TL_* )
-#define BRO_TLB_LIT 0u                                   // uint8[256]: symbols of the current literal code in canonical order
-#define BRO_TLB_CMD 256u                                 // uint16[1 << BRO_RB_CMD]: root of the current insert&copy code
-#define BRO_TLB_DIST (BRO_TLB_CMD + (2u << BRO_RB_CMD))  // uint16[1 << BRO_RB_DIST]: root of the distance code (when there is one)
-static_assert(BRO_TLB_DIST + (2u << BRO_RB_DIST) <= BRO_TL_BYTES, "the decode tables must fit the thread's block");
+// the block while a meta-block is being decoded (bytes; the header's scratch uses the same bytes, BRO_TL_*)
+#define BRO_TLB_LIT 0u                  // uint8[256]: symbols of the current literal code in canonical order
+#define BRO_TLB_CMD_TAB 256u            // uint32[16]: the current insert&copy code (bro_parse_load_canon)
+#define BRO_TLB_DIST_TAB 320u           // uint32[16]: the distance code (when the meta-block has one)
+#define BRO_TLB_CMD_SYMS 384u           // 40 words, three 10-bit symbols each: the first 120 insert&copy symbols in canonical order
+#define BRO_TLB_DIST_SYMS 544u          // 8 words: the first 24 distance symbols in canonical order
+#define BRO_CMD_ONCHIP 120u
+#define BRO_DIST_ONCHIP 24u
+static_assert(BRO_TLB_DIST_SYMS + 4u * (BRO_DIST_ONCHIP / 3u) <= BRO_TL_RING, "the decode tables must fit the thread's block");
 
 // The insert&copy length table (src/lookuptable/mod.rs:123, 704 entries) in 48: a symbol's cell (symbol >> 6) gives the
 // high parts of its insert and copy length codes, bits 3..5 and 0..2 the low parts; tab[0..24) holds base | extra
@@ -110,54 +110,59 @@ BRO_FN void bro_parse_begin(BroParse& ps) {
 
 BRO_FN void bro_parse_finish(BroParse& ps, int st) { ps.st = st; ps.kind = BRO_K_DONE; }
 
-// Narrow copy of a table's root in the thread's block: entry r is a direct hit (symbol | len<<10, len <= root_bits) or
-// 1 = settle it in the table itself.
-BRO_FN void bro_narrow_root_tl(BroTl t, uint32_t off, uint32_t root_bits, const uint16_t* T) {
-#pragma unroll 4
-    for (uint32_t r = 0; r < (1u << root_bits); r += 2u) {     // the table's root is 4-byte aligned: two entries per load, four loads in flight
-        const uint32_t ee = *(const uint32_t*)(T + r);
-        const uint32_t e0 = ee & 0xffffu, e1 = ee >> 16, l0 = e0 >> 10, l1 = e1 >> 10;
-        bro_tl_st32(t, off + 2u * r, ((l0 >= 1u && l0 <= root_bits) ? e0 : 1u) | (((l1 >= 1u && l1 <= root_bits) ? e1 : 1u) << 16));
-    }
-}
-
 #if defined(BRO_HOSTSIM)
-// test-suite instrumentation: look-ups through a narrow root [category][0 all | 1 settled by the table's 8-bit root | 2 canonical search]
+// test-suite instrumentation: canonical look-ups [insert&copy | distance][0 all | 1 symbol fetched from the arena | 2 no code]
 static uint64_t bro_hostsim_root_stats[2][3];
-#define BRO_ROOT_STAT(off, k) (bro_hostsim_root_stats[(off) == BRO_TLB_CMD ? 0 : 1][k]++)
+#define BRO_ROOT_STAT(off, k) (bro_hostsim_root_stats[(off) == BRO_TLB_CMD_TAB ? 0 : 1][k]++)
 #else
 #define BRO_ROOT_STAT(off, k)
 #endif
 
-// One symbol through such a copy (same results as bro_decode_sym on the table).
-BRO_FN int bro_decode_sym_tl(BroBits& s, BroTl t, uint32_t off, uint32_t root_bits, const uint16_t* T, uint32_t& sym) {
+// Make T the thread's current insert&copy (or distance) code: word l = 1..15 of the table block holds limit[l] (the
+// left-justified 15-bit end of all codes of length <= l) | base[l + 1] << 16 (canonical index of the first code of
+// length l + 1 minus its value), word 0 what a look-up without a code needs (max length | single flag << 8 | the
+// single symbol << 16); the first `cap` symbols of the canonical order go into the symbol block, three to a word.
+BRO_FN void bro_parse_load_canon(BroTl t, uint32_t tab, uint32_t syms, uint32_t cap, const uint16_t* T) {
+    bro_tl_st32(t, tab, (uint32_t)T[BRO_T_MAXDEPTH] | (T[BRO_T_SINGLE] ? 0x100u : 0u) | ((uint32_t)T[BRO_T_SINGLE_SYM] << 16));
+#pragma unroll
+    for (uint32_t l = 1; l <= 15u; l++)
+        bro_tl_st32(t, tab + 4u * l, (uint32_t)T[BRO_T_LIMIT + l] | (l < 15u ? (uint32_t)T[BRO_T_BASE + l + 1u] << 16 : 0u));
+#pragma unroll 4
+    for (uint32_t w = 0; w < cap / 3u; w++) {      // (entries behind the code's last symbol are never looked up)
+        const uint16_t* p = T + BRO_T_SORTED + 3u * w;
+        bro_tl_st32(t, syms + 4u * w, ((uint32_t)p[0] & 0x3ffu) | (((uint32_t)p[1] & 0x3ffu) << 10) | (((uint32_t)p[2] & 0x3ffu) << 20));
+    }
+}
+
+// One symbol of such a code (same results as bro_decode_sym on the table; src/huffman/tree/mod.rs:63-92): the code's
+// length is 1 + the number of limits the next 15 bits reach -- found by bisection, and the last limit reached brings the
+// base of the length along -- and its symbol sits at base + (bits >> (15 - length)) of the canonical order.
+BRO_FN int bro_decode_sym_canon(BroBits& s, BroTl t, uint32_t tab, uint32_t syms, uint32_t cap, const uint16_t* T, uint32_t& sym) {
     bro_refill(s);
-    uint32_t peek = bro_peek(s);
-    uint32_t e = bro_tl_ld16(t, off + 2u * (peek & ((1u << root_bits) - 1u)));
-    uint32_t len = e >> 10;
-    BRO_ROOT_STAT(off, 0);
-    if (len != 0u) {
-        if (len > bro_avail(s)) return BRO_SYM_EOF;
-        bro_consume(s, len);
-        sym = e & 0x3ffu;
-        return BRO_SYM_OK;
+    const uint32_t x = bro_brev(bro_peek(s)) >> 17;
+    uint32_t c = 0, base = 0;                                // base[1] = 0: the first code of length 1 is code 0 at index 0
+#pragma unroll
+    for (uint32_t k = 8u; k; k >>= 1) {
+        const uint32_t e = bro_tl_ld32(t, tab + 4u * (c + k));
+        if (x >= (e & 0xffffu)) { c += k; base = e >> 16; }
     }
-    // not in the narrow copy: the table's own 8-bit root settles codes of up to 8 bits with one look-up; only what is
-    // longer takes the canonical search (four dependent look-ups)
-    e = T[peek & (BRO_ROOT_SIZE - 1u)];
-    len = e >> 10;
-    BRO_ROOT_STAT(off, 1);
-    if (len != 0u) {
-        if (len > bro_avail(s)) return BRO_SYM_EOF;
-        bro_consume(s, len);
-        sym = e & 0x3ffu;
-        return BRO_SYM_OK;
+    BRO_ROOT_STAT(tab, 0);
+    if (c >= 15u) {
+        // no code starts with these bits: a one-symbol code (zero bits), or a hole / the end of the input
+        const uint32_t m = bro_tl_ld32(t, tab);
+        BRO_ROOT_STAT(tab, 2);
+        if (m & 0x100u) { sym = m >> 16; return BRO_SYM_OK; }
+        return (bro_avail(s) >= (m & 0xffu) + 1u) ? BRO_SYM_HOLE : BRO_SYM_EOF;
     }
-    BRO_ROOT_STAT(off, 2);
-    uint32_t r = bro_sym_slow(T, peek, e, bro_avail(s));
-    bro_consume(s, (r >> 16) & 0xffu);
-    sym = r & 0xffffu;
-    return (int)(r >> 24);
+    const uint32_t len = c + 1u;
+    if (len > bro_avail(s)) return BRO_SYM_EOF;
+    bro_consume(s, len);
+    const uint32_t idx = (uint32_t)((int)(int16_t)base + (int)(x >> (14u - c))) & 1023u;
+    if (idx < cap) {
+        const uint32_t q = (idx * 0xaaabu) >> 17;             // idx / 3
+        sym = (bro_tl_ld32(t, syms + 4u * q) >> (10u * (idx - 3u * q))) & 0x3ffu;
+    } else { sym = T[BRO_T_SORTED + idx]; BRO_ROOT_STAT(tab, 1); }
+    return BRO_SYM_OK;
 }
 
 // Make T the current literal table: symbols in canonical order into the thread's block, limits and base differences
@@ -254,7 +259,7 @@ BRO_FN bool bro_parse_block_step(BroDec& d, BroParse& ps, BroMbInfo& mb, uint32_
         if (st) { bro_parse_finish(ps, st); return false; }
         bl = tc.blen + 1u;
         if (c == 0u) { ps.toff_lit = bro_parse_table(d, ps, mb, 0u); bro_parse_load_lit(ps, d.scv.t, d.arena + ps.toff_lit); }
-        else if (c == 1u) { ps.toff_cmd = bro_parse_table(d, ps, mb, 1u); bro_narrow_root_tl(d.scv.t, BRO_TLB_CMD, BRO_RB_CMD, d.arena + ps.toff_cmd); }
+        else if (c == 1u) { ps.toff_cmd = bro_parse_table(d, ps, mb, 1u); bro_parse_load_canon(d.scv.t, BRO_TLB_CMD_TAB, BRO_TLB_CMD_SYMS, BRO_CMD_ONCHIP, d.arena + ps.toff_cmd); }
     }
     bl -= 1u;
     if (c == 0u) ps.blen0 = bl; else if (c == 1u) ps.blen1 = bl; else ps.blen2 = bl;
@@ -288,8 +293,8 @@ BRO_FN void bro_parse_header(BroDec& d, BroParse& ps, BroMbInfo& mb) {
             ps.toff_cmd = bro_parse_table(d, ps, mb, 1u);
             ps.toff_lit = bro_parse_table(d, ps, mb, 0u);
             bro_parse_load_lit(ps, d.scv.t, d.arena + ps.toff_lit);
-            bro_narrow_root_tl(d.scv.t, BRO_TLB_CMD, BRO_RB_CMD, d.arena + ps.toff_cmd);
-            if (mb.ntd == 1u) { ps.multi |= 8u; bro_narrow_root_tl(d.scv.t, BRO_TLB_DIST, BRO_RB_DIST, d.arena + mb.o_dist); }
+            bro_parse_load_canon(d.scv.t, BRO_TLB_CMD_TAB, BRO_TLB_CMD_SYMS, BRO_CMD_ONCHIP, d.arena + ps.toff_cmd);
+            if (mb.ntd == 1u) { ps.multi |= 8u; bro_parse_load_canon(d.scv.t, BRO_TLB_DIST_TAB, BRO_TLB_DIST_SYMS, BRO_DIST_ONCHIP, d.arena + mb.o_dist); }
             ps.npostfix = mb.npostfix; ps.ndirect = mb.ndirect; ps.o_dist = mb.o_dist;
             ps.kind = BRO_K_CMD;
             return;
@@ -352,7 +357,7 @@ BRO_FN void bro_parse_round(BroDec& d, BroParse& ps, BroMbInfo& mb) {
     // ---- step 1: insert&copy command symbol and its extra bits ----
     if (ps.kind == BRO_K_CMD && bro_parse_block_step(d, ps, mb, 1u)) {
         uint32_t sym = 0;
-        const int r = bro_decode_sym_tl(d.in, d.scv.t, BRO_TLB_CMD, BRO_RB_CMD, d.arena + ps.toff_cmd, sym);
+        const int r = bro_decode_sym_canon(d.in, d.scv.t, BRO_TLB_CMD_TAB, BRO_TLB_CMD_SYMS, BRO_CMD_ONCHIP, d.arena + ps.toff_cmd, sym);
         if (r != BRO_SYM_OK) bro_parse_finish(ps, r == BRO_SYM_HOLE ? BRO_ST_ParseErrorInsertAndCopyLength : BRO_ST_UnexpectedEOF);
         else {
             uint32_t ie, ce;
@@ -444,7 +449,7 @@ BRO_FN void bro_parse_round(BroDec& d, BroParse& ps, BroMbInfo& mb) {
     // ---- step 3: distance code ----
     if (ps.kind == BRO_K_DIST && bro_parse_block_step(d, ps, mb, 2u)) {
         uint32_t sym = 0;
-        const int r = (ps.multi & 8u) ? bro_decode_sym_tl(d.in, d.scv.t, BRO_TLB_DIST, BRO_RB_DIST, d.arena + ps.o_dist, sym)
+        const int r = (ps.multi & 8u) ? bro_decode_sym_canon(d.in, d.scv.t, BRO_TLB_DIST_TAB, BRO_TLB_DIST_SYMS, BRO_DIST_ONCHIP, d.arena + ps.o_dist, sym)
                                       : bro_decode_sym(d.in, d.arena + bro_parse_table(d, ps, mb, 2u), sym);
         if (r != BRO_SYM_OK) bro_parse_finish(ps, r == BRO_SYM_HOLE ? BRO_ST_ParseErrorDistanceCode : BRO_ST_UnexpectedEOF);
         else { ps.dcode = sym; ps.kind = BRO_K_COPY; }

@@ -47,7 +47,9 @@ typedef struct bro_reader bro_reader; /* the Read-struct: one compressed stream,
 #define BRO_QUIRKS_SPEC 1
 
 /* Create a decoder context on CUDA device `device` (-1 = current device).  Allocates the static dictionary
- * image, the per-warp table arenas and the work counter.  Returns BRO_OK or BRO_CUDA_ERROR. */
+ * image and the work counters; the table arenas and record buffers are allocated by the first batch that needs
+ * them, sized by that batch (a context that only ever decodes single streams holds about 10 MB).  Returns BRO_OK
+ * or BRO_CUDA_ERROR. */
 int bro_ctx_create(bro_ctx** ctx, int device);
 void bro_ctx_destroy(bro_ctx* ctx);
 int bro_ctx_set_quirks(bro_ctx* ctx, int quirks);
@@ -81,8 +83,8 @@ int bro_ctx_last_kernel_ms(bro_ctx* ctx, float* ms4);
  * handed to the fused kernel's retry pass, 1 if AUTO's gate sent the whole batch to the fused kernel}. */
 int bro_ctx_last_batch_stats(bro_ctx* ctx, uint64_t* stats4);
 
-/* Optional: an upper bound on the compressed bytes (d_in_off[n] - d_in_off[0]) of the batches that follow, until changed
- * (0 = forget).  The two-phase path sizes its copy-record arena from it; without it bro_batch_decode reads the two end
+/* Optional: an upper bound on the compressed bytes (d_in_off[n] - d_in_off[0]) of the batches that follow.  The bound is
+ * STICKY: it applies to every later batch of the context until it is changed (0 = forget).  The two-phase path sizes its copy-record arena from it; without it bro_batch_decode reads the two end
  * offsets back from the device (16 bytes, blocking on the stream) before it launches.  A bound that turns out too small
  * costs speed only: streams whose records do not fit are decoded by the fused kernel. */
 int bro_ctx_reserve(bro_ctx* ctx, uint64_t total_in_bytes, uint32_t n_streams);
@@ -95,6 +97,9 @@ int bro_ctx_reserve(bro_ctx* ctx, uint64_t total_in_bytes, uint32_t n_streams);
  *   d_out_len  n: bytes produced for stream i
  *   d_status   n: status of stream i (a bad stream never affects another)
  *   stream     cudaStream_t as void* (NULL = default stream).  The call is asynchronous.
+ * d_in must be readable for 16 bytes past d_in_off[n] (stored meta-blocks are moved in 16-byte granules; the host-buffer
+ * entry points pad their staging buffer accordingly).  The kernels run on the context's device whatever the caller's
+ * current device is.
  * Replaces Decompressor::decompress (src/lib.rs:1545-2170) and all of its helpers. */
 int bro_batch_decode(bro_ctx* ctx, const uint8_t* d_in, const uint64_t* d_in_off, uint8_t* d_out,
                      const uint64_t* d_out_off, uint64_t* d_out_len, int32_t* d_status, uint32_t n, void* stream);
@@ -163,6 +168,9 @@ const char* bro_status_description(int status);
  * stream on the GPU (one-stream batch; the output slot grows geometrically while the status is
  * BRO_OUTPUT_TOO_SMALL) and then serves bytes from a host buffer.  Returns the number of bytes written to
  * `buf` (0 = end of stream) or -(status) when the stream is invalid. */
+/* ctx == NULL (what a drop-in Decompressor::new(r) passes): the reader uses a process-wide default context of the
+ * current device, created by the first read of any such reader and shared by all of them (they take turns; it lives
+ * as long as the process). */
 typedef intptr_t (*bro_read_cb)(void* user, uint8_t* buf, size_t cap);
 bro_reader* bro_reader_new(bro_ctx* ctx, bro_read_cb cb, void* user);
 intptr_t bro_reader_read(bro_reader* r, uint8_t* buf, size_t len);
@@ -175,6 +183,23 @@ void bro_reader_free(bro_reader* r);
  * the buffers are bounded by the largest meta-block plus one window, not by the stream.  bro_reader_read fills `buf`
  * while the stream has data; bytes decoded before an error are delivered first, then -(status). */
 bro_reader* bro_reader_new_streaming(bro_ctx* ctx, bro_read_cb cb, void* user, size_t in_chunk);
+
+/* ---- one batch on several GPUs of one box ----
+ * Streams are independent, so a batch shards by stream with no exchange between GPUs: bro_mg_create makes one context
+ * per device (devices 0 .. ngpus-1; ngpus <= 0 = every visible device); bro_mg_decode_host is bro_batch_decode_host over
+ * all of them -- the batch is cut into one contiguous range of streams per device with (nearly) equal compressed + slot
+ * bytes (bro_mg_partition: first[k] .. first[k+1] are device k's streams, first has ngpus + 1 entries), and every range
+ * is decoded by its own host thread with its own context, copies and kernels of the devices overlapping.  Same
+ * results, same argument meaning as bro_batch_decode_host.  bro_mg_ctx gives access to device k's context (mode,
+ * quirks, counters). */
+typedef struct bro_mg bro_mg;
+int bro_mg_create(bro_mg** mg, int ngpus);
+void bro_mg_destroy(bro_mg* mg);
+int bro_mg_device_count(const bro_mg* mg);
+bro_ctx* bro_mg_ctx(bro_mg* mg, int k);
+int bro_mg_partition(const uint64_t* h_in_off, const uint64_t* h_out_off, uint32_t n, int ngpus, uint32_t* first);
+int bro_mg_decode_host(bro_mg* mg, const uint8_t* h_in, const uint64_t* h_in_off, uint8_t* h_out,
+                       const uint64_t* h_out_off, uint64_t* h_out_len, int32_t* h_status, uint32_t n);
 
 #ifdef __cplusplus
 }
