@@ -310,8 +310,10 @@ struct BroBits {
     uint32_t elen;          // end - base
     uint32_t last;          // offset of the word that holds the stream's last byte
     uint32_t pos;           // offset (from base) of the word that will be requested next; the ring holds the BRO_RING_WORDS words before it
-    uint32_t ri;            // ring slot of the word that follows w1
-    uint32_t w0, w1;
+    uint32_t ri;            // ring slot of the word that follows w2
+    uint32_t w0, w1;        // the window
+    uint32_t w2;            // the word behind it: a slide takes ITS word from the ring one slide before the window needs it, so
+                            // that the shared-memory load is never waited for
     uint32_t bp;            // 0..31 after bro_refill
     uint32_t avail;
 };
@@ -338,21 +340,22 @@ BRO_FN uint32_t bro_load_word(const BroBits& s, uint32_t o) {
 BRO_FN void bro_bits_seek(BroBits& s, const uint8_t* a) {
     const uint32_t off = (uint32_t)(a - s.base), wo = off & ~3u;
     s.ri = 0;
-    s.pos = wo + 8u + 4u * BRO_RING_WORDS;
+    s.pos = wo + 12u + 4u * BRO_RING_WORDS;
     s.bp = 8u * (off & 3u);
     s.avail = a < s.end ? 8u * (uint32_t)(s.end - a) : 0u;
-    if (s.elen == 0u) { s.w0 = s.w1 = 0; return; }            // an empty stream: nothing to read, and nothing is ever consumed
+    if (s.elen == 0u) { s.w0 = s.w1 = s.w2 = 0; return; }     // an empty stream: nothing to read, and nothing is ever consumed
 #if !defined(BRO_HOSTSIM)
     asm volatile("cp.async.wait_all;");                         // no request of the old position may land in a slot later
 #endif
     s.w0 = bro_load_word(s, wo);
     s.w1 = bro_load_word(s, wo + 4u);
+    s.w2 = bro_load_word(s, wo + 8u);
     for (uint32_t j = 0; j < BRO_RING_WORDS; j++) {
 #if defined(BRO_HOSTSIM)
-        bro_tl_st32(s.ring, BRO_TL_RING + 4u * j, bro_load_word(s, wo + 8u + 4u * j));
+        bro_tl_st32(s.ring, BRO_TL_RING + 4u * j, bro_load_word(s, wo + 12u + 4u * j));
 #else
         asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n\tcp.async.commit_group;"
-                     :: "r"(s.ring.base + ((BRO_TL_RING + 4u * j) << 5)), "l"(s.base + bro_word_offset(s, wo + 8u + 4u * j)));
+                     :: "r"(s.ring.base + ((BRO_TL_RING + 4u * j) << 5)), "l"(s.base + bro_word_offset(s, wo + 12u + 4u * j)));
 #endif
     }
 }
@@ -377,7 +380,8 @@ BRO_FN void bro_refill(BroBits& s) {
 #if defined(BRO_HOSTSIM)
     if (s.bp >= 32u) {
         s.w0 = s.w1;
-        s.w1 = bro_tl_ld32(s.ring, BRO_TL_RING + 4u * s.ri);
+        s.w1 = s.w2;
+        s.w2 = bro_tl_ld32(s.ring, BRO_TL_RING + 4u * s.ri);
         bro_tl_st32(s.ring, BRO_TL_RING + 4u * s.ri, bro_load_word(s, s.pos));
         s.pos += 4u;
         s.ri = s.ri + 1u == BRO_RING_WORDS ? 0u : s.ri + 1u;
@@ -388,28 +392,29 @@ BRO_FN void bro_refill(BroBits& s) {
                  ".reg .pred p, w;\n\t"
                  ".reg .u32 o, slot;\n\t"
                  ".reg .u64 a;\n\t"
-                 "setp.ge.u32 p, %2, 32;\n\t"
-                 "mad.lo.u32 slot, %4, 128, %5;\n\t"            // the slot of word ri: interleaved, 128 bytes apart
-                 "min.u32 o, %3, %7;\n\t"
+                 "setp.ge.u32 p, %3, 32;\n\t"
+                 "mad.lo.u32 slot, %5, 128, %6;\n\t"          // the slot of word ri: interleaved, 128 bytes apart
+                 "min.u32 o, %4, %8;\n\t"
                  "cvt.u64.u32 a, o;\n\t"
-                 "add.u64 a, a, %6;\n\t"
-                 "@p cp.async.wait_group %8;\n\t"
+                 "add.u64 a, a, %7;\n\t"
+                 "@p cp.async.wait_group %9;\n\t"
                  "@p mov.u32 %0, %1;\n\t"
-                 "@p ld.shared.u32 %1, [slot];\n\t"
+                 "@p mov.u32 %1, %2;\n\t"
+                 "@p ld.shared.u32 %2, [slot];\n\t"
                  "@p cp.async.ca.shared.global [slot], [a], 4;\n\t"
                  "@p cp.async.commit_group;\n\t"
-                 "@p add.u32 %3, %3, 4;\n\t"
-                 "@p add.u32 %4, %4, 1;\n\t"
-                 "@p sub.u32 %2, %2, 32;\n\t"
-                 "setp.eq.and.u32 w, %4, %9, p;\n\t"
-                 "@w mov.u32 %4, 0;\n\t"
+                 "@p add.u32 %4, %4, 4;\n\t"
+                 "@p add.u32 %5, %5, 1;\n\t"
+                 "@p sub.u32 %3, %3, 32;\n\t"
+                 "setp.eq.and.u32 w, %5, %10, p;\n\t"
+                 "@w mov.u32 %5, 0;\n\t"
                  "}"
-                 : "+r"(s.w0), "+r"(s.w1), "+r"(s.bp), "+r"(s.pos), "+r"(s.ri)
+                 : "+r"(s.w0), "+r"(s.w1), "+r"(s.w2), "+r"(s.bp), "+r"(s.pos), "+r"(s.ri)
                  : "r"(s.ring.base + (BRO_TL_RING << 5)), "l"(s.base), "r"(s.last), "n"(BRO_RING_WORDS - 1u), "n"(BRO_RING_WORDS));
 #endif
 }
 // byte offset (from base) of window word w0
-BRO_FN uint32_t bro_bits_w0(const BroBits& s) { return s.pos - 4u * BRO_RING_WORDS - 8u; }
+BRO_FN uint32_t bro_bits_w0(const BroBits& s) { return s.pos - 4u * BRO_RING_WORDS - 12u; }
 #else
 // ONE WARP (or lane group) PER STREAM: the group loads the compressed bytes 32 words at a time (lane i holds word i,
 // the next chunk is already in flight) and feeds the window by shuffle.
