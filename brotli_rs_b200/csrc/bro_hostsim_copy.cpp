@@ -79,10 +79,25 @@ void run_pieces_staged(uint8_t* out, const Rec* r, const uint32_t* geo, const ui
     }
 }
 
+// bro_run_pieces_bulk of bro_kernels_copy.cu (the product): up to NS pieces of the group are fetched whole into their slots
+// (one bulk copy each on the device: every granule that holds a source byte), then consumed one after the other by all 32 lanes
+template <int NS>
+void run_pieces_bulk(uint8_t* out, const Rec* r, const uint32_t* geo, const uint8_t* const* sp, uint32_t j, uint32_t e) {
+    alignas(16) static uint8_t stage[NS * BRO_STAGE_SLOT_BYTES];
+    for (uint32_t k0 = j; k0 < e; k0 += (uint32_t)NS) {
+        const uint32_t cn = e - k0 < (uint32_t)NS ? e - k0 : (uint32_t)NS;
+        for (uint32_t i = 0; i < cn; i++)
+            for (uint32_t lane = 0; lane < 32u; lane++) bro_piece_issue<32>(stage + i * BRO_STAGE_SLOT_BYTES, sp[k0 + i], geo[k0 + i], lane);
+        for (uint32_t i = 0; i < cn; i++)
+            for (uint32_t lane = 0; lane < 32u; lane++) bro_piece_consume<32>(stage + i * BRO_STAGE_SLOT_BYTES, out + r[k0 + i].dst, geo[k0 + i], lane);
+    }
+}
+
 }  // namespace
 
 // words: the records as phase one wrote them (4 x uint32 each).  group = lanes per piece (32, 16, 8, 4); + 100 = the staged
-// form of the long-record path (BRO_COPY_STAGED) with that many lanes per piece.
+// form of the long-record path (BRO_COPY_STAGED) with that many lanes per piece; 200 + NS = the bulk form (BRO_COPY_BULK, the
+// product) with NS pieces in flight.
 // stats (optional, 3 words): groups executed by the piece path / as short records / periodic fills.
 extern "C" void bro_hostsim_copy_exec(uint8_t* out, const uint8_t* in, const uint32_t* words, uint32_t nrec, int group, uint32_t* stats) {
     const uint32_t out_mis = (uint32_t)((uintptr_t)out & 15u);
@@ -120,7 +135,9 @@ extern "C" void bro_hostsim_copy_exec(uint8_t* out, const uint8_t* in, const uin
                     sp[l] = r[l].kind == BRO_REC_STORED ? in + r[l].a : (const uint8_t*)out + (r[l].dst - r[l].a);
                     geo[l] = bro_piece_geo(r[l].dst + out_mis, (uint32_t)(uintptr_t)sp[l], r[l].len);
                 }
-                if (group == 108) run_pieces_staged<8>(out, r, geo, sp, j, e);
+                if (group == 208) run_pieces_bulk<8>(out, r, geo, sp, j, e);
+                else if (group == 203) run_pieces_bulk<3>(out, r, geo, sp, j, e);
+                else if (group == 108) run_pieces_staged<8>(out, r, geo, sp, j, e);
                 else if (group == 116) run_pieces_staged<16>(out, r, geo, sp, j, e);
                 else if (group == 132) run_pieces_staged<32>(out, r, geo, sp, j, e);
                 else if (group == 4) run_pieces<4>(out, in, r, geo, sp, j, e);

@@ -42,7 +42,23 @@
                               // 16 = 9.7 ms, 32 = 11.3 ms; choosing per group between 8 and 32 spills and loses (12.7 ms)
 #endif
 #ifndef BRO_COPY_STAGED
-#define BRO_COPY_STAGED 0     // 1: long records go through shared memory (bro_run_pieces_staged) -- prepared, NOT measured yet
+#define BRO_COPY_STAGED 0     // 1: long records through shared memory with per-granule cp.async (measured in round 2: 9.9 ms vs
+                              // 9.2 ms on the headline batch -- the issue work of 36 copies per piece eats what the staging wins)
+#endif
+#ifndef BRO_COPY_BULK
+#define BRO_COPY_BULK 0       // 1: long records through shared memory with ONE bulk copy (TMA, cp.async.bulk + mbarrier) per
+                              // piece, bro_run_pieces_bulk.  Correct (GPU parity suite) but measured slower in round 2: 10.2 ms at
+                              // 40 warps per SM against 9.2 ms for the register path -- 83 warp instructions per piece (spin on
+                              // the mbarrier, one piece per consume trip) and the generic -> async proxy fence at every group
+                              // (a MEMBAR: 5.4 stall cycles per issue); profiles/r02_kernel_variants.md
+#endif
+#ifndef BRO_COPY_PF_DIST
+#define BRO_COPY_PF_DIST 8192u   // sources at least this far back (and every stored block: it comes from the compressed
+                                 // input) are asked of DRAM with one bulk prefetch (TMA: cp.async.bulk.prefetch.L2) when their
+                                 // record is fetched, steps before they are loaded; 0xffffffff = never
+#endif
+#ifndef BRO_COPY_SLOTS
+#define BRO_COPY_SLOTS 8      // bulk path: pieces in flight per warp (a slot of BRO_STAGE_SLOT_BYTES each)
 #endif
 #ifndef BRO_COPY_QUADS
 #define BRO_COPY_QUADS 2      // staged path: warp steps (of 32 / GROUP pieces) in flight
@@ -166,6 +182,62 @@ __device__ __forceinline__ void bro_run_pieces_staged(uint8_t* out, uint32_t dst
     }
 }
 
+// ---- the same group with ONE bulk copy per piece (BRO_COPY_BULK, the product) ----
+// A piece's source -- one contiguous range of at most 36 aligned 16-byte granules -- is exactly what the TMA unit's 1-D
+// bulk copy moves: cp.async.bulk global -> shared, completion counted in bytes on an mbarrier.  The lane that holds a
+// record issues the copy of its piece (one instruction instead of 36 per-granule copies or 8 loads per lane), up to
+// BRO_COPY_SLOTS pieces of the group are in flight per warp while no register holds any of their data, the warp sleeps
+// on the mbarrier, and then all 32 lanes realign one piece after the other out of shared memory into aligned 16-byte
+// stores (bro_piece_consume<32>: lane v moves vector v; lanes 0..15 / 16..31 the ragged bytes in front / behind).
+__device__ __forceinline__ void bro_mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void bro_mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bro_mbar_wait(uint32_t bar, uint32_t parity) {
+    asm volatile("{\n\t.reg .pred p;\n"
+                 "BRO_MBAR_WAIT:\n\t"
+                 "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+                 "@p bra BRO_MBAR_DONE;\n\t"
+                 "bra BRO_MBAR_WAIT;\n"
+                 "BRO_MBAR_DONE:\n\t}" :: "r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bro_bulk_load(uint32_t smem_dst, const void* gsrc, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 :: "r"(smem_dst), "l"(gsrc), "r"(bytes), "r"(bar) : "memory");
+}
+
+template <int NS>
+__device__ __forceinline__ void bro_run_pieces_bulk(uint8_t* out, uint32_t dst, uint32_t geo, uint32_t sp_lo, uint32_t sp_hi,
+                                                    unsigned lane, uint32_t j, uint32_t e, uint32_t stage, uint32_t bar, uint32_t& parity) {
+    // what the group reads was written by ordinary stores of this warp (earlier groups: the caller's __syncwarp orders
+    // them) and is now read by the asynchronous proxy: order the two
+    asm volatile("fence.proxy.async;" ::: "memory");
+    for (uint32_t k0 = j; k0 < e; k0 += (uint32_t)NS) {
+        const uint32_t cn = e - k0 < (uint32_t)NS ? e - k0 : (uint32_t)NS;
+        // lane k0 + i holds record k0 + i (a lane's index is its record's index in the batch of 32)
+        const bool mine = lane >= k0 && lane < k0 + cn;
+        const uintptr_t s0 = (uintptr_t)sp_lo | ((uintptr_t)sp_hi << 32);
+        uint32_t bytes = 0;
+        if (mine) bytes = ((BRO_GEO_SRC_MIS(geo) + BRO_GEO_HEAD(geo) + 16u * BRO_GEO_NVEC(geo) + BRO_GEO_TAIL(geo) + 15u) >> 4) << 4;
+        const uint32_t total = __reduce_add_sync(0xffffffffu, bytes);
+        if (lane == k0) bro_mbar_expect_tx(bar, total);
+        __syncwarp();
+        if (mine) bro_bulk_load(stage + (lane - k0) * BRO_STAGE_SLOT_BYTES, (const void*)(s0 & ~(uintptr_t)15), bytes, bar);
+        bro_mbar_wait(bar, parity);
+        parity ^= 1u;
+#pragma unroll 1
+        for (uint32_t i = 0; i < cn; i++) {
+            const int ks = (int)(k0 + i);
+            const uint32_t g = __shfl_sync(0xffffffffu, geo, ks);
+            const uint32_t d = __shfl_sync(0xffffffffu, dst, ks);
+            bro_piece_consume<32>(stage + i * BRO_STAGE_SLOT_BYTES, out + d, g, lane);
+        }
+        __syncwarp();                                                    // every lane has read the slots: they are free for the next pieces
+    }
+}
+
 template <int WARPS>
 __global__ void __launch_bounds__(WARPS * 32, BRO_COPY_MIN_BLOCKS) bro_copy_kernel(BroLaunch p) {
     if (p.gate && p.gate[1]) return;       // AUTO: this batch goes to the fused kernel as a whole
@@ -175,10 +247,22 @@ __global__ void __launch_bounds__(WARPS * 32, BRO_COPY_MIN_BLOCKS) bro_copy_kern
     // (the staged long-record path uses the same bytes as BRO_COPY_QUADS * (32 / GROUP) piece slots; a warp is in one
     // path at a time)
     constexpr uint32_t STAGE_SHORT = BRO_COPY_DEPTH * 32u * 32u;
-    constexpr uint32_t STAGE_LONG = BRO_COPY_STAGED ? BRO_COPY_QUADS * (32u / BRO_COPY_GROUP) * BRO_STAGE_SLOT_BYTES : 0u;
+    constexpr uint32_t STAGE_LONG = BRO_COPY_BULK ? BRO_COPY_SLOTS * BRO_STAGE_SLOT_BYTES :
+                                    BRO_COPY_STAGED ? BRO_COPY_QUADS * (32u / BRO_COPY_GROUP) * BRO_STAGE_SLOT_BYTES : 0u;
     constexpr uint32_t STAGE_WARP = STAGE_SHORT > STAGE_LONG ? STAGE_SHORT : STAGE_LONG;
-    __shared__ __align__(16) uint8_t stage[WARPS * STAGE_WARP];
+    __shared__ __align__(128) uint8_t stage[WARPS * STAGE_WARP];
     const uint32_t stage_base = (uint32_t)__cvta_generic_to_shared(stage) + (threadIdx.x >> 5) * STAGE_WARP;
+#if BRO_COPY_BULK
+    // one mbarrier per warp: the bulk copies of a step complete on it (phase parity kept in a register)
+    __shared__ __align__(8) unsigned long long mbar[WARPS];
+    const uint32_t bar = (uint32_t)__cvta_generic_to_shared(&mbar[threadIdx.x >> 5]);
+    uint32_t bar_parity = 0;
+    if (lane == 0) {
+        bro_mbar_init(bar, 1u);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncwarp();
+#endif
     // Streams come from the parse kernel's completion queue: a warp takes a ticket (one ahead of the stream it works on)
     // and waits until the slot of that ticket holds a stream index -- immediately, when the parse kernel has already
     // ended; with the two kernels side by side this is where the copy kernel follows the parse kernel's progress.  A
@@ -224,6 +308,19 @@ __global__ void __launch_bounds__(WARPS * 32, BRO_COPY_MIN_BLOCKS) bro_copy_kern
             }
             const uint32_t len = lk & BRO_REC_LEN_MASK, kind = lk >> BRO_REC_KIND_SHIFT;
             moved += len;
+            // What bounds this kernel is the chain of memory round trips along a stream (a group's loads follow the stores
+            // of the group before it), and a round trip that misses L2 is three times as long.  Output written a few KB ago
+            // is still in L2; far sources -- written tens of microseconds ago and evicted by the 26 GB that followed -- and
+            // stored blocks are not.  They are known from the records long before they are needed: one bulk prefetch per
+            // record into L2 now, and the loads of the steps that follow find them there (round 1: 28 % of the source
+            // sectors came from DRAM, on the critical path).
+            if (lane < cnt && (kind == BRO_REC_STORED || (a >= BRO_COPY_PF_DIST && a >= len))) {
+                const uintptr_t s0 = (uintptr_t)(kind == BRO_REC_STORED ? in + a : (const uint8_t*)out + (dst - a));
+                const uint32_t span = len < 1024u ? len : 1024u;
+                asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;"
+                             :: "l"(s0 & ~(uintptr_t)15), "r"((((uint32_t)s0 & 15u) + span + 15u) & ~15u) : "memory");
+            }
+            if (b + 32u + lane < n) asm volatile("prefetch.global.L2 [%0];" :: "l"(recs + b + 32u + lane));     // the next records
             uint32_t j = 0;
             while (j < cnt) {
                 // the group [j, e): no record reads what a record of the group writes
@@ -260,7 +357,9 @@ __global__ void __launch_bounds__(WARPS * 32, BRO_COPY_MIN_BLOCKS) bro_copy_kern
                     const uint8_t* sp = kind == BRO_REC_STORED ? in + a : (const uint8_t*)out + (dst - a);
                     const uint32_t sp_lo = (uint32_t)(uintptr_t)sp, sp_hi = (uint32_t)((uintptr_t)sp >> 32);
                     const uint32_t geo = bro_piece_geo(dst + out_mis, sp_lo, len);
-#if BRO_COPY_STAGED
+#if BRO_COPY_BULK
+                    bro_run_pieces_bulk<BRO_COPY_SLOTS>(out, dst, geo, sp_lo, sp_hi, lane, j, e, stage_base, bar, bar_parity);
+#elif BRO_COPY_STAGED
                     bro_run_pieces_staged<BRO_COPY_GROUP>(out, dst, geo, sp_lo, sp_hi, lane, j, e, stage_base);
 #else
                     bro_run_pieces<BRO_COPY_GROUP>(out, dst, geo, sp_lo, sp_hi, lane, j, e);

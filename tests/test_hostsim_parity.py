@@ -190,11 +190,12 @@ def test_parse_sizing_mode():
     assert known >= 600
 
 
-@pytest.mark.parametrize("group", [32, 16, 8, 4, 108, 116, 132])
+@pytest.mark.parametrize("group", [208, 203, 32, 16, 8, 4, 108, 116, 132])
 def test_copy_phase_lane_code(group):
     """phase two as the copy kernel executes it: 32 records at a time, groups of independent records, long records piece
     by piece through the kernel's own lane code (bro_copy_piece.h) with `group` lanes per piece, all loads of a step
-    before its first store (group > 100: the staged form, issue / consume through slots with two steps in flight); short
+    before its first store (group > 100: the staged form, issue / consume through slots with two steps in flight; group >
+    200: the product's bulk form, whole pieces fetched into group - 200 slots, then consumed by 32 lanes each); short
     groups last record first.  Bytes must equal the oracle's."""
     enc = fuzzgen.libbrotli_enc()
     if enc is None:
