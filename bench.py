@@ -50,9 +50,17 @@ def parse_args():
     ap.add_argument("--mode", default="auto", choices=["auto", "warp", "twophase"],
                     help="decode path (bro_ctx_set_mode); auto = the library's default policy")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-strong", action="store_true", help="N > 1: skip the strong-scaling record")
+    ap.add_argument("--no-write-roof", action="store_true", help="skip the fill (write-only bandwidth) measurement")
+    ap.add_argument("--extra-workloads", action=argparse.BooleanOptionalAction, default=None,
+                    help="also run the other BASELINE configurations, a few steps each (default: on for the default run)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-sample-streams", type=int, default=None)
-    return ap.parse_args()
+    args = ap.parse_args()
+    if args.extra_workloads is None:
+        # the default run (what the driver launches) carries the other configurations; tuning runs ask for one workload
+        args.extra_workloads = args.workload == "c4_highratio_w16" and not args.no_e2e and args.impl == "b200"
+    return args
 
 
 def measured_peaks():
@@ -181,6 +189,16 @@ def cpu_sample_size(wl, cores, seconds, n_streams):
     return int(max(cores, min(n_streams, 16384, seconds * 60e6 * cores / per_stream)))
 
 
+def config_record(args, desc, n_streams, n_unique, per_rank, comp, uncomp, world):
+    """the same keys on both arms (the driver compares them)"""
+    return {"workload": args.workload, "description": desc, "streams": n_streams, "unique_streams": n_unique,
+            "streams_per_rank": per_rank, "mode": args.mode, "compressed_bytes": comp, "uncompressed_bytes": uncomp,
+            "l2_policy": "inputs and outputs far larger than L2 (no flush needed)",
+            "parallelism": ("%d rank(s), one %d-stream shard each (weak scaling), no data-path collective" % (world, per_rank))
+                           if args.scaling == "weak" else
+                           ("one batch split over %d rank(s) (strong scaling), no data-path collective" % world)}
+
+
 def run_reference(args):
     """--impl reference: the reference algorithm's CPU implementation (oracle port of brotli-rs; the Rust crate cannot
     be built in this image) with all host threads, each step a bounded sample of the same workload."""
@@ -203,8 +221,10 @@ def run_reference(args):
         "impl": "reference", "metric": "uncompressed GB/s (many-stream batch)", "value": val, "unit": "GB/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total_t / args.steps,
         "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-        "config": {"workload": args.workload, "description": desc, "streams": n_streams,
-                   "sample": "%d streams per step" % sample},
+        "config": config_record(args, desc, n_streams, len(wl["streams"]), n_streams // world if args.scaling == "weak" else n_streams,
+                                float(sum(len(wl["streams"][i]) for i in wl["gidx"])),
+                                float(sum(len(wl["raws"][i]) for i in wl["gidx"] if wl["raws"][i] is not None)), world),
+        "sample": "%d of %d streams per step (a thread pool's throughput does not depend on the batch size)" % (sample, n_streams),
         "cpu_baseline": {"value": val, "unit": "GB/s", "cores": cores, "kind": "port",
                          "sample": "%d of %d streams per step, oracle/brotli_oracle.c (C restatement of brotli-rs 0.3.23), %d threads"
                                    % (sample, n_streams, cores)},
@@ -215,43 +235,185 @@ def run_reference(args):
     return 0
 
 
+class Harness:
+    """One rank's device, distributed helpers and decoder."""
+
+    def __init__(self, args):
+        import torch
+        import torch.distributed as dist
+        from brotli_rs_b200 import BatchDecoder
+        self.torch, self.dist = torch, dist
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+        assert torch.cuda.is_available(), "bench.py needs a GPU (there is no CPU decode path)"
+        torch.cuda.set_device(self.local_rank)
+        self.dev = torch.device("cuda", self.local_rank)
+        if self.world > 1:
+            dist.init_process_group("nccl", device_id=self.dev)
+        self.dec = BatchDecoder(self.local_rank, mode={"auto": None, "warp": BatchDecoder.MODE_WARP,
+                                                       "twophase": BatchDecoder.MODE_TWOPHASE}[args.mode])
+
+    def barrier(self):
+        if self.world > 1:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
+
+    def reduce(self, x, op):
+        if self.world == 1:
+            return x
+        t = self.torch.tensor([x], dtype=self.torch.float64, device=self.dev)
+        self.dist.all_reduce(t, op=op)
+        return float(t.item())
+
+    def max_over_ranks(self, x):
+        return self.reduce(x, self.dist.ReduceOp.MAX if self.world > 1 else None)
+
+    def sum_over_ranks(self, x):
+        return self.reduce(x, self.dist.ReduceOp.SUM if self.world > 1 else None)
+
+
+def measure_fill_gbs(h, nbytes=8 << 30):
+    """Write-only bandwidth of this GPU, measured the way MEASURED_PEAKS.json measures the copy peak (torch, CUDA events,
+    best of 5): the roof of a kernel that mostly WRITES, which a read+write copy figure overstates by its read half."""
+    torch = h.torch
+    buf = torch.empty(nbytes, dtype=torch.uint8, device=h.dev)
+    best = 1e9
+    for _ in range(5):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        a.record(); buf.fill_(7); b.record()
+        torch.cuda.synchronize()
+        best = min(best, a.elapsed_time(b))
+    del buf
+    return nbytes / best / 1e6
+
+
+class Batch:
+    """A workload's batch (or this rank's shard of it) resident on the device, with what is needed to check it."""
+
+    def __init__(self, h, wl, mine):
+        from brotli_rs_b200.batch import slot_offsets
+        torch = h.torch
+        streams, raws, gidx = wl["streams"], wl["raws"], wl["gidx"]
+        self.wl, self.h = wl, h
+        self.ulen_in = np.array([len(s) for s in streams], dtype=np.int64)
+        self.ulen_out = np.array([len(r) if r is not None else 0 for r in raws], dtype=np.int64)
+        self.ucap = np.array([len(r) if r is not None else 70000 for r in raws], dtype=np.int64)
+        self.uidx = gidx[mine]
+        self.n = len(self.uidx)
+        self.in_off = np.concatenate([[0], np.cumsum(self.ulen_in[self.uidx])]).astype(np.int64)
+        self.out_off = slot_offsets(self.ucap[self.uidx]).astype(np.int64)
+        ubuf = torch.from_numpy(np.frombuffer(b"".join(streams), dtype=np.uint8).copy()).to(h.dev)
+        uoff = np.concatenate([[0], np.cumsum(self.ulen_in)]).astype(np.int64)
+        # gather the tiled compressed batch on the device (+ 16 readable bytes behind the last stream: include/brotli_b200.h)
+        delta = torch.from_numpy(uoff[self.uidx] - self.in_off[:-1]).to(h.dev)
+        src_idx = torch.repeat_interleave(delta, torch.from_numpy(self.ulen_in[self.uidx]).to(h.dev)) + torch.arange(int(self.in_off[-1]), device=h.dev)
+        self.d_in = torch.zeros(int(self.in_off[-1]) + 16, dtype=torch.uint8, device=h.dev)
+        self.d_in[: int(self.in_off[-1])] = ubuf[src_idx]
+        del src_idx, delta, ubuf
+        self.d_in_off = torch.from_numpy(self.in_off).to(h.dev)
+        self.d_out_off = torch.from_numpy(self.out_off).to(h.dev)
+        self.d_out = torch.empty(int(self.out_off[-1]), dtype=torch.uint8, device=h.dev)
+        self.d_len = torch.empty(self.n, dtype=torch.int64, device=h.dev)
+        self.d_st = torch.empty(self.n, dtype=torch.int32, device=h.dev)
+        self.comp_bytes = float(self.in_off[-1])
+        self.uncomp_bytes = float(self.ulen_out[self.uidx].sum())
+        self.want_st = torch.from_numpy(wl["status"][self.uidx]).to(h.dev)
+        self.check = np.unique(np.concatenate([np.arange(min(self.n, 2048)), np.random.default_rng(h.rank).integers(0, self.n, 2048)]))
+
+    def decode(self):
+        self.h.dec.decode_device(self.d_in, self.d_in_off, self.d_out, self.d_out_off, self.d_len, self.d_st)
+
+    def parity_gate(self):
+        """a timing is only reported if the results are right: statuses, lengths and ~4,000 sampled slots"""
+        torch, raws = self.h.torch, self.wl["raws"]
+        self.decode()
+        torch.cuda.synchronize()
+        assert bool((self.d_st == self.want_st).all()), "status mismatch for some stream"
+        ok_mask = self.want_st == 0
+        assert float(self.d_len[ok_mask].sum().item()) == self.uncomp_bytes
+        d_raw = torch.from_numpy(np.frombuffer(b"".join(r for r in raws if r is not None), dtype=np.uint8).copy()).to(self.h.dev)
+        roff = np.concatenate([[0], np.cumsum(self.ulen_out)]).astype(np.int64)
+        for k in self.check:
+            u = int(self.uidx[k])
+            if raws[u] is None:
+                continue
+            a = self.d_out[int(self.out_off[k]): int(self.out_off[k]) + int(self.ulen_out[u])]
+            assert torch.equal(a, d_raw[int(roff[u]): int(roff[u + 1])]), "GPU output differs from the expected bytes (stream %d)" % k
+
+    def timed(self, steps, warmup, sampler=None):
+        """-> (total ms of `steps` launches on this rank, per-step ms, launches): CUDA events on the launching stream"""
+        h, torch = self.h, self.h.torch
+        for _ in range(warmup):
+            self.decode()
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(steps + 1)]
+        h.barrier()
+        if sampler:
+            sampler.start()
+        launches0 = h.dec.launch_count
+        ev[0].record()
+        for k in range(steps):
+            self.decode()
+            ev[k + 1].record()
+        h.barrier()
+        assert bool((self.d_st == self.want_st).all())
+        return ev[0].elapsed_time(ev[-1]), [ev[k].elapsed_time(ev[k + 1]) for k in range(steps)], h.dec.launch_count - launches0
+
+    def kernel_times(self, steps):
+        """per-kernel times (CUDA events recorded by the library around its kernels) and the batch's counters"""
+        dec = self.h.dec
+        dec.set_timing(True)
+        ksum = {"order": 0.0, "parse": 0.0, "copy": 0.0, "fused": 0.0}
+        for _ in range(steps):
+            self.decode()
+            for k, v in dec.last_kernel_ms().items():
+                ksum[k] += v
+        dec.set_timing(False)
+        return {k: v / steps for k, v in ksum.items()}, dec.last_batch_stats()
+
+
+def quick_workload(h, name, steps, warmup):
+    """one of the other BASELINE configurations on this rank's GPU, device-resident: -> a small record"""
+    n_streams = DEFAULT_STREAMS[name]
+    wl = build_workload(name, n_streams)
+    b = Batch(h, wl, np.arange(n_streams))
+    b.parity_gate()
+    total_ms, step_ms, _ = b.timed(steps, warmup)
+    kms, stats = b.kernel_times(min(steps, 3))
+    peak, _ = measured_peaks()
+    ms = total_ms / steps
+    rec = {"workload": name, "streams": n_streams, "ms_per_step": ms, "value": b.uncomp_bytes / (ms * 1e-3) / 1e9, "unit": "GB/s",
+           "whole_step_frac": (b.comp_bytes + b.uncomp_bytes) / (ms * 1e-3) / 1e9 / peak,
+           "kernel_ms": {k: v for k, v in kms.items() if v > 0.004}, "retried_streams": stats["retried_streams"],
+           "gated_to_fused": stats["gated_to_fused"], "parity": "statuses, lengths and sampled slots checked"}
+    del b
+    h.torch.cuda.empty_cache()
+    return rec
+
+
+def pcie_ceiling(h, h_out, d_out, h_in, d_in):
+    """bare pinned cudaMemcpyAsync of the step's bytes (H2D then D2H, best of 3): what the link gives this rank"""
+    torch = h.torch
+    best = 1e9
+    for _ in range(3):
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        d_in.copy_(h_in, non_blocking=True)
+        h_out.copy_(d_out, non_blocking=True)
+        torch.cuda.synchronize()
+        best = min(best, time.perf_counter() - t0)
+    return best
+
+
 def main():
     args = parse_args()
     if args.impl == "reference":
         return run_reference(args)
 
-    import torch
-    import torch.distributed as dist
-    from brotli_rs_b200 import BatchDecoder, shard_streams
-    from brotli_rs_b200.batch import slot_offsets
-
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    assert torch.cuda.is_available(), "bench.py needs a GPU (there is no CPU decode path)"
-    torch.cuda.set_device(local_rank)
-    dev = torch.device("cuda", local_rank)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    def max_over_ranks(x):
-        if world == 1:
-            return x
-        t = torch.tensor([x], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
-
-    def sum_over_ranks(x):
-        if world == 1:
-            return x
-        t = torch.tensor([x], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.SUM)
-        return float(t.item())
+    from brotli_rs_b200 import shard_streams
+    h = Harness(args)
+    torch, dist, rank, world, dev, dec = h.torch, h.dist, h.rank, h.world, h.dev, h.dec
 
     # ---- workload: N_UNIQUE distinct streams tiled to the job's batch; this rank's shard ----
     per_rank = args.streams or DEFAULT_STREAMS[args.workload]
@@ -259,86 +421,28 @@ def main():
     wl = build_workload(args.workload, n_streams)
     streams, raws, desc, gidx = wl["streams"], wl["raws"], wl["desc"], wl["gidx"]
     ulen_in = np.array([len(s) for s in streams], dtype=np.int64)
-    ulen_out = np.array([len(r) if r is not None else 0 for r in raws], dtype=np.int64)
     ucap = np.array([len(r) if r is not None else 70000 for r in raws], dtype=np.int64)
     if args.scaling == "weak":
         mine = np.arange(rank * per_rank, (rank + 1) * per_rank)      # every rank: one BASELINE-size shard of the job
     else:
         mine = shard_streams(ulen_in[gidx], ucap[gidx], world, rank)
-    uidx = gidx[mine]
-    n = len(uidx)
-    in_off = np.concatenate([[0], np.cumsum(ulen_in[uidx])]).astype(np.int64)
-    out_off = slot_offsets(ucap[uidx]).astype(np.int64)
-    ubuf = torch.from_numpy(np.frombuffer(b"".join(streams), dtype=np.uint8).copy()).to(dev)
-    uoff = np.concatenate([[0], np.cumsum(ulen_in)]).astype(np.int64)
-    # gather the tiled compressed batch on the device
-    delta = torch.from_numpy(uoff[uidx] - in_off[:-1]).to(dev)
-    src_idx = torch.repeat_interleave(delta, torch.from_numpy(ulen_in[uidx]).to(dev)) + torch.arange(int(in_off[-1]), device=dev)
-    d_in = ubuf[src_idx].contiguous()
-    del src_idx, delta
-    d_in_off = torch.from_numpy(in_off).to(dev)
-    d_out_off = torch.from_numpy(out_off).to(dev)
-    d_out = torch.empty(int(out_off[-1]), dtype=torch.uint8, device=dev)
-    d_len = torch.empty(n, dtype=torch.int64, device=dev)
-    d_st = torch.empty(n, dtype=torch.int32, device=dev)
-    dec = BatchDecoder(local_rank, mode={"auto": None, "warp": BatchDecoder.MODE_WARP, "twophase": BatchDecoder.MODE_TWOPHASE}[args.mode])
-
-    comp_bytes = float(in_off[-1])
-    uncomp_bytes = float(ulen_out[uidx].sum())
-
-    # ---- parity gate (a timing is only reported if the results are right) ----
-    dec.decode_device(d_in, d_in_off, d_out, d_out_off, d_len, d_st)
-    torch.cuda.synchronize()
-    want_st = torch.from_numpy(wl["status"][uidx]).to(dev)
-    assert bool((d_st == want_st).all()), "status mismatch for some stream"
-    ok_mask = want_st == 0
-    assert float(d_len[ok_mask].sum().item()) == uncomp_bytes
-    d_raw = torch.from_numpy(np.frombuffer(b"".join(r for r in raws if r is not None), dtype=np.uint8).copy()).to(dev)
-    roff = np.concatenate([[0], np.cumsum(ulen_out)]).astype(np.int64)
-    check = np.unique(np.concatenate([np.arange(min(n, 2048)), np.random.default_rng(rank).integers(0, n, 2048)]))
-    for k in check:
-        u = int(uidx[k])
-        if raws[u] is None:
-            continue
-        a = d_out[int(out_off[k]): int(out_off[k]) + int(ulen_out[u])]
-        assert torch.equal(a, d_raw[int(roff[u]): int(roff[u + 1])]), "GPU output differs from the expected bytes (stream %d)" % k
-    del d_raw
+    bt = Batch(h, wl, mine)
+    n, uidx, in_off, out_off, ulen_out = bt.n, bt.uidx, bt.in_off, bt.out_off, bt.ulen_out
+    comp_bytes, uncomp_bytes = bt.comp_bytes, bt.uncomp_bytes
+    bt.parity_gate()
 
     # ---- timed region: K launches, CUDA events on the launching stream ----
-    for _ in range(args.warmup):
-        dec.decode_device(d_in, d_in_off, d_out, d_out_off, d_len, d_st)
-    sampler = ClockSampler(local_rank)
-    ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
-    barrier()
-    sampler.start()
-    launches0 = dec.launch_count
-    ev[0].record()
-    for k in range(args.steps):
-        dec.decode_device(d_in, d_in_off, d_out, d_out_off, d_len, d_st)
-        ev[k + 1].record()
-    barrier()
+    sampler = ClockSampler(h.local_rank)
+    total_ms, step_ms, launches = bt.timed(args.steps, args.warmup, sampler)
     clocks = sampler.stop()
-    launches = dec.launch_count - launches0
-    total_ms = ev[0].elapsed_time(ev[-1])
-    step_ms = [ev[k].elapsed_time(ev[k + 1]) for k in range(args.steps)]
-    assert bool((d_st == want_st).all())
-    total_ms_max = max_over_ranks(total_ms)
-    all_uncomp = sum_over_ranks(uncomp_bytes)
-    all_comp = sum_over_ranks(comp_bytes)
+    total_ms_max = h.max_over_ranks(total_ms)
+    all_uncomp = h.sum_over_ranks(uncomp_bytes)
+    all_comp = h.sum_over_ranks(comp_bytes)
     value = all_uncomp * args.steps / (total_ms_max * 1e-3) / 1e9
 
-    # ---- per-kernel times (CUDA events recorded by the library around its kernels, on the launching stream) and the
-    # roofline of the dominant kernel on this rank ----
+    # ---- per-kernel times and the roofline of the dominant kernel on this rank ----
     peak, peak_src = measured_peaks()
-    dec.set_timing(True)
-    ksum = {"order": 0.0, "parse": 0.0, "copy": 0.0, "fused": 0.0}
-    for _ in range(args.steps):
-        dec.decode_device(d_in, d_in_off, d_out, d_out_off, d_len, d_st)
-        for k, v in dec.last_kernel_ms().items():
-            ksum[k] += v
-    dec.set_timing(False)
-    stats = dec.last_batch_stats()
-    kms = {k: v / args.steps for k, v in ksum.items()}
+    kms, stats = bt.kernel_times(args.steps)
     # algorithmic bytes per launch: fused = compressed read + uncompressed written; copy = bytes
     # written by copy records + 16 B per record read; parse = compressed read + bytes it writes itself (literals,
     # dictionary words) + 16 B per record written
@@ -364,16 +468,47 @@ def main():
     kern_ms = kms[dom]
     algo_bytes = algo.get(dom) or (comp_bytes + uncomp_bytes)
     achieved = algo_bytes / (kern_ms * 1e-3) / 1e9
+    mean_step = float(np.mean(step_ms))
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": ncu_traffic(args.workload, algo_bytes, names[dom]), "peak_source": peak_src,
                 "kernel": names[dom], "kernel_ms": kern_ms, "algorithmic_bytes_per_launch": algo_bytes,
-                "kernel_share_of_step": kern_ms / float(np.mean(step_ms)), "kernels": kernels,
-                "whole_step": {"ms": float(np.mean(step_ms)), "algorithmic_bytes": comp_bytes + uncomp_bytes,
-                               "frac": (comp_bytes + uncomp_bytes) / (float(np.mean(step_ms)) * 1e-3) / 1e9 / peak},
+                "kernel_share_of_step": kern_ms / mean_step, "kernels": kernels,
+                "whole_step": {"ms": mean_step, "algorithmic_bytes": comp_bytes + uncomp_bytes,
+                               "frac": (comp_bytes + uncomp_bytes) / (mean_step * 1e-3) / 1e9 / peak},
                 "batch_stats": stats}
+    if rank == 0 and not args.no_write_roof:
+        # The step WRITES 67 x what it reads from DRAM (26 GB of output for 0.4 GB of input; copy sources are re-reads of
+        # recent output, mostly L2 hits).  The read+write copy figure above is the contract's denominator; the roof that
+        # physically bounds a write-dominated kernel is the write-only bandwidth, measured here the same way.
+        fill = measure_fill_gbs(h)
+        roofline["write_roof"] = {"fill_gbs": fill, "how": "torch fill_ of 8 GiB, CUDA events, best of 5, this run",
+                                  "whole_step_frac_of_write_roof": uncomp_bytes / (mean_step * 1e-3) / 1e9 / fill}
+        if two_phase and kms["copy"] > 0.0:
+            roofline["write_roof"]["copy_kernel_frac_of_write_roof"] = stats["copy_bytes"] / (kms["copy"] * 1e-3) / 1e9 / fill
+            # SURVEY.md 8(d) counts the copy phase as 2 x copy bytes (source read + destination write), which is what a
+            # plain device copy of the same bytes moves through the SMs
+            kernels[names["copy"]]["frac_counting_source_reads"] = (2.0 * stats["copy_bytes"] + rec_bytes) / (kms["copy"] * 1e-3) / 1e9 / peak
     if dom == "parse":
         roofline["note"] = ("bro_parse_kernel (entropy decode, one thread per stream) moves few bytes and is latency-bound, not "
                             "HBM-bound (DESIGN.md 3.3); the HBM-bound kernel of the step is bro_copy_kernel, see kernels")
+
+    # ---- strong scaling (N > 1): ONE BASELINE-size batch split over the ranks, next to the weak headline above ----
+    strong = None
+    if world > 1 and args.scaling == "weak" and not args.no_strong:
+        wl1 = build_workload(args.workload, per_rank)
+        mine_s = shard_streams(ulen_in[wl1["gidx"]], ucap[wl1["gidx"]], world, rank)
+        bs = Batch(h, wl1, mine_s)
+        bs.parity_gate()
+        s_ms, _, _ = bs.timed(args.steps, args.warmup)
+        s_ms_max = h.max_over_ranks(s_ms) / args.steps
+        s_uncomp = h.sum_over_ranks(bs.uncomp_bytes)
+        skms, sstats = bs.kernel_times(min(args.steps, 3))
+        strong = {"streams": per_rank, "streams_per_rank": bs.n, "ms_per_step": s_ms_max, "value": s_uncomp / (s_ms_max * 1e-3) / 1e9,
+                  "unit": "GB/s", "speedup_vs_one_gpu": (total_ms_max / args.steps) / s_ms_max,
+                  "speedup_basis": "this run's weak step (every rank decodes the whole %d-stream batch's worth: the N = 1 workload) / the strong step" % per_rank,
+                  "kernel_ms_rank0": {k: v for k, v in skms.items() if v > 0.004}, "gated_to_fused": sstats["gated_to_fused"]}
+        del bs
+        torch.cuda.empty_cache()
 
     # ---- end to end through the C ABI with pinned host buffers ----
     e2e = None
@@ -384,12 +519,12 @@ def main():
         ne = n if (world == 1 or args.scaling == "strong") else max(1, n // world)
         e_in, e_out = int(in_off[ne]), int(out_off[ne])
         h_in = torch.empty(e_in, dtype=torch.uint8).pin_memory()
-        h_in.copy_(d_in[:e_in])
+        h_in.copy_(bt.d_in[:e_in])
         h_out = torch.empty(e_out, dtype=torch.uint8).pin_memory()
         hin_np, hout_np = h_in.numpy(), h_out.numpy()
         in_off_u, out_off_u = in_off[: ne + 1].astype(np.uint64), out_off[: ne + 1].astype(np.uint64)
         dec.decode_host(hin_np, in_off_u, out_off_u, out=hout_np)        # warm-up (also sizes the device staging)
-        barrier()
+        h.barrier()
         t0 = time.perf_counter()
         for _ in range(e2e_steps):
             _, out_len, status = dec.decode_host(hin_np, in_off_u, out_off_u, out=hout_np)
@@ -397,14 +532,22 @@ def main():
         t1 = time.perf_counter()
         e_uncomp = float(ulen_out[uidx[:ne]].sum())
         assert (status == wl["status"][uidx[:ne]]).all() and float(out_len[status == 0].sum()) == e_uncomp
-        for k in check[check < ne][-8:]:
+        for k in bt.check[bt.check < ne][-8:]:
             u = int(uidx[k])
             if raws[u] is not None:
                 assert hout_np[int(out_off[k]): int(out_off[k]) + int(ulen_out[u])].tobytes() == raws[u]
-        e2e_t = max_over_ranks(t1 - t0)
-        e2e = {"value": sum_over_ranks(e_uncomp) * e2e_steps / e2e_t / 1e9, "unit": "GB/s",
+        e2e_t = h.max_over_ranks(t1 - t0)
+        # what the link alone gives: the same bytes with bare pinned copies, all ranks at once
+        h.barrier()
+        ceil_t = h.max_over_ranks(pcie_ceiling(h, h_out, bt.d_out[:e_out], h_in, bt.d_in[:e_in]))
+        sum_uncomp = h.sum_over_ranks(e_uncomp)
+        e2e = {"value": sum_uncomp * e2e_steps / e2e_t / 1e9, "unit": "GB/s",
                "h2d_bytes_per_step": int(e_in + 2 * 8 * (ne + 1)), "d2h_bytes_per_step": int(e_out + 12 * ne),
-               "steps": e2e_steps, "streams_per_rank": int(ne), "api": "bro_batch_decode_host (pinned host buffers, per rank)"}
+               "steps": e2e_steps, "streams_per_rank": int(ne), "api": "bro_batch_decode_host (pinned host buffers, per rank; "
+               "slices of the batch: the copy out of slice k overlaps the decode of slice k + 1)",
+               "ceiling_gbs": sum_uncomp / ceil_t / 1e9,
+               "ceiling": "the same H2D + D2H bytes as bare pinned cudaMemcpyAsync on every rank at once (best of 3), in the metric's unit",
+               "frac_of_ceiling": (sum_uncomp * e2e_steps / e2e_t) / (sum_uncomp / ceil_t)}
         del h_in, h_out
 
     # ---- CPU baseline (rank 0, N = 1 only): the oracle port on the host cores, bounded sample ----
@@ -417,20 +560,33 @@ def main():
                "sample": "%d of %d streams, oracle/brotli_oracle.c (C restatement of brotli-rs 0.3.23; rustc absent), %d threads, %.1f s"
                          % (sample, n_streams, cores, t)}
 
+    # ---- the other BASELINE configurations, device-resident, a few steps each (rank 0's GPU; N = 8 adds only C5) ----
+    extra = None
+    if args.extra_workloads and args.workload == "c4_highratio_w16":
+        del bt
+        torch.cuda.empty_cache()
+        names_x = ["c2_quickfox_x10k", "c3_corpus_x1000", "c5_stored_10k", "c5b_literals_10k"] if world == 1 else ["c5_stored_10k"]
+        extra = []
+        if rank == 0:
+            for nm in names_x:
+                try:
+                    extra.append(quick_workload(h, nm, 5, 3))
+                except Exception as e:     # a side measurement never takes the headline line down
+                    extra.append({"workload": nm, "error": repr(e)[:200]})
+        h.barrier()
+
     if rank == 0:
         line = {
             "metric": "uncompressed GB/s (many-stream batch)", "value": value, "unit": "GB/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": total_ms_max / args.steps,
             "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-            "config": {"workload": args.workload, "description": desc, "streams": n_streams,
-                       "unique_streams": len(streams), "streams_per_rank": n, "mode": args.mode,
-                       "compressed_bytes": all_comp, "uncompressed_bytes": all_uncomp,
-                       "l2_policy": "inputs and outputs far larger than L2 (no flush needed)",
-                       "parallelism": ("%d rank(s), one %d-stream shard each (weak scaling), no data-path collective" % (world, n))
-                                      if args.scaling == "weak" else
-                                      ("one batch split over %d rank(s) (strong scaling), no data-path collective" % world)},
+            "config": config_record(args, desc, n_streams, len(streams), n, all_comp, all_uncomp, world),
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
         }
+        if strong is not None:
+            line["strong"] = strong
+        if extra is not None:
+            line["extra_workloads"] = extra
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

@@ -8,9 +8,9 @@ raise.
 """
 from ._lib import (BroError, OK, OUTPUT_TOO_SMALL, UNEXPECTED_EOF, library_path, load_library,
                    status_description)
-from .batch import BatchDecoder, pack_streams
+from .batch import BatchDecoder, MultiGpuDecoder, mg_partition, pack_streams
 from .decompressor import Decompressor
 from .shard import gather_outputs, scatter_batch, shard_streams
 
-__all__ = ["BatchDecoder", "Decompressor", "BroError", "pack_streams", "shard_streams", "scatter_batch", "gather_outputs", "status_description",
+__all__ = ["BatchDecoder", "MultiGpuDecoder", "mg_partition", "Decompressor", "BroError", "pack_streams", "shard_streams", "scatter_batch", "gather_outputs", "status_description",
            "load_library", "library_path", "OK", "OUTPUT_TOO_SMALL", "UNEXPECTED_EOF"]

@@ -17,6 +17,7 @@ ABI_SYMBOLS = [
     "bro_ctx_create", "bro_ctx_destroy", "bro_ctx_set_quirks", "bro_ctx_set_mode", "bro_ctx_last_cuda_error", "bro_ctx_launch_count",
     "bro_ctx_num_warps", "bro_ctx_reserve", "bro_ctx_set_timing", "bro_ctx_last_kernel_ms", "bro_ctx_last_batch_stats", "bro_batch_decode", "bro_batch_decode_host", "bro_batch_sizes", "bro_batch_decode_unsized_host", "bro_batch_decode_resume", "bro_reader_new_streaming", "bro_free", "bro_status_description",
     "bro_reader_new", "bro_reader_read", "bro_reader_status", "bro_reader_free",
+    "bro_mg_create", "bro_mg_destroy", "bro_mg_device_count", "bro_mg_ctx", "bro_mg_partition", "bro_mg_decode_host",
 ]
 
 READ_CB = ctypes.CFUNCTYPE(ctypes.c_ssize_t, ctypes.c_void_p, ctypes.POINTER(ctypes.c_uint8), ctypes.c_size_t)
@@ -93,6 +94,18 @@ def load_library():
     L.bro_reader_status.argtypes = [vp]
     L.bro_reader_free.restype = None
     L.bro_reader_free.argtypes = [vp]
+    L.bro_mg_create.restype = ctypes.c_int
+    L.bro_mg_create.argtypes = [ctypes.POINTER(vp), ctypes.c_int]
+    L.bro_mg_destroy.restype = None
+    L.bro_mg_destroy.argtypes = [vp]
+    L.bro_mg_device_count.restype = ctypes.c_int
+    L.bro_mg_device_count.argtypes = [vp]
+    L.bro_mg_ctx.restype = vp
+    L.bro_mg_ctx.argtypes = [vp, ctypes.c_int]
+    L.bro_mg_partition.restype = ctypes.c_int
+    L.bro_mg_partition.argtypes = [vp, vp, u32, ctypes.c_int, vp]
+    L.bro_mg_decode_host.restype = ctypes.c_int
+    L.bro_mg_decode_host.argtypes = [vp, vp, vp, vp, vp, vp, vp, u32]
     _LIB = L
     return L
 

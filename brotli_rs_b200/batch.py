@@ -204,3 +204,72 @@ class BatchDecoder:
             b = int(out_off[i])
             res.append((int(status[i]), out[b: b + int(out_len[i])].tobytes()))
         return res
+
+
+def mg_partition(in_off, out_off, ngpus):
+    """bro_mg_partition: the contiguous ranges of streams bro_mg_decode_host gives the devices (n + 1 offsets each;
+    -> ngpus + 1 cut points).  Pure host arithmetic: works without a GPU."""
+    lib = _lib.load_library()
+    in_off = np.ascontiguousarray(in_off, dtype=np.uint64)
+    out_off = np.ascontiguousarray(out_off, dtype=np.uint64)
+    first = np.zeros(ngpus + 1, dtype=np.uint32)
+    st = lib.bro_mg_partition(in_off.ctypes.data, out_off.ctypes.data, len(in_off) - 1, ngpus, first.ctypes.data)
+    if st != 0:
+        raise _lib.BroError(st)
+    return first
+
+
+class MultiGpuDecoder:
+    """bro_mg_*: one batch over several GPUs of this box from ONE process (one context and one host thread per device;
+    streams are independent, nothing crosses between GPUs).  The torch.distributed layer (shard.py, bench.py) is the
+    one-process-per-GPU form of the same sharding."""
+
+    def __init__(self, ngpus=0):
+        import torch
+        if not torch.cuda.is_available():
+            raise RuntimeError("brotli_rs_b200 needs a CUDA device: the decoder has no CPU path")
+        self._lib = _lib.load_library()
+        h = ctypes.c_void_p()
+        st = self._lib.bro_mg_create(ctypes.byref(h), int(ngpus))
+        if st != 0:
+            raise _lib.BroError(st)
+        self._mg = h
+
+    @property
+    def device_count(self):
+        return int(self._lib.bro_mg_device_count(self._mg))
+
+    def set_mode(self, mode):
+        for k in range(self.device_count):
+            self._lib.bro_ctx_set_mode(self._lib.bro_mg_ctx(self._mg, k), int(mode))
+
+    def decode_host(self, in_buf, in_off, out_off, out=None):
+        """bro_mg_decode_host: same arguments and results as BatchDecoder.decode_host"""
+        in_buf = np.ascontiguousarray(in_buf, dtype=np.uint8)
+        in_off = np.ascontiguousarray(in_off, dtype=np.uint64)
+        out_off = np.ascontiguousarray(out_off, dtype=np.uint64)
+        n = len(in_off) - 1
+        if out is None:
+            out = np.empty(int(out_off[-1]), dtype=np.uint8)
+        out_len = np.zeros(n, dtype=np.uint64)
+        status = np.zeros(n, dtype=np.int32)
+        st = self._lib.bro_mg_decode_host(self._mg, in_buf.ctypes.data, in_off.ctypes.data, out.ctypes.data,
+                                          out_off.ctypes.data, out_len.ctypes.data, status.ctypes.data, n)
+        if st != 0:
+            msg = None
+            if st == _lib.CUDA_ERROR:
+                msg = "CUDA error: " + "; ".join(self._lib.bro_ctx_last_cuda_error(self._lib.bro_mg_ctx(self._mg, k)).decode()
+                                                 for k in range(self.device_count))
+            raise _lib.BroError(st, msg)
+        return out, out_len, status
+
+    def close(self):
+        if getattr(self, "_mg", None):
+            self._lib.bro_mg_destroy(self._mg)
+            self._mg = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -40,7 +40,10 @@ struct bro_ctx {
     uint32_t* d_order; size_t d_order_cap;   // size-class order of the batch | records per stream | completion queue (3 * cap)
     uint32_t* d_order_scratch;               // 512 counters
     BroRec* d_rec; size_t d_rec_cap;         // copy records (in records)
-    cudaStream_t side;        // the copy kernel runs here, next to the parse kernel on the caller's stream
+    cudaStream_t main;        // host-buffer path: copies in and kernels
+    uint32_t* h_fault;        // host-buffer path: pinned, one fault word per chunk
+    int host_chunks;          // host-buffer path: slices of a batch whose device -> host copy overlaps the decode of the next
+    cudaStream_t side;        // host-buffer path: copies out (round 1: the copy kernel next to the parse kernel)
     cudaEvent_t ev_fork, ev_join;
     int overlap;              // 1: parse and copy kernels side by side (BRO_B200_OVERLAP=1); 0 (default): one after the other
                               // (always while timing is on, so that bro_ctx_last_kernel_ms reports each kernel alone)
@@ -53,6 +56,7 @@ struct bro_ctx {
     uint32_t twophase_threshold;   // AUTO: batches of at least this many streams take the two-phase path
     int quirks;
     long long watchdog;       // copy kernel: cycles to wait for one completion-queue slot (about half a minute)
+    int parse_lanes;          // BRO_B200_PARSE_LANES=1..32 (tuning): streams per parse warp, 0 = by batch size
     int debug_no_parse;       // BRO_B200_DEBUG_NO_PARSE=1 (test-suite): the parse kernel is not launched, so the copy kernel's watchdog must fire
     uint64_t launches;
     char err[256];
@@ -99,6 +103,11 @@ extern "C" int bro_ctx_create(bro_ctx** out, int device) {
     // The two kernels of the two-phase path run one after the other: the parse kernel's CTA takes an SM's whole shared
     // memory (round 1 could run them side by side through the completion queue; it bought 5 % at best).
     ctx->overlap = 0;
+    if (cudaStreamCreateWithFlags(&ctx->main, cudaStreamNonBlocking) != cudaSuccess) { ctx->main = NULL; cudaGetLastError(); }
+    if (cudaHostAlloc((void**)&ctx->h_fault, 16 * sizeof(uint32_t), cudaHostAllocDefault) != cudaSuccess) { ctx->h_fault = NULL; cudaGetLastError(); }
+    ctx->host_chunks = 4;
+    { const char* hc = getenv("BRO_B200_HOST_CHUNKS"); if (hc && atoi(hc) >= 1 && atoi(hc) <= 16) ctx->host_chunks = atoi(hc); }
+    { const char* pl = getenv("BRO_B200_PARSE_LANES"); if (pl && atoi(pl) >= 1 && atoi(pl) <= 32) ctx->parse_lanes = atoi(pl); }
     ctx->watchdog = 1ll << 36;
     { const char* dbg = getenv("BRO_B200_DEBUG_NO_PARSE"); if (dbg && dbg[0] == '1') { ctx->debug_no_parse = 1; ctx->watchdog = 1ll << 22; } }
     if (cudaStreamCreateWithFlags(&ctx->side, cudaStreamNonBlocking) != cudaSuccess ||
@@ -134,6 +143,8 @@ extern "C" void bro_ctx_destroy(bro_ctx* ctx) {
     if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
     if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
     if (ctx->side) cudaStreamDestroy(ctx->side);
+    if (ctx->main) cudaStreamDestroy(ctx->main);
+    if (ctx->h_fault) cudaFreeHost(ctx->h_fault);
     free(ctx);
 }
 
@@ -290,8 +301,15 @@ extern "C" int bro_batch_decode(bro_ctx* ctx, const uint8_t* d_in, const uint64_
         if (e != cudaSuccess) return bro_fail(ctx, e, "bro_order kernels launch");
         ctx->launches += 3;
         const uint32_t tb = (uint32_t)bro_parse_kernel_block();
+        // A batch smaller than the resident lanes is spread over all SMs: every warp takes fewer streams (a warp's lockstep
+        // steps then serve fewer, busier lanes, and a stream's latency -- which is what a small batch costs -- drops)
+        const uint32_t warps_total = (uint32_t)ctx->grid_t * (tb / 32u);
+        uint32_t lanes = (n + warps_total - 1u) / warps_total;
+        lanes = lanes < 4u ? 4u : lanes > 32u ? 32u : lanes;
+        if (ctx->parse_lanes) lanes = (uint32_t)ctx->parse_lanes;
+        p.lanes = lanes;
         int grid_t = ctx->grid_t;
-        if ((uint32_t)grid_t > (n + tb - 1) / tb) grid_t = (int)((n + tb - 1) / tb);
+        if ((uint32_t)grid_t > (n + lanes * (tb / 32u) - 1u) / (lanes * (tb / 32u))) grid_t = (int)((n + lanes * (tb / 32u) - 1u) / (lanes * (tb / 32u)));
         const uint32_t cw = (uint32_t)bro_copy_kernel_warps_per_cta();
         p.counter = ctx->d_counter + 3; p.order = NULL;
         p.copy_stats = (unsigned long long*)(ctx->d_counter + 4);
@@ -395,6 +413,7 @@ extern "C" int bro_batch_sizes(bro_ctx* ctx, const uint8_t* d_in, const uint64_t
     const uint32_t tb = (uint32_t)bro_parse_kernel_block();
     int grid_t = ctx->grid_t;
     if ((uint32_t)grid_t > (n + tb - 1) / tb) grid_t = (int)((n + tb - 1) / tb);
+    p.lanes = 32;
     p.arena = ctx->d_arena_t; p.counter = ctx->d_counter; p.order = ctx->d_order; p.roots = ctx->d_roots;
     e = (cudaError_t)bro_parse_kernel_launch(&p, grid_t, s);
     if (e != cudaSuccess) return bro_fail(ctx, e, "bro_parse_kernel launch");
@@ -416,12 +435,17 @@ static int bro_reserve(bro_ctx* ctx, void** p, size_t* cap, size_t need) {
     return BRO_ST_OK;
 }
 
+// The end-to-end path of a host-language caller.  A batch's output is tens of times its input, so the device -> host copy
+// is what the call costs (26 GB over PCIe for the headline batch); the decode is cut into up to host_chunks slices of
+// streams and the copy of slice k runs on a second stream while slice k + 1 is decoded, so that the link never waits
+// for a kernel.  Slices share the context's scratch: their kernels run one after the other on one stream.
 extern "C" int bro_batch_decode_host(bro_ctx* ctx, const uint8_t* h_in, const uint64_t* h_in_off, uint8_t* h_out,
                                      const uint64_t* h_out_off, uint64_t* h_out_len, int32_t* h_status, uint32_t n) {
     if (!ctx) return BRO_ST_InvalidArgument;
     if (n == 0) return BRO_ST_OK;
     if (!h_in_off || !h_out_off || !h_out_len || !h_status) return BRO_ST_InvalidArgument;
-    BRO_CUDA(ctx, cudaSetDevice(ctx->device));
+    BroDeviceGuard guard(ctx->device);
+    if (!guard.ok) return bro_fail(ctx, cudaErrorInvalidDevice, "cudaSetDevice(context's device)");
     const uint64_t in_lo = h_in_off[0], in_hi = h_in_off[n], out_lo = h_out_off[0], out_hi = h_out_off[n];
     if (in_hi < in_lo || out_hi < out_lo) return BRO_ST_InvalidArgument;
     const size_t in_bytes = (size_t)(in_hi - in_lo), out_bytes = (size_t)(out_hi - out_lo);
@@ -435,22 +459,52 @@ extern "C" int bro_batch_decode_host(bro_ctx* ctx, const uint8_t* h_in, const ui
     uint64_t* d_out_off = d_in_off + (n + 1);
     uint64_t* d_out_len = d_out_off + (n + 1);
     int32_t* d_status = (int32_t*)(d_out_len + n);
-    cudaStream_t s = 0;
-    if (in_bytes) BRO_CUDA(ctx, cudaMemcpyAsync(ctx->d_in, h_in + in_lo, in_bytes, cudaMemcpyHostToDevice, s));
+    cudaStream_t s = ctx->main ? ctx->main : 0;
+    cudaStream_t sc = (ctx->main && ctx->side && ctx->h_fault) ? ctx->side : s;      // copies out
+    // slices: equal shares of the output bytes, at least 32 MB each (a small batch is one slice)
+    uint32_t chunks = sc != s ? (uint32_t)ctx->host_chunks : 1u;
+    while (chunks > 1u && (out_bytes / chunks < ((size_t)32 << 20) || n < 64u * chunks)) chunks--;
+    uint32_t first[17];
+    first[0] = 0;
+    {
+        uint32_t i = 0;
+        for (uint32_t k = 1; k < chunks; k++) {
+            const uint64_t want = out_lo + (uint64_t)((long double)out_bytes * k / chunks);
+            while (i < n && h_out_off[i + 1] <= want) i++;
+            first[k] = i > first[k - 1] ? i : first[k - 1];
+        }
+        first[chunks] = n;
+    }
     BRO_CUDA(ctx, cudaMemcpyAsync(d_in_off, h_in_off, off_bytes, cudaMemcpyHostToDevice, s));
     BRO_CUDA(ctx, cudaMemcpyAsync(d_out_off, h_out_off, off_bytes, cudaMemcpyHostToDevice, s));
-    // offsets are relative to the caller's buffers; rebase the device pointers instead of rewriting the arrays
     const uint64_t reserved_saved = ctx->reserved_in;
-    ctx->reserved_in = in_bytes ? in_bytes : 1;        // known here: no read-back of the offsets
-    st = bro_batch_decode(ctx, ctx->d_in - in_lo, d_in_off, ctx->d_out - out_lo, d_out_off, d_out_len, d_status, n, s);
-    ctx->reserved_in = reserved_saved;
-    if (st) return st;
-    if (out_bytes) BRO_CUDA(ctx, cudaMemcpyAsync(h_out + out_lo, ctx->d_out, out_bytes, cudaMemcpyDeviceToHost, s));
+    uint32_t fault_local = 0;
+    for (uint32_t k = 0; k < chunks; k++) {
+        const uint32_t a = first[k], b = first[k + 1];
+        if (a == b) continue;
+        const uint64_t ci_lo = h_in_off[a], ci_hi = h_in_off[b], co_lo = h_out_off[a], co_hi = h_out_off[b];
+        if (ci_hi < ci_lo || co_hi < co_lo) { ctx->reserved_in = reserved_saved; return BRO_ST_InvalidArgument; }
+        if (ci_hi > ci_lo) BRO_CUDA(ctx, cudaMemcpyAsync(ctx->d_in + (ci_lo - in_lo), h_in + ci_lo, (size_t)(ci_hi - ci_lo), cudaMemcpyHostToDevice, s));
+        // offsets are relative to the caller's buffers; rebase the device pointers instead of rewriting the arrays
+        ctx->reserved_in = ci_hi > ci_lo ? ci_hi - ci_lo : 1;          // known here: no read-back of the offsets
+        st = bro_batch_decode(ctx, ctx->d_in - in_lo, d_in_off + a, ctx->d_out - out_lo, d_out_off + a, d_out_len + a, d_status + a, b - a, s);
+        ctx->reserved_in = reserved_saved;
+        if (st) return st;
+        if (sc != s) {
+            BRO_CUDA(ctx, cudaMemcpyAsync(ctx->h_fault + k, ctx->d_counter + 11, sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+            BRO_CUDA(ctx, cudaEventRecord(ctx->ev_fork, s));             // (one event: a later record only moves the wait point forward)
+            BRO_CUDA(ctx, cudaStreamWaitEvent(sc, ctx->ev_fork, 0));
+        } else {
+            BRO_CUDA(ctx, cudaMemcpyAsync(&fault_local, ctx->d_counter + 11, sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+        }
+        if (co_hi > co_lo) BRO_CUDA(ctx, cudaMemcpyAsync(h_out + co_lo, ctx->d_out + (co_lo - out_lo), (size_t)(co_hi - co_lo), cudaMemcpyDeviceToHost, sc));
+    }
     BRO_CUDA(ctx, cudaMemcpyAsync(h_out_len, d_out_len, (size_t)n * sizeof(uint64_t), cudaMemcpyDeviceToHost, s));
     BRO_CUDA(ctx, cudaMemcpyAsync(h_status, d_status, (size_t)n * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
-    uint32_t fault = 0;
-    BRO_CUDA(ctx, cudaMemcpyAsync(&fault, ctx->d_counter + 11, sizeof(fault), cudaMemcpyDeviceToHost, s));
     BRO_CUDA(ctx, cudaStreamSynchronize(s));
+    if (sc != s) BRO_CUDA(ctx, cudaStreamSynchronize(sc));
+    uint32_t fault = fault_local;
+    if (sc != s) for (uint32_t k = 0; k < chunks; k++) if (first[k] != first[k + 1]) fault |= ctx->h_fault[k];
     if (fault) {
         // the copy kernel gave up waiting for the parse kernel: statuses say OK for streams whose copies were never made
         snprintf(ctx->err, sizeof(ctx->err), "copy kernel watchdog: a stream of the batch was never announced by the parse kernel");

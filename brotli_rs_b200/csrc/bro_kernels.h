@@ -40,6 +40,8 @@ struct BroLaunch {
     uint32_t* done_tail;
     uint16_t* roots;          // parse kernel: per-thread decode tables (bro_parse.h) when they live in HBM / L2
     unsigned long long* copy_stats;   // [0] bytes moved by records, [1] records executed (this batch)
+    uint32_t lanes;           // parse kernel: streams a warp holds at a time (32 for a full batch; fewer when the batch is smaller
+                              // than the resident lanes, so that it spreads over all SMs and a warp's steps serve fewer, busier lanes)
     uint32_t* fault;          // copy kernel: set to 1 when its watchdog fired (a completion-queue slot was never filled): the
                               // batch is then reported as BRO_ST_CudaError instead of leaving streams marked OK without their copies
     long long watchdog;       // copy kernel: cycles to wait for one completion-queue slot

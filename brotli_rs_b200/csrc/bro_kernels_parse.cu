@@ -82,14 +82,14 @@ __global__ void __launch_bounds__(BRO_PARSE_BLOCK, BRO_PARSE_MIN_BLOCKS) bro_par
                     __threadfence();
                     if (p.done_q) ((volatile uint32_t*)p.done_q)[atomicAdd(p.done_tail, 1u)] = stream;
                 }
-                const uint32_t idle = __ballot_sync(0xffffffffu, ps.kind == BRO_K_DONE);
+                const uint32_t idle = __ballot_sync(0xffffffffu, ps.kind == BRO_K_DONE) & (p.lanes >= 32u ? 0xffffffffu : (1u << p.lanes) - 1u);
                 if (idle != 0u && !exhausted) {
                     const int leader = __ffs(idle) - 1;
                     uint32_t base = 0;
                     if ((int)lane == leader) base = atomicAdd(p.counter, (uint32_t)__popc(idle));
                     base = __shfl_sync(0xffffffffu, base, leader);
                     if (base + (uint32_t)__popc(idle) >= p.n) exhausted = true;
-                    if (ps.kind == BRO_K_DONE) {
+                    if (ps.kind == BRO_K_DONE && ((idle >> lane) & 1u)) {
                         const uint32_t k = base + (uint32_t)__popc(idle & ((1u << lane) - 1u));
                         if (k < p.n) {
                             stream = p.order ? p.order[k] : k;

@@ -64,3 +64,22 @@ def test_sharding_balances_bytes():
         assert (allidx == np.arange(5200)).all()
         tot = np.array([out_lens[s].sum() + in_lens[s].sum() for s in shards], dtype=np.float64)
         assert tot.max() / tot.mean() < 1.02
+
+
+def test_mg_partition_balances_contiguous_ranges():
+    """bro_mg_partition (the split bro_mg_decode_host uses): contiguous, complete, balanced in compressed + slot bytes;
+    host arithmetic only, so it runs without a GPU."""
+    import numpy as np
+    from brotli_rs_b200 import mg_partition
+    rng = np.random.default_rng(3)
+    for n in (1, 7, 5000):
+        in_lens = rng.integers(1, 5000, n)
+        caps = in_lens * rng.integers(1, 70, n)
+        in_off = np.concatenate([[11], 11 + np.cumsum(in_lens)]).astype(np.uint64)       # offsets need not start at 0
+        out_off = np.concatenate([[5], 5 + np.cumsum(caps)]).astype(np.uint64)
+        for g in (1, 2, 3, 8):
+            first = mg_partition(in_off, out_off, g)
+            assert first[0] == 0 and first[-1] == n and (np.diff(first.astype(np.int64)) >= 0).all()
+            if n >= 1000:
+                work = np.array([float(in_lens[first[k]:first[k + 1]].sum() + caps[first[k]:first[k + 1]].sum()) for k in range(g)])
+                assert work.max() / work.mean() < 1.05

@@ -314,10 +314,12 @@ def test_parse_handover_is_retried_by_warp_kernel(dec):
         assert st == 0 and out == r, (i, st)
 
 
-def test_auto_mode_launch_counts():
+def test_auto_mode_launch_counts(monkeypatch):
     """default mode decodes a small batch with ONE launch of the warp kernel and a large one by the two-phase path:
-    3 ordering kernels, the parse kernel, the copy kernel and the fused kernel's retry pass"""
+    3 ordering kernels, the parse kernel, the copy kernel and the fused kernel's retry pass (per slice of the host call:
+    one slice here)"""
     from brotli_rs_b200 import BatchDecoder
+    monkeypatch.setenv("BRO_B200_HOST_CHUNKS", "1")
     files = [f for f in corpus_files() if f[2] is not None and len(f[1]) < 2000]
     streams = [c for _, c, _ in files] * 100
     exps = [e for _, _, e in files] * 100
@@ -367,6 +369,75 @@ def test_device_path_without_reservation():
         for i, r in enumerate(raws):
             assert out[int(out_off[i]): int(out_off[i]) + len(r)].tobytes() == r, (bound, i)
     d.close()
+
+
+def test_dictionary_transform_kats_and_quirk_vectors():
+    """GPU known answers for the static dictionary (reference src/lib.rs:1506-1540, src/transformation/mod.rs:84-209):
+    every transform id 0..120 x every word length 4..24 x word indices {0, last, random} as one-command streams
+    (tests/dictgen.py), plus the appendix D vectors for Q1 / Q3 / Q4 -- on BOTH decode paths (the
+    fused kernel's 32-lane bro_dict_word, phase one's per-thread emit) in BOTH quirk modes (bro_ctx_set_quirks), against
+    the oracle."""
+    import dictgen
+    from brotli_rs_b200 import BatchDecoder
+    appendix_d = [bytes.fromhex(hx) for hx in ("82000000445008122001", "02000000445008122b0106", "02000000445008122a0102",
+                                               "02000000445008122a0108", "e200000044501812a6fb01", "4c8000" + "00" * 257 + "03")]
+    for quirks in (0, 1):
+        kats = dictgen.kat_batch(oracle, quirks, indices_per_length=4)
+        streams = [k[1] for k in kats] + appendix_d
+        want = [(k[2], k[3]) for k in kats] + [oracle.decode(s, quirks) for s in appendix_d]
+        assert {w[0] for w in want} >= ({0, 24, 102} if quirks == 0 else {0, 24})
+        for mode in (BatchDecoder.MODE_WARP, BatchDecoder.MODE_TWOPHASE):
+            d = BatchDecoder(0, quirks=quirks, mode=mode)
+            res = d.decode_streams(streams, [64] * len(streams))
+            d.close()
+            for i, ((st, out), (wst, wout)) in enumerate(zip(res, want)):
+                assert st == wst and (wst != 0 or out == wout), (quirks, mode, kats[i][0] if i < len(kats) else "appendix D %d" % (i - len(kats)), st, wst)
+
+
+def test_default_context_readers_are_cheap():
+    """A reader without a context -- what a drop-in Decompressor::new(r) creates, dozens of them in the reference's own
+    test-suite -- uses the process-wide default context: 40 readers must not take 40 x (or even 1 x) the full-grid arenas."""
+    import torch
+    from brotli_rs_b200 import Decompressor
+    files = [(c, e) for _, c, e in corpus_files() if e is not None and len(e) < 200000][:10]
+    torch.cuda.synchronize()
+    free0, _ = torch.cuda.mem_get_info(0)
+    readers = []
+    for k in range(40):
+        c, e = files[k % len(files)]
+        r = Decompressor(c, streaming=(k % 2 == 1))
+        assert r.read() == e
+        readers.append(r)
+    torch.cuda.synchronize()
+    free1, _ = torch.cuda.mem_get_info(0)
+    assert free0 - free1 < (512 << 20), (free0 - free1) >> 20
+    for r in readers:
+        r.close()
+
+
+def test_mg_decode_host_matches_oracle():
+    """bro_mg_* (one batch over every GPU of the box from one process): same results as the oracle, whatever the number
+    of devices; the partition is contiguous and complete."""
+    import torch
+    from brotli_rs_b200 import MultiGpuDecoder, mg_partition
+    from brotli_rs_b200.batch import pack_streams, slot_offsets
+    files = corpus_files()
+    streams = [c for _, c, _ in files] * 6 + list(fuzzgen.mutations([c for _, c, _ in files], seed=77, count=200))
+    want = [oracle.decode(s) for s in streams]
+    caps = [len(o) if st == 0 else 4096 for st, o in want]
+    in_buf, in_off = pack_streams(streams)
+    out_off = slot_offsets(caps)
+    mg = MultiGpuDecoder(0)
+    assert mg.device_count == torch.cuda.device_count()
+    first = mg_partition(in_off, out_off, mg.device_count)
+    assert first[0] == 0 and first[-1] == len(streams)
+    for _ in range(2):
+        out, out_len, status = mg.decode_host(in_buf, in_off, out_off)
+        for i, (st, o) in enumerate(want):
+            assert int(status[i]) == st, (i, st, int(status[i]))
+            if st == 0:
+                assert out[int(out_off[i]): int(out_off[i]) + int(out_len[i])].tobytes() == o, i
+    mg.close()
 
 
 def test_copy_kernel_watchdog_is_loud(monkeypatch):

@@ -65,6 +65,22 @@ def test_quirk_vectors():
             assert st1 == st and (st != 0 or out1 == out), (hx, quirks, st, st1)
 
 
+def test_dictionary_transform_kats():
+    """every transform id x every word length x a few word indices as one-command streams (tests/dictgen.py), both quirk
+    modes: the fused loops' bro_dict_word and phase one's bro_parse_dict_* against the oracle (reference
+    src/transformation/mod.rs:84-209, src/lib.rs:1506-1540)"""
+    import dictgen
+    seen = set()
+    for quirks in (0, 1):
+        for label, s, st, out in dictgen.kat_batch(oracle, quirks, indices_per_length=2):
+            st1, out1 = hostsim.decode(s, cap=64, quirks=quirks)
+            assert st1 == st and (st != 0 or out1 == out), (label, quirks, st, st1)
+            st2, out2, _, _ = hostsim.parse_decode(s, cap=64, quirks=quirks)
+            assert st2 == st and (st != 0 or out2 == out), (label, quirks, st, st2)
+            seen.add(st)
+    assert seen == {0, 24, 102}
+
+
 # ---- the two-phase path: phase one (bro_parse.h, the parse kernel's per-lane code) + a byte loop over its copy records ----
 
 def _parse_check(stream, cap, want_st, want_out, label, mis=None):
