@@ -423,10 +423,13 @@ def test_mg_decode_host_matches_oracle():
     from brotli_rs_b200.batch import pack_streams, slot_offsets
     files = corpus_files()
     streams = [c for _, c, _ in files] * 6 + list(fuzzgen.mutations([c for _, c, _ in files], seed=77, count=200))
-    want = [oracle.decode(s) for s in streams]
-    caps = [len(o) if st == 0 else 4096 for st, o in want]
+    free = [oracle.decode(s) for s in streams]
+    caps = [len(o) if st == 0 else 4096 for st, o in free]
     in_buf, in_off = pack_streams(streams)
     out_off = slot_offsets(caps)
+    # the oracle with the same slots (a stream that outgrows its slot before it fails is OUTPUT_TOO_SMALL on both sides)
+    o_out, o_len, o_st = oracle.decode_batch(in_buf, in_off, out_off)
+    want = [(int(o_st[i]), o_out[int(out_off[i]): int(out_off[i]) + int(o_len[i])].tobytes()) for i in range(len(streams))]
     mg = MultiGpuDecoder(0)
     assert mg.device_count == torch.cuda.device_count()
     first = mg_partition(in_off, out_off, mg.device_count)
