@@ -129,7 +129,7 @@ class BatchDecoder:
 
     def decode_resume_device(self, d_in, d_in_off, d_out, d_out_off, d_resume, d_out_len=None, d_status=None, stream=None):
         """bro_batch_decode_resume on torch CUDA tensors: decode from and to the resume points in d_resume (uint8
-        tensor of n * 40 bytes, RESUME_DTYPE records; zeros = start of stream).  Returns (d_out_len, d_status)."""
+        tensor of n * 48 bytes, RESUME_DTYPE records; zeros = start of stream).  Returns (d_out_len, d_status)."""
         import torch
         n = d_in_off.numel() - 1
         assert d_out_off.numel() == n + 1 and d_resume.numel() * d_resume.element_size() == n * self.RESUME_DTYPE.itemsize

@@ -83,3 +83,24 @@ def test_mg_partition_balances_contiguous_ranges():
             if n >= 1000:
                 work = np.array([float(in_lens[first[k]:first[k + 1]].sum() + caps[first[k]:first[k + 1]].sum()) for k in range(g)])
                 assert work.max() / work.mean() < 1.05
+
+
+def test_bro_resume_layout_matches_the_shim(tmp_path):
+    """bro_resume crosses the ABI by value (arrays of it in device memory): its C layout must be what the Rust shim in
+    INTEGRATION.md and BatchDecoder.RESUME_DTYPE declare -- 48 bytes, the offsets below."""
+    import subprocess
+    import numpy as np
+    from brotli_rs_b200 import BatchDecoder
+    src = tmp_path / "layout.c"
+    src.write_text('#include <stddef.h>\n#include <stdio.h>\n#include "brotli_b200.h"\n'
+                   'int main(void) { printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu\\n", sizeof(bro_resume), offsetof(bro_resume, in_bits), '
+                   'offsetof(bro_resume, pos), offsetof(bro_resume, window), offsetof(bro_resume, dist), offsetof(bro_resume, p1), '
+                   'offsetof(bro_resume, p2), offsetof(bro_resume, flags), offsetof(bro_resume, reserved)); return 0; }\n')
+    exe = tmp_path / "layout"
+    subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)])
+    got = [int(x) for x in subprocess.check_output([str(exe)]).split()]
+    assert got == [48, 0, 8, 12, 16, 32, 36, 40, 44]
+    dt = BatchDecoder.RESUME_DTYPE
+    assert dt.itemsize == 48 and [dt.fields[k][1] for k in ("in_bits", "pos", "window", "dist", "p1", "p2", "flags", "reserved")] == got[1:]
+    shim = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    assert "pub struct bro_resume" in shim and "pub in_bits: u64" in shim and "pub dist: [u32; 4]" in shim
