@@ -51,6 +51,7 @@ def parse_args():
                     help="decode path (bro_ctx_set_mode); auto = the library's default policy")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-strong", action="store_true", help="N > 1: skip the strong-scaling record")
+    ap.add_argument("--no-exchange", action="store_true", help="N > 1: skip the scatter / gather measurement")
     ap.add_argument("--no-write-roof", action="store_true", help="skip the fill (write-only bandwidth) measurement")
     ap.add_argument("--extra-workloads", action=argparse.BooleanOptionalAction, default=None,
                     help="also run the other BASELINE configurations, a few steps each (default: on for the default run)")
@@ -342,13 +343,15 @@ class Batch:
             a = self.d_out[int(self.out_off[k]): int(self.out_off[k]) + int(self.ulen_out[u])]
             assert torch.equal(a, d_raw[int(roff[u]): int(roff[u + 1])]), "GPU output differs from the expected bytes (stream %d)" % k
 
-    def timed(self, steps, warmup, sampler=None):
-        """-> (total ms of `steps` launches on this rank, per-step ms, launches): CUDA events on the launching stream"""
+    def timed(self, steps, warmup, sampler=None, collective=True):
+        """-> (total ms of `steps` launches on this rank, per-step ms, launches): CUDA events on the launching stream.
+        collective=False: a measurement of this rank alone (no barrier: the other ranks are not in it)"""
         h, torch = self.h, self.h.torch
+        sync = h.barrier if collective else torch.cuda.synchronize
         for _ in range(warmup):
             self.decode()
         ev = [torch.cuda.Event(enable_timing=True) for _ in range(steps + 1)]
-        h.barrier()
+        sync()
         if sampler:
             sampler.start()
         launches0 = h.dec.launch_count
@@ -356,7 +359,7 @@ class Batch:
         for k in range(steps):
             self.decode()
             ev[k + 1].record()
-        h.barrier()
+        sync()
         assert bool((self.d_st == self.want_st).all())
         return ev[0].elapsed_time(ev[-1]), [ev[k].elapsed_time(ev[k + 1]) for k in range(steps)], h.dec.launch_count - launches0
 
@@ -379,7 +382,7 @@ def quick_workload(h, name, steps, warmup):
     wl = build_workload(name, n_streams)
     b = Batch(h, wl, np.arange(n_streams))
     b.parity_gate()
-    total_ms, step_ms, _ = b.timed(steps, warmup)
+    total_ms, step_ms, _ = b.timed(steps, warmup, collective=False)      # rank 0 alone runs the side measurements
     kms, stats = b.kernel_times(min(steps, 3))
     peak, _ = measured_peaks()
     ms = total_ms / steps
@@ -510,6 +513,63 @@ def main():
         del bs
         torch.cuda.empty_cache()
 
+    # ---- the one exchange SURVEY.md 8(e) names: the compressed batch is resident on rank 0 and the decoded streams are wanted
+    # back there.  scatter (NCCL point-to-point, one message per peer) -> decode -> gather, timed separately ----
+    exchange = None
+    if world > 1 and args.scaling == "weak" and not args.no_exchange:
+        from brotli_rs_b200.batch import slot_offsets
+        from brotli_rs_b200.shard import gather_outputs, scatter_batch
+        wl1 = build_workload(args.workload, per_rank)
+        g1 = wl1["gidx"]
+        buf = lens1 = caps1 = None
+        if rank == 0:
+            full = Batch(h, wl1, np.arange(per_rank))
+            buf, lens1, caps1 = full.d_in[: int(full.in_off[-1])], ulen_in[g1], ucap[g1]
+
+        def wall(fn):
+            h.barrier()
+            t0 = time.perf_counter()
+            r = fn()
+            torch.cuda.synchronize()
+            dt = time.perf_counter() - t0
+            return r, h.max_over_ranks(dt)
+
+        best = {"scatter": 1e9, "decode": 1e9, "gather": 1e9}
+        for _ in range(3):
+            (mine_x, my_buf, my_lens, my_caps), t_sc = wall(lambda: scatter_batch(buf, lens1, caps1, src=0, device=dev))
+            x_in_off = torch.from_numpy(np.concatenate([[0], np.cumsum(my_lens)]).astype(np.int64)).to(dev)
+            x_out_off_h = slot_offsets(my_caps).astype(np.int64)
+            x_out_off = torch.from_numpy(x_out_off_h).to(dev)
+            x_in = torch.zeros(my_buf.numel() + 16, dtype=torch.uint8, device=dev)
+            x_in[: my_buf.numel()] = my_buf
+            x_out = torch.empty(int(x_out_off_h[-1]), dtype=torch.uint8, device=dev)
+            x_len = torch.empty(len(mine_x), dtype=torch.int64, device=dev)
+            x_st = torch.empty(len(mine_x), dtype=torch.int32, device=dev)
+            _, t_de = wall(lambda: dec.decode_device(x_in, x_in_off, x_out, x_out_off, x_len, x_st))
+            res, t_ga = wall(lambda: gather_outputs(mine_x, x_out, x_out_off_h, x_len, x_st, per_rank, dst=0))
+            if rank == 0:
+                st_all, len_all, rank_of, slot_off, buffers = res
+                assert (st_all == wl1["status"][g1]).all() and int(len_all.sum()) == int(bt.ulen_out[g1].sum())
+                k = int(np.random.default_rng(1).integers(0, per_rank))
+                u = int(g1[k])
+                assert buffers[rank_of[k]][int(slot_off[k]): int(slot_off[k]) + int(len_all[k])].cpu().numpy().tobytes() == wl1["raws"][u]
+                del buffers, res
+            best = {"scatter": min(best["scatter"], t_sc), "decode": min(best["decode"], t_de), "gather": min(best["gather"], t_ga)}
+            del x_out, x_in, my_buf
+            torch.cuda.empty_cache()
+        comp1 = float(ulen_in[g1].sum())
+        out1 = float(slot_offsets(ucap[g1])[-1])
+        exchange = {"streams": per_rank, "scatter_ms": 1e3 * best["scatter"], "decode_ms": 1e3 * best["decode"], "gather_ms": 1e3 * best["gather"],
+                    "scatter_bytes_sent_by_rank0": comp1 * (world - 1) / world, "gather_bytes_received_by_rank0": out1 * (world - 1) / world,
+                    "scatter_gbs_out_of_rank0": comp1 * (world - 1) / world / best["scatter"] / 1e9,
+                    "gather_gbs_into_rank0": out1 * (world - 1) / world / best["gather"] / 1e9,
+                    "gather_gbs_per_peer_link": out1 / world / best["gather"] / 1e9,
+                    "how": "wall clock around barrier + synchronize, max over ranks, best of 3; torch.distributed batch_isend_irecv over NCCL "
+                           "(one message per peer); the scatter includes the per-shard gather of streams on rank 0 and the 16 B / stream size broadcast"}
+        if rank == 0:
+            del full
+        torch.cuda.empty_cache()
+
     # ---- end to end through the C ABI with pinned host buffers ----
     e2e = None
     if not args.no_e2e:
@@ -585,6 +645,8 @@ def main():
         }
         if strong is not None:
             line["strong"] = strong
+        if exchange is not None:
+            line["exchange"] = exchange
         if extra is not None:
             line["extra_workloads"] = extra
         print(json.dumps(line))

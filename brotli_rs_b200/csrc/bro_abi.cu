@@ -24,7 +24,8 @@ extern "C" const uint8_t bro_dictionary_blob[];   // csrc/dict_blob.c
 struct bro_ctx {
     int device;
     int num_sms;
-    int grid;                 // warp kernel: persistent CTAs
+    int grid;                 // warp kernel, throughput build: persistent CTAs
+    int grid_lat;             // warp kernel, latency build (fewer CTAs per SM, more registers)
     uint32_t num_warps;
     uint16_t* d_arena;        // warp kernel: worst-case arena per warp, for the first `arena_warps` warps of the grid
     uint32_t arena_warps;     // (grow-only, sized by the grids actually launched: a one-stream reader needs 8 warps = 10 MB,
@@ -83,11 +84,12 @@ extern "C" int bro_ctx_create(bro_ctx** out, int device) {
     cudaDeviceProp prop;
     if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) { free(ctx); return BRO_ST_CudaError; }
     ctx->num_sms = prop.multiProcessorCount;
-    int per_sm = 0, per_sm_t = 0, per_sm_c = 0;
-    if (bro_warp_kernel_occupancy(&per_sm) != 0 || per_sm < 1 ||
+    int per_sm2[2] = {0, 0}, per_sm = 0, per_sm_t = 0, per_sm_c = 0;
+    if (bro_warp_kernel_occupancy(per_sm2) != 0 || (per_sm = per_sm2[0]) < 1 || per_sm2[1] < 1 ||
         bro_parse_kernel_occupancy(&per_sm_t) != 0 || per_sm_t < 1 ||
         bro_copy_kernel_occupancy(&per_sm_c) != 0 || per_sm_c < 1) { free(ctx); return BRO_ST_CudaError; }
     ctx->grid = ctx->num_sms * per_sm;
+    ctx->grid_lat = ctx->num_sms * per_sm2[1];
     ctx->num_warps = (uint32_t)ctx->grid * (uint32_t)bro_warp_kernel_warps_per_cta();
     // The parse kernel is bound by the latency of its table look-ups, i.e. by how many streams' tables stay in L2:
     // BRO_B200_PARSE_BLOCKS caps its resident CTAs per SM (tuning knob).
@@ -117,7 +119,7 @@ extern "C" int bro_ctx_create(bro_ctx** out, int device) {
     // then copies at memory speed) has the higher throughput.  It pays once the fused kernel would need several waves
     // of its resident warps; measured on B200 with the headline streams (profiles/r01_kernel_variants.md) the break-even
     // is near 4 waves.
-    ctx->twophase_threshold = 5u * ctx->num_warps;
+    ctx->twophase_threshold = 160u * (uint32_t)ctx->num_sms;      // 23,680 streams on a B200
     const char* env = getenv("BRO_B200_MODE");
     if (env && !strcmp(env, "warp")) ctx->mode = BRO_MODE_WARP;
     if (env && (!strcmp(env, "twophase") || !strcmp(env, "thread"))) ctx->mode = BRO_MODE_TWOPHASE;
@@ -256,9 +258,12 @@ extern "C" int bro_batch_decode(bro_ctx* ctx, const uint8_t* d_in, const uint64_
     p.dict = ctx->d_dict; p.quirk_spec = ctx->quirks;
     p.order = NULL; p.retry_count = ctx->d_counter + 2; p.retry_mode = 0;
     const uint32_t wpc = (uint32_t)bro_warp_kernel_warps_per_cta();
-    int grid_w = ctx->grid;
-    if ((uint32_t)grid_w > (n + wpc - 1) / wpc) grid_w = (int)((n + wpc - 1) / wpc);
     const bool two_phase = ctx->mode == BRO_MODE_TWOPHASE || (ctx->mode == BRO_MODE_AUTO && n >= ctx->twophase_threshold);
+    // the latency build of the fused kernel whenever one stream's decode time is what the call costs: at most a wave of
+    // streams, and behind the two-phase kernels (the retry pass; a batch the gate found bound by its longest stream)
+    const int latency = (two_phase || n <= (uint32_t)ctx->grid_lat * wpc) ? 1 : 0;
+    int grid_w = latency ? ctx->grid_lat : ctx->grid;
+    if ((uint32_t)grid_w > (n + wpc - 1) / wpc) grid_w = (int)((n + wpc - 1) / wpc);
     { int st_a = bro_ensure_arena(ctx, (uint32_t)grid_w * wpc); if (st_a) return st_a; }       // before anything of this batch is in flight
     cudaError_t e;
     if (two_phase) {
@@ -343,7 +348,7 @@ extern "C" int bro_batch_decode(bro_ctx* ctx, const uint8_t* d_in, const uint64_
     p.arena = ctx->d_arena; p.counter = ctx->d_counter + 1;
     p.order = two_phase ? ctx->d_order : NULL;       // size-class order of the batch (largest first) when it was computed
     if (ctx->timing) BRO_CUDA(ctx, cudaEventRecord(ctx->ev[3], s));
-    e = (cudaError_t)bro_warp_kernel_launch(&p, grid_w, s);
+    e = (cudaError_t)bro_warp_kernel_launch(&p, grid_w, latency, s);
     if (e != cudaSuccess) return bro_fail(ctx, e, "bro_decode_warp_kernel launch");
     ctx->launches += 1;
     if (ctx->timing) {

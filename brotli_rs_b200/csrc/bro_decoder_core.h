@@ -144,6 +144,12 @@ BRO_FN uint32_t bro_funnel_r(uint32_t lo, uint32_t hi, unsigned sh) { return __f
 // tables; larger meta-blocks fall back to the warp kernel.  The thread's BroScratch sits at its start.
 #define BRO_THREAD_ARENA_U16 32768u
 
+// capacities of the general command loop's on-chip tables (bro_stage_hot)
+#define BRO_HOT_CMAP_L 1024u    // literal context map: up to 16 block types x 64 contexts
+#define BRO_HOT_CMAP_D 256u     // distance context map: up to 64 block types x 4 contexts
+#define BRO_HOT_MODES 64u       // context modes of up to 64 literal block types
+#define BRO_HOT_LIT_U16 1536u   // narrow roots of the literal codes: 6 codes x 8 bits, 12 x 7, 24 x 6 or 48 x 5
+
 #if defined(BRO_SERIAL)
 // ------------------------------------------------------------------------------------------------------
 // One decoder per THREAD: its on-chip storage is a block of BRO_TL_BYTES of shared memory, interleaved WORD BY WORD
@@ -230,10 +236,13 @@ struct BroScratch {
     BroTlArray<uint8_t, BRO_TL_CL> cl;         // lengths of the code-length code
     BroTlArray<uint8_t, BRO_TL_WORD> word;     // dictionary word staging (<= 24 + 13 bytes)
     uint16_t *root_lit, *root_cmd, *root_dist; // 256-entry root tables of the fused loops (host simulation only)
+    uint8_t *hot_cmap_l, *hot_cmap_d, *hot_modes;   // the general loop's on-chip tables (BRO_HOT_*; host simulation only)
+    uint16_t* hot_lit;
 };
 BRO_FN void bro_scratch_bind(BroScratch& sc, BroTl t) {
     sc.t = t; sc.mtf.t = t; sc.syms.t = t; sc.cnt.t = t; sc.limit.t = t; sc.base.t = t; sc.clc.t = t; sc.cl.t = t; sc.word.t = t;
     sc.root_lit = sc.root_cmd = sc.root_dist = 0;
+    sc.hot_cmap_l = sc.hot_cmap_d = sc.hot_modes = 0; sc.hot_lit = 0;
 }
 // Out-of-line functions get the block's address by value and bind their own view of it (registers), and they work on
 // a register copy of the bit window: a struct passed by reference lives in LOCAL memory for its whole life, and with
@@ -277,6 +286,13 @@ struct BroScratch {
     uint16_t root_lit[256];
     uint16_t root_cmd[256];
     uint16_t root_dist[256];
+    // a meta-block WITH context modelling (several literal / distance codes chosen per symbol, block switches): what its
+    // command loop looks up per symbol -- context modes, both context maps, and narrow roots of all its literal codes
+    // (of its insert&copy and distance codes in root_cmd / root_dist) -- as far as it fits (bro_stage_hot)
+    uint8_t hot_cmap_l[BRO_HOT_CMAP_L];
+    uint8_t hot_cmap_d[BRO_HOT_CMAP_D];
+    uint8_t hot_modes[BRO_HOT_MODES];
+    uint16_t hot_lit[BRO_HOT_LIT_U16];
 };
 BRO_FN uint32_t bro_lens_get(const BroScratch& sc, uint32_t i) { return sc.lens[i]; }
 BRO_FN void bro_lens_put(BroScratch& sc, uint32_t i, uint32_t v) { sc.lens[i] = (uint8_t)v; }
@@ -1657,6 +1673,9 @@ BRO_FN int bro_metablock_tables(BroDec& d, BroMbInfo& mb) {
     }
 #undef BRO_TRY
     bro_syncwarp();
+#if defined(BRO_HOSTSIM) && defined(BRO_MB_STAT)
+    BRO_MB_STAT(ntl, ntd, cat[0].nbl, cat[1].nbl, cat[2].nbl, st);
+#endif
     mb.npostfix = npostfix; mb.ndirect = ndirect; mb.ntl = ntl; mb.ntd = ntd;
     mb.o_modes = o_modes; mb.o_cmap_l = o_cmap_l; mb.o_cmap_d = o_cmap_d;
     mb.o_lit = o_lit; mb.o_cmd = o_cmd; mb.o_dist = o_dist; mb.dist_stride = dist_stride;
@@ -1665,20 +1684,53 @@ BRO_FN int bro_metablock_tables(BroDec& d, BroMbInfo& mb) {
 }
 
 #if !defined(BRO_PARSE)
+// One symbol through a narrow on-chip copy of a table's root (`hot`: 1 << rb entries, an entry is a direct hit -- symbol |
+// len << 10, len <= rb -- or 1 = settle it in the table T itself).  Same results as bro_decode_sym on T.
+BRO_FN int bro_decode_sym_hot(BroBits& s, const uint16_t* hot, uint32_t rb, const uint16_t* T, uint32_t& sym) {
+    bro_refill(s);
+    const uint32_t peek = bro_peek(s);
+    uint32_t e = hot[peek & ((1u << rb) - 1u)];
+    uint32_t len = e >> 10;
+    if (len == 0u) {
+        e = T[peek & (BRO_ROOT_SIZE - 1u)];
+        len = e >> 10;
+        if (len == 0u) {
+            const uint32_t r = bro_sym_slow(T, peek, e, bro_avail(s));
+            bro_consume(s, (r >> 16) & 0xffu);
+            sym = r & 0xffffu;
+            return (int)(r >> 24);
+        }
+    }
+    if (len > bro_avail(s)) return BRO_SYM_EOF;
+    bro_consume(s, len);
+    sym = e & 0x3ffu;
+    return BRO_SYM_OK;
+}
+
+// What the general loop keeps on chip for a meta-block with several codes of a kind
+struct BroHot {
+    uint32_t rb_lit, rb_cmd, rb_dist;    // root bits of the on-chip copies (0 = none: look the tables up in the arena)
+    bool cmap_l, cmap_d, modes;          // the context maps / modes fit their on-chip copies
+};
+
 // The general command loop (src/lib.rs:2003-2141): any number of codes, block switches, literal context modelling.
-BRO_FN int bro_commands_general(BroDec& d, BroScratch& sc, uint32_t mlen, BroMbInfo& mb) {
+// Per literal the reference looks up the context mode of the block type, the context map, and then the code the map
+// names (src/lib.rs:1317-1345).  In round 1 all three were reads of the warp's arena in HBM / L2, one after the other:
+// ~1,400 cycles per symbol on a single warp, which is what bounds a long context-modelled stream (and any batch that
+// holds one).  They are shared-memory look-ups now whenever the meta-block's tables fit (bro_stage_hot).
+BRO_FN int bro_commands_general(BroDec& d, BroScratch& sc, uint32_t mlen, BroMbInfo& mb, const BroHot& hot) {
     const unsigned lane = bro_lane();
     uint16_t* A = d.arena;
     BroBlockCat (&cat)[3] = mb.cat;
     int st;
     const uint32_t npostfix = mb.npostfix, ndirect = mb.ndirect, ntl = mb.ntl, ntd = mb.ntd, dist_stride = mb.dist_stride;
-    const uint8_t* modes = (const uint8_t*)(A + mb.o_modes);
-    const uint8_t* cmap_l = (const uint8_t*)(A + mb.o_cmap_l);
-    const uint8_t* cmap_d = (const uint8_t*)(A + mb.o_cmap_d);
+    const uint8_t* modes = hot.modes ? (const uint8_t*)sc.hot_modes : (const uint8_t*)(A + mb.o_modes);
+    const uint8_t* cmap_l = hot.cmap_l ? (const uint8_t*)sc.hot_cmap_l : (const uint8_t*)(A + mb.o_cmap_l);
+    const uint8_t* cmap_d = hot.cmap_d ? (const uint8_t*)sc.hot_cmap_d : (const uint8_t*)(A + mb.o_cmap_d);
     const uint16_t* const T_lit = A + mb.o_lit;
     const uint16_t* const T_cmd = A + mb.o_cmd;
     const uint16_t* const T_dist = A + mb.o_dist;
-    // one code of a kind: its root table is on chip (bro_decode_compressed_metablock)
+    // one code of a kind: its 8-bit root table is on chip (bro_stage_roots); several: narrow roots of all of them (bro_stage_hot)
     const bool one_lit = ntl == 1u, one_cmd = cat[1].nbl == 1u, one_dist = ntd == 1u;
     const bool lit_simple = one_lit && cat[0].nbl == 1u;   // no context modelling, no literal block switches
     const uint32_t mb_begin = d.pos;   // meta_block.count_output == d.pos - mb_begin
@@ -1689,6 +1741,8 @@ BRO_FN int bro_commands_general(BroDec& d, BroScratch& sc, uint32_t mlen, BroMbI
         if ((st = bro_step_block(d, cat[1]))) return st;
         int r;
         if (one_cmd) r = bro_decode_sym2(d.in, sc.root_cmd, T_cmd, sym);
+        else if (hot.rb_cmd) r = bro_decode_sym_hot(d.in, sc.root_cmd + (cat[1].btype << hot.rb_cmd), hot.rb_cmd,
+                                                    T_cmd + cat[1].btype * BRO_TREE_U16(BRO_ALPHA_CMD), sym);
         else r = bro_decode_sym(d.in, T_cmd + cat[1].btype * BRO_TREE_U16(BRO_ALPHA_CMD), sym);
         if (r == BRO_SYM_HOLE) return BRO_ST_ParseErrorInsertAndCopyLength;
         if (r == BRO_SYM_EOF) return BRO_ST_UnexpectedEOF;
@@ -1719,25 +1773,39 @@ BRO_FN int bro_commands_general(BroDec& d, BroScratch& sc, uint32_t mlen, BroMbI
             uint32_t tail = k & (BRO_W - 1u);
             if (lane < tail) o[k - tail + lane] = (uint8_t)mine;
             d.pos += insert_len;
-        } else
-        for (uint32_t k = 0; k < insert_len; k++) {
-            if ((st = bro_step_block(d, cat[0]))) return st;
-            const uint16_t* T = T_lit;
-            if (ntl >= 2u) {
-                uint32_t bt = cat[0].btype, mode = modes[bt], cid;
-                if (mode == 0u) cid = d.p1 & 0x3fu;
-                else if (mode == 1u) cid = d.p1 >> 2;
-                else if (mode == 2u) cid = (uint32_t)bro_lut0[d.p1] | bro_lut1[d.p2];
-                else cid = ((uint32_t)bro_lut2[d.p1] << 3) | bro_lut2[d.p2];
-                T += (uint32_t)cmap_l[bt * 64u + cid] * BRO_TREE_U16(BRO_ALPHA_LIT);
+        } else {
+            // the general run: block switches and a code per literal chosen by the context; lane k % W keeps literal k, W
+            // literals leave with one coalesced store (nothing is stored behind the end of the slot)
+            const uint32_t pos0 = d.pos;
+            uint32_t mine = 0;
+            for (uint32_t k = 0; k < insert_len; k++) {
+                if ((st = bro_step_block(d, cat[0]))) return st;
+                uint32_t t = 0;
+                if (ntl >= 2u) {
+                    uint32_t bt = cat[0].btype, mode = modes[bt], cid;
+                    if (mode == 0u) cid = d.p1 & 0x3fu;
+                    else if (mode == 1u) cid = d.p1 >> 2;
+                    else if (mode == 2u) cid = (uint32_t)bro_lut0[d.p1] | bro_lut1[d.p2];
+                    else cid = ((uint32_t)bro_lut2[d.p1] << 3) | bro_lut2[d.p2];
+                    t = cmap_l[bt * 64u + cid];
+                }
+                const uint16_t* T = T_lit + t * BRO_TREE_U16(BRO_ALPHA_LIT);
+                uint32_t lit;
+                if (one_lit) r = bro_decode_sym2(d.in, sc.root_lit, T, lit);
+                else if (hot.rb_lit) r = bro_decode_sym_hot(d.in, sc.hot_lit + (t << hot.rb_lit), hot.rb_lit, T, lit);
+                else r = bro_decode_sym(d.in, T, lit);
+                if (r == BRO_SYM_HOLE) return BRO_ST_ParseErrorInsertLiterals;
+                if (r == BRO_SYM_EOF) return BRO_ST_UnexpectedEOF;
+                if (lane == (k & (BRO_W - 1u))) mine = lit;
+                d.pos += 1;
+                d.p2 = d.p1; d.p1 = lit;
+                if (((k + 1u) & (BRO_W - 1u)) == 0u) {
+                    const uint32_t at = pos0 + k + 1u - BRO_W + lane;
+                    if (at < d.cap) d.out[at] = (uint8_t)mine;
+                }
             }
-            uint32_t lit;
-            r = bro_decode_sym(d.in, T, lit);
-            if (r == BRO_SYM_HOLE) return BRO_ST_ParseErrorInsertLiterals;
-            if (r == BRO_SYM_EOF) return BRO_ST_UnexpectedEOF;
-            if (lane == 0 && d.pos < d.cap) d.out[d.pos] = (uint8_t)lit;
-            d.pos += 1;
-            d.p2 = d.p1; d.p1 = lit;
+            const uint32_t tail = insert_len & (BRO_W - 1u), at = pos0 + insert_len - tail + lane;
+            if (lane < tail && at < d.cap) d.out[at] = (uint8_t)mine;
         }
         if (d.pos > d.cap) { d.pos = d.cap; return BRO_ST_OutputTooSmall; }
         if (d.pos - mb_begin == mlen) return 0;                                      // src/lib.rs:2069-2070
@@ -1745,12 +1813,14 @@ BRO_FN int bro_commands_general(BroDec& d, BroScratch& sc, uint32_t mlen, BroMbI
         uint32_t dcode = 0;
         if (sym >= 128u) {
             if ((st = bro_step_block(d, cat[2]))) return st;
-            const uint16_t* T = T_dist;
+            uint32_t t = 0;
             if (ntd >= 2u) {
                 uint32_t cid = copy_len <= 4u ? copy_len - 2u : 3u;
-                T += (uint32_t)cmap_d[cat[2].btype * 4u + cid] * dist_stride;
+                t = cmap_d[cat[2].btype * 4u + cid];
             }
+            const uint16_t* T = T_dist + t * dist_stride;
             if (one_dist) r = bro_decode_sym2(d.in, sc.root_dist, T_dist, dcode);
+            else if (hot.rb_dist) r = bro_decode_sym_hot(d.in, sc.root_dist + (t << hot.rb_dist), hot.rb_dist, T, dcode);
             else r = bro_decode_sym(d.in, T, dcode);
             if (r == BRO_SYM_HOLE) return BRO_ST_ParseErrorDistanceCode;
             if (r == BRO_SYM_EOF) return BRO_ST_UnexpectedEOF;
@@ -1779,6 +1849,41 @@ BRO_FN void bro_stage_roots(BroDec& d, BroScratch& sc, const BroMbInfo& mb) {
     bro_syncwarp();
 }
 
+// root bits such that `count` narrow roots fit `budget` entries (8 .. `min_bits`), or 0
+BRO_FN uint32_t bro_hot_bits(uint32_t count, uint32_t budget, uint32_t min_bits) {
+    for (uint32_t rb = 8u; rb >= min_bits; rb--) if ((count << rb) <= budget) return rb;
+    return 0u;
+}
+
+// narrow roots of `count` tables (stride apart in the arena) into `dst`
+BRO_FN void bro_stage_narrow(uint16_t* dst, const uint16_t* T0, uint32_t stride, uint32_t count, uint32_t rb) {
+    for (uint32_t i = bro_lane(); i < (count << rb); i += BRO_W) {
+        const uint32_t e = T0[(i >> rb) * stride + (i & ((1u << rb) - 1u))], l = e >> 10;
+        dst[i] = (uint16_t)((l >= 1u && l <= rb) ? e : 1u);
+    }
+}
+
+// The on-chip tables of a meta-block with several codes of a kind (the general loop), as far as they fit.
+BRO_FN BroHot bro_stage_hot(BroDec& d, BroScratch& sc, const BroMbInfo& mb) {
+    const unsigned lane = bro_lane();
+    BroHot hot;
+    const uint32_t nl = mb.cat[0].nbl, ni = mb.cat[1].nbl, nd = mb.cat[2].nbl;
+    hot.rb_lit = mb.ntl >= 2u ? bro_hot_bits(mb.ntl, BRO_HOT_LIT_U16, 5u) : 0u;
+    hot.rb_cmd = ni >= 2u ? bro_hot_bits(ni, 256u, 5u) : 0u;
+    hot.rb_dist = mb.ntd >= 2u ? bro_hot_bits(mb.ntd, 256u, 4u) : 0u;
+    hot.cmap_l = mb.ntl >= 2u && 64u * nl <= BRO_HOT_CMAP_L;
+    hot.cmap_d = mb.ntd >= 2u && 4u * nd <= BRO_HOT_CMAP_D;
+    hot.modes = nl <= BRO_HOT_MODES;
+    if (hot.rb_lit) bro_stage_narrow(sc.hot_lit, d.arena + mb.o_lit, BRO_TREE_U16(BRO_ALPHA_LIT), mb.ntl, hot.rb_lit);
+    if (hot.rb_cmd) bro_stage_narrow(sc.root_cmd, d.arena + mb.o_cmd, BRO_TREE_U16(BRO_ALPHA_CMD), ni, hot.rb_cmd);
+    if (hot.rb_dist) bro_stage_narrow(sc.root_dist, d.arena + mb.o_dist, mb.dist_stride, mb.ntd, hot.rb_dist);
+    if (hot.cmap_l) for (uint32_t i = lane; i < 64u * nl; i += BRO_W) sc.hot_cmap_l[i] = ((const uint8_t*)(d.arena + mb.o_cmap_l))[i];
+    if (hot.cmap_d) for (uint32_t i = lane; i < 4u * nd; i += BRO_W) sc.hot_cmap_d[i] = ((const uint8_t*)(d.arena + mb.o_cmap_d))[i];
+    if (hot.modes) for (uint32_t i = lane; i < nl; i += BRO_W) sc.hot_modes[i] = ((const uint8_t*)(d.arena + mb.o_modes))[i];
+    bro_syncwarp();
+    return hot;
+}
+
 // one compressed meta-block after MLEN / ISUNCOMPRESSED: src/lib.rs:1745-2141
 BRO_FN int bro_decode_compressed_metablock(BroDec& d, uint32_t mlen) {
     BroMbInfo mb;
@@ -1788,7 +1893,8 @@ BRO_FN int bro_decode_compressed_metablock(BroDec& d, uint32_t mlen) {
     bro_stage_roots(d, sc, mb);
     if (mb.simple)
         return bro_commands_simple(d, sc, mlen, mb.npostfix, mb.ndirect, d.arena + mb.o_lit, d.arena + mb.o_cmd, d.arena + mb.o_dist);
-    return bro_commands_general(d, sc, mlen, mb);
+    const BroHot hot = bro_stage_hot(d, sc, mb);
+    return bro_commands_general(d, sc, mlen, mb, hot);
 }
 
 #endif

@@ -5,7 +5,12 @@
 #include <stdlib.h>
 #include <string.h>
 
+// test-suite instrumentation: what the meta-block headers of the last decodes announced (histograms, saturating at 63)
+static unsigned g_mb_hist[5][64];
+#define BRO_MB_STAT(ntl, ntd, n0, n1, n2, st) do { if (!(st)) { unsigned v_[5] = {(ntl), (ntd), (n0), (n1), (n2)}; \
+    for (int q_ = 0; q_ < 5; q_++) g_mb_hist[q_][v_[q_] < 63u ? v_[q_] : 63u]++; } } while (0)
 #include "bro_decoder_core.h"
+extern "C" void bro_hostsim_mb_hist(unsigned* out, int reset) { memcpy(out, g_mb_hist, sizeof(g_mb_hist)); if (reset) memset(g_mb_hist, 0, sizeof(g_mb_hist)); }
 
 extern "C" const uint8_t bro_dictionary_blob[];
 
@@ -17,7 +22,12 @@ static void bro_hostsim_bind(BroDec& d, uint8_t* mem) {
     d.in.ring = tl;
     uint16_t* roots = (uint16_t*)(mem + 32u * BRO_TL_BYTES);
     d.scv.root_lit = roots; d.scv.root_cmd = roots + 256; d.scv.root_dist = roots + 512;
+    d.scv.hot_lit = roots + 768;
+    d.scv.hot_cmap_l = (uint8_t*)(roots + 768 + BRO_HOT_LIT_U16);
+    d.scv.hot_cmap_d = d.scv.hot_cmap_l + BRO_HOT_CMAP_L;
+    d.scv.hot_modes = d.scv.hot_cmap_d + BRO_HOT_CMAP_D;
 }
+#define BRO_HOSTSIM_SC_BYTES (32u * BRO_TL_BYTES + (768u + BRO_HOT_LIT_U16) * sizeof(uint16_t) + BRO_HOT_CMAP_L + BRO_HOT_CMAP_D + BRO_HOT_MODES)
 
 // arena_u16 = 0 selects the worst-case arena of the warp kernel; BRO_THREAD_ARENA_U16 simulates the thread kernel
 // (which may answer BRO_ST_ArenaTooSmall, upon which the product re-runs the stream with the warp kernel).
@@ -26,7 +36,7 @@ extern "C" int bro_hostsim_decode(const uint8_t* in, size_t in_len, uint8_t* out
     if (arena_u16 == 0) arena_u16 = BRO_ARENA_U16_MAX;
     BroDec d;
     memset(&d, 0, sizeof(d));
-    uint8_t* sc = (uint8_t*)calloc(32u * BRO_TL_BYTES + 3u * 256u * sizeof(uint16_t), 1);
+    uint8_t* sc = (uint8_t*)calloc(BRO_HOSTSIM_SC_BYTES, 1);
     uint16_t* arena = (uint16_t*)malloc(2u * (size_t)arena_u16);
     bro_hostsim_bind(d, sc);
     d.arena = arena;
@@ -57,7 +67,7 @@ extern "C" int bro_hostsim_decode_resume(const uint8_t* in, size_t in_len, uint8
                                          BroResume* ck) {
     BroDec d;
     memset(&d, 0, sizeof(d));
-    uint8_t* sc = (uint8_t*)calloc(32u * BRO_TL_BYTES + 3u * 256u * sizeof(uint16_t), 1);
+    uint8_t* sc = (uint8_t*)calloc(BRO_HOSTSIM_SC_BYTES, 1);
     uint16_t* arena = (uint16_t*)malloc(2u * (size_t)BRO_ARENA_U16_MAX);
     bro_hostsim_bind(d, sc);
     d.arena = arena;

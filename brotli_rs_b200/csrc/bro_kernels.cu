@@ -12,8 +12,17 @@
 #include "bro_decoder_core.h"
 #include "bro_kernels.h"
 
+// Two builds of the same kernel (measured on B200, profiles/r02_kernel_variants.md):
+//   throughput: 3 CTAs of 8 warps per SM, 80 registers -- batches of a few thousand to a few ten thousand streams
+//               (10,000 x quickfox: 0.73 ms; 4 CTAs / 64 registers: 0.81 ms, 2 CTAs: 0.89 ms);
+//   latency:    2 CTAs per SM, 128 registers, no spills -- whenever a single stream's decode time is what the call costs:
+//               one wave of streams or less, the retry pass of the two-phase path, a batch AUTO's gate found bound by its
+//               longest stream (alice29 alone: 24 ms against 33 ms; corpus x 1000: 300 ms against 343 ms)
 #ifndef BRO_MIN_BLOCKS
-#define BRO_MIN_BLOCKS 4
+#define BRO_MIN_BLOCKS 3
+#endif
+#ifndef BRO_MIN_BLOCKS_LATENCY
+#define BRO_MIN_BLOCKS_LATENCY 2
 #endif
 
 // A full warp per stream has worst-case arenas (it is also the retry kernel); experimental sub-warp groups
@@ -21,9 +30,11 @@
 #define BRO_GROUP_ARENA_U16 (BRO_W == 32u ? BRO_ARENA_U16_MAX : 65536u)
 #define BRO_GROUPS_PER_WARP (32u / BRO_W)
 
-template <int WARPS>
-__global__ void __launch_bounds__(WARPS * 32, BRO_MIN_BLOCKS) bro_decode_warp_kernel(BroLaunch p) {
-    __shared__ BroScratch scratch[WARPS * BRO_GROUPS_PER_WARP];
+template <int WARPS, int MINB>
+__global__ void __launch_bounds__(WARPS * 32, MINB) bro_decode_warp_kernel(BroLaunch p) {
+    // one BroScratch per warp (6.7 KB with the general loop's on-chip tables: dynamic shared memory, 4 CTAs x 8 warps = 214 KB per SM)
+    extern __shared__ __align__(16) uint8_t bro_smem_raw[];
+    BroScratch* const scratch = (BroScratch*)bro_smem_raw;
     const unsigned warp = threadIdx.x / BRO_W, lane = bro_lane();     // "warp" = group of BRO_W lanes
     const unsigned gwarp = blockIdx.x * (WARPS * BRO_GROUPS_PER_WARP) + warp;
     // retry pass of the two-phase path: only the streams the parse kernel handed over -- unless AUTO's gate sent the
@@ -67,17 +78,25 @@ __global__ void __launch_bounds__(WARPS * 32, BRO_MIN_BLOCKS) bro_decode_warp_ke
 }
 
 #define BRO_WARPS_PER_CTA 8
+#define BRO_WARP_KERNEL_SMEM (BRO_WARPS_PER_CTA * BRO_GROUPS_PER_WARP * sizeof(BroScratch))
 
+// blocks_per_sm[0]: the throughput build, [1]: the latency build
 extern "C" int bro_warp_kernel_occupancy(int* blocks_per_sm) {
-    return (int)cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, bro_decode_warp_kernel<BRO_WARPS_PER_CTA>,
-                                                              BRO_WARPS_PER_CTA * 32, 0);
+    cudaError_t e = cudaFuncSetAttribute(bro_decode_warp_kernel<BRO_WARPS_PER_CTA, BRO_MIN_BLOCKS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BRO_WARP_KERNEL_SMEM);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(bro_decode_warp_kernel<BRO_WARPS_PER_CTA, BRO_MIN_BLOCKS_LATENCY>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BRO_WARP_KERNEL_SMEM);
+    if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm[0], bro_decode_warp_kernel<BRO_WARPS_PER_CTA, BRO_MIN_BLOCKS>,
+                                                                            BRO_WARPS_PER_CTA * 32, BRO_WARP_KERNEL_SMEM);
+    if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm[1], bro_decode_warp_kernel<BRO_WARPS_PER_CTA, BRO_MIN_BLOCKS_LATENCY>,
+                                                                            BRO_WARPS_PER_CTA * 32, BRO_WARP_KERNEL_SMEM);
+    return (int)e;
 }
 
 extern "C" int bro_warp_kernel_warps_per_cta() { return BRO_WARPS_PER_CTA * BRO_GROUPS_PER_WARP; }
 extern "C" size_t bro_warp_kernel_arena_bytes() { return 2u * (size_t)BRO_GROUP_ARENA_U16; }
 
-extern "C" int bro_warp_kernel_launch(const BroLaunch* p, int grid, cudaStream_t stream) {
+extern "C" int bro_warp_kernel_launch(const BroLaunch* p, int grid, int latency, cudaStream_t stream) {
     (void)cudaGetLastError();      // a stale error of another library in this process (it is per thread) is not this launch's
-    bro_decode_warp_kernel<BRO_WARPS_PER_CTA><<<grid, BRO_WARPS_PER_CTA * 32, 0, stream>>>(*p);
+    if (latency) bro_decode_warp_kernel<BRO_WARPS_PER_CTA, BRO_MIN_BLOCKS_LATENCY><<<grid, BRO_WARPS_PER_CTA * 32, BRO_WARP_KERNEL_SMEM, stream>>>(*p);
+    else bro_decode_warp_kernel<BRO_WARPS_PER_CTA, BRO_MIN_BLOCKS><<<grid, BRO_WARPS_PER_CTA * 32, BRO_WARP_KERNEL_SMEM, stream>>>(*p);
     return (int)cudaGetLastError();
 }

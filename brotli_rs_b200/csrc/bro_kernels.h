@@ -53,7 +53,7 @@ struct BroLaunch {
 extern "C" int bro_warp_kernel_occupancy(int* blocks_per_sm);
 extern "C" int bro_warp_kernel_warps_per_cta();
 extern "C" size_t bro_warp_kernel_arena_bytes();
-extern "C" int bro_warp_kernel_launch(const BroLaunch* p, int grid, cudaStream_t stream);
+extern "C" int bro_warp_kernel_launch(const BroLaunch* p, int grid, int latency, cudaStream_t stream);
 
 // resumable warp-per-stream kernel (bro_kernels_resume.cu); same arenas and grid as the warp kernel
 extern "C" int bro_resume_kernel_warps_per_cta();

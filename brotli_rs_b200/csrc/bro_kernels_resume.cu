@@ -19,8 +19,9 @@
 
 #define BRO_RESUME_WARPS 8
 
-__global__ void __launch_bounds__(BRO_RESUME_WARPS * 32, 4) bro_decode_resume_kernel(BroLaunch p) {
-    __shared__ BroScratch scratch[BRO_RESUME_WARPS];
+__global__ void __launch_bounds__(BRO_RESUME_WARPS * 32, 2) bro_decode_resume_kernel(BroLaunch p) {      // 128 registers: a reader's one stream is latency-bound
+    extern __shared__ __align__(16) uint8_t bro_smem_raw[];
+    BroScratch* const scratch = (BroScratch*)bro_smem_raw;
     const unsigned warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
     const unsigned gwarp = blockIdx.x * BRO_RESUME_WARPS + warp;
     for (;;) {
@@ -55,6 +56,10 @@ extern "C" int bro_resume_kernel_warps_per_cta() { return BRO_RESUME_WARPS; }
 
 extern "C" int bro_resume_kernel_launch(const BroLaunch* p, int grid, cudaStream_t stream) {
     (void)cudaGetLastError();
-    bro_decode_resume_kernel<<<grid, BRO_RESUME_WARPS * 32, 0, stream>>>(*p);
+    static bool attr_set = false;      // (per process; the attribute is per function and device, set before every first use on a device is overkill: it is idempotent)
+    cudaError_t e = cudaFuncSetAttribute(bro_decode_resume_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(BRO_RESUME_WARPS * sizeof(BroScratch)));
+    if (e != cudaSuccess) return (int)e;
+    (void)attr_set;
+    bro_decode_resume_kernel<<<grid, BRO_RESUME_WARPS * 32, BRO_RESUME_WARPS * sizeof(BroScratch), stream>>>(*p);
     return (int)cudaGetLastError();
 }

@@ -60,8 +60,8 @@ int bro_ctx_set_quirks(bro_ctx* ctx, int quirks);
  *             every LZ77 copy into a record; phase two executes the records with one warp per stream at memory speed.
  *             Streams phase one cannot decode (literal context modelling, libbrotli quality >= 10) are re-run by the
  *             fused kernel inside the same call.
- *   AUTO (default): TWOPHASE for batches of at least 5 x bro_ctx_num_warps streams (the fused kernel would need that
- *             many waves of its resident warps), WARP below -- and also for a large batch that is bound by its longest
+ *   AUTO (default): TWOPHASE for batches of at least 160 streams per SM (23,680 on a B200: the fused kernel would need
+ *             several waves of its resident warps), WARP below -- and also for a large batch that is bound by its longest
  *             stream (decided on the device from the compressed sizes: the two-phase kernels return at once).
  * The environment variable BRO_B200_MODE=warp|twophase sets the initial mode. */
 #define BRO_MODE_AUTO 0
@@ -84,8 +84,8 @@ int bro_ctx_last_kernel_ms(bro_ctx* ctx, float* ms4);
 int bro_ctx_last_batch_stats(bro_ctx* ctx, uint64_t* stats4);
 
 /* Optional: an upper bound on the compressed bytes (d_in_off[n] - d_in_off[0]) of the batches that follow.  The bound is
- * STICKY: it applies to every later batch of the context until it is changed (0 = forget).  The two-phase path sizes its copy-record arena from it; without it bro_batch_decode reads the two end
- * offsets back from the device (16 bytes, blocking on the stream) before it launches.  A bound that turns out too small
+ * STICKY: it applies to every later batch of the context until it is changed (0 = forget).  The two-phase path sizes its
+ * copy-record arena from it; without it bro_batch_decode reads the two end offsets back from the device (16 bytes, blocking on the stream) before it launches.  A bound that turns out too small
  * costs speed only: streams whose records do not fit are decoded by the fused kernel. */
 int bro_ctx_reserve(bro_ctx* ctx, uint64_t total_in_bytes, uint32_t n_streams);
 

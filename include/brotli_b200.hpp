@@ -137,4 +137,32 @@ inline std::vector<BatchItem> decode_batch(bro_ctx* ctx, const std::vector<std::
     return res;
 }
 
+// One batch over several GPUs of the box from this process (bro_mg_*): streams and the capacity of every stream's slot in,
+// status and bytes out.  ngpus <= 0: every visible device.
+inline std::vector<BatchItem> decode_batch_multi_gpu(const std::vector<std::vector<uint8_t>>& streams, const std::vector<size_t>& capacities,
+                                                     int ngpus = 0) {
+    const uint32_t n = static_cast<uint32_t>(streams.size());
+    std::vector<uint64_t> in_off(n + 1, 0), out_off(n + 1, 0), out_len(n, 0);
+    std::vector<int32_t> status(n, 0);
+    for (uint32_t i = 0; i < n; i++) {
+        in_off[i + 1] = in_off[i] + streams[i].size();
+        out_off[i + 1] = out_off[i] + ((capacities[i] + 15) & ~static_cast<size_t>(15));      // 16-byte aligned slot starts
+    }
+    std::vector<uint8_t> in(in_off[n] + 16), out(out_off[n] ? out_off[n] : 1);
+    for (uint32_t i = 0; i < n; i++)
+        for (size_t k = 0; k < streams[i].size(); k++) in[in_off[i] + k] = streams[i][k];
+    bro_mg* mg = nullptr;
+    int st = bro_mg_create(&mg, ngpus);
+    if (st != BRO_OK) throw Error(st);
+    st = bro_mg_decode_host(mg, in.data(), in_off.data(), out.data(), out_off.data(), out_len.data(), status.data(), n);
+    bro_mg_destroy(mg);
+    if (st != BRO_OK) throw Error(st);
+    std::vector<BatchItem> res(n);
+    for (uint32_t i = 0; i < n; i++) {
+        res[i].status = status[i];
+        if (status[i] == BRO_OK && out_len[i]) res[i].bytes.assign(out.begin() + out_off[i], out.begin() + out_off[i] + out_len[i]);
+    }
+    return res;
+}
+
 }  // namespace brotli

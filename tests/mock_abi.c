@@ -77,3 +77,32 @@ intptr_t bro_reader_read(bro_reader* r, uint8_t* buf, size_t len) {
 }
 int bro_reader_status(const bro_reader* r) { return r->status; }
 void bro_reader_free(bro_reader* r) { if (r) { bro_oracle_free(r->out); free(r); } }
+
+/* bro_mg_*: the mock has one "device" */
+struct bro_mg { bro_ctx* ctx; };
+int bro_mg_create(bro_mg** mg, int ngpus) {
+    if (ngpus > 1) return 104;
+    *mg = (bro_mg*)calloc(1, sizeof(bro_mg));
+    return *mg ? bro_ctx_create(&(*mg)->ctx, 0) : 104;
+}
+void bro_mg_destroy(bro_mg* mg) { if (mg) { bro_ctx_destroy(mg->ctx); free(mg); } }
+int bro_mg_device_count(const bro_mg* mg) { return mg ? 1 : 0; }
+bro_ctx* bro_mg_ctx(bro_mg* mg, int k) { return (mg && k == 0) ? mg->ctx : NULL; }
+int bro_mg_partition(const uint64_t* h_in_off, const uint64_t* h_out_off, uint32_t n, int ngpus, uint32_t* first) {
+    (void)h_in_off; (void)h_out_off;
+    for (int k = 0; k <= ngpus; k++) first[k] = k == 0 ? 0 : n;
+    return BRO_OK;
+}
+int bro_mg_decode_host(bro_mg* mg, const uint8_t* h_in, const uint64_t* h_in_off, uint8_t* h_out, const uint64_t* h_out_off,
+                       uint64_t* h_out_len, int32_t* h_status, uint32_t n) {
+    for (uint32_t i = 0; i < n; i++) {
+        uint8_t* part = NULL;
+        size_t len = 0;
+        h_status[i] = bro_oracle_decode(h_in + h_in_off[i], (size_t)(h_in_off[i + 1] - h_in_off[i]), &part, &len, mg->ctx->quirks);
+        if (h_status[i] == BRO_OK && len > h_out_off[i + 1] - h_out_off[i]) h_status[i] = BRO_OUTPUT_TOO_SMALL;
+        h_out_len[i] = h_status[i] == BRO_OK ? len : 0;
+        if (h_status[i] == BRO_OK && len) memcpy(h_out + h_out_off[i], part, len);
+        bro_oracle_free(part);
+    }
+    return BRO_OK;
+}

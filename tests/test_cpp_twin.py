@@ -29,6 +29,27 @@ int main(int argc, char** argv) {
         bro_ctx_destroy(ctx);
         return 0;
     }
+    if (argc > 3 && !std::strcmp(argv[1], "mg")) {
+        // multi-GPU batch mode: argv[2] = devices (0 = all), argv[3..] = compressed files, each decoded 40 times; slots sized by a
+        // first unsized decode; prints the device count, then "status size" per distinct stream if every replica agrees
+        bro_ctx* ctx = nullptr;
+        if (bro_ctx_create(&ctx, -1) != BRO_OK) return 4;
+        std::vector<std::vector<uint8_t>> streams;
+        for (int i = 3; i < argc; i++) streams.push_back(slurp(argv[i]));
+        const auto first = brotli::decode_batch(ctx, streams);
+        bro_ctx_destroy(ctx);
+        std::vector<std::vector<uint8_t>> many;
+        std::vector<size_t> caps;
+        for (int rep = 0; rep < 40; rep++)
+            for (size_t i = 0; i < streams.size(); i++) { many.push_back(streams[i]); caps.push_back(first[i].bytes.size() + (first[i].status ? 4096 : 0)); }
+        const auto res = brotli::decode_batch_multi_gpu(many, caps, std::atoi(argv[2]));
+        for (size_t k = 0; k < res.size(); k++) {
+            const auto& want = first[k % streams.size()];
+            if (res[k].status != want.status || (want.status == 0 && res[k].bytes != want.bytes)) { std::printf("MISMATCH %zu\n", k); return 2; }
+        }
+        for (const auto& it : first) std::printf("%d %zu\n", it.status, it.bytes.size());
+        return 0;
+    }
     if (argc > 4 && !std::strcmp(argv[1], "stream")) {
         // streaming mode: argv[2] = compressed file, argv[3] = expected file, argv[4] = bytes asked of the file at a time
         std::ifstream f(argv[2], std::ios::binary);
@@ -89,6 +110,11 @@ def test_cpp_twin_doctest_and_error(tmp_path):
                        capture_output=True, text=True)
     want = ["0 %d" % os.path.getsize(os.path.join(DATA, n)) for n in names] + ["23 0"]
     assert r.returncode == 0 and r.stdout.split("\n")[:6] == want, r.stdout + r.stderr
+    # brotli::decode_batch_multi_gpu (bro_mg_*): 240 streams over every GPU of the box, and over one
+    for ngpus in ("0", "1"):
+        r = subprocess.run([exe, "mg", ngpus] + [os.path.join(DATA, n + ".compressed") for n in names] + [os.path.join(DATA, "frewsxcv_06.compressed")],
+                           capture_output=True, text=True)
+        assert r.returncode == 0 and r.stdout.split("\n")[:6] == want, r.stdout + r.stderr
 
 
 # ---- tools/corpus_driver.cpp: the reference's command-line driver (src/main.rs:49-70) ----
@@ -184,5 +210,8 @@ def test_host_code_against_mock_library(tmp_path):
     assert r.returncode == 0 and r.stdout.startswith("EQUAL 912868"), r.stdout + r.stderr
     bn = ["64x", "alice29.txt", "quickfox_repeated", "random_org_10k.bin", "empty"]
     r = subprocess.run([exe, "batch"] + [os.path.join(DATA, n + ".compressed") for n in bn] + [os.path.join(DATA, "frewsxcv_06.compressed")],
+                       capture_output=True, text=True)
+    assert r.returncode == 0 and r.stdout.split("\n")[:6] == ["0 %d" % os.path.getsize(os.path.join(DATA, n)) for n in bn] + ["23 0"], r.stdout + r.stderr
+    r = subprocess.run([exe, "mg", "0"] + [os.path.join(DATA, n + ".compressed") for n in bn] + [os.path.join(DATA, "frewsxcv_06.compressed")],
                        capture_output=True, text=True)
     assert r.returncode == 0 and r.stdout.split("\n")[:6] == ["0 %d" % os.path.getsize(os.path.join(DATA, n)) for n in bn] + ["23 0"], r.stdout + r.stderr

@@ -323,12 +323,12 @@ def test_auto_mode_launch_counts(monkeypatch):
     files = [f for f in corpus_files() if f[2] is not None and len(f[1]) < 2000]
     streams = [c for _, c, _ in files] * 100
     exps = [e for _, _, e in files] * 100
-    probe = BatchDecoder(0)
-    many = -(-5 * probe.num_warps // len(streams))           # AUTO takes the two-phase path from 5 x num_warps streams
-    probe.close()
+    import torch
+    threshold = 160 * torch.cuda.get_device_properties(0).multi_processor_count      # AUTO takes the two-phase path from 160 streams per SM
+    many = -(-threshold // len(streams))
     for mode, reps, want in ((None, 1, 1), (BatchDecoder.MODE_TWOPHASE, 1, 6), (None, many, 6)):
         d = BatchDecoder(0, mode=mode)
-        assert len(streams) < 5 * d.num_warps <= len(streams) * many
+        assert len(streams) < threshold <= len(streams) * many
         before = d.launch_count
         res = d.decode_streams(streams * reps, [len(e) for e in exps] * reps)
         assert d.launch_count - before == want
