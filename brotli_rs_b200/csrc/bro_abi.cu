@@ -258,13 +258,30 @@ extern "C" int bro_batch_decode(bro_ctx* ctx, const uint8_t* d_in, const uint64_
     p.dict = ctx->d_dict; p.quirk_spec = ctx->quirks;
     p.order = NULL; p.retry_count = ctx->d_counter + 2; p.retry_mode = 0;
     const uint32_t wpc = (uint32_t)bro_warp_kernel_warps_per_cta();
-    const bool two_phase = ctx->mode == BRO_MODE_TWOPHASE || (ctx->mode == BRO_MODE_AUTO && n >= ctx->twophase_threshold);
-    // the latency build of the fused kernel whenever one stream's decode time is what the call costs: at most a wave of
-    // streams, and behind the two-phase kernels (the retry pass; a batch the gate found bound by its longest stream)
-    const int latency = (two_phase || n <= (uint32_t)ctx->grid_lat * wpc) ? 1 : 0;
-    int grid_w = latency ? ctx->grid_lat : ctx->grid;
+    // AUTO: the two-phase path for a large batch (160 streams per SM: whatever the streams are, the fused kernel would need
+    // many waves), and from 32 streams per SM when the streams are not tiny (512 compressed bytes on average: below that a
+    // stream is mostly headers and one warp per stream is as good) -- measured break-even on the headline streams: ~4,000
+    uint64_t total_in = ctx->reserved_in;
+    bool two_phase = ctx->mode == BRO_MODE_TWOPHASE || (ctx->mode == BRO_MODE_AUTO && n >= ctx->twophase_threshold);
+    if (!two_phase && ctx->mode == BRO_MODE_AUTO && n >= 32u * (uint32_t)ctx->num_sms) {
+        if (total_in == 0) {
+            uint64_t ends[2];
+            BRO_CUDA(ctx, cudaMemcpyAsync(&ends[0], d_in_off, sizeof(uint64_t), cudaMemcpyDeviceToHost, s));
+            BRO_CUDA(ctx, cudaMemcpyAsync(&ends[1], d_in_off + n, sizeof(uint64_t), cudaMemcpyDeviceToHost, s));
+            BRO_CUDA(ctx, cudaStreamSynchronize(s));
+            if (ends[1] < ends[0]) return BRO_ST_InvalidArgument;
+            total_in = ends[1] - ends[0] ? ends[1] - ends[0] : 1;
+        }
+        two_phase = total_in >= 512ull * n;
+    }
+    // The fused kernel has a throughput and a latency build (bro_kernels.cu).  On its own: by the number of streams.  Behind
+    // the two-phase kernels both are launched and decide on the device (BroLaunch::fused_role).
+    const uint32_t lat_warps = (uint32_t)ctx->grid_lat * wpc;
+    const int latency = n <= lat_warps ? 1 : 0;
+    int grid_w = ctx->grid, grid_l = ctx->grid_lat;
     if ((uint32_t)grid_w > (n + wpc - 1) / wpc) grid_w = (int)((n + wpc - 1) / wpc);
-    { int st_a = bro_ensure_arena(ctx, (uint32_t)grid_w * wpc); if (st_a) return st_a; }       // before anything of this batch is in flight
+    if ((uint32_t)grid_l > (n + wpc - 1) / wpc) grid_l = (int)((n + wpc - 1) / wpc);
+    { int st_a = bro_ensure_arena(ctx, (uint32_t)(grid_w > grid_l ? grid_w : grid_l) * wpc); if (st_a) return st_a; }       // before anything of this batch is in flight
     cudaError_t e;
     if (two_phase) {
         // PHASE ONE: one thread per stream (bro_parse_kernel), streams handed out by compressed-size class; literals and
@@ -281,7 +298,6 @@ extern "C" int bro_batch_decode(bro_ctx* ctx, const uint8_t* d_in, const uint64_
         if ((st = bro_grow(ctx, (void**)&ctx->d_order, &ctx->d_order_cap, (size_t)n, 3 * sizeof(uint32_t)))) return st;
         // the record arena is sized from the compressed bytes of the batch: the caller's bound (bro_ctx_reserve), else
         // the two end offsets are read back (16 bytes, blocking on `s`)
-        uint64_t total_in = ctx->reserved_in;
         if (total_in == 0) {
             uint64_t ends[2];
             BRO_CUDA(ctx, cudaMemcpyAsync(&ends[0], d_in_off, sizeof(uint64_t), cudaMemcpyDeviceToHost, s));
@@ -348,7 +364,16 @@ extern "C" int bro_batch_decode(bro_ctx* ctx, const uint8_t* d_in, const uint64_
     p.arena = ctx->d_arena; p.counter = ctx->d_counter + 1;
     p.order = two_phase ? ctx->d_order : NULL;       // size-class order of the batch (largest first) when it was computed
     if (ctx->timing) BRO_CUDA(ctx, cudaEventRecord(ctx->ev[3], s));
-    e = (cudaError_t)bro_warp_kernel_launch(&p, grid_w, latency, s);
+    if (two_phase) {
+        p.fused_small = lat_warps;
+        p.fused_role = 1;
+        e = (cudaError_t)bro_warp_kernel_launch(&p, grid_l, 1, s);
+        if (e == cudaSuccess && n > lat_warps) {       // (more streams than a latency wave could ever be retried)
+            p.fused_role = 2;
+            e = (cudaError_t)bro_warp_kernel_launch(&p, grid_w, 0, s);
+            ctx->launches += 1;
+        }
+    } else e = (cudaError_t)bro_warp_kernel_launch(&p, latency ? grid_l : grid_w, latency, s);
     if (e != cudaSuccess) return bro_fail(ctx, e, "bro_decode_warp_kernel launch");
     ctx->launches += 1;
     if (ctx->timing) {

@@ -39,8 +39,13 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) bro_decode_warp_kernel(BroLa
     const unsigned gwarp = blockIdx.x * (WARPS * BRO_GROUPS_PER_WARP) + warp;
     // retry pass of the two-phase path: only the streams the parse kernel handed over -- unless AUTO's gate sent the
     // whole batch here
-    const bool retry = p.retry_mode && !(p.gate && p.gate[1]);
+    const bool gated = p.gate && p.gate[1];
+    const bool retry = p.retry_mode && !gated;
     if (retry && *p.retry_count == 0u) return;
+    if (p.fused_role) {
+        const bool small = gated || (retry && *p.retry_count <= p.fused_small);
+        if ((p.fused_role == 1) != small) return;      // the other build's job
+    }
     for (;;) {
         uint32_t i = 0;
         if (lane == 0) {

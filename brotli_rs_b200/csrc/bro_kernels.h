@@ -22,6 +22,10 @@ struct BroLaunch {
     uint32_t* retry_count;    // parse kernel: +1 per stream it hands to the fused kernel (status ArenaTooSmall, NeedFused
                               // or RecordsFull); the warp kernel in retry mode decodes exactly those (exits at once if 0)
     int retry_mode;
+    int fused_role;           // warp kernel behind the two-phase kernels: BOTH builds are launched and each decides on the device
+                              // whether the pass is its job -- 1 = the latency build: a batch the gate found bound by its longest
+                              // stream, or at most fused_small streams to retry; 2 = the throughput build: the rest; 0 = unconditional
+    uint32_t fused_small;
     int quirk_spec;
     // two-phase path: copy records.  Stream i owns records [rec_base(i), rec_base(i+1)) of `rec`, where
     // rec_base(i) = ((in_off[i] - in_off[0]) >> 1) + 32 * i; a stream whose share ends beyond rec_total, or that needs

@@ -145,11 +145,12 @@ __global__ void bro_order_hist_kernel(const uint64_t* in_off, uint32_t n, uint32
     }
 }
 
-// BRO_GATE_RATIO: throughput of the fused kernel over the decode rate of a single stream (both in compressed bytes
-// per second, measured on B200: ~10 GB/s over ~1 MB/s).  A batch whose longest stream, decoded alone, takes longer
-// than the whole batch would take at full throughput is bound by that stream on either path, and then the two-phase
-// path only adds the serial tails of its phases: the fused kernel takes the whole batch.
-#define BRO_GATE_RATIO 10000ull
+// BRO_GATE_RATIO: A batch whose longest stream, decoded alone, takes longer than the whole batch would take at full
+// throughput is bound by that stream on either path, and then the two-phase path only adds the serial tails of its phases
+// (a stream alone: ~2 ms per 4 KB on a fused warp, ~3.5 ms through parse + copy): the fused kernel takes the whole batch.
+// The ratio is where the two paths were measured to break even on B200 (round 2: 3,000 headline streams 2.0 ms fused /
+// 2.6 ms two-phase, 6,000: 4.0 / 2.8, i.e. at ~4,500 streams of equal size).
+#define BRO_GATE_RATIO 4500ull
 
 __global__ void bro_order_scan_kernel(const uint32_t* hist, uint32_t* cursor, const uint64_t* in_off, uint32_t n, uint32_t* gate) {
     __shared__ uint32_t s[256];

@@ -315,9 +315,9 @@ def test_parse_handover_is_retried_by_warp_kernel(dec):
 
 
 def test_auto_mode_launch_counts(monkeypatch):
-    """default mode decodes a small batch with ONE launch of the warp kernel and a large one by the two-phase path:
-    3 ordering kernels, the parse kernel, the copy kernel and the fused kernel's retry pass (per slice of the host call:
-    one slice here)"""
+    """default mode decodes a small batch of small streams with ONE launch of the warp kernel and a large one by the
+    two-phase path: 3 ordering kernels, the parse kernel, the copy kernel and the fused kernel's retry pass (per slice of
+    the host call: one slice here)"""
     from brotli_rs_b200 import BatchDecoder
     monkeypatch.setenv("BRO_B200_HOST_CHUNKS", "1")
     files = [f for f in corpus_files() if f[2] is not None and len(f[1]) < 2000]
@@ -326,12 +326,15 @@ def test_auto_mode_launch_counts(monkeypatch):
     import torch
     threshold = 160 * torch.cuda.get_device_properties(0).multi_processor_count      # AUTO takes the two-phase path from 160 streams per SM
     many = -(-threshold // len(streams))
+    lat_wave = 16 * torch.cuda.get_device_properties(0).multi_processor_count      # resident warps of the fused kernel's latency build
     for mode, reps, want in ((None, 1, 1), (BatchDecoder.MODE_TWOPHASE, 1, 6), (None, many, 6)):
         d = BatchDecoder(0, mode=mode)
         assert len(streams) < threshold <= len(streams) * many
         before = d.launch_count
         res = d.decode_streams(streams * reps, [len(e) for e in exps] * reps)
-        assert d.launch_count - before == want
+        # behind the two-phase kernels both builds of the fused kernel are launched when the batch exceeds a latency wave
+        # (they decide on the device whose job the pass is)
+        assert d.launch_count - before == want + (1 if want == 6 and len(streams) * reps > lat_wave else 0)
         for (st, out), e in zip(res, exps * reps):
             assert st == 0 and out == e
         d.close()
