@@ -138,7 +138,7 @@ class ClockSampler:
         return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(smax)), "reasons": sorted(reasons), "samples": len(sm)}
 
 
-DEFAULT_STREAMS = {"c4_highratio_w16": 100000, "c5_stored_10k": 100000, "c5b_literals_10k": 100000,
+DEFAULT_STREAMS = {"c6_text_q11_w16": 20000, "c7_far_w22": 8000, "c4_highratio_w16": 100000, "c5_stored_10k": 100000, "c5b_literals_10k": 100000,
                    "c2_quickfox_x10k": 10000, "c3_corpus_x1000": 52000, "c1_alice29_single": 1}
 
 
@@ -156,16 +156,24 @@ def build_workload(name, n_streams):
         _, streams, raws, status = w.corpus_workload(data, only={"quickfox_repeated.compressed"})
         desc = "copies of data/quickfox_repeated.compressed (58 B -> 176,128 B, one overlapping copy at distance 43)"
         gidx = np.zeros(n_streams, dtype=np.int64)
+    elif name == "c6_text_q11_w16":
+        # round 2 (VERDICT "decide with data"): alice29.txt at quality 11, lgwin 16 -- context-modelled, 11 % of the output from
+        # the static dictionary: the fused kernel's general loop and bro_dict_word
+        raw = open(os.path.join(data, "alice29.txt"), "rb").read()
+        enc = w.libbrotli_enc()
+        streams, raws, status = [w.compress(enc, raw, 11, 16)], [raw], [0]
+        desc = "copies of alice29.txt at quality 11 / lgwin 16 (%d -> %d B; literal context modelling, static dictionary)" % (len(streams[0]), len(raw))
+        gidx = np.zeros(n_streams, dtype=np.int64)
     elif name == "c3_corpus_x1000":
         _, streams, raws, status = w.corpus_workload(data)
         desc = "every data/*compressed* stream (52, 9 invalid) x replicas, shuffled with default_rng(0)"
         gidx = np.tile(np.arange(len(streams)), (n_streams + len(streams) - 1) // len(streams))[:n_streams]
         np.random.default_rng(0).shuffle(gidx)
     else:
-        streams, raws = w.make_unique_streams(name, N_UNIQUE)
+        streams, raws = w.make_unique_streams(name, N_UNIQUE if name != "c7_far_w22" else 64)
         status = [0] * len(streams)
         desc = w.WORKLOADS[name][5]
-        gidx = np.arange(n_streams) % N_UNIQUE
+        gidx = np.arange(n_streams) % len(streams)
     return {"streams": streams, "raws": raws, "status": np.array(status, dtype=np.int32), "gidx": gidx, "desc": desc}
 
 

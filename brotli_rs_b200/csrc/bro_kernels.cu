@@ -24,6 +24,13 @@
 #ifndef BRO_MIN_BLOCKS_LATENCY
 #define BRO_MIN_BLOCKS_LATENCY 2
 #endif
+// BRO_DICT_SMEM=1 (measured variant, not the product: profiles/r02_kernel_variants.md): the 122,784-byte static dictionary
+// image in shared memory, one CTA of BRO_WARPS_PER_CTA (14) warps per SM -- what BASELINE's north_star suggests.  The
+// product keeps the image in HBM / L2 (it is L1-resident wherever it is used) and the shared memory for 24 warps per SM.
+#ifndef BRO_DICT_SMEM
+#define BRO_DICT_SMEM 0
+#endif
+#define BRO_DICT_IMAGE_BYTES 122784u
 
 // A full warp per stream has worst-case arenas (it is also the retry kernel); experimental sub-warp groups
 // (-DBRO_GROUP_W=16|8) get 128 KiB each.
@@ -35,6 +42,11 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) bro_decode_warp_kernel(BroLa
     // one BroScratch per warp (6.7 KB with the general loop's on-chip tables: dynamic shared memory, 4 CTAs x 8 warps = 214 KB per SM)
     extern __shared__ __align__(16) uint8_t bro_smem_raw[];
     BroScratch* const scratch = (BroScratch*)bro_smem_raw;
+#if BRO_DICT_SMEM
+    uint8_t* const s_dict = bro_smem_raw + ((WARPS * BRO_GROUPS_PER_WARP * sizeof(BroScratch) + 15u) & ~(size_t)15);
+    for (unsigned i = threadIdx.x; i < BRO_DICT_IMAGE_BYTES / 16u; i += WARPS * 32) ((uint4*)s_dict)[i] = ((const uint4*)p.dict)[i];
+    __syncthreads();
+#endif
     const unsigned warp = threadIdx.x / BRO_W, lane = bro_lane();     // "warp" = group of BRO_W lanes
     const unsigned gwarp = blockIdx.x * (WARPS * BRO_GROUPS_PER_WARP) + warp;
     // retry pass of the two-phase path: only the streams the parse kernel handed over -- unless AUTO's gate sent the
@@ -64,7 +76,11 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) bro_decode_warp_kernel(BroLa
         d.arena = p.arena + (size_t)gwarp * BRO_GROUP_ARENA_U16;
         d.arena_cap = BRO_GROUP_ARENA_U16;
         d.arena_base = 0;
+#if BRO_DICT_SMEM
+        d.dict = s_dict;
+#else
         d.dict = p.dict;
+#endif
         d.out = p.out + out_b;
         uint64_t cap = out_e - out_b;
         d.cap = cap > BRO_MAX_SLOT ? (uint32_t)BRO_MAX_SLOT : (uint32_t)cap;
@@ -82,8 +98,10 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) bro_decode_warp_kernel(BroLa
     }
 }
 
+#ifndef BRO_WARPS_PER_CTA
 #define BRO_WARPS_PER_CTA 8
-#define BRO_WARP_KERNEL_SMEM (BRO_WARPS_PER_CTA * BRO_GROUPS_PER_WARP * sizeof(BroScratch))
+#endif
+#define BRO_WARP_KERNEL_SMEM (((BRO_WARPS_PER_CTA * BRO_GROUPS_PER_WARP * sizeof(BroScratch) + 15u) & ~(size_t)15) + (BRO_DICT_SMEM ? BRO_DICT_IMAGE_BYTES : 0u))
 
 // blocks_per_sm[0]: the throughput build, [1]: the latency build
 extern "C" int bro_warp_kernel_occupancy(int* blocks_per_sm) {

@@ -34,6 +34,9 @@
 #ifndef BRO_PARSE_LITS_PER_ROUND
 #define BRO_PARSE_LITS_PER_ROUND 8
 #endif
+#ifndef BRO_PARSE_LITS_LONG
+#define BRO_PARSE_LITS_LONG 64
+#endif
 
 // What bounded this kernel in round 1 was not instruction issue but the L2 / HBM round trips on a lane's critical path
 // (one per look-up in a table of the arena, one per access to local memory: the threads' stacks did not fit L1), and a
@@ -388,11 +391,17 @@ BRO_FN void bro_parse_round(BroDec& d, BroParse& ps, BroMbInfo& mb) {
     // input (a literal code has at most 15 bits) and no block switch is due, they need no checks at all.  This loop is
     // the critical path of a literal-heavy stream: every instruction in it is paid in full by a single lane.
     {
+        // a round serves up to BRO_PARSE_LITS_PER_ROUND literals per lane, so that lanes waiting for their distance code or
+        // their copy are not held up by a neighbour's long run -- unless no lane waits: then long runs go on (the round's
+        // other steps are pure overhead for a stream that is all literals)
+        const uint32_t per_round = bro_any(ps.kind == BRO_K_DIST || ps.kind == BRO_K_COPY) ? (uint32_t)BRO_PARSE_LITS_PER_ROUND : (uint32_t)BRO_PARSE_LITS_LONG;
         uint32_t fast = 0;
         if (ps.kind == BRO_K_LIT) {
-            uint32_t n = ps.ins_rem < BRO_PARSE_LITS_PER_ROUND ? ps.ins_rem : (uint32_t)BRO_PARSE_LITS_PER_ROUND;
+            uint32_t n = ps.ins_rem < per_round ? ps.ins_rem : per_round;
             if ((ps.multi & 1u) && ps.blen0 < n) n = ps.blen0;     // literals left in the current block (0: a switch is due)
-            if (d.pos <= d.cap && n <= d.cap - d.pos && bro_avail(d.in) >= 16u * n) fast = n;
+            const uint32_t room = d.pos <= d.cap ? d.cap - d.pos : 0u, safe = bro_avail(d.in) >> 4;
+            n = n < room ? n : room;
+            fast = n < safe ? n : safe;      // (whatever is left over -- or everything, when this is 0 -- is the general loop's)
         }
         const BroTl tl = d.scv.t;
         uint8_t* op = d.out + d.pos;
@@ -400,7 +409,7 @@ BRO_FN void bro_parse_round(BroDec& d, BroParse& ps, BroMbInfo& mb) {
         // two literals per slide of the window: after bro_refill the window holds 64 bits from a bit position < 32, and a
         // literal code has at most 15 bits, so the second literal of a pair still finds its bits (bro_peek_wide)
 #pragma unroll 1
-        for (uint32_t u = 0; u < BRO_PARSE_LITS_PER_ROUND; u += 2u) {
+        for (uint32_t u = 0; u < per_round; u += 2u) {
             if (!bro_any(u < fast)) break;
             if (u < fast) {
                 bro_refill(d.in);

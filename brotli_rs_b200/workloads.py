@@ -55,6 +55,13 @@ def synthetic_raw(kind, seed, size):
         return bytes(out[:size])
     if kind == "small_alpha":
         return bytes(rng.integers(0, 4, size, dtype=np.uint8))
+    if kind == "far_half":                    # round 2, C7: the second half repeats the first, size / 2 bytes back (far beyond
+        half = size // 2                      # what L2 keeps per stream), with 4 single-byte mutations per 2 KiB
+        a = rng.integers(0, 256, half, dtype=np.uint8)
+        b = a.copy()
+        idx = rng.integers(0, half, 4 * (half // 2048))
+        b[idx] = rng.integers(0, 256, len(idx), dtype=np.uint8)
+        return a.tobytes() + b.tobytes()
     raise ValueError(kind)
 
 
@@ -71,6 +78,9 @@ WORKLOADS = {
                          "synthetic 64 KiB-window high-ratio streams (2 KiB block x128, 4 mutations/rep, q5 lgwin16)"),
     "c5_stored_10k": ("random", 10000, 2000, 5, 16, "10,000 random bytes per stream -> stored meta-block (random_org_10k-like)"),
     "c5b_literals_10k": ("skewed", 10000, 2000, 5, 16, "10,000 skewed bytes per stream -> entropy-coded literals"),
+    # round 2 (VERDICT "decide with data"): far references in a large window (WBITS 22: copies 512 KiB back, stored first half)
+    "c7_far_w22": ("far_half", 1 << 20, 3000, 5, 22,
+                   "1 MiB per stream, second half = first half 512 KiB back with mutations (q5 lgwin22): far-source copies"),
 }
 
 

@@ -4,7 +4,7 @@ N=${1:-2}
 mkdir -p gpurun_out
 nvidia-smi -L | head -8
 timeout 600 python -m pytest tests/test_gpu_parity.py -m gpu -q -k "mg_decode" 2>&1 | tail -3 | tee gpurun_out/r2d_mg_pytest_$N.log
-timeout 1200 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus $N --steps 10 --warmup 3 > gpurun_out/r2d_bench_$N.json 2> gpurun_out/r2d_bench_$N.err
+timeout 700 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus $N --steps 10 --warmup 3 > gpurun_out/r2d_bench_$N.json 2> gpurun_out/r2d_bench_$N.err
 tail -3 gpurun_out/r2d_bench_$N.err
 python - <<PY
 import json
