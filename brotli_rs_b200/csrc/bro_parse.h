@@ -99,14 +99,15 @@ struct BroParse {
     // 65536 + base[k + 2] - base[k + 1] (base[L] = canonical index of the first code of length L minus its value), so
     // that ONE sum over the limits the next 15 bits reach yields both the code's length and its base (bro_parse_lit)
     uint32_t lit_lim[15], lit_dbb[15];
-    uint32_t lit_misc;        // max length | single flag << 8 | single symbol << 16
+    uint32_t lit_misc;        // max length | single flag << 8 | single symbol << 16 | bit 9: no code of 1..5 bits | bit 10: none of 11..15 bits
+    uint32_t lit_low;         // sum of lit_dbb[0..5) (what the five shortest lengths contribute when the code has none of them)
     int st;                   // final status once kind == BRO_K_DONE
 };
 
 BRO_FN void bro_parse_begin(BroParse& ps) {
     ps.kind = BRO_K_HEADER; ps.toff_cmd = 0; ps.toff_lit = 0; ps.ins_rem = 0; ps.copy_len = 0; ps.dcode = 0; ps.need_dist = 0;
     ps.mb_begin = 0; ps.mlen = 0; ps.blen0 = ps.blen1 = ps.blen2 = 0; ps.multi = 0; ps.is_last = 0; ps.started = 0; ps.st = 0;
-    ps.npostfix = 0; ps.ndirect = 0; ps.o_dist = 0; ps.lit_misc = 0;
+    ps.npostfix = 0; ps.ndirect = 0; ps.o_dist = 0; ps.lit_misc = 0; ps.lit_low = 5u * 65536u;
 #pragma unroll
     for (int i = 0; i < 15; i++) { ps.lit_lim[i] = 0; ps.lit_dbb[i] = 65536u; }
 }
@@ -180,6 +181,12 @@ BRO_FN void bro_parse_load_lit(BroParse& ps, BroTl t, const uint16_t* T) {
         prev = next;
     }
     ps.lit_misc = (uint32_t)T[BRO_T_MAXDEPTH] | (T[BRO_T_SINGLE] ? 0x100u : 0u) | ((uint32_t)T[BRO_T_SINGLE_SYM] << 16);
+    // Codes of real data use a band of lengths (the headline streams: 7..10 bits).  A length without codes below the band has
+    // limit 0 (always reached), one above it the limit 32768 (never reached): when that holds for a whole group of five
+    // lengths in every lane of the warp, the group's compares are skipped (bro_parse_lit)
+    if ((ps.lit_lim[0] | ps.lit_lim[1] | ps.lit_lim[2] | ps.lit_lim[3] | ps.lit_lim[4]) == 0u) ps.lit_misc |= 0x200u;
+    if (ps.lit_lim[9] == 32768u) ps.lit_misc |= 0x400u;      // limits grow with the length: all of 11..15 are 32768 too
+    ps.lit_low = ps.lit_dbb[0] + ps.lit_dbb[1] + ps.lit_dbb[2] + ps.lit_dbb[3] + ps.lit_dbb[4];
     // sorted[] starts 8 bytes into a 16-byte granule of the table record: 64 loads of four symbols, eight in flight
 #pragma unroll 8
     for (uint32_t i = 0; i < 64u; i++) {
@@ -197,14 +204,20 @@ BRO_FN void bro_parse_load_lit(BroParse& ps, BroTl t, const uint16_t* T) {
 // src/huffman/tree/mod.rs:63-92).  Canonical decode: the code's length is 1 + the number of limits the next 15 bits
 // (first bit most significant) reach, its symbol sits at base[length] + (bits >> (15 - length)) of the canonical order.
 // -> BRO_SYM_*; len = bits to consume (not consumed here: the caller knows whether `avail` must be checked).
-BRO_FN int bro_parse_lit(const BroParse& ps, BroTl t, uint32_t peek, uint32_t avail, uint32_t& sym, uint32_t& len) {
+BRO_FN int bro_parse_lit(const BroParse& ps, BroTl t, uint32_t peek, uint32_t avail, uint32_t& sym, uint32_t& len,
+                         bool skip_low = false, bool skip_high = false) {      // warp-uniform: see bro_parse_load_lit
     const uint32_t x = bro_brev(peek) >> 17;
     uint32_t acc0 = 0, acc1 = 0, acc2 = 0;                   // three partial sums: a shorter dependency chain
+    if (skip_low) acc0 = ps.lit_low;
+    else {
 #pragma unroll
-    for (uint32_t k = 0; k < 15u; k += 3u) {
-        if (x >= ps.lit_lim[k]) acc0 += ps.lit_dbb[k];
-        if (x >= ps.lit_lim[k + 1u]) acc1 += ps.lit_dbb[k + 1u];
-        if (x >= ps.lit_lim[k + 2u]) acc2 += ps.lit_dbb[k + 2u];
+        for (uint32_t k = 0; k < 5u; k++) if (x >= ps.lit_lim[k]) acc0 += ps.lit_dbb[k];
+    }
+#pragma unroll
+    for (uint32_t k = 5; k < 10u; k++) if (x >= ps.lit_lim[k]) acc1 += ps.lit_dbb[k];
+    if (!skip_high) {
+#pragma unroll
+        for (uint32_t k = 10; k < 15u; k++) if (x >= ps.lit_lim[k]) acc2 += ps.lit_dbb[k];
     }
     const uint32_t acc = acc0 + acc1 + acc2;
     const uint32_t count = (acc + 32768u) >> 16;             // limits reached (|base| < 32768)
@@ -406,6 +419,7 @@ BRO_FN void bro_parse_round(BroDec& d, BroParse& ps, BroMbInfo& mb) {
         const BroTl tl = d.scv.t;
         uint8_t* op = d.out + d.pos;
         uint32_t done = 0;
+        const bool skip_low = !bro_any(fast != 0u && !(ps.lit_misc & 0x200u)), skip_high = !bro_any(fast != 0u && !(ps.lit_misc & 0x400u));
         // two literals per slide of the window: after bro_refill the window holds 64 bits from a bit position < 32, and a
         // literal code has at most 15 bits, so the second literal of a pair still finds its bits (bro_peek_wide)
 #pragma unroll 1
@@ -414,13 +428,13 @@ BRO_FN void bro_parse_round(BroDec& d, BroParse& ps, BroMbInfo& mb) {
             if (u < fast) {
                 bro_refill(d.in);
                 uint32_t sym = 0, len = 0;
-                int r = bro_parse_lit(ps, tl, bro_peek(d.in), bro_avail(d.in), sym, len);
+                int r = bro_parse_lit(ps, tl, bro_peek(d.in), bro_avail(d.in), sym, len, skip_low, skip_high);
                 if (r == BRO_SYM_OK) {
                     bro_consume(d.in, len);
                     if (!d.sizing) op[u] = (uint8_t)sym;
                     done = u + 1u;
                     if (u + 1u < fast) {
-                        r = bro_parse_lit(ps, tl, bro_peek_wide(d.in), bro_avail(d.in), sym, len);
+                        r = bro_parse_lit(ps, tl, bro_peek_wide(d.in), bro_avail(d.in), sym, len, skip_low, skip_high);
                         if (r == BRO_SYM_OK) {
                             bro_consume(d.in, len);
                             if (!d.sizing) op[u + 1u] = (uint8_t)sym;
