@@ -204,8 +204,11 @@ BRO_FN void bro_parse_load_lit(BroParse& ps, BroTl t, const uint16_t* T) {
 // src/huffman/tree/mod.rs:63-92).  Canonical decode: the code's length is 1 + the number of limits the next 15 bits
 // (first bit most significant) reach, its symbol sits at base[length] + (bits >> (15 - length)) of the canonical order.
 // -> BRO_SYM_*; len = bits to consume (not consumed here: the caller knows whether `avail` must be checked).
-BRO_FN int bro_parse_lit(const BroParse& ps, BroTl t, uint32_t peek, uint32_t avail, uint32_t& sym, uint32_t& len,
-                         bool skip_low = false, bool skip_high = false) {      // warp-uniform: see bro_parse_load_lit
+// Split in two so that a caller can find the codes of several literals before it fetches their symbols (the look-ups then
+// overlap): bro_parse_lit_find -> `ref` = position in the canonical order (or 0x80000000 | the symbol of a one-symbol code),
+// bro_parse_lit_fetch -> the symbol.
+BRO_FN int bro_parse_lit_find(const BroParse& ps, uint32_t peek, uint32_t avail, uint32_t& ref, uint32_t& len,
+                              bool skip_low = false, bool skip_high = false) {      // warp-uniform: see bro_parse_load_lit
     const uint32_t x = bro_brev(peek) >> 17;
     uint32_t acc0 = 0, acc1 = 0, acc2 = 0;                   // three partial sums: a shorter dependency chain
     if (skip_low) acc0 = ps.lit_low;
@@ -224,13 +227,22 @@ BRO_FN int bro_parse_lit(const BroParse& ps, BroTl t, uint32_t peek, uint32_t av
     if (count >= 15u) {
         // no code starts with these bits: a one-symbol code (zero bits), or a hole / the end of the input
         len = 0;
-        if (ps.lit_misc & 0x100u) { sym = ps.lit_misc >> 16; return BRO_SYM_OK; }
+        if (ps.lit_misc & 0x100u) { ref = 0x80000000u | (ps.lit_misc >> 16); return BRO_SYM_OK; }
         return (avail >= (ps.lit_misc & 0xffu) + 1u) ? BRO_SYM_HOLE : BRO_SYM_EOF;
     }
     len = count + 1u;
     const int base = (int)(acc - (count << 16));
-    sym = bro_tl_ld8(t, BRO_TLB_LIT + ((uint32_t)(base + (int)(x >> (14u - count))) & 255u));
+    ref = (uint32_t)(base + (int)(x >> (14u - count))) & 255u;
     return BRO_SYM_OK;
+}
+BRO_FN uint32_t bro_parse_lit_fetch(BroTl t, uint32_t ref) {
+    return (ref & 0x80000000u) ? (ref & 0xffu) : bro_tl_ld8(t, BRO_TLB_LIT + ref);
+}
+BRO_FN int bro_parse_lit(const BroParse& ps, BroTl t, uint32_t peek, uint32_t avail, uint32_t& sym, uint32_t& len) {
+    uint32_t ref = 0;
+    const int r = bro_parse_lit_find(ps, peek, avail, ref, len);
+    if (r == BRO_SYM_OK) sym = bro_parse_lit_fetch(t, ref);
+    return r;
 }
 
 // The same with the end-of-input check, consuming the bits.
@@ -427,19 +439,20 @@ BRO_FN void bro_parse_round(BroDec& d, BroParse& ps, BroMbInfo& mb) {
             if (!bro_any(u < fast)) break;
             if (u < fast) {
                 bro_refill(d.in);
-                uint32_t sym = 0, len = 0;
-                int r = bro_parse_lit(ps, tl, bro_peek(d.in), bro_avail(d.in), sym, len, skip_low, skip_high);
+                uint32_t ref0 = 0, ref1 = 0, len = 0;
+                int r = bro_parse_lit_find(ps, bro_peek(d.in), bro_avail(d.in), ref0, len, skip_low, skip_high);
                 if (r == BRO_SYM_OK) {
                     bro_consume(d.in, len);
-                    if (!d.sizing) op[u] = (uint8_t)sym;
                     done = u + 1u;
                     if (u + 1u < fast) {
-                        r = bro_parse_lit(ps, tl, bro_peek_wide(d.in), bro_avail(d.in), sym, len, skip_low, skip_high);
-                        if (r == BRO_SYM_OK) {
-                            bro_consume(d.in, len);
-                            if (!d.sizing) op[u + 1u] = (uint8_t)sym;
-                            done = u + 2u;
-                        }
+                        r = bro_parse_lit_find(ps, bro_peek_wide(d.in), bro_avail(d.in), ref1, len, skip_low, skip_high);
+                        if (r == BRO_SYM_OK) { bro_consume(d.in, len); done = u + 2u; }
+                    }
+                    // both symbols are fetched once both codes are known: the two look-ups overlap
+                    if (!d.sizing) {
+                        const uint32_t sym0 = bro_parse_lit_fetch(tl, ref0), sym1 = done == u + 2u ? bro_parse_lit_fetch(tl, ref1) : 0u;
+                        op[u] = (uint8_t)sym0;
+                        if (done == u + 2u) op[u + 1u] = (uint8_t)sym1;
                     }
                 }
                 if (r != BRO_SYM_OK) { bro_parse_finish(ps, r == BRO_SYM_HOLE ? BRO_ST_ParseErrorInsertLiterals : BRO_ST_UnexpectedEOF); fast = 0; }

@@ -1,6 +1,6 @@
 #!/usr/bin/env python3
 """Top source lines of a kernel by executed warp instructions / stall samples, from an ncu report captured with
---import-source on (the kernel must be compiled with -lineinfo).  usage: ncu_lines.py report.ncu-rep [top N]"""
+--import-source on (the kernel must be compiled with -lineinfo).  usage: ncu_lines.py report.ncu-rep [top N] [kernel regex]"""
 import csv
 import io
 import subprocess
@@ -8,7 +8,8 @@ import sys
 
 rep = sys.argv[1]
 top = int(sys.argv[2]) if len(sys.argv) > 2 else 40
-out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "cuda,sass"], capture_output=True, text=True).stdout
+kern = ["-k", "regex:" + sys.argv[3]] if len(sys.argv) > 3 else []
+out = subprocess.run(["ncu", "-i", rep] + kern + ["--page", "source", "--csv", "--print-source", "cuda,sass"], capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(out)))
 lines = []
 cur_file = None
