@@ -95,26 +95,53 @@ def ncu_traffic(workload, algorithmic_bytes, kernel):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe).  The sampler is started before
+    the warm-up (nvidia-smi takes a few hundred ms to come up, longer with a process per rank on an 8-GPU box) and every row
+    carries its timestamp; the rows that fall inside the timed window are the ones reported.  A timed region shorter than the
+    sampling interval falls back to the rows of the warm-up that ran right before it under the same load, and says so."""
+    Q = ("timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    NAMES = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
 
     def __init__(self, gpu_index):
         self.gpu = gpu_index
         self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
         self.p = None
+        self.t0 = self.t1 = None
 
     def start(self):
+        if self.p is not None:
+            return
         try:
             self.p = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q,
-                                       "--format=csv,noheader,nounits", "-lms", "100"], stdout=self.f, stderr=subprocess.DEVNULL)
+                                       "--format=csv,noheader,nounits", "-lms", "25"], stdout=self.f, stderr=subprocess.DEVNULL)
         except Exception:
             self.p = None
+
+    def has_rows(self):
+        try:
+            return os.path.getsize(self.f.name) > 0
+        except OSError:
+            return False
+
+    def mark_begin(self):
+        self.t0 = time.time()
+
+    def mark_end(self):
+        self.t1 = time.time()
+
+    @staticmethod
+    def _when(text):
+        import datetime
+        try:
+            return datetime.datetime.strptime(text.strip(), "%Y/%m/%d %H:%M:%S.%f").timestamp()
+        except Exception:
+            return None
 
     def stop(self):
         if self.p is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
+        time.sleep(0.05)
         self.p.terminate()
         try:
             self.p.wait(timeout=5)
@@ -123,19 +150,37 @@ class ClockSampler:
         self.f.flush()
         rows = [r.split(",") for r in open(self.f.name).read().strip().splitlines() if r.strip()]
         os.unlink(self.f.name)
-        sm, smax, reasons = [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        parsed = []
         for r in rows:
             try:
-                sm.append(float(r[1])); smax.append(float(r[2]))
+                parsed.append((self._when(r[0]), float(r[1]), float(r[2]),
+                               [nm for k, nm in enumerate(self.NAMES) if len(r) > 5 + k and r[5 + k].strip().lower() == "active"]))
             except Exception:
                 continue
-            for k, nm in enumerate(names):
-                if len(r) > 5 + k and r[5 + k].strip().lower() == "active":
-                    reasons.add(nm)
-        if not sm:
+        inside = [p for p in parsed if p[0] is not None and self.t0 is not None and self.t0 <= p[0] <= self.t1]
+        window = "timed region"
+        if not inside:
+            inside, window = parsed, "warm-up + timed region (no nvidia-smi row fell inside the timed region itself)"
+        if not inside:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
-        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(smax)), "reasons": sorted(reasons), "samples": len(sm)}
+        return {"sm_mhz": float(np.median([p[1] for p in inside])), "sm_max_mhz": float(max(p[2] for p in inside)),
+                "reasons": sorted({nm for p in inside for nm in p[3]}), "samples": len(inside), "window": window}
+
+
+def combine_clocks(h, clocks):
+    """every rank sampled its own GPU: the line reports the slowest rank's median clock and the union of the throttle reasons"""
+    if h.world == 1:
+        return clocks
+    every = [None] * h.world
+    h.dist.all_gather_object(every, clocks)
+    have = [c for c in every if c.get("sm_mhz") is not None]
+    if not have:
+        return every[0]
+    out = {"sm_mhz": min(c["sm_mhz"] for c in have), "sm_max_mhz": max(c["sm_max_mhz"] for c in have),
+           "reasons": sorted({r for c in every for r in c["reasons"]}), "samples": sum(c["samples"] for c in have),
+           "window": have[0]["window"] if all(c["window"] == have[0]["window"] for c in have) else "mixed",
+           "ranks": "min of the ranks' median SM clocks; reasons of all %d ranks" % h.world}
+    return out
 
 
 DEFAULT_STREAMS = {"c6_text_q11_w16": 20000, "c7_far_w22": 8000, "c4_highratio_w16": 100000, "c5_stored_10k": 100000, "c5b_literals_10k": 100000,
@@ -356,18 +401,29 @@ class Batch:
         collective=False: a measurement of this rank alone (no barrier: the other ranks are not in it)"""
         h, torch = self.h, self.h.torch
         sync = h.barrier if collective else torch.cuda.synchronize
+        if sampler:
+            sampler.start()
         for _ in range(warmup):
             self.decode()
+        if sampler and sampler.p is not None:
+            # keep the load on (untimed) until nvidia-smi has delivered its first row, so that the timed region is sampled
+            for _ in range(400):
+                torch.cuda.synchronize()
+                if sampler.has_rows():
+                    break
+                self.decode()
         ev = [torch.cuda.Event(enable_timing=True) for _ in range(steps + 1)]
         sync()
         if sampler:
-            sampler.start()
+            sampler.mark_begin()
         launches0 = h.dec.launch_count
         ev[0].record()
         for k in range(steps):
             self.decode()
             ev[k + 1].record()
         sync()
+        if sampler:
+            sampler.mark_end()
         assert bool((self.d_st == self.want_st).all())
         return ev[0].elapsed_time(ev[-1]), [ev[k].elapsed_time(ev[k + 1]) for k in range(steps)], h.dec.launch_count - launches0
 
@@ -404,17 +460,40 @@ def quick_workload(h, name, steps, warmup):
 
 
 def pcie_ceiling(h, h_out, d_out, h_in, d_in):
-    """bare pinned cudaMemcpyAsync of the step's bytes (H2D then D2H, best of 3): what the link gives this rank"""
+    """bare pinned cudaMemcpyAsync of the step's bytes (H2D and D2H), EVERY rank at once: each of the 3 trials starts at a
+    barrier and counts as its slowest rank's time (the ranks share the host's memory and PCIe roots); best trial"""
     torch = h.torch
     best = 1e9
     for _ in range(3):
-        torch.cuda.synchronize()
+        h.barrier()
         t0 = time.perf_counter()
         d_in.copy_(h_in, non_blocking=True)
         h_out.copy_(d_out, non_blocking=True)
         torch.cuda.synchronize()
-        best = min(best, time.perf_counter() - t0)
+        best = min(best, h.max_over_ranks(time.perf_counter() - t0))
     return best
+
+
+def bind_to_gpu_numa_node(torch, local_rank):
+    """Run this rank's host threads (and so first-touch its pinned staging) on the NUMA node its GPU hangs off: with one
+    process per GPU on a two-socket box the copies otherwise cross the socket link.  -> a note for the bench line."""
+    try:
+        pr = torch.cuda.get_device_properties(local_rank)
+        bdf = "%04x:%02x:%02x.0" % (pr.pci_domain_id, pr.pci_bus_id, pr.pci_device_id)
+        node = int(open("/sys/bus/pci/devices/%s/numa_node" % bdf).read().strip())
+        if node < 0:
+            return "numa node of %s unknown: not bound" % bdf
+        cpus = set()
+        for part in open("/sys/devices/system/node/node%d/cpulist" % node).read().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if not cpus:
+            return "no allowed cpu on node %d: not bound" % node
+        os.sched_setaffinity(0, cpus)
+        return "host threads bound to NUMA node %d (%d cpus) of GPU %s" % (node, len(cpus), bdf)
+    except Exception as e:      # sysfs layout differs, no permission ...: measured unbound
+        return "not bound (%s)" % type(e).__name__
 
 
 def main():
@@ -445,7 +524,7 @@ def main():
     # ---- timed region: K launches, CUDA events on the launching stream ----
     sampler = ClockSampler(h.local_rank)
     total_ms, step_ms, launches = bt.timed(args.steps, args.warmup, sampler)
-    clocks = sampler.stop()
+    clocks = combine_clocks(h, sampler.stop())
     total_ms_max = h.max_over_ranks(total_ms)
     all_uncomp = h.sum_over_ranks(uncomp_bytes)
     all_comp = h.sum_over_ranks(comp_bytes)
@@ -585,6 +664,7 @@ def main():
         # Host memory for the end-to-end leg is bounded per BOX: with N ranks each pins 1/N of a BASELINE-size batch (at
         # weak scaling the first 1/N of its shard), so that N = 8 does not pin 8 x 26 GB.
         ne = n if (world == 1 or args.scaling == "strong") else max(1, n // world)
+        numa_note = bind_to_gpu_numa_node(torch, h.local_rank) if world > 1 else "single rank: not bound"
         e_in, e_out = int(in_off[ne]), int(out_off[ne])
         h_in = torch.empty(e_in, dtype=torch.uint8).pin_memory()
         h_in.copy_(bt.d_in[:e_in])
@@ -607,14 +687,16 @@ def main():
         e2e_t = h.max_over_ranks(t1 - t0)
         # what the link alone gives: the same bytes with bare pinned copies, all ranks at once
         h.barrier()
-        ceil_t = h.max_over_ranks(pcie_ceiling(h, h_out, bt.d_out[:e_out], h_in, bt.d_in[:e_in]))
+        ceil_t = pcie_ceiling(h, h_out, bt.d_out[:e_out], h_in, bt.d_in[:e_in])
         sum_uncomp = h.sum_over_ranks(e_uncomp)
         e2e = {"value": sum_uncomp * e2e_steps / e2e_t / 1e9, "unit": "GB/s",
                "h2d_bytes_per_step": int(e_in + 2 * 8 * (ne + 1)), "d2h_bytes_per_step": int(e_out + 12 * ne),
                "steps": e2e_steps, "streams_per_rank": int(ne), "api": "bro_batch_decode_host (pinned host buffers, per rank; "
                "slices of the batch: the copy out of slice k overlaps the decode of slice k + 1)",
                "ceiling_gbs": sum_uncomp / ceil_t / 1e9,
-               "ceiling": "the same H2D + D2H bytes as bare pinned cudaMemcpyAsync on every rank at once (best of 3), in the metric's unit",
+               "ceiling": "the same H2D + D2H bytes as bare pinned cudaMemcpyAsync on every rank at once (each trial from a barrier, "
+                          "its slowest rank; best of 3), in the metric's unit",
+               "numa": numa_note,
                "frac_of_ceiling": (sum_uncomp * e2e_steps / e2e_t) / (sum_uncomp / ceil_t)}
         del h_in, h_out
 
