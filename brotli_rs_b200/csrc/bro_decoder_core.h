@@ -790,6 +790,8 @@ struct BroDec {
     const uint32_t* ic;       // insert / copy length codes -> base | extra bits << 16 (bro_ic_lookup; shared memory)
     uint32_t out_mis;         // (address of out) & 15: pieces are cut at 16-byte boundaries of the destination ADDRESS
     uint32_t sizing;          // 1: only measure the stream (bro_batch_sizes): nothing is written, the slot is unbounded
+    uint32_t imm;             // 1: this stream's copies are executed by its own thread as they are decoded (no records): what a
+                              // meta-block WITH literal context modelling needs -- the two bytes in front of every literal
 #endif
 };
 
@@ -1575,6 +1577,7 @@ struct BroMbInfo {
     uint32_t npostfix, ndirect, ntl, ntd;
     uint32_t o_modes, o_cmap_l, o_cmap_d, o_lit, o_cmd, o_dist, dist_stride;
     bool simple;              // one literal / insert&copy / distance code and no block switches: no context modelling
+    bool lctx;                // (two-phase path) the literal code of a symbol depends on the two bytes in front of it
 };
 
 // Header of a compressed meta-block: block-type codes, NPOSTFIX/NDIRECT, context modes and maps, and all prefix code
@@ -1628,6 +1631,7 @@ BRO_FN int bro_metablock_tables(BroDec& d, BroMbInfo& mb) {
     uint8_t* cmap_l = (uint8_t*)(A + o_cmap_l);
     uint8_t* cmap_d = (uint8_t*)(A + o_cmap_d);
     uint32_t ntl = 1, ntd = 1;
+    bool lctx = false;
     for (uint32_t j = 0; j < 2u; j++) {
         uint32_t nt = 1;
         BRO_TRY(bro_read_nbltypes(d.in, nt));
@@ -1641,9 +1645,17 @@ BRO_FN int bro_metablock_tables(BroDec& d, BroMbInfo& mb) {
         // Phase one of the two-phase path never sees the bytes copies produce, so it can decode a meta-block only if
         // no block type's literal context map depends on the context; found out here, before the prefix codes
         // (the bulk of the header) are read.
-        if (!st && j == 0u && nt >= 2u)
+        if (!st && j == 0u && nt >= 2u) {
+            bool dep = false;
             for (uint32_t q = 0; q < 64u * cat[0].nbl; q++)
-                if (cmap_l[q] != cmap_l[q & ~63u]) st = BRO_ST_NeedFused;
+                if (cmap_l[q] != cmap_l[q & ~63u]) dep = true;
+            if (dep) {
+                // ... unless the thread executes the stream's copies itself (bro_parse.h, immediate mode): possible when
+                // nothing of the stream has been left to phase two yet, and not when the stream is only measured
+                if (d.sizing || (!d.imm && d.nrec != 0u)) st = BRO_ST_NeedFused;
+                else { d.imm = 1u; lctx = true; }
+            }
+        }
 #endif
     }
     // prefix codes (src/lib.rs:1016-1068): NTREESL literal codes, NBLTYPESI insert&copy codes, NTREESD distance codes
@@ -1664,8 +1676,8 @@ BRO_FN int bro_metablock_tables(BroDec& d, BroMbInfo& mb) {
             else { alphabet = dist_alphabet; T = A + o_dist + (i - n_l - n_i) * dist_stride; }
 #if defined(BRO_PARSE)
             // literal and insert&copy tables, and the distance table when there is one, are decoded canonically
-            // (bro_parse.h): no root
-            st = bro_read_prefix_code(d.in, sc, alphabet, T, i >= n_l + n_i && ntd >= 2u);
+            // (bro_parse.h): no root.  Literal codes chosen per context are looked up in the arena: root.
+            st = bro_read_prefix_code(d.in, sc, alphabet, T, i < n_l ? lctx : (i >= n_l + n_i && ntd >= 2u));
 #else
             st = bro_read_prefix_code(d.in, sc, alphabet, T);
 #endif
@@ -1680,6 +1692,7 @@ BRO_FN int bro_metablock_tables(BroDec& d, BroMbInfo& mb) {
     mb.o_modes = o_modes; mb.o_cmap_l = o_cmap_l; mb.o_cmap_d = o_cmap_d;
     mb.o_lit = o_lit; mb.o_cmd = o_cmd; mb.o_dist = o_dist; mb.dist_stride = dist_stride;
     mb.simple = ntl == 1u && ntd == 1u && cat[0].nbl == 1u && cat[1].nbl == 1u && cat[2].nbl == 1u;
+    mb.lctx = lctx;
     return st;
 }
 
@@ -1993,7 +2006,9 @@ BRO_FN int bro_next_metablock(BroDec& d, bool after_last, uint32_t& is_last, uin
                 if ((uint64_t)(d.in.end - a) < (uint64_t)mlen) return BRO_ST_UnexpectedEOF;
                 if (mlen > d.cap - d.pos) return BRO_ST_OutputTooSmall;
 #if defined(BRO_PARSE)
-                if (!bro_rec_push(d, d.pos, mlen, BRO_REC_STORED, (uint32_t)(a - d.in_base))) return BRO_ST_RecordsFull;
+                if (d.imm) {
+                    if (!d.sizing) for (uint32_t i = 0; i < mlen; i++) d.out[d.pos + i] = a[i];      // rare: a stored block between context-modelled ones
+                } else if (!bro_rec_push(d, d.pos, mlen, BRO_REC_STORED, (uint32_t)(a - d.in_base))) return BRO_ST_RecordsFull;
 #else
                 bro_syncwarp();
                 bro_copy_far(d.out + d.pos, a, mlen);

@@ -105,7 +105,7 @@ __global__ void __launch_bounds__(BRO_PARSE_BLOCK, BRO_PARSE_MIN_BLOCKS) bro_par
                             // this stream's share of the record arena: one record per 2 compressed bytes + 32
                             const uint64_t rec_b = BRO_REC_BASE(p.in_off, stream);
                             const uint64_t rec_n = BRO_REC_BASE(p.in_off, stream + 1) - rec_b;
-                            d.rec = p.rec + rec_b; d.nrec = 0; d.in_base = p.in + in_b;
+                            d.rec = p.rec + rec_b; d.nrec = 0; d.imm = 0; d.in_base = p.in + in_b;
                             d.rec_cap = rec_n > 0x0fffffffull ? 0x0fffffffu : (uint32_t)rec_n;
                             bro_bits_init(d.in, p.in + in_b, p.in + in_e);
                             bro_parse_begin(ps);

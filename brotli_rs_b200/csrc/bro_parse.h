@@ -14,9 +14,13 @@
 //     one per piece of at most 32 aligned 16-byte vectors (bro_rec_push); phase two (bro_kernels_copy.cu) executes the
 //     records of a stream in order, one warp per stream;
 //   * in sizing mode (bro_batch_sizes) nothing at all: only the decoded size of every stream.
-// Copies are never materialised here, so a meta-block whose literal context map really depends on the two previous
-// bytes (libbrotli quality >= 10) cannot be decoded by this path: the stream is handed to the fused warp kernel's
-// retry pass with BRO_ST_NeedFused (as are streams that outgrow the thread arena or their share of the record arena).
+// A meta-block whose literal context map really depends on the two previous bytes (libbrotli quality >= 10) needs the
+// bytes copies produce while it is decoded.  Such a stream is decoded in IMMEDIATE MODE: its thread executes every copy
+// itself as soon as it is decoded (no records: phase two has nothing to do for the stream), so the two bytes in front of
+// every literal are there -- its own stores, read back.  The mode is entered at the first such meta-block, provided the
+// stream has left nothing to phase two so far (otherwise, and in sizing mode, the stream is handed to the fused warp
+// kernel's retry pass with BRO_ST_NeedFused, as are streams that outgrow the thread arena or their share of the record
+// arena).  Per stream this is slower than the fused kernel's warp; per batch it is what 32 streams per warp buy.
 //
 // Include with BRO_THREAD_MODE (device) or BRO_HOSTSIM (CPU test-suite) and BRO_PARSE defined.
 #pragma once
@@ -91,7 +95,9 @@ struct BroParse {
     uint32_t need_dist;       // the command carries an explicit distance code (symbol >= 128)
     uint32_t mb_begin, mlen;  // meta-block: output position at its start, MLEN
     uint32_t blen0, blen1, blen2;   // symbols left in the current block per category (valid when the category has >= 2 types)
-    uint32_t multi;           // bit c: category c has >= 2 block types; bit 3: one distance table (its root is on chip)
+    uint32_t multi;           // bit c: category c has >= 2 block types; bit 3: one distance table (its root is on chip);
+                              // bit 4: literal codes are chosen per context (immediate mode: toff_lit = the context map row of
+                              // the current block type), bits 5-6: its context mode, bit 7: the context map is in the block
     uint32_t is_last;         // ISLAST of the current meta-block
     uint32_t started;         // the stream header has been read
     uint32_t npostfix, ndirect, o_dist;   // of the current meta-block (copies of BroMbInfo fields, which lives on the stack)
@@ -272,6 +278,43 @@ BRO_FN uint32_t bro_parse_table(const BroDec& d, const BroParse& ps, const BroMb
     return mb.o_dist + t * mb.dist_stride;
 }
 
+#define BRO_PM_LCTX 0x10u
+#define BRO_PM_CMAP_ONCHIP 0x80u
+// Literal codes chosen per context (src/lib.rs:1286-1365): the context map row and the context mode of the current literal
+// block type.  The map of up to four block types lives in the thread's block (where the literal symbols of a meta-block
+// without context modelling are), a larger one is read from the arena.
+BRO_FN void bro_parse_ctx_row(const BroDec& d, BroParse& ps, const BroMbInfo& mb) {
+    const uint32_t bt = mb.cat[0].btype;
+    const uint32_t mode = ((const uint8_t*)(d.arena + mb.o_modes))[bt] & 3u;
+    ps.multi = (ps.multi & ~0x60u) | (mode << 5);
+    ps.toff_lit = ((ps.multi & BRO_PM_CMAP_ONCHIP) ? BRO_TLB_LIT : 2u * mb.o_cmap_l) + 64u * bt;
+}
+
+// Immediate mode: an LZ77 back-reference executed by the stream's own thread (src/lib.rs:1483-1505).  A source that does
+// not overlap the next 8 bytes is moved 8 loads at a time; a short period is kept in a register.
+BRO_FN void bro_parse_copy_now(uint8_t* o, uint32_t distance, uint32_t len) {
+    const uint8_t* s = o - distance;
+    uint32_t k = 0;
+    if (distance >= 8u) {
+        for (; k + 8u <= len; k += 8u) {
+            uint32_t b[8];
+#pragma unroll
+            for (int i = 0; i < 8; i++) b[i] = s[k + (uint32_t)i];
+#pragma unroll
+            for (int i = 0; i < 8; i++) o[k + (uint32_t)i] = (uint8_t)b[i];
+        }
+        for (; k < len; k++) o[k] = s[k];
+    } else {
+        uint64_t pat = 0;
+        for (uint32_t i = 0; i < distance; i++) pat |= (uint64_t)s[i] << (8u * i);
+        uint32_t j = 0;
+        for (; k < len; k++) {
+            o[k] = (uint8_t)(pat >> (8u * j));
+            if (++j == distance) j = 0;
+        }
+    }
+}
+
 // Count the next symbol of category c against its current block; when the block is exhausted, read the block switch
 // (src/lib.rs:1182-1250).  Rare (blocks are hundreds of symbols long), so the switch itself is an out-of-line call.
 // Returns false when the stream ended with an error.
@@ -286,7 +329,10 @@ BRO_FN bool bro_parse_block_step(BroDec& d, BroParse& ps, BroMbInfo& mb, uint32_
         mb.cat[c] = tc;
         if (st) { bro_parse_finish(ps, st); return false; }
         bl = tc.blen + 1u;
-        if (c == 0u) { ps.toff_lit = bro_parse_table(d, ps, mb, 0u); bro_parse_load_lit(ps, d.scv.t, d.arena + ps.toff_lit); }
+        if (c == 0u) {
+            if (ps.multi & BRO_PM_LCTX) bro_parse_ctx_row(d, ps, mb);
+            else { ps.toff_lit = bro_parse_table(d, ps, mb, 0u); bro_parse_load_lit(ps, d.scv.t, d.arena + ps.toff_lit); }
+        }
         else if (c == 1u) { ps.toff_cmd = bro_parse_table(d, ps, mb, 1u); bro_parse_load_canon(d.scv.t, BRO_TLB_CMD_TAB, BRO_TLB_CMD_SYMS, BRO_CMD_ONCHIP, d.arena + ps.toff_cmd); }
     }
     bl -= 1u;
@@ -315,12 +361,27 @@ BRO_FN void bro_parse_header(BroDec& d, BroParse& ps, BroMbInfo& mb) {
         ps.is_last = is_last; ps.mlen = mlen; ps.mb_begin = d.pos;
         st = bro_metablock_tables(d, mb);
         if (!st) {
-            // (a literal context map that depends on the context has ended the stream with BRO_ST_NeedFused)
+            // (a literal context map that depends on the context has switched the stream to immediate mode -- mb.lctx --
+            // or ended it with BRO_ST_NeedFused)
             ps.multi = (mb.cat[0].nbl >= 2u ? 1u : 0u) | (mb.cat[1].nbl >= 2u ? 2u : 0u) | (mb.cat[2].nbl >= 2u ? 4u : 0u);
             ps.blen0 = mb.cat[0].blen; ps.blen1 = mb.cat[1].blen; ps.blen2 = mb.cat[2].blen;
             ps.toff_cmd = bro_parse_table(d, ps, mb, 1u);
-            ps.toff_lit = bro_parse_table(d, ps, mb, 0u);
-            bro_parse_load_lit(ps, d.scv.t, d.arena + ps.toff_lit);
+            if (mb.lctx) {
+                // immediate mode (the stream's copies so far were executed by this thread, or there were none): the
+                // context map into the block if it fits, the two bytes in front of the meta-block from the output
+                ps.multi |= BRO_PM_LCTX;
+                if (mb.cat[0].nbl <= 4u) {
+                    ps.multi |= BRO_PM_CMAP_ONCHIP;
+                    for (uint32_t w = 0; w < 16u * mb.cat[0].nbl; w++)
+                        bro_tl_st32(d.scv.t, BRO_TLB_LIT + 4u * w, ((const uint32_t*)(d.arena + mb.o_cmap_l))[w]);
+                }
+                bro_parse_ctx_row(d, ps, mb);
+                d.p1 = d.pos >= 1u ? d.out[d.pos - 1u] : 0u;
+                d.p2 = d.pos >= 2u ? d.out[d.pos - 2u] : 0u;
+            } else {
+                ps.toff_lit = bro_parse_table(d, ps, mb, 0u);
+                bro_parse_load_lit(ps, d.scv.t, d.arena + ps.toff_lit);
+            }
             bro_parse_load_canon(d.scv.t, BRO_TLB_CMD_TAB, BRO_TLB_CMD_SYMS, BRO_CMD_ONCHIP, d.arena + ps.toff_cmd);
             if (mb.ntd == 1u) { ps.multi |= 8u; bro_parse_load_canon(d.scv.t, BRO_TLB_DIST_TAB, BRO_TLB_DIST_SYMS, BRO_DIST_ONCHIP, d.arena + mb.o_dist); }
             ps.npostfix = mb.npostfix; ps.ndirect = mb.ndirect; ps.o_dist = mb.o_dist;
@@ -421,7 +482,7 @@ BRO_FN void bro_parse_round(BroDec& d, BroParse& ps, BroMbInfo& mb) {
         // other steps are pure overhead for a stream that is all literals)
         const uint32_t per_round = bro_any(ps.kind == BRO_K_DIST || ps.kind == BRO_K_COPY) ? (uint32_t)BRO_PARSE_LITS_PER_ROUND : (uint32_t)BRO_PARSE_LITS_LONG;
         uint32_t fast = 0;
-        if (ps.kind == BRO_K_LIT) {
+        if (ps.kind == BRO_K_LIT && !(ps.multi & BRO_PM_LCTX)) {
             uint32_t n = ps.ins_rem < per_round ? ps.ins_rem : per_round;
             if ((ps.multi & 1u) && ps.blen0 < n) n = ps.blen0;     // literals left in the current block (0: a switch is due)
             const uint32_t room = d.pos <= d.cap ? d.cap - d.pos : 0u, safe = bro_avail(d.in) >> 4;
@@ -468,7 +529,7 @@ BRO_FN void bro_parse_round(BroDec& d, BroParse& ps, BroMbInfo& mb) {
     // General loop: the lanes the fast loop could not take (near the end of the slot or of the input, block switches)
 #pragma unroll 1
     for (int u = 0; u < BRO_PARSE_LITS_PER_ROUND; u++) {
-        const bool slow = ps.kind == BRO_K_LIT && (((ps.multi & 1u) && ps.blen0 == 0u) || d.pos > d.cap || ps.ins_rem > d.cap - d.pos || bro_avail(d.in) < 16u * BRO_PARSE_LITS_PER_ROUND);
+        const bool slow = ps.kind == BRO_K_LIT && !(ps.multi & BRO_PM_LCTX) && (((ps.multi & 1u) && ps.blen0 == 0u) || d.pos > d.cap || ps.ins_rem > d.cap - d.pos || bro_avail(d.in) < 16u * BRO_PARSE_LITS_PER_ROUND);
         if (!bro_any(slow)) break;
         if (slow && bro_parse_block_step(d, ps, mb, 0u)) {
             uint32_t sym = 0;
@@ -479,6 +540,35 @@ BRO_FN void bro_parse_round(BroDec& d, BroParse& ps, BroMbInfo& mb) {
                 if (d.pos < d.cap && !d.sizing) d.out[d.pos] = (uint8_t)sym;
                 d.pos += 1;
                 if (--ps.ins_rem == 0u) bro_parse_after_literals(d, ps);
+            }
+        }
+    }
+    // Context loop (immediate mode): the code of every literal is chosen by the two bytes in front of it (src/lib.rs:1286-1365);
+    // its table is looked up in the arena (8-bit root + canonical search, as the fused kernel does)
+    if (bro_any(ps.kind == BRO_K_LIT && (ps.multi & BRO_PM_LCTX))) {
+        const uint32_t per_round = bro_any(ps.kind == BRO_K_DIST || ps.kind == BRO_K_COPY) ? (uint32_t)BRO_PARSE_LITS_PER_ROUND : (uint32_t)BRO_PARSE_LITS_LONG;
+#pragma unroll 1
+        for (uint32_t u = 0; u < per_round; u++) {
+            const bool cx = ps.kind == BRO_K_LIT && (ps.multi & BRO_PM_LCTX);
+            if (!bro_any(cx)) break;
+            if (cx && bro_parse_block_step(d, ps, mb, 0u)) {
+                const uint32_t mode = (ps.multi >> 5) & 3u;
+                uint32_t cid;
+                if (mode == 0u) cid = d.p1 & 0x3fu;
+                else if (mode == 1u) cid = d.p1 >> 2;
+                else if (mode == 2u) cid = (uint32_t)bro_lut0[d.p1] | bro_lut1[d.p2];
+                else cid = ((uint32_t)bro_lut2[d.p1] << 3) | bro_lut2[d.p2];
+                const uint32_t t = (ps.multi & BRO_PM_CMAP_ONCHIP) ? bro_tl_ld8(d.scv.t, ps.toff_lit + cid) : ((const uint8_t*)d.arena)[ps.toff_lit + cid];
+                uint32_t sym = 0;
+                const int r = bro_decode_sym(d.in, d.arena + mb.o_lit + t * BRO_TREE_U16(BRO_ALPHA_LIT), sym);
+                if (r != BRO_SYM_OK) bro_parse_finish(ps, r == BRO_SYM_HOLE ? BRO_ST_ParseErrorInsertLiterals : BRO_ST_UnexpectedEOF);
+                else {
+                    // a run that does not fit the slot is still decoded: a decode error inside it wins over OutputTooSmall
+                    if (d.pos < d.cap) d.out[d.pos] = (uint8_t)sym;
+                    d.pos += 1;
+                    d.p2 = d.p1; d.p1 = sym;
+                    if (--ps.ins_rem == 0u) bro_parse_after_literals(d, ps);
+                }
             }
         }
     }
@@ -500,6 +590,12 @@ BRO_FN void bro_parse_round(BroDec& d, BroParse& ps, BroMbInfo& mb) {
                 // an LZ77 back-reference: phase two materialises it
                 if (ps.mlen < mb_out + copy_len) st = BRO_ST_ExceededExpectedBytes;                              // src/lib.rs:2105-2108
                 else if (copy_len > d.cap - d.pos) st = BRO_ST_OutputTooSmall;
+                else if (d.imm) {
+                    // immediate mode: the copy itself, and the two bytes the next literal's context is made of (copy_len >= 2)
+                    bro_parse_copy_now(d.out + d.pos, distance, copy_len);
+                    d.pos += copy_len;
+                    d.p1 = d.out[d.pos - 1u]; d.p2 = d.out[d.pos - 2u];
+                }
                 else if (!bro_rec_push(d, d.pos, copy_len, BRO_REC_LZ, distance)) st = BRO_ST_RecordsFull;
                 else d.pos += copy_len;
             } else if (copy_len < 4u || copy_len > 24u) st = BRO_ST_InvalidLengthInStaticDictionary;
@@ -518,6 +614,10 @@ BRO_FN void bro_parse_round(BroDec& d, BroParse& ps, BroMbInfo& mb) {
                     else {
                         if (!d.sizing) bro_parse_dict_emit(d.out + d.pos, d.dict, copy_len, index, tid, from, wl);
                         d.pos += (uint32_t)n;
+                        if (ps.multi & BRO_PM_LCTX) {
+                            d.p1 = d.pos >= 1u ? d.out[d.pos - 1u] : 0u;
+                            d.p2 = d.pos >= 2u ? d.out[d.pos - 2u] : 0u;
+                        }
                     }
                 }
             }

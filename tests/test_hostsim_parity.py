@@ -146,6 +146,41 @@ def test_parse_fresh_streams():
             assert st in hostsim.RETRY or (st, out) == (0, raw), (name, q, st)
 
 
+def test_parse_immediate_mode():
+    """literal context modelling (libbrotli quality >= 10) inside phase one: the stream's thread executes its copies itself
+    (no records) and reads the two context bytes back -- text at quality 10 / 11, and mutations of those streams against the
+    oracle, status by status"""
+    import os
+    from conftest import DATA
+    enc = fuzzgen.libbrotli_enc()
+    if enc is None:
+        pytest.skip("system libbrotlienc not present")
+    streams = []
+    for name, q, lgwin in (("alice29.txt", 11, 16), ("alice29.txt", 10, 22), ("asyoulik.txt", 11, 22), ("lcet10.txt", 11, 18)):
+        raw = open(os.path.join(DATA, name), "rb").read()[:120000]
+        comp = fuzzgen.compress(enc, raw, q, lgwin)
+        st, out, nrec, steps = hostsim.parse_decode(comp, cap=len(raw))
+        assert (st, out, nrec) == (0, raw, 0), (name, q, lgwin, st, nrec)
+        streams.append(comp)
+        # a slot that is too small, by one byte and by a lot
+        for cap in (len(raw) - 1, len(raw) // 3):
+            st0, out0 = _oracle_slot(comp, cap)
+            st1, out1, _, _ = hostsim.parse_decode(comp, cap=cap)
+            assert st1 == st0, (name, cap, st0, st1)
+    rng = np.random.default_rng(97)
+    seen, handled = set(), 0
+    for m in fuzzgen.mutations(streams, seed=8, count=1200, max_len=60000):
+        st, out = oracle.decode(m)
+        cap = len(out) if st == 0 else len(out) + (1 << 20)
+        if rng.random() < 0.25:
+            cap = int(rng.integers(0, len(out) + 100))
+        st0, out0 = _oracle_slot(m, cap)
+        if _parse_check(m, cap, st0, out0, (m[:16].hex(), len(m), cap)):
+            handled += 1
+            seen.add(st0)
+    assert handled >= 900 and len(seen) >= 8, (handled, sorted(seen))
+
+
 def test_parse_record_arena_overflow():
     """a stream with more copies than its share of the record arena is handed to the fused kernel"""
     enc = fuzzgen.libbrotli_enc()
