@@ -123,6 +123,14 @@ BRO_FN uint32_t bro_funnel_r(uint32_t lo, uint32_t hi, unsigned sh) { return __f
 #define BRO_T_MAXDEPTH (BRO_ROOT_SIZE + 34u)
 #define BRO_T_SORTED (BRO_ROOT_SIZE + 36u)
 #define BRO_TREE_U16(alphabet) (((BRO_T_SORTED + (alphabet)) + 7u) & ~7u)
+// Distance between the literal tables of a meta-block.  The two-phase path looks tables of context-modelled literals up in
+// the arena (bro_parse.h): there a table starts on a 128-byte line (the first 64 root entries = the line a stream keeps hot;
+// L2 allocates whole lines, so a hot sector in a line of cold ones costs four times its size).
+#if defined(BRO_PARSE)
+#define BRO_LIT_STRIDE_U16 ((BRO_TREE_U16(BRO_ALPHA_LIT) + 63u) & ~63u)
+#else
+#define BRO_LIT_STRIDE_U16 BRO_TREE_U16(BRO_ALPHA_LIT)
+#endif
 
 // largest output slot one stream may use: positions are 32-bit and one command may add up to 2 * (2^24 + 22594) bytes
 #define BRO_MAX_SLOT 0xf0000000ull
@@ -1662,7 +1670,10 @@ BRO_FN int bro_metablock_tables(BroDec& d, BroMbInfo& mb) {
     const uint32_t dist_alphabet = 16u + ndirect + (48u << npostfix);
     const uint32_t dist_stride = BRO_TREE_U16(dist_alphabet);
     uint32_t o_lit = 0, o_cmd = 0, o_dist = 0;
-    BRO_ALLOC(o_lit, ntl * BRO_TREE_U16(BRO_ALPHA_LIT));
+#if defined(BRO_PARSE)
+    top = (top + 63u) & ~63u;
+#endif
+    BRO_ALLOC(o_lit, ntl * BRO_LIT_STRIDE_U16);
     BRO_ALLOC(o_cmd, cat[1].nbl * BRO_TREE_U16(BRO_ALPHA_CMD));
     BRO_ALLOC(o_dist, ntd * dist_stride);
 #undef BRO_ALLOC
@@ -1671,7 +1682,7 @@ BRO_FN int bro_metablock_tables(BroDec& d, BroMbInfo& mb) {
         for (uint32_t i = 0; !st && i < total; i++) {
             uint32_t alphabet;
             uint16_t* T;
-            if (i < n_l) { alphabet = BRO_ALPHA_LIT; T = A + o_lit + i * BRO_TREE_U16(BRO_ALPHA_LIT); }
+            if (i < n_l) { alphabet = BRO_ALPHA_LIT; T = A + o_lit + i * BRO_LIT_STRIDE_U16; }
             else if (i < n_l + n_i) { alphabet = BRO_ALPHA_CMD; T = A + o_cmd + (i - n_l) * BRO_TREE_U16(BRO_ALPHA_CMD); }
             else { alphabet = dist_alphabet; T = A + o_dist + (i - n_l - n_i) * dist_stride; }
 #if defined(BRO_PARSE)
@@ -1802,7 +1813,7 @@ BRO_FN int bro_commands_general(BroDec& d, BroScratch& sc, uint32_t mlen, BroMbI
                     else cid = ((uint32_t)bro_lut2[d.p1] << 3) | bro_lut2[d.p2];
                     t = cmap_l[bt * 64u + cid];
                 }
-                const uint16_t* T = T_lit + t * BRO_TREE_U16(BRO_ALPHA_LIT);
+                const uint16_t* T = T_lit + t * BRO_LIT_STRIDE_U16;
                 uint32_t lit;
                 if (one_lit) r = bro_decode_sym2(d.in, sc.root_lit, T, lit);
                 else if (hot.rb_lit) r = bro_decode_sym_hot(d.in, sc.hot_lit + (t << hot.rb_lit), hot.rb_lit, T, lit);
@@ -1887,7 +1898,7 @@ BRO_FN BroHot bro_stage_hot(BroDec& d, BroScratch& sc, const BroMbInfo& mb) {
     hot.cmap_l = mb.ntl >= 2u && 64u * nl <= BRO_HOT_CMAP_L;
     hot.cmap_d = mb.ntd >= 2u && 4u * nd <= BRO_HOT_CMAP_D;
     hot.modes = nl <= BRO_HOT_MODES;
-    if (hot.rb_lit) bro_stage_narrow(sc.hot_lit, d.arena + mb.o_lit, BRO_TREE_U16(BRO_ALPHA_LIT), mb.ntl, hot.rb_lit);
+    if (hot.rb_lit) bro_stage_narrow(sc.hot_lit, d.arena + mb.o_lit, BRO_LIT_STRIDE_U16, mb.ntl, hot.rb_lit);
     if (hot.rb_cmd) bro_stage_narrow(sc.root_cmd, d.arena + mb.o_cmd, BRO_TREE_U16(BRO_ALPHA_CMD), ni, hot.rb_cmd);
     if (hot.rb_dist) bro_stage_narrow(sc.root_dist, d.arena + mb.o_dist, mb.dist_stride, mb.ntd, hot.rb_dist);
     if (hot.cmap_l) for (uint32_t i = lane; i < 64u * nl; i += BRO_W) sc.hot_cmap_l[i] = ((const uint8_t*)(d.arena + mb.o_cmap_l))[i];

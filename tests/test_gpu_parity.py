@@ -314,6 +314,38 @@ def test_parse_handover_is_retried_by_warp_kernel(dec):
         assert st == 0 and out == r, (i, st)
 
 
+def test_context_modelled_streams_immediate_mode():
+    """libbrotli quality 10 / 11 text (literal context modelling) is decoded by the two-phase path ITSELF: the parse kernel's
+    thread executes the stream's copies and reads the context bytes back (immediate mode), nothing is handed to the fused
+    kernel; mutations of the same streams against the oracle, status by status"""
+    from brotli_rs_b200 import BatchDecoder
+    enc = fuzzgen.libbrotli_enc()
+    if enc is None:
+        pytest.skip("system libbrotlienc not present")
+    streams, raws = [], []
+    rng = np.random.default_rng(3)
+    for name in ("alice29.txt", "asyoulik.txt", "lcet10.txt", "plrabn12.txt"):
+        text = open(os.path.join(DATA, name), "rb").read()
+        for q, lgwin in ((11, 16), (10, 22), (11, 22), (11, 18)):
+            for size in (3000, 40000, 140000):
+                o = int(rng.integers(0, max(1, len(text) - size)))
+                raw = text[o: o + size]
+                streams.append(fuzzgen.compress(enc, raw, q, lgwin)); raws.append(raw)
+    d = BatchDecoder(0, mode=BatchDecoder.MODE_TWOPHASE)
+    res = d.decode_streams(streams * 8, [len(r) for r in raws] * 8)
+    for i, ((st, out), r) in enumerate(zip(res, raws * 8)):
+        assert st == 0 and out == r, (i, st)
+    assert d.last_batch_stats()["retried_streams"] == 0
+    muts = list(fuzzgen.mutations(streams, seed=12, count=1500, max_len=60000))
+    caps = []
+    for m in muts:
+        st, out = oracle.decode(m)
+        caps.append(len(out) if (st == 0 and rng.random() < 0.75) else int(rng.integers(0, len(out) + 100)) if rng.random() < 0.5 else len(out) + 4096)
+    status = check_batch(d, muts, caps, "context-modelled mutations")
+    assert len(set(int(x) for x in status)) >= 8
+    d.close()
+
+
 def test_auto_mode_launch_counts(monkeypatch):
     """default mode decodes a small batch of small streams with ONE launch of the warp kernel and a large one by the
     two-phase path: 3 ordering kernels, the parse kernel, the copy kernel and the fused kernel's retry pass (per slice of
