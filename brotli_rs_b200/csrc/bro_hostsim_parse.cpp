@@ -80,7 +80,7 @@ extern "C" int bro_hostsim_parse_decode(const uint8_t* in, size_t in_len, uint8_
     unsigned steps = 0;
     while (ps.kind != BRO_K_DONE) {
         if (ps.kind == BRO_K_HEADER) bro_parse_header(d, ps, mb);
-        else { bro_parse_round(d, ps, mb); steps++; }
+        else { if (d.imm) bro_parse_round<true>(d, ps, mb); else bro_parse_round<false>(d, ps, mb); steps++; }
     }
     // phase two, the obvious way
     if (ps.st == BRO_ST_OK && !g_sizing && g_copy_group) {

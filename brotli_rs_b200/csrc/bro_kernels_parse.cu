@@ -50,6 +50,7 @@ __global__ void __launch_bounds__(BRO_PARSE_BLOCK, BRO_PARSE_MIN_BLOCKS) bro_par
     uint32_t stream = 0;
     uint32_t waited = 0;          // warp-uniform: trips since the first lane reached a boundary
     bool exhausted = false;       // warp-uniform: the queue is empty
+    bool warp_imm = false;        // warp-uniform: some lane decodes its stream in immediate mode (only a header changes that)
     ps.kind = BRO_K_DONE; ps.st = -1;   // st < 0: no stream to report
     {
         BroTl tl;
@@ -116,9 +117,11 @@ __global__ void __launch_bounds__(BRO_PARSE_BLOCK, BRO_PARSE_MIN_BLOCKS) bro_par
                 }
                 if (__all_sync(0xffffffffu, ps.kind == BRO_K_DONE && ps.st < 0)) break;
                 if (ps.kind == BRO_K_HEADER) bro_parse_header(d, ps, mb);
+                warp_imm = __any_sync(0xffffffffu, ps.kind < BRO_K_HEADER && d.imm != 0u) != 0;
             }
         } else waited = 0;
-        bro_parse_round(d, ps, mb);
+        if (warp_imm) bro_parse_round<true>(d, ps, mb);
+        else bro_parse_round<false>(d, ps, mb);
     }
 }
 

@@ -33,6 +33,7 @@
 #define BRO_K_LIT 1u       // next: a literal                                (src/lib.rs:1286-1365)
 #define BRO_K_DIST 2u      // next: a distance code                          (src/lib.rs:1367-1410)
 #define BRO_K_COPY 3u      // next: distance resolution and the copy itself  (src/lib.rs:1412-1542)
+#define BRO_K_LITX 4u      // next: a literal whose code is chosen by the two bytes in front of it (immediate mode)
 #define BRO_K_HEADER 6u    // at a meta-block boundary (or before the stream header): structured code
 #define BRO_K_DONE 7u      // no stream
 #ifndef BRO_PARSE_LITS_PER_ROUND
@@ -506,6 +507,9 @@ BRO_FN void bro_parse_dict_emit(uint8_t* o, const uint8_t* dict, uint32_t copy_l
 // insert&copy symbol, up to BRO_PARSE_LITS_PER_ROUND of its literals, its distance code, its copy -- in four steps
 // that the lanes of a warp execute together, each lane taking part in the steps its state calls for.  There is no
 // early exit inside a step (an error parks the lane in BRO_K_DONE), so the lanes meet again after every step.
+// IMM = false: no lane of the warp is in immediate mode (warp-uniform, known after the headers): the code of that mode is
+// compiled out, so that batches without context modelling run exactly the loop they ran before the mode existed.
+template <bool IMM>
 BRO_FN void bro_parse_round(BroDec& d, BroParse& ps, BroMbInfo& mb) {
     // ---- step 1: insert&copy command symbol and its extra bits ----
     if (ps.kind == BRO_K_CMD && bro_parse_block_step(d, ps, mb, 1u)) {
@@ -531,7 +535,7 @@ BRO_FN void bro_parse_round(BroDec& d, BroParse& ps, BroMbInfo& mb) {
             else if (ps.mlen < (d.pos - ps.mb_begin) + insert_len) bro_parse_finish(ps, BRO_ST_ExceededExpectedBytes);   // src/lib.rs:2036-2039
             else {
                 ps.ins_rem = insert_len; ps.copy_len = copy_len; ps.need_dist = sym >= 128u; ps.dcode = 0;
-                if (insert_len != 0u) ps.kind = BRO_K_LIT;
+                if (insert_len != 0u) ps.kind = (IMM && (ps.multi & BRO_PM_LCTX)) ? BRO_K_LITX : BRO_K_LIT;
                 else bro_parse_after_literals(d, ps);
             }
         }
@@ -546,7 +550,7 @@ BRO_FN void bro_parse_round(BroDec& d, BroParse& ps, BroMbInfo& mb) {
         // other steps are pure overhead for a stream that is all literals)
         const uint32_t per_round = bro_any(ps.kind == BRO_K_DIST || ps.kind == BRO_K_COPY) ? (uint32_t)BRO_PARSE_LITS_PER_ROUND : (uint32_t)BRO_PARSE_LITS_LONG;
         uint32_t fast = 0;
-        if (ps.kind == BRO_K_LIT && !(ps.multi & BRO_PM_LCTX)) {
+        if (ps.kind == BRO_K_LIT) {
             uint32_t n = ps.ins_rem < per_round ? ps.ins_rem : per_round;
             if ((ps.multi & 1u) && ps.blen0 < n) n = ps.blen0;     // literals left in the current block (0: a switch is due)
             const uint32_t room = d.pos <= d.cap ? d.cap - d.pos : 0u, safe = bro_avail(d.in) >> 4;
@@ -593,7 +597,7 @@ BRO_FN void bro_parse_round(BroDec& d, BroParse& ps, BroMbInfo& mb) {
     // General loop: the lanes the fast loop could not take (near the end of the slot or of the input, block switches)
 #pragma unroll 1
     for (int u = 0; u < BRO_PARSE_LITS_PER_ROUND; u++) {
-        const bool slow = ps.kind == BRO_K_LIT && !(ps.multi & BRO_PM_LCTX) && (((ps.multi & 1u) && ps.blen0 == 0u) || d.pos > d.cap || ps.ins_rem > d.cap - d.pos || bro_avail(d.in) < 16u * BRO_PARSE_LITS_PER_ROUND);
+        const bool slow = ps.kind == BRO_K_LIT && (((ps.multi & 1u) && ps.blen0 == 0u) || d.pos > d.cap || ps.ins_rem > d.cap - d.pos || bro_avail(d.in) < 16u * BRO_PARSE_LITS_PER_ROUND);
         if (!bro_any(slow)) break;
         if (slow && bro_parse_block_step(d, ps, mb, 0u)) {
             uint32_t sym = 0;
@@ -609,11 +613,11 @@ BRO_FN void bro_parse_round(BroDec& d, BroParse& ps, BroMbInfo& mb) {
     }
     // Context loop (immediate mode): the code of every literal is chosen by the two bytes in front of it (src/lib.rs:1286-1365);
     // its table is looked up in the arena (8-bit root + canonical search, as the fused kernel does)
-    if (bro_any(ps.kind == BRO_K_LIT && (ps.multi & BRO_PM_LCTX))) {
+    if (IMM && bro_any(ps.kind == BRO_K_LITX)) {
         const uint32_t per_round = bro_any(ps.kind == BRO_K_DIST || ps.kind == BRO_K_COPY) ? (uint32_t)BRO_PARSE_LITS_PER_ROUND : (uint32_t)BRO_PARSE_LITS_LONG;
 #pragma unroll 1
         for (uint32_t u = 0; u < per_round; u++) {
-            const bool cx = ps.kind == BRO_K_LIT && (ps.multi & BRO_PM_LCTX);
+            const bool cx = ps.kind == BRO_K_LITX;
             if (!bro_any(cx)) break;
             if (cx && bro_parse_block_step(d, ps, mb, 0u)) {
                 const uint32_t mode = (ps.multi >> 5) & 3u;
@@ -654,7 +658,7 @@ BRO_FN void bro_parse_round(BroDec& d, BroParse& ps, BroMbInfo& mb) {
                 // an LZ77 back-reference: phase two materialises it
                 if (ps.mlen < mb_out + copy_len) st = BRO_ST_ExceededExpectedBytes;                              // src/lib.rs:2105-2108
                 else if (copy_len > d.cap - d.pos) st = BRO_ST_OutputTooSmall;
-                else if (d.imm) {
+                else if (IMM && d.imm) {
                     // immediate mode: the copy itself; it leaves the two bytes the next literal's context is made of (copy_len >= 2)
                     bro_parse_copy_now(d.out + d.pos, distance, copy_len, d.p1, d.p2);
                     d.pos += copy_len;
@@ -677,7 +681,7 @@ BRO_FN void bro_parse_round(BroDec& d, BroParse& ps, BroMbInfo& mb) {
                     else {
                         if (!d.sizing) bro_parse_dict_emit(d.out + d.pos, d.dict, copy_len, index, tid, from, wl);
                         d.pos += (uint32_t)n;
-                        if (ps.multi & BRO_PM_LCTX) {
+                        if (IMM && (ps.multi & BRO_PM_LCTX)) {
                             d.p1 = d.pos >= 1u ? d.out[d.pos - 1u] : 0u;
                             d.p2 = d.pos >= 2u ? d.out[d.pos - 2u] : 0u;
                         }
