@@ -203,7 +203,7 @@ def build_workload(name, n_streams):
         gidx = np.zeros(n_streams, dtype=np.int64)
     elif name == "c6_text_q11_w16":
         # round 2 (VERDICT "decide with data"): alice29.txt at quality 11, lgwin 16 -- context-modelled, 11 % of the output from
-        # the static dictionary: the fused kernel's general loop and bro_dict_word
+        # the static dictionary: the parse kernel's immediate mode (bro_parse.h), or the fused kernel's general loop (--mode warp)
         raw = open(os.path.join(data, "alice29.txt"), "rb").read()
         enc = w.libbrotli_enc()
         streams, raws, status = [w.compress(enc, raw, 11, 16)], [raw], [0]
@@ -715,7 +715,8 @@ def main():
     if args.extra_workloads and args.workload == "c4_highratio_w16":
         del bt
         torch.cuda.empty_cache()
-        names_x = ["c2_quickfox_x10k", "c3_corpus_x1000", "c5_stored_10k", "c5b_literals_10k"] if world == 1 else ["c5_stored_10k"]
+        names_x = ["c1_alice29_single", "c2_quickfox_x10k", "c3_corpus_x1000", "c5_stored_10k", "c5b_literals_10k",
+                   "c6_text_q11_w16", "c7_far_w22"] if world == 1 else ["c5_stored_10k"]
         extra = []
         if rank == 0:
             for nm in names_x:
