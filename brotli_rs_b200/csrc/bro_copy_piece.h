@@ -190,3 +190,91 @@ BRO_PIECE_FN void bro_piece_consume(bro_stage_ptr slot, uint8_t* dp, uint32_t g,
     }
 #undef BRO_PIECE_VECTORS
 }
+
+// ------------------------------------------------------------------------------------------------------
+// The WINDOW form of the same piece (BRO_COPY_WINDOW, bro_kernels_copy.cu): the warp keeps the last BRO_WIN_BYTES of the
+// stream's output in a ring of shared memory -- the sliding window of src/ringbuffer/mod.rs:8-73, staged on chip.  Every
+// piece deposits what it stores (bro_piece_store_win), and a piece whose source lies in the ring takes it from there
+// (bro_piece_load_win) instead of HBM / L2: the chain of memory round trips along a stream (a copy reads what the copy before
+// it wrote) then runs through shared memory.  Ring coordinates are (output position + (address of the slot & 15)) &
+// BRO_WIN_MASK, so that what is 16-byte aligned in the output is 16-byte aligned in the ring and a vector never wraps.
+// ------------------------------------------------------------------------------------------------------
+#ifndef BRO_WIN_BYTES
+#define BRO_WIN_BYTES 4096u
+#endif
+#define BRO_WIN_MASK (BRO_WIN_BYTES - 1u)
+#define BRO_GEO_GAP(g) (((g) >> 28) & 7u)     /* bytes phase one wrote between the record before this one and this one: 0..4, 7 = more */
+#define BRO_GAP_BIG 7u
+
+#if defined(__CUDACC__)
+BRO_PIECE_FN void bro_stage_st16(bro_stage_ptr a, const bro_v16& v) {
+    asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" :: "r"(a), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+BRO_PIECE_FN void bro_stage_st8(bro_stage_ptr a, uint32_t b) { asm volatile("st.shared.u8 [%0], %1;" :: "r"(a), "r"(b) : "memory"); }
+#else
+BRO_PIECE_FN void bro_stage_st16(bro_stage_ptr a, const bro_v16& v) { *(bro_v16*)a = v; }
+BRO_PIECE_FN void bro_stage_st8(bro_stage_ptr a, uint32_t b) { *a = (uint8_t)b; }
+#endif
+
+// so: ring coordinate (not yet masked) of the piece's first source byte.  Same contents of d as bro_piece_load leaves.
+template <int G>
+BRO_PIECE_FN void bro_piece_load_win(BroPieceData<G>& d, bro_stage_ptr w, uint32_t so, uint32_t g, uint32_t bl) {
+    const uint32_t head = BRO_GEO_HEAD(g), nvec = BRO_GEO_NVEC(g), tail = BRO_GEO_TAIL(g);
+#pragma unroll
+    for (int i = 0; i < 32 / G; i++) {
+        const uint32_t slot = bl + (uint32_t)(G * i);
+        const bool back = slot >= 16u;
+        const uint32_t b = slot & 15u;
+        if (b < (back ? tail : head)) d.rb[i] = bro_stage_ld8(w + ((so + (back ? head + 16u * nvec : 0u) + b) & BRO_WIN_MASK));
+    }
+    const uint32_t q = ((so + head) & ~15u) + 16u * bl;       // the granule that holds the first source byte of this lane's first vector
+#pragma unroll
+    for (int i = 0; i < 32 / G; i++) {
+        if (bl + (uint32_t)(G * i) < nvec) {
+            d.A[i] = bro_stage_ld16(w + ((q + 16u * (uint32_t)(G * i)) & BRO_WIN_MASK));
+            if (g & 0x0f000000u) d.B[i] = bro_stage_ld16(w + ((q + 16u * (uint32_t)(G * i) + 16u) & BRO_WIN_MASK));
+        }
+    }
+}
+
+// bro_piece_store + the same bytes into the ring.  dp: address of the piece's first destination byte; dofs: its ring
+// coordinate (not yet masked; (dofs + head) & 15 == 0 as ((uintptr_t)dp + head) & 15 == 0).
+template <int G>
+BRO_PIECE_FN void bro_piece_store_win(const BroPieceData<G>& d, uint8_t* dp, bro_stage_ptr w, uint32_t dofs, uint32_t g, uint32_t bl) {
+    const uint32_t head = BRO_GEO_HEAD(g), nvec = BRO_GEO_NVEC(g), tail = BRO_GEO_TAIL(g), sh = BRO_GEO_SHIFT(g);
+#pragma unroll
+    for (int i = 0; i < 32 / G; i++) {
+        const uint32_t slot = bl + (uint32_t)(G * i);
+        const bool back = slot >= 16u;
+        const uint32_t b = slot & 15u;
+        if (b < (back ? tail : head)) {
+            const uint32_t o = (back ? head + 16u * nvec : 0u) + b;
+            dp[o] = (uint8_t)d.rb[i];
+            bro_stage_st8(w + ((dofs + o) & BRO_WIN_MASK), d.rb[i]);
+        }
+    }
+    bro_v16* const dv = (bro_v16*)(dp + head) + bl;
+    const uint32_t wv = dofs + head + 16u * bl;
+    const unsigned bs = 8u * (sh & 3u);
+#define BRO_PIECE_VECTORS(EXPR)                                                         \
+    _Pragma("unroll") for (int i = 0; i < 32 / G; i++)                                  \
+        if (bl + (uint32_t)(G * i) < nvec) {                                            \
+            const bro_v16 v = (EXPR);                                                   \
+            dv[G * i] = v;                                                              \
+            bro_stage_st16(w + ((wv + 16u * (uint32_t)(G * i)) & BRO_WIN_MASK), v);     \
+        }
+    if (sh == 0u) { BRO_PIECE_VECTORS(d.A[i]) }
+    else switch (sh >> 2) {
+        case 0: BRO_PIECE_VECTORS(bro_funnel16<0>(d.A[i], d.B[i], bs)) break;
+        case 1: BRO_PIECE_VECTORS(bro_funnel16<1>(d.A[i], d.B[i], bs)) break;
+        case 2: BRO_PIECE_VECTORS(bro_funnel16<2>(d.A[i], d.B[i], bs)) break;
+        default: BRO_PIECE_VECTORS(bro_funnel16<3>(d.A[i], d.B[i], bs)) break;
+    }
+#undef BRO_PIECE_VECTORS
+}
+
+// Is the source [spos, spos + len) of a back-reference in the ring?  wlo: first position deposited without a break since
+// the ring was last started, whi: the position behind the last deposit (what the ring holds is [max(wlo, whi - BRO_WIN_BYTES), whi)).
+BRO_PIECE_FN bool bro_win_holds(uint32_t spos, uint32_t len, uint32_t wlo, uint32_t whi) {
+    return spos >= wlo && spos + len <= whi && spos + BRO_WIN_BYTES >= whi;
+}

@@ -278,6 +278,17 @@ BRO_FN void bro_lens_push(const BroScratch& sc, BroLensWriter& lw, uint32_t i, u
     if (w != lw.w) { bro_tl_st32(sc.t, BRO_TL_LENS + 4u * lw.w, lw.acc); lw.acc = 0; lw.w = w; }
     lw.acc |= v << (4u * (i & 7u));
 }
+// a run of `count` lengths v from index i on (repeat code 16: up to the whole alphabet), eight lengths per trip
+BRO_FN void bro_lens_push_run(const BroScratch& sc, BroLensWriter& lw, uint32_t i, uint32_t count, uint32_t v) {
+    const uint32_t pat = v * 0x11111111u;
+    while (count) {
+        const uint32_t w = i >> 3, o = i & 7u;
+        if (w != lw.w) { bro_tl_st32(sc.t, BRO_TL_LENS + 4u * lw.w, lw.acc); lw.acc = 0; lw.w = w; }
+        const uint32_t n = 8u - o < count ? 8u - o : count;
+        lw.acc |= (pat & (0xffffffffu >> (4u * (8u - n)))) << (4u * o);
+        i += n; count -= n;
+    }
+}
 BRO_FN void bro_lens_end(const BroScratch& sc, BroLensWriter& lw) { bro_tl_st32(sc.t, BRO_TL_LENS + 4u * lw.w, lw.acc); }
 #else
 // per-warp on-chip scratch (shared memory on the device)
@@ -1022,7 +1033,7 @@ BRO_FN int bro_read_complex_code(BroBits& in, BroScratch& sc, uint32_t hskip, ui
                 count = newrep;
             }
 #if defined(BRO_SERIAL)
-            for (uint32_t k = 0; k < count; k++) bro_lens_push(sc, lw, i + k, last_nz);
+            bro_lens_push_run(sc, lw, i, count, last_nz);
 #else
             for (uint32_t k = lane; k < count; k += BRO_W) sc.lens[i + k] = (uint8_t)last_nz;
 #endif
@@ -1731,6 +1742,27 @@ BRO_FN int bro_decode_sym_hot(BroBits& s, const uint16_t* hot, uint32_t rb, cons
     return BRO_SYM_OK;
 }
 
+
+#if !defined(BRO_SERIAL) && BRO_W == 32u
+// The literal code of block type bt when it does not depend on the context -- the 64 entries of the type's context map row
+// name one tree (every stream without literal context modelling that has literal block types: libbrotli quality 5..9 on
+// mixed data) -- or BRO_ROW_CTX.  The 8-bit root of that tree is staged in sc.root_lit (unless the meta-block has one
+// literal code, whose root bro_stage_roots staged), so that the runs of the block are decoded lane-parallel.
+#define BRO_ROW_CTX 0xffffffffu
+BRO_FN uint32_t bro_lit_row(BroScratch& sc, const uint16_t* T_lit, const uint8_t* cmap_l, uint32_t ntl, uint32_t bt) {
+    if (ntl < 2u) return 0u;
+    const unsigned lane = bro_lane();
+    const uint8_t* row = cmap_l + 64u * bt;
+    const uint32_t t0 = row[0];
+    const bool same = row[lane] == t0 && row[32u + lane] == t0;
+    if (!__all_sync(0xffffffffu, same)) return BRO_ROW_CTX;
+    bro_syncwarp();                                                       // (lanes may still be reading the root staged before)
+    const uint16_t* T = T_lit + t0 * BRO_LIT_STRIDE_U16;
+    for (uint32_t r = lane; r < 256u; r += BRO_W) sc.root_lit[r] = T[r];
+    bro_syncwarp();
+    return t0;
+}
+#endif
 // What the general loop keeps on chip for a meta-block with several codes of a kind
 struct BroHot {
     uint32_t rb_lit, rb_cmd, rb_dist;    // root bits of the on-chip copies (0 = none: look the tables up in the arena)
@@ -1758,6 +1790,10 @@ BRO_FN int bro_commands_general(BroDec& d, BroScratch& sc, uint32_t mlen, BroMbI
     const bool one_lit = ntl == 1u, one_cmd = cat[1].nbl == 1u, one_dist = ntd == 1u;
     const bool lit_simple = one_lit && cat[0].nbl == 1u;   // no context modelling, no literal block switches
     const uint32_t mb_begin = d.pos;   // meta_block.count_output == d.pos - mb_begin
+#if !defined(BRO_SERIAL) && BRO_W == 32u
+    uint32_t row = bro_lit_row(sc, T_lit, cmap_l, ntl, cat[0].btype);   // the tree of the current literal block type, or BRO_ROW_CTX
+    (void)lit_simple;
+#endif
     // command loop (src/lib.rs:2003-2141)
     for (;;) {
         // ---- phase one: entropy decode of one insert&copy command ----
@@ -1781,6 +1817,102 @@ BRO_FN int bro_commands_general(BroDec& d, BroScratch& sc, uint32_t mlen, BroMbI
         // literals (src/lib.rs:1286-1365).  The reference decodes all literals of a command before it emits any, so a
         // decode error inside the run wins over a full output slot: keep decoding (without storing) past the end of
         // the slot and report OutputTooSmall only if the whole run decoded.
+#if !defined(BRO_SERIAL) && BRO_W == 32u
+        // The run in CHUNKS of literals that share a block (the block accounting of src/lib.rs:1296-1302 done per chunk: a
+        // literal that finds its block exhausted reads the block switch first).  A chunk whose code does not depend on the
+        // context is decoded LANE-PARALLEL as in bro_commands_simple: lane l looks up the code that would start at bit offset
+        // l of the next 32 bits, the codes really present are the chain 0 -> len(0) -> ..., walked with one shuffle per
+        // literal.  (Round 2 decoded every literal of a meta-block with block types one at a time, ~1,300 cycles each on a
+        // single warp: what bounded the corpus batch -- data/metablock_reset has 460,000 such literals.)
+        {
+            uint32_t k = 0;
+            while (k < insert_len) {
+                uint32_t n = insert_len - k;
+                if (cat[0].nbl >= 2u) {
+                    if (cat[0].blen == 0u) {
+                        if ((st = bro_block_switch(d.in, d.arena, cat[0]))) return st;
+                        row = bro_lit_row(sc, T_lit, cmap_l, ntl, cat[0].btype);
+                        if (n > cat[0].blen + 1u) n = cat[0].blen + 1u;
+                        cat[0].blen -= n - 1u;
+                    } else {
+                        if (n > cat[0].blen) n = cat[0].blen;
+                        cat[0].blen -= n;
+                    }
+                }
+                const uint32_t pos0 = d.pos;
+                if (row != BRO_ROW_CTX) {
+                    const uint16_t* T = T_lit + row * BRO_LIT_STRIDE_U16;
+                    const BroRoot r_lit = bro_root_ref(sc.root_lit);
+                    uint32_t kk = 0;
+                    while (kk < n) {
+                        bro_refill(d.in);
+                        const uint32_t w2 = bro_shfl(d.in.cur, d.in.wi);                  // the word after the window, not consumed
+                        const uint32_t lo = bro_funnel_r(d.in.w0, d.in.w1, d.in.bp);     // stream bits [0, 32)
+                        const uint32_t hi = bro_funnel_r(d.in.w1, w2, d.in.bp);          // stream bits [32, 64)
+                        const uint32_t e = bro_root_get(r_lit, bro_funnel_r(lo, hi, lane) & 0xffu);
+                        const uint32_t len_l = e >> 10;                                   // 0: longer than 8 bits (or a hole)
+                        uint32_t want = n - kk, bit = 0, mask = 0, cnt = 0;
+                        while (cnt < want) {
+                            const uint32_t L = bro_shfl(len_l, bit);
+                            if (L == 0u || bit + L > 32u) break;
+                            mask |= 1u << bit;
+                            bit += L;
+                            cnt++;
+                            if (bit >= 32u) break;
+                        }
+                        if (cnt != 0u) {
+                            const uint32_t at = pos0 + kk + bro_popc(mask & bro_lanemask_lt());
+                            if (((mask >> lane) & 1u) && at < d.cap) d.out[at] = (uint8_t)e;
+                            // the two bytes in front of the next literal (a later block may be context-modelled)
+                            const uint32_t last = 31u - (uint32_t)__clz(mask), rest = mask & ~(1u << last);
+                            const uint32_t b1 = bro_shfl(e, last) & 0xffu, b2 = bro_shfl(e, rest ? 31u - (uint32_t)__clz(rest) : 0u) & 0xffu;
+                            d.p2 = rest ? b2 : d.p1; d.p1 = b1;
+                            kk += cnt;
+                            bro_consume(d.in, bit);
+                        } else {
+                            uint32_t lit;
+                            r = bro_decode_sym_onchip(d.in, r_lit, T, lit);
+                            if (r != BRO_SYM_OK) return r == BRO_SYM_HOLE ? BRO_ST_ParseErrorInsertLiterals : BRO_ST_UnexpectedEOF;
+                            if (lane == 0 && pos0 + kk < d.cap) d.out[pos0 + kk] = (uint8_t)lit;
+                            d.p2 = d.p1; d.p1 = lit;
+                            kk++;
+                        }
+                    }
+                    if ((int32_t)d.in.avail < 0) return BRO_ST_UnexpectedEOF;             // checkpoint (the rounds consume unchecked)
+                    d.pos += n;
+                } else {
+                    // a code per literal chosen by the context; lane kk % W keeps literal kk, W literals leave with one coalesced
+                    // store (nothing is stored behind the end of the slot)
+                    uint32_t mine = 0;
+                    const uint32_t bt = cat[0].btype, mode = modes[bt];
+                    for (uint32_t kk = 0; kk < n; kk++) {
+                        uint32_t cid;
+                        if (mode == 0u) cid = d.p1 & 0x3fu;
+                        else if (mode == 1u) cid = d.p1 >> 2;
+                        else if (mode == 2u) cid = (uint32_t)bro_lut0[d.p1] | bro_lut1[d.p2];
+                        else cid = ((uint32_t)bro_lut2[d.p1] << 3) | bro_lut2[d.p2];
+                        const uint32_t t = cmap_l[bt * 64u + cid];
+                        const uint16_t* T = T_lit + t * BRO_LIT_STRIDE_U16;
+                        uint32_t lit;
+                        if (hot.rb_lit) r = bro_decode_sym_hot(d.in, sc.hot_lit + (t << hot.rb_lit), hot.rb_lit, T, lit);
+                        else r = bro_decode_sym(d.in, T, lit);
+                        if (r == BRO_SYM_HOLE) return BRO_ST_ParseErrorInsertLiterals;
+                        if (r == BRO_SYM_EOF) return BRO_ST_UnexpectedEOF;
+                        if (lane == (kk & (BRO_W - 1u))) mine = lit;
+                        d.pos += 1;
+                        d.p2 = d.p1; d.p1 = lit;
+                        if (((kk + 1u) & (BRO_W - 1u)) == 0u) {
+                            const uint32_t at = pos0 + kk + 1u - BRO_W + lane;
+                            if (at < d.cap) d.out[at] = (uint8_t)mine;
+                        }
+                    }
+                    const uint32_t tail = n & (BRO_W - 1u), at = pos0 + n - tail + lane;
+                    if (lane < tail && at < d.cap) d.out[at] = (uint8_t)mine;
+                }
+                k += n;
+            }
+        }
+#else
         if (lit_simple && insert_len <= d.cap - d.pos) {
             // fast path: one literal code, no block switches, the run fits the slot.  Lane k%W keeps literal k and the
             // group stores W literals with one coalesced store.
@@ -1831,6 +1963,7 @@ BRO_FN int bro_commands_general(BroDec& d, BroScratch& sc, uint32_t mlen, BroMbI
             const uint32_t tail = insert_len & (BRO_W - 1u), at = pos0 + insert_len - tail + lane;
             if (lane < tail && at < d.cap) d.out[at] = (uint8_t)mine;
         }
+#endif
         if (d.pos > d.cap) { d.pos = d.cap; return BRO_ST_OutputTooSmall; }
         if (d.pos - mb_begin == mlen) return 0;                                      // src/lib.rs:2069-2070
         // distance code (src/lib.rs:1367-1410)

@@ -52,6 +52,15 @@
                               // the mbarrier, one piece per consume trip) and the generic -> async proxy fence at every group
                               // (a MEMBAR: 5.4 stall cycles per issue); profiles/r02_kernel_variants.md
 #endif
+#ifndef BRO_COPY_WINDOW
+#define BRO_COPY_WINDOW 0     // 1: the sliding window staged in shared memory (bro_run_pieces_win): a warp keeps the last
+                              // BRO_WIN_BYTES of its stream's output in a ring on chip, and a long record whose source lies in the
+                              // ring reads it there -- the store -> load round trip through L2 between dependent copies, which is
+                              // what bounded the register path (profiles/r02_kernel_variants.md section 2), leaves the chain
+#endif
+#ifndef BRO_COPY_PIN_TID
+#define BRO_COPY_PIN_TID 0
+#endif
 #ifndef BRO_COPY_PF_DIST
 #define BRO_COPY_PF_DIST 8192u   // sources at least this far back (and every stored block: it comes from the compressed
                                  // input) are asked of DRAM with one bulk prefetch (TMA: cp.async.bulk.prefetch.L2) when their
@@ -238,24 +247,98 @@ __device__ __forceinline__ void bro_run_pieces_bulk(uint8_t* out, uint32_t dst, 
     }
 }
 
+
+// ---- the same group with the sliding window staged in shared memory (BRO_COPY_WINDOW, the product) ----
+// The ring `win` (BRO_WIN_BYTES per warp) holds the output positions [max(wlo, whi - BRO_WIN_BYTES), whi) of the stream the
+// warp works on.  A step moves up to 32 / G pieces of the group, one per lane group, in two phases with a __syncwarp between
+// them: every lane group LOADS its piece -- from the ring when its source lies there (bro_win_holds), else from global memory
+// as bro_run_pieces does -- and then STORES it to the output and DEPOSITS the same bytes in the ring, together with the few
+// bytes phase one wrote between the record before and this one (literals: fetched from the output when the records were
+// loaded, long before they are needed; geo bits 28..30 say how many).  A record with more such bytes in front of it than a
+// lane keeps (BRO_GAP_BIG) starts a step of its own and starts the ring afresh at its destination.  Because all loads of a
+// step precede its deposits, a source BRO_WIN_BYTES back is still intact when it is read.
+// wlo / whi / seen / hit are warp-uniform.  hit / seen: pieces served by the ring / pieces moved (the caller stops depositing
+// for a stream whose copies reach further back than the ring).
+#define BRO_WIN_NONE 0xffffffffu
+template <int G>
+__device__ __forceinline__ void bro_run_pieces_win(uint8_t* out, uint32_t out_mis, uint32_t dst, uint32_t end, uint32_t geo,
+                                                   uint32_t sp_lo, uint32_t sp_hi, uint32_t gapw, unsigned lane, uint32_t j,
+                                                   uint32_t e, uint32_t win, bool dep, uint32_t& wlo, uint32_t& whi, uint32_t& seen, uint32_t& hit) {
+    // dep = false: the group is moved without the ring (stored meta-blocks -- their source is the compressed input -- and
+    // streams for which the ring was given up); whi == BRO_WIN_NONE then, so that no source is looked for in the ring
+    constexpr int PP = 32 / G;
+    const uint32_t bl = lane & (uint32_t)(G - 1), sub = lane / (uint32_t)G;
+    const uint32_t big = __ballot_sync(0xffffffffu, BRO_GEO_GAP(geo) == BRO_GAP_BIG);
+    const uint32_t out_lo = (uint32_t)(uintptr_t)out;
+    uint32_t k0 = j;
+    while (k0 < e) {
+        // the records of this step: k0 .. k0 + m - 1 (a record with a big gap in front of it starts a step)
+        uint32_t m = e - k0 < (uint32_t)PP ? e - k0 : (uint32_t)PP;
+        const uint32_t bm = (big >> (k0 + 1u)) & ((1u << (m - 1u)) - 1u);
+        if (bm) m = (uint32_t)__ffs(bm);
+        const bool fresh = dep && (whi == BRO_WIN_NONE || ((big >> k0) & 1u));
+        if (fresh) wlo = whi = __shfl_sync(0xffffffffu, dst, (int)k0);        // nothing in front of record k0 is in the ring
+        const uint32_t k = k0 + sub;
+        const int ks = (int)(k & 31u);
+        uint32_t g = __shfl_sync(0xffffffffu, geo, ks);
+        const uint32_t s_lo = __shfl_sync(0xffffffffu, sp_lo, ks);
+        const uintptr_t s0 = (uintptr_t)s_lo | ((uintptr_t)__shfl_sync(0xffffffffu, sp_hi, ks) << 32);
+        const uint32_t d = __shfl_sync(0xffffffffu, dst, ks);
+        const uint32_t gw = __shfl_sync(0xffffffffu, gapw, ks);
+        if (sub >= m) g = 0;
+        uint32_t gn = BRO_GEO_GAP(g);
+        if (gn == BRO_GAP_BIG || (fresh && sub == 0u)) gn = 0;                // (in front of wlo: not part of the ring)
+        const uint32_t spos = s_lo - out_lo;                                  // output position of the first source byte
+        const uint32_t len = BRO_GEO_HEAD(g) + 16u * BRO_GEO_NVEC(g) + BRO_GEO_TAIL(g);
+        const bool inwin = dep && g != 0u && bro_win_holds(spos, len, wlo, whi);
+        BroPieceData<G> D;
+        if (inwin) bro_piece_load_win<G>(D, win, spos + out_mis, g, bl);
+        else bro_piece_load<G>(D, (const uint8_t*)s0, g, bl);
+        hit += (uint32_t)__popc(__ballot_sync(0xffffffffu, inwin && bl == 0u));
+        seen += m;
+        __syncwarp();                                                         // every load from the ring precedes the deposits
+        if (!dep) bro_piece_store<G>(D, out + d, g, bl);
+        else if (g != 0u) {
+            bro_piece_store_win<G>(D, out + d, win, d + out_mis, g, bl);
+            if (bl < gn) bro_stage_st8(win + ((d + out_mis - gn + bl) & BRO_WIN_MASK), (gw >> (8u * bl)) & 0xffu);
+        }
+        if (dep) whi = __shfl_sync(0xffffffffu, end, (int)(k0 + m - 1u));
+        __syncwarp();                                                         // the deposits are there for the next step's loads
+        k0 += m;
+    }
+}
+
 template <int WARPS>
 __global__ void __launch_bounds__(WARPS * 32, BRO_COPY_MIN_BLOCKS) bro_copy_kernel(BroLaunch p) {
     if (p.gate && p.gate[1]) return;       // AUTO: this batch goes to the fused kernel as a whole
-    const unsigned lane = threadIdx.x & 31u;
+    // (values derived from %tid come out of a shuffle so that ptxas keeps them in registers instead of re-reading the special
+    // register and redoing the arithmetic wherever they are used)
+#if BRO_COPY_PIN_TID
+    const unsigned tid = __shfl_sync(0xffffffffu, threadIdx.x, threadIdx.x & 31u);
+#else
+    const unsigned tid = threadIdx.x;
+#endif
+    const unsigned lane = tid & 31u;
     // staging: per warp BRO_COPY_DEPTH rounds x 32 lanes x 32 bytes (the two aligned 16-byte granules that hold a
     // unit's 16 source bytes)
     // (the staged long-record path uses the same bytes as BRO_COPY_QUADS * (32 / GROUP) piece slots; a warp is in one
     // path at a time)
     constexpr uint32_t STAGE_SHORT = BRO_COPY_DEPTH * 32u * 32u;
+    // (the window path keeps its ring in the same bytes: a group that goes through the short-record path starts the ring afresh)
     constexpr uint32_t STAGE_LONG = BRO_COPY_BULK ? BRO_COPY_SLOTS * BRO_STAGE_SLOT_BYTES :
-                                    BRO_COPY_STAGED ? BRO_COPY_QUADS * (32u / BRO_COPY_GROUP) * BRO_STAGE_SLOT_BYTES : 0u;
+                                    BRO_COPY_STAGED ? BRO_COPY_QUADS * (32u / BRO_COPY_GROUP) * BRO_STAGE_SLOT_BYTES :
+                                    BRO_COPY_WINDOW ? BRO_WIN_BYTES : 0u;
     constexpr uint32_t STAGE_WARP = STAGE_SHORT > STAGE_LONG ? STAGE_SHORT : STAGE_LONG;
     __shared__ __align__(128) uint8_t stage[WARPS * STAGE_WARP];
-    const uint32_t stage_base = (uint32_t)__cvta_generic_to_shared(stage) + (threadIdx.x >> 5) * STAGE_WARP;
+#if BRO_COPY_PIN_TID
+    const uint32_t stage_base = __shfl_sync(0xffffffffu, (uint32_t)__cvta_generic_to_shared(stage) + (tid >> 5) * STAGE_WARP, 0);
+#else
+    const uint32_t stage_base = (uint32_t)__cvta_generic_to_shared(stage) + (tid >> 5) * STAGE_WARP;
+#endif
 #if BRO_COPY_BULK
     // one mbarrier per warp: the bulk copies of a step complete on it (phase parity kept in a register)
     __shared__ __align__(8) unsigned long long mbar[WARPS];
-    const uint32_t bar = (uint32_t)__cvta_generic_to_shared(&mbar[threadIdx.x >> 5]);
+    const uint32_t bar = (uint32_t)__cvta_generic_to_shared(&mbar[tid >> 5]);
     uint32_t bar_parity = 0;
     if (lane == 0) {
         bro_mbar_init(bar, 1u);
@@ -299,6 +382,11 @@ __global__ void __launch_bounds__(WARPS * 32, BRO_COPY_MIN_BLOCKS) bro_copy_kern
         const uint8_t* const in = p.in + in_b;
         const uint32_t out_mis = (uint32_t)((uintptr_t)out & 15u);   // destination alignment is that of the address
         unsigned long long moved = 0;                                // bytes this lane's records move (measurement)
+#if BRO_COPY_WINDOW
+        // the ring of this stream (bro_run_pieces_win): empty; tail_end = where the last record of the batch before ended
+        uint32_t wlo = 0, whi = BRO_WIN_NONE, w_seen = 0, w_hit = 0, tail_end = 0;
+        bool win_on = true;
+#endif
         for (uint32_t b = 0; b < n; b += 32u) {
             const uint32_t cnt = n - b < 32u ? n - b : 32u;
             uint32_t dst = 0, lk = 0, a = 0;
@@ -308,6 +396,26 @@ __global__ void __launch_bounds__(WARPS * 32, BRO_COPY_MIN_BLOCKS) bro_copy_kern
             }
             const uint32_t len = lk & BRO_REC_LEN_MASK, kind = lk >> BRO_REC_KIND_SHIFT;
             moved += len;
+#if BRO_COPY_WINDOW
+            // what phase one wrote between the record before and this one (the literals of the command, a dictionary word):
+            // up to four such bytes are fetched now -- nothing on the way to them depends on this kernel's stores -- and go
+            // into the ring with the record
+            const uint32_t end = dst + len;
+            uint32_t gapcode = 0, gapw = 0;
+            if (win_on) {
+                uint32_t prev = __shfl_up_sync(0xffffffffu, end, 1);
+                if (lane == 0) prev = tail_end;
+                const uint32_t gap = dst - prev;
+                gapcode = gap <= 4u ? gap : BRO_GAP_BIG;
+                if (lane < cnt && gap - 1u < 4u) {
+                    uint32_t gb[4];
+#pragma unroll
+                    for (uint32_t i = 0; i < 4u; i++) gb[i] = i < gap ? out[prev + i] : 0u;
+                    gapw = gb[0] | (gb[1] << 8) | (gb[2] << 16) | (gb[3] << 24);
+                }
+                tail_end = __shfl_sync(0xffffffffu, end, (int)(cnt - 1u));
+            }
+#endif
             // What bounds this kernel is the chain of memory round trips along a stream (a group's loads follow the stores
             // of the group before it), and a round trip that misses L2 is three times as long.  Output written a few KB ago
             // is still in L2; far sources -- written tens of microseconds ago and evicted by the 26 GB that followed -- and
@@ -341,6 +449,9 @@ __global__ void __launch_bounds__(WARPS * 32, BRO_COPY_MIN_BLOCKS) bro_copy_kern
                         __syncwarp();
                     }
                     j += 1u;
+#if BRO_COPY_WINDOW
+                    whi = BRO_WIN_NONE;
+#endif
                     continue;
                 }
                 // units of my record: head bytes up to the next 16-byte boundary, 16-byte vectors, tail bytes
@@ -356,6 +467,15 @@ __global__ void __launch_bounds__(WARPS * 32, BRO_COPY_MIN_BLOCKS) bro_copy_kern
                     // per record (lane-local, broadcast per piece): source address and geometry
                     const uint8_t* sp = kind == BRO_REC_STORED ? in + a : (const uint8_t*)out + (dst - a);
                     const uint32_t sp_lo = (uint32_t)(uintptr_t)sp, sp_hi = (uint32_t)((uintptr_t)sp >> 32);
+#if BRO_COPY_WINDOW
+                    const uint32_t geo = bro_piece_geo(dst + out_mis, sp_lo, len) | (gapcode << 28);
+                    const bool dep = win_on && !__any_sync(0xffffffffu, mine && kind == BRO_REC_STORED);
+                    if (!dep) whi = BRO_WIN_NONE;
+                    bro_run_pieces_win<BRO_COPY_GROUP>(out, out_mis, dst, end, geo, sp_lo, sp_hi, gapw, lane, j, e, stage_base, dep,
+                                                       wlo, whi, w_seen, w_hit);
+                    // a stream whose copies reach further back than the ring: stop depositing
+                    if (w_seen >= 64u && 4u * w_hit < w_seen) win_on = false;
+#else
                     const uint32_t geo = bro_piece_geo(dst + out_mis, sp_lo, len);
 #if BRO_COPY_BULK
                     bro_run_pieces_bulk<BRO_COPY_SLOTS>(out, dst, geo, sp_lo, sp_hi, lane, j, e, stage_base, bar, bar_parity);
@@ -364,10 +484,14 @@ __global__ void __launch_bounds__(WARPS * 32, BRO_COPY_MIN_BLOCKS) bro_copy_kern
 #else
                     bro_run_pieces<BRO_COPY_GROUP>(out, dst, geo, sp_lo, sp_hi, lane, j, e);
 #endif
+#endif
                     j = e;
                     continue;
                 }
                 // SHORT records: one segmented copy over all units of the group
+#if BRO_COPY_WINDOW
+                whi = BRO_WIN_NONE;       // (its staging slots are the ring's bytes)
+#endif
                 const uint32_t units = mine ? head + nvec + tail : 0u;
                 uint32_t incl = units;
 #pragma unroll

@@ -26,6 +26,9 @@
 #endif
 #define BRO_PARSE_MIN_BLOCKS 1
 #define BRO_PARSE_SMEM (BRO_PARSE_BLOCK * BRO_TL_BYTES)
+#ifndef BRO_PARSE_PIN_TID
+#define BRO_PARSE_PIN_TID 1
+#endif
 #ifndef BRO_PARSE_PATIENCE
 #define BRO_PARSE_PATIENCE 1024u
 #endif
@@ -34,8 +37,16 @@
 
 __global__ void __launch_bounds__(BRO_PARSE_BLOCK, BRO_PARSE_MIN_BLOCKS) bro_parse_kernel(BroLaunch p) {
     if (p.gate && p.gate[1]) return;       // AUTO: this batch goes to the fused kernel as a whole
-    const unsigned t = blockIdx.x * BRO_PARSE_BLOCK + threadIdx.x;
-    const unsigned lane = threadIdx.x & 31u;
+#if BRO_PARSE_PIN_TID
+    // ptxas does not keep values derived from %tid in registers: it re-reads the special register (S2R, tens of cycles) and
+    // redoes the arithmetic wherever they are used -- in front of every shared-memory look-up of the decode loop.  A value that
+    // comes out of a shuffle cannot be recomputed, so it stays in its register.
+    const unsigned tid = __shfl_sync(0xffffffffu, threadIdx.x, threadIdx.x & 31u);
+#else
+    const unsigned tid = threadIdx.x;
+#endif
+    const unsigned t = blockIdx.x * BRO_PARSE_BLOCK + tid;
+    const unsigned lane = tid & 31u;
     uint16_t* const arena = p.arena + (size_t)t * BRO_THREAD_ARENA_STRIDE_U16;
     BroDec d;
     BroParse ps;
@@ -45,7 +56,7 @@ __global__ void __launch_bounds__(BRO_PARSE_BLOCK, BRO_PARSE_MIN_BLOCKS) bro_par
     // insert/copy length table.  Nothing of a thread's working set is in local memory.
     extern __shared__ __align__(16) uint8_t s_blocks[];
     __shared__ uint32_t s_ic[48];
-    if (threadIdx.x < 48u) bro_ic_compact_entry(threadIdx.x, s_ic[threadIdx.x]);
+    if (tid < 48u) bro_ic_compact_entry(tid, s_ic[tid]);
     __syncthreads();
     uint32_t stream = 0;
     uint32_t waited = 0;          // warp-uniform: trips since the first lane reached a boundary
@@ -54,7 +65,10 @@ __global__ void __launch_bounds__(BRO_PARSE_BLOCK, BRO_PARSE_MIN_BLOCKS) bro_par
     ps.kind = BRO_K_DONE; ps.st = -1;   // st < 0: no stream to report
     {
         BroTl tl;
-        tl.base = (uint32_t)__cvta_generic_to_shared(s_blocks) + (threadIdx.x >> 5) * (32u * BRO_TL_BYTES) + 4u * lane;
+        tl.base = (uint32_t)__cvta_generic_to_shared(s_blocks) + (tid >> 5) * (32u * BRO_TL_BYTES) + 4u * lane;
+#if BRO_PARSE_PIN_TID
+        tl.base = __shfl_sync(0xffffffffu, tl.base, lane);      // (the same: the block's address, pinned)
+#endif
         bro_scratch_bind(d.scv, tl);
         d.in.ring = tl;
     }

@@ -96,6 +96,12 @@ class copy_group:
         self.L.bro_hostsim_parse_copy_stats(st)
         return tuple(st)
 
+    def win_stats(self):
+        """window form (group 308): (pieces served by the ring, pieces moved) since the last call"""
+        st = (ctypes.c_uint64 * 2)()
+        self.L.bro_hostsim_copy_win_stats(st)
+        return int(st[0]), int(st[1])
+
 
 def parse_records(data: bytes, cap: int = 1 << 20):
     """The copy records phase one writes for a stream: -> (status, [(dst, len, kind, a)], out_mis) where out_mis is the

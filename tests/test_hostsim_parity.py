@@ -241,13 +241,14 @@ def test_parse_sizing_mode():
     assert known >= 600
 
 
-@pytest.mark.parametrize("group", [208, 203, 32, 16, 8, 4, 108, 116, 132])
+@pytest.mark.parametrize("group", [308, 208, 203, 32, 16, 8, 4, 108, 116, 132])
 def test_copy_phase_lane_code(group):
     """phase two as the copy kernel executes it: 32 records at a time, groups of independent records, long records piece
     by piece through the kernel's own lane code (bro_copy_piece.h) with `group` lanes per piece, all loads of a step
     before its first store (group > 100: the staged form, issue / consume through slots with two steps in flight; group >
-    200: the product's bulk form, whole pieces fetched into group - 200 slots, then consumed by 32 lanes each); short
-    groups last record first.  Bytes must equal the oracle's."""
+    200: the bulk form, whole pieces fetched into group - 200 slots, then consumed by 32 lanes each; 308: the product's window
+    form -- the last 4 KiB of output in a ring, sources taken from the ring where they lie in it); short groups last record
+    first.  Bytes must equal the oracle's."""
     enc = fuzzgen.libbrotli_enc()
     if enc is None:
         pytest.skip("system libbrotlienc not present")
@@ -272,6 +273,9 @@ def test_copy_phase_lane_code(group):
                 p, s, f = cg.stats()
                 pieces, shorts, fills = pieces + p, shorts + s, fills + f
     assert handled >= 40 and pieces >= 100 and shorts >= 100 and fills >= 10, (handled, pieces, shorts, fills)
+    if group == 308:
+        hits, seen = cg.win_stats()
+        assert hits >= 300 and seen > hits, (hits, seen)      # the ring served sources, and not all of them
 
 
 # ---- the resumable decode behind the streaming reader (bro_decode_stream_resume + the reader's loop, tests/hostsim.py) ----
