@@ -798,6 +798,9 @@ struct BroDec {
 #define BRO_DSC(d) ((d).scv)
 #else
     BroScratch* sc;           // this warp's scratch in shared memory
+    uint16_t* root10;         // latency build only (else 0): 1,024 entries of shared memory for the 10-bit literal root of the
+                              // general loop's lane-parallel rounds (bro_lit_row).  The throughput build runs 24 warps per SM
+                              // and needs what is left of the SM's 256 KB as L1 for its tables: 2 KB more per warp cost it 5 %
 #define BRO_DSC(d) (*(d).sc)
 #endif
     const uint8_t* dict;      // 122,784-byte static dictionary image
@@ -1373,6 +1376,21 @@ BRO_FN int bro_emit_copy(BroDec& d, BroScratch& sc, uint32_t mlen, uint32_t mb_b
     if (distance <= max_allowed) {
         if (mlen < mb_out + copy_len) return BRO_ST_ExceededExpectedBytes;     // src/lib.rs:2105-2108
         if (copy_len > d.cap - d.pos) return BRO_ST_OutputTooSmall;
+#if !defined(BRO_SERIAL) && BRO_W == 32u
+        if (track_ctx && copy_len <= BRO_W) {
+            // the copy of a text-like stream (8 bytes on average): a byte per lane, in line, and the two bytes the next literal's
+            // context is made of come from the lanes that moved them instead of a read-back from memory
+            bro_syncwarp();
+            uint8_t* dst = d.out + d.pos;
+            const uint8_t* src = dst - distance;
+            uint32_t idx = lane, v = 0;
+            if (distance < copy_len) idx = lane % distance;
+            if (lane < copy_len) { v = src[idx]; dst[lane] = (uint8_t)v; }
+            d.pos += copy_len;
+            d.p1 = bro_shfl(v, copy_len - 1u); d.p2 = bro_shfl(v, copy_len - 2u);                          // copy_len >= 2
+            return 0;
+        }
+#endif
         bro_lz_copy(d.out, d.pos, distance, copy_len);
         d.pos += copy_len;
         if (track_ctx) {
@@ -1749,16 +1767,37 @@ BRO_FN int bro_decode_sym_hot(BroBits& s, const uint16_t* hot, uint32_t rb, cons
 // mixed data) -- or BRO_ROW_CTX.  The 8-bit root of that tree is staged in sc.root_lit (unless the meta-block has one
 // literal code, whose root bro_stage_roots staged), so that the runs of the block are decoded lane-parallel.
 #define BRO_ROW_CTX 0xffffffffu
-BRO_FN uint32_t bro_lit_row(BroScratch& sc, const uint16_t* T_lit, const uint8_t* cmap_l, uint32_t ntl, uint32_t bt) {
-    if (ntl < 2u) return 0u;
+BRO_FN uint32_t bro_lit_row(BroScratch& sc, uint16_t* root10, const uint16_t* T_lit, const uint8_t* cmap_l, uint32_t ntl, uint32_t bt) {
     const unsigned lane = bro_lane();
-    const uint8_t* row = cmap_l + 64u * bt;
-    const uint32_t t0 = row[0];
-    const bool same = row[lane] == t0 && row[32u + lane] == t0;
-    if (!__all_sync(0xffffffffu, same)) return BRO_ROW_CTX;
-    bro_syncwarp();                                                       // (lanes may still be reading the root staged before)
+    uint32_t t0 = 0;
+    if (ntl >= 2u) {
+        const uint8_t* row = cmap_l + 64u * bt;
+        t0 = row[0];
+        const bool same = row[lane] == t0 && row[32u + lane] == t0;
+        if (!__all_sync(0xffffffffu, same)) return BRO_ROW_CTX;
+    }
+    bro_syncwarp();                                                       // (lanes may still be reading the roots staged before)
     const uint16_t* T = T_lit + t0 * BRO_LIT_STRIDE_U16;
-    for (uint32_t r = lane; r < 256u; r += BRO_W) sc.root_lit[r] = T[r];
+    if (ntl >= 2u) for (uint32_t r = lane; r < 256u; r += BRO_W) sc.root_lit[r] = T[r];
+    if (root10 == 0) { bro_syncwarp(); return t0; }
+    // the 10-bit root, from the canonical form of the code: entry i answers the stream bits i (first bit = bit 0).  Real data
+    // has literal codes of 9 and 10 bits all the time (data/metablock_reset: a third of its literals), and a code the root
+    // does not answer ends a lane-parallel round
+    uint32_t lim[10];
+    int base[10];
+#pragma unroll
+    for (uint32_t L = 1; L <= 10u; L++) { lim[L - 1u] = T[BRO_T_LIMIT + L]; base[L - 1u] = (int)(int16_t)T[BRO_T_BASE + L]; }
+    const bool single = T[BRO_T_SINGLE] != 0;
+    for (uint32_t i = lane; i < 1024u; i += BRO_W) {
+        const uint32_t x = bro_brev(i) >> 17;                             // the ten bits left-justified in 15, first bit most significant
+        uint32_t e = 0;
+#pragma unroll
+        for (uint32_t L = 10u; L >= 1u; L--)                              // the shortest length whose limit x stays under
+            if (x < lim[L - 1u]) e = (uint32_t)(base[L - 1u] + (int)(x >> (15u - L))) | (L << 16);
+        if (e != 0u && !single) e = (uint32_t)T[BRO_T_SORTED + (e & 0xffffu)] | ((e >> 16) << 10);
+        else e = 0;
+        root10[i] = (uint16_t)e;
+    }
     bro_syncwarp();
     return t0;
 }
@@ -1790,15 +1829,18 @@ BRO_FN int bro_commands_general(BroDec& d, BroScratch& sc, uint32_t mlen, BroMbI
     const bool one_lit = ntl == 1u, one_cmd = cat[1].nbl == 1u, one_dist = ntd == 1u;
     const bool lit_simple = one_lit && cat[0].nbl == 1u;   // no context modelling, no literal block switches
     const uint32_t mb_begin = d.pos;   // meta_block.count_output == d.pos - mb_begin
+    // (the block categories live in the caller's frame, i.e. in local memory: whether a category has block types at all is asked
+    // once, not at every symbol)
+    const bool types0 = cat[0].nbl >= 2u, types1 = cat[1].nbl >= 2u, types2 = cat[2].nbl >= 2u;
 #if !defined(BRO_SERIAL) && BRO_W == 32u
-    uint32_t row = bro_lit_row(sc, T_lit, cmap_l, ntl, cat[0].btype);   // the tree of the current literal block type, or BRO_ROW_CTX
+    uint32_t row = bro_lit_row(sc, d.root10, T_lit, cmap_l, ntl, cat[0].btype);   // the tree of the current literal block type, or BRO_ROW_CTX
     (void)lit_simple;
 #endif
     // command loop (src/lib.rs:2003-2141)
     for (;;) {
         // ---- phase one: entropy decode of one insert&copy command ----
         uint32_t sym, extra;
-        if ((st = bro_step_block(d, cat[1]))) return st;
+        if (types1 && (st = bro_step_block(d, cat[1]))) return st;
         int r;
         if (one_cmd) r = bro_decode_sym2(d.in, sc.root_cmd, T_cmd, sym);
         else if (hot.rb_cmd) r = bro_decode_sym_hot(d.in, sc.root_cmd + (cat[1].btype << hot.rb_cmd), hot.rb_cmd,
@@ -1808,10 +1850,20 @@ BRO_FN int bro_commands_general(BroDec& d, BroScratch& sc, uint32_t mlen, BroMbI
         if (r == BRO_SYM_EOF) return BRO_ST_UnexpectedEOF;
         uint32_t ie = bro_ic_insert[sym], ce = bro_ic_copy[sym];
         uint32_t insert_len = ie & 0xffffu, copy_len = ce & 0xffffu;
-        if (!bro_read_bits(d.in, ie >> 16, extra)) return BRO_ST_UnexpectedEOF;   // insert extra bits first
-        insert_len += extra;
-        if (!bro_read_bits(d.in, ce >> 16, extra)) return BRO_ST_UnexpectedEOF;
-        copy_len += extra;
+        {
+            const uint32_t ib = ie >> 16, cb = ce >> 16;                             // insert extra bits come first
+            if (ib + cb <= 25u) {
+                // both fields from one window read (the common case: short lengths carry few extra bits)
+                if (!bro_read_bits(d.in, ib + cb, extra)) return BRO_ST_UnexpectedEOF;
+                insert_len += extra & ((1u << ib) - 1u);
+                copy_len += extra >> ib;
+            } else {
+                if (!bro_read_bits(d.in, ib, extra)) return BRO_ST_UnexpectedEOF;
+                insert_len += extra;
+                if (!bro_read_bits(d.in, cb, extra)) return BRO_ST_UnexpectedEOF;
+                copy_len += extra;
+            }
+        }
         uint32_t mb_out = d.pos - mb_begin;
         if (mlen < mb_out + insert_len) return BRO_ST_ExceededExpectedBytes;       // src/lib.rs:2036-2039
         // literals (src/lib.rs:1286-1365).  The reference decodes all literals of a command before it emits any, so a
@@ -1828,10 +1880,10 @@ BRO_FN int bro_commands_general(BroDec& d, BroScratch& sc, uint32_t mlen, BroMbI
             uint32_t k = 0;
             while (k < insert_len) {
                 uint32_t n = insert_len - k;
-                if (cat[0].nbl >= 2u) {
+                if (types0) {
                     if (cat[0].blen == 0u) {
                         if ((st = bro_block_switch(d.in, d.arena, cat[0]))) return st;
-                        row = bro_lit_row(sc, T_lit, cmap_l, ntl, cat[0].btype);
+                        row = bro_lit_row(sc, d.root10, T_lit, cmap_l, ntl, cat[0].btype);
                         if (n > cat[0].blen + 1u) n = cat[0].blen + 1u;
                         cat[0].blen -= n - 1u;
                     } else {
@@ -1849,8 +1901,9 @@ BRO_FN int bro_commands_general(BroDec& d, BroScratch& sc, uint32_t mlen, BroMbI
                         const uint32_t w2 = bro_shfl(d.in.cur, d.in.wi);                  // the word after the window, not consumed
                         const uint32_t lo = bro_funnel_r(d.in.w0, d.in.w1, d.in.bp);     // stream bits [0, 32)
                         const uint32_t hi = bro_funnel_r(d.in.w1, w2, d.in.bp);          // stream bits [32, 64)
-                        const uint32_t e = bro_root_get(r_lit, bro_funnel_r(lo, hi, lane) & 0xffu);
-                        const uint32_t len_l = e >> 10;                                   // 0: longer than 8 bits (or a hole)
+                        const uint32_t mine_bits = bro_funnel_r(lo, hi, lane);
+                        const uint32_t e = d.root10 ? (uint32_t)d.root10[mine_bits & 0x3ffu] : bro_root_get(r_lit, mine_bits & 0xffu);
+                        const uint32_t len_l = e >> 10;                                   // 0: longer than the root (or a hole)
                         uint32_t want = n - kk, bit = 0, mask = 0, cnt = 0;
                         while (cnt < want) {
                             const uint32_t L = bro_shfl(len_l, bit);
@@ -1935,7 +1988,7 @@ BRO_FN int bro_commands_general(BroDec& d, BroScratch& sc, uint32_t mlen, BroMbI
             const uint32_t pos0 = d.pos;
             uint32_t mine = 0;
             for (uint32_t k = 0; k < insert_len; k++) {
-                if ((st = bro_step_block(d, cat[0]))) return st;
+                if (types0 && (st = bro_step_block(d, cat[0]))) return st;
                 uint32_t t = 0;
                 if (ntl >= 2u) {
                     uint32_t bt = cat[0].btype, mode = modes[bt], cid;
@@ -1969,7 +2022,7 @@ BRO_FN int bro_commands_general(BroDec& d, BroScratch& sc, uint32_t mlen, BroMbI
         // distance code (src/lib.rs:1367-1410)
         uint32_t dcode = 0;
         if (sym >= 128u) {
-            if ((st = bro_step_block(d, cat[2]))) return st;
+            if (types2 && (st = bro_step_block(d, cat[2]))) return st;
             uint32_t t = 0;
             if (ntd >= 2u) {
                 uint32_t cid = copy_len <= 4u ? copy_len - 2u : 3u;
@@ -2104,6 +2157,26 @@ BRO_FN int bro_next_metablock(BroDec& d, bool after_last, uint32_t& is_last, uin
 #if !defined(BRO_PARSE)
         if (CK) bro_checkpoint(d, ck, in_start, BRO_RESUME_HEADER);
 #endif
+        if (!CK) {
+            // An empty metadata block that starts on a byte boundary is the single byte 0x06 (ISLAST 0, MNIBBLES 3, reserved bit
+            // 0, MSKIPBYTES 0, two zero fill bits; src/lib.rs:1617-1683): the reference's data/empty.compressed.17 / .18 hold
+            // 65,537 of them in a row, 12 % of the corpus batch's warp time when they took the general route below.
+            // (.18: 65,537 blocks of three bytes -- 0x16 = the same with MSKIPBYTES 1, the skip length minus one, the bytes skipped;
+            // up to two skipped bytes stay inside one window read)
+            bro_refill(d.in);
+            while ((bro_avail(d.in) & 7u) == 0u && bro_avail(d.in) >= 8u) {
+                const uint32_t pk = bro_peek(d.in);
+                uint32_t take = 0;
+                if ((pk & 0xffu) == 0x06u) take = 8u;
+                else if ((pk & 0xffu) == 0x16u && bro_avail(d.in) >= 16u) {
+                    const uint32_t skip = ((pk >> 8) & 0xffu) + 1u;
+                    if (skip <= 2u && bro_avail(d.in) >= 16u + 8u * skip) take = 16u + 8u * skip;
+                }
+                if (take == 0u) break;
+                bro_consume(d.in, take);
+                bro_refill(d.in);
+            }
+        }
         if (!bro_read_bits(d.in, 1, is_last)) return BRO_ST_UnexpectedEOF;
         if (is_last) {
             if (!bro_read_bits(d.in, 1, b)) return BRO_ST_UnexpectedEOF;

@@ -37,6 +37,14 @@
 #define BRO_GROUP_ARENA_U16 (BRO_W == 32u ? BRO_ARENA_U16_MAX : 65536u)
 #define BRO_GROUPS_PER_WARP (32u / BRO_W)
 
+#ifndef BRO_WARPS_PER_CTA
+#define BRO_WARPS_PER_CTA 8
+#endif
+#define BRO_WARP_KERNEL_SMEM_BASE (((BRO_WARPS_PER_CTA * BRO_GROUPS_PER_WARP * sizeof(BroScratch) + 15u) & ~(size_t)15) + (BRO_DICT_SMEM ? BRO_DICT_IMAGE_BYTES : 0u))
+#define BRO_WARP_KERNEL_SMEM_LATENCY (BRO_WARP_KERNEL_SMEM_BASE + 2048u * BRO_WARPS_PER_CTA)
+// (a variant build whose two builds are one and the same instance gets the larger launch for both)
+#define BRO_WARP_KERNEL_SMEM (BRO_MIN_BLOCKS == BRO_MIN_BLOCKS_LATENCY ? BRO_WARP_KERNEL_SMEM_LATENCY : BRO_WARP_KERNEL_SMEM_BASE)
+
 template <int WARPS, int MINB>
 __global__ void __launch_bounds__(WARPS * 32, MINB) bro_decode_warp_kernel(BroLaunch p) {
     // one BroScratch per warp (6.7 KB with the general loop's on-chip tables: dynamic shared memory, 4 CTAs x 8 warps = 214 KB per SM)
@@ -73,6 +81,8 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) bro_decode_warp_kernel(BroLa
         const uint64_t out_b = p.out_off[i], out_e = p.out_off[i + 1];
         BroDec d;
         d.sc = &scratch[warp];
+        // (the latency build's launch carries 2 KB more shared memory per warp, behind the scratch blocks and the dictionary image)
+        d.root10 = MINB == BRO_MIN_BLOCKS_LATENCY && BRO_W == 32u ? (uint16_t*)(bro_smem_raw + BRO_WARP_KERNEL_SMEM_BASE) + 1024u * warp : (uint16_t*)0;
         d.arena = p.arena + (size_t)gwarp * BRO_GROUP_ARENA_U16;
         d.arena_cap = BRO_GROUP_ARENA_U16;
         d.arena_base = 0;
@@ -98,19 +108,15 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) bro_decode_warp_kernel(BroLa
     }
 }
 
-#ifndef BRO_WARPS_PER_CTA
-#define BRO_WARPS_PER_CTA 8
-#endif
-#define BRO_WARP_KERNEL_SMEM (((BRO_WARPS_PER_CTA * BRO_GROUPS_PER_WARP * sizeof(BroScratch) + 15u) & ~(size_t)15) + (BRO_DICT_SMEM ? BRO_DICT_IMAGE_BYTES : 0u))
 
 // blocks_per_sm[0]: the throughput build, [1]: the latency build
 extern "C" int bro_warp_kernel_occupancy(int* blocks_per_sm) {
     cudaError_t e = cudaFuncSetAttribute(bro_decode_warp_kernel<BRO_WARPS_PER_CTA, BRO_MIN_BLOCKS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BRO_WARP_KERNEL_SMEM);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(bro_decode_warp_kernel<BRO_WARPS_PER_CTA, BRO_MIN_BLOCKS_LATENCY>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BRO_WARP_KERNEL_SMEM);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(bro_decode_warp_kernel<BRO_WARPS_PER_CTA, BRO_MIN_BLOCKS_LATENCY>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BRO_WARP_KERNEL_SMEM_LATENCY);
     if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm[0], bro_decode_warp_kernel<BRO_WARPS_PER_CTA, BRO_MIN_BLOCKS>,
                                                                             BRO_WARPS_PER_CTA * 32, BRO_WARP_KERNEL_SMEM);
     if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm[1], bro_decode_warp_kernel<BRO_WARPS_PER_CTA, BRO_MIN_BLOCKS_LATENCY>,
-                                                                            BRO_WARPS_PER_CTA * 32, BRO_WARP_KERNEL_SMEM);
+                                                                            BRO_WARPS_PER_CTA * 32, BRO_WARP_KERNEL_SMEM_LATENCY);
     return (int)e;
 }
 
@@ -119,7 +125,7 @@ extern "C" size_t bro_warp_kernel_arena_bytes() { return 2u * (size_t)BRO_GROUP_
 
 extern "C" int bro_warp_kernel_launch(const BroLaunch* p, int grid, int latency, cudaStream_t stream) {
     (void)cudaGetLastError();      // a stale error of another library in this process (it is per thread) is not this launch's
-    if (latency) bro_decode_warp_kernel<BRO_WARPS_PER_CTA, BRO_MIN_BLOCKS_LATENCY><<<grid, BRO_WARPS_PER_CTA * 32, BRO_WARP_KERNEL_SMEM, stream>>>(*p);
+    if (latency) bro_decode_warp_kernel<BRO_WARPS_PER_CTA, BRO_MIN_BLOCKS_LATENCY><<<grid, BRO_WARPS_PER_CTA * 32, BRO_WARP_KERNEL_SMEM_LATENCY, stream>>>(*p);
     else bro_decode_warp_kernel<BRO_WARPS_PER_CTA, BRO_MIN_BLOCKS><<<grid, BRO_WARPS_PER_CTA * 32, BRO_WARP_KERNEL_SMEM, stream>>>(*p);
     return (int)cudaGetLastError();
 }

@@ -33,6 +33,7 @@ __global__ void __launch_bounds__(BRO_RESUME_WARPS * 32, 2) bro_decode_resume_ke
         const uint64_t out_b = p.out_off[i], out_e = p.out_off[i + 1];
         BroDec d;
         d.sc = &scratch[warp];
+        d.root10 = 0;
         d.arena = p.arena + (size_t)gwarp * BRO_ARENA_U16_MAX;
         d.arena_cap = BRO_ARENA_U16_MAX;
         d.arena_base = 0;
