@@ -27,11 +27,15 @@
 #include "bro_decoder_core.h"
 #include "bro_kernels.h"
 
+// 2 CTAs of 10 warps per SM: the 102-register cap of that shape is what the kernel needs to hold a step's data without spilling
+// (92 registers).  Measured on B200 (profiles/r02_kernel_variants.md section 9): 3 x 8 warps at 80 registers (28 bytes of spills,
+// the product until then) 9.00 ms on the headline batch, 2 x 10 warps 8.86 ms (far sources, c7: 1.84 -> 1.72 ms); 4 x 7 warps at 72
+// registers 10.6 ms, 5 x 6 at 64 registers 11.8 ms -- every spilled register costs more than the warps it buys.
 #ifndef BRO_COPY_WARPS
-#define BRO_COPY_WARPS 8
+#define BRO_COPY_WARPS 10
 #endif
 #ifndef BRO_COPY_MIN_BLOCKS
-#define BRO_COPY_MIN_BLOCKS 3
+#define BRO_COPY_MIN_BLOCKS 2
 #endif
 #ifndef BRO_COPY_PIECES
 #define BRO_COPY_PIECES 4     // long records: pieces in flight per warp (their data is held in registers)
