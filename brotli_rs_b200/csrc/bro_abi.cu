@@ -34,7 +34,7 @@ struct bro_ctx {
     uint32_t num_threads;
     uint16_t* d_arena_t;      // parse kernel: 64 KiB arena per thread
     uint16_t* d_roots; size_t roots_bytes;   // parse kernel: compact per-thread literal tables (bro_parse.h)
-    int grid_c;               // copy kernel: persistent CTAs
+    int grid_c[2];            // copy kernel: persistent CTAs of its two shapes (bro_kernels.h)
     uint8_t* d_dict;
     uint32_t* d_counter;      // queue heads: [0] parse kernel, [1] warp kernel, [3] copy kernel; [2] retry count;
                               // [4..7] as two uint64: bytes moved / records executed by the copy kernel (last batch)
@@ -84,10 +84,10 @@ extern "C" int bro_ctx_create(bro_ctx** out, int device) {
     cudaDeviceProp prop;
     if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) { free(ctx); return BRO_ST_CudaError; }
     ctx->num_sms = prop.multiProcessorCount;
-    int per_sm2[2] = {0, 0}, per_sm = 0, per_sm_t = 0, per_sm_c = 0;
+    int per_sm2[2] = {0, 0}, per_sm = 0, per_sm_t = 0, per_sm_c[2] = {0, 0};
     if (bro_warp_kernel_occupancy(per_sm2) != 0 || (per_sm = per_sm2[0]) < 1 || per_sm2[1] < 1 ||
         bro_parse_kernel_occupancy(&per_sm_t) != 0 || per_sm_t < 1 ||
-        bro_copy_kernel_occupancy(&per_sm_c) != 0 || per_sm_c < 1) { free(ctx); return BRO_ST_CudaError; }
+        bro_copy_kernel_occupancy(per_sm_c) != 0 || per_sm_c[0] < 1 || per_sm_c[1] < 1) { free(ctx); return BRO_ST_CudaError; }
     ctx->grid = ctx->num_sms * per_sm;
     ctx->grid_lat = ctx->num_sms * per_sm2[1];
     ctx->num_warps = (uint32_t)ctx->grid * (uint32_t)bro_warp_kernel_warps_per_cta();
@@ -100,7 +100,8 @@ extern "C" int bro_ctx_create(bro_ctx** out, int device) {
     if (pb_want < per_sm_t) per_sm_t = pb_want;
     ctx->grid_t = ctx->num_sms * per_sm_t;
     ctx->num_threads = (uint32_t)ctx->grid_t * (uint32_t)bro_parse_kernel_block();
-    ctx->grid_c = ctx->num_sms * per_sm_c;
+    ctx->grid_c[0] = ctx->num_sms * per_sm_c[0];
+    ctx->grid_c[1] = ctx->num_sms * per_sm_c[1];
     ctx->mode = BRO_MODE_AUTO;
     // The two kernels of the two-phase path run one after the other: the parse kernel's CTA takes an SM's whole shared
     // memory (round 1 could run them side by side through the completion queue; it bought 5 % at best).
@@ -331,7 +332,13 @@ extern "C" int bro_batch_decode(bro_ctx* ctx, const uint8_t* d_in, const uint64_
         p.lanes = lanes;
         int grid_t = ctx->grid_t;
         if ((uint32_t)grid_t > (n + lanes * (tb / 32u) - 1u) / (lanes * (tb / 32u))) grid_t = (int)((n + lanes * (tb / 32u) - 1u) / (lanes * (tb / 32u)));
-        const uint32_t cw = (uint32_t)bro_copy_kernel_warps_per_cta();
+        // the copy kernel's shape: the one whose warps take fewer streams one after the other, the throughput shape when both
+        // take as many (any batch that fills the GPU several times over)
+        const uint32_t cw0 = (uint32_t)bro_copy_kernel_warps_per_cta(0), cw1 = (uint32_t)bro_copy_kernel_warps_per_cta(1);
+        const uint32_t warps0 = (uint32_t)ctx->grid_c[0] * cw0, warps1 = (uint32_t)ctx->grid_c[1] * cw1;
+        int cshape = (n + warps1 - 1u) / warps1 < (n + warps0 - 1u) / warps0 && n < 8u * warps0 ? 1 : 0;
+        { const char* cs = getenv("BRO_B200_COPY_SHAPE"); if (cs && (cs[0] == '0' || cs[0] == '1')) cshape = cs[0] - '0'; }
+        const uint32_t cw = cshape ? cw1 : cw0;
         p.counter = ctx->d_counter + 3; p.order = NULL;
         p.copy_stats = (unsigned long long*)(ctx->d_counter + 4);
         const bool overlap = ctx->overlap && !ctx->timing && ctx->side;
@@ -349,10 +356,10 @@ extern "C" int bro_batch_decode(bro_ctx* ctx, const uint8_t* d_in, const uint64_
         ctx->launches += 1;
         p.counter = ctx->d_counter + 3; p.order = NULL;
         p.fault = ctx->d_counter + 11; p.watchdog = ctx->watchdog;
-        int grid_c = ctx->grid_c;      // side by side, one CTA per SM fits next to the parse kernel; the others start as its CTAs exit
+        int grid_c = ctx->grid_c[cshape];      // side by side, one CTA per SM fits next to the parse kernel; the others start as its CTAs exit
         if ((uint32_t)grid_c > (n + cw - 1) / cw) grid_c = (int)((n + cw - 1) / cw);
         if (ctx->timing) BRO_CUDA(ctx, cudaEventRecord(ctx->ev[2], s));
-        e = (cudaError_t)bro_copy_kernel_launch(&p, grid_c, overlap ? ctx->side : s);
+        e = (cudaError_t)bro_copy_kernel_launch(&p, grid_c, cshape, overlap ? ctx->side : s);
         if (e != cudaSuccess) return bro_fail(ctx, e, "bro_copy_kernel launch");
         ctx->launches += 1;
         if (overlap) {

@@ -73,8 +73,10 @@ extern "C" int bro_parse_kernel_launch(const BroLaunch* p, int grid, cudaStream_
 // bro_batch_sizes: turn the internal hand-over statuses into BRO_ST_SizeUnknown
 extern "C" int bro_sizes_finish_launch(int32_t* status, uint32_t n, cudaStream_t stream);
 // two-phase path, phase two: the copy kernel (one warp per stream) (bro_kernels_copy.cu)
+// two shapes of the same kernel (0: 2 CTAs x 10 warps per SM, no spills -- batches that fill the GPU; 1: 3 x 8 warps -- small
+// batches, where the streams a warp takes one after the other are what the kernel costs); blocks_per_sm[2]
 extern "C" int bro_copy_kernel_occupancy(int* blocks_per_sm);
-extern "C" int bro_copy_kernel_warps_per_cta();
-extern "C" int bro_copy_kernel_launch(const BroLaunch* p, int grid, cudaStream_t stream);
+extern "C" int bro_copy_kernel_warps_per_cta(int shape);
+extern "C" int bro_copy_kernel_launch(const BroLaunch* p, int grid, int shape, cudaStream_t stream);
 // order[] <- stream indices grouped by compressed-size class, largest first.  scratch: 512 uint32.
 extern "C" int bro_order_launch(const uint64_t* in_off, uint32_t n, uint32_t* order, uint32_t* scratch, uint32_t* gate, cudaStream_t stream);

@@ -37,6 +37,15 @@
 #ifndef BRO_COPY_MIN_BLOCKS
 #define BRO_COPY_MIN_BLOCKS 2
 #endif
+// The second shape, 3 CTAs of 8 warps (80 registers): 20 % more warps per SM for a batch so small that what it costs is the
+// number of streams a warp has to take one after the other (a rank's share of a batch under strong scaling: 12,500 streams are
+// 3.5 per warp with this shape, 4.2 -- i.e. five rounds instead of four -- with the first).  The host chooses (bro_abi.cu).
+#ifndef BRO_COPY_WARPS_SMALL
+#define BRO_COPY_WARPS_SMALL 8
+#endif
+#ifndef BRO_COPY_MIN_BLOCKS_SMALL
+#define BRO_COPY_MIN_BLOCKS_SMALL 3
+#endif
 #ifndef BRO_COPY_PIECES
 #define BRO_COPY_PIECES 4     // long records: pieces in flight per warp (their data is held in registers)
 #endif
@@ -312,8 +321,8 @@ __device__ __forceinline__ void bro_run_pieces_win(uint8_t* out, uint32_t out_mi
     }
 }
 
-template <int WARPS>
-__global__ void __launch_bounds__(WARPS * 32, BRO_COPY_MIN_BLOCKS) bro_copy_kernel(BroLaunch p) {
+template <int WARPS, int MINB>
+__global__ void __launch_bounds__(WARPS * 32, MINB) bro_copy_kernel(BroLaunch p) {
     if (p.gate && p.gate[1]) return;       // AUTO: this batch goes to the fused kernel as a whole
     // (values derived from %tid come out of a shuffle so that ptxas keeps them in registers instead of re-reading the special
     // register and redoing the arithmetic wherever they are used)
@@ -584,14 +593,19 @@ __global__ void __launch_bounds__(WARPS * 32, BRO_COPY_MIN_BLOCKS) bro_copy_kern
     }
 }
 
+// shape 0: the throughput shape, 1: the small-batch shape
 extern "C" int bro_copy_kernel_occupancy(int* blocks_per_sm) {
-    return (int)cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, bro_copy_kernel<BRO_COPY_WARPS>,
-                                                              BRO_COPY_WARPS * 32, 0);
+    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm[0], bro_copy_kernel<BRO_COPY_WARPS, BRO_COPY_MIN_BLOCKS>,
+                                                                  BRO_COPY_WARPS * 32, 0);
+    if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm[1], bro_copy_kernel<BRO_COPY_WARPS_SMALL, BRO_COPY_MIN_BLOCKS_SMALL>,
+                                                                            BRO_COPY_WARPS_SMALL * 32, 0);
+    return (int)e;
 }
-extern "C" int bro_copy_kernel_warps_per_cta() { return BRO_COPY_WARPS; }
+extern "C" int bro_copy_kernel_warps_per_cta(int shape) { return shape ? BRO_COPY_WARPS_SMALL : BRO_COPY_WARPS; }
 
-extern "C" int bro_copy_kernel_launch(const BroLaunch* p, int grid, cudaStream_t stream) {
+extern "C" int bro_copy_kernel_launch(const BroLaunch* p, int grid, int shape, cudaStream_t stream) {
     (void)cudaGetLastError();
-    bro_copy_kernel<BRO_COPY_WARPS><<<grid, BRO_COPY_WARPS * 32, 0, stream>>>(*p);
+    if (shape) bro_copy_kernel<BRO_COPY_WARPS_SMALL, BRO_COPY_MIN_BLOCKS_SMALL><<<grid, BRO_COPY_WARPS_SMALL * 32, 0, stream>>>(*p);
+    else bro_copy_kernel<BRO_COPY_WARPS, BRO_COPY_MIN_BLOCKS><<<grid, BRO_COPY_WARPS * 32, 0, stream>>>(*p);
     return (int)cudaGetLastError();
 }
