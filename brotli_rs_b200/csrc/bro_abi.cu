@@ -322,7 +322,30 @@ extern "C" int bro_batch_decode(bro_ctx* ctx, const uint8_t* d_in, const uint64_
         e = (cudaError_t)bro_order_launch(d_in_off, n, d_order, ctx->d_order_scratch, p.gate, s);
         if (e != cudaSuccess) return bro_fail(ctx, e, "bro_order kernels launch");
         ctx->launches += 3;
-        const uint32_t tb = (uint32_t)bro_parse_kernel_block();
+        uint32_t tb = (uint32_t)bro_parse_kernel_block();
+        // A batch of several waves (more streams than resident lanes): fewer warps per SM.  The parse kernel's throughput per SM
+        // saturates at ten warps (a full wave of the headline streams takes 3.05 / 3.45 / 3.9 ms with 10 / 11 / 12 warps per SM,
+        // i.e. 105 / 102 / 98 streams per ms), and what a batch costs is its waves, the last one nearly in full however few
+        // streams it holds: cost(w) = wave time(w) x (waves + 0.35 x the empty part of the last wave), fitted to batches of
+        // 60,000 ... 160,000 streams (profiles/r02_kernel_variants.md section 10).  The 100,000 headline streams are two even
+        // waves of eleven warps: 6.76 ms against 7.07 ms with twelve and 7.54 ms with ten.
+        {
+            const uint32_t full = (uint32_t)ctx->grid_t * tb;                     // resident lanes with the full block
+            if (n > full && !ctx->parse_lanes && tb == 384u) {
+                static const float wave_ms[3] = {3.05f, 3.45f, 3.9f};
+                float best = 0.f;
+                uint32_t best_w = 12u;
+                for (uint32_t w = 10u; w <= 12u; w++) {
+                    const float waves = (float)n / (float)((uint32_t)ctx->grid_t * 32u * w);
+                    const float frac = waves - (float)(uint32_t)waves;
+                    const float cost = wave_ms[w - 10u] * (waves + (frac > 0.f ? 0.35f * (1.f - frac) : 0.f));
+                    if (w == 10u || cost < best) { best = cost; best_w = w; }
+                }
+                tb = best_w * 32u;
+            }
+            const char* pw = getenv("BRO_B200_PARSE_WARPS");
+            if (pw && atoi(pw) >= 2 && (uint32_t)atoi(pw) * 32u <= (uint32_t)bro_parse_kernel_block()) tb = (uint32_t)atoi(pw) * 32u;
+        }
         // A batch smaller than the resident lanes is spread over all SMs: every warp takes fewer streams (a warp's lockstep
         // steps then serve fewer, busier lanes, and a stream's latency -- which is what a small batch costs -- drops)
         const uint32_t warps_total = (uint32_t)ctx->grid_t * (tb / 32u);
@@ -351,7 +374,7 @@ extern "C" int bro_batch_decode(bro_ctx* ctx, const uint8_t* d_in, const uint64_
         }
         p.arena = ctx->d_arena_t; p.counter = ctx->d_counter; p.order = d_order; p.roots = ctx->d_roots;
         if (ctx->timing) BRO_CUDA(ctx, cudaEventRecord(ctx->ev[1], s));
-        e = ctx->debug_no_parse ? cudaSuccess : (cudaError_t)bro_parse_kernel_launch(&p, grid_t, s);
+        e = ctx->debug_no_parse ? cudaSuccess : (cudaError_t)bro_parse_kernel_launch(&p, grid_t, (int)tb, s);
         if (e != cudaSuccess) return bro_fail(ctx, e, "bro_parse_kernel launch");
         ctx->launches += 1;
         p.counter = ctx->d_counter + 3; p.order = NULL;
@@ -452,7 +475,7 @@ extern "C" int bro_batch_sizes(bro_ctx* ctx, const uint8_t* d_in, const uint64_t
     if ((uint32_t)grid_t > (n + tb - 1) / tb) grid_t = (int)((n + tb - 1) / tb);
     p.lanes = 32;
     p.arena = ctx->d_arena_t; p.counter = ctx->d_counter; p.order = ctx->d_order; p.roots = ctx->d_roots;
-    e = (cudaError_t)bro_parse_kernel_launch(&p, grid_t, s);
+    e = (cudaError_t)bro_parse_kernel_launch(&p, grid_t, 0, s);
     if (e != cudaSuccess) return bro_fail(ctx, e, "bro_parse_kernel launch");
     ctx->launches += 1;
     e = (cudaError_t)bro_sizes_finish_launch(d_status, n, s);          // internal hand-over statuses -> BRO_SIZE_UNKNOWN

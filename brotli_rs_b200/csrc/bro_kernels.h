@@ -69,7 +69,7 @@ extern "C" int bro_parse_kernel_occupancy(int* blocks_per_sm);
 extern "C" int bro_parse_kernel_block();
 extern "C" size_t bro_parse_kernel_arena_bytes();
 extern "C" size_t bro_parse_kernel_roots_bytes();
-extern "C" int bro_parse_kernel_launch(const BroLaunch* p, int grid, cudaStream_t stream);
+extern "C" int bro_parse_kernel_launch(const BroLaunch* p, int grid, int threads, cudaStream_t stream);   // threads: 0 = the full block
 // bro_batch_sizes: turn the internal hand-over statuses into BRO_ST_SizeUnknown
 extern "C" int bro_sizes_finish_launch(int32_t* status, uint32_t n, cudaStream_t stream);
 // two-phase path, phase two: the copy kernel (one warp per stream) (bro_kernels_copy.cu)

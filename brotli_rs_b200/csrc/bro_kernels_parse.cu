@@ -226,8 +226,14 @@ extern "C" int bro_parse_kernel_block() { return BRO_PARSE_BLOCK; }
 extern "C" size_t bro_parse_kernel_arena_bytes() { return 2u * (size_t)BRO_THREAD_ARENA_STRIDE_U16; }
 extern "C" size_t bro_parse_kernel_roots_bytes() { return 0; }   // (round 1 kept literal tables in HBM; everything is on chip now)
 
-extern "C" int bro_parse_kernel_launch(const BroLaunch* p, int grid, cudaStream_t stream) {
+// threads: a multiple of 32 up to bro_parse_kernel_block() (0 = that).  The kernel is compiled for the full block (its
+// registers), but a launch may bring fewer warps per SM: throughput saturates at 10-11 warps per SM and the twelfth costs
+// more in contention than it adds (profiles/r02_kernel_variants.md section 10), so the host sizes the block to the batch.
+extern "C" int bro_parse_kernel_launch(const BroLaunch* p, int grid, int threads, cudaStream_t stream) {
     (void)cudaGetLastError();
-    bro_parse_kernel<<<grid, BRO_PARSE_BLOCK, BRO_PARSE_SMEM, stream>>>(*p);
+    if (threads <= 0 || threads > BRO_PARSE_BLOCK) threads = BRO_PARSE_BLOCK;
+    threads = (threads + 31) & ~31;
+    if (threads < 64) threads = 64;                    // (the CTA's first 48 threads fill the insert/copy length table)
+    bro_parse_kernel<<<grid, threads, (size_t)threads * BRO_TL_BYTES, stream>>>(*p);
     return (int)cudaGetLastError();
 }
