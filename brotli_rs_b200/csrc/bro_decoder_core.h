@@ -2161,15 +2161,16 @@ BRO_FN int bro_next_metablock(BroDec& d, bool after_last, uint32_t& is_last, uin
             // An empty metadata block that starts on a byte boundary is the single byte 0x06 (ISLAST 0, MNIBBLES 3, reserved bit
             // 0, MSKIPBYTES 0, two zero fill bits; src/lib.rs:1617-1683): the reference's data/empty.compressed.17 / .18 hold
             // 65,537 of them in a row, 12 % of the corpus batch's warp time when they took the general route below.
-            // (.18: 65,537 blocks of three bytes -- 0x16 = the same with MSKIPBYTES 1, the skip length minus one, the bytes skipped;
-            // up to two skipped bytes stay inside one window read)
+            // (.18: 65,537 blocks of three bytes -- the same header with MSKIPBYTES 1, followed AT ONCE, i.e. from bit 6 on, by the
+            // eight bits of the skip length minus one, then two zero fill bits, then the bytes skipped; up to two skipped bytes
+            // stay inside one window read)
             bro_refill(d.in);
             while ((bro_avail(d.in) & 7u) == 0u && bro_avail(d.in) >= 8u) {
                 const uint32_t pk = bro_peek(d.in);
                 uint32_t take = 0;
                 if ((pk & 0xffu) == 0x06u) take = 8u;
-                else if ((pk & 0xffu) == 0x16u && bro_avail(d.in) >= 16u) {
-                    const uint32_t skip = ((pk >> 8) & 0xffu) + 1u;
+                else if ((pk & 0xc03fu) == 0x0016u && bro_avail(d.in) >= 16u) {
+                    const uint32_t skip = ((pk >> 6) & 0xffu) + 1u;
                     if (skip <= 2u && bro_avail(d.in) >= 16u + 8u * skip) take = 16u + 8u * skip;
                 }
                 if (take == 0u) break;

@@ -125,6 +125,26 @@ def test_mutation_fuzz(dec):
     assert len(set(int(s) for s in status)) >= 15
 
 
+def test_metadata_block_runs(dec):
+    """runs of metadata meta-blocks (src/lib.rs:1617-1683; the byte-at-a-time fast path of bro_next_metablock): intact, truncated,
+    with bytes behind their end, with a corrupt header byte and desynchronised streams (tests/test_hostsim_parity.py builds them)"""
+    from test_hostsim_parity import _metadata_stream
+    rng = np.random.default_rng(18)
+    streams = []
+    for trial in range(1200):
+        n = int(rng.integers(1, 40))
+        r = int(rng.integers(0, 4))
+        corrupt = (int(rng.integers(0, n)), int(rng.choice([0x0e, 0x46, 0x86, 0x07, 0x36, 0x17, 0x00, 0xff]))) if r == 0 else None
+        s, _ = _metadata_stream(rng, n, corrupt=corrupt, desync=trial % 2 == 1)
+        if r == 1:
+            s = s[: int(rng.integers(1, len(s)))]
+        elif r == 2:
+            s = s + rng.integers(0, 256, int(rng.integers(1, 4)), dtype=np.uint8).tobytes()
+        streams.append(s)
+    st = check_batch(dec, streams, [64] * len(streams), "metadata runs")
+    assert len(set(int(x) for x in st)) >= 6
+
+
 def test_slot_guard_bytes(dec):
     """no stream writes past its slot: sentinel bytes between slots survive"""
     import torch

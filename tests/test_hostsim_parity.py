@@ -359,3 +359,67 @@ def test_largest_window_far_reference():
     assert (st, out) == (0, raw)
     st, served, calls, max_in, max_out = hostsim.stream_decode(comp, [1 << 16], out_cap=1 << 20)
     assert (st, served) == (0, raw) and max_out <= 1 << 25
+
+
+# ---- runs of metadata meta-blocks (src/lib.rs:1617-1683): the byte-at-a-time fast path of bro_next_metablock ----
+
+def _metadata_stream(rng, n_blocks, tail=b"\x03", corrupt=None, desync=False):
+    """WBITS 16 + an empty metadata block (one byte, 0x0c: the stream is byte aligned behind it), then n_blocks metadata blocks on
+    byte boundaries and the empty last meta-block (0x03).  A metadata block: ISLAST 0, MNIBBLES 3, reserved 0, MSKIPBYTES k (six
+    bits), then AT ONCE k bytes of skip length minus one, then zero fill bits up to the byte boundary, then the bytes skipped:
+    0x06 for k = 0; 16 bits 0x16 | (L - 1) << 6 for k = 1; 24 bits 0x26 | (L - 1) << 6 for k = 2 (the reference combines the two
+    length bytes its own way, quirk Q1: whatever it makes of them, both decoders must agree).
+    corrupt = (block index, byte): that block's first byte is replaced.  desync: the skip length is written byte aligned (as a
+    first version of the fast path read it -- wrongly): the decoder then skips too little or too much and takes the random bytes that
+    follow for meta-block headers, which is the best test of those there is."""
+    out = bytearray(b"\x0c")
+    plain = corrupt is None and not desync          # -> the reference decodes it to nothing, cleanly
+    for k in range(n_blocks):
+        kind = int(rng.integers(0, 6))
+        if corrupt is not None and corrupt[0] == k:
+            out.append(corrupt[1])
+            continue
+        if kind <= 1:
+            out.append(0x06)
+        elif kind <= 4:
+            skip = int(rng.integers(1, 6))                      # 1..5 bytes skipped: the fast path takes up to two, the general route the rest
+            hdr = bytes([0x16, skip - 1]) if desync else (0x16 | ((skip - 1) << 6)).to_bytes(2, "little")
+            out += hdr + rng.integers(0, 256, skip, dtype=np.uint8).tobytes()
+        else:
+            skip = int(rng.integers(257, 700))
+            plain = False                                       # (quirk Q1: the reference skips another number of bytes)
+            hdr = bytes([0x26, (skip - 1) & 0xff, (skip - 1) >> 8]) if desync else (0x26 | ((skip - 1) << 6)).to_bytes(3, "little")
+            out += hdr + rng.integers(0, 256, skip, dtype=np.uint8).tobytes()
+    return bytes(out) + tail, plain
+
+
+def test_metadata_block_runs():
+    """status (and the empty output) of streams that are runs of metadata blocks -- intact, truncated, with bytes behind their end,
+    with a corrupt header byte, and desynchronised -- equal the oracle's on the fused logic and on phase one of the two-phase path"""
+    rng = np.random.default_rng(8)
+    seen = set()
+    ok_intact = 0
+    for trial in range(600):
+        n = int(rng.integers(1, 40))
+        corrupt = None
+        r = int(rng.integers(0, 4))
+        desync = trial % 2 == 1
+        if r == 0:
+            corrupt = (int(rng.integers(0, n)), int(rng.choice([0x0e, 0x46, 0x86, 0x07, 0x36, 0x17, 0x00, 0xff])))
+        s, plain = _metadata_stream(rng, n, corrupt=corrupt, desync=desync)
+        if r == 1:
+            s = s[: int(rng.integers(1, len(s)))]                # truncated
+        elif r == 2:
+            s = s + rng.integers(0, 256, int(rng.integers(1, 4)), dtype=np.uint8).tobytes()     # bytes behind the end of the stream
+        st, out = oracle.decode(s)
+        seen.add(st)
+        if r == 3 and plain:
+            assert (st, out) == (0, b""), (trial, st)
+            ok_intact += 1
+        st0, out0 = hostsim.decode(s, cap=64)
+        assert st0 == st and (st != 0 or out0 == out), (trial, st, st0, s.hex())
+        st1, out1, _, _ = hostsim.parse_decode(s, cap=64)
+        if st1 in hostsim.RETRY:
+            continue
+        assert st1 == st and (st != 0 or out1 == out), (trial, st, st1, s.hex())
+    assert ok_intact >= 10 and 0 in seen and len(seen) >= 6, (ok_intact, seen)
