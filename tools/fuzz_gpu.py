@@ -24,13 +24,30 @@ def main():
     ap.add_argument("--seed", type=int, default=1)
     ap.add_argument("--slack", default="tight", choices=["exact", "tight", "generous"])
     ap.add_argument("--streaming", type=int, default=200, help="streams also decoded through Decompressor(streaming=...) (resumable kernel)")
+    ap.add_argument("--blocktypes", type=int, default=0,
+                    help="seed the mutations with this many fresh libbrotli streams of heterogeneous payloads (quality 5-9: literal / "
+                         "insert&copy / distance block types and block switches without literal context modelling) instead of the corpus")
     args = ap.parse_args()
     import fuzzgen
     from brotli_rs_b200 import BatchDecoder
     from oracle import oracle
     data = os.path.join(ROOT, "tests", "golden", "data")
     corpus = [open(os.path.join(data, f), "rb").read() for f in sorted(os.listdir(data)) if ".compressed" in f]
-    streams = list(fuzzgen.mutations(corpus, seed=args.seed, count=args.count)) + [c for c in corpus if len(c) < 70000]
+    if args.blocktypes:
+        enc = fuzzgen.libbrotli_enc()
+        if enc is None:
+            print("libbrotlienc.so.1 not present: --blocktypes needs it")
+            return 2
+        g = np.random.default_rng(args.seed + 77)
+        kinds = ["words", "skewed", "small_alpha", "random", "runs", "repeat2k"]
+        corpus = []
+        for i in range(args.blocktypes):
+            raw = bytearray()
+            size = int(g.integers(20000, 260000))
+            while len(raw) < size:
+                raw += fuzzgen.synthetic_raw(kinds[int(g.integers(len(kinds)))], int(g.integers(1 << 30)), int(g.integers(2000, 40000)))
+            corpus.append(fuzzgen.compress(enc, bytes(raw[:size]), int(g.integers(5, 10)), int(g.integers(16, 23))))
+    streams = list(fuzzgen.mutations(corpus, seed=args.seed, count=args.count)) + [c for c in corpus if len(c) < 70000 or args.blocktypes]
     rng = np.random.default_rng(args.seed)
     from brotli_rs_b200.batch import pack_streams, slot_offsets
     caps = []
