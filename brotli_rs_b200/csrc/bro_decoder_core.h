@@ -96,7 +96,11 @@ BRO_FN uint32_t bro_group_mask() { return (BRO_W == 32u ? 0xffffffffu : ((1u << 
 BRO_FN uint32_t bro_shfl(uint32_t v, unsigned src) { return __shfl_sync(bro_group_mask(), v, (int)src, (int)BRO_W); }
 BRO_FN uint32_t bro_match_any(uint32_t v) { return __match_any_sync(bro_group_mask(), v) >> bro_group_shift(); }
 BRO_FN uint32_t bro_lanemask_lt() { return (1u << bro_lane()) - 1u; }
+#if defined(BRO_WARPSIM)
+#define bro_syncwarp() bro_ws_syncwarp_at(__LINE__)   /* the simulation counts the barriers by source line and can leave one out */
+#else
 BRO_FN void bro_syncwarp() { __syncwarp(bro_group_mask()); }
+#endif
 #endif
 BRO_FN uint32_t bro_brev(uint32_t x) { return __brev(x); }
 BRO_FN uint32_t bro_popc(uint32_t x) { return (uint32_t)__popc(x); }
@@ -1447,7 +1451,7 @@ BRO_FN int bro_resolve_distance(BroDec& d, uint32_t dcode, uint32_t npostfix, ui
 #if !defined(BRO_PARSE)   /* the fused command loops (the two-phase path has its own: bro_parse.h) */
 // Reference to a 256-entry root table held on chip (shared memory in the group modes): a 32-bit shared-window
 // address, so that a lookup is one add and one LDS and the base lives in ONE register for the whole loop.
-#if defined(BRO_SERIAL)
+#if defined(BRO_SERIAL) || defined(BRO_WARPSIM)   /* (BRO_WARPSIM: the 32-lane form compiled for the host, bro_warpsim.cpp -- CPU test-suite only) */
 typedef const uint16_t* BroRoot;
 BRO_FN BroRoot bro_root_ref(const uint16_t* p) { return p; }
 BRO_FN uint32_t bro_root_get(BroRoot r, uint32_t idx) { return r[idx]; }

@@ -144,10 +144,11 @@ RESUME_HEADER, RESUME_LAST, RESUME_ENDED = 1, 2, 4
 UNEXPECTED_EOF, EXPECTED_END_OF_STREAM, OUTPUT_TOO_SMALL = 24, 2, 100
 
 
-def stream_decode(data: bytes, chunk_sizes, out_cap=1 << 16, quirks=0, max_calls=100000):
+def stream_decode(data: bytes, chunk_sizes, out_cap=1 << 16, quirks=0, max_calls=100000, step=None):
     """The streaming reader's loop (bro_reader_* in bro_abi.cu) over the host simulation of the resumable decode: the
     input arrives in pieces of chunk_sizes (cycled), the output buffer holds the history (at most a window) plus what one
-    call produces.  -> (final status, bytes served before it, calls, largest input buffer, largest output buffer)."""
+    call produces.  -> (final status, bytes served before it, calls, largest input buffer, largest output buffer).
+    step(buf, out, n_out, quirks, ck) -> status: another implementation of the one call (tests/warpsim.py: the 32-lane form)."""
     L = lib()
     L.bro_hostsim_decode_resume.restype = ctypes.c_int
     L.bro_hostsim_decode_resume.argtypes = [ctypes.c_char_p, ctypes.c_size_t, ctypes.c_void_p, ctypes.c_size_t,
@@ -171,7 +172,10 @@ def stream_decode(data: bytes, chunk_sizes, out_cap=1 << 16, quirks=0, max_calls
         max_in = max(max_in, len(buf))
         n_out = ctypes.c_size_t()
         before = (ck.in_bits, ck.pos, ck.flags)
-        st = L.bro_hostsim_decode_resume(buf, len(buf), ctypes.addressof(out), len(out), ctypes.byref(n_out), quirks, ctypes.byref(ck))
+        if step is None:
+            st = L.bro_hostsim_decode_resume(buf, len(buf), ctypes.addressof(out), len(out), ctypes.byref(n_out), quirks, ctypes.byref(ck))
+        else:
+            st = step(buf, out, n_out, quirks, ck)
         calls += 1
         assert calls <= max_calls, "the streaming loop does not terminate"
         progress = (ck.in_bits, ck.pos, ck.flags) != before

@@ -1,0 +1,271 @@
+"""CPU-side check of the FUSED kernel's 32-lane code (bro_decoder_core.h with BRO_W = 32, exactly what
+bro_decode_warp_kernel and bro_decode_resume_kernel compile) against the oracle: tests/warpsim.py runs the 32 lanes as
+fibers that meet at the warp intrinsics, in ascending, descending and shuffled lane order, at every alignment of the
+compressed stream and of the output slot.  The second half is a race check under the CUDA memory model (ThreadSanitizer
+over the same fibers; only __syncwarp orders memory between lanes), including the global-memory buffers that
+compute-sanitizer's racecheck does not see.  The GPU parity tests proper are tests/test_gpu_parity.py."""
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+import fuzzgen
+import warpsim
+from conftest import ROOT, corpus_files, stream_vectors
+from oracle import oracle
+
+pytestmark = pytest.mark.skipif(not warpsim.available(), reason="the fiber switch of bro_warpsim.cpp is x86-64 only")
+
+CORE = os.path.join(ROOT, "brotli_rs_b200", "csrc", "bro_decoder_core.h")
+
+
+def _check(stream, label, cap=None, quirks=0, configs=None):
+    st, out = oracle.decode(stream, quirks=quirks)
+    if cap is None:
+        cap = len(out) if st == 0 else len(out) + (1 << 16)
+    for latency, order, in_mis, out_mis in configs or [(False, warpsim.ASCENDING, 0, 0)]:
+        warpsim.set_alignment(in_mis, out_mis)
+        st1, out1 = warpsim.decode(stream, cap=cap, quirks=quirks, latency=latency, order=order, seed=in_mis + 1)
+        assert st1 == st and (st != 0 or out1 == out), (label, latency, order, in_mis, out_mis, st, st1)
+    warpsim.set_alignment(0, 0)
+    return st
+
+
+def _configs(rng, n):
+    """n (build, lane order, stream alignment mod 128, slot alignment mod 16) tuples; both builds and all orders appear"""
+    out = []
+    for k in range(n):
+        out.append((bool(k & 1), warpsim.ORDERS[(k >> 1) % 3], int(rng.integers(128)), int(rng.integers(16))))
+    return out
+
+
+def test_corpus_and_vectors():
+    rng = np.random.default_rng(2)
+    for name, comp, _ in corpus_files():
+        big = len(comp) > 100000
+        _check(comp, name, configs=_configs(rng, 2 if big else 6))
+    for name, inp, _, _ in stream_vectors():
+        if len(inp) > 100000:
+            continue
+        _check(inp, name, configs=_configs(rng, 6))
+
+
+def test_every_slot_alignment_of_the_copy_streams():
+    """the warp copies (bro_lz_copy / bro_copy_far: ragged head, 16-byte vectors, ragged tail; periodic fills) at all 16
+    alignments of the slot, in all three lane orders"""
+    names = ("backward65536.compressed", "zeros.compressed", "quickfox_repeated.compressed", "compressed_file.compressed",
+             "random_org_10k.bin.compressed", "64x.compressed", "ukkonooa.compressed")
+    for name, comp, _ in corpus_files():
+        if name in names:
+            _check(comp, name, configs=[(False, order, 8 * m + 3, m) for m in range(16) for order in warpsim.ORDERS])
+
+
+def test_mutation_fuzz():
+    corpus = [c for _, c, _ in corpus_files()]
+    rng = np.random.default_rng(17)
+    seen = set()
+    for m in fuzzgen.mutations(corpus, seed=21, count=1500, max_len=52000):
+        st, out = oracle.decode(m)
+        cap = len(out) if st == 0 else len(out) + (1 << 16)
+        if rng.random() < 0.25:
+            cap = int(rng.integers(0, len(out) + 100))
+        o, ol, sts = oracle.decode_batch(np.frombuffer(m, dtype=np.uint8), np.array([0, len(m)], dtype=np.uint64),
+                                         np.array([0, cap], dtype=np.uint64))
+        st0, out0 = int(sts[0]), o[: int(ol[0])].tobytes()
+        latency, order, in_mis, out_mis = _configs(rng, int(rng.integers(1, 7)))[-1]
+        warpsim.set_alignment(in_mis, out_mis)
+        st1, out1 = warpsim.decode(m, cap=cap, latency=latency, order=order, seed=len(seen))
+        assert st1 == st0 and (st0 != 0 or out1 == out0), (st0, st1, m[:16].hex(), len(m), cap, latency, order, in_mis, out_mis)
+        seen.add(st0)
+    warpsim.set_alignment(0, 0)
+    assert len(seen) >= 15
+
+
+def test_fresh_streams():
+    """every quality band of libbrotli (1: one code of each kind; 5-9: block types; 10-11: context modelling -> the general loop
+    with its on-chip tables and, in the latency build, the 10-bit literal root)"""
+    enc = fuzzgen.libbrotli_enc()
+    if enc is None:
+        pytest.skip("system libbrotlienc not present")
+    rng = np.random.default_rng(4)
+    k = 0
+    for kind in ("random", "skewed", "repeat2k", "runs", "words", "small_alpha"):
+        for q, lgwin, size in ((1, 18, 30000), (5, 16, 70000), (9, 10, 20000), (11, 22, 40000), (11, 16, 9000)):
+            raw = fuzzgen.synthetic_raw(kind, 100 + k, size)
+            k += 1
+            comp = fuzzgen.compress(enc, raw, q, lgwin)
+            for latency, order, in_mis, out_mis in _configs(rng, 4):
+                warpsim.set_alignment(in_mis, out_mis)
+                assert warpsim.decode(comp, cap=len(raw), latency=latency, order=order) == (0, raw), (kind, q, lgwin, latency, order)
+    # heterogeneous streams: literal block types without context modelling (the lane-parallel chunks of the general loop)
+    kinds = ["words", "skewed", "small_alpha", "random", "runs", "repeat2k"]
+    for i in range(6):
+        raw = bytearray()
+        while len(raw) < 90000:
+            raw += fuzzgen.synthetic_raw(kinds[int(rng.integers(len(kinds)))], int(rng.integers(1 << 30)), int(rng.integers(2000, 30000)))
+        raw = bytes(raw)
+        comp = fuzzgen.compress(enc, raw, int(rng.integers(5, 10)), int(rng.integers(16, 23)))
+        for latency, order, in_mis, out_mis in _configs(rng, 4):
+            warpsim.set_alignment(in_mis, out_mis)
+            assert warpsim.decode(comp, cap=len(raw), latency=latency, order=order) == (0, raw), (i, latency, order)
+    warpsim.set_alignment(0, 0)
+
+
+def test_quirk_vectors_and_dictionary_kats():
+    """SURVEY appendix D in both quirk modes, and every transform id x word length (tests/dictgen.py) through the 32-lane
+    bro_dict_word (reference src/transformation/mod.rs:84-209, src/lib.rs:1506-1540)"""
+    import dictgen
+    for hx in ("82000000445008122001", "02000000445008122b0106", "02000000445008122a0102", "02000000445008122a0108",
+               "e200000044501812a6fb01", "4c8000" + "00" * 257 + "03"):
+        for quirks in (0, 1):
+            _check(bytes.fromhex(hx), hx, cap=1024, quirks=quirks, configs=[(False, o, 5, 3) for o in warpsim.ORDERS])
+    seen = set()
+    k = 0
+    for quirks in (0, 1):
+        for label, s, st, out in dictgen.kat_batch(oracle, quirks, indices_per_length=2):
+            k += 1
+            warpsim.set_alignment(k % 128, k % 16)
+            st1, out1 = warpsim.decode(s, cap=64, quirks=quirks, order=warpsim.ORDERS[k % 3], latency=bool(k & 1))
+            assert st1 == st and (st != 0 or out1 == out), (label, quirks, st, st1)
+            seen.add(st)
+    warpsim.set_alignment(0, 0)
+    assert 0 in seen and len(seen) >= 2
+
+
+def test_stream_resume():
+    """the resume kernel's 32-lane code behind the streaming reader's loop: input in pieces, bounded buffers"""
+    rng = np.random.default_rng(6)
+    for name, comp, _ in corpus_files():
+        if len(comp) > 60000:
+            continue
+        st, out = oracle.decode(comp)
+        for chunks, order in (([7], warpsim.DESCENDING), ([int(x) for x in rng.integers(1, 3000, 16)], warpsim.SHUFFLED)):
+            if chunks == [7] and len(comp) > 5000:
+                chunks = [997]
+            st1, served, calls, _, _ = warpsim.stream_decode(comp, chunks, order=order)
+            assert st1 == st and (served == out if st == 0 else out.startswith(served)), (name, chunks[:3], st, st1)
+    corpus = [c for _, c, _ in corpus_files()]
+    for m in fuzzgen.mutations(corpus, seed=31, count=250, max_len=30000):
+        st, out = oracle.decode(m)
+        chunks = [int(x) for x in rng.integers(1, max(2, len(m)), 4)]
+        st1, served, _, _, _ = warpsim.stream_decode(m, chunks, order=warpsim.ORDERS[len(m) % 3])
+        assert st1 == st and (served == out if st == 0 else out.startswith(served)), (m[:16].hex(), chunks, st, st1)
+
+
+# ---- the barriers ----
+
+def _barrier_line(pattern):
+    """line number of the first bro_syncwarp() at or after the line matching `pattern` in bro_decoder_core.h"""
+    lines = open(CORE).read().split("\n")
+    for i, text in enumerate(lines):
+        if re.search(pattern, text):
+            for j in range(i, len(lines)):
+                if "bro_syncwarp();" in lines[j]:
+                    return j + 1
+    raise AssertionError("pattern not found: " + pattern)
+
+
+def test_lane_orders_notice_a_missing_barrier():
+    """mutation check of the simulation itself: with the bro_syncwarp() between the prefix of a periodic fill and the copy
+    that reads it left out (the read-after-write round 1's review found by inspection), one of the lane orders must produce
+    wrong bytes -- and with it in place none does (test_every_slot_alignment_of_the_copy_streams)"""
+    line = _barrier_line(r"i < n0; i \+= BRO_W\) dst\[i\] = src\[i % dist\]")
+    comp = [c for n, c, _ in corpus_files() if n == "backward65536.compressed"][0]
+    st, out = oracle.decode(comp)
+    wrong = 0
+    with warpsim.drop_sync(line):
+        for m in range(16):
+            for order in warpsim.ORDERS:
+                warpsim.set_alignment(0, m)
+                try:
+                    wrong += warpsim.decode(comp, cap=len(out), order=order) != (st, out)
+                except AssertionError:
+                    wrong += 1
+    warpsim.set_alignment(0, 0)
+    assert wrong >= 1
+    assert warpsim.decode(comp, cap=len(out), order=warpsim.DESCENDING) == (st, out)
+
+
+def _tsan_binary():
+    build = os.path.join(ROOT, "tests", "_build")
+    os.makedirs(build, exist_ok=True)
+    exe = os.path.join(build, "warpsim_tsan")
+    csrc = os.path.join(ROOT, "brotli_rs_b200", "csrc")
+    srcs = [os.path.join(csrc, "bro_warpsim.cpp"), os.path.join(ROOT, "oracle", "dict_blob.c")]
+    deps = srcs + [os.path.join(csrc, f) for f in ("bro_decoder_core.h", "bro_records.h", "bro_status.h", "bro_tables_generated.h")]
+    if not (os.path.exists(exe) and all(os.path.getmtime(exe) >= os.path.getmtime(d) for d in deps)):
+        cmd = ["g++", "-std=c++17", "-O1", "-g", "-fsanitize=thread", "-DBRO_WARPSIM_MAIN", "-Wno-unknown-pragmas", "-o", exe] + srcs + \
+              ["-Wa,-I" + os.path.join(ROOT, "brotli_rs_b200", "data")]
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if r.returncode != 0:
+            pytest.skip("g++ -fsanitize=thread does not build here: " + r.stderr[-300:])
+    probe = subprocess.run([exe], capture_output=True, text=True)
+    if "usage" not in probe.stderr:
+        pytest.skip("ThreadSanitizer does not start here: " + probe.stderr[-300:])
+    return exe
+
+
+def _tsan_run(exe, files, latency=0, order=0, quirks=0, align=(0, 0), drop=None):
+    """-> (ThreadSanitizer reports, {file: (status, out_len, fnv1a64 hex)}, stderr)"""
+    env = dict(os.environ, BRO_WS_ALIGN="%d,%d" % align, TSAN_OPTIONS="exitcode=66 history_size=4")
+    if drop is not None:
+        env["BRO_WS_DROP_SYNC"] = str(drop)
+    r = subprocess.run([exe, str(latency), str(order), "1", str(quirks), "0"] + ["%s:%d" % f for f in files], env=env, capture_output=True,
+                       text=True, timeout=600)
+    assert r.returncode in (0, 66), r.stderr[-2000:]
+    res = {}
+    for ln in r.stdout.splitlines():
+        name, st, n, h, err = ln.rsplit(" ", 4)
+        assert err == "0", ln
+        res[name] = (int(st), int(n), h)
+    return r.stderr.count("WARNING: ThreadSanitizer"), res, r.stderr
+
+
+def _fnv(b):
+    h = 1469598103934665603
+    for x in b:
+        h = ((h ^ x) * 1099511628211) & 0xffffffffffffffff
+    return "%016x" % h
+
+
+def test_no_data_race_between_lanes(tmp_path):
+    """the corpus, context-modelled and block-typed fresh streams and mutated streams under the race detector, both builds, several
+    alignments: no byte is stored by one lane and touched by another without a __syncwarp in between -- shared-memory scratch, table
+    arena and output slot alike -- and a left-out barrier IS reported (the detector detects)"""
+    exe = _tsan_binary()
+    files, expect = [], {}
+
+    def add(name, comp):
+        st, out = oracle.decode(comp)
+        p = str(tmp_path / name)
+        open(p, "wb").write(comp)
+        files.append((p, len(out)))
+        expect[p] = (st, out)
+
+    for name, comp, _ in corpus_files():
+        if len(comp) <= 170000:
+            add(name, comp)
+    corpus = [c for _, c, _ in corpus_files()]
+    for i, m in enumerate(fuzzgen.mutations(corpus, seed=77, count=120, max_len=30000)):
+        add("mut%03d" % i, m)
+    enc = fuzzgen.libbrotli_enc()
+    if enc is not None:
+        k = 0
+        for kind in ("words", "skewed", "runs", "repeat2k"):
+            for q, lgwin, size in ((5, 16, 60000), (9, 18, 40000), (11, 16, 30000), (10, 22, 30000)):
+                k += 1
+                add("fresh%02d" % k, fuzzgen.compress(enc, fuzzgen.synthetic_raw(kind, 900 + k, size), q, lgwin))
+    for latency, order, align in ((0, 0, (0, 0)), (1, 1, (77, 5)), (0, 2, (3, 15)), (1, 0, (124, 9))):
+        races, res, err = _tsan_run(exe, files, latency=latency, order=order, align=align)
+        assert races == 0, err[:6000]
+        for p, (st, out) in expect.items():
+            st1, n1, h1 = res[p]
+            assert st1 == st and (st != 0 or (n1, h1) == (len(out), _fnv(out))), (os.path.basename(p), latency, order, align, st, st1)
+    # the detector detects: the barrier in front of pass 2 of the table build (its stores to the per-length positions are read by
+    # other lanes), and the one behind the staging of the general loop's on-chip tables
+    small = [f for f in files if os.path.basename(f[0]) in ("alice29.txt.compressed", "10x10y.compressed", "fresh03", "fresh04")]
+    for pattern in (r"T\[BRO_T_MAXDEPTH \+ 1u\] = 0;", r"if \(hot\.modes\) for \(uint32_t i = lane; i < nl"):
+        races, _, err = _tsan_run(exe, small, drop=_barrier_line(pattern))
+        assert races >= 1, pattern

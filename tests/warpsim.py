@@ -1,0 +1,124 @@
+"""Builds and binds the 32-LANE host simulation of the fused warp-per-stream decoder (brotli_rs_b200/csrc/bro_warpsim.cpp).
+
+CPU TEST-SUITE ONLY.  tests/hostsim.py runs bro_decoder_core.h with a 1-lane warp; this one compiles the very code the
+fused kernel and the resume kernel run (BRO_W = 32) with g++ and executes its 32 lanes as fibers that meet at the warp
+intrinsics, in a lane order the test chooses -- so the lane-parallel table build, the shuffle-fed bit window, the
+lane-parallel literal rounds and the warp copies are checked against the oracle where no GPU exists, and a missing
+__syncwarp shows up as a wrong answer in one of the orders.  The product library never contains or calls it.
+"""
+import ctypes
+import os
+import platform
+import subprocess
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+CSRC = os.path.join(ROOT, "brotli_rs_b200", "csrc")
+BUILD = os.path.join(ROOT, "tests", "_build")
+_LIB = None
+
+ASCENDING, DESCENDING, SHUFFLED = 0, 1, 2
+ORDERS = (ASCENDING, DESCENDING, SHUFFLED)
+SIM_ERRORS = {1: "lanes met at different intrinsics / masks (divergent collective)", 2: "a lane returned while another waited for it",
+              3: "status or output length differs between lanes", 4: "a lane called a collective whose mask does not name it",
+              100: "bytes written outside the output slot"}
+
+
+def available():
+    return platform.machine() == "x86_64"
+
+
+def _build():
+    os.makedirs(BUILD, exist_ok=True)
+    so = os.path.join(BUILD, "libbro_warpsim.so")
+    srcs = [os.path.join(CSRC, "bro_warpsim.cpp"), os.path.join(ROOT, "oracle", "dict_blob.c")]
+    deps = srcs + [os.path.join(CSRC, f) for f in ("bro_decoder_core.h", "bro_records.h", "bro_status.h", "bro_tables_generated.h")]
+    if os.path.exists(so) and all(os.path.getmtime(so) >= os.path.getmtime(d) for d in deps):
+        return so
+    cmd = ["g++", "-std=c++17", "-fPIC", "-shared", "-Wno-unknown-pragmas", "-O2", "-o", so] + srcs + \
+          ["-Wa,-I" + os.path.join(ROOT, "brotli_rs_b200", "data")]
+    subprocess.check_call(cmd)
+    return so
+
+
+class BroResume(ctypes.Structure):
+    """bro_records.h: BroResume == include/brotli_b200.h: bro_resume (layout pinned by tests/test_abi_library.py)"""
+    _fields_ = [("in_bits", ctypes.c_uint64), ("pos", ctypes.c_uint32), ("window", ctypes.c_uint32), ("dist", ctypes.c_uint32 * 4),
+                ("p1", ctypes.c_uint32), ("p2", ctypes.c_uint32), ("flags", ctypes.c_uint32), ("reserved", ctypes.c_uint32)]
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        L = ctypes.CDLL(_build())
+        L.bro_warpsim_decode.restype = ctypes.c_int
+        L.bro_warpsim_decode.argtypes = [ctypes.c_char_p, ctypes.c_size_t, ctypes.c_char_p, ctypes.c_size_t, ctypes.POINTER(ctypes.c_size_t),
+                                         ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_uint64, ctypes.POINTER(ctypes.c_int)]
+        L.bro_warpsim_decode_resume.restype = ctypes.c_int
+        L.bro_warpsim_decode_resume.argtypes = [ctypes.c_char_p, ctypes.c_size_t, ctypes.c_char_p, ctypes.c_size_t, ctypes.POINTER(ctypes.c_size_t),
+                                                ctypes.c_int, ctypes.c_int, ctypes.c_uint64, ctypes.POINTER(BroResume), ctypes.POINTER(ctypes.c_int)]
+        L.bro_warpsim_last_rendezvous.restype = ctypes.c_uint64
+        assert L.bro_warpsim_resume_bytes() == ctypes.sizeof(BroResume)
+        _LIB = L
+    return _LIB
+
+
+def decode(data: bytes, cap: int = 1 << 20, quirks: int = 0, latency: bool = False, order: int = ASCENDING, seed: int = 1):
+    """One stream through the fused kernel's per-warp code.  latency: the latency build (a 10-bit literal root on chip for the
+    general loop's lane-parallel rounds).  -> (status, bytes); raises when the warp itself misbehaved (SIM_ERRORS)."""
+    out = ctypes.create_string_buffer(max(cap, 1))
+    n, err = ctypes.c_size_t(), ctypes.c_int()
+    st = lib().bro_warpsim_decode(data, len(data), out, cap, ctypes.byref(n), quirks, int(latency), order, seed, ctypes.byref(err))
+    if err.value:
+        raise AssertionError("warp simulation: " + SIM_ERRORS.get(err.value, str(err.value)))
+    return st, out.raw[: n.value]
+
+
+def rendezvous():
+    """warp intrinsics executed by the last decode"""
+    return int(lib().bro_warpsim_last_rendezvous())
+
+
+def stream_decode(data: bytes, chunk_sizes, out_cap=1 << 16, quirks=0, order=ASCENDING, seed=1):
+    """tests/hostsim.py's streaming-reader loop with the resume kernel's 32-lane code as the one call"""
+    import hostsim
+    L = lib()
+
+    def step(buf, out, n_out, q, ck):
+        err = ctypes.c_int()
+        st = L.bro_warpsim_decode_resume(buf, len(buf), ctypes.cast(out, ctypes.c_char_p), len(out), ctypes.byref(n_out), q, order, seed,
+                                         ctypes.cast(ctypes.byref(ck), ctypes.POINTER(BroResume)), ctypes.byref(err))
+        if err.value:
+            raise AssertionError("warp simulation: " + SIM_ERRORS.get(err.value, str(err.value)))
+        return st
+
+    return hostsim.stream_decode(data, chunk_sizes, out_cap=out_cap, quirks=quirks, step=step)
+
+
+def sync_hits(reset=True):
+    """{line of bro_decoder_core.h: executions of the bro_syncwarp() there} since the last reset"""
+    import numpy as np
+    hits = np.zeros(4096, dtype=np.uint64)
+    L = lib()
+    L.bro_warpsim_sync_hits.restype = None
+    L.bro_warpsim_sync_hits.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int]
+    L.bro_warpsim_sync_hits(hits.ctypes.data, 4096, int(reset))
+    return {int(i): int(hits[i]) for i in hits.nonzero()[0]}
+
+
+class drop_sync:
+    """with drop_sync(line): the bro_syncwarp() on that line of bro_decoder_core.h is left out (a mutation the lane orders must notice)"""
+
+    def __init__(self, line):
+        self.line = line
+
+    def __enter__(self):
+        lib().bro_warpsim_drop_sync(self.line)
+        return self
+
+    def __exit__(self, *exc):
+        lib().bro_warpsim_drop_sync(-1)
+
+
+def set_alignment(in_mis=0, out_mis=0):
+    """address of the stream's first byte mod 128 and of the output slot's first byte mod 16 for the decodes that follow"""
+    lib().bro_warpsim_set_alignment(in_mis, out_mis)
