@@ -17,7 +17,7 @@ static uint32_t g_sizing = 0;         // next decodes only measure (bro_batch_si
 extern "C" void bro_hostsim_parse_set_sizing(unsigned on) { g_sizing = on; }
 
 // phase two of the next decodes: 0 = the obvious byte loop over the records; 32, 16, 8 = the copy kernel's grouping and
-// piece code with that many lanes per piece (bro_hostsim_copy.cpp)
+// piece code with that many lanes per piece (bro_hostsim_copy.cpp); -1 = none (phase one only)
 static int g_copy_group = 0;
 static uint32_t g_copy_stats[3];
 extern "C" void bro_hostsim_parse_set_copy_group(int group) { g_copy_group = group; }
@@ -83,7 +83,9 @@ extern "C" int bro_hostsim_parse_decode(const uint8_t* in, size_t in_len, uint8_
         else { if (d.imm) bro_parse_round<true>(d, ps, mb); else bro_parse_round<false>(d, ps, mb); steps++; }
     }
     // phase two, the obvious way
-    if (ps.st == BRO_ST_OK && !g_sizing && g_copy_group) {
+    if (g_copy_group < 0) {
+        // phase one only: the caller executes the exported records itself (bro_warpsim_copy.cpp: the copy kernel's own code)
+    } else if (ps.st == BRO_ST_OK && !g_sizing && g_copy_group) {
         static_assert(sizeof(BroRec) == 16, "a record is four words");
         bro_hostsim_copy_exec(out, in, (const uint32_t*)rec, d.nrec, g_copy_group, g_copy_stats);
     } else if (ps.st == BRO_ST_OK && !g_sizing) {

@@ -1,7 +1,9 @@
 // Launch interface between the C ABI (bro_abi.cu) and the kernels (bro_kernels.cu, bro_kernels_parse.cu,
 // bro_kernels_copy.cu, bro_kernels_resume.cu).
 #pragma once
+#if !defined(BRO_WARPSIM)   /* (BRO_WARPSIM: a kernel compiled for the host by the CPU test-suite, bro_warpsim_copy.cpp) */
 #include <cuda_runtime.h>
+#endif
 #include <stddef.h>
 #include <stdint.h>
 

@@ -20,7 +20,9 @@
 //
 // Roofline: HBM.  Algorithmic bytes per stream = output bytes written by records + 16 bytes per record read; sources
 // are re-reads of recent output (L2 hits for windows that fit).
+#if !defined(BRO_WARPSIM)   /* (BRO_WARPSIM: this kernel compiled for the host, 32 lanes as fibers -- CPU test-suite only, bro_warpsim_copy.cpp) */
 #include <cuda_runtime.h>
+#endif
 #include <stdint.h>
 
 #include "bro_copy_piece.h"
@@ -92,6 +94,9 @@
 // Ampere-style asynchronous copy global -> shared, 16 bytes, L2 only (the sources were written moments ago by this very
 // SM's write-through stores and are not in L1 anyway).  No register holds the data, so a lane can have several in
 // flight; cp.async.wait_all makes the lane's own copies visible to itself.
+#if !defined(BRO_WARPSIM)   /* (the simulation supplies these three and has no use for prefetches) */
+#define BRO_PREFETCH_BULK_L2(addr, bytes) asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" :: "l"(addr), "r"(bytes) : "memory")
+#define BRO_PREFETCH_L2(ptr) asm volatile("prefetch.global.L2 [%0];" :: "l"(ptr))
 __device__ __forceinline__ void bro_cp_async16(uint32_t smem_addr, const void* gptr) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(smem_addr), "l"(gptr) : "memory");
 }
@@ -101,6 +106,7 @@ __device__ __forceinline__ uint4 bro_lds128(uint32_t smem_addr) {
     asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(smem_addr));
     return v;
 }
+#endif
 
 // 16 bytes from an arbitrary address: two aligned 16-byte loads and a funnel (the bytes before/after the 16 wanted
 // ones lie in the same 16-byte granules as wanted bytes, i.e. inside the same allocation)
@@ -438,10 +444,9 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) bro_copy_kernel(BroLaunch p)
             if (lane < cnt && (kind == BRO_REC_STORED || (a >= BRO_COPY_PF_DIST && a >= len))) {
                 const uintptr_t s0 = (uintptr_t)(kind == BRO_REC_STORED ? in + a : (const uint8_t*)out + (dst - a));
                 const uint32_t span = len < 1024u ? len : 1024u;
-                asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;"
-                             :: "l"(s0 & ~(uintptr_t)15), "r"((((uint32_t)s0 & 15u) + span + 15u) & ~15u) : "memory");
+                BRO_PREFETCH_BULK_L2(s0 & ~(uintptr_t)15, (((uint32_t)s0 & 15u) + span + 15u) & ~15u);
             }
-            if (b + 32u + lane < n) asm volatile("prefetch.global.L2 [%0];" :: "l"(recs + b + 32u + lane));     // the next records
+            if (b + 32u + lane < n) BRO_PREFETCH_L2(recs + b + 32u + lane);     // the next records
             uint32_t j = 0;
             while (j < cnt) {
                 // the group [j, e): no record reads what a record of the group writes
@@ -593,6 +598,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) bro_copy_kernel(BroLaunch p)
     }
 }
 
+#if !defined(BRO_WARPSIM)
 // shape 0: the throughput shape, 1: the small-batch shape
 extern "C" int bro_copy_kernel_occupancy(int* blocks_per_sm) {
     cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm[0], bro_copy_kernel<BRO_COPY_WARPS, BRO_COPY_MIN_BLOCKS>,
@@ -609,3 +615,4 @@ extern "C" int bro_copy_kernel_launch(const BroLaunch* p, int grid, int shape, c
     else bro_copy_kernel<BRO_COPY_WARPS, BRO_COPY_MIN_BLOCKS><<<grid, BRO_COPY_WARPS * 32, 0, stream>>>(*p);
     return (int)cudaGetLastError();
 }
+#endif

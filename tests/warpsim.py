@@ -122,3 +122,56 @@ class drop_sync:
 def set_alignment(in_mis=0, out_mis=0):
     """address of the stream's first byte mod 128 and of the output slot's first byte mod 16 for the decodes that follow"""
     lib().bro_warpsim_set_alignment(in_mis, out_mis)
+
+
+# ---- the copy kernel (bro_kernels_copy.cu compiled for the host, bro_warpsim_copy.cpp) behind phase one's host simulation ----
+_LIB_COPY = None
+COPY_SOURCES = ("bro_warpsim_copy.cpp", "bro_hostsim_parse.cpp", "bro_hostsim_copy.cpp")
+COPY_DEPS = ("bro_warpsim.h", "bro_kernels_copy.cu", "bro_copy_piece.h", "bro_kernels.h", "bro_decoder_core.h", "bro_parse.h", "bro_records.h",
+             "bro_status.h", "bro_tables_generated.h")
+
+
+def _build_copy():
+    os.makedirs(BUILD, exist_ok=True)
+    so = os.path.join(BUILD, "libbro_warpsim_copy.so")
+    srcs = [os.path.join(CSRC, f) for f in COPY_SOURCES] + [os.path.join(ROOT, "oracle", "dict_blob.c")]
+    deps = srcs + [os.path.join(CSRC, f) for f in COPY_DEPS]
+    if os.path.exists(so) and all(os.path.getmtime(so) >= os.path.getmtime(d) for d in deps):
+        return so
+    cmd = ["g++", "-std=c++17", "-fPIC", "-shared", "-Wno-unknown-pragmas", "-O2", "-o", so] + srcs + \
+          ["-Wa,-I" + os.path.join(ROOT, "brotli_rs_b200", "data")]
+    subprocess.check_call(cmd)
+    return so
+
+
+def two_phase(streams, caps, quirks=0, shape=0, order=ASCENDING, seed=1, in_mis=0, out_mis=0, queue_seed=0):
+    """A batch through the two-phase path: phase one = the parse kernel's per-lane code on the host, phase two = ONE launch of the
+    copy kernel's own code by a simulated warp (shape 0 / 1: the kernel's two instantiations).  -> [(status, bytes)], (bytes moved by
+    records, records executed); a status in hostsim.RETRY means the product would hand that stream to the fused kernel."""
+    import numpy as np
+    global _LIB_COPY
+    if _LIB_COPY is None:
+        L = ctypes.CDLL(_build_copy())
+        L.bro_warpsim_two_phase.restype = ctypes.c_int
+        L.bro_warpsim_two_phase.argtypes = [ctypes.c_void_p] * 6 + [ctypes.c_uint32, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_uint64,
+                                            ctypes.c_uint, ctypes.c_uint, ctypes.c_uint64, ctypes.c_void_p]
+        _LIB_COPY = L
+    n = len(streams)
+    in_off = np.zeros(n + 1, dtype=np.uint64)
+    in_off[1:] = np.cumsum([len(s) for s in streams])
+    out_off = np.zeros(n + 1, dtype=np.uint64)
+    out_off[1:] = np.cumsum(caps)
+    inb = np.frombuffer(b"".join(streams) + b"\0", dtype=np.uint8).copy()
+    out = np.zeros(int(out_off[n]) + 1, dtype=np.uint8)
+    out_len = np.zeros(n, dtype=np.uint64)
+    status = np.zeros(n, dtype=np.int32)
+    stats = np.zeros(2, dtype=np.uint64)
+    err = _LIB_COPY.bro_warpsim_two_phase(inb.ctypes.data, in_off.ctypes.data, out.ctypes.data, out_off.ctypes.data, out_len.ctypes.data,
+                                          status.ctypes.data, n, quirks, shape, order, seed, in_mis, out_mis, queue_seed, stats.ctypes.data)
+    if err:
+        raise AssertionError("warp simulation (copy kernel): " + SIM_ERRORS.get(err, str(err)))
+    res = []
+    for i in range(n):
+        b = int(out_off[i])
+        res.append((int(status[i]), out[b: b + int(out_len[i])].tobytes()))
+    return res, (int(stats[0]), int(stats[1]))
