@@ -193,6 +193,13 @@ BRO_FN void bro_tl_st32(BroTl t, uint32_t b, uint32_t v) {
     uint8_t* p = t.base + bro_tl_off(b);
     p[0] = (uint8_t)v; p[1] = (uint8_t)(v >> 8); p[2] = (uint8_t)(v >> 16); p[3] = (uint8_t)(v >> 24);
 }
+#elif defined(BRO_WARPSIM) && defined(BRO_THREAD_MODE)   /* the parse kernel compiled for the host (bro_warpsim_parse.cpp, CPU test-suite): the same window addresses */
+BRO_FN uint32_t bro_tl_ld8(BroTl t, uint32_t b) { return *ws_smem_ptr(t.base + bro_tl_off(b)); }
+BRO_FN void bro_tl_st8(BroTl t, uint32_t b, uint32_t v) { *ws_smem_ptr(t.base + bro_tl_off(b)) = (uint8_t)v; }
+BRO_FN uint32_t bro_tl_ld16(BroTl t, uint32_t b) { return *(const uint16_t*)ws_smem_ptr(t.base + bro_tl_off(b)); }
+BRO_FN void bro_tl_st16(BroTl t, uint32_t b, uint32_t v) { *(uint16_t*)ws_smem_ptr(t.base + bro_tl_off(b)) = (uint16_t)v; }
+BRO_FN uint32_t bro_tl_ld32(BroTl t, uint32_t b) { return *(const uint32_t*)ws_smem_ptr(t.base + (b << 5)); }
+BRO_FN void bro_tl_st32(BroTl t, uint32_t b, uint32_t v) { *(uint32_t*)ws_smem_ptr(t.base + (b << 5)) = v; }
 #else
 BRO_FN uint32_t bro_tl_ld8(BroTl t, uint32_t b) { uint32_t v; asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(t.base + bro_tl_off(b))); return v; }
 BRO_FN void bro_tl_st8(BroTl t, uint32_t b, uint32_t v) { asm volatile("st.shared.u8 [%0], %1;" :: "r"(t.base + bro_tl_off(b)), "r"(v) : "memory"); }
@@ -383,7 +390,9 @@ BRO_FN void bro_bits_seek(BroBits& s, const uint8_t* a) {
     s.bp = 8u * (off & 3u);
     s.avail = a < s.end ? 8u * (uint32_t)(s.end - a) : 0u;
     if (s.elen == 0u) { s.w0 = s.w1 = s.w2 = 0; return; }     // an empty stream: nothing to read, and nothing is ever consumed
-#if !defined(BRO_HOSTSIM)
+#if defined(BRO_WARPSIM)
+    ws_ring_wait_group(0u);
+#elif !defined(BRO_HOSTSIM)
     asm volatile("cp.async.wait_all;");                         // no request of the old position may land in a slot later
 #endif
     s.w0 = bro_load_word(s, wo);
@@ -392,6 +401,8 @@ BRO_FN void bro_bits_seek(BroBits& s, const uint8_t* a) {
     for (uint32_t j = 0; j < BRO_RING_WORDS; j++) {
 #if defined(BRO_HOSTSIM)
         bro_tl_st32(s.ring, BRO_TL_RING + 4u * j, bro_load_word(s, wo + 12u + 4u * j));
+#elif defined(BRO_WARPSIM)
+        ws_ring_issue(s.ring.base + ((BRO_TL_RING + 4u * j) << 5), s.base + bro_word_offset(s, wo + 12u + 4u * j));
 #else
         asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n\tcp.async.commit_group;"
                      :: "r"(s.ring.base + ((BRO_TL_RING + 4u * j) << 5)), "l"(s.base + bro_word_offset(s, wo + 12u + 4u * j)));
@@ -425,6 +436,20 @@ BRO_FN void bro_refill(BroBits& s) {
         s.pos += 4u;
         s.ri = s.ri + 1u == BRO_RING_WORDS ? 0u : s.ri + 1u;
         s.bp -= 32u;
+    }
+#elif defined(BRO_WARPSIM)
+    // the block below, statement by statement; the asynchronous copies land as late as the wait allows (bro_warpsim_parse.cpp)
+    if (s.bp >= 32u) {
+        const uint32_t slot = s.ring.base + (BRO_TL_RING << 5) + s.ri * 128u;
+        ws_ring_wait_group(BRO_RING_WORDS - 1u);
+        s.w0 = s.w1;
+        s.w1 = s.w2;
+        s.w2 = *(const uint32_t*)ws_smem_ptr(slot);
+        ws_ring_issue(slot, s.base + (s.pos < s.last ? s.pos : s.last));
+        s.pos += 4u;
+        s.ri += 1u;
+        s.bp -= 32u;
+        if (s.ri == BRO_RING_WORDS) s.ri = 0u;
     }
 #else
     asm volatile("{\n\t"

@@ -11,7 +11,9 @@
 // entered by the lanes of a warp TOGETHER: a lane that reaches a meta-block boundary waits (up to BRO_PARSE_PATIENCE
 // rounds of the others) until every lane is at a boundary, and lanes whose stream ended pull their next stream at the
 // same moment.  Streams are handed out by compressed-size class, so the lanes of a warp hold similar streams.
+#if !defined(BRO_WARPSIM)   /* (BRO_WARPSIM: this kernel compiled for the host, 32 lanes as fibers -- CPU test-suite only, bro_warpsim_parse.cpp) */
 #include <cuda_runtime.h>
+#endif
 #include <stdint.h>
 
 #define BRO_THREAD_MODE 1
@@ -54,7 +56,11 @@ __global__ void __launch_bounds__(BRO_PARSE_BLOCK, BRO_PARSE_MIN_BLOCKS) bro_par
     // shared memory: per warp 32 lane-interleaved blocks (the table reader's scratch while a header is read, the decode
     // tables of the current block types inside a meta-block: bro_decoder_core.h, bro_parse.h), per CTA the
     // insert/copy length table.  Nothing of a thread's working set is in local memory.
+#if defined(BRO_WARPSIM)
+    uint8_t* const s_blocks = ws_dynamic_smem;
+#else
     extern __shared__ __align__(16) uint8_t s_blocks[];
+#endif
     __shared__ uint32_t s_ic[48];
     if (tid < 48u) bro_ic_compact_entry(tid, s_ic[tid]);
     __syncthreads();
@@ -139,6 +145,7 @@ __global__ void __launch_bounds__(BRO_PARSE_BLOCK, BRO_PARSE_MIN_BLOCKS) bro_par
     }
 }
 
+#if !defined(BRO_WARPSIM)
 // ---- size-class ordering: 256 classes (8 per power of two of the compressed size), largest class first ----
 __device__ __forceinline__ uint32_t bro_size_class(uint64_t len) {
     uint32_t l = len > 0xffffffffull ? 0xffffffffu : (uint32_t)len;
@@ -237,3 +244,4 @@ extern "C" int bro_parse_kernel_launch(const BroLaunch* p, int grid, int threads
     bro_parse_kernel<<<grid, threads, (size_t)threads * BRO_TL_BYTES, stream>>>(*p);
     return (int)cudaGetLastError();
 }
+#endif

@@ -382,3 +382,83 @@ def test_copy_kernel_no_data_race_between_lanes(tmp_path):
     for pattern in (r"stores of earlier groups are visible", r"done \+= m;"):
         races, _ = run(0, 0, (3, 5), drop=_copy_barrier_line(pattern))
         assert races >= 1, pattern
+
+
+# ---- the parse kernel (phase one) and both kernels of the two-phase path back to back ----
+
+def _kernels_check(streams, label, configs, quirks=0):
+    import hostsim
+    exp = [oracle.decode(s, quirks=quirks) for s in streams]
+    caps = [len(out) for _, out in exp]
+    handed = 0
+    for k, (lanes, order, in_mis, out_mis, hand_out) in enumerate(configs):
+        ho = None if hand_out is None else hand_out(len(streams))
+        res, retry, queue = warpsim.two_phase_kernels(streams, caps, quirks=quirks, lanes=lanes, hand_out=ho, order=order, seed=k + 1, in_mis=in_mis,
+                                                      out_mis=out_mis, copy_shape=k & 1, copy_order=warpsim.ORDERS[(k + 1) % 3])
+        assert sorted(queue) == list(range(len(streams)))
+        for i, ((st, out), (st1, out1)) in enumerate(zip(exp, res)):
+            if st1 in hostsim.RETRY:
+                handed += 1
+                continue
+            assert st1 == st and (st != 0 or out1 == out), (label, i, lanes, order, in_mis, out_mis, st, st1)
+    return handed
+
+
+def test_parse_and_copy_kernels_corpus_batch():
+    """the corpus as one batch through the parse kernel (32 streams to a warp: boundary protocol, hand-out, completion queue, lanes
+    in immediate mode next to lanes that write records, 65,537 empty meta-blocks next to text) and then the copy kernel, which takes
+    the streams in the order the parse kernel finished them"""
+    streams = [c for _, c, _ in corpus_files()]
+    rev = lambda n: list(range(n - 1, -1, -1))
+    assert _kernels_check(streams, "corpus", [(32, warpsim.ASCENDING, 0, 0, None), (32, warpsim.DESCENDING, 5, 9, rev),
+                                              (32, warpsim.SHUFFLED, 13, 3, None), (7, warpsim.SHUFFLED, 2, 15, rev),
+                                              (1, warpsim.ASCENDING, 1, 1, None)]) == 0
+
+
+def test_parse_and_copy_kernels_fresh_mutated_and_sizing():
+    import hostsim
+    rng = np.random.default_rng(12)
+    corpus = [c for _, c, _ in corpus_files()]
+    muts = list(fuzzgen.mutations(corpus, seed=91, count=600, max_len=30000))
+    seen = set(oracle.decode(m)[0] for m in muts)
+    assert len(seen) >= 15
+    _kernels_check(muts, "mutated", [(32, warpsim.SHUFFLED, 7, 11, None), (32, warpsim.DESCENDING, 0, 4, None)])
+    enc = fuzzgen.libbrotli_enc()
+    if enc is not None:
+        streams, k = [], 0
+        for kind in ("random", "skewed", "repeat2k", "runs", "words", "small_alpha"):
+            for q, lgwin, size in ((1, 18, 30000), (5, 16, 70000), (9, 10, 20000), (11, 22, 40000), (10, 16, 9000), (6, 22, 120000)):
+                k += 1
+                streams.append(fuzzgen.compress(enc, fuzzgen.synthetic_raw(kind, 1300 + k, size), q, lgwin))
+        _kernels_check(streams, "fresh", [(32, warpsim.ASCENDING, 3, 6, None), (32, warpsim.SHUFFLED, 12, 1, None), (4, warpsim.DESCENDING, 0, 0, None)])
+    # quirk vectors and dictionary words in spec mode
+    import dictgen
+    for quirks in (0, 1):
+        kats = [s for _, s, _, _ in dictgen.kat_batch(oracle, quirks, indices_per_length=1)]
+        _kernels_check(kats, "kats", [(32, warpsim.SHUFFLED, 1, 2, None)], quirks=quirks)
+    # sizing mode (bro_batch_sizes): nothing is written, every stream's decoded size is reported
+    streams = [c for _, c, _ in corpus_files()]
+    res, retry, _ = warpsim.two_phase_kernels(streams, [0] * len(streams), sizing=True, order=warpsim.SHUFFLED)
+    for s, (st1, size) in zip(streams, res):
+        st, out = oracle.decode(s)
+        assert st1 in hostsim.RETRY or (st1 == st and (st != 0 or size == len(out))), (st, st1, size, len(out))
+
+
+def test_parse_kernel_ring_wait_is_exact():
+    """the compressed words reach a lane through asynchronous copies into a ring; the simulation lets every copy land as late as the
+    kernel's cp.async.wait_group allows.  With the kernel's own count the batch decodes; let one more group stay in flight than the
+    kernel asks for and the window takes a word that has not arrived -- the batch must come out wrong (the simulation would notice
+    a wait that is one group short)"""
+    import hostsim
+    streams = [c for n, c, _ in corpus_files() if n in ("alice29.txt.compressed", "asyoulik.txt.compressed", "ukkonooa.compressed")]
+    exp = [oracle.decode(s) for s in streams]
+    caps = [len(o) for _, o in exp]
+    res, _, _ = warpsim.two_phase_kernels(streams, caps)
+    assert [r for r in res] == exp
+    L = warpsim._lib_parse()
+    L.bro_warpsim_parse_ring_slack(1)
+    try:
+        res, _, _ = warpsim.two_phase_kernels(streams, caps)
+    finally:
+        L.bro_warpsim_parse_ring_slack(0)
+    assert [r for r in res] != exp

@@ -175,3 +175,90 @@ def two_phase(streams, caps, quirks=0, shape=0, order=ASCENDING, seed=1, in_mis=
         b = int(out_off[i])
         res.append((int(status[i]), out[b: b + int(out_len[i])].tobytes()))
     return res, (int(stats[0]), int(stats[1]))
+
+
+# ---- the parse kernel (bro_kernels_parse.cu compiled for the host, bro_warpsim_parse.cpp), and both kernels back to back ----
+_LIB_PARSE = None
+PARSE_DEPS = ("bro_warpsim.h", "bro_kernels_parse.cu", "bro_parse.h", "bro_kernels.h", "bro_decoder_core.h", "bro_records.h", "bro_status.h",
+              "bro_tables_generated.h")
+
+
+def _lib_parse():
+    global _LIB_PARSE
+    if _LIB_PARSE is None:
+        os.makedirs(BUILD, exist_ok=True)
+        so = os.path.join(BUILD, "libbro_warpsim_parse.so")
+        srcs = [os.path.join(CSRC, "bro_warpsim_parse.cpp"), os.path.join(ROOT, "oracle", "dict_blob.c")]
+        deps = srcs + [os.path.join(CSRC, f) for f in PARSE_DEPS]
+        if not (os.path.exists(so) and all(os.path.getmtime(so) >= os.path.getmtime(d) for d in deps)):
+            subprocess.check_call(["g++", "-std=c++17", "-fPIC", "-shared", "-Wno-unknown-pragmas", "-O2", "-o", so] + srcs +
+                                  ["-Wa,-I" + os.path.join(ROOT, "brotli_rs_b200", "data")])
+        L = ctypes.CDLL(so)
+        L.bro_warpsim_parse_launch.restype = ctypes.c_int
+        L.bro_warpsim_parse_launch.argtypes = [ctypes.c_void_p] * 8 + [ctypes.c_uint64, ctypes.c_uint32, ctypes.c_void_p, ctypes.c_uint32, ctypes.c_int,
+                                               ctypes.c_int, ctypes.c_int, ctypes.c_uint64, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p]
+        _LIB_PARSE = L
+    return _LIB_PARSE
+
+
+PARSE_ERRORS = {102: "a stream was never reported", 103: "the completion queue does not hold every stream exactly once"}
+
+
+def two_phase_kernels(streams, caps, quirks=0, lanes=32, hand_out=None, order=ASCENDING, seed=1, in_mis=0, out_mis=0, ring_late=True,
+                      copy_shape=0, copy_order=None, sizing=False):
+    """A batch through BOTH kernels of the two-phase path as compiled for the host: ONE launch of the parse kernel (a warp holding
+    `lanes` streams at a time, streams handed out in `hand_out` order) and ONE launch of the copy kernel over the completion queue
+    the parse kernel left.  -> [(status, bytes)], streams handed to the fused kernel, completion order.  sizing: bro_batch_sizes'
+    mode (only the parse kernel; bytes are empty, out_len = decoded size -> [(status, size)])."""
+    import numpy as np
+    import hostsim
+    two_phase([], [])            # (loads the copy library)
+    LP, LC = _lib_parse(), _LIB_COPY
+    LC.bro_warpsim_copy_launch.restype = ctypes.c_int
+    LC.bro_warpsim_copy_launch.argtypes = [ctypes.c_void_p] * 7 + [ctypes.c_uint32, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_uint64,
+                                           ctypes.c_void_p]
+    n = len(streams)
+    PAD = 256
+    in_off = np.zeros(n + 1, dtype=np.uint64)
+    in_off[1:] = np.cumsum([len(s) for s in streams])
+    out_off = np.zeros(n + 1, dtype=np.uint64)
+    out_off[1:] = np.cumsum(caps)
+
+    def padded(nbytes, mis, fill):
+        raw = np.full(nbytes + 2 * PAD + 16, fill, dtype=np.uint8)
+        start = (-raw.ctypes.data) % 16 + PAD + mis
+        return raw, start
+
+    in_raw, in_s = padded(int(in_off[n]), in_mis, 0xee)
+    in_raw[in_s: in_s + int(in_off[n])] = np.frombuffer(b"".join(streams), dtype=np.uint8)
+    out_raw, out_s = padded(int(out_off[n]), out_mis, 0xdd)
+    rec_total = (int(in_off[n]) >> 1) + 32 * n
+    rec_raw = np.full(4 * (rec_total + 8), 0xabababab, dtype=np.uint32)
+    rec_s = ((-rec_raw.ctypes.data) % 16) // 4
+    out_len = np.zeros(n + 1, dtype=np.uint64)
+    status = np.zeros(n + 1, dtype=np.int32)
+    nrec = np.zeros(n + 1, dtype=np.uint32)
+    done_q = np.zeros(n + 1, dtype=np.uint32)
+    retry = np.zeros(1, dtype=np.uint32)
+    ho = None if hand_out is None else np.asarray(hand_out, dtype=np.uint32)
+    err = LP.bro_warpsim_parse_launch(in_raw.ctypes.data + in_s, in_off.ctypes.data, out_raw.ctypes.data + out_s, out_off.ctypes.data,
+                                      out_len.ctypes.data, status.ctypes.data, nrec.ctypes.data, rec_raw.ctypes.data + 4 * rec_s, rec_total, n,
+                                      None if ho is None else ho.ctypes.data, lanes, quirks, int(sizing), order, seed, int(ring_late),
+                                      done_q.ctypes.data, retry.ctypes.data)
+    if err:
+        raise AssertionError("warp simulation (parse kernel): " + (PARSE_ERRORS.get(err) or SIM_ERRORS.get(err, str(err))))
+    assert int(retry[0]) == sum(int(s) in hostsim.RETRY for s in status[:n])
+    if sizing:
+        return [(int(status[i]), int(out_len[i])) for i in range(n)], int(retry[0]), done_q[:n].tolist()
+    stats = np.zeros(2, dtype=np.uint64)
+    err = LC.bro_warpsim_copy_launch(in_raw.ctypes.data + in_s, in_off.ctypes.data, out_raw.ctypes.data + out_s, out_off.ctypes.data,
+                                     status.ctypes.data, nrec.ctypes.data, rec_raw.ctypes.data + 4 * rec_s, n, done_q.ctypes.data, copy_shape,
+                                     order if copy_order is None else copy_order, seed, stats.ctypes.data)
+    if err:
+        raise AssertionError("warp simulation (copy kernel): " + SIM_ERRORS.get(err, str(err)))
+    assert (out_raw[:out_s] == 0xdd).all() and (out_raw[out_s + int(out_off[n]):] == 0xdd).all(), "bytes written outside the batch's output"
+    res = []
+    for i in range(n):
+        b = out_s + int(out_off[i])
+        res.append((int(status[i]), out_raw[b: b + int(out_len[i])].tobytes()))
+    return res, int(retry[0]), done_q[:n].tolist()
