@@ -6,7 +6,9 @@
 // (shared-memory scratch, a worst-case table arena in HBM) and the grid.  It serves small batches (lowest latency
 // per stream) and, as the retry pass of the two-phase path, the streams the parse kernel hands over (literal context
 // modelling, tables larger than a thread arena, more copy records than the stream's share).
+#if !defined(BRO_WARPSIM)   /* (BRO_WARPSIM: this kernel compiled for the host, 32 lanes as fibers -- CPU test-suite only, bro_warpsim.cpp) */
 #include <cuda_runtime.h>
+#endif
 #include <stdint.h>
 
 #include "bro_decoder_core.h"
@@ -48,7 +50,11 @@
 template <int WARPS, int MINB>
 __global__ void __launch_bounds__(WARPS * 32, MINB) bro_decode_warp_kernel(BroLaunch p) {
     // one BroScratch per warp (6.7 KB with the general loop's on-chip tables: dynamic shared memory, 4 CTAs x 8 warps = 214 KB per SM)
+#if defined(BRO_WARPSIM)
+    uint8_t* const bro_smem_raw = ws_dynamic_smem;
+#else
     extern __shared__ __align__(16) uint8_t bro_smem_raw[];
+#endif
     BroScratch* const scratch = (BroScratch*)bro_smem_raw;
 #if BRO_DICT_SMEM
     uint8_t* const s_dict = bro_smem_raw + ((WARPS * BRO_GROUPS_PER_WARP * sizeof(BroScratch) + 15u) & ~(size_t)15);
@@ -109,6 +115,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) bro_decode_warp_kernel(BroLa
 }
 
 
+#if !defined(BRO_WARPSIM)
 // blocks_per_sm[0]: the throughput build, [1]: the latency build
 extern "C" int bro_warp_kernel_occupancy(int* blocks_per_sm) {
     cudaError_t e = cudaFuncSetAttribute(bro_decode_warp_kernel<BRO_WARPS_PER_CTA, BRO_MIN_BLOCKS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BRO_WARP_KERNEL_SMEM);
@@ -129,3 +136,4 @@ extern "C" int bro_warp_kernel_launch(const BroLaunch* p, int grid, int latency,
     else bro_decode_warp_kernel<BRO_WARPS_PER_CTA, BRO_MIN_BLOCKS><<<grid, BRO_WARPS_PER_CTA * 32, BRO_WARP_KERNEL_SMEM, stream>>>(*p);
     return (int)cudaGetLastError();
 }
+#endif

@@ -25,7 +25,10 @@
 
 #include "bro_warpsim.h"
 
-#include "bro_decoder_core.h"
+// bro_kernels.cu itself (it includes bro_decoder_core.h in the 32-lane form): the fused kernel's work-queue loop, retry pass and
+// hand-out order are run by bro_warpsim_fused_launch below; the per-stream entry points further down call the decoder directly
+static uint8_t ws_dynamic_smem[96 * 1024] __attribute__((aligned(128)));
+#include "bro_kernels.cu"
 
 extern "C" const uint8_t bro_dictionary_blob[];
 
@@ -82,6 +85,7 @@ static uint64_t g_last_rendezvous;
 // in / out: the caller's buffers; the simulation decodes from and into padded copies (the kernels read whole aligned
 // words and 16-byte granules around what they need, inside allocations the product pads).
 // order: 0 ascending, 1 descending, 2 shuffled (seed).  *sim_err: WS_ERR_* (0 = the warp behaved).
+static size_t g_guard_in_slack = 16, g_guard_out_slack = 0;
 static unsigned g_in_mis, g_out_mis;      // address of the stream's first byte mod 128, of the slot's first byte mod 16
 
 static int ws_decode(const uint8_t* in, size_t in_len, uint8_t* out, size_t cap, size_t* out_len, int quirks, int latency,
@@ -94,6 +98,13 @@ static int ws_decode(const uint8_t* in, size_t in_len, uint8_t* out, size_t cap,
     uint8_t* outb = (uint8_t*)malloc(cap + 2 * PAD + 16);
     uint8_t* out_al = (uint8_t*)(((uintptr_t)outb + PAD + 15) & ~(uintptr_t)15) + (g_out_mis & 15u);
     memset(outb, 0xdd, cap + 2 * PAD + 16);
+    if (ws_guard_mode) {
+        // the buffers end (or begin) at unmapped pages: the compressed stream with the 16 readable bytes behind it that
+        // include/brotli_b200.h asks of a caller, the output slot with g_guard_out_slack
+        in_al = ws_guard_alloc(in_len, g_guard_in_slack, 0, 0xee);
+        memcpy(in_al, in, in_len);
+        out_al = ws_guard_alloc(cap, g_guard_out_slack, 0, 0xdd);
+    }
     if (ck) memcpy(out_al, out, ck->pos <= cap ? ck->pos : cap);         // the history
     WsJob j;
     j.in = in_al; j.in_len = in_len; j.out = out_al; j.cap = cap; j.quirks = quirks; j.latency = latency; j.ck = ck;
@@ -111,8 +122,10 @@ static int ws_decode(const uint8_t* in, size_t in_len, uint8_t* out, size_t cap,
     if (err) n = 0;
     // nothing outside the slot may have been written
     bool clobber = false;
-    for (uint8_t* p = outb; p < out_al && !clobber; p++) clobber = *p != 0xdd;
-    for (uint8_t* p = out_al + cap; p < outb + cap + 2 * PAD + 16 && !clobber; p++) clobber = *p != 0xdd;
+    if (!ws_guard_mode) {
+        for (uint8_t* p = outb; p < out_al && !clobber; p++) clobber = *p != 0xdd;
+        for (uint8_t* p = out_al + cap; p < outb + cap + 2 * PAD + 16 && !clobber; p++) clobber = *p != 0xdd;
+    } else if (ws_guard_mode == 1) for (size_t k = 0; k < g_guard_out_slack; k++) clobber |= out_al[cap + k] != 0xdd;
     if (clobber && !*sim_err) *sim_err = 100;
     if (n > cap) n = cap;
     memcpy(out, out_al, ck ? (w->lane[0].ret_pos <= cap && !err ? cap : 0) : n);
@@ -146,6 +159,38 @@ extern "C" void bro_warpsim_sync_hits(uint64_t* hits, int n, int reset) {
 }
 extern "C" void bro_warpsim_drop_sync(int line) { g_sync_drop_line = line; }
 
+// ------------------------------------------------------------------------------------------------------
+// one launch of bro_decode_warp_kernel over a batch: one CTA, of which warp 0 runs (the others would only take other streams)
+// ------------------------------------------------------------------------------------------------------
+struct WsFusedJob { BroLaunch p; int latency; };
+static void ws_fused_lane(void* arg) {
+    WsFusedJob* j = (WsFusedJob*)arg;
+    if (j->latency) bro_decode_warp_kernel<BRO_WARPS_PER_CTA, BRO_MIN_BLOCKS_LATENCY>(j->p);
+    else bro_decode_warp_kernel<BRO_WARPS_PER_CTA, BRO_MIN_BLOCKS>(j->p);
+    ws_lane_result(ws_me(), 0, 0);
+}
+// Buffers as in BroLaunch, owned by the caller (addressable a few bytes either side of the batch).  retry_mode: only the streams
+// whose status[] holds one of the hand-over codes are decoded (the second pass of the two-phase path); order: hand-out order or NULL.
+extern "C" int bro_warpsim_fused_launch(const uint8_t* in, const uint64_t* in_off, uint8_t* out, const uint64_t* out_off, uint64_t* out_len,
+                                        int32_t* status, uint32_t n, const uint32_t* order, int retry_mode, int latency, int quirks,
+                                        int lane_order, uint64_t seed) {
+    WsFusedJob j;
+    memset(&j, 0, sizeof(j));
+    uint32_t counter = 0, retry = 0;
+    for (uint32_t i = 0; i < n; i++) retry += retry_mode && BRO_ST_IS_RETRY(status[i]);
+    uint16_t* arena = (uint16_t*)aligned_alloc(128, ((2u * (size_t)BRO_ARENA_U16_MAX) + 127u) & ~(size_t)127);
+    j.p.in = in; j.p.in_off = in_off; j.p.out = out; j.p.out_off = out_off; j.p.out_len = out_len; j.p.status = status; j.p.n = n;
+    j.p.arena = arena; j.p.dict = bro_dictionary_blob; j.p.counter = &counter; j.p.order = order; j.p.retry_count = &retry;
+    j.p.retry_mode = retry_mode; j.p.quirk_spec = quirks;
+    j.latency = latency;
+    memset(ws_dynamic_smem, 0xcc, sizeof(ws_dynamic_smem));
+    WsWarp* w = (WsWarp*)malloc(sizeof(WsWarp));
+    const int err = ws_run(w, ws_fused_lane, &j, lane_order, seed);
+    g_last_rendezvous = w->rendezvous;
+    free(w); free(arena);
+    return err;
+}
+
 #if defined(BRO_WARPSIM_MAIN)
 // warpsim_tsan <latency 0|1> <order 0|1|2> <seed> <quirks 0|1> <slack> file...: every file is one compressed stream, decoded
 // into a slot of (bytes the oracle produced, passed as "file:size") + slack.  Prints "name status out_len fnv1a64(out)" per stream;
@@ -157,6 +202,14 @@ int main(int argc, char** argv) {
     const size_t slack = strtoull(argv[5], 0, 10);
     int bad = 0;
     if (getenv("BRO_WS_ALIGN")) { unsigned a = 0, b = 0; sscanf(getenv("BRO_WS_ALIGN"), "%u,%u", &a, &b); bro_warpsim_set_alignment(a, b); }
+    if (getenv("BRO_WS_GUARD")) {        // "back,<in slack>,<out slack>" or "front"
+        const char* g = getenv("BRO_WS_GUARD");
+        unsigned a = 16, b = 0;
+        ws_guard_mode = g[0] == 'f' ? 2 : 1;
+        if (ws_guard_mode == 1) sscanf(g, "back,%u,%u", &a, &b);
+        g_guard_in_slack = a; g_guard_out_slack = b;
+        ws_guard_install();
+    }
     if (getenv("BRO_WS_DROP_SYNC")) g_sync_drop_line = atoi(getenv("BRO_WS_DROP_SYNC"));      // mutation: the report must name it
     for (int a = 6; a < argc; a++) {
         char* colon = strrchr(argv[a], ':');

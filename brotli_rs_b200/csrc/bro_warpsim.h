@@ -278,6 +278,7 @@ static inline uint4 make_uint4(uint32_t x, uint32_t y, uint32_t z, uint32_t w) {
 struct WsTid { unsigned x; };
 WS_NO_TSAN static unsigned ws_tid() { return g_ws->lane[g_ws->cur].tid; }
 #define threadIdx (WsTid{ws_tid()})
+#define blockIdx (WsTid{0u})          /* one CTA */
 static inline uint32_t __shfl_sync(uint32_t mask, uint32_t v, int src, int width = 32) {
     return ws_collective(WS_OP_SHFL, mask, v, ((uint32_t)width << 8) | ((uint32_t)src & 255u));
 }
@@ -338,6 +339,41 @@ static inline size_t __cvta_generic_to_shared(const void* p) { return (size_t)(u
 static inline uint8_t* ws_smem_ptr(uint32_t a) { return (uint8_t*)(ws_smem_base() + a); }
 static inline uint32_t min(uint32_t a, uint32_t b) { return a < b ? a : b; }
 static inline uint32_t max(uint32_t a, uint32_t b) { return a > b ? a : b; }
+
+// ------------------------------------------------------------------------------------------------------
+// Guarded buffers: how far beyond what it was given does a kernel READ?  (ws_guard_mode: 0 none; 1 = the byte `slack` bytes
+// behind the buffer's end is the first byte of an unmapped page; 2 = the buffer starts a page whose predecessor is unmapped.)
+// A touch of the unmapped page ends the process with exit code 97 (the drivers with a main() install the handler).
+// ------------------------------------------------------------------------------------------------------
+#include <signal.h>
+#include <sys/mman.h>
+#include <unistd.h>
+static int ws_guard_mode;
+static inline uint8_t* ws_guard_alloc(size_t bytes, size_t slack, unsigned mis, uint8_t fill) {
+    const size_t page = 4096;
+    const size_t body = (bytes + slack + mis + 2 * page - 1) / page * page;
+    uint8_t* m = (uint8_t*)mmap(0, body + 2 * page, PROT_READ | PROT_WRITE, MAP_PRIVATE | MAP_ANONYMOUS, -1, 0);
+    if (m == (uint8_t*)MAP_FAILED) abort();
+    memset(m, fill, body + 2 * page);
+    mprotect(m, page, PROT_NONE);
+    mprotect(m + page + body, page, PROT_NONE);
+    return ws_guard_mode == 2 ? m + page + mis : m + page + body - slack - bytes;      // (never unmapped: test processes are short-lived)
+}
+static void ws_guard_handler(int, siginfo_t* si, void*) {
+    char msg[96];
+    const int n = snprintf(msg, sizeof(msg), "GUARD: access at %p outside the buffers a caller must provide\n", si->si_addr);
+    if (write(2, msg, (size_t)n) < 0) {}
+    _exit(97);
+}
+static inline void ws_guard_install() {
+    static uint8_t alt[65536];
+    stack_t ss; ss.ss_sp = alt; ss.ss_size = sizeof(alt); ss.ss_flags = 0;
+    sigaltstack(&ss, 0);
+    struct sigaction sa;
+    memset(&sa, 0, sizeof(sa));
+    sa.sa_sigaction = ws_guard_handler; sa.sa_flags = SA_SIGINFO | SA_ONSTACK;
+    sigaction(SIGSEGV, &sa, 0);
+}
 
 // bro_syncwarp() by source line: how often each barrier of the header ran, and one line whose barrier is left out (a
 // mutation: the test-suite checks that the lane orders notice -- tests/test_warpsim_parity.py)

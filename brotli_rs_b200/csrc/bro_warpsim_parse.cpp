@@ -19,8 +19,6 @@ static unsigned ws_tid_base;
 struct WsTidB { unsigned x; };
 #undef threadIdx
 #define threadIdx (WsTidB{ws_tid() + ws_tid_base})
-struct WsBlk { unsigned x; };
-#define blockIdx (WsBlk{0u})
 static inline void __syncthreads() { __syncwarp(0xffffffffu); }      // (one warp of the CTA runs at a time)
 
 // the ring's asynchronous copies (global -> shared, 4 bytes, one commit group each), per lane, oldest first

@@ -194,7 +194,7 @@ def _tsan_binary():
     exe = os.path.join(build, "warpsim_tsan")
     csrc = os.path.join(ROOT, "brotli_rs_b200", "csrc")
     srcs = [os.path.join(csrc, "bro_warpsim.cpp"), os.path.join(ROOT, "oracle", "dict_blob.c")]
-    deps = srcs + [os.path.join(csrc, f) for f in ("bro_decoder_core.h", "bro_records.h", "bro_status.h", "bro_tables_generated.h")]
+    deps = srcs + [os.path.join(csrc, f) for f in ("bro_warpsim.h", "bro_decoder_core.h", "bro_records.h", "bro_status.h", "bro_tables_generated.h")]
     if not (os.path.exists(exe) and all(os.path.getmtime(exe) >= os.path.getmtime(d) for d in deps)):
         cmd = ["g++", "-std=c++17", "-O1", "-g", "-fsanitize=thread", "-DBRO_WARPSIM_MAIN", "-Wno-unknown-pragmas", "-o", exe] + srcs + \
               ["-Wa,-I" + os.path.join(ROOT, "brotli_rs_b200", "data")]
@@ -462,3 +462,68 @@ def test_parse_kernel_ring_wait_is_exact():
     finally:
         L.bro_warpsim_parse_ring_slack(0)
     assert [r for r in res] != exp
+
+
+def test_fused_code_stays_inside_the_granules_of_its_buffers(tmp_path):
+    """how far beyond what a caller provides does the fused kernel's code READ (or write)?  The compressed stream and the output slot
+    are placed so that the first byte behind the 16-byte granule that holds their last byte -- or the byte in front of their first
+    -- lies in an unmapped page: the corpus decodes without touching it.  (include/brotli_b200.h asks for 16 readable bytes behind
+    the compressed batch; aligned granules that hold a wanted byte are all the code reads, which no real allocation ends inside.)"""
+    build = os.path.join(ROOT, "tests", "_build")
+    os.makedirs(build, exist_ok=True)
+    exe = os.path.join(build, "warpsim_guard")
+    csrc = os.path.join(ROOT, "brotli_rs_b200", "csrc")
+    srcs = [os.path.join(csrc, "bro_warpsim.cpp"), os.path.join(ROOT, "oracle", "dict_blob.c")]
+    deps = srcs + [os.path.join(csrc, f) for f in ("bro_warpsim.h", "bro_decoder_core.h", "bro_records.h", "bro_status.h", "bro_tables_generated.h")]
+    if not (os.path.exists(exe) and all(os.path.getmtime(exe) >= os.path.getmtime(d) for d in deps)):
+        subprocess.check_call(["g++", "-std=c++17", "-O2", "-g", "-DBRO_WARPSIM_MAIN", "-Wno-unknown-pragmas", "-o", exe] + srcs +
+                              ["-Wa,-I" + os.path.join(ROOT, "brotli_rs_b200", "data")])
+    files, expect = [], {}
+    for name, comp, _ in corpus_files():
+        st, out = oracle.decode(comp)
+        p = str(tmp_path / name)
+        open(p, "wb").write(comp)
+        files.append("%s:%d" % (p, len(out)))
+        expect[p] = (st, out)
+    for k, guard in enumerate(("back,16,0", "back,1,1", "back,7,3", "back,15,15", "front")):
+        r = subprocess.run([exe, str(k & 1), str(k % 3), "1", "0", "0"] + files, env=dict(os.environ, BRO_WS_GUARD=guard), capture_output=True,
+                           text=True, timeout=600)
+        assert r.returncode == 0, (guard, r.returncode, r.stderr[-300:])
+        for ln in r.stdout.splitlines():
+            name, st1, n1, h1, err = ln.rsplit(" ", 4)
+            st, out = expect[name]
+            assert err == "0" and int(st1) == st and (st != 0 or (int(n1), h1) == (len(out), _fnv(out))), (guard, ln)
+
+
+def test_two_phase_path_with_its_retry_pass():
+    """the product's whole two-phase call on the CPU: parse kernel, copy kernel, then bro_decode_warp_kernel (bro_kernels.cu itself:
+    work queue, retry mode) over the same buffers for the streams phase one handed over -- every status final and equal to the
+    oracle's, slots too small included, and streams that were not handed over untouched by the third launch"""
+    import hostsim
+    rng = np.random.default_rng(23)
+    corpus = [c for _, c, _ in corpus_files()]
+    enc = fuzzgen.libbrotli_enc()
+    fresh = []
+    if enc is not None:
+        # 4-symbol data: copies so short that they outnumber the stream's share of the record arena (-> RecordsFull); heterogeneous
+        # payloads at quality 9-11: more prefix codes than a thread's arena holds (-> ArenaTooSmall)
+        for k, (kind, q, lgwin, size) in enumerate((("small_alpha", 5, 16, 30000), ("small_alpha", 9, 18, 20000), ("small_alpha", 7, 22, 40000),
+                                                    ("words", 11, 22, 60000), ("skewed", 10, 16, 50000))):
+            fresh.append(fuzzgen.compress(enc, fuzzgen.synthetic_raw(kind, 2000 + k, size), q, lgwin))
+    muts = list(fuzzgen.mutations(corpus + fresh * 4, seed=123, count=900, max_len=30000)) + fresh
+    handed = 0
+    for part in range(0, len(muts), 300):
+        streams = muts[part: part + 300]
+        caps, exp = [], []
+        for s in streams:
+            st, out = oracle.decode(s)
+            cap = len(out) if rng.random() < 0.6 else int(rng.integers(0, len(out) + 64))
+            o, ol, sts = oracle.decode_batch(np.frombuffer(s, dtype=np.uint8), np.array([0, len(s)], dtype=np.uint64), np.array([0, cap], dtype=np.uint64))
+            caps.append(cap)
+            exp.append((int(sts[0]), o[: int(ol[0])].tobytes()))
+        res, retry, _ = warpsim.two_phase_kernels(streams, caps, order=warpsim.ORDERS[(part // 300) % 3], in_mis=part % 16, out_mis=(part // 7) % 16,
+                                                  retry_pass=True, retry_latency=bool(part & 256))
+        handed += retry
+        for i, (e, r) in enumerate(zip(exp, res)):
+            assert r[0] == e[0] and (e[0] != 0 or r[1] == e[1]), (part + i, e[0], r[0], streams[i][:16].hex())
+    assert enc is None or handed >= 3, handed

@@ -31,7 +31,7 @@ def _build():
     os.makedirs(BUILD, exist_ok=True)
     so = os.path.join(BUILD, "libbro_warpsim.so")
     srcs = [os.path.join(CSRC, "bro_warpsim.cpp"), os.path.join(ROOT, "oracle", "dict_blob.c")]
-    deps = srcs + [os.path.join(CSRC, f) for f in ("bro_decoder_core.h", "bro_records.h", "bro_status.h", "bro_tables_generated.h")]
+    deps = srcs + [os.path.join(CSRC, f) for f in ("bro_warpsim.h", "bro_decoder_core.h", "bro_records.h", "bro_status.h", "bro_tables_generated.h")]
     if os.path.exists(so) and all(os.path.getmtime(so) >= os.path.getmtime(d) for d in deps):
         return so
     cmd = ["g++", "-std=c++17", "-fPIC", "-shared", "-Wno-unknown-pragmas", "-O2", "-o", so] + srcs + \
@@ -205,11 +205,13 @@ PARSE_ERRORS = {102: "a stream was never reported", 103: "the completion queue d
 
 
 def two_phase_kernels(streams, caps, quirks=0, lanes=32, hand_out=None, order=ASCENDING, seed=1, in_mis=0, out_mis=0, ring_late=True,
-                      copy_shape=0, copy_order=None, sizing=False):
+                      copy_shape=0, copy_order=None, sizing=False, retry_pass=False, retry_latency=False):
     """A batch through BOTH kernels of the two-phase path as compiled for the host: ONE launch of the parse kernel (a warp holding
     `lanes` streams at a time, streams handed out in `hand_out` order) and ONE launch of the copy kernel over the completion queue
     the parse kernel left.  -> [(status, bytes)], streams handed to the fused kernel, completion order.  sizing: bro_batch_sizes'
-    mode (only the parse kernel; bytes are empty, out_len = decoded size -> [(status, size)])."""
+    mode (only the parse kernel; bytes are empty, out_len = decoded size -> [(status, size)]).  retry_pass: the third launch of the
+    product's two-phase path as well -- bro_decode_warp_kernel in retry mode over the same buffers decodes exactly the streams phase
+    one handed over, so that every status is final."""
     import numpy as np
     import hostsim
     two_phase([], [])            # (loads the copy library)
@@ -256,6 +258,19 @@ def two_phase_kernels(streams, caps, quirks=0, lanes=32, hand_out=None, order=AS
                                      order if copy_order is None else copy_order, seed, stats.ctypes.data)
     if err:
         raise AssertionError("warp simulation (copy kernel): " + SIM_ERRORS.get(err, str(err)))
+    if retry_pass and int(retry[0]):
+        LF = lib()
+        LF.bro_warpsim_fused_launch.restype = ctypes.c_int
+        LF.bro_warpsim_fused_launch.argtypes = [ctypes.c_void_p] * 6 + [ctypes.c_uint32, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                                ctypes.c_int, ctypes.c_uint64]
+        before = status[:n].copy()
+        err = LF.bro_warpsim_fused_launch(in_raw.ctypes.data + in_s, in_off.ctypes.data, out_raw.ctypes.data + out_s, out_off.ctypes.data,
+                                          out_len.ctypes.data, status.ctypes.data, n, None, 1, int(retry_latency), quirks, order, seed)
+        if err:
+            raise AssertionError("warp simulation (fused kernel, retry pass): " + SIM_ERRORS.get(err, str(err)))
+        keep = np.array([int(x) not in hostsim.RETRY for x in before])
+        assert (status[:n][keep] == before[keep]).all(), "the retry pass touched a stream that was not handed over"
+        assert not any(int(x) in hostsim.RETRY for x in status[:n])
     assert (out_raw[:out_s] == 0xdd).all() and (out_raw[out_s + int(out_off[n]):] == 0xdd).all(), "bytes written outside the batch's output"
     res = []
     for i in range(n):
