@@ -145,7 +145,6 @@ __global__ void __launch_bounds__(BRO_PARSE_BLOCK, BRO_PARSE_MIN_BLOCKS) bro_par
     }
 }
 
-#if !defined(BRO_WARPSIM)
 // ---- size-class ordering: 256 classes (8 per power of two of the compressed size), largest class first ----
 __device__ __forceinline__ uint32_t bro_size_class(uint64_t len) {
     uint32_t l = len > 0xffffffffull ? 0xffffffffu : (uint32_t)len;
@@ -202,6 +201,7 @@ __global__ void bro_order_scatter_kernel(const uint64_t* in_off, uint32_t n, uin
     if (i < n) order[base + (uint32_t)__popc(peers & ((1u << lane) - 1u))] = i;
 }
 
+#if !defined(BRO_WARPSIM)   /* (the launchers are the device's; the simulation runs the kernels above CTA by CTA, bro_warpsim_parse.cpp) */
 extern "C" int bro_order_launch(const uint64_t* in_off, uint32_t n, uint32_t* order, uint32_t* scratch, uint32_t* gate, cudaStream_t stream) {
     cudaError_t e = cudaMemsetAsync(scratch, 0, 512 * sizeof(uint32_t), stream);
     if (e != cudaSuccess) return (int)e;
@@ -213,11 +213,14 @@ extern "C" int bro_order_launch(const uint64_t* in_off, uint32_t n, uint32_t* or
     return (int)cudaGetLastError();
 }
 
+#endif
+
 __global__ void bro_sizes_finish_kernel(int32_t* status, uint32_t n) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n && BRO_ST_IS_RETRY(status[i])) status[i] = BRO_ST_SizeUnknown;
 }
 
+#if !defined(BRO_WARPSIM)
 extern "C" int bro_sizes_finish_launch(int32_t* status, uint32_t n, cudaStream_t stream) {
     (void)cudaGetLastError();
     bro_sizes_finish_kernel<<<(n + 255u) / 256u, 256, 0, stream>>>(status, n);

@@ -173,19 +173,21 @@ static void ws_fused_lane(void* arg) {
 // whose status[] holds one of the hand-over codes are decoded (the second pass of the two-phase path); order: hand-out order or NULL.
 extern "C" int bro_warpsim_fused_launch(const uint8_t* in, const uint64_t* in_off, uint8_t* out, const uint64_t* out_off, uint64_t* out_len,
                                         int32_t* status, uint32_t n, const uint32_t* order, int retry_mode, int latency, int quirks,
-                                        int lane_order, uint64_t seed) {
+                                        int lane_order, uint64_t seed, int nthreads) {
     WsFusedJob j;
     memset(&j, 0, sizeof(j));
     uint32_t counter = 0, retry = 0;
     for (uint32_t i = 0; i < n; i++) retry += retry_mode && BRO_ST_IS_RETRY(status[i]);
-    uint16_t* arena = (uint16_t*)aligned_alloc(128, ((2u * (size_t)BRO_ARENA_U16_MAX) + 127u) & ~(size_t)127);
+    if (nthreads < 32) nthreads = 32;
+    if (nthreads > 32 * BRO_WARPS_PER_CTA) abort();
+    uint16_t* arena = (uint16_t*)aligned_alloc(128, ((2u * (size_t)BRO_ARENA_U16_MAX * BRO_WARPS_PER_CTA) + 127u) & ~(size_t)127);
     j.p.in = in; j.p.in_off = in_off; j.p.out = out; j.p.out_off = out_off; j.p.out_len = out_len; j.p.status = status; j.p.n = n;
     j.p.arena = arena; j.p.dict = bro_dictionary_blob; j.p.counter = &counter; j.p.order = order; j.p.retry_count = &retry;
     j.p.retry_mode = retry_mode; j.p.quirk_spec = quirks;
     j.latency = latency;
     memset(ws_dynamic_smem, 0xcc, sizeof(ws_dynamic_smem));
     WsWarp* w = (WsWarp*)malloc(sizeof(WsWarp));
-    const int err = ws_run(w, ws_fused_lane, &j, lane_order, seed);
+    const int err = ws_run(w, ws_fused_lane, &j, lane_order, seed, nthreads);
     g_last_rendezvous = w->rendezvous;
     free(w); free(arena);
     return err;

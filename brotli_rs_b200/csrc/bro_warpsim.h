@@ -54,8 +54,8 @@ asm(".text\n"
     "  ret\n"
     ".size bro_ws_switch,.-bro_ws_switch\n");
 
-enum { WS_LANES = 32, WS_STACK = 512 * 1024 };
-enum { WS_OP_NONE = 0, WS_OP_SHFL, WS_OP_MATCH, WS_OP_ALL, WS_OP_ANY, WS_OP_BALLOT, WS_OP_SYNC, WS_OP_SHFL_UP, WS_OP_SHFL_XOR, WS_OP_ADD };
+enum { WS_LANES = 32, WS_MAX_THREADS = 256, WS_STACK = 512 * 1024 };     // a CTA of up to 8 warps
+enum { WS_OP_NONE = 0, WS_OP_SHFL, WS_OP_MATCH, WS_OP_ALL, WS_OP_ANY, WS_OP_BALLOT, WS_OP_SYNC, WS_OP_SHFL_UP, WS_OP_SHFL_XOR, WS_OP_ADD, WS_OP_MAX, WS_OP_SYNC_CTA };
 enum { WS_ERR_NONE = 0, WS_ERR_DIVERGENT = 1, WS_ERR_EXIT_WHILE_WAITED = 2, WS_ERR_NOT_UNIFORM = 3, WS_ERR_BAD_MASK = 4 };
 
 struct WsLane {
@@ -68,20 +68,21 @@ struct WsLane {
     uint32_t ret_pos;
     void* fiber;             // ThreadSanitizer's view of this lane (race-detection build)
 };
-struct WsWarp {
-    WsLane lane[WS_LANES];
+struct WsWarp {                          // (a CTA: nthreads / 32 warps; the name is from when it was one)
+    WsLane lane[WS_MAX_THREADS];
+    int nthreads;
     int cur;
     void* main_sp;
     int order_mode;          // 0 ascending, 1 descending, 2 shuffled at every rendezvous
     uint64_t rng;
-    int perm[WS_LANES];      // perm[k] = the lane that runs k-th
-    int where[WS_LANES];     // inverse
+    int perm[WS_MAX_THREADS];      // perm[k] = the thread that runs k-th
+    int where[WS_MAX_THREADS];     // inverse
     int err;
     uint64_t rendezvous;
     void (*body)(void*);
     void* arg;
     void* main_fiber;
-    char sync_token, start_token, end_token;     // addresses the happens-before edges hang on
+    char sync_token[WS_MAX_THREADS / 32], cta_token, start_token, end_token;     // addresses the happens-before edges hang on
 };
 static WsWarp* g_ws;
 
@@ -94,14 +95,15 @@ WS_NO_TSAN static void ws_switch_to(WsWarp* w, void** save_sp, int to) {
 }
 
 WS_NO_TSAN static void ws_set_order(WsWarp* w) {
-    for (int k = 0; k < WS_LANES; k++) w->perm[k] = w->order_mode == 1 ? WS_LANES - 1 - k : k;
+    const int N = w->nthreads;
+    for (int k = 0; k < N; k++) w->perm[k] = w->order_mode == 1 ? N - 1 - k : k;
     if (w->order_mode == 2)
-        for (int k = WS_LANES - 1; k > 0; k--) {
+        for (int k = N - 1; k > 0; k--) {
             w->rng = w->rng * 6364136223846793005ull + 1442695040888963407ull;
             const int j = (int)((w->rng >> 33) % (uint64_t)(k + 1));
             const int t = w->perm[k]; w->perm[k] = w->perm[j]; w->perm[j] = t;
         }
-    for (int k = 0; k < WS_LANES; k++) w->where[w->perm[k]] = k;
+    for (int k = 0; k < N; k++) w->where[w->perm[k]] = k;
 }
 
 // the run is over (clean or not): back to the caller of ws_run
@@ -114,8 +116,8 @@ WS_NO_TSAN static void ws_to_main(WsWarp* w) {
 WS_NO_TSAN static void ws_yield(WsWarp* w) {
     const int from = w->cur;
     int k = w->where[from];
-    for (int n = 0; n < WS_LANES; n++) {
-        k = (k + 1) % WS_LANES;
+    for (int n = 0; n < w->nthreads; n++) {
+        k = (k + 1) % w->nthreads;
         const int l = w->perm[k];
         if (!w->lane[l].done) {
             if (l == from) return;
@@ -136,53 +138,62 @@ WS_NO_TSAN static void ws_fail(WsWarp* w, int err) {
 WS_NO_TSAN static uint32_t ws_collective_raw(uint32_t op, uint32_t mask, uint32_t a, uint32_t b) {
     WsWarp* w = g_ws;
     WsLane* me = &w->lane[w->cur];
-    if (!((mask >> me->tid) & 1u)) ws_fail(w, WS_ERR_BAD_MASK);
+    // the threads this one meets: the lanes of its warp that the mask names -- or, at __syncthreads, the whole CTA
+    const bool cta = op == WS_OP_SYNC_CTA;
+    WsLane* const wl = cta ? w->lane : &w->lane[me->tid & ~31u];       // lane 0 of the set
+    const int cnt = cta ? w->nthreads : WS_LANES;
+    const unsigned lane = cta ? me->tid : (me->tid & 31u);
+    if (!cta && !((mask >> lane) & 1u)) ws_fail(w, WS_ERR_BAD_MASK);
+#define WS_IN(l) (cta || ((mask >> (l)) & 1u))
     me->waiting = 1; me->op = op; me->mask = mask; me->a = a; me->b = b;
     for (;;) {
-        // have all the lanes this one names arrived?
+        // have all the threads this one names arrived?
         bool all = true;
-        for (int l = 0; l < WS_LANES && all; l++)
-            if ((mask >> l) & 1u) {
-                if (w->lane[l].done) ws_fail(w, WS_ERR_EXIT_WHILE_WAITED);
-                if (!w->lane[l].waiting) all = false;
+        for (int l = 0; l < cnt && all; l++)
+            if (WS_IN(l)) {
+                if (wl[l].done) ws_fail(w, WS_ERR_EXIT_WHILE_WAITED);
+                if (!wl[l].waiting || (wl[l].op == WS_OP_SYNC_CTA) != cta) all = false;
             }
         if (all) break;
         ws_yield(w);
-        if (!me->waiting) return me->result;      // the last arriver released this lane
-        // a full round without progress cannot happen silently: a lane that runs either arrives, returns or fails
+        if (!me->waiting) return me->result;      // the last arriver released this thread
+        // a full round without progress cannot happen silently: a thread that runs either arrives, returns or fails
     }
-    // this lane is the last to arrive: same intrinsic, same mask everywhere, then compute and release
-    for (int l = 0; l < WS_LANES; l++)
-        if (((mask >> l) & 1u) && (w->lane[l].op != op || w->lane[l].mask != mask)) ws_fail(w, WS_ERR_DIVERGENT);
+    // this thread is the last to arrive: same intrinsic, same mask everywhere, then compute and release
+    for (int l = 0; l < cnt; l++)
+        if (WS_IN(l) && (wl[l].op != op || wl[l].mask != mask)) ws_fail(w, WS_ERR_DIVERGENT);
     uint32_t ballot = 0;
-    for (int l = 0; l < WS_LANES; l++) if (((mask >> l) & 1u) && w->lane[l].a) ballot |= 1u << l;
-    for (int l = 0; l < WS_LANES; l++) {
-        if (!((mask >> l) & 1u)) continue;
-        WsLane* t = &w->lane[l];
+    if (!cta) for (int l = 0; l < WS_LANES; l++) if (((mask >> l) & 1u) && wl[l].a) ballot |= 1u << l;
+    for (int l = 0; l < cnt; l++) {
+        if (!WS_IN(l)) continue;
+        WsLane* t = &wl[l];
         uint32_t r = 0;
         switch (op) {
         case WS_OP_SHFL: {
             const uint32_t width = t->b >> 8, src = t->b & 255u;
             const uint32_t from = ((uint32_t)l & ~(width - 1u)) | (src & (width - 1u));
-            r = ((mask >> from) & 1u) ? w->lane[from].a : t->a;     // (a lane outside the mask: undefined on the device)
+            r = ((mask >> from) & 1u) ? wl[from].a : t->a;     // (a lane outside the mask: undefined on the device)
             break;
         }
         case WS_OP_SHFL_UP: {
             const uint32_t width = t->b >> 8, delta = t->b & 255u;
             const uint32_t in_seg = (uint32_t)l & (width - 1u);
-            r = in_seg >= delta && ((mask >> (l - (int)delta)) & 1u) ? w->lane[l - (int)delta].a : t->a;
+            r = in_seg >= delta && ((mask >> (l - (int)delta)) & 1u) ? wl[l - (int)delta].a : t->a;
             break;
         }
         case WS_OP_SHFL_XOR: {
             const uint32_t from = (uint32_t)l ^ (t->b & 255u);
-            r = from < WS_LANES && ((mask >> from) & 1u) ? w->lane[from].a : t->a;
+            r = from < WS_LANES && ((mask >> from) & 1u) ? wl[from].a : t->a;
             break;
         }
         case WS_OP_ADD:
-            for (int j = 0; j < WS_LANES; j++) if ((mask >> j) & 1u) r += w->lane[j].a;
+            for (int j = 0; j < WS_LANES; j++) if ((mask >> j) & 1u) r += wl[j].a;
+            break;
+        case WS_OP_MAX:
+            for (int j = 0; j < WS_LANES; j++) if (((mask >> j) & 1u) && wl[j].a > r) r = wl[j].a;
             break;
         case WS_OP_MATCH:
-            for (int j = 0; j < WS_LANES; j++) if (((mask >> j) & 1u) && w->lane[j].a == t->a) r |= 1u << j;
+            for (int j = 0; j < WS_LANES; j++) if (((mask >> j) & 1u) && wl[j].a == t->a) r |= 1u << j;
             break;
         case WS_OP_ALL: r = ballot == mask; break;
         case WS_OP_ANY: r = ballot != 0u; break;
@@ -192,20 +203,22 @@ WS_NO_TSAN static uint32_t ws_collective_raw(uint32_t op, uint32_t mask, uint32_
         t->result = r;
         t->waiting = 0;
     }
+#undef WS_IN
     w->rendezvous++;
     if (w->order_mode == 2) ws_set_order(w);
     return me->result;
 }
 
-// __syncwarp is the one intrinsic that orders memory: everything a lane did before it happens-before everything any lane
-// does after it
+// __syncwarp (and __syncthreads for the CTA) are the intrinsics that order memory: everything a thread did before one
+// happens-before everything any thread it met there does after it
 WS_NO_TSAN static uint32_t ws_collective(uint32_t op, uint32_t mask, uint32_t a, uint32_t b) {
 #if WS_TSAN
-    if (op == WS_OP_SYNC) __tsan_release(&g_ws->sync_token);
+    char* const token = op == WS_OP_SYNC_CTA ? &g_ws->cta_token : &g_ws->sync_token[g_ws->lane[g_ws->cur].tid >> 5];
+    if (op == WS_OP_SYNC || op == WS_OP_SYNC_CTA) __tsan_release(token);
 #endif
     const uint32_t r = ws_collective_raw(op, mask, a, b);
 #if WS_TSAN
-    if (op == WS_OP_SYNC) __tsan_acquire(&g_ws->sync_token);
+    if (op == WS_OP_SYNC || op == WS_OP_SYNC_CTA) __tsan_acquire(token);
 #endif
     return r;
 }
@@ -221,18 +234,24 @@ WS_NO_TSAN static void ws_trampoline() {
 #endif
     WsLane* me = &w->lane[w->cur];
     me->done = 1;
-    // a lane must not leave while another waits for it at a rendezvous
-    for (int l = 0; l < WS_LANES; l++)
-        if (w->lane[l].waiting && ((w->lane[l].mask >> me->tid) & 1u)) ws_fail(w, WS_ERR_EXIT_WHILE_WAITED);
+    // a thread must not leave while another waits for it at a rendezvous (a lane of its warp that names it, or anyone at __syncthreads)
+    for (int l = 0; l < w->nthreads; l++) {
+        const WsLane* o = &w->lane[l];
+        if (!o->waiting) continue;
+        if (o->op == WS_OP_SYNC_CTA || ((o->tid >> 5) == (me->tid >> 5) && ((o->mask >> (me->tid & 31u)) & 1u))) ws_fail(w, WS_ERR_EXIT_WHILE_WAITED);
+    }
     ws_yield(w);                // to the next live lane, or to main when this was the last
     abort();
 }
 
-WS_NO_TSAN static int ws_run(WsWarp* w, void (*body)(void*), void* arg, int order_mode, uint64_t seed) {
+// nthreads: a multiple of 32 up to WS_MAX_THREADS (the CTA's warps run interleaved, thread by thread, in the chosen order)
+WS_NO_TSAN static int ws_run(WsWarp* w, void (*body)(void*), void* arg, int order_mode, uint64_t seed, int nthreads = WS_LANES) {
     memset(w, 0, sizeof(*w));
+    if (nthreads < WS_LANES || nthreads > WS_MAX_THREADS || (nthreads & 31)) abort();
+    w->nthreads = nthreads;
     w->body = body; w->arg = arg; w->order_mode = order_mode; w->rng = seed * 2654435761ull + 1ull;
     ws_set_order(w);
-    for (int l = 0; l < WS_LANES; l++) {
+    for (int l = 0; l < nthreads; l++) {
         WsLane* t = &w->lane[l];
         t->tid = (unsigned)l;
         t->stack = (uint8_t*)malloc(WS_STACK);
@@ -254,14 +273,14 @@ WS_NO_TSAN static int ws_run(WsWarp* w, void (*body)(void*), void* arg, int orde
     ws_switch_to(w, &w->main_sp, w->cur);
 #if WS_TSAN
     __tsan_acquire(&w->end_token);
-    for (int l = 0; l < WS_LANES; l++) __tsan_destroy_fiber(w->lane[l].fiber);
+    for (int l = 0; l < nthreads; l++) __tsan_destroy_fiber(w->lane[l].fiber);
 #endif
     g_ws = 0;
     int alive = 0;
-    for (int l = 0; l < WS_LANES; l++) { alive += !w->lane[l].done; free(w->lane[l].stack); }
+    for (int l = 0; l < nthreads; l++) { alive += !w->lane[l].done; free(w->lane[l].stack); }
     if (!w->err && alive) w->err = WS_ERR_DIVERGENT;
     if (!w->err)
-        for (int l = 1; l < WS_LANES; l++)
+        for (int l = 1; l < nthreads; l++)
             if (w->lane[l].ret_status != w->lane[0].ret_status || w->lane[l].ret_pos != w->lane[0].ret_pos) w->err = WS_ERR_NOT_UNIFORM;
     return w->err;
 }
@@ -278,7 +297,9 @@ static inline uint4 make_uint4(uint32_t x, uint32_t y, uint32_t z, uint32_t w) {
 struct WsTid { unsigned x; };
 WS_NO_TSAN static unsigned ws_tid() { return g_ws->lane[g_ws->cur].tid; }
 #define threadIdx (WsTid{ws_tid()})
-#define blockIdx (WsTid{0u})          /* one CTA */
+static unsigned ws_block_idx;         // the CTA being run (a grid is run CTA after CTA)
+#define blockIdx (WsTid{ws_block_idx})
+#define blockDim (WsTid{(unsigned)g_ws->nthreads})
 static inline uint32_t __shfl_sync(uint32_t mask, uint32_t v, int src, int width = 32) {
     return ws_collective(WS_OP_SHFL, mask, v, ((uint32_t)width << 8) | ((uint32_t)src & 255u));
 }
@@ -319,6 +340,9 @@ static inline unsigned long long __shfl_xor_sync(uint32_t mask, unsigned long lo
     return lo | ((unsigned long long)hi << 32);
 }
 static inline uint32_t __reduce_add_sync(uint32_t mask, uint32_t v) { return ws_collective(WS_OP_ADD, mask, v, 0); }
+static inline uint32_t __reduce_max_sync(uint32_t mask, uint32_t v) { return ws_collective(WS_OP_MAX, mask, v, 0); }
+static inline void __syncthreads() { (void)ws_collective(WS_OP_SYNC_CTA, 0, 0, 0); }
+WS_NO_TSAN static uint32_t atomicMax(uint32_t* p, uint32_t v) { const uint32_t o = *p; if (v > o) *p = v; return o; }
 // atomics and the rest of the kernel-level surface: one warp runs at a time, so a plain read-modify-write is atomic here
 // (not instrumented: on the device these are atomic operations, not data accesses)
 WS_NO_TSAN static uint32_t atomicAdd(uint32_t* p, uint32_t v) { const uint32_t o = *p; *p = o + v; return o; }
@@ -336,7 +360,8 @@ typedef void* cudaStream_t;
 static uint8_t ws_smem_anchor[16] __attribute__((aligned(16)));
 static inline uintptr_t ws_smem_base() { return (uintptr_t)ws_smem_anchor - 0x40000000u; }
 static inline size_t __cvta_generic_to_shared(const void* p) { return (size_t)(uint32_t)((uintptr_t)p - ws_smem_base()); }
-static inline uint8_t* ws_smem_ptr(uint32_t a) { return (uint8_t*)(ws_smem_base() + a); }
+static int ws_smem_skew_lane = -1;      // mutation: this lane's shared-memory accesses land 4 bytes further on -- in its neighbour's words
+static inline uint8_t* ws_smem_ptr(uint32_t a) { return (uint8_t*)(ws_smem_base() + a) + (ws_smem_skew_lane >= 0 && (int)ws_tid() == ws_smem_skew_lane ? 4 : 0); }
 static inline uint32_t min(uint32_t a, uint32_t b) { return a < b ? a : b; }
 static inline uint32_t max(uint32_t a, uint32_t b) { return a > b ? a : b; }
 

@@ -20,8 +20,8 @@
 
 // the asynchronous copies of a lane (global -> shared, 16 bytes): issued now, performed at the lane's wait
 struct WsAsyncCopy { uint32_t dst; const void* src; };
-static WsAsyncCopy g_async[WS_LANES][64];
-static int g_async_n[WS_LANES];
+static WsAsyncCopy g_async[WS_MAX_THREADS][64];
+static int g_async_n[WS_MAX_THREADS];
 WS_NO_TSAN static int ws_async_push(uint32_t dst, const void* src) {
     const unsigned l = ws_tid();
     if (g_async_n[l] >= 64) abort();
@@ -77,7 +77,7 @@ static uint64_t g_copy_rendezvous;
 // (NULL = identity).  Returns the simulation's verdict (0 = the warp behaved); stats[0..1] = bytes moved, records executed.
 extern "C" int bro_warpsim_copy_launch(const uint8_t* in, const uint64_t* in_off, uint8_t* out, const uint64_t* out_off, const int32_t* status,
                                        const uint32_t* nrec, const uint32_t* rec_words, uint32_t n, const uint32_t* queue_order, int shape,
-                                       int order, uint64_t seed, unsigned long long* stats) {
+                                       int order, uint64_t seed, unsigned long long* stats, int nthreads = 32) {
     WsCopyJob j;
     memset(&j, 0, sizeof(j));
     uint32_t counter = 0, fault = 0;
@@ -91,7 +91,8 @@ extern "C" int bro_warpsim_copy_launch(const uint8_t* in, const uint64_t* in_off
     j.shape = shape;
     memset(g_async_n, 0, sizeof(g_async_n));
     WsWarp* w = (WsWarp*)malloc(sizeof(WsWarp));
-    int err = ws_run(w, ws_copy_lane, &j, order, seed);
+    if (nthreads > 32 * (shape ? BRO_COPY_WARPS_SMALL : BRO_COPY_WARPS)) abort();       // (the kernel's staging is sized for its block)
+    int err = ws_run(w, ws_copy_lane, &j, order, seed, nthreads < 32 ? 32 : nthreads);
     g_copy_rendezvous = w->rendezvous;
     if (!err && fault) err = 101;
     if (stats) { stats[0] = cs[0]; stats[1] = cs[1]; }

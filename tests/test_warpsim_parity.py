@@ -527,3 +527,88 @@ def test_two_phase_path_with_its_retry_pass():
         for i, (e, r) in enumerate(zip(exp, res)):
             assert r[0] == e[0] and (e[0] != 0 or r[1] == e[1]), (part + i, e[0], r[0], streams[i][:16].hex())
     assert enc is None or handed >= 3, handed
+
+
+def test_parse_kernel_lanes_never_meet(tmp_path):
+    """the parse kernel under the race detector: 32 unrelated streams to a warp, and nothing one lane touches is touched by another
+    -- its stream, slot, records, table arena, and its block of shared memory, which is interleaved WORD BY WORD with the blocks
+    of the other 31 lanes (bro_decoder_core.h, BroTl).  A lane whose shared-memory accesses land one word further on (in its
+    neighbour's words) is reported."""
+    import hostsim
+    build = os.path.join(ROOT, "tests", "_build")
+    os.makedirs(build, exist_ok=True)
+    exe = os.path.join(build, "warpsim_parse_tsan")
+    csrc = os.path.join(ROOT, "brotli_rs_b200", "csrc")
+    srcs = [os.path.join(csrc, "bro_warpsim_parse.cpp"), os.path.join(ROOT, "oracle", "dict_blob.c")]
+    deps = srcs + [os.path.join(csrc, f) for f in warpsim.PARSE_DEPS]
+    if not (os.path.exists(exe) and all(os.path.getmtime(exe) >= os.path.getmtime(d) for d in deps)):
+        r = subprocess.run(["g++", "-std=c++17", "-O1", "-g", "-fsanitize=thread", "-DBRO_WARPSIM_MAIN", "-Wno-unknown-pragmas", "-o", exe] + srcs +
+                           ["-Wa,-I" + os.path.join(ROOT, "brotli_rs_b200", "data")], capture_output=True, text=True)
+        if r.returncode != 0:
+            pytest.skip("g++ -fsanitize=thread does not build here: " + r.stderr[-300:])
+    if "usage" not in subprocess.run([exe], capture_output=True, text=True).stderr:
+        pytest.skip("ThreadSanitizer does not start here")
+    files, expect = [], {}
+    streams = [(n, c) for n, c, _ in corpus_files()]
+    corpus = [c for _, c in streams]
+    streams += [("mut%03d" % i, m) for i, m in enumerate(fuzzgen.mutations(corpus, seed=201, count=150, max_len=30000))]
+    for name, comp in streams:
+        st, out = oracle.decode(comp)
+        p = str(tmp_path / name)
+        open(p, "wb").write(comp)
+        files.append("%s:%d" % (p, len(out)))
+        expect[p] = (st, len(out))
+    for lanes, order in ((32, 0), (32, 2), (6, 1)):
+        r = subprocess.run([exe, str(lanes), str(order), "1"] + files, env=dict(os.environ, TSAN_OPTIONS="exitcode=66"), capture_output=True,
+                           text=True, timeout=900)
+        assert r.returncode == 0 and "WARNING: ThreadSanitizer" not in r.stderr, r.stderr[:5000]
+        for ln in r.stdout.splitlines():
+            name, st1, n1, nrec, err = ln.rsplit(" ", 4)
+            st, size = expect[name]
+            assert err == "0" and (int(st1) in hostsim.RETRY or (int(st1) == st and (st != 0 or int(n1) == size))), ln
+    r = subprocess.run([exe, "32", "0", "1"] + files[:20], env=dict(os.environ, TSAN_OPTIONS="exitcode=66", BRO_WS_SMEM_SKEW="5"),
+                       capture_output=True, text=True, timeout=900)
+    assert "WARNING: ThreadSanitizer" in r.stderr
+
+
+def test_eight_warps_side_by_side_and_the_ordering_kernels():
+    """every launch of the two-phase call with a CTA of eight warps (256 threads, run interleaved thread by thread): the warps compete
+    for the streams of the work queues -- parse kernel, copy kernel, the fused kernel's retry pass -- and interleave their entries
+    in the completion queue; the streams are handed out in the order the size-class ordering kernels produce, which must be a
+    permutation that puts larger classes first, with the batch's longest stream and AUTO's verdict in the gate"""
+    rng = np.random.default_rng(77)
+    corpus = [c for _, c, _ in corpus_files()]
+    streams = corpus + list(fuzzgen.mutations(corpus, seed=311, count=500, max_len=20000))
+    in_off = np.zeros(len(streams) + 1, dtype=np.uint64)
+    in_off[1:] = np.cumsum([len(s) for s in streams])
+    lens = np.diff(in_off).astype(np.int64)
+
+    def size_class(l):
+        b = int(l).bit_length() - 1 if l else 0
+        sub = (int(l) >> (b - 3)) & 7 if b >= 3 else 0
+        return 255 - (b * 8 + sub)
+
+    for order in warpsim.ORDERS:
+        ho, gate = warpsim.order_streams(in_off, order=order, seed=5)
+        assert sorted(ho.tolist()) == list(range(len(streams)))
+        classes = [size_class(lens[i]) for i in ho]
+        assert classes == sorted(classes)
+        assert int(gate[0]) == int(lens.max()) and int(gate[1]) == int(int(lens.max()) * 4500 > int(in_off[-1]))
+    # a batch of equal streams is not bound by its longest one
+    eq = np.arange(0, 6001, dtype=np.uint64) * np.uint64(3900)
+    ho, gate = warpsim.order_streams(eq)
+    assert sorted(ho.tolist()) == list(range(6000)) and int(gate[1]) == 0 and int(gate[0]) == 3900
+    exp, caps = [], []
+    for s in streams:
+        st, out = oracle.decode(s)
+        cap = len(out) if rng.random() < 0.7 else int(rng.integers(0, len(out) + 64))
+        o, ol, sts = oracle.decode_batch(np.frombuffer(s, dtype=np.uint8), np.array([0, len(s)], dtype=np.uint64), np.array([0, cap], dtype=np.uint64))
+        caps.append(cap)
+        exp.append((int(sts[0]), o[: int(ol[0])].tobytes()))
+    ho, _ = warpsim.order_streams(in_off)
+    for k, (order, threads) in enumerate(((warpsim.SHUFFLED, 256), (warpsim.DESCENDING, 128), (warpsim.ASCENDING, 64))):
+        res, _, queue = warpsim.two_phase_kernels(streams, caps, hand_out=ho.tolist(), order=order, seed=k + 3, in_mis=3 * k, out_mis=5 * k,
+                                                  copy_shape=k & 1, retry_pass=True, threads=threads)
+        assert sorted(queue) == list(range(len(streams)))
+        for i, (e, r) in enumerate(zip(exp, res)):
+            assert r[0] == e[0] and (e[0] != 0 or r[1] == e[1]), (threads, i, e[0], r[0])

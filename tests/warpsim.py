@@ -196,7 +196,7 @@ def _lib_parse():
         L = ctypes.CDLL(so)
         L.bro_warpsim_parse_launch.restype = ctypes.c_int
         L.bro_warpsim_parse_launch.argtypes = [ctypes.c_void_p] * 8 + [ctypes.c_uint64, ctypes.c_uint32, ctypes.c_void_p, ctypes.c_uint32, ctypes.c_int,
-                                               ctypes.c_int, ctypes.c_int, ctypes.c_uint64, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p]
+                                               ctypes.c_int, ctypes.c_int, ctypes.c_uint64, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int]
         _LIB_PARSE = L
     return _LIB_PARSE
 
@@ -205,20 +205,21 @@ PARSE_ERRORS = {102: "a stream was never reported", 103: "the completion queue d
 
 
 def two_phase_kernels(streams, caps, quirks=0, lanes=32, hand_out=None, order=ASCENDING, seed=1, in_mis=0, out_mis=0, ring_late=True,
-                      copy_shape=0, copy_order=None, sizing=False, retry_pass=False, retry_latency=False):
+                      copy_shape=0, copy_order=None, sizing=False, retry_pass=False, retry_latency=False, threads=32):
     """A batch through BOTH kernels of the two-phase path as compiled for the host: ONE launch of the parse kernel (a warp holding
     `lanes` streams at a time, streams handed out in `hand_out` order) and ONE launch of the copy kernel over the completion queue
     the parse kernel left.  -> [(status, bytes)], streams handed to the fused kernel, completion order.  sizing: bro_batch_sizes'
     mode (only the parse kernel; bytes are empty, out_len = decoded size -> [(status, size)]).  retry_pass: the third launch of the
     product's two-phase path as well -- bro_decode_warp_kernel in retry mode over the same buffers decodes exactly the streams phase
-    one handed over, so that every status is final."""
+    one handed over, so that every status is final.  threads: the CTA of every launch (32 ... 256: up to eight warps side by side,
+    competing for the streams of the work queues and interleaving their entries in the completion queue)."""
     import numpy as np
     import hostsim
     two_phase([], [])            # (loads the copy library)
     LP, LC = _lib_parse(), _LIB_COPY
     LC.bro_warpsim_copy_launch.restype = ctypes.c_int
     LC.bro_warpsim_copy_launch.argtypes = [ctypes.c_void_p] * 7 + [ctypes.c_uint32, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_uint64,
-                                           ctypes.c_void_p]
+                                           ctypes.c_void_p, ctypes.c_int]
     n = len(streams)
     PAD = 256
     in_off = np.zeros(n + 1, dtype=np.uint64)
@@ -246,7 +247,7 @@ def two_phase_kernels(streams, caps, quirks=0, lanes=32, hand_out=None, order=AS
     err = LP.bro_warpsim_parse_launch(in_raw.ctypes.data + in_s, in_off.ctypes.data, out_raw.ctypes.data + out_s, out_off.ctypes.data,
                                       out_len.ctypes.data, status.ctypes.data, nrec.ctypes.data, rec_raw.ctypes.data + 4 * rec_s, rec_total, n,
                                       None if ho is None else ho.ctypes.data, lanes, quirks, int(sizing), order, seed, int(ring_late),
-                                      done_q.ctypes.data, retry.ctypes.data)
+                                      done_q.ctypes.data, retry.ctypes.data, threads)
     if err:
         raise AssertionError("warp simulation (parse kernel): " + (PARSE_ERRORS.get(err) or SIM_ERRORS.get(err, str(err))))
     assert int(retry[0]) == sum(int(s) in hostsim.RETRY for s in status[:n])
@@ -255,17 +256,17 @@ def two_phase_kernels(streams, caps, quirks=0, lanes=32, hand_out=None, order=AS
     stats = np.zeros(2, dtype=np.uint64)
     err = LC.bro_warpsim_copy_launch(in_raw.ctypes.data + in_s, in_off.ctypes.data, out_raw.ctypes.data + out_s, out_off.ctypes.data,
                                      status.ctypes.data, nrec.ctypes.data, rec_raw.ctypes.data + 4 * rec_s, n, done_q.ctypes.data, copy_shape,
-                                     order if copy_order is None else copy_order, seed, stats.ctypes.data)
+                                     order if copy_order is None else copy_order, seed, stats.ctypes.data, threads)
     if err:
         raise AssertionError("warp simulation (copy kernel): " + SIM_ERRORS.get(err, str(err)))
     if retry_pass and int(retry[0]):
         LF = lib()
         LF.bro_warpsim_fused_launch.restype = ctypes.c_int
         LF.bro_warpsim_fused_launch.argtypes = [ctypes.c_void_p] * 6 + [ctypes.c_uint32, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int,
-                                                ctypes.c_int, ctypes.c_uint64]
+                                                ctypes.c_int, ctypes.c_uint64, ctypes.c_int]
         before = status[:n].copy()
         err = LF.bro_warpsim_fused_launch(in_raw.ctypes.data + in_s, in_off.ctypes.data, out_raw.ctypes.data + out_s, out_off.ctypes.data,
-                                          out_len.ctypes.data, status.ctypes.data, n, None, 1, int(retry_latency), quirks, order, seed)
+                                          out_len.ctypes.data, status.ctypes.data, n, None, 1, int(retry_latency), quirks, order, seed, threads)
         if err:
             raise AssertionError("warp simulation (fused kernel, retry pass): " + SIM_ERRORS.get(err, str(err)))
         keep = np.array([int(x) not in hostsim.RETRY for x in before])
@@ -277,3 +278,20 @@ def two_phase_kernels(streams, caps, quirks=0, lanes=32, hand_out=None, order=AS
         b = out_s + int(out_off[i])
         res.append((int(status[i]), out_raw[b: b + int(out_len[i])].tobytes()))
     return res, int(retry[0]), done_q[:n].tolist()
+
+
+def order_streams(in_off, order=ASCENDING, seed=1):
+    """the size-class ordering kernels (bro_order_*: what bro_order_launch launches in front of the parse kernel), CTA by CTA
+    -> (order[n], gate[2])"""
+    import numpy as np
+    L = _lib_parse()
+    L.bro_warpsim_order.restype = ctypes.c_int
+    L.bro_warpsim_order.argtypes = [ctypes.c_void_p, ctypes.c_uint32, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_uint64]
+    in_off = np.ascontiguousarray(in_off, dtype=np.uint64)
+    n = len(in_off) - 1
+    out = np.full(n + 1, 0xffffffff, dtype=np.uint32)
+    gate = np.zeros(2, dtype=np.uint32)
+    err = L.bro_warpsim_order(in_off.ctypes.data, n, out.ctypes.data, gate.ctypes.data, order, seed)
+    if err:
+        raise AssertionError("warp simulation (ordering kernels): " + SIM_ERRORS.get(err, str(err)))
+    return out[:n], gate
