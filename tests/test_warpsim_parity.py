@@ -558,9 +558,9 @@ def test_parse_kernel_lanes_never_meet(tmp_path):
         open(p, "wb").write(comp)
         files.append("%s:%d" % (p, len(out)))
         expect[p] = (st, len(out))
-    for lanes, order in ((32, 0), (32, 2), (6, 1)):
-        r = subprocess.run([exe, str(lanes), str(order), "1"] + files, env=dict(os.environ, TSAN_OPTIONS="exitcode=66"), capture_output=True,
-                           text=True, timeout=900)
+    for lanes, order, threads in ((32, 0, 32), (32, 2, 64), (6, 1, 32)):         # (64 threads: two warps side by side, one insert/copy table)
+        r = subprocess.run([exe, str(lanes), str(order), "1"] + files, env=dict(os.environ, TSAN_OPTIONS="exitcode=66", BRO_WS_THREADS=str(threads)),
+                           capture_output=True, text=True, timeout=900)
         assert r.returncode == 0 and "WARNING: ThreadSanitizer" not in r.stderr, r.stderr[:5000]
         for ln in r.stdout.splitlines():
             name, st1, n1, nrec, err = ln.rsplit(" ", 4)

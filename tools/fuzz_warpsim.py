@@ -1,8 +1,8 @@
 #!/usr/bin/env python3
 """CPU fuzz campaign over the KERNELS' OWN CODE as compiled for the host (tests/warpsim.py: 32 lanes as fibers): mutated streams
 -- seeded with the corpus and with fresh libbrotli streams of every quality band, heterogeneous payloads included -- go through
-(a) the fused kernel's per-warp code, both builds, and (b) the parse kernel and then the copy kernel as one batch, under a random
-lane order, stream / slot alignment, slot capacity (exact, too small, generous) and warp occupancy (`lanes`), and are compared
+(a) the fused kernel's per-warp code, both builds, and (b) the three launches of the two-phase call as one batch -- parse kernel,
+copy kernel, the fused kernel's retry pass; CTAs of 1, 2 or 8 warps -- under a random lane order, stream / slot alignment, slot capacity (exact, too small, generous) and warp occupancy (`lanes`), and are compared
 with the oracle (status class and bytes).  The GPU twin of this harness is tools/fuzz_gpu.py.
 
     python tools/fuzz_warpsim.py [--count 4000] [--seed 1] [--jobs 8] [--fresh 24]
@@ -76,16 +76,15 @@ def worker(args):
         order, copy_order = int(rng.integers(3)), int(rng.integers(3))
         ho = [int(x) for x in rng.permutation(len(part))] if rng.random() < 0.5 else None
         try:
-            res, _, _ = warpsim.two_phase_kernels([streams[i] for i in part], [caps[i] for i in part], lanes=lanes, hand_out=ho, order=order,
-                                                  seed=k, in_mis=int(rng.integers(16)), out_mis=int(rng.integers(16)), copy_shape=int(rng.integers(2)),
-                                                  copy_order=copy_order)
+            res, nretry, _ = warpsim.two_phase_kernels([streams[i] for i in part], [caps[i] for i in part], lanes=lanes, hand_out=ho, order=order,
+                                                       seed=k, in_mis=int(rng.integers(16)), out_mis=int(rng.integers(16)), copy_shape=int(rng.integers(2)),
+                                                       copy_order=copy_order, retry_pass=True, retry_latency=bool(rng.integers(2)),
+                                                       threads=int(rng.choice([32, 32, 64, 256])))
+            handed += nretry
         except AssertionError as e:
             bad.append(("two-phase", job, part[0], "sim", str(e), "", len(part), lanes, order, copy_order))
             continue
         for i, got in zip(part, res):
-            if got[0] in hostsim.RETRY:
-                handed += 1
-                continue
             if got[0] != exp[i][0] or (exp[i][0] == 0 and got[1] != exp[i][1]):
                 bad.append(("two-phase", job, i, exp[i][0], got[0], streams[i].hex()[:64], len(streams[i]), caps[i], lanes, order))
     return bad, classes, handed, len(streams)
@@ -107,7 +106,7 @@ def main():
     classes = set().union(*[r[1] for r in results])
     for b in bad[:40]:
         print("MISMATCH", b)
-    print("fuzz_warpsim: %d streams x (fused code, parse + copy kernels), %d status classes, %d handed to the fused kernel by phase one, %d mismatches"
+    print("fuzz_warpsim: %d streams x (fused code; parse + copy kernels + retry pass), %d status classes, %d handed to the fused kernel by phase one, %d mismatches"
           % (sum(r[3] for r in results), len(classes), sum(r[2] for r in results), len(bad)))
     return 1 if bad else 0
 
