@@ -11,7 +11,9 @@
 //
 // A kernel of its own rather than a mode of bro_decode_warp_kernel, so that the batch kernel's code and register
 // allocation stay what was tuned and measured.
+#if !defined(BRO_WARPSIM)   /* (BRO_WARPSIM: this kernel compiled for the host, 32 lanes as fibers -- CPU test-suite only, bro_warpsim.cpp) */
 #include <cuda_runtime.h>
+#endif
 #include <stdint.h>
 
 #include "bro_decoder_core.h"
@@ -20,7 +22,11 @@
 #define BRO_RESUME_WARPS 8
 
 __global__ void __launch_bounds__(BRO_RESUME_WARPS * 32, 2) bro_decode_resume_kernel(BroLaunch p) {      // 128 registers: a reader's one stream is latency-bound
+#if defined(BRO_WARPSIM)
+    uint8_t* const bro_smem_raw = ws_dynamic_smem;
+#else
     extern __shared__ __align__(16) uint8_t bro_smem_raw[];
+#endif
     BroScratch* const scratch = (BroScratch*)bro_smem_raw;
     const unsigned warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
     const unsigned gwarp = blockIdx.x * BRO_RESUME_WARPS + warp;
@@ -53,6 +59,7 @@ __global__ void __launch_bounds__(BRO_RESUME_WARPS * 32, 2) bro_decode_resume_ke
     }
 }
 
+#if !defined(BRO_WARPSIM)
 extern "C" int bro_resume_kernel_warps_per_cta() { return BRO_RESUME_WARPS; }
 
 extern "C" int bro_resume_kernel_launch(const BroLaunch* p, int grid, cudaStream_t stream) {
@@ -64,3 +71,4 @@ extern "C" int bro_resume_kernel_launch(const BroLaunch* p, int grid, cudaStream
     bro_decode_resume_kernel<<<grid, BRO_RESUME_WARPS * 32, BRO_RESUME_WARPS * sizeof(BroScratch), stream>>>(*p);
     return (int)cudaGetLastError();
 }
+#endif

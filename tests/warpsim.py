@@ -295,3 +295,14 @@ def order_streams(in_off, order=ASCENDING, seed=1):
     if err:
         raise AssertionError("warp simulation (ordering kernels): " + SIM_ERRORS.get(err, str(err)))
     return out[:n], gate
+
+
+def sizes_finish(status):
+    """bro_sizes_finish_kernel over a status array (bro_batch_sizes' last launch: hand-over codes -> SizeUnknown) -> new array"""
+    import numpy as np
+    L = _lib_parse()
+    L.bro_warpsim_sizes_finish.restype = ctypes.c_int
+    L.bro_warpsim_sizes_finish.argtypes = [ctypes.c_void_p, ctypes.c_uint32]
+    st = np.ascontiguousarray(status, dtype=np.int32).copy()
+    assert L.bro_warpsim_sizes_finish(st.ctypes.data, len(st)) == 0
+    return st

@@ -48,11 +48,13 @@ def worker(args):
     streams = list(fuzzgen.mutations(corpus, seed=1000 * seed + job, count=count, max_len=60000))
     bad, classes, handed = [], set(), 0
     caps, exp = [], []
+    quirks = job & 1          # odd workers decode in BRO_QUIRKS_SPEC mode, against the oracle in the same mode
     for s in streams:
-        st, out = oracle.decode(s)
+        st, out = oracle.decode(s, quirks=quirks)
         r = rng.random()
         cap = len(out) if r < 0.4 else len(out) + 4096 if r < 0.6 else int(rng.integers(0, len(out) + 64))
-        o, ol, sts = oracle.decode_batch(np.frombuffer(s, dtype=np.uint8), np.array([0, len(s)], dtype=np.uint64), np.array([0, cap], dtype=np.uint64))
+        o, ol, sts = oracle.decode_batch(np.frombuffer(s, dtype=np.uint8), np.array([0, len(s)], dtype=np.uint64), np.array([0, cap], dtype=np.uint64),
+                                         quirks=quirks)
         caps.append(cap)
         exp.append((int(sts[0]), o[: int(ol[0])].tobytes()))
         classes.add(int(sts[0]))
@@ -61,11 +63,23 @@ def worker(args):
         latency, order = bool(rng.integers(2)), int(rng.integers(3))
         warpsim.set_alignment(int(rng.integers(128)), int(rng.integers(16)))
         try:
-            got = warpsim.decode(s, cap=caps[i], latency=latency, order=order, seed=i + 1)
+            got = warpsim.decode(s, cap=caps[i], quirks=quirks, latency=latency, order=order, seed=i + 1)
         except AssertionError as e:
             got = ("sim", str(e))
         if got[0] != exp[i][0] or (exp[i][0] == 0 and got[1] != exp[i][1]):
             bad.append(("fused", job, i, exp[i][0], got[0], s.hex()[:64], len(s), caps[i], latency, order))
+    # (a') one stream in sixteen through the streaming reader's loop over the resume kernel's code, input in random pieces
+    warpsim.set_alignment(0, 0)
+    for i in range(0, len(streams), 16):
+        s = streams[i]
+        chunks = [int(x) for x in rng.integers(1, max(2, len(s)), 4)]
+        st, out = oracle.decode(s, quirks=quirks)
+        try:
+            st1, served, _, _, _ = warpsim.stream_decode(s, chunks, quirks=quirks, order=int(rng.integers(3)), seed=i + 1)
+        except AssertionError as e:
+            st1, served = "sim", b""
+        if st1 != st or (st == 0 and served != out) or (st != 0 and not out.startswith(served)):
+            bad.append(("streaming", job, i, st, st1, s.hex()[:64], len(s), chunks))
     # (b) both kernels of the two-phase path, in batches of up to 96 streams
     k = 0
     while k < len(streams):
@@ -76,7 +90,7 @@ def worker(args):
         order, copy_order = int(rng.integers(3)), int(rng.integers(3))
         ho = [int(x) for x in rng.permutation(len(part))] if rng.random() < 0.5 else None
         try:
-            res, nretry, _ = warpsim.two_phase_kernels([streams[i] for i in part], [caps[i] for i in part], lanes=lanes, hand_out=ho, order=order,
+            res, nretry, _ = warpsim.two_phase_kernels([streams[i] for i in part], [caps[i] for i in part], quirks=quirks, lanes=lanes, hand_out=ho, order=order,
                                                        seed=k, in_mis=int(rng.integers(16)), out_mis=int(rng.integers(16)), copy_shape=int(rng.integers(2)),
                                                        copy_order=copy_order, retry_pass=True, retry_latency=bool(rng.integers(2)),
                                                        threads=int(rng.choice([32, 32, 64, 256])))
@@ -106,7 +120,7 @@ def main():
     classes = set().union(*[r[1] for r in results])
     for b in bad[:40]:
         print("MISMATCH", b)
-    print("fuzz_warpsim: %d streams x (fused code; parse + copy kernels + retry pass), %d status classes, %d handed to the fused kernel by phase one, %d mismatches"
+    print("fuzz_warpsim: %d streams x (fused code; parse + copy kernels + retry pass; 1 in 16 through the streaming reader), both quirk modes, %d status classes, %d handed to the fused kernel by phase one, %d mismatches"
           % (sum(r[3] for r in results), len(classes), sum(r[2] for r in results), len(bad)))
     return 1 if bad else 0
 
