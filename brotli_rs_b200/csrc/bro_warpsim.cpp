@@ -225,6 +225,43 @@ int main(int argc, char** argv) {
         ws_guard_install();
     }
     if (getenv("BRO_WS_DROP_SYNC")) g_sync_drop_line = atoi(getenv("BRO_WS_DROP_SYNC"));      // mutation: the report must name it
+    if (getenv("BRO_WS_BATCH")) {
+        // BRO_WS_BATCH=<threads>: the files as ONE batch through bro_decode_warp_kernel itself, a CTA of threads / 32 warps that take
+        // streams from the work queue side by side (each with its own scratch block and table arena: nothing may be shared)
+        const int threads = atoi(getenv("BRO_WS_BATCH"));
+        const uint32_t n = (uint32_t)(argc - 6);
+        uint64_t* in_off = (uint64_t*)calloc(2u * (n + 1u), sizeof(uint64_t));
+        uint64_t* out_off = in_off + (n + 1u);
+        const size_t PADB = 256;
+        uint8_t* in = (uint8_t*)calloc(2 * PADB, 1);
+        for (uint32_t i = 0; i < n; i++) {
+            char* colon = strrchr(argv[6 + i], ':');
+            if (!colon) return 2;
+            *colon = 0;
+            out_off[i + 1] = out_off[i] + strtoull(colon + 1, 0, 10) + slack;
+            FILE* f = fopen(argv[6 + i], "rb");
+            if (!f) { perror(argv[6 + i]); return 2; }
+            fseek(f, 0, SEEK_END);
+            const size_t len = (size_t)ftell(f);
+            fseek(f, 0, SEEK_SET);
+            in = (uint8_t*)realloc(in, PADB + (size_t)in_off[i] + len + PADB);
+            if (fread(in + PADB + in_off[i], 1, len, f) != len) return 2;
+            fclose(f);
+            in_off[i + 1] = in_off[i] + len;
+        }
+        memset(in + PADB + in_off[n], 0, PADB);
+        uint8_t* out = (uint8_t*)calloc((size_t)out_off[n] + 2 * PADB, 1);
+        uint64_t* out_len = (uint64_t*)calloc(n + 1u, sizeof(uint64_t));
+        int32_t* status = (int32_t*)calloc(n + 1u, sizeof(int32_t));
+        const int err = bro_warpsim_fused_launch(in + PADB, in_off, out + PADB, out_off, out_len, status, n, 0, 0, latency, quirks, order, seed, threads);
+        for (uint32_t i = 0; i < n; i++) {
+            uint64_t h = 1469598103934665603ull;
+            const uint64_t cap = out_off[i + 1] - out_off[i], len = out_len[i] < cap ? out_len[i] : cap;
+            for (uint64_t k = 0; k < len; k++) h = (h ^ out[PADB + out_off[i] + k]) * 1099511628211ull;
+            printf("%s %d %llu %016llx %d\n", argv[6 + i], status[i], (unsigned long long)len, (unsigned long long)h, err);
+        }
+        return err ? 3 : 0;
+    }
     for (int a = 6; a < argc; a++) {
         char* colon = strrchr(argv[a], ':');
         if (!colon) return 2;

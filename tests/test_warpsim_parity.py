@@ -207,11 +207,14 @@ def _tsan_binary():
     return exe
 
 
-def _tsan_run(exe, files, latency=0, order=0, quirks=0, align=(0, 0), drop=None):
-    """-> (ThreadSanitizer reports, {file: (status, out_len, fnv1a64 hex)}, stderr)"""
+def _tsan_run(exe, files, latency=0, order=0, quirks=0, align=(0, 0), drop=None, batch_threads=None):
+    """-> (ThreadSanitizer reports, {file: (status, out_len, fnv1a64 hex)}, stderr).  batch_threads: the files as one batch through
+    bro_decode_warp_kernel itself with a CTA of that many threads"""
     env = dict(os.environ, BRO_WS_ALIGN="%d,%d" % align, TSAN_OPTIONS="exitcode=66 history_size=4")
     if drop is not None:
         env["BRO_WS_DROP_SYNC"] = str(drop)
+    if batch_threads:
+        env["BRO_WS_BATCH"] = str(batch_threads)
     r = subprocess.run([exe, str(latency), str(order), "1", str(quirks), "0"] + ["%s:%d" % f for f in files], env=env, capture_output=True,
                        text=True, timeout=600)
     assert r.returncode in (0, 66), r.stderr[-2000:]
@@ -257,12 +260,19 @@ def test_no_data_race_between_lanes(tmp_path):
             for q, lgwin, size in ((5, 16, 60000), (9, 18, 40000), (11, 16, 30000), (10, 22, 30000)):
                 k += 1
                 add("fresh%02d" % k, fuzzgen.compress(enc, fuzzgen.synthetic_raw(kind, 900 + k, size), q, lgwin))
-    for latency, order, align in ((0, 0, (0, 0)), (1, 1, (77, 5)), (0, 2, (124, 15))):
+    for latency, order, align in ((0, 0, (0, 0)), (1, 1, (77, 5))):
         races, res, err = _tsan_run(exe, files, latency=latency, order=order, align=align)
         assert races == 0, err[:6000]
         for p, (st, out) in expect.items():
             st1, n1, h1 = res[p]
             assert st1 == st and (st != 0 or (n1, h1) == (len(out), _fnv(out))), (os.path.basename(p), latency, order, align, st, st1)
+    # the same streams as ONE batch through bro_decode_warp_kernel itself, eight warps taking streams from the work queue side by side
+    # (each warp its own scratch block in shared memory and its own table arena): no report, same results
+    races, res, err = _tsan_run(exe, files, latency=1, order=2, batch_threads=256)
+    assert races == 0, err[:6000]
+    for p, (st, out) in expect.items():
+        st1, n1, h1 = res[p]
+        assert st1 == st and (st != 0 or (n1, h1) == (len(out), _fnv(out))), (os.path.basename(p), "batch", st, st1)
     # the detector detects: the barrier in front of pass 2 of the table build (its stores to the per-length positions are read by
     # other lanes), and the one behind the staging of the general loop's on-chip tables
     small = [f for f in files if os.path.basename(f[0]) in ("alice29.txt.compressed", "10x10y.compressed", "fresh03", "fresh04")]
