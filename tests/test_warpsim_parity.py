@@ -3,7 +3,9 @@ bro_decode_warp_kernel and bro_decode_resume_kernel compile) against the oracle:
 fibers that meet at the warp intrinsics, in ascending, descending and shuffled lane order, at every alignment of the
 compressed stream and of the output slot.  The second half is a race check under the CUDA memory model (ThreadSanitizer
 over the same fibers; only __syncwarp orders memory between lanes), including the global-memory buffers that
-compute-sanitizer's racecheck does not see.  The GPU parity tests proper are tests/test_gpu_parity.py."""
+compute-sanitizer's racecheck does not see.  The race-check and guarded-buffer binaries are also built with
+-fsanitize=undefined (no recovery): a misaligned vector access -- a fault on the device -- a shift by 32 or more, or a signed
+overflow in the kernels' code ends the run.  The GPU parity tests proper are tests/test_gpu_parity.py."""
 import os
 import re
 import subprocess
@@ -196,7 +198,7 @@ def _tsan_binary():
     srcs = [os.path.join(csrc, "bro_warpsim.cpp"), os.path.join(ROOT, "oracle", "dict_blob.c")]
     deps = srcs + [os.path.join(csrc, f) for f in ("bro_warpsim.h", "bro_decoder_core.h", "bro_records.h", "bro_status.h", "bro_tables_generated.h")]
     if not (os.path.exists(exe) and all(os.path.getmtime(exe) >= os.path.getmtime(d) for d in deps)):
-        cmd = ["g++", "-std=c++17", "-O1", "-g", "-fsanitize=thread", "-DBRO_WARPSIM_MAIN", "-Wno-unknown-pragmas", "-o", exe] + srcs + \
+        cmd = ["g++", "-std=c++17", "-O1", "-g", "-fsanitize=thread,undefined", "-fno-sanitize-recover=undefined", "-DBRO_WARPSIM_MAIN", "-Wno-unknown-pragmas", "-o", exe] + srcs + \
               ["-Wa,-I" + os.path.join(ROOT, "brotli_rs_b200", "data")]
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
@@ -213,6 +215,7 @@ def _tsan_run(exe, files, latency=0, order=0, quirks=0, align=(0, 0), drop=None,
     env = dict(os.environ, BRO_WS_ALIGN="%d,%d" % align, TSAN_OPTIONS="exitcode=66 history_size=4")
     if drop is not None:
         env["BRO_WS_DROP_SYNC"] = str(drop)
+        env["TSAN_OPTIONS"] += " halt_on_error=1"         # (a mutation run only has to produce its first report)
     if batch_threads:
         env["BRO_WS_BATCH"] = str(batch_threads)
     r = subprocess.run([exe, str(latency), str(order), "1", str(quirks), "0"] + ["%s:%d" % f for f in files], env=env, capture_output=True,
@@ -251,7 +254,7 @@ def test_no_data_race_between_lanes(tmp_path):
         if len(comp) <= 170000:
             add(name, comp)
     corpus = [c for _, c, _ in corpus_files()]
-    for i, m in enumerate(fuzzgen.mutations(corpus, seed=77, count=120, max_len=30000)):
+    for i, m in enumerate(fuzzgen.mutations(corpus, seed=77, count=60, max_len=30000)):
         add("mut%03d" % i, m)
     enc = fuzzgen.libbrotli_enc()
     if enc is not None:
@@ -347,7 +350,7 @@ def test_copy_kernel_no_data_race_between_lanes(tmp_path):
     deps = srcs + [os.path.join(csrc, f) for f in warpsim.COPY_DEPS]
     if not (os.path.exists(exe) and all(os.path.getmtime(exe) >= os.path.getmtime(d) for d in deps)):
         os.makedirs(build, exist_ok=True)
-        r = subprocess.run(["g++", "-std=c++17", "-O1", "-g", "-fsanitize=thread", "-DBRO_WARPSIM_MAIN", "-Wno-unknown-pragmas", "-o", exe] + srcs +
+        r = subprocess.run(["g++", "-std=c++17", "-O1", "-g", "-fsanitize=thread,undefined", "-fno-sanitize-recover=undefined", "-DBRO_WARPSIM_MAIN", "-Wno-unknown-pragmas", "-o", exe] + srcs +
                            ["-Wa,-I" + os.path.join(ROOT, "brotli_rs_b200", "data")], capture_output=True, text=True)
         if r.returncode != 0:
             pytest.skip("g++ -fsanitize=thread does not build here: " + r.stderr[-300:])
@@ -377,6 +380,7 @@ def test_copy_kernel_no_data_race_between_lanes(tmp_path):
                    TSAN_OPTIONS="exitcode=66 suppressions=" + os.path.join(ROOT, "tests", "warpsim_tsan.supp"))
         if drop is not None:
             env["BRO_WS_DROP_SYNC"] = str(drop)
+            env["TSAN_OPTIONS"] += " halt_on_error=1"
         r = subprocess.run([exe, str(shape), str(order), "1", str(queue_seed)] + files, env=env, capture_output=True, text=True, timeout=900)
         assert r.returncode in (0, 66), r.stderr[-2000:]
         return r.stderr.count("WARNING: ThreadSanitizer"), r
@@ -389,6 +393,9 @@ def test_copy_kernel_no_data_race_between_lanes(tmp_path):
             name, st1, n1, h1, err = ln.rsplit(" ", 4)
             st, out = expect[name]
             assert err == "0" and (int(st1) in hostsim.RETRY or (int(st1) == st and (st != 0 or (int(n1), h1) == (len(out), _fnv(out))))), ln
+    all_files = list(files)
+    del files[:]
+    files.extend(f for f in all_files if any(k in f for k in ("64x", "backward65536", "quickfox", "alice29", "zeros", "monkey", "ukkonooa")))
     for pattern in (r"stores of earlier groups are visible", r"done \+= m;"):
         races, _ = run(0, 0, (3, 5), drop=_copy_barrier_line(pattern))
         assert races >= 1, pattern
@@ -486,7 +493,8 @@ def test_fused_code_stays_inside_the_granules_of_its_buffers(tmp_path):
     srcs = [os.path.join(csrc, "bro_warpsim.cpp"), os.path.join(ROOT, "oracle", "dict_blob.c")]
     deps = srcs + [os.path.join(csrc, f) for f in ("bro_warpsim.h", "bro_decoder_core.h", "bro_records.h", "bro_status.h", "bro_tables_generated.h")]
     if not (os.path.exists(exe) and all(os.path.getmtime(exe) >= os.path.getmtime(d) for d in deps)):
-        subprocess.check_call(["g++", "-std=c++17", "-O2", "-g", "-DBRO_WARPSIM_MAIN", "-Wno-unknown-pragmas", "-o", exe] + srcs +
+        subprocess.check_call(["g++", "-std=c++17", "-O2", "-g", "-fsanitize=undefined", "-fno-sanitize-recover=undefined", "-DBRO_WARPSIM_MAIN",
+                               "-Wno-unknown-pragmas", "-o", exe] + srcs +
                               ["-Wa,-I" + os.path.join(ROOT, "brotli_rs_b200", "data")])
     files, expect = [], {}
     for name, comp, _ in corpus_files():
@@ -552,7 +560,7 @@ def test_parse_kernel_lanes_never_meet(tmp_path):
     srcs = [os.path.join(csrc, "bro_warpsim_parse.cpp"), os.path.join(ROOT, "oracle", "dict_blob.c")]
     deps = srcs + [os.path.join(csrc, f) for f in warpsim.PARSE_DEPS]
     if not (os.path.exists(exe) and all(os.path.getmtime(exe) >= os.path.getmtime(d) for d in deps)):
-        r = subprocess.run(["g++", "-std=c++17", "-O1", "-g", "-fsanitize=thread", "-DBRO_WARPSIM_MAIN", "-Wno-unknown-pragmas", "-o", exe] + srcs +
+        r = subprocess.run(["g++", "-std=c++17", "-O1", "-g", "-fsanitize=thread,undefined", "-fno-sanitize-recover=undefined", "-DBRO_WARPSIM_MAIN", "-Wno-unknown-pragmas", "-o", exe] + srcs +
                            ["-Wa,-I" + os.path.join(ROOT, "brotli_rs_b200", "data")], capture_output=True, text=True)
         if r.returncode != 0:
             pytest.skip("g++ -fsanitize=thread does not build here: " + r.stderr[-300:])
