@@ -634,3 +634,59 @@ def test_eight_warps_side_by_side_and_the_ordering_kernels():
         assert sorted(queue) == list(range(len(streams)))
         for i, (e, r) in enumerate(zip(exp, res)):
             assert r[0] == e[0] and (e[0] != 0 or r[1] == e[1]), (threads, i, e[0], r[0])
+
+
+def test_kernels_under_address_sanitizer(tmp_path):
+    """memory safety of the kernels' code on valid and mutated streams (the CPU twin of compute-sanitizer memcheck over
+    tools/fuzz_gpu.py): the fused kernel as a batch of eight warps, the parse kernel, and the copy kernel behind phase one, built with
+    -fsanitize=address,undefined -- table arenas, scratch blocks, shared-memory arrays, records, streams and slots all have red zones"""
+    build = os.path.join(ROOT, "tests", "_build")
+    os.makedirs(build, exist_ok=True)
+    csrc = os.path.join(ROOT, "brotli_rs_b200", "csrc")
+    blob = os.path.join(ROOT, "oracle", "dict_blob.c")
+    targets = (("warpsim_asan", ["bro_warpsim.cpp"], ("bro_warpsim.h", "bro_kernels.cu", "bro_kernels_resume.cu", "bro_decoder_core.h")),
+               ("warpsim_parse_asan", ["bro_warpsim_parse.cpp"], warpsim.PARSE_DEPS),
+               ("warpsim_copy_asan", list(warpsim.COPY_SOURCES), warpsim.COPY_DEPS))
+    exes = {}
+    for name, sources, dep_names in targets:
+        exe = os.path.join(build, name)
+        srcs = [os.path.join(csrc, f) for f in sources] + [blob]
+        deps = srcs + [os.path.join(csrc, f) for f in dep_names]
+        if not (os.path.exists(exe) and all(os.path.getmtime(exe) >= os.path.getmtime(d) for d in deps)):
+            r = subprocess.run(["g++", "-std=c++17", "-O1", "-g", "-fsanitize=address,undefined", "-fno-sanitize-recover=undefined", "-DBRO_WARPSIM_MAIN",
+                                "-Wno-unknown-pragmas", "-o", exe] + srcs + ["-Wa,-I" + os.path.join(ROOT, "brotli_rs_b200", "data")],
+                               capture_output=True, text=True)
+            if r.returncode != 0:
+                pytest.skip("g++ -fsanitize=address does not build here: " + r.stderr[-300:])
+        exes[name] = exe
+    import hostsim
+    rng = np.random.default_rng(5)
+    files, expect = [], {}
+    streams = [(n, c) for n, c, _ in corpus_files() if len(c) <= 170000]
+    corpus = [c for _, c in streams]
+    streams += [("mut%03d" % i, m) for i, m in enumerate(fuzzgen.mutations(corpus, seed=401, count=250, max_len=30000))]
+    for name, comp in streams:
+        st, out = oracle.decode(comp)
+        cap = len(out) if rng.random() < 0.7 else int(rng.integers(0, len(out) + 64))
+        o, ol, sts = oracle.decode_batch(np.frombuffer(comp, dtype=np.uint8), np.array([0, len(comp)], dtype=np.uint64), np.array([0, cap], dtype=np.uint64))
+        p = str(tmp_path / name)
+        open(p, "wb").write(comp)
+        files.append("%s:%d" % (p, cap))
+        expect[p] = (int(sts[0]), o[: int(ol[0])].tobytes())
+    env = dict(os.environ, ASAN_OPTIONS="detect_leaks=0:abort_on_error=0:exitcode=55")
+    runs = (([exes["warpsim_asan"], "1", "2", "1", "0", "0"], dict(env, BRO_WS_BATCH="256"), True),
+            ([exes["warpsim_asan"], "0", "1", "3", "0", "0"], dict(env, BRO_WS_ALIGN="101,7"), True),
+            ([exes["warpsim_parse_asan"], "32", "2", "1"], dict(env, BRO_WS_THREADS="64"), False),
+            ([exes["warpsim_copy_asan"], "0", "2", "1", "5"], dict(env, BRO_WS_ALIGN="3,5"), True))
+    for cmd, e, has_bytes in runs:
+        r = subprocess.run(cmd + files, env=e, capture_output=True, text=True, timeout=900)
+        assert r.returncode == 0 and "ERROR: AddressSanitizer" not in r.stderr and "runtime error" not in r.stderr, (cmd[0], r.returncode, r.stderr[:4000])
+        for ln in r.stdout.splitlines():
+            name, st1, n1, tail, err = ln.rsplit(" ", 4)
+            st, out = expect[name]
+            assert err == "0", ln
+            if int(st1) in hostsim.RETRY:
+                continue
+            assert int(st1) == st, (cmd[0], ln, st)
+            if st == 0:
+                assert int(n1) == len(out) and (not has_bytes or tail == _fnv(out)), (cmd[0], ln)
