@@ -202,7 +202,8 @@ class BatchDecoder:
         res = []
         for i in range(len(streams)):
             b = int(out_off[i])
-            res.append((int(status[i]), out[b: b + int(out_len[i])].tobytes()))
+            n = min(int(out_len[i]), int(out_off[i + 1]) - b)      # (a failed stream may report a position beyond its slot)
+            res.append((int(status[i]), out[b: b + n].tobytes()))
         return res
 
 

@@ -104,13 +104,71 @@ def worker(args):
     return bad, classes, handed, len(streams)
 
 
+def asan_worker(args):
+    """one chunk of mutated streams through the address-sanitizer builds of the three simulated kernels (tests/_build/warpsim_*_asan,
+    built by tests/test_warpsim_parity.py::test_kernels_under_address_sanitizer) -> (problems, streams)"""
+    job, count, seed, fresh = args
+    import subprocess
+    import tempfile
+    import fuzzgen
+    import hostsim
+    from oracle import oracle
+    rng = np.random.default_rng(7000 * seed + job)
+    streams = list(fuzzgen.mutations(seeds(fresh, seed), seed=7000 * seed + job, count=count, max_len=60000))
+    build = os.path.join(ROOT, "tests", "_build")
+    bad = []
+    with tempfile.TemporaryDirectory() as tmp:
+        for k0 in range(0, len(streams), 300):
+            files, expect = [], {}
+            for i, s in enumerate(streams[k0: k0 + 300]):
+                st, out = oracle.decode(s)
+                cap = len(out) if rng.random() < 0.6 else int(rng.integers(0, len(out) + 64))
+                o, ol, sts = oracle.decode_batch(np.frombuffer(s, dtype=np.uint8), np.array([0, len(s)], dtype=np.uint64), np.array([0, cap], dtype=np.uint64))
+                p = os.path.join(tmp, "s%05d" % (k0 + i))
+                open(p, "wb").write(s)
+                files.append("%s:%d" % (p, cap))
+                expect[p] = (int(sts[0]), int(ol[0]))
+            env = dict(os.environ, ASAN_OPTIONS="detect_leaks=0:exitcode=55")
+            runs = (([os.path.join(build, "warpsim_asan"), str(int(rng.integers(2))), str(int(rng.integers(3))), str(k0 + 1), "0", "0"],
+                     dict(env, BRO_WS_BATCH=str(int(rng.choice([32, 64, 256]))))),
+                    ([os.path.join(build, "warpsim_asan"), str(int(rng.integers(2))), str(int(rng.integers(3))), str(k0 + 1), "0", "0"],
+                     dict(env, BRO_WS_ALIGN="%d,%d" % (int(rng.integers(128)), int(rng.integers(16))))),
+                    ([os.path.join(build, "warpsim_parse_asan"), str(int(rng.choice([32, 32, 9, 1]))), str(int(rng.integers(3))), str(k0 + 1)],
+                     dict(env, BRO_WS_THREADS=str(int(rng.choice([32, 64]))))),
+                    ([os.path.join(build, "warpsim_copy_asan"), str(int(rng.integers(2))), str(int(rng.integers(3))), str(k0 + 1), str(k0 + 5)],
+                     dict(env, BRO_WS_ALIGN="%d,%d" % (int(rng.integers(16)), int(rng.integers(16))))))
+            for cmd, e in runs:
+                r = subprocess.run(cmd + files, env=e, capture_output=True, text=True)
+                if r.returncode != 0 or "ERROR: AddressSanitizer" in r.stderr or "runtime error" in r.stderr:
+                    bad.append((os.path.basename(cmd[0]), job, k0, r.returncode, r.stderr[:1500]))
+                    continue
+                for ln in r.stdout.splitlines():
+                    name, st1, n1, _, err = ln.rsplit(" ", 4)
+                    st, n = expect[name]
+                    if err != "0" or not (int(st1) in hostsim.RETRY or (int(st1) == st and (st != 0 or int(n1) == n))):
+                        bad.append((os.path.basename(cmd[0]), job, k0, ln, st))
+    return bad, len(streams)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--count", type=int, default=4000)
     ap.add_argument("--seed", type=int, default=1)
     ap.add_argument("--jobs", type=int, default=min(8, os.cpu_count() or 1))
     ap.add_argument("--fresh", type=int, default=24, help="fresh libbrotli streams (qualities 1-11, windows 10-22, heterogeneous payloads) added to the seeds")
+    ap.add_argument("--asan", action="store_true", help="run the streams through the address-sanitizer builds of the simulated kernels instead "
+                                                        "(memory safety; statuses and sizes against the oracle)")
     args = ap.parse_args()
+    if args.asan:
+        per = (args.count + args.jobs - 1) // args.jobs
+        with multiprocessing.Pool(args.jobs) as pool:
+            results = pool.map(asan_worker, [(j, per, args.seed, args.fresh) for j in range(args.jobs)])
+        bad = [b for r in results for b in r[0]]
+        for b in bad[:20]:
+            print("PROBLEM", b)
+        print("fuzz_warpsim --asan: %d streams x (fused kernel as a batch and stream by stream, parse kernel, copy kernel) under -fsanitize=address,undefined, %d problems"
+              % (sum(r[1] for r in results), len(bad)))
+        return 1 if bad else 0
     import warpsim
     warpsim.lib(); warpsim.two_phase([], []); warpsim._lib_parse()       # build once, before the workers start
     per = (args.count + args.jobs - 1) // args.jobs
