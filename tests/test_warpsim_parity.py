@@ -209,13 +209,14 @@ def _tsan_binary():
     return exe
 
 
-def _tsan_run(exe, files, latency=0, order=0, quirks=0, align=(0, 0), drop=None, batch_threads=None):
+def _tsan_run(exe, files, latency=0, order=0, quirks=0, align=(0, 0), drop=None, batch_threads=None, halt=True):
     """-> (ThreadSanitizer reports, {file: (status, out_len, fnv1a64 hex)}, stderr).  batch_threads: the files as one batch through
     bro_decode_warp_kernel itself with a CTA of that many threads"""
     env = dict(os.environ, BRO_WS_ALIGN="%d,%d" % align, TSAN_OPTIONS="exitcode=66 history_size=4")
     if drop is not None:
         env["BRO_WS_DROP_SYNC"] = str(drop)
-        env["TSAN_OPTIONS"] += " halt_on_error=1"         # (a mutation run only has to produce its first report)
+        if halt:
+            env["TSAN_OPTIONS"] += " halt_on_error=1"     # (a mutation run only has to produce its first report)
     if batch_threads:
         env["BRO_WS_BATCH"] = str(batch_threads)
     r = subprocess.run([exe, str(latency), str(order), "1", str(quirks), "0"] + ["%s:%d" % f for f in files], env=env, capture_output=True,

@@ -83,7 +83,7 @@ def main(build_only=False):
         total = 0
         for latency in (0, 1):
             try:
-                races, _, _ = T._tsan_run(exe, files, latency=latency, order=0, align=(3, 1), drop=line)
+                races, _, _ = T._tsan_run(exe, files, latency=latency, order=0, align=(3, 1), drop=line, halt=False)
             except AssertionError:
                 return "the warp diverged"
             total += races
