@@ -107,7 +107,7 @@ def worker(args):
 def asan_worker(args):
     """one chunk of mutated streams through the address-sanitizer builds of the three simulated kernels (tests/_build/warpsim_*_asan,
     built by tests/test_warpsim_parity.py::test_kernels_under_address_sanitizer) -> (problems, streams)"""
-    job, count, seed, fresh = args
+    job, count, seed, fresh, kind = args
     import subprocess
     import tempfile
     import fuzzgen
@@ -128,18 +128,20 @@ def asan_worker(args):
                 open(p, "wb").write(s)
                 files.append("%s:%d" % (p, cap))
                 expect[p] = (int(sts[0]), int(ol[0]))
-            env = dict(os.environ, ASAN_OPTIONS="detect_leaks=0:exitcode=55")
-            runs = (([os.path.join(build, "warpsim_asan"), str(int(rng.integers(2))), str(int(rng.integers(3))), str(k0 + 1), "0", "0"],
+            env = dict(os.environ, ASAN_OPTIONS="detect_leaks=0:exitcode=55",
+                       TSAN_OPTIONS="exitcode=66 suppressions=" + os.path.join(ROOT, "tests", "warpsim_tsan.supp"))
+            sfx = "_" + kind
+            runs = (([os.path.join(build, "warpsim" + sfx), str(int(rng.integers(2))), str(int(rng.integers(3))), str(k0 + 1), "0", "0"],
                      dict(env, BRO_WS_BATCH=str(int(rng.choice([32, 64, 256]))))),
-                    ([os.path.join(build, "warpsim_asan"), str(int(rng.integers(2))), str(int(rng.integers(3))), str(k0 + 1), "0", "0"],
+                    ([os.path.join(build, "warpsim" + sfx), str(int(rng.integers(2))), str(int(rng.integers(3))), str(k0 + 1), "0", "0"],
                      dict(env, BRO_WS_ALIGN="%d,%d" % (int(rng.integers(128)), int(rng.integers(16))))),
-                    ([os.path.join(build, "warpsim_parse_asan"), str(int(rng.choice([32, 32, 9, 1]))), str(int(rng.integers(3))), str(k0 + 1)],
+                    ([os.path.join(build, "warpsim_parse" + sfx), str(int(rng.choice([32, 32, 9, 1]))), str(int(rng.integers(3))), str(k0 + 1)],
                      dict(env, BRO_WS_THREADS=str(int(rng.choice([32, 64]))))),
-                    ([os.path.join(build, "warpsim_copy_asan"), str(int(rng.integers(2))), str(int(rng.integers(3))), str(k0 + 1), str(k0 + 5)],
+                    ([os.path.join(build, "warpsim_copy" + sfx), str(int(rng.integers(2))), str(int(rng.integers(3))), str(k0 + 1), str(k0 + 5)],
                      dict(env, BRO_WS_ALIGN="%d,%d" % (int(rng.integers(16)), int(rng.integers(16))))))
             for cmd, e in runs:
                 r = subprocess.run(cmd + files, env=e, capture_output=True, text=True)
-                if r.returncode != 0 or "ERROR: AddressSanitizer" in r.stderr or "runtime error" in r.stderr:
+                if r.returncode != 0 or "ERROR: AddressSanitizer" in r.stderr or "runtime error" in r.stderr or "WARNING: ThreadSanitizer" in r.stderr:
                     bad.append((os.path.basename(cmd[0]), job, k0, r.returncode, r.stderr[:1500]))
                     continue
                 for ln in r.stdout.splitlines():
@@ -156,18 +158,20 @@ def main():
     ap.add_argument("--seed", type=int, default=1)
     ap.add_argument("--jobs", type=int, default=min(8, os.cpu_count() or 1))
     ap.add_argument("--fresh", type=int, default=24, help="fresh libbrotli streams (qualities 1-11, windows 10-22, heterogeneous payloads) added to the seeds")
+    ap.add_argument("--tsan", action="store_true", help="... through the race-detector builds (ThreadSanitizer over the lanes, only __syncwarp / "
+                                                        "__syncthreads order memory) instead")
     ap.add_argument("--asan", action="store_true", help="run the streams through the address-sanitizer builds of the simulated kernels instead "
                                                         "(memory safety; statuses and sizes against the oracle)")
     args = ap.parse_args()
-    if args.asan:
+    if args.asan or args.tsan:
         per = (args.count + args.jobs - 1) // args.jobs
         with multiprocessing.Pool(args.jobs) as pool:
-            results = pool.map(asan_worker, [(j, per, args.seed, args.fresh) for j in range(args.jobs)])
+            results = pool.map(asan_worker, [(j, per, args.seed, args.fresh, "tsan" if args.tsan else "asan") for j in range(args.jobs)])
         bad = [b for r in results for b in r[0]]
         for b in bad[:20]:
             print("PROBLEM", b)
-        print("fuzz_warpsim --asan: %d streams x (fused kernel as a batch and stream by stream, parse kernel, copy kernel) under -fsanitize=address,undefined, %d problems"
-              % (sum(r[1] for r in results), len(bad)))
+        print("fuzz_warpsim --%s: %d streams x (fused kernel as a batch and stream by stream, parse kernel, copy kernel) under -fsanitize=%s,undefined, %d problems"
+              % ("tsan" if args.tsan else "asan", sum(r[1] for r in results), "thread" if args.tsan else "address", len(bad)))
         return 1 if bad else 0
     import warpsim
     warpsim.lib(); warpsim.two_phase([], []); warpsim._lib_parse()       # build once, before the workers start
